@@ -1,0 +1,114 @@
+/* rrtmgp_b200_ext.h - extension entry points beside the reference's extern-mode kernel ABI.
+ *
+ * The reference keeps several O(ncol*nlay*ngpt) loops of the hot path in its Fortran FRONTEND,
+ * not behind the bind(C) kernel boundary (SURVEY.md section 8a').  A device-resident path needs
+ * them as kernels too.  They are declared here, each citing the frontend lines it replaces.
+ * Unlike the Fortran-facing symbols in rte_kernels.h / rrtmgp_kernels.h (all arguments by
+ * reference), these are plain C calls: sizes and scalars BY VALUE, arrays as pointers
+ * (host or device, same classification rules), Fortran array order, 1-based index VALUES.
+ *
+ * Also here: the memory/stream plumbing the C++ frontend (rrtmgp_b200_frontend.h) is written
+ * against.  The frontend never dereferences array data itself, so the same frontend source links
+ * against this CUDA library (device memory) or against the CPU oracle (host memory) - the
+ * analogue of the reference's RTE_KERNEL_MODE switch.
+ */
+#ifndef RRTMGP_B200_EXT_H
+#define RRTMGP_B200_EXT_H
+
+#include <stddef.h>
+#include "rte_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------- backend plumbing ---------------- */
+/* "cuda-sm_100a" for the product library, "cpu-oracle" for the oracle. */
+const char* rrtmgpb_backend_name(void);
+/* Working-memory allocation in the backend's memory space (stream-ordered pool on CUDA). */
+void* rrtmgpb_mem_alloc(size_t bytes);
+void rrtmgpb_mem_free(void* p);
+/* Copies between HOST memory and backend memory (plain memcpy on the oracle). */
+void rrtmgpb_mem_to_backend(void* dst_backend, const void* src_host, size_t bytes);
+void rrtmgpb_mem_to_host(void* dst_host, const void* src_backend, size_t bytes);
+void rrtmgpb_mem_copy(void* dst_backend, const void* src_backend, size_t bytes);
+/* CUDA: all kernels are launched on this stream (default: the legacy default stream). */
+void rrtmgpb_set_stream(void* cuda_stream);
+void* rrtmgpb_get_stream(void);
+void rrtmgpb_set_device(int device);
+/* Blocks until all work queued by this library has finished (no-op on the oracle). */
+void rrtmgpb_sync(void);
+/* Number of kernel launches issued by this library since the last reset (bench.py gpu_launches). */
+long long rrtmgpb_launch_count(int reset);
+
+/* ---------------- physical constants ---------------- */
+/* replaces mo_gas_optics_constants.F90:42-51 init_constants(); NULL keeps the current value */
+void rrtmgpb_init_constants(const Float* gravity, const Float* mol_weight_dry_air,
+                            const Float* heat_capacity_dry_air);
+
+/* ---------------- solver options ---------------- */
+/* lw_solver_2stream level-source selection.  0 (default): reference DEFAULT-kernel behaviour,
+ * every g-point uses g-point 1's level source (mo_rte_solver_kernels.F90:422 passes the rank-3
+ * array to a rank-2 dummy); 1: per-g-point level source as in the reference's accel kernels
+ * (accel/mo_rte_solver_kernels.F90:958-962). */
+void rrtmgpb_set_lw_2stream_lev_source_per_gpt(int on);
+
+/* ---------------- frontend-resident loops as kernels (SURVEY 8a') ---------------- */
+/* replaces the Fortran function get_layer_number / get_col_dry, rte/kernels/mo_gas_optics_utils.F90:127-152
+ * (not bind(C) in the reference: api/mo_gas_optics_utils.F90:53-66).  vmr_h2o(ncol,nlay),
+ * plev(ncol,nlay+1) -> col_dry(ncol,nlay) */
+void rrtmgpb_get_col_dry(int ncol, int nlay, const Float* vmr_h2o, const Float* plev, Float* col_dry);
+/* replaces get_layer_mass, rte/kernels/mo_gas_optics_utils.F90:97-125 */
+void rrtmgpb_get_layer_mass(int ncol, int nlay, int ngas, const Float* vmr, const Float* plev,
+                            const Float* mol_weights, Float m_dry, Float* layer_mass);
+/* replaces mo_gas_optics_rrtmgp.F90:594-609: col_gas(:,:,0) = col_dry; col_gas(:,:,i) = vmr(:,:,i)*col_dry.
+ * vmr(ncol,nlay,ngas) -> col_gas(ncol,nlay,0:ngas) */
+void rrtmgpb_col_gas_from_vmr(int ncol, int nlay, int ngas, const Float* vmr, const Float* col_dry,
+                              Float* col_gas);
+/* replaces combine_abs_and_rayleigh, mo_gas_optics_rrtmgp.F90:1954-2002.  kind: 1 = 1scl (tau only;
+ * ssa, g ignored), 2 = 2str (tau, ssa, g = 0).  Output arrays may alias tau_abs (in-place is safe). */
+void rrtmgpb_combine_abs_and_rayleigh(int ncol, int nlay, int ngpt, int kind, const Float* tau_abs,
+                                      const Float* tau_rayleigh, Float* tau, Float* ssa, Float* g);
+/* replaces the tlev interpolation in source(), mo_gas_optics_rrtmgp.F90:893-911 */
+void rrtmgpb_interpolate_tlev(int ncol, int nlay, const Float* play, const Float* plev, const Float* tlay,
+                              Float* tlev);
+/* replaces mo_gas_optics_rrtmgp.F90:405-411: toa_src(icol,igpt) = solar_source(igpt) */
+void rrtmgpb_broadcast_by_gpt(int ncol, int ngpt, const Float* per_gpt, Float* out);
+/* replaces expand_and_transpose, rte/frontend/mo_rte_lw.F90:478-501 and mo_rte_sw.F90:399-422:
+ * arr_in(nband,ncol) -> arr_out(ncol,ngpt) */
+void rrtmgpb_expand_and_transpose(int ncol, int nband, int ngpt, const int* band_lims_gpt,
+                                  const Float* arr_in, Float* arr_out);
+/* replaces mo_rte_sw.F90:87-93: mu0_bylay(icol,ilay) = mu0(icol) */
+void rrtmgpb_broadcast_by_lay(int ncol, int nlay, const Float* per_col, Float* out);
+/* replaces the cloud masks mo_cloud_optics_rrtmgp.F90:334-341 */
+void rrtmgpb_cloud_masks(int ncol, int nlay, const Float* clwp, const Float* ciwp, Bool* liqmsk,
+                         Bool* icemsk);
+/* replaces the liquid+ice combination mo_cloud_optics_rrtmgp.F90:399-424.  kind 1: tau = (ltau-ltaussa)
+ * + (itau-itaussa); kind 2: tau, ssa, g with epsilon() guards. */
+void rrtmgpb_cloud_combine(int ncol, int nlay, int ngpt, int kind, const Float* ltau, const Float* ltaussa,
+                           const Float* ltaussag, const Float* itau, const Float* itaussa,
+                           const Float* itaussag, Float* tau, Float* ssa, Float* g);
+/* value checks, rte/frontend/mo_rte_util_array_validation.F90:52-...: return 1 if any element violates.
+ * mask may be NULL (no mask). */
+int rrtmgpb_any_vals_less_than(size_t n, const Float* array, const Bool* mask, Float check_value);
+int rrtmgpb_any_vals_outside(size_t n, const Float* array, const Bool* mask, Float checkMin, Float checkMax);
+
+/* ---------------- fused variants used by the device-resident frontend ---------------- */
+/* As rrtmgp_compute_tau_absorption but ASSIGNS tau instead of accumulating into a pre-zeroed array:
+ * saves the zero_array_3D plane write and the plane read (mo_gas_optics_rrtmgp.F90:637-665,679-706). */
+void rrtmgpb_compute_tau_absorption_assign(
+    int ncol, int nlay, int nbnd, int ngpt, int ngas, int nflav, int neta, int npres, int ntemp,
+    int nminorlower, int nminorklower, int nminorupper, int nminorkupper, int idx_h2o,
+    const int* gpoint_flavor, const int* band_lims_gpt, const Float* kmajor, const Float* kminor_lower,
+    const Float* kminor_upper, const int* minor_limits_gpt_lower, const int* minor_limits_gpt_upper,
+    const Bool* minor_scales_with_density_lower, const Bool* minor_scales_with_density_upper,
+    const Bool* scale_by_complement_lower, const Bool* scale_by_complement_upper,
+    const int* idx_minor_lower, const int* idx_minor_upper, const int* idx_minor_scaling_lower,
+    const int* idx_minor_scaling_upper, const int* kminor_start_lower, const int* kminor_start_upper,
+    const Bool* tropo, const Float* col_mix, const Float* fmajor, const Float* fminor, const Float* play,
+    const Float* tlay, const Float* col_gas, const int* jeta, const int* jtemp, const int* jpress, Float* tau);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRTMGP_B200_EXT_H */

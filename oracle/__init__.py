@@ -1,0 +1,35 @@
+"""ORACLE - TEST INFRASTRUCTURE ONLY.
+
+Python loader for the CPU restatement of the reference kernels (oracle/*.c).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+Nothing under rte_rrtmgp_b200/ imports it.
+"""
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+
+def build(fast=False):
+    target = "fast" if fast else "all"
+    subprocess.run(["make", "-s", "-C", _HERE, target], check=True)
+    return os.path.join(_HERE, "_build", "liboracle_fast.so" if fast else "liboracle.so")
+
+
+def lib(fast=False):
+    """KernelLib over the oracle (parity build by default; `fast` = -O3 -march=native build)."""
+    key = bool(fast)
+    if key not in _LIBS:
+        from rte_rrtmgp_b200.abi import KernelLib
+
+        path = os.path.join(_HERE, "_build", "liboracle_fast.so" if fast else "liboracle.so")
+        srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+        front = os.path.join(_HERE, "..", "rte_rrtmgp_b200", "csrc", "frontend")
+        if os.path.isdir(front):
+            srcs += [os.path.join(front, f) for f in os.listdir(front)]
+        stale = (not os.path.exists(path)) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs)
+        if stale:
+            build(fast)
+        _LIBS[key] = KernelLib(path)
+    return _LIBS[key]

@@ -1,0 +1,158 @@
+/* ORACLE - TEST INFRASTRUCTURE ONLY (see rte_solver_ref.c header for the rules).
+ *
+ * CPU restatement in plain C of the O(ncol*nlay*ngpt) loops that the reference keeps in its
+ * Fortran FRONTEND (SURVEY.md section 8a'), under the extension names of
+ * include/rrtmgp_b200_ext.h, plus the host-memory version of the backend plumbing.
+ * Each function cites the frontend lines it follows.  PARITY UNPINNED by reference golden data
+ * (the frontend loops are only exercised by the reference's data-dependent regression tests).
+ */
+#include <float.h>
+#include <stdlib.h>
+#include <string.h>
+#include "oracle_ext.h"
+
+#define MAXF(a, b) (((a) > (b)) ? (a) : (b))
+
+const char* rrtmgpb_backend_name(void) { return "cpu-oracle"; }
+void* rrtmgpb_mem_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void rrtmgpb_mem_free(void* p) { free(p); }
+void rrtmgpb_mem_to_backend(void* d, const void* s, size_t n) { memcpy(d, s, n); }
+void rrtmgpb_mem_to_host(void* d, const void* s, size_t n) { memcpy(d, s, n); }
+void rrtmgpb_mem_copy(void* d, const void* s, size_t n) { memmove(d, s, n); }
+void rrtmgpb_set_stream(void* s) { (void)s; }
+void* rrtmgpb_get_stream(void) { return NULL; }
+void rrtmgpb_set_device(int d) { (void)d; }
+void rrtmgpb_sync(void) {}
+long long rrtmgpb_launch_count(int reset) { (void)reset; return 0; }
+void rrtmgpb_set_lw_2stream_lev_source_per_gpt(int on) { oracle_set_lw_2stream_lev_source_per_gpt(on); }
+
+/* mo_gas_optics_rrtmgp.F90:594-609 */
+void rrtmgpb_col_gas_from_vmr(int ncol, int nlay, int ngas, const Float* vmr, const Float* col_dry,
+                              Float* col_gas) {
+  const size_t ncl = (size_t)ncol * nlay;
+  for (size_t c = 0; c < ncl; ++c) col_gas[c] = col_dry[c];
+  for (int igas = 1; igas <= ngas; ++igas)
+    for (size_t c = 0; c < ncl; ++c) col_gas[c + ncl * igas] = vmr[c + ncl * (igas - 1)] * col_dry[c];
+}
+
+/* combine_abs_and_rayleigh, mo_gas_optics_rrtmgp.F90:1954-2002 */
+void rrtmgpb_combine_abs_and_rayleigh(int ncol, int nlay, int ngpt, int kind, const Float* tau_abs,
+                                      const Float* tau_rayleigh, Float* tau, Float* ssa, Float* g) {
+  const size_t n = (size_t)ncol * nlay * ngpt;
+  const Float tiny = (sizeof(Float) == 8) ? (Float)DBL_MIN : (Float)FLT_MIN;
+  if (kind == 1) {
+    for (size_t i = 0; i < n; ++i) tau[i] = tau_abs[i] + tau_rayleigh[i];
+    return;
+  }
+  for (size_t i = 0; i < n; ++i) {
+    const Float t = tau_abs[i] + tau_rayleigh[i];
+    if (t > (Float)2 * tiny) ssa[i] = tau_rayleigh[i] / t; else ssa[i] = 0;
+    tau[i] = t;
+  }
+  for (size_t i = 0; i < n; ++i) g[i] = 0; /* :2002 zero_array(g) */
+}
+
+/* source(): tlev interpolation, mo_gas_optics_rrtmgp.F90:893-911 */
+void rrtmgpb_interpolate_tlev(int ncol, int nlay, const Float* play, const Float* plev, const Float* tlay,
+                              Float* tlev) {
+#define A2(a, i, l) a[(size_t)(i) + (size_t)ncol * (size_t)(l)]
+  for (int i = 0; i < ncol; ++i) {
+    A2(tlev, i, 0) = A2(tlay, i, 0) + (A2(plev, i, 0) - A2(play, i, 0)) * (A2(tlay, i, 1) - A2(tlay, i, 0)) /
+                                          (A2(play, i, 1) - A2(play, i, 0));
+    A2(tlev, i, nlay) = A2(tlay, i, nlay - 1) + (A2(plev, i, nlay) - A2(play, i, nlay - 1)) *
+                                                    (A2(tlay, i, nlay - 1) - A2(tlay, i, nlay - 2)) /
+                                                    (A2(play, i, nlay - 1) - A2(play, i, nlay - 2));
+  }
+  for (int l = 1; l < nlay; ++l)
+    for (int i = 0; i < ncol; ++i)
+      A2(tlev, i, l) = (A2(play, i, l - 1) * A2(tlay, i, l - 1) * (A2(plev, i, l) - A2(play, i, l)) +
+                        A2(play, i, l) * A2(tlay, i, l) * (A2(play, i, l - 1) - A2(plev, i, l))) /
+                       (A2(plev, i, l) * (A2(play, i, l - 1) - A2(play, i, l)));
+#undef A2
+}
+
+/* mo_gas_optics_rrtmgp.F90:405-411 */
+void rrtmgpb_broadcast_by_gpt(int ncol, int ngpt, const Float* per_gpt, Float* out) {
+  for (int g = 0; g < ngpt; ++g)
+    for (int i = 0; i < ncol; ++i) out[(size_t)i + (size_t)ncol * g] = per_gpt[g];
+}
+
+/* expand_and_transpose, mo_rte_lw.F90:478-501 */
+void rrtmgpb_expand_and_transpose(int ncol, int nband, int ngpt, const int* band_lims_gpt,
+                                  const Float* arr_in, Float* arr_out) {
+  (void)ngpt;
+  for (int b = 0; b < nband; ++b)
+    for (int i = 0; i < ncol; ++i)
+      for (int g = band_lims_gpt[2 * b] - 1; g < band_lims_gpt[2 * b + 1]; ++g)
+        arr_out[(size_t)i + (size_t)ncol * g] = arr_in[(size_t)b + (size_t)nband * i];
+}
+
+/* mo_rte_sw.F90:87-93 */
+void rrtmgpb_broadcast_by_lay(int ncol, int nlay, const Float* per_col, Float* out) {
+  for (int l = 0; l < nlay; ++l)
+    for (int i = 0; i < ncol; ++i) out[(size_t)i + (size_t)ncol * l] = per_col[i];
+}
+
+/* mo_cloud_optics_rrtmgp.F90:334-341 */
+void rrtmgpb_cloud_masks(int ncol, int nlay, const Float* clwp, const Float* ciwp, Bool* liqmsk, Bool* icemsk) {
+  const size_t ncl = (size_t)ncol * nlay;
+  for (size_t c = 0; c < ncl; ++c) { liqmsk[c] = clwp[c] > 0; icemsk[c] = ciwp[c] > 0; }
+}
+
+/* mo_cloud_optics_rrtmgp.F90:399-424 */
+void rrtmgpb_cloud_combine(int ncol, int nlay, int ngpt, int kind, const Float* ltau, const Float* ltaussa,
+                           const Float* ltaussag, const Float* itau, const Float* itaussa,
+                           const Float* itaussag, Float* tau, Float* ssa, Float* g) {
+  const size_t n = (size_t)ncol * nlay * ngpt;
+  const Float eps = (sizeof(Float) == 8) ? (Float)DBL_EPSILON : (Float)FLT_EPSILON;
+  if (kind == 1) {
+    for (size_t i = 0; i < n; ++i) tau[i] = (ltau[i] - ltaussa[i]) + (itau[i] - itaussa[i]);
+    return;
+  }
+  for (size_t i = 0; i < n; ++i) {
+    const Float t = ltau[i] + itau[i];
+    const Float ts = ltaussa[i] + itaussa[i];
+    g[i] = (ltaussag[i] + itaussag[i]) / MAXF(eps, ts);
+    ssa[i] = ts / MAXF(eps, t);
+    tau[i] = t;
+  }
+}
+
+/* mo_rte_util_array_validation.F90 any_vals_less_than / any_vals_outside (masked and unmasked) */
+int rrtmgpb_any_vals_less_than(size_t n, const Float* a, const Bool* mask, Float v) {
+  for (size_t i = 0; i < n; ++i)
+    if ((!mask || mask[i]) && a[i] < v) return 1;
+  return 0;
+}
+int rrtmgpb_any_vals_outside(size_t n, const Float* a, const Bool* mask, Float lo, Float hi) {
+  for (size_t i = 0; i < n; ++i)
+    if ((!mask || mask[i]) && (a[i] < lo || a[i] > hi)) return 1;
+  return 0;
+}
+
+/* extern void rrtmgp_compute_tau_absorption(...) is in rrtmgp_gas_optics_ref.c */
+#include "rrtmgp_kernels.h"
+#include "rte_kernels.h"
+void rrtmgpb_compute_tau_absorption_assign(
+    int ncol, int nlay, int nbnd, int ngpt, int ngas, int nflav, int neta, int npres, int ntemp,
+    int nminorlower, int nminorklower, int nminorupper, int nminorkupper, int idx_h2o,
+    const int* gpoint_flavor, const int* band_lims_gpt, const Float* kmajor, const Float* kminor_lower,
+    const Float* kminor_upper, const int* minor_limits_gpt_lower, const int* minor_limits_gpt_upper,
+    const Bool* minor_scales_with_density_lower, const Bool* minor_scales_with_density_upper,
+    const Bool* scale_by_complement_lower, const Bool* scale_by_complement_upper,
+    const int* idx_minor_lower, const int* idx_minor_upper, const int* idx_minor_scaling_lower,
+    const int* idx_minor_scaling_upper, const int* kminor_start_lower, const int* kminor_start_upper,
+    const Bool* tropo, const Float* col_mix, const Float* fmajor, const Float* fminor, const Float* play,
+    const Float* tlay, const Float* col_gas, const int* jeta, const int* jtemp, const int* jpress, Float* tau) {
+  /* the reference sequence: zero_array then accumulate (mo_gas_optics_rrtmgp.F90:679-706) */
+  zero_array_3D(&ncol, &nlay, &ngpt, tau);
+  rrtmgp_compute_tau_absorption(&ncol, &nlay, &nbnd, &ngpt, &ngas, &nflav, &neta, &npres, &ntemp,
+                                &nminorlower, &nminorklower, &nminorupper, &nminorkupper, &idx_h2o,
+                                gpoint_flavor, band_lims_gpt, kmajor, kminor_lower, kminor_upper,
+                                minor_limits_gpt_lower, minor_limits_gpt_upper,
+                                minor_scales_with_density_lower, minor_scales_with_density_upper,
+                                scale_by_complement_lower, scale_by_complement_upper, idx_minor_lower,
+                                idx_minor_upper, idx_minor_scaling_lower, idx_minor_scaling_upper,
+                                kminor_start_lower, kminor_start_upper, tropo, col_mix, fmajor, fminor, play,
+                                tlay, col_gas, jeta, jtemp, jpress, tau);
+}

@@ -1,0 +1,91 @@
+"""Restatement of the reference's tests/rte_lw_solver_unit_tests.F90 at kernel level.
+
+Oracle leg (CPU): pins oracle/rte_solver_ref.c against the analytic gray-radiative-equilibrium
+solution with the reference's own spacing()-based tolerances (:316-331, mo_comparisons.F90:43-55).
+GPU leg (-m gpu): the CUDA kernels, called through the C-ABI, against the same analytic answers
+and against the oracle.  libdevice exp() and FMA contraction differ from glibc/no-FMA by a few ulp,
+so the GPU-vs-analytic tolerances are stated explicitly where they are wider than the reference's.
+"""
+import numpy as np
+import pytest
+
+import refcases as rc
+
+NCOL, NLAY = 8, 16
+SFC_T = np.array([285.0] * (NCOL // 2) + [310.0] * (NCOL // 2))
+TOTAL_TAU = np.array([0.1, 1.0, 10.0, 50.0, 0.1, 1.0, 10.0, 50.0])
+SFC_EMIS_GPT = np.ones((NCOL, 1), order="F")
+
+
+def _tols(device):
+    # (OLR, net-constancy, default) in units of spacing(); reference uses 8 / 100 / 2 (3 for vr).
+    return (8.0, 100.0, 3.0) if device is None else (16.0, 200.0, 8.0)
+
+
+@pytest.mark.parametrize("top_at_1", [True, False])
+def test_gray_radiative_equilibrium(backend, top_at_1):
+    lib, device = backend
+    olr_tol, net_tol, _ = _tols(device)
+    prob = rc.gray_rad_equil(SFC_T, TOTAL_TAU, NLAY, top_at_1)
+    up, dn = rc.lw_noscat_broadband(lib, device, prob, SFC_EMIS_GPT)
+    toa = 0 if top_at_1 else NLAY
+    # :316-321  OLR = 2 sigma T^4 / (2 + D tau)
+    assert rc.allclose(up[:, toa], rc.gray_rad_equil_olr(SFC_T, TOTAL_TAU), tol=olr_tol), rc.max_spacings(
+        up[:, toa], rc.gray_rad_equil_olr(SFC_T, TOTAL_TAU))
+    # :327-331  net flux constant with height
+    net = dn - up
+    assert rc.allclose(net, np.repeat(net[:, :1], NLAY + 1, axis=1), tol=net_tol)
+
+
+def test_vertical_orientation_invariance(backend):
+    lib, device = backend
+    tol = _tols(device)[2]
+    prob = rc.gray_rad_equil(SFC_T, TOTAL_TAU, NLAY, True)
+    ref_up, ref_dn = rc.lw_noscat_broadband(lib, device, prob, SFC_EMIS_GPT)
+    up, dn = rc.lw_noscat_broadband(lib, device, rc.vr(prob), SFC_EMIS_GPT)
+    assert rc.allclose(up[:, ::-1], ref_up, tol=tol)  # :153-158 (tol 3 there)
+    assert rc.allclose(dn[:, ::-1], ref_dn, tol=tol)
+
+
+def test_subsetting_invariance(backend):
+    """:139-144 clear_sky_subset: doing the problem in column subsets gives the same fluxes."""
+    lib, device = backend
+    prob = rc.gray_rad_equil(SFC_T, TOTAL_TAU, NLAY, True)
+    ref_up, ref_dn = rc.lw_noscat_broadband(lib, device, prob, SFC_EMIS_GPT)
+    for s, e in ((0, 3), (3, 8)):
+        sub = {k: (np.asfortranarray(v[s:e]) if isinstance(v, np.ndarray) else v) for k, v in prob.items()}
+        up, dn = rc.lw_noscat_broadband(lib, device, sub, np.asfortranarray(SFC_EMIS_GPT[s:e]))
+        assert rc.allclose(up, ref_up[s:e]) and rc.allclose(dn, ref_dn[s:e])
+
+
+def test_jacobian_does_not_change_fluxes_and_predicts_perturbation(backend):
+    lib, device = backend
+    prob = rc.gray_rad_equil(SFC_T, TOTAL_TAU, NLAY, True)
+    ref_up, ref_dn = rc.lw_noscat_broadband(lib, device, prob, SFC_EMIS_GPT)
+    up, dn, jac = rc.lw_noscat_broadband(lib, device, prob, SFC_EMIS_GPT, do_jacobians=True)
+    assert rc.allclose(up, ref_up) and rc.allclose(dn, ref_dn)  # :171-172
+    # :176-189 surface warmed by 1 K: flux(T+1) ~ flux + Jacobian (reference only prints the error)
+    pert = dict(prob)
+    pert["sfc_source"] = np.asfortranarray((rc.SIGMA / rc.PI * (SFC_T + 1.0) ** 4)[:, None])
+    up1, _ = rc.lw_noscat_broadband(lib, device, pert, SFC_EMIS_GPT)
+    assert np.max(np.abs(up1 - (ref_up + jac)) / up1) < 0.01
+
+
+def test_rescaling_with_zero_ssa_matches_noscat(backend):
+    """:194-210 Tang rescaling with ssa = g = 0 must reproduce the no-scattering fluxes."""
+    lib, device = backend
+    prob = rc.gray_rad_equil(SFC_T, TOTAL_TAU, NLAY, True)
+    ref_up, ref_dn = rc.lw_noscat_broadband(lib, device, prob, SFC_EMIS_GPT)
+    zeros = np.zeros_like(prob["tau"])
+    up, dn, _ = rc.lw_noscat_broadband(lib, device, prob, SFC_EMIS_GPT, do_jacobians=True, rescale=(zeros, zeros))
+    assert rc.allclose(up, ref_up) and rc.allclose(dn, ref_dn)
+
+
+def test_specified_transport_angle(backend):
+    """:215-221 passing lw_Ds = D explicitly equals the default secant."""
+    lib, device = backend
+    prob = rc.gray_rad_equil(SFC_T, TOTAL_TAU, NLAY, True)
+    ref_up, ref_dn = rc.lw_noscat_broadband(lib, device, prob, SFC_EMIS_GPT)
+    Ds = np.full((NCOL, 1, 1), rc.D_DIFF, order="F")
+    up, dn = rc.lw_noscat_broadband(lib, device, prob, SFC_EMIS_GPT, Ds=Ds)
+    assert rc.allclose(up, ref_up) and rc.allclose(dn, ref_dn)
