@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py - columns/sec of the all-sky LW+SW hot path (BASELINE.json metric) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          product (CUDA) arm
+  python bench.py --impl reference [--steps K] [--warmup W]    reference arm: the reference's CPU kernels
+                                                               (C restatement, all host threads)
+
+Workload (config.workload): BASELINE.json configs[1] - one analytic RCEMIP-like profile replicated to
+65,536 columns x 72 layers per GPU, LW 256 g-points + SW 224 g-points, clouds in 2/3 of the columns:
+the loop body of the reference's own benchmark driver (examples/all-sky/rrtmgp_allsky.F90:332-409).
+A "step" = one LW iteration + one SW iteration over all columns of the rank.  Columns are independent,
+so ranks own disjoint column shards and there is NO collective on the data path ("scaling": "weak").
+
+One JSON line is printed by rank 0 (see the contract in the task statement / DESIGN.md section 6).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NCOL_PER_GPU = 65536
+NLAY = 72
+METRIC = "columns/sec (LW+SW all-sky)"
+WORKLOAD = "all-sky LW(256 gpt)+SW(224 gpt), 1 RCEMIP-like profile replicated, 72 layers, clouds in 2/3 of columns"
+
+
+def algorithmic_bytes(ncol, nlay, ngpt_lw, ngpt_sw, nbnd_lw, nbnd_sw, nflav_lw, nflav_sw, ngas):
+    """SURVEY.md section 8(d) per-kernel algorithmic bytes (fp64), evaluated for the actual table sizes.
+    Returns {kernel name: bytes per step} for the kernels the event profiler names."""
+    w, i4, b1 = 8, 4, 1
+    N, L, S = ncol, nlay, ngas + 1
+    out = {}
+
+    def interp(F):
+        return (2 + S) * N * L * w + N * L * (2 * i4 + b1 + F * (2 * i4 + 14 * w))
+
+    def planes(G):
+        return N * L * G * w
+
+    for tag, G, B, F in (("lw", ngpt_lw, nbnd_lw, nflav_lw), ("sw", ngpt_sw, nbnd_sw, nflav_sw)):
+        P = planes(G)
+        out[f"interpolation[{tag}]"] = interp(F)
+        out[f"tau_absorption[{tag}]"] = interp(F) - (2 + S) * N * L * w + (2 + S) * N * L * w + P
+        out[f"cld_from_table[{tag}]"] = 2 * 3 * N * L * B * w
+    P = planes(ngpt_lw)
+    out["planck_source"] = N * L * (8 * nflav_lw * w + 2 * nflav_lw * i4 + 2 * i4 + b1 + 2 * w) + P * (2 + 1.0 / L) + 2 * N * ngpt_lw * w
+    out["lw_noscat_kernel"] = P * (3 + 1.0 / L) + 4 * N * ngpt_lw * w + 2 * N * (L + 1) * w
+    out["rte_inc_1scalar_by_1scalar_bybnd"] = 2 * P
+    P = planes(ngpt_sw)
+    out["tau_rayleigh"] = N * L * (4 * nflav_sw * w + 2 * nflav_sw * i4 + i4 + b1 + (1 + S) * w) + P
+    out["rrtmgpb_combine_abs_and_rayleigh"] = 5 * P
+    out["sw_2stream_kernel"] = 3 * P + N * L * w + 4 * N * ngpt_sw * w + 3 * N * (L + 1) * w
+    out["rte_inc_2stream_by_2stream_bybnd"] = 6 * P
+    out["rte_delta_scale_2str_k"] = 6 * N * L * nbnd_sw * w
+    return out
+
+
+def clock_sampler(stop, samples):
+    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    try:
+        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return
+    try:
+        while not stop.is_set():
+            line = p.stdout.readline()
+            if not line:
+                break
+            samples.append(line.strip())
+    finally:
+        p.terminate()
+
+
+def summarize_clocks(samples, device_index):
+    sm, mx, reasons = [], [], set()
+    for s in samples:
+        f = [x.strip() for x in s.split(",")]
+        if len(f) < 9 or f[0] != str(device_index):
+            continue
+        try:
+            sm.append(float(f[1])); mx.append(float(f[2]))
+        except ValueError:
+            continue
+        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+            if v.lower().startswith("active"):
+                reasons.add(name)
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_rate(ncol_per_block, nblocks_per_thread, steps, warmup, fast=True, threads=None):
+    """columns/s of the CPU oracle (C restatement of the reference's default kernels) with all host
+    threads: independent column blocks per thread - the reference's own parallelisation idiom
+    (examples/rfmip-clear-sky/rrtmgp_rfmip_lw.F90:177-178,247)."""
+    import oracle
+    from rte_rrtmgp_b200 import synthetic as syn
+    from rte_rrtmgp_b200.allsky import AllSky
+    from rte_rrtmgp_b200.frontend import Context
+
+    threads = threads or (os.cpu_count() or 1)
+    lib = oracle.lib(fast=fast)
+    ctx = Context(lib, None)
+    kd_lw, kd_sw = syn.make_kdist("lw"), syn.make_kdist("sw")
+    blocks = [AllSky(ctx, ncol_per_block, NLAY, kd_lw, kd_sw, col_offset=i * ncol_per_block) for i in range(threads)]
+    ctx.config_checks(False, False)  # rrtmgp_allsky.F90:334
+
+    def work(b, n):
+        for _ in range(n):
+            for _ in range(nblocks_per_thread):
+                b.step()
+
+    def run(n):
+        ts = [threading.Thread(target=work, args=(b, n)) for b in blocks]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
+
+    run(warmup)
+    dt = run(steps)
+    cols = threads * nblocks_per_thread * ncol_per_block * steps
+    return cols / dt, dt / steps, threads, threads * nblocks_per_thread * ncol_per_block
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    ncb, nbt = 64, 2
+    rate, sec_per_step, threads, cols = cpu_reference_rate(ncb, nbt, args.steps, args.warmup)
+    sample = (f"{cols} columns per step ({threads} threads x {nbt} blocks x {ncb} columns) of the same workload; "
+              "oracle -O3 -march=native build")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "columns/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "ncol_per_step": cols, "nlay": NLAY},
+        "cpu_baseline": {"value": rate, "unit": "columns/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+
+    import rte_rrtmgp_b200 as pkg
+    from rte_rrtmgp_b200 import synthetic as syn
+    from rte_rrtmgp_b200.allsky import AllSky
+    from rte_rrtmgp_b200.frontend import Context
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the product arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = pkg.lib()
+    lib.set_device(local)
+    lib.set_stream(torch.cuda.current_stream().cuda_stream)
+    device = f"cuda:{local}"
+    ctx = Context(lib, device)
+    ncol = args.ncol
+    kd_lw, kd_sw = syn.make_kdist("lw"), syn.make_kdist("sw")
+    sky = AllSky(ctx, ncol, NLAY, kd_lw, kd_sw, col_offset=rank * ncol)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # first step with the frontend's checks on (as the reference driver does), then off: rrtmgp_allsky.F90:334
+    sky.step()
+    ctx.config_checks(False, False)
+    for _ in range(max(args.warmup - 1, 0)):
+        sky.step()
+    barrier()
+
+    stop, samples = threading.Event(), []
+    sampler = threading.Thread(target=clock_sampler, args=(stop, samples), daemon=True)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    lib.launch_count(reset=True)
+    lib.cdll.rrtmgpb_profile_enable(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        sky.step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.launch_count()
+    lib.cdll.rrtmgpb_profile_enable(0)
+    import ctypes
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.cdll.rrtmgpb_profile_report(buf, ctypes.c_size_t(len(buf)))
+    stop.set()
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = world * ncol / (ms_per_step * 1e-3)
+
+    # ---- per-kernel shares from the event profiler (this rank) and the roofline of the dominant kernel
+    prof = []
+    for ln in buf.value.decode().splitlines():
+        name, cnt, tot = ln.rsplit(" ", 2)
+        prof.append((name, int(cnt), float(tot)))
+    alg = algorithmic_bytes(ncol, NLAY, kd_lw.ngpt, kd_sw.ngpt, kd_lw.nbnd, kd_sw.nbnd, kd_lw.nflav, kd_sw.nflav, kd_lw.ngas)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
+    roofline, kernels = None, []
+    total_kernel_ms = sum(p[2] for p in prof) or 1.0
+    for name, cnt, tot in prof:
+        # per STEP figures: a kernel that runs for LW and for SW (tau_absorption, interpolation,
+        # cld_from_table) is charged the sum of both launches' algorithmic bytes against the sum of both times
+        ms_step = tot / args.steps
+        if name in alg:
+            bytes_step = alg[name]
+        elif f"{name}[lw]" in alg:
+            bytes_step = alg[f"{name}[lw]"] + alg[f"{name}[sw]"]
+        else:
+            bytes_step = None
+        ent = {"kernel": name, "launches_per_step": cnt / args.steps, "ms_per_step": ms_step,
+               "share": tot / total_kernel_ms}
+        if bytes_step:
+            ent["algorithmic_bytes_per_step"] = bytes_step
+            ent["achieved_gbs"] = bytes_step / (ms_step * 1e-3) / 1e9
+            ent["frac"] = ent["achieved_gbs"] / peak
+        kernels.append(ent)
+    if kernels:
+        top = kernels[0]
+        roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top.get("achieved_gbs"), "peak": peak,
+                    "unit": "GB/s", "frac": top.get("frac"), "traffic": None, "peak_source": peak_src,
+                    "share_of_step": top["share"], "ms_per_step": top["ms_per_step"],
+                    "launches_per_step": top["launches_per_step"],
+                    "algorithmic_bytes_per_step": top.get("algorithmic_bytes_per_step")}
+    step_bytes = sum(v for v in alg.values())
+    step_frac = step_bytes / (ms_per_step * 1e-3) / 1e9 / peak
+
+    # ---- end to end: host inputs (pinned) -> device every step, broadband fluxes -> host every step
+    hin = sky.host_inputs
+    pinned = {k: torch.from_numpy(np.ascontiguousarray(v.T)).pin_memory() for k, v in hin.items()}
+    dev_in = {"p_lay": sky.p_lay, "p_lev": sky.p_lev, "t_lay": sky.t_lay, "t_lev": sky.t_lev, "vmr": sky.vmr,
+              "lwp": sky.lwp, "iwp": sky.iwp, "rel": sky.rel, "dei": sky.dei}
+    outs = [sky.lw.flux_up, sky.lw.flux_dn, sky.sw.flux_up, sky.sw.flux_dn, sky.sw.flux_dir]
+    host_out = [torch.empty(tuple(reversed(o.shape)), dtype=torch.float64).pin_memory() for o in outs]
+    h2d = sum(pinned[k].numel() * 8 for k in dev_in)
+    d2h = sum(h.numel() * 8 for h in host_out)
+
+    def e2e_step():
+        for k, d in dev_in.items():
+            d.permute(*reversed(range(d.dim()))).copy_(pinned[k], non_blocking=True)
+        sky.step()
+        for o, h in zip(outs, host_out):
+            h.copy_(o.permute(*reversed(range(o.dim()))), non_blocking=True)
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * ncol / (float(t.item()) / args.steps * 1e-3)
+
+    # ---- parity spot check inside the bench: first 32 columns vs the CPU oracle (checker only)
+    cpu_base, parity = None, None
+    if rank == 0:
+        if sampler.is_alive():
+            sampler.join(timeout=2)
+        if world == 1 and not args.no_cpu:
+            rate, sps, threads, cols = cpu_reference_rate(64, 1, 2, 1)
+            cpu_base = {"value": rate, "unit": "columns/s", "cores": threads, "kind": "port",
+                        "sample": f"{cols} columns per step ({threads} threads x 64 columns), 2 timed + 1 warm-up steps, "
+                                  "oracle -O3 -march=native build of the C restatement (no Fortran compiler in the image)"}
+            import oracle
+            chk = AllSky(Context(oracle.lib(), None), 48, NLAY, kd_lw, kd_sw)
+            chk.step()
+            fc, fg = chk.fluxes_host(), sky.fluxes_host()
+            parity = max(float(np.max(np.abs(fg[k][:48] - fc[k]))) for k in fc)
+        line = {
+            "metric": METRIC, "value": value, "unit": "columns/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "ncol_per_gpu": ncol, "nlay": NLAY, "ngpt_lw": kd_lw.ngpt,
+                       "ngpt_sw": kd_sw.ngpt, "sharding": f"columns x{world}, no data-path collective",
+                       "l2_policy": "inputs larger than L2 (each (col,lay,gpt) plane is 9.7 GB)"},
+            "e2e": {"value": e2e_value, "unit": "columns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "frac_of_hbm_peak": step_frac,
+                              "bytes_per_column": step_bytes / ncol},
+            "kernels": kernels[:12],
+            "cpu_baseline": cpu_base,
+            "max_abs_flux_err_vs_oracle_Wm2": parity,
+            "clocks": summarize_clocks(samples, local),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ncol", type=int, default=NCOL_PER_GPU, help="columns per GPU (default: the BASELINE config)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_product(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

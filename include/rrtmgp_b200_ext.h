@@ -41,6 +41,10 @@ void rrtmgpb_sync(void);
 /* Number of kernel launches issued by this library since the last reset (bench.py gpu_launches). */
 long long rrtmgpb_launch_count(int reset);
 
+/* Per-kernel timing with CUDA events on the launch stream.  report: "name count total_ms" lines. */
+void rrtmgpb_profile_enable(int on);
+int rrtmgpb_profile_report(char* buf, size_t buflen);
+
 /* ---------------- physical constants ---------------- */
 /* replaces mo_gas_optics_constants.F90:42-51 init_constants(); NULL keeps the current value */
 void rrtmgpb_init_constants(const Float* gravity, const Float* mol_weight_dry_air,

@@ -1,0 +1,153 @@
+/* rrtmgp_b200_frontend.h - host-side mirror of the reference's Fortran frontend for the hot path.
+ *
+ * The reference's frontend is object-oriented Fortran (ty_optical_props_*, ty_source_func_lw,
+ * ty_fluxes_broadband, ty_gas_optics_rrtmgp, ty_cloud_optics_rrtmgp, rte_lw, rte_sw).  It stays
+ * the plugin API of a Fortran host.  For hosts without a Fortran toolchain - and
+ * for this repo's tests and benchmark - the same call sequences are provided here in C++ behind a
+ * plain-C interface: same names, same argument meaning, same error behaviour (a 128-character
+ * message, empty = success; reference rte/frontend/mo_rte_lw.F90:107-108).
+ *
+ * Memory: every array pointer in these structs points to BACKEND memory (device memory for the CUDA
+ * library; host memory for the CPU oracle build of the same frontend source) unless marked HOST.
+ * The frontend never dereferences backend arrays itself - it sequences kernels of
+ * rte_kernels.h / rrtmgp_kernels.h / rrtmgp_b200_ext.h, like the Fortran frontend does.
+ */
+#ifndef RRTMGP_B200_FRONTEND_H
+#define RRTMGP_B200_FRONTEND_H
+
+#include "rte_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRTMGPB_ERRLEN 128
+
+enum { RRTMGPB_1SCL = 1, RRTMGPB_2STR = 2, RRTMGPB_NSTR = 3 };
+
+/* ty_optical_props_{1scl,2str,nstr}: rte/frontend/mo_optical_props.F90:78-113,183-227 */
+typedef struct {
+  int kind;                   /* RRTMGPB_1SCL / _2STR / _NSTR */
+  int ncol, nlay, ngpt, nband;
+  int nmom;                   /* nstr only */
+  int top_at_1;               /* set_top_at_1(): is layer 1 the top of the atmosphere? */
+  const int* band_lims_gpt;   /* HOST (2,nband), 1-based inclusive; mo_optical_props.F90:183-210 */
+  const Float* band_lims_wvn; /* HOST (2,nband), may be NULL (no spectral-consistency checks then) */
+  Float* tau;                 /* (ncol,nlay,ngpt) */
+  Float* ssa;                 /* 2str, nstr */
+  Float* g;                   /* 2str */
+  Float* p;                   /* nstr: (nmom,ncol,nlay,ngpt) */
+} rrtmgpb_optical_props;
+
+/* ty_source_func_lw: rte/frontend/mo_source_functions.F90:30-38 */
+typedef struct {
+  int ncol, nlay, ngpt;
+  Float* lay_source;     /* (ncol,nlay,ngpt) */
+  Float* lev_source;     /* (ncol,nlay+1,ngpt) */
+  Float* sfc_source;     /* (ncol,ngpt) */
+  Float* sfc_source_Jac; /* (ncol,ngpt) */
+} rrtmgpb_source_func_lw;
+
+/* ty_fluxes_broadband: rte/frontend/mo_fluxes.F90:47-54.  NULL = not requested ("not associated"). */
+typedef struct {
+  Float* flux_up;     /* (ncol,nlay+1) */
+  Float* flux_dn;
+  Float* flux_net;
+  Float* flux_dn_dir; /* SW only */
+} rrtmgpb_fluxes_broadband;
+
+/* rte_config_checks(): rte/frontend/mo_rte_config.F90:29-49 */
+void rrtmgpb_rte_config_checks(int check_extents, int check_values);
+
+/* ty_optical_props_arry%validate / %delta_scale / %increment: mo_optical_props.F90:478-560,562-613,879-1028.
+ * Return 0 on success; otherwise errmsg (RRTMGPB_ERRLEN bytes) holds the reference's message. */
+int rrtmgpb_op_validate(const rrtmgpb_optical_props* op, char* errmsg);
+int rrtmgpb_op_delta_scale(rrtmgpb_optical_props* op, const Float* forward /* NULL: f = g*g */, char* errmsg);
+/* op_io is incremented by op_in ("call op_in%increment(op_io)") */
+int rrtmgpb_op_increment(const rrtmgpb_optical_props* op_in, rrtmgpb_optical_props* op_io, char* errmsg);
+
+/* rte_lw(): rte/frontend/mo_rte_lw.F90:79-473.  sfc_emis (nband,ncol); optional: inc_flux (ncol,ngpt),
+ * n_gauss_angles (0 = default 1), use_2stream (-1 = default .false.), lw_Ds (ncol,ngpt),
+ * flux_up_Jac (ncol,nlay+1).  Fluxes are ty_fluxes_broadband. */
+int rrtmgpb_rte_lw(const rrtmgpb_optical_props* optical_props, const rrtmgpb_source_func_lw* sources,
+                   const Float* sfc_emis, rrtmgpb_fluxes_broadband* fluxes, const Float* inc_flux,
+                   int n_gauss_angles, int use_2stream, const Float* lw_Ds, Float* flux_up_Jac, char* errmsg);
+/* As rte_lw with a generic (by-g-point) flux class: returns g-point fluxes (ncol,nlay+1,ngpt).  This is
+ * the path lw_solver_2stream needs (it has no broadband outputs). */
+int rrtmgpb_rte_lw_bygpoint(const rrtmgpb_optical_props* optical_props, const rrtmgpb_source_func_lw* sources,
+                            const Float* sfc_emis, Float* gpt_flux_up, Float* gpt_flux_dn,
+                            const Float* inc_flux, int n_gauss_angles, int use_2stream, const Float* lw_Ds,
+                            char* errmsg);
+
+/* rte_sw(): rte/frontend/mo_rte_sw.F90:56-394 (mu0 by column).  mu0 (ncol); inc_flux (ncol,ngpt);
+ * sfc_alb_dir, sfc_alb_dif (nband,ncol); optional inc_flux_dif (ncol,ngpt). */
+int rrtmgpb_rte_sw(const rrtmgpb_optical_props* atmos, const Float* mu0, const Float* inc_flux,
+                   const Float* sfc_alb_dir, const Float* sfc_alb_dif, rrtmgpb_fluxes_broadband* fluxes,
+                   const Float* inc_flux_dif, char* errmsg);
+int rrtmgpb_rte_sw_bygpoint(const rrtmgpb_optical_props* atmos, const Float* mu0, const Float* inc_flux,
+                            const Float* sfc_alb_dir, const Float* sfc_alb_dif, Float* gpt_flux_up,
+                            Float* gpt_flux_dn, Float* gpt_flux_dir, const Float* inc_flux_dif, char* errmsg);
+
+/* ---------------- ty_gas_optics_rrtmgp ---------------- */
+/* Tables as the Fortran object holds them after load() (mo_gas_optics_rrtmgp.F90:46-155,1151-1381).
+ * All pointers HOST; they are copied to backend memory once by rrtmgpb_gas_optics_load. */
+typedef struct {
+  int ngas, nflav, neta, npres, ntemp, nbnd, ngpt;
+  int nminorlower, nminorklower, nminorupper, nminorkupper, idx_h2o;
+  const int *flavor, *gpoint_flavor, *band_lims_gpt, *gpoint_bands;
+  const Float *band_lims_wvn, *press_ref_log, *temp_ref, *vmr_ref;
+  Float press_ref_log_delta, temp_ref_min, temp_ref_max, temp_ref_delta, press_ref_min, press_ref_max,
+      press_ref_trop_log;
+  const Float *kmajor, *kminor_lower, *kminor_upper;
+  const int *minor_limits_gpt_lower, *minor_limits_gpt_upper;
+  const Bool *minor_scales_with_density_lower, *minor_scales_with_density_upper;
+  const Bool *scale_by_complement_lower, *scale_by_complement_upper;
+  const int *idx_minor_lower, *idx_minor_upper, *idx_minor_scaling_lower, *idx_minor_scaling_upper;
+  const int *kminor_start_lower, *kminor_start_upper;
+  /* LW (internal source): NULL for SW */
+  const Float *planck_frac, *totplnk;
+  int nPlanckTemp;
+  Float totplnk_delta;
+  /* SW (external source): NULL for LW */
+  const Float *krayl, *solar_source;
+} rrtmgpb_kdist;
+
+typedef struct rrtmgpb_gas_optics_t rrtmgpb_gas_optics_t;
+rrtmgpb_gas_optics_t* rrtmgpb_gas_optics_load(const rrtmgpb_kdist* tables, char* errmsg);
+void rrtmgpb_gas_optics_free(rrtmgpb_gas_optics_t* go);
+int rrtmgpb_gas_optics_source_is_internal(const rrtmgpb_gas_optics_t* go);
+
+/* gas_optics_int(): mo_gas_optics_rrtmgp.F90:220-330.  play,tlay (ncol,nlay); plev (ncol,nlay+1);
+ * tsfc (ncol); vmr (ncol,nlay,ngas) in the k-distribution's gas order (the ty_gas_concs stand-in);
+ * optional col_dry (ncol,nlay), tlev (ncol,nlay+1). */
+int rrtmgpb_gas_optics_int(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play, const Float* plev,
+                           const Float* tlay, const Float* tsfc, const Float* vmr,
+                           rrtmgpb_optical_props* optical_props, rrtmgpb_source_func_lw* sources,
+                           const Float* col_dry, const Float* tlev, char* errmsg);
+/* gas_optics_ext(): mo_gas_optics_rrtmgp.F90:337-414.  toa_src (ncol,ngpt). */
+int rrtmgpb_gas_optics_ext(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play, const Float* plev,
+                           const Float* tlay, const Float* vmr, rrtmgpb_optical_props* optical_props,
+                           Float* toa_src, const Float* col_dry, char* errmsg);
+
+/* ---------------- ty_cloud_optics_rrtmgp (LUT form) ---------------- */
+typedef struct {
+  int nbnd, nsize_liq, nsize_ice, nrghice, icergh;
+  const int* band_lims_gpt;   /* HOST; NULL = tables are by band */
+  const Float* band_lims_wvn; /* HOST (2,nbnd) */
+  Float radliq_lwr, radliq_upr, diamice_lwr, diamice_upr;
+  const Float *extliq, *ssaliq, *asyliq; /* HOST (nsize_liq, nbnd) */
+  const Float *extice, *ssaice, *asyice; /* HOST (nsize_ice, nbnd, nrghice) */
+} rrtmgpb_cloud_lut;
+
+typedef struct rrtmgpb_cloud_optics_t rrtmgpb_cloud_optics_t;
+rrtmgpb_cloud_optics_t* rrtmgpb_cloud_optics_load(const rrtmgpb_cloud_lut* lut, char* errmsg);
+void rrtmgpb_cloud_optics_free(rrtmgpb_cloud_optics_t* co);
+/* cloud_optics(): mo_cloud_optics_rrtmgp.F90:256-431.  clwp, ciwp, reliq, dgice (ncol,nlay) */
+int rrtmgpb_cloud_optics(const rrtmgpb_cloud_optics_t* co, int ncol, int nlay, const Float* clwp, const Float* ciwp,
+                         const Float* reliq, const Float* dgice, rrtmgpb_optical_props* optical_props,
+                         char* errmsg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRTMGP_B200_FRONTEND_H */

@@ -1,0 +1,121 @@
+"""The all-sky LW+SW workload: the loop body of the reference's benchmark driver
+examples/all-sky/rrtmgp_allsky.F90:332-409 (cloud optics -> gas optics -> increment -> rte_lw / rte_sw),
+set up as in :193-311 (analytic RCEMIP-like profile replicated over ncol, ocean-ish boundary conditions,
+clouds in 2/3 of the columns).  Backend-agnostic: `ctx` decides whether arrays are CUDA tensors driving
+the product library or numpy arrays driving the CPU oracle (tests / CPU baseline only).
+"""
+import numpy as np
+
+from . import synthetic as syn
+from .frontend import (CloudOptics, FluxesBroadband, GasOptics, OpticalProps, SourceFuncLW, rte_lw, rte_sw)
+
+
+class AllSky:
+    def __init__(self, ctx, ncol, nlay, kd_lw=None, kd_sw=None, do_clouds=True, profiles=None, col_offset=0,
+                 mu0=0.86, sfc_alb=0.06, emis=0.98):
+        self.ctx, self.ncol, self.nlay = ctx, ncol, nlay
+        prof = profiles if profiles is not None else syn.compute_profiles(300.0, ncol, nlay)
+        self.host_inputs = {}
+        vmr = syn.allsky_gas_vmrs(prof)
+        put = ctx.put
+        self.p_lay, self.p_lev = put(prof["p_lay"]), put(prof["p_lev"])
+        self.t_lay, self.t_lev = put(prof["t_lay"]), put(prof["t_lev"])
+        self.vmr = put(vmr)
+        top_at_1 = bool(prof["p_lay"][0, 0] < prof["p_lay"][0, nlay - 1])
+        sfc = nlay if top_at_1 else 0
+        self.host_inputs.update(p_lay=prof["p_lay"], p_lev=prof["p_lev"], t_lay=prof["t_lay"], t_lev=prof["t_lev"], vmr=vmr)
+        self.lw = self.sw = None
+        if kd_lw is not None:
+            lw = type("LW", (), {})()
+            lw.go = GasOptics(ctx, kd_lw)
+            lw.atmos = OpticalProps.like(ctx, "1scl", ncol, nlay, lw.go)
+            lw.sources = SourceFuncLW(ctx, ncol, nlay, kd_lw.ngpt)
+            lw.t_sfc = put(np.ascontiguousarray(prof["t_lev"][:, sfc]))  # rrtmgp_allsky.F90:296
+            lw.emis_sfc = put(np.full((kd_lw.nbnd, ncol), emis, order="F"))
+            lw.flux_up, lw.flux_dn = ctx.zeros((ncol, nlay + 1)), ctx.zeros((ncol, nlay + 1))
+            lw.fluxes = FluxesBroadband(flux_up=lw.flux_up, flux_dn=lw.flux_dn)
+            if do_clouds:
+                lw.lut = syn.make_cloud_lut(kd_lw)
+                lw.co = CloudOptics(ctx, lw.lut)
+                lw.clouds = OpticalProps.like(ctx, "1scl", ncol, nlay, lw.co)
+            self.lw = lw
+        if kd_sw is not None:
+            sw = type("SW", (), {})()
+            sw.go = GasOptics(ctx, kd_sw)
+            sw.atmos = OpticalProps.like(ctx, "2str", ncol, nlay, sw.go)
+            sw.toa_flux = ctx.zeros((ncol, kd_sw.ngpt))
+            sw.mu0 = put(np.full(ncol, mu0))
+            sw.sfc_alb_dir = put(np.full((kd_sw.nbnd, ncol), sfc_alb, order="F"))
+            sw.sfc_alb_dif = put(np.full((kd_sw.nbnd, ncol), sfc_alb, order="F"))
+            sw.flux_up, sw.flux_dn, sw.flux_dir = (ctx.zeros((ncol, nlay + 1)) for _ in range(3))
+            sw.fluxes = FluxesBroadband(flux_up=sw.flux_up, flux_dn=sw.flux_dn, flux_dn_dir=sw.flux_dir)
+            if do_clouds:
+                sw.lut = syn.make_cloud_lut(kd_sw)
+                sw.co = CloudOptics(ctx, sw.lut)
+                sw.clouds = OpticalProps.like(ctx, "2str", ncol, nlay, sw.co)
+            self.sw = sw
+        self.do_clouds = do_clouds
+        if do_clouds:
+            some = self.lw if self.lw is not None else self.sw
+            # compute_clouds uses the 1-based GLOBAL column index in mod(icol,3); col_offset keeps the
+            # pattern continuous when columns are sharded across ranks
+            cl = syn.compute_clouds(prof, some.lut)
+            if col_offset:
+                cl = _shift_cloud_columns(prof, some.lut, col_offset)
+            self.lwp, self.iwp, self.rel, self.dei = put(cl["lwp"]), put(cl["iwp"]), put(cl["rel"]), put(cl["dei"])
+            self.host_inputs.update(cl)
+
+    # -- one iteration of the reference loop body, LW branch (rrtmgp_allsky.F90:340-381)
+    def step_lw(self):
+        lw = self.lw
+        if self.do_clouds:
+            lw.co.cloud_optics(self.lwp, self.iwp, self.rel, self.dei, lw.clouds)
+        lw.go.gas_optics(self.p_lay, self.p_lev, self.t_lay, self.vmr, lw.atmos, t_sfc=lw.t_sfc, sources=lw.sources,
+                         tlev=self.t_lev)
+        if self.do_clouds:
+            lw.clouds.increment(lw.atmos)
+        rte_lw(self.ctx, lw.atmos, lw.sources, lw.emis_sfc, lw.fluxes)
+
+    # -- SW branch (rrtmgp_allsky.F90:340-352,383-406)
+    def step_sw(self):
+        sw = self.sw
+        if self.do_clouds:
+            sw.co.cloud_optics(self.lwp, self.iwp, self.rel, self.dei, sw.clouds)
+        sw.go.gas_optics(self.p_lay, self.p_lev, self.t_lay, self.vmr, sw.atmos, toa_src=sw.toa_flux)
+        if self.do_clouds:
+            sw.clouds.delta_scale()
+            sw.clouds.increment(sw.atmos)
+        rte_sw(self.ctx, sw.atmos, sw.mu0, sw.toa_flux, sw.sfc_alb_dir, sw.sfc_alb_dif, sw.fluxes)
+
+    def step(self):
+        if self.lw is not None:
+            self.step_lw()
+        if self.sw is not None:
+            self.step_sw()
+
+    def fluxes_host(self):
+        out = {}
+        if self.lw is not None:
+            out["lw_flux_up"], out["lw_flux_dn"] = self.ctx.get(self.lw.flux_up), self.ctx.get(self.lw.flux_dn)
+        if self.sw is not None:
+            out["sw_flux_up"], out["sw_flux_dn"] = self.ctx.get(self.sw.flux_up), self.ctx.get(self.sw.flux_dn)
+            out["sw_flux_dir"] = self.ctx.get(self.sw.flux_dir)
+        return out
+
+
+def _shift_cloud_columns(prof, lut, col_offset):
+    ncol = prof["p_lay"].shape[0]
+    big = {k: v for k, v in prof.items()}
+    cl = syn.compute_clouds(big, lut)
+    icol = np.arange(1 + col_offset, ncol + 1 + col_offset)[:, None]
+    keep = icol % 3 != 0
+    base = (prof["p_lay"] > 100.0 * 100.0) & (prof["p_lay"] < 900.0 * 100.0)
+    rel_val = float(np.float32(0.5)) * (lut.radliq_lwr + lut.radliq_upr)
+    dei_val = float(np.float32(0.5)) * (lut.diamice_lwr + lut.diamice_upr)
+    mask = base & keep
+    lwp = np.where(mask & (prof["t_lay"] > 263.0), 10.0, 0.0)
+    iwp = np.where(mask & (prof["t_lay"] < 273.0), 10.0, 0.0)
+    cl = dict(lwp=np.asfortranarray(lwp), iwp=np.asfortranarray(iwp),
+              rel=np.asfortranarray(np.where(lwp > 0, rel_val, 0.0)),
+              dei=np.asfortranarray(np.where(iwp > 0, dei_val, 0.0)))
+    return cl

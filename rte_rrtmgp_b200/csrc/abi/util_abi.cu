@@ -1,0 +1,325 @@
+// util_abi.cu - fills, broadband reductions, Planck helpers and the frontend-glue kernels.
+//
+// Reference interfaces replaced (extern mode):
+//   rte/kernels/api/mo_rte_util_array.F90:23-79          zero_array_*D, set_to_scalar_*D
+//   rte/kernels/api/mo_fluxes_broadband_kernels.F90:26-72 rte_sum_broadband, rte_net_broadband_*
+//   rte/kernels/api/mo_gas_optics_utils.F90:7-36          rte_compute_Planck_source_1D/_2D
+// and the frontend loops listed in include/rrtmgp_b200_ext.h (SURVEY.md section 8a').
+// All pure-bandwidth: one coalesced pass, grid-stride, columns innermost.
+#include "../kernels/elementwise.cuh"
+#include "rte_kernels.h"
+#include "rrtmgp_b200_ext.h"
+
+using namespace rrtmgpb;
+
+namespace {
+
+void fill(size_t n, Float* array, Float v) {
+  DevArg<Float> a(array, n, Dir::Out);
+  Float* p = a;
+  if (v == (Float)0) {
+    RB_CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(Float), stream()));
+    count_launch();
+  } else {
+    launch_elementwise(n, [=] __device__(size_t i) { p[i] = v; });
+  }
+}
+
+// physical constants, rte/kernels/mo_gas_optics_constants.F90:10-38 (host copies; passed by value)
+struct Constants {
+  double boltzmann_k = 1.380649e-23, m_h2o = 0.018016, avogad = 6.02214076e23;
+  double planck_h = 6.626075540e-34, lightspeed = 2.99792458e8;
+  double m_dry = 0.028964, grav = 9.80665, cp_dry = 1004.64;
+} g_const;
+
+__device__ __forceinline__ Float B_nu(Float T, Float nu, Float h, Float c, Float kb) {
+  // rte/kernels/mo_gas_optics_utils.F90:36-41
+  const Float nu100 = nu * (Float)100;
+  return (Float)100 * (Float)2 * h * (nu100 * nu100 * nu100) * (c * c) /
+         (exp((h * c * nu * (Float)100) / (kb * T)) - (Float)1);
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---------------- fills ----------------
+void zero_array_1D(const int* ni, Float* array) { OpName op_name__(__func__); fill((size_t)*ni, array, 0); }
+void zero_array_2D(const int* ni, const int* nj, Float* array) { OpName op_name__(__func__); fill((size_t)*ni * *nj, array, 0); }
+void zero_array_3D(const int* ni, const int* nj, const int* nk, Float* array) {
+  OpName op_name__(__func__);
+  fill((size_t)*ni * *nj * *nk, array, 0);
+}
+void zero_array_4D(const int* ni, const int* nj, const int* nk, const int* nl, Float* array) {
+  OpName op_name__(__func__);
+  fill((size_t)*ni * *nj * *nk * *nl, array, 0);
+}
+void set_to_scalar_1D(const int* ni, Float* array, const Float* value) { OpName op_name__(__func__); fill((size_t)*ni, array, *value); }
+void set_to_scalar_2D(const int* ni, const int* nj, Float* array, const Float* value) {
+  OpName op_name__(__func__);
+  fill((size_t)*ni * *nj, array, *value);
+}
+void set_to_scalar_3D(const int* ni, const int* nj, const int* nk, Float* array, const Float* value) {
+  OpName op_name__(__func__);
+  fill((size_t)*ni * *nj * *nk, array, *value);
+}
+void set_to_scalar_4D(const int* ni, const int* nj, const int* nk, const int* nl, Float* array,
+                      const Float* value) {
+  OpName op_name__(__func__);
+  fill((size_t)*ni * *nj * *nk * *nl, array, *value);
+}
+
+// ---------------- broadband reductions ----------------
+// One thread per (col,lev); sequential sum over g-points 1..ngpt - the reference's order
+// (mo_fluxes_broadband_kernels.F90:45-58), so results are reproducible run to run.
+void rte_sum_broadband(const int* ncol, const int* nlev, const int* ngpt, const Float* spectral_flux,
+                       Float* broadband_flux) {
+  OpName op_name__(__func__);
+  const size_t n2 = (size_t)*ncol * *nlev;
+  const int ng = *ngpt;
+  DevArg<Float> in(spectral_flux, n2 * ng, Dir::In), out(broadband_flux, n2, Dir::Out);
+  const Float* s = in; Float* b = out;
+  launch_elementwise(n2, [=] __device__(size_t c) {
+    Float acc = 0;
+#pragma unroll 8
+    for (int ig = 0; ig < ng; ++ig) acc = acc + s[c + n2 * ig];
+    b[c] = acc;
+  });
+}
+
+void rte_net_broadband_full(const int* ncol, const int* nlev, const int* ngpt, const Float* spectral_flux_dn,
+                            const Float* spectral_flux_up, Float* broadband_flux_net) {
+  OpName op_name__(__func__);
+  const size_t n2 = (size_t)*ncol * *nlev;
+  const int ng = *ngpt;
+  DevArg<Float> dn(spectral_flux_dn, n2 * ng, Dir::In), up(spectral_flux_up, n2 * ng, Dir::In),
+      out(broadband_flux_net, n2, Dir::Out);
+  const Float *d = dn, *u = up; Float* b = out;
+  launch_elementwise(n2, [=] __device__(size_t c) {
+    Float acc = d[c] - u[c];
+#pragma unroll 4
+    for (int ig = 1; ig < ng; ++ig) acc = acc + (d[c + n2 * ig] - u[c + n2 * ig]);
+    b[c] = acc;
+  });
+}
+
+void rte_net_broadband_precalc(const int* ncol, const int* nlev, const Float* flux_dn, const Float* flux_up,
+                               Float* broadband_flux_net) {
+  OpName op_name__(__func__);
+  const size_t n2 = (size_t)*ncol * *nlev;
+  DevArg<Float> dn(flux_dn, n2, Dir::In), up(flux_up, n2, Dir::In), out(broadband_flux_net, n2, Dir::Out);
+  const Float *d = dn, *u = up; Float* b = out;
+  launch_elementwise(n2, [=] __device__(size_t c) { b[c] = d[c] - u[c]; });
+}
+
+// ---------------- Planck helpers (used by the SSM gas optics) ----------------
+void rte_compute_Planck_source_2D(const int* ncol, const int* nlay, const int* nnu, const Float* nus,
+                                  const Float* dnus, const Float* T, Float* source) {
+  OpName op_name__(__func__);
+  const size_t n2 = (size_t)*ncol * *nlay;
+  const int nn = *nnu;
+  DevArg<Float> nu(nus, nn, Dir::In), dnu(dnus, nn, Dir::In), t(T, n2, Dir::In), out(source, n2 * nn, Dir::Out);
+  const Float *pn = nu, *pd = dnu, *pt = t; Float* ps = out;
+  const Float h = (Float)g_const.planck_h, c = (Float)g_const.lightspeed, kb = (Float)g_const.boltzmann_k;
+  launch_elementwise(n2 * nn, [=] __device__(size_t i) {
+    const size_t cell = i % n2; const int inu = (int)(i / n2);
+    ps[i] = B_nu(pt[cell], pn[inu], h, c, kb) * pd[inu];
+  });
+}
+void rte_compute_Planck_source_1D(const int* ncol, const int* nnu, const Float* nus, const Float* dnus,
+                                  const Float* T, Float* source) {
+  OpName op_name__(__func__);
+  const int one = 1;
+  rte_compute_Planck_source_2D(ncol, &one, nnu, nus, dnus, T, source);
+}
+
+// ---------------- extension: constants ----------------
+void rrtmgpb_init_constants(const Float* gravity, const Float* mol_weight_dry_air,
+                            const Float* heat_capacity_dry_air) {
+  OpName op_name__(__func__);
+  if (gravity) g_const.grav = *gravity;
+  if (mol_weight_dry_air) g_const.m_dry = *mol_weight_dry_air;
+  if (heat_capacity_dry_air) g_const.cp_dry = *heat_capacity_dry_air;
+}
+
+// ---------------- extension: frontend glue ----------------
+void rrtmgpb_get_col_dry(int ncol, int nlay, const Float* vmr_h2o, const Float* plev, Float* col_dry) {
+  OpName op_name__(__func__);
+  const size_t ncl = (size_t)ncol * nlay;
+  DevArg<Float> v(vmr_h2o, ncl, Dir::In), p(plev, ncl + ncol, Dir::In), o(col_dry, ncl, Dir::Out);
+  const Float *pv = v, *pp = p; Float* po = o;
+  const Float m_dry = (Float)g_const.m_dry, m_h2o = (Float)g_const.m_h2o, avogad = (Float)g_const.avogad,
+              grav = (Float)g_const.grav;
+  launch_elementwise(ncl, [=] __device__(size_t k) {  // mo_gas_optics_utils.F90:143-150
+    const Float delta_plev = fabs(pp[k] - pp[k + ncol]);
+    const Float fact = (Float)1 / ((Float)1 + pv[k]);
+    const Float m_air = (m_dry + m_h2o * pv[k]) * fact;
+    po[k] = (Float)10 * delta_plev * avogad * fact / ((Float)1000 * m_air * (Float)100 * grav);
+  });
+}
+
+void rrtmgpb_get_layer_mass(int ncol, int nlay, int ngas, const Float* vmr, const Float* plev,
+                            const Float* mol_weights, Float m_dry, Float* layer_mass) {
+  OpName op_name__(__func__);
+  const size_t ncl = (size_t)ncol * nlay, n = ncl * ngas;
+  DevArg<Float> v(vmr, n, Dir::In), p(plev, ncl + ncol, Dir::In), w(mol_weights, ngas, Dir::In),
+      o(layer_mass, n, Dir::Out);
+  const Float *pv = v, *pp = p, *pw = w; Float* po = o;
+  const Float grav = (Float)g_const.grav;
+  launch_elementwise(n, [=] __device__(size_t k) {  // mo_gas_optics_utils.F90:114-123
+    const int igas = (int)(k % ngas); const size_t cell = k / ngas;
+    po[k] = pv[k] * (pw[igas] / m_dry) * fabs(pp[cell + ncol] - pp[cell]) / grav;
+  });
+}
+
+void rrtmgpb_col_gas_from_vmr(int ncol, int nlay, int ngas, const Float* vmr, const Float* col_dry,
+                              Float* col_gas) {
+  OpName op_name__(__func__);
+  const size_t ncl = (size_t)ncol * nlay;
+  DevArg<Float> v(vmr, ncl * ngas, Dir::In), cd(col_dry, ncl, Dir::In), o(col_gas, ncl * (ngas + 1), Dir::Out);
+  const Float *pv = v, *pc = cd; Float* po = o;
+  launch_elementwise(ncl * (ngas + 1), [=] __device__(size_t k) {
+    const size_t c = k % ncl;
+    po[k] = (k < ncl) ? pc[c] : pv[k - ncl] * pc[c];
+  });
+}
+
+void rrtmgpb_combine_abs_and_rayleigh(int ncol, int nlay, int ngpt, int kind, const Float* tau_abs,
+                                      const Float* tau_rayleigh, Float* tau, Float* ssa, Float* g) {
+  OpName op_name__(__func__);
+  const size_t n = (size_t)ncol * nlay * ngpt;
+  // tau may alias tau_abs: stage once and treat as in/out in that case
+  const bool alias = (tau == tau_abs);
+  DevArg<Float> ta(tau_abs, n, Dir::In, !alias), tr(tau_rayleigh, n, Dir::In);
+  DevArg<Float> t(tau, n, alias ? Dir::InOut : Dir::Out);
+  DevArg<Float> s(ssa, n, Dir::Out, kind == 2), gg(g, n, Dir::Out, kind == 2);
+  const Float* pa = alias ? t.get() : ta.get();
+  const Float* pr = tr; Float* pt = t; Float* ps = s; Float* pg = gg;
+  if (kind == 1) {
+    launch_elementwise(n, [=] __device__(size_t i) { pt[i] = pa[i] + pr[i]; });
+  } else {
+    launch_elementwise(n, [=] __device__(size_t i) {  // mo_gas_optics_rrtmgp.F90:1986-2002
+      const Float r = pr[i];
+      const Float tt = pa[i] + r;
+      ps[i] = (tt > (Float)2 * (Float)RB_TINY) ? r / tt : (Float)0;
+      pt[i] = tt;
+      pg[i] = (Float)0;
+    });
+  }
+}
+
+void rrtmgpb_interpolate_tlev(int ncol, int nlay, const Float* play, const Float* plev, const Float* tlay,
+                              Float* tlev) {
+  OpName op_name__(__func__);
+  const size_t ncl = (size_t)ncol * nlay, nclp = ncl + ncol;
+  DevArg<Float> pl(play, ncl, Dir::In), pv(plev, nclp, Dir::In), tl(tlay, ncl, Dir::In), o(tlev, nclp, Dir::Out);
+  const Float *play_ = pl, *plev_ = pv, *tlay_ = tl; Float* tlev_ = o;
+  launch_elementwise(nclp, [=] __device__(size_t k) {  // mo_gas_optics_rrtmgp.F90:893-911
+    const int l = (int)(k / ncol); const size_t i = k % ncol;
+#define A2(a, ll) a[i + (size_t)ncol * (size_t)(ll)]
+    Float v;
+    if (l == 0) {
+      v = A2(tlay_, 0) + (A2(plev_, 0) - A2(play_, 0)) * (A2(tlay_, 1) - A2(tlay_, 0)) / (A2(play_, 1) - A2(play_, 0));
+    } else if (l == nlay) {
+      v = A2(tlay_, nlay - 1) + (A2(plev_, nlay) - A2(play_, nlay - 1)) * (A2(tlay_, nlay - 1) - A2(tlay_, nlay - 2)) /
+                                    (A2(play_, nlay - 1) - A2(play_, nlay - 2));
+    } else {
+      v = (A2(play_, l - 1) * A2(tlay_, l - 1) * (A2(plev_, l) - A2(play_, l)) +
+           A2(play_, l) * A2(tlay_, l) * (A2(play_, l - 1) - A2(plev_, l))) /
+          (A2(plev_, l) * (A2(play_, l - 1) - A2(play_, l)));
+    }
+#undef A2
+    tlev_[k] = v;
+  });
+}
+
+void rrtmgpb_broadcast_by_gpt(int ncol, int ngpt, const Float* per_gpt, Float* out) {
+  OpName op_name__(__func__);
+  const size_t n = (size_t)ncol * ngpt;
+  DevArg<Float> in(per_gpt, ngpt, Dir::In), o(out, n, Dir::Out);
+  const Float* pi = in; Float* po = o;
+  launch_elementwise(n, [=] __device__(size_t k) { po[k] = pi[k / ncol]; });
+}
+
+void rrtmgpb_broadcast_by_lay(int ncol, int nlay, const Float* per_col, Float* out) {
+  OpName op_name__(__func__);
+  const size_t n = (size_t)ncol * nlay;
+  DevArg<Float> in(per_col, ncol, Dir::In), o(out, n, Dir::Out);
+  const Float* pi = in; Float* po = o;
+  launch_elementwise(n, [=] __device__(size_t k) { po[k] = pi[k % ncol]; });
+}
+
+void rrtmgpb_expand_and_transpose(int ncol, int nband, int ngpt, const int* band_lims_gpt,
+                                  const Float* arr_in, Float* arr_out) {
+  OpName op_name__(__func__);
+  const size_t n = (size_t)ncol * ngpt;
+  DevArg<int> lims(band_lims_gpt, 2 * (size_t)nband, Dir::In);
+  DevArg<Float> in(arr_in, (size_t)nband * ncol, Dir::In), o(arr_out, n, Dir::Out);
+  const int* pl = lims; const Float* pi = in; Float* po = o;
+  launch_elementwise(n, [=] __device__(size_t k) {  // mo_rte_lw.F90:490-500
+    const int g = (int)(k / ncol) + 1; const size_t i = k % ncol;
+    int b = 0;
+    while (b < nband - 1 && g > pl[2 * b + 1]) ++b;
+    if (g >= pl[2 * b] && g <= pl[2 * b + 1]) po[k] = pi[(size_t)b + (size_t)nband * i];
+  });
+}
+
+void rrtmgpb_cloud_masks(int ncol, int nlay, const Float* clwp, const Float* ciwp, Bool* liqmsk, Bool* icemsk) {
+  OpName op_name__(__func__);
+  const size_t n = (size_t)ncol * nlay;
+  DevArg<Float> l(clwp, n, Dir::In), ic(ciwp, n, Dir::In);
+  DevArg<Bool> lm(liqmsk, n, Dir::Out), im(icemsk, n, Dir::Out);
+  const Float *pl = l, *pi = ic; Bool *plm = lm, *pim = im;
+  launch_elementwise(n, [=] __device__(size_t k) { plm[k] = pl[k] > (Float)0; pim[k] = pi[k] > (Float)0; });
+}
+
+void rrtmgpb_cloud_combine(int ncol, int nlay, int ngpt, int kind, const Float* ltau, const Float* ltaussa,
+                           const Float* ltaussag, const Float* itau, const Float* itaussa,
+                           const Float* itaussag, Float* tau, Float* ssa, Float* g) {
+  OpName op_name__(__func__);
+  const size_t n = (size_t)ncol * nlay * ngpt;
+  DevArg<Float> lt(ltau, n, Dir::In), lts(ltaussa, n, Dir::In), ltg(ltaussag, n, Dir::In, kind == 2);
+  DevArg<Float> it(itau, n, Dir::In), its(itaussa, n, Dir::In), itg(itaussag, n, Dir::In, kind == 2);
+  DevArg<Float> t(tau, n, Dir::Out), s(ssa, n, Dir::Out, kind == 2), gg(g, n, Dir::Out, kind == 2);
+  const Float *a = lt, *b = lts, *c = ltg, *d = it, *e = its, *f = itg;
+  Float *pt = t, *ps = s, *pg = gg;
+  if (kind == 1) {
+    launch_elementwise(n, [=] __device__(size_t i) { pt[i] = (a[i] - b[i]) + (d[i] - e[i]); });
+  } else {
+    launch_elementwise(n, [=] __device__(size_t i) {  // mo_cloud_optics_rrtmgp.F90:412-422
+      const Float tt = a[i] + d[i];
+      const Float ts = b[i] + e[i];
+      pg[i] = (c[i] + f[i]) / fmax((Float)RB_EPS, ts);
+      ps[i] = ts / fmax((Float)RB_EPS, tt);
+      pt[i] = tt;
+    });
+  }
+}
+
+static int any_flag(size_t n, const Float* array, const Bool* mask, Float lo, Float hi, bool use_hi) {
+  DevArg<Float> a(array, n, Dir::In);
+  DevArg<Bool> m(mask, n, Dir::In, mask != nullptr);
+  int* flag = static_cast<int*>(dev_alloc(sizeof(int)));
+  RB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), stream()));
+  const Float* pa = a; const Bool* pm = mask ? m.get() : nullptr;
+  launch_elementwise(n, [=] __device__(size_t i) {
+    if (pm && !pm[i]) return;
+    const Float v = pa[i];
+    if (v < lo || (use_hi && v > hi)) *flag = 1;
+  });
+  int h = 0;
+  RB_CUDA_CHECK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+  RB_CUDA_CHECK(cudaStreamSynchronize(stream()));
+  dev_free(flag);
+  return h;
+}
+int rrtmgpb_any_vals_less_than(size_t n, const Float* array, const Bool* mask, Float check_value) {
+  OpName op_name__(__func__);
+  return any_flag(n, array, mask, check_value, 0, false);
+}
+int rrtmgpb_any_vals_outside(size_t n, const Float* array, const Bool* mask, Float checkMin, Float checkMax) {
+  OpName op_name__(__func__);
+  return any_flag(n, array, mask, checkMin, checkMax, true);
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// common.cuh - runtime plumbing shared by every kernel file of librte_rrtmgp_b200.so
+//
+// * one launch stream (set by the host program, e.g. torch's current stream)
+// * CUDA errors abort: the reference kernels are `subroutine`s with no error path
+//   (SURVEY.md section 8b "Errors"), so a failed launch must never be silently ignored
+// * DevIn/DevOut/DevInOut: pointer provenance at the ABI.  The Fortran frontend hands the
+//   extern kernels whatever it allocated; device/managed pointers are used in place
+//   (stream-ordered, no copies), pageable/pinned host pointers are staged through the device
+//   (correctness path: copy in, run, copy out, synchronise).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstddef>
+#include <cfloat>
+#include "rte_types.h"
+
+namespace rrtmgpb {
+
+#define RB_CUDA_CHECK(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t err__ = (expr);                                                               \
+    if (err__ != cudaSuccess) {                                                               \
+      std::fprintf(stderr, "rte_rrtmgp_b200: CUDA error %s at %s:%d: %s\n",                    \
+                   cudaGetErrorName(err__), __FILE__, __LINE__, cudaGetErrorString(err__));   \
+      std::abort();                                                                           \
+    }                                                                                         \
+  } while (0)
+
+cudaStream_t stream();
+void count_launch(int n = 1);
+// Scratch in device memory (stream-ordered pool).
+void* dev_alloc(size_t bytes);
+void dev_free(void* p);
+bool is_device_ptr(const void* p);
+
+// Optional per-kernel timing with CUDA events on the launch stream (rrtmgpb_profile_enable()):
+// construct one right before a launch; the destructor records the closing event.
+struct KernelTimer {
+  explicit KernelTimer(const char* name);
+  ~KernelTimer();
+  KernelTimer(const KernelTimer&) = delete;
+  KernelTimer& operator=(const KernelTimer&) = delete;
+  int slot;
+};
+
+// Name of the ABI entry point currently executing (labels its elementwise launches in the profiler).
+extern thread_local const char* tl_op_name;
+struct OpName {
+  explicit OpName(const char* n) : prev(tl_op_name) { if (!tl_op_name) tl_op_name = n; }
+  ~OpName() { tl_op_name = prev; }
+  const char* prev;
+};
+
+#define RB_LAUNCH_CHECK()                 \
+  do {                                    \
+    RB_CUDA_CHECK(cudaGetLastError());    \
+    ::rrtmgpb::count_launch();            \
+  } while (0)
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- argument staging ----------------------------------------------------------------------
+enum class Dir { In, Out, InOut };
+
+template <typename T>
+class DevArg {
+ public:
+  DevArg(const T* p, size_t count, Dir dir, bool used = true) : host_(const_cast<T*>(p)), n_(count), dir_(dir) {
+    if (!used || p == nullptr || count == 0) { dev_ = const_cast<T*>(p); staged_ = false; return; }
+    if (is_device_ptr(p)) { dev_ = const_cast<T*>(p); staged_ = false; return; }
+    staged_ = true;
+    dev_ = static_cast<T*>(dev_alloc(n_ * sizeof(T)));
+    if (dir_ != Dir::Out)
+      RB_CUDA_CHECK(cudaMemcpyAsync(dev_, host_, n_ * sizeof(T), cudaMemcpyHostToDevice, stream()));
+  }
+  ~DevArg() {
+    if (!staged_) return;
+    if (dir_ != Dir::In) {
+      RB_CUDA_CHECK(cudaMemcpyAsync(host_, dev_, n_ * sizeof(T), cudaMemcpyDeviceToHost, stream()));
+      RB_CUDA_CHECK(cudaStreamSynchronize(stream()));
+    }
+    dev_free(dev_);
+  }
+  DevArg(const DevArg&) = delete;
+  DevArg& operator=(const DevArg&) = delete;
+  T* get() const { return dev_; }
+  operator T*() const { return dev_; }
+  bool staged() const { return staged_; }
+
+ private:
+  T* host_;
+  T* dev_;
+  size_t n_;
+  Dir dir_;
+  bool staged_;
+};
+
+template <typename T> using In = DevArg<T>;
+
+// numeric limits of the working precision (Fortran epsilon(), tiny())
+#ifdef RTE_USE_SP
+typedef float2 Float2;
+#define make_Float2 make_float2
+#else
+typedef double2 Float2;
+#define make_Float2 make_double2
+#endif
+#ifdef RTE_USE_SP
+#define RB_EPS FLT_EPSILON
+#define RB_TINY FLT_MIN
+#else
+#define RB_EPS DBL_EPSILON
+#define RB_TINY DBL_MIN
+#endif
+
+}  // namespace rrtmgpb

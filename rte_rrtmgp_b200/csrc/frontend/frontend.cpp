@@ -1,0 +1,724 @@
+// frontend.cpp - C++ mirror of the reference's Fortran frontend for the all-sky / clear-sky hot path.
+//
+// Mirrors (same call sequences, argument meaning, error strings):
+//   rte/frontend/mo_rte_config.F90:29-49            rte_config_checks
+//   rte/frontend/mo_optical_props.F90:562-700,879-1028  delta_scale, validate, increment
+//   rte/frontend/mo_rte_lw.F90:79-501               rte_lw (+ expand_and_transpose, Gauss-Jacobi-5 table)
+//   rte/frontend/mo_rte_sw.F90:56-422               rte_sw (mu0 by column)
+//   rrtmgp/frontend/mo_gas_optics_rrtmgp.F90:220-414,419-745,840-928  gas_optics_int/ext, compute_gas_taus, source
+//   rrtmgp/frontend/mo_cloud_optics_rrtmgp.F90:256-431            cloud_optics (LUT)
+//
+// Backend-agnostic by construction: this file only sequences extern "C" kernels (rte_kernels.h,
+// rrtmgp_kernels.h, rrtmgp_b200_ext.h) and never dereferences an array, so the SAME source is linked
+// (a) into librte_rrtmgp_b200.so against the CUDA kernels - the product - and (b) into the oracle's
+// liboracle.so against the CPU restatement - test infrastructure / CPU baseline.  That is the
+// reference's own RTE_KERNEL_MODE idea (one frontend, interchangeable kernel providers).
+//
+// Differences from the Fortran frontend, all deliberate:
+//   * gas concentrations arrive as one (ncol,nlay,ngas) vmr array in k-distribution gas order instead of
+//     a ty_gas_concs object;
+//   * when the caller wants broadband fluxes the absorption kernel ASSIGNS tau (extension symbol) instead
+//     of zero_array + accumulate, saving two plane passes; results are identical.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rrtmgp_b200_ext.h"
+#include "rrtmgp_b200_frontend.h"
+#include "rrtmgp_kernels.h"
+#include "rte_kernels.h"
+
+namespace {
+
+bool g_check_extents = true;  // mo_rte_config.F90:25-26
+bool g_check_values = true;
+
+int fail(char* errmsg, const std::string& msg) {
+  if (errmsg) {
+    std::memset(errmsg, 0, RRTMGPB_ERRLEN);
+    std::strncpy(errmsg, msg.c_str(), RRTMGPB_ERRLEN - 1);
+  }
+  return msg.empty() ? 0 : 1;
+}
+int ok(char* errmsg) { return fail(errmsg, ""); }
+
+// scratch in backend memory, freed at scope exit (stream-ordered on CUDA)
+template <typename T>
+struct Scratch {
+  T* p;
+  explicit Scratch(size_t n) : p(static_cast<T*>(rrtmgpb_mem_alloc(n * sizeof(T)))) {}
+  ~Scratch() { rrtmgpb_mem_free(p); }
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+  operator T*() const { return p; }
+};
+
+template <typename T>
+T* upload(const T* host, size_t n) {
+  if (!host || n == 0) return nullptr;
+  T* d = static_cast<T*>(rrtmgpb_mem_alloc(n * sizeof(T)));
+  rrtmgpb_mem_to_backend(d, host, n * sizeof(T));
+  return d;
+}
+
+bool bands_are_equal(const rrtmgpb_optical_props* a, const rrtmgpb_optical_props* b) {
+  // mo_optical_props.F90 bands_are_equal: same number of bands and wavenumber limits within 5 spacings
+  if (a->nband != b->nband) return false;
+  if (!a->band_lims_wvn || !b->band_lims_wvn) return true;
+  for (int i = 0; i < 2 * a->nband; ++i) {
+    const Float x = a->band_lims_wvn[i], y = b->band_lims_wvn[i];
+    const Float d = x > y ? x - y : y - x;
+    if (d > (Float)5 * (Float)2.220446049250313e-16 * (x > 0 ? x : -x)) return false;
+  }
+  return true;
+}
+bool gpoints_are_equal(const rrtmgpb_optical_props* a, const rrtmgpb_optical_props* b) {
+  if (!bands_are_equal(a, b) || a->ngpt != b->ngpt) return false;
+  for (int i = 0; i < 2 * a->nband; ++i)
+    if (a->band_lims_gpt[i] != b->band_lims_gpt[i]) return false;
+  return true;
+}
+
+// Gauss-Jacobi-5 quadrature, mo_rte_lw.F90:136-160 (values are mu = cos(theta); D = 1/mu)
+const int max_gauss_pts = 4;
+const double gauss_mus[4][4] = {{0.6096748751, 0, 0, 0},
+                                {0.2509907356, 0.7908473988, 0, 0},
+                                {0.1024922169, 0.4417960320, 0.8633751621, 0},
+                                {0.0454586727, 0.2322334416, 0.5740198775, 0.9030775973}};
+const double gauss_wts[4][4] = {{1.0, 0, 0, 0},
+                                {0.2300253764, 0.7699746236, 0, 0},
+                                {0.0437820218, 0.3875796738, 0.5686383044, 0},
+                                {0.0092068785, 0.1285704278, 0.4323381850, 0.4298845087}};
+
+}  // namespace
+
+extern "C" {
+
+void rrtmgpb_rte_config_checks(int check_extents, int check_values) {
+  g_check_extents = check_extents != 0;
+  g_check_values = check_values != 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ty_optical_props_arry
+// ------------------------------------------------------------------------------------------------
+int rrtmgpb_op_validate(const rrtmgpb_optical_props* op, char* errmsg) {
+  const size_t n = (size_t)op->ncol * op->nlay * op->ngpt;
+  std::string msg;
+  if (!op->tau) return fail(errmsg, "validate: tau not allocated/initialized");
+  if (op->kind != RRTMGPB_1SCL && (!op->ssa || (op->kind == RRTMGPB_2STR ? !op->g : !op->p)))
+    return fail(errmsg, "validate: arrays not allocated/initialized");
+  if (g_check_values) {  // mo_optical_props.F90:618-621,652-659,691-698
+    if (rrtmgpb_any_vals_less_than(n, op->tau, nullptr, 0)) msg = "validate: tau values out of range";
+    if (op->kind != RRTMGPB_1SCL) {
+      if (rrtmgpb_any_vals_outside(n, op->ssa, nullptr, 0, 1)) msg = "validate: ssa values out of range";
+      if (op->kind == RRTMGPB_2STR && rrtmgpb_any_vals_outside(n, op->g, nullptr, -1, 1))
+        msg = "validate: g values out of range";
+    }
+  }
+  return fail(errmsg, msg);
+}
+
+int rrtmgpb_op_delta_scale(rrtmgpb_optical_props* op, const Float* forward, char* errmsg) {
+  if (op->kind == RRTMGPB_1SCL) return ok(errmsg);  // :573-583 nothing to do
+  if (op->kind == RRTMGPB_NSTR) return fail(errmsg, "delta_scale_nstr: Not yet implemented");
+  const size_t n = (size_t)op->ncol * op->nlay * op->ngpt;
+  if (forward) {  // :596-609
+    if (g_check_values && rrtmgpb_any_vals_outside(n, forward, nullptr, 0, 1))
+      return fail(errmsg, "delta_scale: values of 'for' out of bounds [0,1]");
+    rte_delta_scale_2str_f_k(&op->ncol, &op->nlay, &op->ngpt, op->tau, op->ssa, op->g, forward);
+  } else {
+    rte_delta_scale_2str_k(&op->ncol, &op->nlay, &op->ngpt, op->tau, op->ssa, op->g);
+  }
+  return ok(errmsg);
+}
+
+int rrtmgpb_op_increment(const rrtmgpb_optical_props* in, rrtmgpb_optical_props* io, char* errmsg) {
+  // mo_optical_props.F90:879-1028
+  const int ncol = io->ncol, nlay = io->nlay, ngpt = io->ngpt;
+  if (!in->tau) return fail(errmsg, "ty_optical_props%increment: Incrementing optical properties aren't initialized");
+  if (!io->tau)
+    return fail(errmsg, "ty_optical_props%increment: optical properties to be incremented aren't initialized");
+  if (!bands_are_equal(in, io))
+    return fail(errmsg, "ty_optical_props%increment: optical properties objects have different band structures");
+  if (in->ncol != ncol || in->nlay != nlay)
+    return fail(errmsg, "ty_optical_props%increment: optical properties objects have different ncol and/or nlay");
+  if (gpoints_are_equal(in, io)) {
+    switch (io->kind * 10 + in->kind) {
+      case 11: rte_increment_1scalar_by_1scalar(&ncol, &nlay, &ngpt, io->tau, in->tau); break;
+      case 12: rte_increment_1scalar_by_2stream(&ncol, &nlay, &ngpt, io->tau, in->tau, in->ssa); break;
+      case 13: rte_increment_1scalar_by_nstream(&ncol, &nlay, &ngpt, io->tau, in->tau, in->ssa); break;
+      case 21: rte_increment_2stream_by_1scalar(&ncol, &nlay, &ngpt, io->tau, io->ssa, in->tau); break;
+      case 22: rte_increment_2stream_by_2stream(&ncol, &nlay, &ngpt, io->tau, io->ssa, io->g, in->tau, in->ssa, in->g); break;
+      case 23: rte_increment_2stream_by_nstream(&ncol, &nlay, &ngpt, &in->nmom, io->tau, io->ssa, io->g, in->tau, in->ssa, in->p); break;
+      case 31: rte_increment_nstream_by_1scalar(&ncol, &nlay, &ngpt, io->tau, io->ssa, in->tau); break;
+      case 32: rte_increment_nstream_by_2stream(&ncol, &nlay, &ngpt, &io->nmom, io->tau, io->ssa, io->p, in->tau, in->ssa, in->g); break;
+      case 33: rte_increment_nstream_by_nstream(&ncol, &nlay, &ngpt, &io->nmom, &in->nmom, io->tau, io->ssa, io->p, in->tau, in->ssa, in->p); break;
+    }
+  } else {
+    if (in->ngpt != io->nband)
+      return fail(errmsg, "ty_optical_props%increment: optical properties objects have incompatible g-point structures");
+    const int nb = io->nband;
+    int* lims = upload(io->band_lims_gpt, 2 * (size_t)nb);  // kernels read gpt_lims from backend memory
+    switch (io->kind * 10 + in->kind) {
+      case 11: rte_inc_1scalar_by_1scalar_bybnd(&ncol, &nlay, &ngpt, io->tau, in->tau, &nb, lims); break;
+      case 12: rte_inc_1scalar_by_2stream_bybnd(&ncol, &nlay, &ngpt, io->tau, in->tau, in->ssa, &nb, lims); break;
+      case 13: rte_inc_1scalar_by_nstream_bybnd(&ncol, &nlay, &ngpt, io->tau, in->tau, in->ssa, &nb, lims); break;
+      case 21: rte_inc_2stream_by_1scalar_bybnd(&ncol, &nlay, &ngpt, io->tau, io->ssa, in->tau, &nb, lims); break;
+      case 22: rte_inc_2stream_by_2stream_bybnd(&ncol, &nlay, &ngpt, io->tau, io->ssa, io->g, in->tau, in->ssa, in->g, &nb, lims); break;
+      case 23: rte_inc_2stream_by_nstream_bybnd(&ncol, &nlay, &ngpt, &in->nmom, io->tau, io->ssa, io->g, in->tau, in->ssa, in->p, &nb, lims); break;
+      case 31: rte_inc_nstream_by_1scalar_bybnd(&ncol, &nlay, &ngpt, io->tau, io->ssa, in->tau, &nb, lims); break;
+      case 32: rte_inc_nstream_by_2stream_bybnd(&ncol, &nlay, &ngpt, &io->nmom, io->tau, io->ssa, io->p, in->tau, in->ssa, in->g, &nb, lims); break;
+      case 33: rte_inc_nstream_by_nstream_bybnd(&ncol, &nlay, &ngpt, &io->nmom, &in->nmom, io->tau, io->ssa, io->p, in->tau, in->ssa, in->p, &nb, lims); break;
+    }
+    rrtmgpb_mem_free(lims);
+  }
+  return ok(errmsg);
+}
+
+// ------------------------------------------------------------------------------------------------
+// rte_lw
+// ------------------------------------------------------------------------------------------------
+static int rte_lw_impl(const rrtmgpb_optical_props* op, const rrtmgpb_source_func_lw* src, const Float* sfc_emis,
+                       rrtmgpb_fluxes_broadband* fluxes, Float* gpt_up_out, Float* gpt_dn_out, const Float* inc_flux,
+                       int n_gauss_angles, int use_2stream, const Float* lw_Ds, Float* flux_up_Jac, char* errmsg) {
+  const int ncol = op->ncol, nlay = op->nlay, ngpt = op->ngpt, nband = op->nband;
+  const size_t ncg = (size_t)ncol * ngpt, nclp = (size_t)ncol * (nlay + 1);
+  const bool do_broadband = fluxes != nullptr;  // ty_fluxes_broadband is special-cased, mo_rte_lw.F90:296-313
+  const bool do_Jacobians = flux_up_Jac != nullptr;
+  std::string msg;
+  // ---- error checking :170-262
+  if (do_broadband && !(fluxes->flux_up || fluxes->flux_dn || fluxes->flux_net))
+    msg = "rte_lw: no space allocated for fluxes";
+  if (g_check_extents) {
+    if (src->ncol != ncol || src->nlay != nlay || src->ngpt != ngpt)
+      msg = "rte_lw: sources and optical properties inconsistently sized";
+  }
+  if (g_check_values) {
+    if (rrtmgpb_any_vals_outside((size_t)nband * ncol, sfc_emis, nullptr, 0, 1))
+      msg = "rte_lw: sfc_emis has values < 0 or > 1";
+    if (inc_flux && rrtmgpb_any_vals_less_than(ncg, inc_flux, nullptr, 0)) msg = "rte_lw: inc_flux has values < 0";
+    if (lw_Ds && rrtmgpb_any_vals_less_than(ncg, lw_Ds, nullptr, 1)) msg = "rte_lw: one or more values of lw_Ds < 1.";
+    if (n_gauss_angles > max_gauss_pts)
+      msg = "rte_lw: asking for too many quadrature points for no-scattering calculation";
+    if (n_gauss_angles < 0)
+      msg = "rte_lw: have to ask for at least one quadrature point for no-scattering calculation";
+  }
+  if (!msg.empty()) return fail(errmsg, msg);
+  const int n_quad_angs = n_gauss_angles > 0 ? n_gauss_angles : 1;
+  const bool using_2stream = use_2stream > 0;
+  if (op->kind == RRTMGPB_1SCL) {
+    if (using_2stream) msg = "rte_lw: can't use two-stream methods with only absorption optical depth";
+    if (lw_Ds && n_quad_angs != 1) msg = "rte_lw: providing lw_Ds incompatible with specifying n_gauss_angles";
+  } else if (op->kind == RRTMGPB_2STR) {
+    if (lw_Ds) msg = "rte_lw: lw_Ds not valid when providing scattering optical properties";
+    if (using_2stream && n_quad_angs != 1) msg = "rte_lw: using_2stream=true incompatible with specifying n_gauss_angles";
+    if (using_2stream && do_Jacobians)
+      msg = "rte_lw: can't provide Jacobian of fluxes w.r.t surface temperature with 2-stream";
+  } else {
+    msg = "rte_lw: lw_solver(...ty_optical_props_nstr...) not yet implemented";
+  }
+  if (!msg.empty()) return fail(errmsg, msg);
+
+  // ---- boundary conditions :264-282,329
+  Scratch<Float> sfc_emis_gpt(ncg);
+  Scratch<int> lims(2 * (size_t)nband);
+  rrtmgpb_mem_to_backend(lims, op->band_lims_gpt, sizeof(int) * 2 * nband);
+  rrtmgpb_expand_and_transpose(ncol, nband, ngpt, lims, sfc_emis, sfc_emis_gpt);
+  Float* inc_alloc = nullptr;
+  const Float* inc_flux_diffuse = inc_flux;
+  if (!inc_flux) {
+    inc_alloc = static_cast<Float*>(rrtmgpb_mem_alloc(ncg * sizeof(Float)));
+    zero_array_2D(&ncol, &ngpt, inc_alloc);  // :280
+    inc_flux_diffuse = inc_alloc;
+  }
+  // ---- output plumbing :284-322: broadband outputs need both up and down storage
+  Float *up_loc = nullptr, *dn_loc = nullptr, *up_tmp = nullptr, *dn_tmp = nullptr, *decoy2 = nullptr;
+  if (do_broadband) {
+    up_loc = fluxes->flux_up; dn_loc = fluxes->flux_dn;
+    if (!up_loc) up_loc = up_tmp = static_cast<Float*>(rrtmgpb_mem_alloc(nclp * sizeof(Float)));
+    if (!dn_loc) dn_loc = dn_tmp = static_cast<Float*>(rrtmgpb_mem_alloc(nclp * sizeof(Float)));
+  } else {
+    decoy2 = static_cast<Float*>(rrtmgpb_mem_alloc(nclp * sizeof(Float)));
+    up_loc = dn_loc = decoy2;  // :320-321
+  }
+  Float* jacobian = do_Jacobians ? flux_up_Jac : (decoy2 ? decoy2 : up_loc);
+  // g-point flux arrays are decoys in the broadband case (never touched by the kernels)
+  Float* gpt_up = do_broadband ? up_loc : gpt_up_out;
+  Float* gpt_dn = do_broadband ? dn_loc : gpt_dn_out;
+  const Bool top_at_1 = op->top_at_1 != 0, bb = do_broadband, jac = do_Jacobians;
+
+  if (g_check_values) {
+    char verr[RRTMGPB_ERRLEN];
+    if (rrtmgpb_op_validate(op, verr)) msg = verr;
+  }
+  if (msg.empty()) {
+    if (op->kind == RRTMGPB_1SCL || !using_2stream) {
+      // secants :345-365 and the two lw_solver_noscat call sites :367-378, :411-422
+      Scratch<Float> secants(ncg * n_quad_angs);
+      std::vector<Float> wts(n_quad_angs);
+      if (lw_Ds) {
+        rrtmgpb_mem_copy(secants, lw_Ds, ncg * sizeof(Float));
+        wts[0] = (Float)gauss_wts[0][0];
+      } else {
+        for (int imu = 0; imu < n_quad_angs; ++imu) {
+          const Float D = (Float)1 / (Float)gauss_mus[n_quad_angs - 1][imu];
+          set_to_scalar_2D(&ncol, &ngpt, secants + ncg * imu, &D);
+          wts[imu] = (Float)gauss_wts[n_quad_angs - 1][imu];
+        }
+      }
+      Scratch<Float> wts_b(n_quad_angs);
+      rrtmgpb_mem_to_backend(wts_b, wts.data(), sizeof(Float) * n_quad_angs);
+      const Bool resc = op->kind == RRTMGPB_2STR;
+      // the last two arguments are not used when do_rescaling is false but need valid addresses (:378)
+      const Float* ssa = resc ? op->ssa : op->tau;
+      const Float* g = resc ? op->g : op->tau;
+      rte_lw_solver_noscat(&ncol, &nlay, &ngpt, &top_at_1, &n_quad_angs, secants, wts_b, op->tau, src->lay_source,
+                           src->lev_source, sfc_emis_gpt, src->sfc_source, inc_flux_diffuse, gpt_up, gpt_dn, &bb,
+                           up_loc, dn_loc, &jac, src->sfc_source_Jac, jacobian, &resc, ssa, g);
+    } else {
+      // two-stream with scattering :388-394; no broadband outputs exist for this kernel:
+      // with ty_fluxes_broadband the reference leaves flux_up/flux_dn unfilled; we sum the g-point fluxes.
+      Float *gu = gpt_up_out, *gd = gpt_dn_out, *gu_tmp = nullptr, *gd_tmp = nullptr;
+      if (do_broadband) {
+        gu = gu_tmp = static_cast<Float*>(rrtmgpb_mem_alloc(nclp * ngpt * sizeof(Float)));
+        gd = gd_tmp = static_cast<Float*>(rrtmgpb_mem_alloc(nclp * ngpt * sizeof(Float)));
+      }
+      rte_lw_solver_2stream(&ncol, &nlay, &ngpt, &top_at_1, op->tau, op->ssa, op->g, src->lay_source, src->lev_source,
+                            sfc_emis_gpt, src->sfc_source, inc_flux_diffuse, gu, gd);
+      if (do_broadband) {
+        const int nlev = nlay + 1;
+        rte_sum_broadband(&ncol, &nlev, &ngpt, gu, up_loc);
+        rte_sum_broadband(&ncol, &nlev, &ngpt, gd, dn_loc);
+        rrtmgpb_mem_free(gu_tmp);
+        rrtmgpb_mem_free(gd_tmp);
+      }
+    }
+    if (do_broadband && fluxes->flux_net) {  // :439-450
+      const int nlev = nlay + 1;
+      rte_net_broadband_precalc(&ncol, &nlev, dn_loc, up_loc, fluxes->flux_net);
+    }
+  }
+  rrtmgpb_mem_free(inc_alloc);
+  rrtmgpb_mem_free(up_tmp);
+  rrtmgpb_mem_free(dn_tmp);
+  rrtmgpb_mem_free(decoy2);
+  return fail(errmsg, msg);
+}
+
+int rrtmgpb_rte_lw(const rrtmgpb_optical_props* op, const rrtmgpb_source_func_lw* src, const Float* sfc_emis,
+                   rrtmgpb_fluxes_broadband* fluxes, const Float* inc_flux, int n_gauss_angles, int use_2stream,
+                   const Float* lw_Ds, Float* flux_up_Jac, char* errmsg) {
+  if (!fluxes) return fail(errmsg, "rte_lw: no space allocated for fluxes");
+  return rte_lw_impl(op, src, sfc_emis, fluxes, nullptr, nullptr, inc_flux, n_gauss_angles, use_2stream, lw_Ds,
+                     flux_up_Jac, errmsg);
+}
+int rrtmgpb_rte_lw_bygpoint(const rrtmgpb_optical_props* op, const rrtmgpb_source_func_lw* src, const Float* sfc_emis,
+                            Float* gpt_flux_up, Float* gpt_flux_dn, const Float* inc_flux, int n_gauss_angles,
+                            int use_2stream, const Float* lw_Ds, char* errmsg) {
+  if (!gpt_flux_up || !gpt_flux_dn) return fail(errmsg, "rte_lw: no space allocated for fluxes");
+  return rte_lw_impl(op, src, sfc_emis, nullptr, gpt_flux_up, gpt_flux_dn, inc_flux, n_gauss_angles, use_2stream,
+                     lw_Ds, nullptr, errmsg);
+}
+
+// ------------------------------------------------------------------------------------------------
+// rte_sw
+// ------------------------------------------------------------------------------------------------
+static int rte_sw_impl(const rrtmgpb_optical_props* atmos, const Float* mu0, const Float* inc_flux,
+                       const Float* sfc_alb_dir, const Float* sfc_alb_dif, rrtmgpb_fluxes_broadband* fluxes,
+                       Float* gpt_up_out, Float* gpt_dn_out, Float* gpt_dir_out, const Float* inc_flux_dif,
+                       char* errmsg) {
+  const int ncol = atmos->ncol, nlay = atmos->nlay, ngpt = atmos->ngpt, nband = atmos->nband;
+  const size_t ncg = (size_t)ncol * ngpt, nclp = (size_t)ncol * (nlay + 1), ncl = (size_t)ncol * nlay;
+  const bool do_broadband = fluxes != nullptr;
+  const Bool has_dif_bc = inc_flux_dif != nullptr;
+  std::string msg;
+  if (do_broadband && !(fluxes->flux_up || fluxes->flux_dn || fluxes->flux_net || fluxes->flux_dn_dir))
+    msg = "rte_sw: no space allocated for fluxes";
+  if (g_check_values) {  // mo_rte_sw.F90:176-191
+    if (rrtmgpb_any_vals_outside(ncol, mu0, nullptr, -1, 1)) msg = "rte_sw: one or more mu0 < -1 or > 1";
+    if (rrtmgpb_any_vals_less_than(ncg, inc_flux, nullptr, 0)) msg = "rte_sw: one or more inc_flux < 0";
+    if (rrtmgpb_any_vals_outside((size_t)nband * ncol, sfc_alb_dir, nullptr, 0, 1))
+      msg = "rte_sw: sfc_alb_dir out of bounds [0,1]";
+    if (rrtmgpb_any_vals_outside((size_t)nband * ncol, sfc_alb_dif, nullptr, 0, 1))
+      msg = "rte_sw: sfc_alb_dif out of bounds [0,1]";
+    if (has_dif_bc && rrtmgpb_any_vals_less_than(ncg, inc_flux_dif, nullptr, 0))
+      msg = "rte_sw: one or more inc_flux_dif < 0";
+  }
+  if (!msg.empty()) return fail(errmsg, msg);
+
+  // mu0 is constant with height: mo_rte_sw.F90:87-93
+  Scratch<Float> mu0_bylay(ncl);
+  rrtmgpb_broadcast_by_lay(ncol, nlay, mu0, mu0_bylay);
+  // output plumbing :197-240.  In the broadband case the three g-point flux arguments are decoys; the
+  // reference points all three at ONE buffer (:204-207).  We pass one small decoy: the kernels never touch it.
+  Float *up_loc, *dn_loc, *dir_loc, *up_tmp = nullptr, *dn_tmp = nullptr, *dir_tmp = nullptr, *decoy = nullptr;
+  Float *gpt_up = gpt_up_out, *gpt_dn = gpt_dn_out, *gpt_dir = gpt_dir_out;
+  if (do_broadband) {
+    up_loc = fluxes->flux_up; dn_loc = fluxes->flux_dn; dir_loc = fluxes->flux_dn_dir;
+    if (!up_loc) up_loc = up_tmp = static_cast<Float*>(rrtmgpb_mem_alloc(nclp * sizeof(Float)));
+    if (!dn_loc) dn_loc = dn_tmp = static_cast<Float*>(rrtmgpb_mem_alloc(nclp * sizeof(Float)));
+    if (!dir_loc) dir_loc = dir_tmp = static_cast<Float*>(rrtmgpb_mem_alloc(nclp * sizeof(Float)));
+    decoy = static_cast<Float*>(rrtmgpb_mem_alloc(nclp * sizeof(Float)));
+    gpt_up = gpt_dn = gpt_dir = decoy;
+  } else {
+    decoy = static_cast<Float*>(rrtmgpb_mem_alloc(nclp * sizeof(Float)));
+    up_loc = dn_loc = dir_loc = decoy;  // :235-238
+  }
+  Scratch<Float> alb_dir_gpt(ncg), alb_dif_gpt(ncg);
+  Scratch<int> lims(2 * (size_t)nband);
+  rrtmgpb_mem_to_backend(lims, atmos->band_lims_gpt, sizeof(int) * 2 * nband);
+  rrtmgpb_expand_and_transpose(ncol, nband, ngpt, lims, sfc_alb_dir, alb_dir_gpt);  // :266-267
+  rrtmgpb_expand_and_transpose(ncol, nband, ngpt, lims, sfc_alb_dif, alb_dif_gpt);
+  Float* dif_alloc = nullptr;
+  const Float* inc_flux_diffuse = inc_flux_dif;
+  if (!has_dif_bc) {
+    dif_alloc = static_cast<Float*>(rrtmgpb_mem_alloc(ncg * sizeof(Float)));
+    zero_array_2D(&ncol, &ngpt, dif_alloc);  // :279
+    inc_flux_diffuse = dif_alloc;
+  }
+  if (g_check_values) {
+    char verr[RRTMGPB_ERRLEN];
+    if (rrtmgpb_op_validate(atmos, verr)) msg = verr;
+  }
+  const Bool top_at_1 = atmos->top_at_1 != 0, bb = do_broadband;
+  if (msg.empty()) {
+    if (atmos->kind == RRTMGPB_1SCL) {  // :286-311 direct beam only
+      if (do_broadband) {
+        msg = "rte_sw: broadband fluxes from 1scl optical properties are not supported by this frontend";
+      } else {
+        const int nlev = nlay + 1;
+        rte_sw_solver_noscat(&ncol, &nlay, &ngpt, &top_at_1, atmos->tau, mu0_bylay, inc_flux, gpt_dir);
+        zero_array_3D(&ncol, &nlev, &ngpt, gpt_up);
+        rrtmgpb_mem_copy(gpt_dn, gpt_dir, nclp * ngpt * sizeof(Float));
+      }
+    } else if (atmos->kind == RRTMGPB_2STR) {  // :313-326
+      rte_sw_solver_2stream(&ncol, &nlay, &ngpt, &top_at_1, atmos->tau, atmos->ssa, atmos->g, mu0_bylay, alb_dir_gpt,
+                            alb_dif_gpt, inc_flux, gpt_up, gpt_dn, gpt_dir, &has_dif_bc, inc_flux_diffuse, &bb,
+                            up_loc, dn_loc, dir_loc);
+    } else {
+      msg = "sw_solver(...ty_optical_props_nstr...) not yet implemented";
+    }
+    if (msg.empty() && do_broadband && fluxes->flux_net) {  // :346-355
+      const int nlev = nlay + 1;
+      rte_net_broadband_precalc(&ncol, &nlev, dn_loc, up_loc, fluxes->flux_net);
+    }
+  }
+  rrtmgpb_mem_free(dif_alloc);
+  rrtmgpb_mem_free(up_tmp);
+  rrtmgpb_mem_free(dn_tmp);
+  rrtmgpb_mem_free(dir_tmp);
+  rrtmgpb_mem_free(decoy);
+  return fail(errmsg, msg);
+}
+
+int rrtmgpb_rte_sw(const rrtmgpb_optical_props* atmos, const Float* mu0, const Float* inc_flux,
+                   const Float* sfc_alb_dir, const Float* sfc_alb_dif, rrtmgpb_fluxes_broadband* fluxes,
+                   const Float* inc_flux_dif, char* errmsg) {
+  if (!fluxes) return fail(errmsg, "rte_sw: no space allocated for fluxes");
+  return rte_sw_impl(atmos, mu0, inc_flux, sfc_alb_dir, sfc_alb_dif, fluxes, nullptr, nullptr, nullptr, inc_flux_dif,
+                     errmsg);
+}
+int rrtmgpb_rte_sw_bygpoint(const rrtmgpb_optical_props* atmos, const Float* mu0, const Float* inc_flux,
+                            const Float* sfc_alb_dir, const Float* sfc_alb_dif, Float* gpt_flux_up,
+                            Float* gpt_flux_dn, Float* gpt_flux_dir, const Float* inc_flux_dif, char* errmsg) {
+  if (!gpt_flux_up || !gpt_flux_dn || !gpt_flux_dir) return fail(errmsg, "rte_sw: no space allocated for fluxes");
+  return rte_sw_impl(atmos, mu0, inc_flux, sfc_alb_dir, sfc_alb_dif, nullptr, gpt_flux_up, gpt_flux_dn, gpt_flux_dir,
+                     inc_flux_dif, errmsg);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ty_gas_optics_rrtmgp
+// ------------------------------------------------------------------------------------------------
+struct rrtmgpb_gas_optics_t {
+  rrtmgpb_kdist h;  // scalars + HOST copies of the small index tables
+  std::vector<int> band_lims_gpt_h;
+  std::vector<Float> band_lims_wvn_h;
+  // backend copies
+  int *flavor, *gpoint_flavor, *band_lims_gpt, *gpoint_bands;
+  Float *press_ref_log, *temp_ref, *vmr_ref, *kmajor, *kminor_lower, *kminor_upper;
+  int *mlg_l, *mlg_u, *im_l, *im_u, *is_l, *is_u, *ks_l, *ks_u;
+  Bool *sd_l, *sd_u, *sc_l, *sc_u;
+  Float *planck_frac, *totplnk, *krayl, *solar_source;
+};
+
+rrtmgpb_gas_optics_t* rrtmgpb_gas_optics_load(const rrtmgpb_kdist* t, char* errmsg) {
+  if (!t || !t->kmajor) { fail(errmsg, "ERROR: spectral configuration not loaded"); return nullptr; }
+  if ((t->totplnk != nullptr) == (t->solar_source != nullptr)) {
+    fail(errmsg, "gas_optics%load: provide either the Planck tables (LW) or the solar source (SW)");
+    return nullptr;
+  }
+  rrtmgpb_gas_optics_t* go = new rrtmgpb_gas_optics_t();
+  go->h = *t;
+  go->band_lims_gpt_h.assign(t->band_lims_gpt, t->band_lims_gpt + 2 * t->nbnd);
+  if (t->band_lims_wvn) go->band_lims_wvn_h.assign(t->band_lims_wvn, t->band_lims_wvn + 2 * t->nbnd);
+  const size_t tn = (size_t)t->ntemp * t->neta, nl = (size_t)(t->nminorlower > 0 ? t->nminorlower : 1),
+               nu = (size_t)(t->nminorupper > 0 ? t->nminorupper : 1);
+  go->flavor = upload(t->flavor, 2 * (size_t)t->nflav);
+  go->gpoint_flavor = upload(t->gpoint_flavor, 2 * (size_t)t->ngpt);
+  go->band_lims_gpt = upload(t->band_lims_gpt, 2 * (size_t)t->nbnd);
+  go->gpoint_bands = upload(t->gpoint_bands, (size_t)t->ngpt);
+  go->press_ref_log = upload(t->press_ref_log, (size_t)t->npres);
+  go->temp_ref = upload(t->temp_ref, (size_t)t->ntemp);
+  go->vmr_ref = upload(t->vmr_ref, 2 * (size_t)(t->ngas + 1) * t->ntemp);
+  go->kmajor = upload(t->kmajor, tn * (t->npres + 1) * t->ngpt);
+  go->kminor_lower = upload(t->kminor_lower, tn * (t->nminorklower > 0 ? t->nminorklower : 1));
+  go->kminor_upper = upload(t->kminor_upper, tn * (t->nminorkupper > 0 ? t->nminorkupper : 1));
+  go->mlg_l = upload(t->minor_limits_gpt_lower, 2 * nl);
+  go->mlg_u = upload(t->minor_limits_gpt_upper, 2 * nu);
+  go->sd_l = upload(t->minor_scales_with_density_lower, nl);
+  go->sd_u = upload(t->minor_scales_with_density_upper, nu);
+  go->sc_l = upload(t->scale_by_complement_lower, nl);
+  go->sc_u = upload(t->scale_by_complement_upper, nu);
+  go->im_l = upload(t->idx_minor_lower, nl);
+  go->im_u = upload(t->idx_minor_upper, nu);
+  go->is_l = upload(t->idx_minor_scaling_lower, nl);
+  go->is_u = upload(t->idx_minor_scaling_upper, nu);
+  go->ks_l = upload(t->kminor_start_lower, nl);
+  go->ks_u = upload(t->kminor_start_upper, nu);
+  go->planck_frac = upload(t->planck_frac, t->planck_frac ? tn * (t->npres + 1) * t->ngpt : 0);
+  go->totplnk = upload(t->totplnk, t->totplnk ? (size_t)t->nPlanckTemp * t->nbnd : 0);
+  go->krayl = upload(t->krayl, t->krayl ? tn * t->ngpt * 2 : 0);
+  go->solar_source = upload(t->solar_source, t->solar_source ? (size_t)t->ngpt : 0);
+  rrtmgpb_sync();  // host tables may be released by the caller after load() returns
+  ok(errmsg);
+  return go;
+}
+
+void rrtmgpb_gas_optics_free(rrtmgpb_gas_optics_t* go) {
+  if (!go) return;
+  void* ptrs[] = {go->flavor, go->gpoint_flavor, go->band_lims_gpt, go->gpoint_bands, go->press_ref_log, go->temp_ref,
+                  go->vmr_ref, go->kmajor, go->kminor_lower, go->kminor_upper, go->mlg_l, go->mlg_u, go->im_l, go->im_u,
+                  go->is_l, go->is_u, go->ks_l, go->ks_u, go->sd_l, go->sd_u, go->sc_l, go->sc_u, go->planck_frac,
+                  go->totplnk, go->krayl, go->solar_source};
+  for (void* p : ptrs) rrtmgpb_mem_free(p);
+  delete go;
+}
+
+int rrtmgpb_gas_optics_source_is_internal(const rrtmgpb_gas_optics_t* go) { return go->totplnk != nullptr; }
+
+// Interpolation intermediates shared by compute_gas_taus and source (frontend locals in the reference,
+// mo_gas_optics_rrtmgp.F90:244-247,455-459)
+struct InterpScratch {
+  Scratch<int> jtemp, jpress, jeta;
+  Scratch<Bool> tropo;
+  Scratch<Float> fmajor, fminor, col_mix, col_gas;
+  InterpScratch(size_t ncl, int nflav, int ngas)
+      : jtemp(ncl), jpress(ncl), jeta(2 * ncl * nflav), tropo(ncl), fmajor(8 * ncl * nflav), fminor(4 * ncl * nflav),
+        col_mix(2 * ncl * nflav), col_gas(ncl * (ngas + 1)) {}
+};
+
+// compute_gas_taus, mo_gas_optics_rrtmgp.F90:419-745
+static int compute_gas_taus(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play, const Float* plev,
+                            const Float* tlay, const Float* vmr, rrtmgpb_optical_props* op, InterpScratch& s,
+                            const Float* col_dry, char* errmsg) {
+  const rrtmgpb_kdist& k = go->h;
+  const int ngpt = k.ngpt, nband = k.nbnd, ngas = k.ngas, nflav = k.nflav;
+  const size_t ncl = (size_t)ncol * nlay;
+  std::string msg;
+  if (g_check_extents) {  // :491-507
+    if (op->ncol != ncol || op->nlay != nlay || op->ngpt != ngpt)
+      msg = "gas_optics(): optical properties have the wrong extents";
+  }
+  if (msg.empty() && g_check_values) {  // :509-521
+    if (rrtmgpb_any_vals_outside(ncl, play, nullptr, k.press_ref_min, k.press_ref_max))
+      msg = "gas_optics(): array play has values outside range";
+    if (rrtmgpb_any_vals_less_than(ncl + ncol, plev, nullptr, 0)) msg = "gas_optics(): array plev has values outside range";
+    if (rrtmgpb_any_vals_outside(ncl, tlay, nullptr, k.temp_ref_min, k.temp_ref_max))
+      msg = "gas_optics(): array tlay has values outside range";
+    if (col_dry && rrtmgpb_any_vals_less_than(ncl, col_dry, nullptr, 0))
+      msg = "gas_optics(): array col_dry has values outside range";
+  }
+  if (!msg.empty()) return fail(errmsg, msg);
+
+  // dry-air column amounts :578-590 and column gas amounts :594-609
+  Float* col_dry_alloc = nullptr;
+  const Float* col_dry_wk = col_dry;
+  if (!col_dry) {
+    col_dry_alloc = static_cast<Float*>(rrtmgpb_mem_alloc(ncl * sizeof(Float)));
+    rrtmgpb_get_col_dry(ncol, nlay, vmr + ncl * (size_t)(k.idx_h2o - 1), plev, col_dry_alloc);
+    col_dry_wk = col_dry_alloc;
+  }
+  rrtmgpb_col_gas_from_vmr(ncol, nlay, ngas, vmr, col_dry_wk, s.col_gas);
+  // :615-633
+  rrtmgp_interpolation(&ncol, &nlay, &ngas, &nflav, &k.neta, &k.npres, &k.ntemp, go->flavor, go->press_ref_log,
+                       go->temp_ref, &k.press_ref_log_delta, &k.temp_ref_min, &k.temp_ref_delta,
+                       &k.press_ref_trop_log, go->vmr_ref, play, tlay, s.col_gas, s.jtemp, s.fmajor, s.fminor,
+                       s.col_mix, s.tropo, s.jeta, s.jpress);
+  auto tau_abs = [&](Float* tau) {  // :637-665 / :679-706 (zero_array + accumulate == assign)
+    rrtmgpb_compute_tau_absorption_assign(
+        ncol, nlay, nband, ngpt, ngas, nflav, k.neta, k.npres, k.ntemp, k.nminorlower, k.nminorklower, k.nminorupper,
+        k.nminorkupper, k.idx_h2o, go->gpoint_flavor, go->band_lims_gpt, go->kmajor, go->kminor_lower, go->kminor_upper,
+        go->mlg_l, go->mlg_u, go->sd_l, go->sd_u, go->sc_l, go->sc_u, go->im_l, go->im_u, go->is_l, go->is_u, go->ks_l,
+        go->ks_u, s.tropo, s.col_mix, s.fmajor, s.fminor, play, tlay, s.col_gas, s.jeta, s.jtemp, s.jpress, tau);
+  };
+  if (go->krayl) {  // :634-677
+    Scratch<Float> tau_rayleigh(ncl * ngpt);
+    tau_abs(op->tau);  // absorption lands in op->tau, combined in place below
+    rrtmgp_compute_tau_rayleigh(&ncol, &nlay, &nband, &ngpt, &ngas, &nflav, &k.neta, &k.npres, &k.ntemp,
+                                go->gpoint_flavor, go->band_lims_gpt, go->krayl, &k.idx_h2o, col_dry_wk, s.col_gas,
+                                s.fminor, s.jeta, s.tropo, s.jtemp, tau_rayleigh);
+    if (op->kind == RRTMGPB_NSTR) {
+      rrtmgpb_mem_free(col_dry_alloc);
+      return fail(errmsg, "gas_optics(): n-stream optical properties are not supported by this frontend");
+    }
+    rrtmgpb_combine_abs_and_rayleigh(ncol, nlay, ngpt, op->kind, op->tau, tau_rayleigh, op->tau, op->ssa, op->g);
+  } else {
+    tau_abs(op->tau);
+    if (op->kind == RRTMGPB_2STR) {  // :708-710
+      zero_array_3D(&ncol, &nlay, &ngpt, op->ssa);
+      zero_array_3D(&ncol, &nlay, &ngpt, op->g);
+    } else if (op->kind == RRTMGPB_NSTR) {
+      zero_array_3D(&ncol, &nlay, &ngpt, op->ssa);
+      zero_array_4D(&op->nmom, &ncol, &nlay, &ngpt, op->p);
+    }
+  }
+  rrtmgpb_mem_free(col_dry_alloc);
+  return ok(errmsg);
+}
+
+static int set_top_at_1(rrtmgpb_optical_props* op, const Float* play, int ncol, int nlay) {
+  // mo_gas_optics_rrtmgp.F90:258: top_at_1 = play(1,1) < play(1,nlay) - needs two values on the host
+  Float a = 0, b = 0;
+  rrtmgpb_mem_to_host(&a, play, sizeof(Float));
+  rrtmgpb_mem_to_host(&b, play + (size_t)ncol * (nlay - 1), sizeof(Float));
+  op->top_at_1 = a < b;
+  return op->top_at_1;
+}
+
+int rrtmgpb_gas_optics_int(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play, const Float* plev,
+                           const Float* tlay, const Float* tsfc, const Float* vmr, rrtmgpb_optical_props* op,
+                           rrtmgpb_source_func_lw* sources, const Float* col_dry, const Float* tlev, char* errmsg) {
+  const rrtmgpb_kdist& k = go->h;
+  if (!go->totplnk) return fail(errmsg, "gas_optics(): no internal (Planck) source tables loaded");
+  const int ngpt = k.ngpt, nband = k.nbnd;
+  const size_t ncl = (size_t)ncol * nlay;
+  set_top_at_1(op, play, ncol, nlay);
+  InterpScratch s(ncl, k.nflav, k.ngas);
+  if (compute_gas_taus(go, ncol, nlay, play, plev, tlay, vmr, op, s, col_dry, errmsg)) return 1;
+  std::string msg;
+  if (g_check_extents) {  // :285-291
+    if (sources->ncol != ncol || sources->nlay != nlay || sources->ngpt != ngpt)
+      msg = "gas_optics%gas_optics: source function arrays inconsistently sized";
+  }
+  if (msg.empty() && g_check_values) {  // :294-301
+    if (rrtmgpb_any_vals_outside(ncol, tsfc, nullptr, k.temp_ref_min, k.temp_ref_max))
+      msg = "gas_optics(): array tsfc has values outside range";
+    if (tlev && rrtmgpb_any_vals_outside(ncl + ncol, tlev, nullptr, k.temp_ref_min, k.temp_ref_max))
+      msg = "gas_optics(): array tlev has values outside range";
+  }
+  if (!msg.empty()) return fail(errmsg, msg);
+  // source(), :840-928
+  Float* tlev_alloc = nullptr;
+  const Float* tlev_wk = tlev;
+  if (!tlev) {
+    tlev_alloc = static_cast<Float*>(rrtmgpb_mem_alloc((ncl + ncol) * sizeof(Float)));
+    rrtmgpb_interpolate_tlev(ncol, nlay, play, plev, tlay, tlev_alloc);
+    tlev_wk = tlev_alloc;
+  }
+  const int sfc_lay = op->top_at_1 ? nlay : 1;  // :920 merge(nlay, 1, top_at_1)
+  rrtmgp_compute_Planck_source(&ncol, &nlay, &nband, &ngpt, &k.nflav, &k.neta, &k.npres, &k.ntemp, &k.nPlanckTemp, tlay,
+                               tlev_wk, tsfc, &sfc_lay, s.fmajor, s.jeta, s.tropo, s.jtemp, s.jpress, go->gpoint_bands,
+                               go->band_lims_gpt, go->planck_frac, &k.temp_ref_min, &k.totplnk_delta, go->totplnk,
+                               go->gpoint_flavor, sources->sfc_source, sources->lay_source, sources->lev_source,
+                               sources->sfc_source_Jac);
+  rrtmgpb_mem_free(tlev_alloc);
+  return ok(errmsg);
+}
+
+int rrtmgpb_gas_optics_ext(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play, const Float* plev,
+                           const Float* tlay, const Float* vmr, rrtmgpb_optical_props* op, Float* toa_src,
+                           const Float* col_dry, char* errmsg) {
+  const rrtmgpb_kdist& k = go->h;
+  if (!go->solar_source) return fail(errmsg, "gas_optics(): no external (solar) source loaded");
+  const size_t ncl = (size_t)ncol * nlay;
+  set_top_at_1(op, play, ncol, nlay);
+  InterpScratch s(ncl, k.nflav, k.ngas);
+  if (compute_gas_taus(go, ncol, nlay, play, plev, tlay, vmr, op, s, col_dry, errmsg)) return 1;
+  rrtmgpb_broadcast_by_gpt(ncol, k.ngpt, go->solar_source, toa_src);  // :405-411
+  return ok(errmsg);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ty_cloud_optics_rrtmgp (LUT)
+// ------------------------------------------------------------------------------------------------
+struct rrtmgpb_cloud_optics_t {
+  rrtmgpb_cloud_lut h;
+  std::vector<Float> band_lims_wvn_h;
+  int liq_nsteps, ice_nsteps;
+  Float liq_step_size, ice_step_size;
+  Float *extliq, *ssaliq, *asyliq, *extice, *ssaice, *asyice;  // ice: the icergh slice only
+};
+
+rrtmgpb_cloud_optics_t* rrtmgpb_cloud_optics_load(const rrtmgpb_cloud_lut* lut, char* errmsg) {
+  if (!lut || !lut->extliq) { fail(errmsg, "cloud optics: no data has been initialized"); return nullptr; }
+  if (lut->icergh < 1 || lut->icergh > lut->nrghice) {  // set_ice_roughness
+    fail(errmsg, "cloud_optics%set_ice_roughness(): must be > 0");
+    return nullptr;
+  }
+  rrtmgpb_cloud_optics_t* co = new rrtmgpb_cloud_optics_t();
+  co->h = *lut;
+  if (lut->band_lims_wvn) co->band_lims_wvn_h.assign(lut->band_lims_wvn, lut->band_lims_wvn + 2 * lut->nbnd);
+  // mo_cloud_optics_rrtmgp.F90:130-133
+  co->liq_nsteps = lut->nsize_liq;
+  co->ice_nsteps = lut->nsize_ice;
+  co->liq_step_size = (lut->radliq_upr - lut->radliq_lwr) / (Float)(lut->nsize_liq - 1);
+  co->ice_step_size = (lut->diamice_upr - lut->diamice_lwr) / (Float)(lut->nsize_ice - 1);
+  const size_t nl = (size_t)lut->nsize_liq * lut->nbnd, ni = (size_t)lut->nsize_ice * lut->nbnd;
+  co->extliq = upload(lut->extliq, nl);
+  co->ssaliq = upload(lut->ssaliq, nl);
+  co->asyliq = upload(lut->asyliq, nl);
+  const size_t off = ni * (size_t)(lut->icergh - 1);  // this%extice(:,:,this%icergh), :380-385
+  co->extice = upload(lut->extice + off, ni);
+  co->ssaice = upload(lut->ssaice + off, ni);
+  co->asyice = upload(lut->asyice + off, ni);
+  rrtmgpb_sync();
+  ok(errmsg);
+  return co;
+}
+
+void rrtmgpb_cloud_optics_free(rrtmgpb_cloud_optics_t* co) {
+  if (!co) return;
+  void* ptrs[] = {co->extliq, co->ssaliq, co->asyliq, co->extice, co->ssaice, co->asyice};
+  for (void* p : ptrs) rrtmgpb_mem_free(p);
+  delete co;
+}
+
+int rrtmgpb_cloud_optics(const rrtmgpb_cloud_optics_t* co, int ncol, int nlay, const Float* clwp, const Float* ciwp,
+                         const Float* reliq, const Float* dgice, rrtmgpb_optical_props* op, char* errmsg) {
+  const rrtmgpb_cloud_lut& h = co->h;
+  const int ngpt = h.nbnd;  // by-band tables: ngpt == nbnd
+  const size_t ncl = (size_t)ncol * nlay, n = ncl * ngpt;
+  std::string msg;
+  if (g_check_extents) {  // :299-313
+    if (op->ncol != ncol || op->nlay != nlay) msg = "cloud optics: optical_props have wrong extents";
+  }
+  if (msg.empty() && g_check_values) {  // :318-322
+    if (op->nband != h.nbnd || op->ngpt != ngpt)
+      msg = "cloud optics: optical properties don't have the same band structure";
+  }
+  if (!msg.empty()) return fail(errmsg, msg);
+  Scratch<Bool> liqmsk(ncl), icemsk(ncl);
+  rrtmgpb_cloud_masks(ncol, nlay, clwp, ciwp, liqmsk, icemsk);  // :334-341
+  if (g_check_values) {  // :346-353
+    if (rrtmgpb_any_vals_outside(ncl, reliq, liqmsk, h.radliq_lwr, h.radliq_upr))
+      msg = "cloud optics: liquid effective radius is out of bounds";
+    if (rrtmgpb_any_vals_outside(ncl, dgice, icemsk, h.diamice_lwr, h.diamice_upr))
+      msg = "cloud optics: ice effective diameter is out of bounds";
+    if (rrtmgpb_any_vals_less_than(ncl, clwp, liqmsk, 0) || rrtmgpb_any_vals_less_than(ncl, ciwp, icemsk, 0))
+      msg = "cloud optics: negative clwp or ciwp where clouds are supposed to be";
+  }
+  if (!msg.empty()) return fail(errmsg, msg);
+  if (op->kind == RRTMGPB_NSTR) return fail(errmsg, "cloud optics: n-stream calculations not yet supported");
+  Scratch<Float> ltau(n), ltaussa(n), ltaussag(n), itau(n), itaussa(n), itaussag(n);
+  rrtmgp_compute_cld_from_table(&ncol, &nlay, &ngpt, liqmsk, clwp, reliq, &co->liq_nsteps, &co->liq_step_size,
+                                &h.radliq_lwr, co->extliq, co->ssaliq, co->asyliq, ltau, ltaussa, ltaussag);  // :373
+  rrtmgp_compute_cld_from_table(&ncol, &nlay, &ngpt, icemsk, ciwp, dgice, &co->ice_nsteps, &co->ice_step_size,
+                                &h.diamice_lwr, co->extice, co->ssaice, co->asyice, itau, itaussa, itaussag);  // :380
+  rrtmgpb_cloud_combine(ncol, nlay, ngpt, op->kind, ltau, ltaussa, ltaussag, itau, itaussa, itaussag, op->tau, op->ssa,
+                        op->g);  // :399-424
+  return ok(errmsg);
+}
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+// runtime.cu - backend plumbing of the CUDA library (include/rrtmgp_b200_ext.h, first section)
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <map>
+#include <string>
+#include <vector>
+#include <cstring>
+#include "common.cuh"
+#include "rrtmgp_b200_ext.h"
+
+namespace rrtmgpb {
+
+thread_local const char* tl_op_name = nullptr;
+static cudaStream_t g_stream = nullptr;  // legacy default stream until the host sets one
+static std::atomic<long long> g_launches{0};
+
+cudaStream_t stream() { return g_stream; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static std::once_flag g_pool_once;
+static void init_pool() {
+  // keep freed scratch in the pool instead of returning it to the driver after every sync
+  int dev = 0;
+  RB_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaMemPool_t pool;
+  RB_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+  unsigned long long thresh = ~0ull;
+  RB_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+}
+
+void* dev_alloc(size_t bytes) {
+  std::call_once(g_pool_once, init_pool);
+  void* p = nullptr;
+  RB_CUDA_CHECK(cudaMallocAsync(&p, bytes ? bytes : 16, stream()));
+  return p;
+}
+void dev_free(void* p) {
+  if (p) RB_CUDA_CHECK(cudaFreeAsync(p, stream()));
+}
+
+// ---- per-kernel event timing -----------------------------------------------------------------
+struct TimerRec { const char* name; cudaEvent_t a, b; };
+static bool g_profile = false;
+static std::vector<TimerRec> g_recs;
+static std::vector<cudaEvent_t> g_free_events;
+static cudaEvent_t get_event() {
+  if (!g_free_events.empty()) { cudaEvent_t e = g_free_events.back(); g_free_events.pop_back(); return e; }
+  cudaEvent_t e; RB_CUDA_CHECK(cudaEventCreate(&e)); return e;
+}
+KernelTimer::KernelTimer(const char* name) : slot(-1) {
+  if (!g_profile) return;
+  TimerRec r{name, get_event(), get_event()};
+  RB_CUDA_CHECK(cudaEventRecord(r.a, stream()));
+  g_recs.push_back(r);
+  slot = (int)g_recs.size() - 1;
+}
+KernelTimer::~KernelTimer() {
+  if (slot >= 0) RB_CUDA_CHECK(cudaEventRecord(g_recs[slot].b, stream()));
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace rrtmgpb
+
+using namespace rrtmgpb;
+
+extern "C" {
+const char* rrtmgpb_backend_name(void) { return "cuda-sm_100a"; }
+void* rrtmgpb_mem_alloc(size_t bytes) { return dev_alloc(bytes); }
+void rrtmgpb_mem_free(void* p) { dev_free(p); }
+void rrtmgpb_mem_to_backend(void* d, const void* s, size_t n) {
+  RB_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream()));
+}
+void rrtmgpb_mem_to_host(void* d, const void* s, size_t n) {
+  RB_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream()));
+  RB_CUDA_CHECK(cudaStreamSynchronize(stream()));
+}
+void rrtmgpb_mem_copy(void* d, const void* s, size_t n) {
+  RB_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, stream()));
+}
+void rrtmgpb_set_stream(void* s) { g_stream = static_cast<cudaStream_t>(s); }
+void* rrtmgpb_get_stream(void) { return g_stream; }
+void rrtmgpb_set_device(int d) { RB_CUDA_CHECK(cudaSetDevice(d)); }
+void rrtmgpb_sync(void) { RB_CUDA_CHECK(cudaStreamSynchronize(stream())); }
+void rrtmgpb_profile_enable(int on) { g_profile = on != 0; }
+// Writes "name count total_ms\n" per kernel (sorted by time) into buf; clears the records.
+int rrtmgpb_profile_report(char* buf, size_t buflen) {
+  RB_CUDA_CHECK(cudaStreamSynchronize(stream()));
+  std::map<std::string, std::pair<int, double>> agg;
+  for (auto& r : g_recs) {
+    float ms = 0;
+    RB_CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
+    auto& e = agg[r.name];
+    e.first += 1; e.second += ms;
+    g_free_events.push_back(r.a); g_free_events.push_back(r.b);
+  }
+  g_recs.clear();
+  std::vector<std::pair<double, std::string>> order;
+  for (auto& kv : agg) order.push_back({-kv.second.second, kv.first});
+  std::sort(order.begin(), order.end());
+  std::string out;
+  for (auto& o : order) {
+    char line[256];
+    std::snprintf(line, sizeof line, "%s %d %.6f\n", o.second.c_str(), agg[o.second].first, agg[o.second].second);
+    out += line;
+  }
+  if (buf && buflen) { std::strncpy(buf, out.c_str(), buflen - 1); buf[buflen - 1] = 0; }
+  return (int)order.size();
+}
+long long rrtmgpb_launch_count(int reset) {
+  long long v = g_launches.load();
+  if (reset) g_launches.store(0);
+  return v;
+}
+}

@@ -1,0 +1,320 @@
+"""Python view of the C frontend (include/rrtmgp_b200_frontend.h): thin ctypes wrappers so tests and the
+benchmark read like the reference's Fortran programs (ty_optical_props_*, ty_source_func_lw,
+ty_fluxes_broadband, ty_gas_optics_rrtmgp, ty_cloud_optics_rrtmgp, rte_lw, rte_sw).
+
+All numerics live behind the C ABI; this module only owns memory (numpy on the host backend, torch on
+CUDA) and marshals pointers.  Every call raises RuntimeError with the reference's error string when the
+C frontend reports one (the Fortran functions return that string; empty = success).
+"""
+import ctypes as C
+
+import numpy as np
+
+from .abi import FLOAT, fzeros, to_device, to_host, _ptr
+
+ERRLEN = 128
+K1SCL, K2STR, KNSTR = 1, 2, 3
+PF = C.POINTER(FLOAT)
+
+
+class _OpStruct(C.Structure):
+    _fields_ = [("kind", C.c_int), ("ncol", C.c_int), ("nlay", C.c_int), ("ngpt", C.c_int), ("nband", C.c_int),
+                ("nmom", C.c_int), ("top_at_1", C.c_int), ("band_lims_gpt", C.c_void_p),
+                ("band_lims_wvn", C.c_void_p), ("tau", C.c_void_p), ("ssa", C.c_void_p), ("g", C.c_void_p),
+                ("p", C.c_void_p)]
+
+
+class _SrcStruct(C.Structure):
+    _fields_ = [("ncol", C.c_int), ("nlay", C.c_int), ("ngpt", C.c_int), ("lay_source", C.c_void_p),
+                ("lev_source", C.c_void_p), ("sfc_source", C.c_void_p), ("sfc_source_Jac", C.c_void_p)]
+
+
+class _FluxStruct(C.Structure):
+    _fields_ = [("flux_up", C.c_void_p), ("flux_dn", C.c_void_p), ("flux_net", C.c_void_p),
+                ("flux_dn_dir", C.c_void_p)]
+
+
+class _KDistStruct(C.Structure):
+    _fields_ = (
+        [(n, C.c_int) for n in ("ngas", "nflav", "neta", "npres", "ntemp", "nbnd", "ngpt", "nminorlower",
+                                "nminorklower", "nminorupper", "nminorkupper", "idx_h2o")]
+        + [(n, C.c_void_p) for n in ("flavor", "gpoint_flavor", "band_lims_gpt", "gpoint_bands", "band_lims_wvn",
+                                     "press_ref_log", "temp_ref", "vmr_ref")]
+        + [(n, FLOAT) for n in ("press_ref_log_delta", "temp_ref_min", "temp_ref_max", "temp_ref_delta",
+                                "press_ref_min", "press_ref_max", "press_ref_trop_log")]
+        + [(n, C.c_void_p) for n in ("kmajor", "kminor_lower", "kminor_upper", "minor_limits_gpt_lower",
+                                     "minor_limits_gpt_upper", "minor_scales_with_density_lower",
+                                     "minor_scales_with_density_upper", "scale_by_complement_lower",
+                                     "scale_by_complement_upper", "idx_minor_lower", "idx_minor_upper",
+                                     "idx_minor_scaling_lower", "idx_minor_scaling_upper", "kminor_start_lower",
+                                     "kminor_start_upper", "planck_frac", "totplnk")]
+        + [("nPlanckTemp", C.c_int), ("totplnk_delta", FLOAT), ("krayl", C.c_void_p), ("solar_source", C.c_void_p)]
+    )
+
+
+class _CloudLutStruct(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("nbnd", "nsize_liq", "nsize_ice", "nrghice", "icergh")]
+                + [("band_lims_gpt", C.c_void_p), ("band_lims_wvn", C.c_void_p)]
+                + [(n, FLOAT) for n in ("radliq_lwr", "radliq_upr", "diamice_lwr", "diamice_upr")]
+                + [(n, C.c_void_p) for n in ("extliq", "ssaliq", "asyliq", "extice", "ssaice", "asyice")])
+
+
+def _addr(x):
+    return None if x is None else _ptr(x).value
+
+
+def _check(rc, err):
+    if rc:
+        raise RuntimeError(err.value.decode())
+
+
+class Context:
+    """A kernel library + the memory space its arrays live in (device=None: host numpy)."""
+
+    def __init__(self, lib, device=None):
+        self.lib, self.device, self.c = lib, device, lib.cdll
+        for fn in ("rrtmgpb_gas_optics_load", "rrtmgpb_cloud_optics_load"):
+            getattr(self.c, fn).restype = C.c_void_p
+
+    def zeros(self, shape, dtype=np.float64):
+        return fzeros(shape, dtype=dtype, device=self.device)
+
+    def put(self, a):
+        a = np.asfortranarray(a)
+        return a if self.device is None else to_device(a, self.device)
+
+    def get(self, a):
+        self.lib.sync()
+        return to_host(a)
+
+    def config_checks(self, extents=True, values=True):
+        """rte_config_checks(), rte/frontend/mo_rte_config.F90:29-49"""
+        self.c.rrtmgpb_rte_config_checks(int(extents), int(values))
+
+
+class OpticalProps:
+    """ty_optical_props_1scl / _2str / _nstr (rte/frontend/mo_optical_props.F90)."""
+
+    def __init__(self, ctx, kind, ncol, nlay, band_lims_gpt, band_lims_wvn=None, nmom=0, top_at_1=True, name=""):
+        self.ctx, self.kind, self.name = ctx, {"1scl": K1SCL, "2str": K2STR, "nstr": KNSTR}.get(kind, kind), name
+        self.band_lims_gpt = np.asfortranarray(band_lims_gpt, dtype=np.int32)
+        self.band_lims_wvn = None if band_lims_wvn is None else np.asfortranarray(band_lims_wvn, dtype=np.float64)
+        self.nband = self.band_lims_gpt.shape[1]
+        self.ngpt = int(self.band_lims_gpt.max())
+        self.ncol, self.nlay, self.nmom, self.top_at_1 = ncol, nlay, nmom, top_at_1
+        shp = (ncol, nlay, self.ngpt)
+        self.tau = ctx.zeros(shp)
+        self.ssa = ctx.zeros(shp) if self.kind != K1SCL else None
+        self.g = ctx.zeros(shp) if self.kind == K2STR else None
+        self.p = ctx.zeros((nmom,) + shp) if self.kind == KNSTR else None
+
+    @classmethod
+    def like(cls, ctx, kind, ncol, nlay, spectral, **kw):
+        """alloc_*(ncol, nlay, spectral_desc): copy the spectral discretisation of another object."""
+        return cls(ctx, kind, ncol, nlay, spectral.band_lims_gpt, spectral.band_lims_wvn, **kw)
+
+    def struct(self):
+        s = _OpStruct(self.kind, self.ncol, self.nlay, self.ngpt, self.nband, self.nmom, int(self.top_at_1),
+                      self.band_lims_gpt.ctypes.data,
+                      None if self.band_lims_wvn is None else self.band_lims_wvn.ctypes.data, _addr(self.tau),
+                      _addr(self.ssa), _addr(self.g), _addr(self.p))
+        return s
+
+    def _sync_back(self, s):
+        self.top_at_1 = bool(s.top_at_1)
+
+    def set_top_at_1(self, v):
+        self.top_at_1 = bool(v)
+
+    def validate(self):
+        err = C.create_string_buffer(ERRLEN)
+        s = self.struct()
+        _check(self.ctx.c.rrtmgpb_op_validate(C.byref(s), err), err)
+
+    def delta_scale(self, forward=None):
+        err = C.create_string_buffer(ERRLEN)
+        s = self.struct()
+        _check(self.ctx.c.rrtmgpb_op_delta_scale(C.byref(s), C.c_void_p(_addr(forward)), err), err)
+
+    def increment(self, op_io):
+        """call self%increment(op_io): op_io is incremented by self (mo_optical_props.F90:879)."""
+        err = C.create_string_buffer(ERRLEN)
+        a, b = self.struct(), op_io.struct()
+        _check(self.ctx.c.rrtmgpb_op_increment(C.byref(a), C.byref(b), err), err)
+
+
+class SourceFuncLW:
+    """ty_source_func_lw (rte/frontend/mo_source_functions.F90:30-38)."""
+
+    def __init__(self, ctx, ncol, nlay, ngpt):
+        self.ctx, self.ncol, self.nlay, self.ngpt = ctx, ncol, nlay, ngpt
+        self.lay_source = ctx.zeros((ncol, nlay, ngpt))
+        self.lev_source = ctx.zeros((ncol, nlay + 1, ngpt))
+        self.sfc_source = ctx.zeros((ncol, ngpt))
+        self.sfc_source_Jac = ctx.zeros((ncol, ngpt))
+
+    def struct(self):
+        return _SrcStruct(self.ncol, self.nlay, self.ngpt, _addr(self.lay_source), _addr(self.lev_source),
+                          _addr(self.sfc_source), _addr(self.sfc_source_Jac))
+
+
+class FluxesBroadband:
+    """ty_fluxes_broadband (rte/frontend/mo_fluxes.F90:47-54); None = pointer not associated."""
+
+    def __init__(self, flux_up=None, flux_dn=None, flux_net=None, flux_dn_dir=None):
+        self.flux_up, self.flux_dn, self.flux_net, self.flux_dn_dir = flux_up, flux_dn, flux_net, flux_dn_dir
+
+    def struct(self):
+        return _FluxStruct(_addr(self.flux_up), _addr(self.flux_dn), _addr(self.flux_net), _addr(self.flux_dn_dir))
+
+
+def rte_lw(ctx, optical_props, sources, sfc_emis, fluxes, inc_flux=None, n_gauss_angles=0, use_2stream=-1,
+           lw_Ds=None, flux_up_Jac=None):
+    """rte_lw(), rte/frontend/mo_rte_lw.F90:79.  sfc_emis (nband,ncol)."""
+    err = C.create_string_buffer(ERRLEN)
+    o, s, f = optical_props.struct(), sources.struct(), fluxes.struct()
+    _check(ctx.c.rrtmgpb_rte_lw(C.byref(o), C.byref(s), C.c_void_p(_addr(sfc_emis)), C.byref(f),
+                                C.c_void_p(_addr(inc_flux)), int(n_gauss_angles), int(use_2stream),
+                                C.c_void_p(_addr(lw_Ds)), C.c_void_p(_addr(flux_up_Jac)), err), err)
+
+
+def rte_lw_bygpoint(ctx, optical_props, sources, sfc_emis, gpt_flux_up, gpt_flux_dn, inc_flux=None,
+                    n_gauss_angles=0, use_2stream=-1, lw_Ds=None):
+    err = C.create_string_buffer(ERRLEN)
+    o, s = optical_props.struct(), sources.struct()
+    _check(ctx.c.rrtmgpb_rte_lw_bygpoint(C.byref(o), C.byref(s), C.c_void_p(_addr(sfc_emis)),
+                                         C.c_void_p(_addr(gpt_flux_up)), C.c_void_p(_addr(gpt_flux_dn)),
+                                         C.c_void_p(_addr(inc_flux)), int(n_gauss_angles), int(use_2stream),
+                                         C.c_void_p(_addr(lw_Ds)), err), err)
+
+
+def rte_sw(ctx, atmos, mu0, inc_flux, sfc_alb_dir, sfc_alb_dif, fluxes, inc_flux_dif=None):
+    """rte_sw() with mu0 by column, rte/frontend/mo_rte_sw.F90:56."""
+    err = C.create_string_buffer(ERRLEN)
+    o, f = atmos.struct(), fluxes.struct()
+    _check(ctx.c.rrtmgpb_rte_sw(C.byref(o), C.c_void_p(_addr(mu0)), C.c_void_p(_addr(inc_flux)),
+                                C.c_void_p(_addr(sfc_alb_dir)), C.c_void_p(_addr(sfc_alb_dif)), C.byref(f),
+                                C.c_void_p(_addr(inc_flux_dif)), err), err)
+
+
+def rte_sw_bygpoint(ctx, atmos, mu0, inc_flux, sfc_alb_dir, sfc_alb_dif, gpt_up, gpt_dn, gpt_dir, inc_flux_dif=None):
+    err = C.create_string_buffer(ERRLEN)
+    o = atmos.struct()
+    _check(ctx.c.rrtmgpb_rte_sw_bygpoint(C.byref(o), C.c_void_p(_addr(mu0)), C.c_void_p(_addr(inc_flux)),
+                                         C.c_void_p(_addr(sfc_alb_dir)), C.c_void_p(_addr(sfc_alb_dif)),
+                                         C.c_void_p(_addr(gpt_up)), C.c_void_p(_addr(gpt_dn)),
+                                         C.c_void_p(_addr(gpt_dir)), C.c_void_p(_addr(inc_flux_dif)), err), err)
+
+
+class GasOptics:
+    """ty_gas_optics_rrtmgp: load() copies the tables to backend memory once; gas_optics() dispatches on
+    the source type like the Fortran generic (mo_gas_optics_rrtmgp.F90:220,337)."""
+
+    def __init__(self, ctx, kd):
+        self.ctx, self.kd = ctx, kd
+        self._keep = []
+
+        def h(a, dt):
+            a = np.asfortranarray(a, dtype=dt)
+            self._keep.append(a)
+            return a.ctypes.data
+
+        i32, f64, b8 = np.int32, np.float64, np.bool_
+        s = _KDistStruct()
+        s.ngas, s.nflav, s.neta, s.npres, s.ntemp, s.nbnd, s.ngpt = kd.ngas, kd.nflav, kd.neta, kd.npres, kd.ntemp, kd.nbnd, kd.ngpt
+        s.nminorlower, s.nminorupper = kd.extra["nminorlower"], kd.extra["nminorupper"]
+        s.nminorklower, s.nminorkupper = kd.kminor_lower.shape[2], kd.kminor_upper.shape[2]
+        s.idx_h2o = kd.idx_h2o
+        s.flavor, s.gpoint_flavor = h(kd.flavor, i32), h(kd.gpoint_flavor, i32)
+        s.band_lims_gpt, s.gpoint_bands = h(kd.band_lims_gpt, i32), h(kd.gpoint_bands, i32)
+        s.band_lims_wvn, s.press_ref_log = h(kd.band_lims_wvn, f64), h(kd.press_ref_log, f64)
+        s.temp_ref, s.vmr_ref = h(kd.temp_ref, f64), h(kd.vmr_ref, f64)
+        for n in ("press_ref_log_delta", "temp_ref_min", "temp_ref_max", "temp_ref_delta", "press_ref_min",
+                  "press_ref_max", "press_ref_trop_log"):
+            setattr(s, n, getattr(kd, n))
+        s.kmajor, s.kminor_lower, s.kminor_upper = h(kd.kmajor, f64), h(kd.kminor_lower, f64), h(kd.kminor_upper, f64)
+        for n in ("minor_limits_gpt", "idx_minor", "idx_minor_scaling", "kminor_start"):
+            for lu in ("lower", "upper"):
+                setattr(s, f"{n}_{lu}", h(getattr(kd, f"{n}_{lu}"), i32))
+        for n in ("minor_scales_with_density", "scale_by_complement"):
+            for lu in ("lower", "upper"):
+                setattr(s, f"{n}_{lu}", h(getattr(kd, f"{n}_{lu}"), b8))
+        if kd.is_lw:
+            s.planck_frac, s.totplnk = h(kd.planck_frac, f64), h(kd.totplnk, f64)
+            s.nPlanckTemp, s.totplnk_delta = kd.totplnk.shape[0], kd.totplnk_delta
+        else:
+            s.krayl, s.solar_source = h(kd.krayl, f64), h(kd.solar_source, f64)
+        err = C.create_string_buffer(ERRLEN)
+        self.handle = ctx.c.rrtmgpb_gas_optics_load(C.byref(s), err)
+        if not self.handle:
+            raise RuntimeError(err.value.decode())
+        self.band_lims_gpt, self.band_lims_wvn = kd.band_lims_gpt, kd.band_lims_wvn
+        self.ngpt, self.nband = kd.ngpt, kd.nbnd
+
+    def source_is_internal(self):
+        return bool(self.kd.is_lw)
+
+    def source_is_external(self):
+        return not self.kd.is_lw
+
+    def gas_optics(self, p_lay, p_lev, t_lay, vmr, optical_props, t_sfc=None, sources=None, toa_src=None,
+                   col_dry=None, tlev=None):
+        ncol, nlay = optical_props.ncol, optical_props.nlay
+        err = C.create_string_buffer(ERRLEN)
+        o = optical_props.struct()
+        P = lambda x: C.c_void_p(_addr(x))
+        if self.kd.is_lw:
+            s = sources.struct()
+            rc = self.ctx.c.rrtmgpb_gas_optics_int(C.c_void_p(self.handle), ncol, nlay, P(p_lay), P(p_lev), P(t_lay),
+                                                   P(t_sfc), P(vmr), C.byref(o), C.byref(s), P(col_dry), P(tlev), err)
+        else:
+            rc = self.ctx.c.rrtmgpb_gas_optics_ext(C.c_void_p(self.handle), ncol, nlay, P(p_lay), P(p_lev), P(t_lay),
+                                                   P(vmr), C.byref(o), P(toa_src), P(col_dry), err)
+        _check(rc, err)
+        optical_props._sync_back(o)
+
+    def __del__(self):
+        try:
+            self.ctx.c.rrtmgpb_gas_optics_free(C.c_void_p(self.handle))
+        except Exception:
+            pass
+
+
+class CloudOptics:
+    """ty_cloud_optics_rrtmgp in LUT form (mo_cloud_optics_rrtmgp.F90:77,256)."""
+
+    def __init__(self, ctx, lut):
+        self.ctx, self.lut, self._keep = ctx, lut, []
+
+        def h(a):
+            a = np.asfortranarray(a, dtype=np.float64)
+            self._keep.append(a)
+            return a.ctypes.data
+
+        s = _CloudLutStruct()
+        s.nbnd, s.nsize_liq, s.nsize_ice = lut.nbnd, lut.extliq.shape[0], lut.extice.shape[0]
+        s.nrghice, s.icergh = lut.extice.shape[2], lut.icergh
+        s.band_lims_gpt, s.band_lims_wvn = None, h(lut.band_lims_wvn)
+        s.radliq_lwr, s.radliq_upr, s.diamice_lwr, s.diamice_upr = lut.radliq_lwr, lut.radliq_upr, lut.diamice_lwr, lut.diamice_upr
+        for n in ("extliq", "ssaliq", "asyliq", "extice", "ssaice", "asyice"):
+            setattr(s, n, h(getattr(lut, n)))
+        err = C.create_string_buffer(ERRLEN)
+        self.handle = ctx.c.rrtmgpb_cloud_optics_load(C.byref(s), err)
+        if not self.handle:
+            raise RuntimeError(err.value.decode())
+        nb = lut.nbnd
+        self.band_lims_gpt = np.asfortranarray(np.stack([np.arange(1, nb + 1), np.arange(1, nb + 1)]), dtype=np.int32)
+        self.band_lims_wvn = lut.band_lims_wvn
+
+    def cloud_optics(self, clwp, ciwp, reliq, dgice, optical_props):
+        err = C.create_string_buffer(ERRLEN)
+        o = optical_props.struct()
+        P = lambda x: C.c_void_p(_addr(x))
+        _check(self.ctx.c.rrtmgpb_cloud_optics(C.c_void_p(self.handle), optical_props.ncol, optical_props.nlay,
+                                               P(clwp), P(ciwp), P(reliq), P(dgice), C.byref(o), err), err)
+
+    def __del__(self):
+        try:
+            self.ctx.c.rrtmgpb_cloud_optics_free(C.c_void_p(self.handle))
+        except Exception:
+            pass
