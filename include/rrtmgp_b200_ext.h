@@ -57,6 +57,10 @@ void rrtmgpb_init_constants(const Float* gravity, const Float* mol_weight_dry_ai
  * (accel/mo_rte_solver_kernels.F90:958-962). */
 void rrtmgpb_set_lw_2stream_lev_source_per_gpt(int on);
 
+/* Solver kernel family: 0 (default) = register-resident warp-systolic kernels when nlay <= 80 (shared-memory
+ * tile kernels otherwise, and for Tang rescaling); 1 = always the shared-memory tile kernels. */
+void rrtmgpb_set_solver_variant(int variant);
+
 /* ---------------- frontend-resident loops as kernels (SURVEY 8a') ---------------- */
 /* replaces the Fortran function get_layer_number / get_col_dry, rte/kernels/mo_gas_optics_utils.F90:127-152
  * (not bind(C) in the reference: api/mo_gas_optics_utils.F90:53-66).  vmr_h2o(ncol,nlay),

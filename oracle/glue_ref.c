@@ -24,6 +24,7 @@ void* rrtmgpb_get_stream(void) { return NULL; }
 void rrtmgpb_set_device(int d) { (void)d; }
 void rrtmgpb_sync(void) {}
 long long rrtmgpb_launch_count(int reset) { (void)reset; return 0; }
+void rrtmgpb_set_solver_variant(int v) { (void)v; }
 void rrtmgpb_profile_enable(int on) { (void)on; }
 int rrtmgpb_profile_report(char* buf, size_t n) { if (buf && n) buf[0] = 0; return 0; }
 void rrtmgpb_set_lw_2stream_lev_source_per_gpt(int on) { oracle_set_lw_2stream_lev_source_per_gpt(on); }

@@ -18,6 +18,7 @@
 //   * `intent(out)` arrays whose controlling flag is false are decoys that may alias:
 //     they are never read or written here and no pointer is __restrict__.
 #include "../kernels/elementwise.cuh"
+#include "../kernels/solver_reg.cuh"
 #include "rte_kernels.h"
 #include "rrtmgp_b200_ext.h"
 
@@ -27,6 +28,7 @@ namespace {
 
 constexpr int kSolverThreads = 256;
 static int g_lw2s_lev_per_gpt = 0;
+static int g_solver_variant = 0;  // 0: register/warp-systolic kernels when nlay <= 80, else tiles; 1: always tiles
 
 struct Orient {
   int nlay;
@@ -543,9 +545,38 @@ void launch_tile(K kern, const P& p, dim3 grid, size_t smem, const char* name) {
     default: launch_tile(KERNEL<4>, params, grid, smem, #KERNEL); break;          \
   }
 
+
+// register-resident kernels: chunk length CL = ceil(nlay/8) in {8,9,10}
+inline int reg_chunk_len(int nlay) {
+  if (g_solver_variant != 0) return 0;
+  if (nlay <= 64) return 8;
+  if (nlay <= 72) return 9;
+  if (nlay <= 80) return 10;
+  return 0;
+}
+inline int reg_gpt_groups(int ncol, int ngpt) {
+  const int ctas = ceil_div(ncol, (kRegThreads / 32) * kRegCols);
+  int groups = ceil_div(148 * 8, ctas);
+  if (groups < 1) groups = 1;
+  if (groups > ngpt) groups = ngpt;
+  return groups;
+}
+#define DISPATCH_CL(cl, KERNEL, params, grid)                                                    \
+  {                                                                                              \
+    KernelTimer timer(#KERNEL);                                                                  \
+    switch (cl) {                                                                                \
+      case 8: KERNEL<8><<<grid, kRegThreads, 0, stream()>>>(params); break;                      \
+      case 9: KERNEL<9><<<grid, kRegThreads, 0, stream()>>>(params); break;                      \
+      default: KERNEL<10><<<grid, kRegThreads, 0, stream()>>>(params); break;                    \
+    }                                                                                            \
+    RB_LAUNCH_CHECK();                                                                           \
+  }
+
 }  // namespace
 
 extern "C" {
+
+void rrtmgpb_set_solver_variant(int v) { g_solver_variant = v; }
 
 void rrtmgpb_set_lw_2stream_lev_source_per_gpt(int on) { g_lw2s_lev_per_gpt = on ? 1 : 0; }
 
@@ -572,6 +603,31 @@ void rte_lw_solver_noscat(const int* ncol_, const int* nlay_, const int* ngpt_, 
   p.sfc_src = a_ss; p.inc_flux = a_inc; p.flux_up = a_fu; p.flux_dn = a_fd; p.do_broadband = bb; p.bb_up = a_bu;
   p.bb_dn = a_bd; p.do_jac = jac; p.sfc_srcJac = a_sj; p.flux_upJac = a_fj; p.do_rescaling = resc; p.ssa = a_ssa;
   p.g = a_g;
+  if (const int cl = resc ? 0 : reg_chunk_len(nlay)) {
+    LwNoscatRegParams q;
+    q.ncol = ncol; q.nlay = nlay; q.ngpt = ngpt; q.top_at_1 = p.top_at_1; q.nmus = nmus; q.Ds = p.Ds;
+    q.weights = p.weights; q.tau = p.tau; q.lay_source = p.lay_source; q.lev_source = p.lev_source;
+    q.sfc_emis = p.sfc_emis; q.sfc_src = p.sfc_src; q.inc_flux = p.inc_flux; q.flux_up = p.flux_up;
+    q.flux_dn = p.flux_dn; q.do_broadband = bb; q.bb_up = p.bb_up; q.bb_dn = p.bb_dn; q.do_jac = jac;
+    q.sfc_srcJac = p.sfc_srcJac; q.flux_upJac = p.flux_upJac;
+    const int groups = (bb || jac) ? 1 : reg_gpt_groups(ncol, ngpt);
+    q.gpt_per_block = ceil_div(ngpt, groups);
+    dim3 grid(ceil_div(ncol, (kRegThreads / 32) * kRegCols), ceil_div(ngpt, q.gpt_per_block));
+    {
+      KernelTimer timer("lw_noscat_reg_kernel");
+#define LWREG(CLV) \
+  if (jac) lw_noscat_reg_kernel<CLV, true><<<grid, kRegThreads, 0, stream()>>>(q); \
+  else lw_noscat_reg_kernel<CLV, false><<<grid, kRegThreads, 0, stream()>>>(q)
+      switch (cl) {
+        case 8: LWREG(8); break;
+        case 9: LWREG(9); break;
+        default: LWREG(10); break;
+      }
+#undef LWREG
+      RB_LAUNCH_CHECK();
+    }
+    return;
+  }
   const int nlev = nlay + 1;
   const size_t per_col = (size_t)3 * nlay + (resc ? 2 * nlay + 2 * nlev : 0) + (bb ? 2 * nlev : 0) + (jac ? nlev : 0);
   const int tc = pick_tc(per_col);
@@ -597,6 +653,17 @@ void rte_lw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
   p.ncol = ncol; p.nlay = nlay; p.ngpt = ngpt; p.top_at_1 = *top_at_1 ? 1 : 0; p.lev_per_gpt = g_lw2s_lev_per_gpt;
   p.tau = a_tau; p.ssa = a_ssa; p.g = a_g; p.lay_source = a_lay; p.lev_source = a_lev; p.sfc_emis = a_em;
   p.sfc_src = a_ss; p.inc_flux = a_inc; p.flux_up = a_fu; p.flux_dn = a_fd;
+  if (const int cl = reg_chunk_len(nlay)) {
+    Lw2sRegParams q;
+    q.ncol = ncol; q.nlay = nlay; q.ngpt = ngpt; q.top_at_1 = p.top_at_1; q.lev_per_gpt = p.lev_per_gpt;
+    q.tau = p.tau; q.ssa = p.ssa; q.g = p.g; q.lay_source = p.lay_source; q.lev_source = p.lev_source;
+    q.sfc_emis = p.sfc_emis; q.sfc_src = p.sfc_src; q.inc_flux = p.inc_flux; q.flux_up = p.flux_up;
+    q.flux_dn = p.flux_dn;
+    q.gpt_per_block = ceil_div(ngpt, reg_gpt_groups(ncol, ngpt));
+    dim3 grid(ceil_div(ncol, (kRegThreads / 32) * kRegCols), ceil_div(ngpt, q.gpt_per_block));
+    DISPATCH_CL(cl, lw_2stream_reg_kernel, q, grid);
+    return;
+  }
   const size_t per_col = (size_t)6 * nlay;
   const int tc = pick_tc(per_col);
   const int groups = gpt_groups(ncol, tc, ngpt);
@@ -639,6 +706,18 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
   p.tau = a_tau; p.ssa = a_ssa; p.g = a_g; p.mu0 = a_mu; p.sfc_alb_dir = a_ad; p.sfc_alb_dif = a_af;
   p.inc_flux_dir = a_inc; p.flux_up = a_fu; p.flux_dn = a_fd; p.flux_dir = a_fr; p.has_dif_bc = bc;
   p.inc_flux_dif = a_dif; p.do_broadband = bb; p.bb_up = a_bu; p.bb_dn = a_bd; p.bb_dir = a_br;
+  if (const int cl = reg_chunk_len(nlay)) {
+    SwRegParams q;
+    q.ncol = ncol; q.nlay = nlay; q.ngpt = ngpt; q.top_at_1 = p.top_at_1; q.tau = p.tau; q.ssa = p.ssa; q.g = p.g;
+    q.mu0 = p.mu0; q.sfc_alb_dir = p.sfc_alb_dir; q.sfc_alb_dif = p.sfc_alb_dif; q.inc_flux_dir = p.inc_flux_dir;
+    q.flux_up = p.flux_up; q.flux_dn = p.flux_dn; q.flux_dir = p.flux_dir; q.has_dif_bc = bc;
+    q.inc_flux_dif = p.inc_flux_dif; q.do_broadband = bb; q.bb_up = p.bb_up; q.bb_dn = p.bb_dn; q.bb_dir = p.bb_dir;
+    const int groups = bb ? 1 : reg_gpt_groups(ncol, ngpt);
+    q.gpt_per_block = ceil_div(ngpt, groups);
+    dim3 grid(ceil_div(ncol, (kRegThreads / 32) * kRegCols), ceil_div(ngpt, q.gpt_per_block));
+    DISPATCH_CL(cl, sw_2stream_reg_kernel, q, grid);
+    return;
+  }
   const int nlev = nlay + 1;
   const size_t per_col = (size_t)6 * nlay + (bb ? 3 * nlev : 0);
   const int tc = pick_tc(per_col);

@@ -1,0 +1,502 @@
+// solver_reg.cuh - register-resident, warp-systolic RTE solvers (the hot-path variants).
+//
+// Layout of the work inside a warp (32 lanes):
+//     lane = c*8 + j      c in 0..3  : one of the warp's 4 consecutive columns
+//                         j in 0..7  : a CHUNK of CL consecutive layers, counted from the top
+// so a warp owns 4 (column, g-point) recurrences at a time and every lane owns CL cells of one of them.
+//   phase A  every lane computes its CL cells (the exp / sqrt / divide-heavy two-stream or Planck-source
+//            algebra) straight from global memory into REGISTERS: CL independent cells per lane give the
+//            instruction-level parallelism that hides the fp64 latencies; no shared memory, no barrier.
+//   phase B  the layer-serial recurrences (transport / direct beam / adding) run chunk by chunk: the lane
+//            holding chunk j advances the chain through its CL layers out of registers and hands the chain
+//            state (intensity, or (albedo, source), or flux) to the lane of the next chunk with ONE warp
+//            shuffle.  Eight hand-overs per sweep replace the per-layer shared/global traffic of a
+//            thread-per-column design.
+//   Broadband sums live in registers of the lane that owns the level, accumulated in g-point order (the
+//   reference's order, mo_rte_solver_kernels.F90:216-218,601-604): deterministic, no atomics.
+// Layers beyond nlay (padding of the last chunk) are exact pass-through cells (T = 1, R = 0, no source).
+// Every input plane is read from HBM once (32-byte sectors: 4 consecutive columns x 8 layers per request).
+//
+// Numerics follow rte/kernels/mo_rte_solver_kernels.F90 (line numbers cited inline).  Two documented
+// reassociations w.r.t. the reference (results differ by ~1 ulp of the affected term):
+//   * adding: flux_dn(l+1) = a*flux_dn(l) + b with a = Tdif*denom, b = (Rdif*src + src_dn)*denom
+//     instead of (Tdif*flux_dn + Rdif*src + src_dn)*denom (:1197-1199)
+//   * SW broadband_dn adds the direct beam before the diffuse flux of the same g-point (:603)
+#pragma once
+#include "../common.cuh"
+
+namespace rrtmgpb {
+
+constexpr int kRegThreads = 128;  // 4 warps = 16 columns per CTA
+constexpr int kRegChunks = 8;
+constexpr int kRegCols = 4;
+
+struct RegOrient {
+  int nlay, top_at_1;
+  __device__ __forceinline__ int lay(int k) const { return top_at_1 ? k : nlay - 1 - k; }
+  __device__ __forceinline__ int lev(int k) const { return top_at_1 ? k : nlay - k; }
+};
+
+__device__ __forceinline__ Float reg_pi() { return (Float)3.14159265358979323846; }
+
+// ---------------------------------------------------------------------------------------------------
+// LW no-scattering (mo_rte_solver_kernels.F90:51-240, 620-745), without Tang rescaling.
+// ---------------------------------------------------------------------------------------------------
+struct LwNoscatRegParams {
+  int ncol, nlay, ngpt, top_at_1, nmus;
+  const Float *Ds, *weights, *tau, *lay_source, *lev_source, *sfc_emis, *sfc_src, *inc_flux;
+  Float *flux_up, *flux_dn;
+  int do_broadband;
+  Float *bb_up, *bb_dn;
+  int do_jac;
+  const Float* sfc_srcJac;
+  Float* flux_upJac;
+  int gpt_per_block;
+};
+
+template <int CL, bool JAC>
+__global__ void __launch_bounds__(kRegThreads, 3) lw_noscat_reg_kernel(const LwNoscatRegParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = lane >> 3, j = lane & 7;
+  const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
+  const bool col_ok = col_raw < p.ncol;
+  const size_t col = col_ok ? col_raw : p.ncol - 1;  // out-of-range lanes shadow the last column, never store
+  const int nlay = p.nlay, nlev = nlay + 1;
+  const size_t ncol = p.ncol, ncl = ncol * nlay, nclp = ncol * nlev;
+  const RegOrient o{nlay, p.top_at_1};
+  const Float pi = reg_pi();
+  const Float tau_thresh = sqrt(sqrt((Float)RB_EPS));  // :636
+  const int k0 = j * CL;                                // first layer (from the top) of this lane's chunk
+  const int gb = blockIdx.y * p.gpt_per_block, ge = min(p.ngpt, gb + p.gpt_per_block);
+
+  // broadband accumulators: slot i <-> level k0+i+1 (below layer k0+i); *_top <-> level 0 (lane j == 0)
+  Float acc_up[CL], acc_dn[CL], acc_jac[JAC ? CL : 1];
+  Float acc_up_top = 0, acc_dn_top = 0, acc_jac_top = 0;
+#pragma unroll
+  for (int i = 0; i < CL; ++i) { acc_up[i] = 0; acc_dn[i] = 0; if (JAC) acc_jac[JAC ? i : 0] = 0; }
+
+  for (int g = gb; g < ge; ++g) {
+    const size_t gi = col + ncol * g;
+    const Float emis = p.sfc_emis[gi], ssrc = p.sfc_src[gi], inc = p.inc_flux[gi];
+    const Float sjac = JAC ? p.sfc_srcJac[gi] : (Float)0;
+    Float* fup = p.flux_up + nclp * g;
+    Float* fdn = p.flux_dn + nclp * g;
+    for (int imu = 0; imu < p.nmus; ++imu) {
+      const Float w = p.weights[imu];
+      const Float piw = pi * w;
+      const Float D = p.Ds[col + ncol * ((size_t)g + (size_t)p.ngpt * imu)];
+      // ---------------- phase A: CL cells per lane, in registers ----------------
+      Float tr[CL], sd[CL], su[CL], Blev[CL + 1];
+#pragma unroll
+      for (int i = 0; i <= CL; ++i) {
+        const int kk = min(k0 + i, nlay);
+        Blev[i] = p.lev_source[col + ncol * o.lev(kk) + nclp * g];
+      }
+#pragma unroll
+      for (int i = 0; i < CL; ++i) {
+        const int k = k0 + i;
+        if (k < nlay) {
+          const size_t i3 = col + ncol * o.lay(k) + ncl * g;
+          const Float tau_loc = p.tau[i3] * D;                                    // :181
+          const Float t = exp(-tau_loc);                                          // :182
+          Float fact;                                                             // :652-656
+          if (tau_loc > tau_thresh) fact = ((Float)1 - t) / tau_loc - t;
+          else fact = tau_loc * ((Float)0.5 + tau_loc * (-(Float)1 / (Float)3 + tau_loc * (Float)1 / (Float)8));
+          const Float lay = p.lay_source[i3];
+          // :660-663; source_dn uses the Planck source at the layer's BOTTOM level, source_up at its TOP
+          // level in either orientation (:638-644)
+          sd[i] = ((Float)1 - t) * Blev[i + 1] + (Float)2 * fact * (lay - Blev[i + 1]);
+          su[i] = ((Float)1 - t) * Blev[i] + (Float)2 * fact * (lay - Blev[i]);
+          tr[i] = t;
+        } else {
+          tr[i] = 1; sd[i] = 0; su[i] = 0;
+        }
+      }
+      // record one level value; slot < 0 means the top level (only lane j == 0 calls it with -1)
+      auto rec_dn = [&](int i, Float I) {
+        const int klev = (i < 0) ? 0 : k0 + i + 1;
+        if (klev > nlay || !col_ok) return;
+        if (!p.do_broadband) {
+          Float* q = fdn + col + ncol * o.lev(klev);
+          *q = (imu == 0) ? piw * I : *q + piw * I;                                // :223, :357
+        }
+      };
+      auto rec_up = [&](int i, Float I) {
+        const int klev = (i < 0) ? 0 : k0 + i + 1;
+        if (klev > nlay || !col_ok) return;
+        if (!p.do_broadband) {
+          Float* q = fup + col + ncol * o.lev(klev);
+          *q = (imu == 0) ? piw * I : *q + piw * I;                                // :224, :356
+        }
+      };
+      // ---------------- phase B1: downward transport, :697-706 ----------------
+      Float I = inc / (pi * w);                                                    // :144
+      if (j == 0) { acc_dn_top += w * I; rec_dn(-1, I); }
+      for (int jj = 0; jj < kRegChunks; ++jj) {
+        const Float from_above = __shfl_up_sync(0xffffffffu, I, 1);
+        if (j == jj) {
+          if (jj > 0) I = from_above;
+#pragma unroll
+          for (int i = 0; i < CL; ++i) {
+            I = tr[i] * I + sd[i];
+            acc_dn[i] += w * I;                                                    // :218 (scaled by pi at the end)
+            rec_dn(i, I);
+          }
+        }
+      }
+      // surface: the lane of the last chunk holds the intensity at the surface (:198-202)
+      Float Iu = I * ((Float)1 - emis) + emis * ssrc;
+      Float Ij = emis * sjac;
+      // ---------------- phase B2: upward transport, :729-743 ----------------
+      for (int jj = kRegChunks - 1; jj >= 0; --jj) {
+        const Float from_below = __shfl_down_sync(0xffffffffu, Iu, 1);
+        const Float jac_below = JAC ? __shfl_down_sync(0xffffffffu, Ij, 1) : (Float)0;
+        if (j == jj) {
+          if (jj < kRegChunks - 1) { Iu = from_below; Ij = jac_below; }
+#pragma unroll
+          for (int i = CL - 1; i >= 0; --i) {
+            // the incoming value sits at the level below layer k0+i: record it, then cross the layer
+            if (k0 + i < nlay) { acc_up[i] += w * Iu; if (JAC) acc_jac[JAC ? i : 0] += w * Ij; }
+            rec_up(i, Iu);
+            Iu = tr[i] * Iu + su[i];
+            if (JAC) Ij = tr[i] * Ij;
+          }
+        }
+      }
+      if (j == 0) { acc_up_top += w * Iu; acc_jac_top += w * Ij; rec_up(-1, Iu); }
+    }
+  }
+  // ---------------- epilogue: spectrally integrated outputs (:233-238) ----------------
+  if (col_ok && (p.do_broadband || JAC)) {
+#pragma unroll
+    for (int i = 0; i < CL; ++i) {
+      const int klev = k0 + i + 1;
+      if (klev <= nlay) {
+        const size_t o2 = col + ncol * o.lev(klev);
+        if (p.do_broadband) { p.bb_up[o2] = pi * acc_up[i]; p.bb_dn[o2] = pi * acc_dn[i]; }
+        if (JAC) p.flux_upJac[o2] = pi * acc_jac[JAC ? i : 0];
+      }
+    }
+    if (j == 0) {
+      const size_t o2 = col + ncol * o.lev(0);
+      if (p.do_broadband) { p.bb_up[o2] = pi * acc_up_top; p.bb_dn[o2] = pi * acc_dn_top; }
+      if (JAC) p.flux_upJac[o2] = pi * acc_jac_top;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// adding (Shonk & Hogan 2008), mo_rte_solver_kernels.F90:1135-1245, on register chunks.
+// In:  R[i] = Rdif, T[i] = Tdif, SU[i] = src_up, SD[i] = src_dn of layer k0+i (from the top).
+// The upward sweep overwrites them with what the downward sweep needs:
+//       T[i] <- a = Tdif*denom       SD[i] <- b = (Rdif*src_below + src_dn)*denom
+//       R[i] <- albedo below layer   SU[i] <- source below layer
+// rec(i, fup, fdn): fluxes at the level below layer k0+i;  rec(-1, ...) at the top level (lane j == 0).
+// ---------------------------------------------------------------------------------------------------
+template <int CL, typename Rec>
+__device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL], Float (&SU)[CL], Float (&SD)[CL],
+                                           Float albedo_sfc, Float src_sfc, Float flux_dn_top, Rec rec) {
+  Float alb = albedo_sfc, src = src_sfc;  // :1166-1168
+  for (int jj = kRegChunks - 1; jj >= 0; --jj) {
+    const Float alb_b = __shfl_down_sync(0xffffffffu, alb, 1);
+    const Float src_b = __shfl_down_sync(0xffffffffu, src, 1);
+    if (j == jj) {
+      if (jj < kRegChunks - 1) { alb = alb_b; src = src_b; }
+#pragma unroll
+      for (int i = CL - 1; i >= 0; --i) {  // :1174-1186
+        const Float r = R[i], t = T[i], sup = SU[i], sdn = SD[i];
+        const Float denom = (Float)1 / ((Float)1 - r * alb);
+        const Float a = t * denom;
+        R[i] = alb;
+        SU[i] = src;
+        T[i] = a;
+        SD[i] = (r * src + sdn) * denom;
+        const Float albn = r + t * t * alb * denom;
+        src = sup + a * (src + alb * sdn);
+        alb = albn;
+      }
+    }
+  }
+  // lane j == 0 now holds albedo and source at the top of the domain
+  Float fdn = flux_dn_top;
+  if (j == 0) rec(-1, fdn * alb + src, fdn);  // :1190
+  for (int jj = 0; jj < kRegChunks; ++jj) {
+    const Float from_above = __shfl_up_sync(0xffffffffu, fdn, 1);
+    if (j == jj) {
+      if (jj > 0) fdn = from_above;
+#pragma unroll
+      for (int i = 0; i < CL; ++i) {  // :1196-1202
+        fdn = T[i] * fdn + SD[i];
+        rec(i, fdn * R[i] + SU[i], fdn);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SW two-stream (mo_rte_solver_kernels.F90:503-609, 985-1127)
+// ---------------------------------------------------------------------------------------------------
+struct SwRegParams {
+  int ncol, nlay, ngpt, top_at_1;
+  const Float *tau, *ssa, *g, *mu0, *sfc_alb_dir, *sfc_alb_dif, *inc_flux_dir;
+  Float *flux_up, *flux_dn, *flux_dir;
+  int has_dif_bc;
+  const Float* inc_flux_dif;
+  int do_broadband;
+  Float *bb_up, *bb_dn, *bb_dir;
+  int gpt_per_block;
+};
+
+template <int CL>
+__global__ void __launch_bounds__(kRegThreads, 3) sw_2stream_reg_kernel(const SwRegParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = lane >> 3, j = lane & 7;
+  const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
+  const bool col_ok = col_raw < p.ncol;
+  const size_t col = col_ok ? col_raw : p.ncol - 1;
+  const int nlay = p.nlay, nlev = nlay + 1;
+  const size_t ncol = p.ncol, ncl = ncol * nlay, nclp = ncol * nlev;
+  const RegOrient o{nlay, p.top_at_1};
+  const Float eps = (Float)RB_EPS;
+  const Float min_k = (Float)1.e4 * eps;  // :1005
+  const Float min_mu0 = sqrt(eps);        // :1006
+  const int k0 = j * CL;
+  const int gb = blockIdx.y * p.gpt_per_block, ge = min(p.ngpt, gb + p.gpt_per_block);
+
+  Float acc_up[CL], acc_dn[CL], acc_dir[CL];
+  Float acc_up_top = 0, acc_dn_top = 0, acc_dir_top = 0;
+#pragma unroll
+  for (int i = 0; i < CL; ++i) { acc_up[i] = 0; acc_dn[i] = 0; acc_dir[i] = 0; }
+  const Float mu0_top = p.mu0[col + ncol * o.lay(0)];
+  const Float mu0_sfc = p.mu0[col + ncol * o.lay(nlay - 1)];
+
+  for (int g = gb; g < ge; ++g) {
+    const size_t gi = col + ncol * g;
+    Float* gup = p.flux_up + nclp * g;
+    Float* gdn = p.flux_dn + nclp * g;
+    Float* gdir = p.flux_dir + nclp * g;
+    // ---------------- phase A: two-stream layer properties (:1027-1108) ----------------
+    Float R[CL], T[CL], A3[CL], A4[CL], A5[CL];  // Rdif, Tdif, Rdir->src_up, Tdir->src_dn, Tnoscat
+#pragma unroll
+    for (int i = 0; i < CL; ++i) {
+      const int k = k0 + i;
+      if (k < nlay) {
+        const size_t i2 = col + ncol * o.lay(k);
+        const size_t i3 = i2 + ncl * g;
+        const Float tau_s = p.tau[i3], w0_s = p.ssa[i3], g_s = p.g[i3];
+        const Float mu0 = p.mu0[i2];
+        const Float gamma1 = ((Float)8 - w0_s * ((Float)5 + (Float)3 * g_s)) * (Float).25;
+        const Float gamma2 = (Float)3 * (w0_s * ((Float)1 - g_s)) * (Float).25;
+        const Float kk = sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), min_k));
+        const Float exp_minusktau = exp(-tau_s * kk);
+        const Float exp_minus2ktau = exp_minusktau * exp_minusktau;
+        Float RT_term = (Float)1 / (kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau));
+        R[i] = RT_term * gamma2 * ((Float)1 - exp_minus2ktau);
+        T[i] = RT_term * (Float)2 * kk * exp_minusktau;
+        const Float mu0_s = fmax(min_mu0, mu0);
+        const Float k_mu = kk * mu0_s;
+        const Float om = (Float)1 - k_mu * k_mu;
+        RT_term = w0_s * RT_term / (fabs(om) >= eps ? om : eps);
+        const Float gamma3 = ((Float)2 - (Float)3 * mu0_s * g_s) * (Float).25;
+        const Float gamma4 = (Float)1 - gamma3;
+        const Float alpha1 = gamma1 * gamma4 + gamma2 * gamma3;
+        const Float alpha2 = gamma1 * gamma3 + gamma2 * gamma4;
+        const Float k_gamma3 = kk * gamma3;
+        const Float k_gamma4 = kk * gamma4;
+        const Float Tnoscat = exp(-tau_s / mu0_s);
+        Float Rdir = RT_term * (((Float)1 - k_mu) * (alpha2 + k_gamma3) -
+                                ((Float)1 + k_mu) * (alpha2 - k_gamma3) * exp_minus2ktau -
+                                (Float)2.0 * (k_gamma3 - alpha2 * k_mu) * exp_minusktau * Tnoscat);
+        Float Tdir = -RT_term * (((Float)1 + k_mu) * (alpha1 + k_gamma4) * Tnoscat -
+                                 ((Float)1 - k_mu) * (alpha1 - k_gamma4) * exp_minus2ktau * Tnoscat -
+                                 (Float)2.0 * (k_gamma4 + alpha1 * k_mu) * exp_minusktau);
+        Rdir = fmax((Float)0, fmin(Rdir, ((Float)1 - Tnoscat)));         // :1107
+        Tdir = fmax((Float)0, fmin(Tdir, ((Float)1 - Tnoscat - Rdir)));  // :1108
+        const bool night = !(mu0 > (Float)0);  // :1122-1125: no source for diffuse light where mu0 <= 0
+        A3[i] = night ? (Float)0 : Rdir;
+        A4[i] = night ? (Float)0 : Tdir;
+        A5[i] = Tnoscat;
+      } else {
+        R[i] = 0; T[i] = 1; A3[i] = 0; A4[i] = 0; A5[i] = 1;
+      }
+    }
+    // ---------------- phase B1: direct beam and its sources, :1110-1112 ----------------
+    Float dir = p.inc_flux_dir[gi] * mu0_top;  // :575
+    if (j == 0) {
+      acc_dir_top += dir;
+      acc_dn_top += dir;
+      if (!p.do_broadband && col_ok) gdir[col + ncol * o.lev(0)] = dir;
+    }
+    for (int jj = 0; jj < kRegChunks; ++jj) {
+      const Float from_above = __shfl_up_sync(0xffffffffu, dir, 1);
+      if (j == jj) {
+        if (jj > 0) dir = from_above;
+#pragma unroll
+        for (int i = 0; i < CL; ++i) {
+          const Float s_up = A3[i] * dir, s_dn = A4[i] * dir;
+          dir = A5[i] * dir;
+          A3[i] = s_up;
+          A4[i] = s_dn;
+          if (k0 + i < nlay) {
+            acc_dir[i] += dir;  // :604
+            acc_dn[i] += dir;   // direct part of :603
+            if (!p.do_broadband && col_ok) gdir[col + ncol * o.lev(k0 + i + 1)] = dir;
+          }
+          A5[i] = dir;  // direct flux below layer k0+i, for the g-point totals (:606)
+        }
+      }
+    }
+    // the lane of the last chunk holds the direct flux at the surface (:1120)
+    const Float src_sfc = (mu0_sfc > (Float)0) ? dir * p.sfc_alb_dir[gi] : (Float)0;
+    const Float dn_top = p.has_dif_bc ? p.inc_flux_dif[gi] : (Float)0;  // :579-583
+    const Float dir_top_g = p.inc_flux_dir[gi] * mu0_top;
+    // fluxes at the top level (lane j == 0 only)
+    auto rec_top = [&](Float fup, Float fdn) {
+      acc_up_top += fup;                                                     // :602
+      acc_dn_top += fdn;                                                     // diffuse part of :603
+      if (!p.do_broadband && col_ok) {
+        const size_t q = col + ncol * o.lev(0);
+        gup[q] = fup;
+        gdn[q] = fdn + dir_top_g;                                            // :606
+      }
+    };
+    // adding (:1135-1245) with in-register accumulation; same algebra as adding_reg() above, written
+    // out here so the accumulator updates use static register indices
+    {
+      Float alb = p.sfc_alb_dif[gi], src = src_sfc;
+      for (int jj = kRegChunks - 1; jj >= 0; --jj) {
+        const Float alb_b = __shfl_down_sync(0xffffffffu, alb, 1);
+        const Float src_b = __shfl_down_sync(0xffffffffu, src, 1);
+        if (j == jj) {
+          if (jj < kRegChunks - 1) { alb = alb_b; src = src_b; }
+#pragma unroll
+          for (int i = CL - 1; i >= 0; --i) {  // :1174-1186
+            const Float r = R[i], t = T[i], sup = A3[i], sdn = A4[i];
+            const Float denom = (Float)1 / ((Float)1 - r * alb);
+            const Float a = t * denom;
+            R[i] = alb;
+            A3[i] = src;
+            T[i] = a;
+            A4[i] = (r * src + sdn) * denom;
+            const Float albn = r + t * t * alb * denom;
+            src = sup + a * (src + alb * sdn);
+            alb = albn;
+          }
+        }
+      }
+      Float fdn = dn_top;
+      if (j == 0) rec_top(fdn * alb + src, fdn);  // :1190
+      for (int jj = 0; jj < kRegChunks; ++jj) {
+        const Float from_above = __shfl_up_sync(0xffffffffu, fdn, 1);
+        if (j == jj) {
+          if (jj > 0) fdn = from_above;
+#pragma unroll
+          for (int i = 0; i < CL; ++i) {  // :1196-1202
+            fdn = T[i] * fdn + A4[i];
+            const Float fup = fdn * R[i] + A3[i];
+            if (k0 + i < nlay) { acc_up[i] += fup; acc_dn[i] += fdn; }
+            if (!p.do_broadband && col_ok && k0 + i < nlay) {
+              const size_t q = col + ncol * o.lev(k0 + i + 1);
+              gup[q] = fup;
+              gdn[q] = fdn + A5[i];  // :606
+            }
+          }
+        }
+      }
+    }
+  }
+  if (p.do_broadband && col_ok) {
+#pragma unroll
+    for (int i = 0; i < CL; ++i) {
+      const int klev = k0 + i + 1;
+      if (klev <= nlay) {
+        const size_t o2 = col + ncol * o.lev(klev);
+        p.bb_up[o2] = acc_up[i]; p.bb_dn[o2] = acc_dn[i]; p.bb_dir[o2] = acc_dir[i];
+      }
+    }
+    if (j == 0) {
+      const size_t o2 = col + ncol * o.lev(0);
+      p.bb_up[o2] = acc_up_top; p.bb_dn[o2] = acc_dn_top; p.bb_dir[o2] = acc_dir_top;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LW two-stream (mo_rte_solver_kernels.F90:377-440, 854-967): g-point fluxes only
+// ---------------------------------------------------------------------------------------------------
+struct Lw2sRegParams {
+  int ncol, nlay, ngpt, top_at_1, lev_per_gpt;
+  const Float *tau, *ssa, *g, *lay_source, *lev_source, *sfc_emis, *sfc_src, *inc_flux;
+  Float *flux_up, *flux_dn;
+  int gpt_per_block;
+};
+
+template <int CL>
+__global__ void __launch_bounds__(kRegThreads, 4) lw_2stream_reg_kernel(const Lw2sRegParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = lane >> 3, j = lane & 7;
+  const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
+  const bool col_ok = col_raw < p.ncol;
+  const size_t col = col_ok ? col_raw : p.ncol - 1;
+  const int nlay = p.nlay, nlev = nlay + 1;
+  const size_t ncol = p.ncol, ncl = ncol * nlay, nclp = ncol * nlev;
+  const RegOrient o{nlay, p.top_at_1};
+  const Float pi = reg_pi();
+  const Float LW_diff_sec = (Float)1.66f;  // :870 single-precision literal widened to wp
+  const int k0 = j * CL;
+  const int gb = blockIdx.y * p.gpt_per_block, ge = min(p.ngpt, gb + p.gpt_per_block);
+
+  for (int g = gb; g < ge; ++g) {
+    const size_t gi = col + ncol * g;
+    const size_t gsrc = p.lev_per_gpt ? g : 0;  // reference default-kernel quirk (:422), see the ABI header
+    Float* gup = p.flux_up + nclp * g;
+    Float* gdn = p.flux_dn + nclp * g;
+    Float R[CL], T[CL], SU[CL], SD[CL], Blev[CL + 1];
+#pragma unroll
+    for (int i = 0; i <= CL; ++i) {
+      const int kk = min(k0 + i, nlay);
+      Blev[i] = p.lev_source[col + ncol * o.lev(kk) + nclp * gsrc];
+    }
+#pragma unroll
+    for (int i = 0; i < CL; ++i) {
+      const int k = k0 + i;
+      if (k < nlay) {
+        const size_t i3 = col + ncol * o.lay(k) + ncl * g;
+        const Float tau = p.tau[i3], w0 = p.ssa[i3], gg = p.g[i3];
+        const Float gamma1 = LW_diff_sec * ((Float)1 - (Float)0.5 * w0 * ((Float)1 + gg));   // :879
+        const Float gamma2 = LW_diff_sec * (Float)0.5 * w0 * ((Float)1 - gg);                // :880
+        const Float kk = sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), (Float)1.e-12));   // :885
+        const Float exp_minusktau = exp(-tau * kk);
+        const Float exp_minus2ktau = exp_minusktau * exp_minusktau;
+        const Float RT_term = (Float)1 / (kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau));
+        const Float rdif = RT_term * gamma2 * ((Float)1 - exp_minus2ktau);
+        const Float tdif = RT_term * (Float)2 * kk * exp_minusktau;
+        const Float lev_top = Blev[i], lev_bot = Blev[i + 1];
+        Float s_up = 0, s_dn = 0;
+        if (tau > (Float)1.0e-8) {  // :947-957
+          const Float Z = (lev_bot - lev_top) / (tau * (gamma1 + gamma2));
+          const Float Zup_top = Z + lev_top;
+          const Float Zup_bottom = Z + lev_bot;
+          const Float Zdn_top = -Z + lev_top;
+          const Float Zdn_bottom = -Z + lev_bot;
+          s_up = pi * (Zup_top - rdif * Zdn_top - tdif * Zup_bottom);
+          s_dn = pi * (Zdn_bottom - rdif * Zup_bottom - tdif * Zdn_top);
+        }
+        R[i] = rdif; T[i] = tdif; SU[i] = s_up; SD[i] = s_dn;
+      } else {
+        R[i] = 0; T[i] = 1; SU[i] = 0; SD[i] = 0;
+      }
+    }
+    const Float emis = p.sfc_emis[gi];
+    auto rec = [&](int i, Float fup, Float fdn) {
+      const int klev = (i < 0) ? 0 : k0 + i + 1;
+      if (klev > nlay || !col_ok) return;
+      const size_t q = col + ncol * o.lev(klev);
+      gup[q] = fup;
+      gdn[q] = fdn;
+    };
+    adding_reg<CL>(j, R, T, SU, SD, (Float)1 - emis, pi * emis * p.sfc_src[gi], p.inc_flux[gi], rec);
+  }
+}
+
+}  // namespace rrtmgpb

@@ -34,11 +34,17 @@ def cuda_lib():
     return _cuda_lib()
 
 
-@pytest.fixture(params=["oracle", pytest.param("cuda", marks=pytest.mark.gpu)])
+@pytest.fixture(params=["oracle", pytest.param("cuda", marks=pytest.mark.gpu),
+                        pytest.param("cuda-tile", marks=pytest.mark.gpu)])
 def backend(request):
-    """(KernelLib, device) for the CPU oracle and - under `-m gpu` - for the CUDA product library."""
+    """(KernelLib, device) for the CPU oracle and - under `-m gpu` - for the CUDA product library, once with
+    the default (register / warp-systolic) solver kernels and once forced onto the shared-memory tile kernels."""
     if request.param == "oracle":
         import oracle
 
-        return oracle.lib(), None
-    return _cuda_lib(), "cuda:0"
+        yield oracle.lib(), None
+        return
+    lib = _cuda_lib()
+    lib.cdll.rrtmgpb_set_solver_variant(1 if request.param == "cuda-tile" else 0)
+    yield lib, "cuda:0"
+    lib.cdll.rrtmgpb_set_solver_variant(0)

@@ -24,9 +24,12 @@ def _run(lib, device, ncol, nlay, kd_lw, kd_sw, profiles=None, do_clouds=True):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("ncol,nlay", [(24, 72), (37, 60), (130, 72)])
-def test_allsky_replicated_profile(oracle_lib, cuda_lib, kdists, ncol, nlay):
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("ncol,nlay", [(24, 72), (37, 60), (130, 72), (21, 78), (19, 96)])
+def test_allsky_replicated_profile(oracle_lib, cuda_lib, kdists, ncol, nlay, variant):
+    """variant 0: register / warp-systolic solvers (nlay <= 80; 96 layers falls back to tiles); 1: tile solvers."""
     kd_lw, kd_sw = kdists
+    cuda_lib.cdll.rrtmgpb_set_solver_variant(variant)
     g = _run(cuda_lib, "cuda:0", ncol, nlay, kd_lw, kd_sw)
     c = _run(oracle_lib, None, ncol, nlay, kd_lw, kd_sw)
     fg, fc = g.fluxes_host(), c.fluxes_host()
@@ -39,6 +42,7 @@ def test_allsky_replicated_profile(oracle_lib, cuda_lib, kdists, ncol, nlay):
                          ("sw g", g.sw.atmos.g, c.sw.atmos.g)):
         x, y = g.ctx.get(ga), c.ctx.get(ca)
         np.testing.assert_allclose(x, y, rtol=1e-12, atol=1e-300, err_msg=name)
+    cuda_lib.cdll.rrtmgpb_set_solver_variant(0)
 
 
 @pytest.mark.gpu
