@@ -53,11 +53,13 @@ def algorithmic_bytes(ncol, nlay, ngpt_lw, ngpt_sw, nbnd_lw, nbnd_sw, nflav_lw, 
     P = planes(ngpt_lw)
     out["planck_source"] = N * L * (8 * nflav_lw * w + 2 * nflav_lw * i4 + 2 * i4 + b1 + 2 * w) + P * (2 + 1.0 / L) + 2 * N * ngpt_lw * w
     out["lw_noscat_kernel"] = P * (3 + 1.0 / L) + 4 * N * ngpt_lw * w + 2 * N * (L + 1) * w
+    out["lw_noscat_reg_kernel"] = out["lw_noscat_kernel"]
     out["rte_inc_1scalar_by_1scalar_bybnd"] = 2 * P
     P = planes(ngpt_sw)
     out["tau_rayleigh"] = N * L * (4 * nflav_sw * w + 2 * nflav_sw * i4 + i4 + b1 + (1 + S) * w) + P
     out["rrtmgpb_combine_abs_and_rayleigh"] = 5 * P
     out["sw_2stream_kernel"] = 3 * P + N * L * w + 4 * N * ngpt_sw * w + 3 * N * (L + 1) * w
+    out["sw_2stream_reg_kernel"] = out["sw_2stream_kernel"]
     out["rte_inc_2stream_by_2stream_bybnd"] = 6 * P
     out["rte_delta_scale_2str_k"] = 6 * N * L * nbnd_sw * w
     return out

@@ -615,15 +615,25 @@ void rte_lw_solver_noscat(const int* ncol_, const int* nlay_, const int* ngpt_, 
     dim3 grid(ceil_div(ncol, (kRegThreads / 32) * kRegCols), ceil_div(ngpt, q.gpt_per_block));
     {
       KernelTimer timer("lw_noscat_reg_kernel");
-#define LWREG(CLV) \
-  if (jac) lw_noscat_reg_kernel<CLV, true><<<grid, kRegThreads, 0, stream()>>>(q); \
-  else lw_noscat_reg_kernel<CLV, false><<<grid, kRegThreads, 0, stream()>>>(q)
+#define LWREG2(CLV, BBV, JACV)                                                                              \
+  {                                                                                                         \
+    const size_t smem = (size_t)2 * lw_noscat_reg_slots<CLV>() * kRegThreads * sizeof(Float);               \
+    auto kern = lw_noscat_reg_kernel<CLV, BBV, JACV>;                                                       \
+    RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    kern<<<grid, kRegThreads, smem, stream()>>>(q);                                                         \
+  }
+#define LWREG(CLV)                                    \
+  if (bb && jac) LWREG2(CLV, true, true)              \
+  else if (bb) LWREG2(CLV, true, false)               \
+  else if (jac) LWREG2(CLV, false, true)              \
+  else LWREG2(CLV, false, false)
       switch (cl) {
         case 8: LWREG(8); break;
         case 9: LWREG(9); break;
         default: LWREG(10); break;
       }
 #undef LWREG
+#undef LWREG2
       RB_LAUNCH_CHECK();
     }
     return;
@@ -715,7 +725,26 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
     const int groups = bb ? 1 : reg_gpt_groups(ncol, ngpt);
     q.gpt_per_block = ceil_div(ngpt, groups);
     dim3 grid(ceil_div(ncol, (kRegThreads / 32) * kRegCols), ceil_div(ngpt, q.gpt_per_block));
-    DISPATCH_CL(cl, sw_2stream_reg_kernel, q, grid);
+    {
+      KernelTimer timer("sw_2stream_reg_kernel");
+#define SWREG2(CLV, BBV)                                                                                    \
+  {                                                                                                         \
+    const size_t smem = ((size_t)2 * sw_reg_slots<CLV>() + CLV) * kRegThreads * sizeof(Float);              \
+    auto kern = sw_2stream_reg_kernel<CLV, BBV>;                                                            \
+    RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    kern<<<grid, kRegThreads, smem, stream()>>>(q);                                                         \
+  }
+#define SWREG(CLV) \
+  if (bb) SWREG2(CLV, true) else SWREG2(CLV, false)
+      switch (cl) {
+        case 8: SWREG(8); break;
+        case 9: SWREG(9); break;
+        default: SWREG(10); break;
+      }
+#undef SWREG
+#undef SWREG2
+      RB_LAUNCH_CHECK();
+    }
     return;
   }
   const int nlev = nlay + 1;

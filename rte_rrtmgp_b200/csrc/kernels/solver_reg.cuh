@@ -4,9 +4,12 @@
 //     lane = c*8 + j      c in 0..3  : one of the warp's 4 consecutive columns
 //                         j in 0..7  : a CHUNK of CL consecutive layers, counted from the top
 // so a warp owns 4 (column, g-point) recurrences at a time and every lane owns CL cells of one of them.
+//   prefetch every lane copies the inputs of its CL cells for g-point g+1 from global memory into its own
+//            shared-memory slots with cp.async (LDGSTS) while g-point g is being processed: two stages,
+//            lane-private slots, so completion is a per-thread cp.async.wait_group - no block barrier;
 //   phase A  every lane computes its CL cells (the exp / sqrt / divide-heavy two-stream or Planck-source
-//            algebra) straight from global memory into REGISTERS: CL independent cells per lane give the
-//            instruction-level parallelism that hides the fp64 latencies; no shared memory, no barrier.
+//            algebra) into REGISTERS: CL independent cells per lane give the instruction-level
+//            parallelism that hides the fp64 latencies;
 //   phase B  the layer-serial recurrences (transport / direct beam / adding) run chunk by chunk: the lane
 //            holding chunk j advances the chain through its CL layers out of registers and hands the chain
 //            state (intensity, or (albedo, source), or flux) to the lane of the next chunk with ONE warp
@@ -39,6 +42,18 @@ struct RegOrient {
 
 __device__ __forceinline__ Float reg_pi() { return (Float)3.14159265358979323846; }
 
+// 8-byte asynchronous global->shared copy (LDGSTS); lane-private destination
+__device__ __forceinline__ void cp_async_f(Float* smem_dst, const Float* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem_src), "n"((int)sizeof(Float)) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// slot v of this thread in stage s: [s][v][thread] - consecutive threads hit consecutive 8-byte words
+#define RB_SLOT(base, nslots, s, v) ((base) + ((size_t)((s) * (nslots) + (v)) * kRegThreads + threadIdx.x))
+
 // ---------------------------------------------------------------------------------------------------
 // LW no-scattering (mo_rte_solver_kernels.F90:51-240, 620-745), without Tang rescaling.
 // ---------------------------------------------------------------------------------------------------
@@ -54,13 +69,19 @@ struct LwNoscatRegParams {
   int gpt_per_block;
 };
 
-template <int CL, bool JAC>
+template <int CL>
+__host__ __device__ constexpr int lw_noscat_reg_slots() { return 3 * CL + 1 + 5; }  // tau, lay, lev(+1), emis, sfc_src, inc_flux, jac, D(angle 1)
+
+template <int CL, bool BB, bool JAC>
 __global__ void __launch_bounds__(kRegThreads, 3) lw_noscat_reg_kernel(const LwNoscatRegParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Float* sm = reinterpret_cast<Float*>(smem_raw);
+  constexpr int NS = lw_noscat_reg_slots<CL>();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = lane >> 3, j = lane & 7;
   const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
   const bool col_ok = col_raw < p.ncol;
-  const size_t col = col_ok ? col_raw : p.ncol - 1;  // out-of-range lanes shadow the last column, never store
+  const int col = col_ok ? col_raw : p.ncol - 1;  // out-of-range lanes shadow the last column, never store
   const int nlay = p.nlay, nlev = nlay + 1;
   const size_t ncol = p.ncol, ncl = ncol * nlay, nclp = ncol * nlev;
   const RegOrient o{nlay, p.top_at_1};
@@ -68,70 +89,94 @@ __global__ void __launch_bounds__(kRegThreads, 3) lw_noscat_reg_kernel(const LwN
   const Float tau_thresh = sqrt(sqrt((Float)RB_EPS));  // :636
   const int k0 = j * CL;                                // first layer (from the top) of this lane's chunk
   const int gb = blockIdx.y * p.gpt_per_block, ge = min(p.ngpt, gb + p.gpt_per_block);
+  // in-plane offsets are 32-bit (ncol*(nlay+1) < 2^31); plane bases are 64-bit
+  const int lay_step = p.top_at_1 ? p.ncol : -p.ncol;
+  const int off_lay0 = col + p.ncol * o.lay(min(k0, nlay - 1));  // layer k0
+  const int off_lev0 = col + p.ncol * o.lev(min(k0, nlay));      // level k0
+
+  auto prefetch = [&](int g, int s) {
+    const Float* tau_g = p.tau + ncl * g;
+    const Float* lay_g = p.lay_source + ncl * g;
+    const Float* lev_g = p.lev_source + nclp * g;
+#pragma unroll
+    for (int i = 0; i < CL; ++i) {
+      const int off = (k0 + i < nlay) ? off_lay0 + lay_step * i : off_lay0;
+      cp_async_f(RB_SLOT(sm, NS, s, i), tau_g + off);
+      cp_async_f(RB_SLOT(sm, NS, s, CL + i), lay_g + off);
+    }
+#pragma unroll
+    for (int i = 0; i <= CL; ++i) {
+      const int off = (k0 + i <= nlay) ? off_lev0 + lay_step * i : off_lev0;
+      cp_async_f(RB_SLOT(sm, NS, s, 2 * CL + i), lev_g + off);
+    }
+    const size_t gi = (size_t)col + ncol * g;
+    cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 1), p.sfc_emis + gi);
+    cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 2), p.sfc_src + gi);
+    cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 3), p.inc_flux + gi);
+    if (JAC) cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 4), p.sfc_srcJac + gi);
+    cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 5), p.Ds + gi);
+  };
 
   // broadband accumulators: slot i <-> level k0+i+1 (below layer k0+i); *_top <-> level 0 (lane j == 0)
-  Float acc_up[CL], acc_dn[CL], acc_jac[JAC ? CL : 1];
+  Float acc_up[BB ? CL : 1], acc_dn[BB ? CL : 1], acc_jac[JAC ? CL : 1];
   Float acc_up_top = 0, acc_dn_top = 0, acc_jac_top = 0;
 #pragma unroll
-  for (int i = 0; i < CL; ++i) { acc_up[i] = 0; acc_dn[i] = 0; if (JAC) acc_jac[JAC ? i : 0] = 0; }
+  for (int i = 0; i < CL; ++i) {
+    if (BB) { acc_up[BB ? i : 0] = 0; acc_dn[BB ? i : 0] = 0; }
+    if (JAC) acc_jac[JAC ? i : 0] = 0;
+  }
 
+  if (gb < ge) prefetch(gb, 0);
+  cp_async_commit();
   for (int g = gb; g < ge; ++g) {
-    const size_t gi = col + ncol * g;
-    const Float emis = p.sfc_emis[gi], ssrc = p.sfc_src[gi], inc = p.inc_flux[gi];
-    const Float sjac = JAC ? p.sfc_srcJac[gi] : (Float)0;
+    const int s = (g - gb) & 1;
+    if (g + 1 < ge) prefetch(g + 1, s ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();  // everything but the newest group (stage s^1) has landed; slots are lane-private
+    const Float emis = *RB_SLOT(sm, NS, s, 3 * CL + 1), ssrc = *RB_SLOT(sm, NS, s, 3 * CL + 2),
+                inc = *RB_SLOT(sm, NS, s, 3 * CL + 3);
+    const Float sjac = JAC ? *RB_SLOT(sm, NS, s, 3 * CL + 4) : (Float)0;
     Float* fup = p.flux_up + nclp * g;
     Float* fdn = p.flux_dn + nclp * g;
     for (int imu = 0; imu < p.nmus; ++imu) {
       const Float w = p.weights[imu];
       const Float piw = pi * w;
-      const Float D = p.Ds[col + ncol * ((size_t)g + (size_t)p.ngpt * imu)];
+      const Float D = (imu == 0) ? *RB_SLOT(sm, NS, s, 3 * CL + 5)
+                               : p.Ds[(size_t)col + ncol * ((size_t)g + (size_t)p.ngpt * imu)];
       // ---------------- phase A: CL cells per lane, in registers ----------------
-      Float tr[CL], sd[CL], su[CL], Blev[CL + 1];
-#pragma unroll
-      for (int i = 0; i <= CL; ++i) {
-        const int kk = min(k0 + i, nlay);
-        Blev[i] = p.lev_source[col + ncol * o.lev(kk) + nclp * g];
-      }
+      Float tr[CL], sd[CL], su[CL];
+      Float Btop = *RB_SLOT(sm, NS, s, 2 * CL);
 #pragma unroll
       for (int i = 0; i < CL; ++i) {
-        const int k = k0 + i;
-        if (k < nlay) {
-          const size_t i3 = col + ncol * o.lay(k) + ncl * g;
-          const Float tau_loc = p.tau[i3] * D;                                    // :181
-          const Float t = exp(-tau_loc);                                          // :182
-          Float fact;                                                             // :652-656
+        const Float Bbot = *RB_SLOT(sm, NS, s, 2 * CL + i + 1);
+        if (k0 + i < nlay) {
+          const Float tau_loc = *RB_SLOT(sm, NS, s, i) * D;                        // :181
+          const Float t = exp(-tau_loc);                                           // :182
+          Float fact;                                                              // :652-656
           if (tau_loc > tau_thresh) fact = ((Float)1 - t) / tau_loc - t;
           else fact = tau_loc * ((Float)0.5 + tau_loc * (-(Float)1 / (Float)3 + tau_loc * (Float)1 / (Float)8));
-          const Float lay = p.lay_source[i3];
+          const Float lay = *RB_SLOT(sm, NS, s, CL + i);
           // :660-663; source_dn uses the Planck source at the layer's BOTTOM level, source_up at its TOP
           // level in either orientation (:638-644)
-          sd[i] = ((Float)1 - t) * Blev[i + 1] + (Float)2 * fact * (lay - Blev[i + 1]);
-          su[i] = ((Float)1 - t) * Blev[i] + (Float)2 * fact * (lay - Blev[i]);
+          sd[i] = ((Float)1 - t) * Bbot + (Float)2 * fact * (lay - Bbot);
+          su[i] = ((Float)1 - t) * Btop + (Float)2 * fact * (lay - Btop);
           tr[i] = t;
         } else {
           tr[i] = 1; sd[i] = 0; su[i] = 0;
         }
+        Btop = Bbot;
       }
-      // record one level value; slot < 0 means the top level (only lane j == 0 calls it with -1)
-      auto rec_dn = [&](int i, Float I) {
-        const int klev = (i < 0) ? 0 : k0 + i + 1;
+      // g-point flux of one level (only when spectrally resolved output is requested)
+      auto store = [&](Float* gflux, int klev, Float I) {
         if (klev > nlay || !col_ok) return;
-        if (!p.do_broadband) {
-          Float* q = fdn + col + ncol * o.lev(klev);
-          *q = (imu == 0) ? piw * I : *q + piw * I;                                // :223, :357
-        }
-      };
-      auto rec_up = [&](int i, Float I) {
-        const int klev = (i < 0) ? 0 : k0 + i + 1;
-        if (klev > nlay || !col_ok) return;
-        if (!p.do_broadband) {
-          Float* q = fup + col + ncol * o.lev(klev);
-          *q = (imu == 0) ? piw * I : *q + piw * I;                                // :224, :356
-        }
+        Float* q = gflux + (size_t)col + ncol * o.lev(klev);
+        *q = (imu == 0) ? piw * I : *q + piw * I;                                  // :223-224, :356-357
       };
       // ---------------- phase B1: downward transport, :697-706 ----------------
       Float I = inc / (pi * w);                                                    // :144
-      if (j == 0) { acc_dn_top += w * I; rec_dn(-1, I); }
+      if (j == 0) {
+        if (BB) acc_dn_top += w * I; else store(fdn, 0, I);
+      }
       for (int jj = 0; jj < kRegChunks; ++jj) {
         const Float from_above = __shfl_up_sync(0xffffffffu, I, 1);
         if (j == jj) {
@@ -139,8 +184,8 @@ __global__ void __launch_bounds__(kRegThreads, 3) lw_noscat_reg_kernel(const LwN
 #pragma unroll
           for (int i = 0; i < CL; ++i) {
             I = tr[i] * I + sd[i];
-            acc_dn[i] += w * I;                                                    // :218 (scaled by pi at the end)
-            rec_dn(i, I);
+            if (BB) acc_dn[BB ? i : 0] += w * I;                                   // :218 (scaled by pi at the end)
+            else store(fdn, k0 + i + 1, I);
           }
         }
       }
@@ -156,30 +201,35 @@ __global__ void __launch_bounds__(kRegThreads, 3) lw_noscat_reg_kernel(const LwN
 #pragma unroll
           for (int i = CL - 1; i >= 0; --i) {
             // the incoming value sits at the level below layer k0+i: record it, then cross the layer
-            if (k0 + i < nlay) { acc_up[i] += w * Iu; if (JAC) acc_jac[JAC ? i : 0] += w * Ij; }
-            rec_up(i, Iu);
+            if (k0 + i < nlay) {
+              if (BB) acc_up[BB ? i : 0] += w * Iu; else store(fup, k0 + i + 1, Iu);
+              if (JAC) acc_jac[JAC ? i : 0] += w * Ij;
+            }
             Iu = tr[i] * Iu + su[i];
             if (JAC) Ij = tr[i] * Ij;
           }
         }
       }
-      if (j == 0) { acc_up_top += w * Iu; acc_jac_top += w * Ij; rec_up(-1, Iu); }
+      if (j == 0) {
+        if (BB) acc_up_top += w * Iu; else store(fup, 0, Iu);
+        if (JAC) acc_jac_top += w * Ij;
+      }
     }
   }
   // ---------------- epilogue: spectrally integrated outputs (:233-238) ----------------
-  if (col_ok && (p.do_broadband || JAC)) {
+  if (col_ok && (BB || JAC)) {
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
       const int klev = k0 + i + 1;
       if (klev <= nlay) {
-        const size_t o2 = col + ncol * o.lev(klev);
-        if (p.do_broadband) { p.bb_up[o2] = pi * acc_up[i]; p.bb_dn[o2] = pi * acc_dn[i]; }
+        const size_t o2 = (size_t)col + ncol * o.lev(klev);
+        if (BB) { p.bb_up[o2] = pi * acc_up[BB ? i : 0]; p.bb_dn[o2] = pi * acc_dn[BB ? i : 0]; }
         if (JAC) p.flux_upJac[o2] = pi * acc_jac[JAC ? i : 0];
       }
     }
     if (j == 0) {
-      const size_t o2 = col + ncol * o.lev(0);
-      if (p.do_broadband) { p.bb_up[o2] = pi * acc_up_top; p.bb_dn[o2] = pi * acc_dn_top; }
+      const size_t o2 = (size_t)col + ncol * o.lev(0);
+      if (BB) { p.bb_up[o2] = pi * acc_up_top; p.bb_dn[o2] = pi * acc_dn_top; }
       if (JAC) p.flux_upJac[o2] = pi * acc_jac_top;
     }
   }
@@ -191,11 +241,12 @@ __global__ void __launch_bounds__(kRegThreads, 3) lw_noscat_reg_kernel(const LwN
 // The upward sweep overwrites them with what the downward sweep needs:
 //       T[i] <- a = Tdif*denom       SD[i] <- b = (Rdif*src_below + src_dn)*denom
 //       R[i] <- albedo below layer   SU[i] <- source below layer
-// rec(i, fup, fdn): fluxes at the level below layer k0+i;  rec(-1, ...) at the top level (lane j == 0).
+// top(fup, fdn): fluxes at the top level (lane j == 0); lev(i, fup, fdn): at the level below layer k0+i,
+// called with a compile-time-constant i so that callers can index register arrays with it.
 // ---------------------------------------------------------------------------------------------------
-template <int CL, typename Rec>
+template <int CL, typename Top, typename Lev>
 __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL], Float (&SU)[CL], Float (&SD)[CL],
-                                           Float albedo_sfc, Float src_sfc, Float flux_dn_top, Rec rec) {
+                                           Float albedo_sfc, Float src_sfc, Float flux_dn_top, Top top, Lev lev) {
   Float alb = albedo_sfc, src = src_sfc;  // :1166-1168
   for (int jj = kRegChunks - 1; jj >= 0; --jj) {
     const Float alb_b = __shfl_down_sync(0xffffffffu, alb, 1);
@@ -219,7 +270,7 @@ __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL]
   }
   // lane j == 0 now holds albedo and source at the top of the domain
   Float fdn = flux_dn_top;
-  if (j == 0) rec(-1, fdn * alb + src, fdn);  // :1190
+  if (j == 0) top(fdn * alb + src, fdn);  // :1190
   for (int jj = 0; jj < kRegChunks; ++jj) {
     const Float from_above = __shfl_up_sync(0xffffffffu, fdn, 1);
     if (j == jj) {
@@ -227,7 +278,7 @@ __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL]
 #pragma unroll
       for (int i = 0; i < CL; ++i) {  // :1196-1202
         fdn = T[i] * fdn + SD[i];
-        rec(i, fdn * R[i] + SU[i], fdn);
+        lev(i, fdn * R[i] + SU[i], fdn);
       }
     }
   }
@@ -248,12 +299,19 @@ struct SwRegParams {
 };
 
 template <int CL>
+__host__ __device__ constexpr int sw_reg_slots() { return 3 * CL + 4; }  // tau, ssa, g, alb_dir, alb_dif, inc_dir, inc_dif
+
+template <int CL, bool BB>
 __global__ void __launch_bounds__(kRegThreads, 3) sw_2stream_reg_kernel(const SwRegParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Float* sm = reinterpret_cast<Float*>(smem_raw);
+  constexpr int NS = sw_reg_slots<CL>();
+  Float* sm_mu0 = sm + (size_t)2 * NS * kRegThreads;  // [CL][thread], loaded once
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = lane >> 3, j = lane & 7;
   const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
   const bool col_ok = col_raw < p.ncol;
-  const size_t col = col_ok ? col_raw : p.ncol - 1;
+  const int col = col_ok ? col_raw : p.ncol - 1;
   const int nlay = p.nlay, nlev = nlay + 1;
   const size_t ncol = p.ncol, ncl = ncol * nlay, nclp = ncol * nlev;
   const RegOrient o{nlay, p.top_at_1};
@@ -262,29 +320,56 @@ __global__ void __launch_bounds__(kRegThreads, 3) sw_2stream_reg_kernel(const Sw
   const Float min_mu0 = sqrt(eps);        // :1006
   const int k0 = j * CL;
   const int gb = blockIdx.y * p.gpt_per_block, ge = min(p.ngpt, gb + p.gpt_per_block);
+  const int lay_step = p.top_at_1 ? p.ncol : -p.ncol;
+  const int off_lay0 = col + p.ncol * o.lay(min(k0, nlay - 1));
 
-  Float acc_up[CL], acc_dn[CL], acc_dir[CL];
+  auto prefetch = [&](int g, int s) {
+    const Float* tau_g = p.tau + ncl * g;
+    const Float* ssa_g = p.ssa + ncl * g;
+    const Float* g_g = p.g + ncl * g;
+#pragma unroll
+    for (int i = 0; i < CL; ++i) {
+      const int off = (k0 + i < nlay) ? off_lay0 + lay_step * i : off_lay0;
+      cp_async_f(RB_SLOT(sm, NS, s, i), tau_g + off);
+      cp_async_f(RB_SLOT(sm, NS, s, CL + i), ssa_g + off);
+      cp_async_f(RB_SLOT(sm, NS, s, 2 * CL + i), g_g + off);
+    }
+    const size_t gi = (size_t)col + ncol * g;
+    cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 0), p.sfc_alb_dir + gi);
+    cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 1), p.sfc_alb_dif + gi);
+    cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 2), p.inc_flux_dir + gi);
+    if (p.has_dif_bc) cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 3), p.inc_flux_dif + gi);
+  };
+
+  Float acc_up[BB ? CL : 1], acc_dn[BB ? CL : 1], acc_dir[BB ? CL : 1];
   Float acc_up_top = 0, acc_dn_top = 0, acc_dir_top = 0;
 #pragma unroll
-  for (int i = 0; i < CL; ++i) { acc_up[i] = 0; acc_dn[i] = 0; acc_dir[i] = 0; }
-  const Float mu0_top = p.mu0[col + ncol * o.lay(0)];
-  const Float mu0_sfc = p.mu0[col + ncol * o.lay(nlay - 1)];
+  for (int i = 0; i < (BB ? CL : 1); ++i) { acc_up[i] = 0; acc_dn[i] = 0; acc_dir[i] = 0; }
+
+  if (gb < ge) prefetch(gb, 0);
+  cp_async_commit();
+#pragma unroll
+  for (int i = 0; i < CL; ++i)
+    sm_mu0[i * kRegThreads + threadIdx.x] = p.mu0[(k0 + i < nlay) ? off_lay0 + lay_step * i : off_lay0];
+  const Float mu0_top = p.mu0[(size_t)col + ncol * o.lay(0)];
+  const Float mu0_sfc = p.mu0[(size_t)col + ncol * o.lay(nlay - 1)];
 
   for (int g = gb; g < ge; ++g) {
-    const size_t gi = col + ncol * g;
+    const int s = (g - gb) & 1;
+    if (g + 1 < ge) prefetch(g + 1, s ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
     Float* gup = p.flux_up + nclp * g;
     Float* gdn = p.flux_dn + nclp * g;
     Float* gdir = p.flux_dir + nclp * g;
     // ---------------- phase A: two-stream layer properties (:1027-1108) ----------------
-    Float R[CL], T[CL], A3[CL], A4[CL], A5[CL];  // Rdif, Tdif, Rdir->src_up, Tdir->src_dn, Tnoscat
+    Float R[CL], T[CL], A3[CL], A4[CL], A5[CL];  // Rdif, Tdif, Rdir->src_up, Tdir->src_dn, Tnoscat->direct flux
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
-      const int k = k0 + i;
-      if (k < nlay) {
-        const size_t i2 = col + ncol * o.lay(k);
-        const size_t i3 = i2 + ncl * g;
-        const Float tau_s = p.tau[i3], w0_s = p.ssa[i3], g_s = p.g[i3];
-        const Float mu0 = p.mu0[i2];
+      if (k0 + i < nlay) {
+        const Float tau_s = *RB_SLOT(sm, NS, s, i), w0_s = *RB_SLOT(sm, NS, s, CL + i),
+                    g_s = *RB_SLOT(sm, NS, s, 2 * CL + i);
+        const Float mu0 = sm_mu0[i * kRegThreads + threadIdx.x];
         const Float gamma1 = ((Float)8 - w0_s * ((Float)5 + (Float)3 * g_s)) * (Float).25;
         const Float gamma2 = (Float)3 * (w0_s * ((Float)1 - g_s)) * (Float).25;
         const Float kk = sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), min_k));
@@ -320,12 +405,14 @@ __global__ void __launch_bounds__(kRegThreads, 3) sw_2stream_reg_kernel(const Sw
         R[i] = 0; T[i] = 1; A3[i] = 0; A4[i] = 0; A5[i] = 1;
       }
     }
+    const Float alb_dir = *RB_SLOT(sm, NS, s, 3 * CL + 0), alb_dif = *RB_SLOT(sm, NS, s, 3 * CL + 1);
+    const Float dir_top_g = *RB_SLOT(sm, NS, s, 3 * CL + 2) * mu0_top;                  // :575
+    const Float dn_top = p.has_dif_bc ? *RB_SLOT(sm, NS, s, 3 * CL + 3) : (Float)0;     // :579-583
     // ---------------- phase B1: direct beam and its sources, :1110-1112 ----------------
-    Float dir = p.inc_flux_dir[gi] * mu0_top;  // :575
+    Float dir = dir_top_g;
     if (j == 0) {
-      acc_dir_top += dir;
-      acc_dn_top += dir;
-      if (!p.do_broadband && col_ok) gdir[col + ncol * o.lev(0)] = dir;
+      if (BB) { acc_dir_top += dir; acc_dn_top += dir; }
+      else if (col_ok) gdir[(size_t)col + ncol * o.lev(0)] = dir;
     }
     for (int jj = 0; jj < kRegChunks; ++jj) {
       const Float from_above = __shfl_up_sync(0xffffffffu, dir, 1);
@@ -338,84 +425,45 @@ __global__ void __launch_bounds__(kRegThreads, 3) sw_2stream_reg_kernel(const Sw
           A3[i] = s_up;
           A4[i] = s_dn;
           if (k0 + i < nlay) {
-            acc_dir[i] += dir;  // :604
-            acc_dn[i] += dir;   // direct part of :603
-            if (!p.do_broadband && col_ok) gdir[col + ncol * o.lev(k0 + i + 1)] = dir;
+            if (BB) { acc_dir[BB ? i : 0] += dir; acc_dn[BB ? i : 0] += dir; }  // :604, direct part of :603
+            else if (col_ok) gdir[(size_t)col + ncol * o.lev(k0 + i + 1)] = dir;
           }
           A5[i] = dir;  // direct flux below layer k0+i, for the g-point totals (:606)
         }
       }
     }
     // the lane of the last chunk holds the direct flux at the surface (:1120)
-    const Float src_sfc = (mu0_sfc > (Float)0) ? dir * p.sfc_alb_dir[gi] : (Float)0;
-    const Float dn_top = p.has_dif_bc ? p.inc_flux_dif[gi] : (Float)0;  // :579-583
-    const Float dir_top_g = p.inc_flux_dir[gi] * mu0_top;
-    // fluxes at the top level (lane j == 0 only)
-    auto rec_top = [&](Float fup, Float fdn) {
-      acc_up_top += fup;                                                     // :602
-      acc_dn_top += fdn;                                                     // diffuse part of :603
-      if (!p.do_broadband && col_ok) {
-        const size_t q = col + ncol * o.lev(0);
+    const Float src_sfc = (mu0_sfc > (Float)0) ? dir * alb_dir : (Float)0;
+    auto top = [&](Float fup, Float fdn) {
+      if (BB) { acc_up_top += fup; acc_dn_top += fdn; }                        // :602, diffuse part of :603
+      else if (col_ok) {
+        const size_t q = (size_t)col + ncol * o.lev(0);
         gup[q] = fup;
-        gdn[q] = fdn + dir_top_g;                                            // :606
+        gdn[q] = fdn + dir_top_g;                                             // :606
       }
     };
-    // adding (:1135-1245) with in-register accumulation; same algebra as adding_reg() above, written
-    // out here so the accumulator updates use static register indices
-    {
-      Float alb = p.sfc_alb_dif[gi], src = src_sfc;
-      for (int jj = kRegChunks - 1; jj >= 0; --jj) {
-        const Float alb_b = __shfl_down_sync(0xffffffffu, alb, 1);
-        const Float src_b = __shfl_down_sync(0xffffffffu, src, 1);
-        if (j == jj) {
-          if (jj < kRegChunks - 1) { alb = alb_b; src = src_b; }
-#pragma unroll
-          for (int i = CL - 1; i >= 0; --i) {  // :1174-1186
-            const Float r = R[i], t = T[i], sup = A3[i], sdn = A4[i];
-            const Float denom = (Float)1 / ((Float)1 - r * alb);
-            const Float a = t * denom;
-            R[i] = alb;
-            A3[i] = src;
-            T[i] = a;
-            A4[i] = (r * src + sdn) * denom;
-            const Float albn = r + t * t * alb * denom;
-            src = sup + a * (src + alb * sdn);
-            alb = albn;
-          }
-        }
+    auto lev = [&](int i, Float fup, Float fdn) {
+      if (k0 + i >= nlay) return;
+      if (BB) { acc_up[BB ? i : 0] += fup; acc_dn[BB ? i : 0] += fdn; }
+      else if (col_ok) {
+        const size_t q = (size_t)col + ncol * o.lev(k0 + i + 1);
+        gup[q] = fup;
+        gdn[q] = fdn + A5[i];                                                 // :606
       }
-      Float fdn = dn_top;
-      if (j == 0) rec_top(fdn * alb + src, fdn);  // :1190
-      for (int jj = 0; jj < kRegChunks; ++jj) {
-        const Float from_above = __shfl_up_sync(0xffffffffu, fdn, 1);
-        if (j == jj) {
-          if (jj > 0) fdn = from_above;
-#pragma unroll
-          for (int i = 0; i < CL; ++i) {  // :1196-1202
-            fdn = T[i] * fdn + A4[i];
-            const Float fup = fdn * R[i] + A3[i];
-            if (k0 + i < nlay) { acc_up[i] += fup; acc_dn[i] += fdn; }
-            if (!p.do_broadband && col_ok && k0 + i < nlay) {
-              const size_t q = col + ncol * o.lev(k0 + i + 1);
-              gup[q] = fup;
-              gdn[q] = fdn + A5[i];  // :606
-            }
-          }
-        }
-      }
-    }
+    };
+    adding_reg<CL>(j, R, T, A3, A4, alb_dif, src_sfc, dn_top, top, lev);
   }
-  if (p.do_broadband && col_ok) {
+  if (BB && col_ok) {
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
       const int klev = k0 + i + 1;
       if (klev <= nlay) {
-        const size_t o2 = col + ncol * o.lev(klev);
-        p.bb_up[o2] = acc_up[i]; p.bb_dn[o2] = acc_dn[i]; p.bb_dir[o2] = acc_dir[i];
+        const size_t o2 = (size_t)col + ncol * o.lev(klev);
+        p.bb_up[o2] = acc_up[BB ? i : 0]; p.bb_dn[o2] = acc_dn[BB ? i : 0]; p.bb_dir[o2] = acc_dir[BB ? i : 0];
       }
     }
     if (j == 0) {
-      const size_t o2 = col + ncol * o.lev(0);
+      const size_t o2 = (size_t)col + ncol * o.lev(0);
       p.bb_up[o2] = acc_up_top; p.bb_dn[o2] = acc_dn_top; p.bb_dir[o2] = acc_dir_top;
     }
   }
@@ -488,14 +536,19 @@ __global__ void __launch_bounds__(kRegThreads, 4) lw_2stream_reg_kernel(const Lw
       }
     }
     const Float emis = p.sfc_emis[gi];
-    auto rec = [&](int i, Float fup, Float fdn) {
-      const int klev = (i < 0) ? 0 : k0 + i + 1;
-      if (klev > nlay || !col_ok) return;
-      const size_t q = col + ncol * o.lev(klev);
+    auto top = [&](Float fup, Float fdn) {
+      if (!col_ok) return;
+      const size_t q = col + ncol * o.lev(0);
       gup[q] = fup;
       gdn[q] = fdn;
     };
-    adding_reg<CL>(j, R, T, SU, SD, (Float)1 - emis, pi * emis * p.sfc_src[gi], p.inc_flux[gi], rec);
+    auto lev = [&](int i, Float fup, Float fdn) {
+      if (k0 + i >= nlay || !col_ok) return;
+      const size_t q = col + ncol * o.lev(k0 + i + 1);
+      gup[q] = fup;
+      gdn[q] = fdn;
+    };
+    adding_reg<CL>(j, R, T, SU, SD, (Float)1 - emis, pi * emis * p.sfc_src[gi], p.inc_flux[gi], top, lev);
   }
 }
 
