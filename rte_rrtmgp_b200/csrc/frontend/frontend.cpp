@@ -11,7 +11,7 @@
 // Backend-agnostic by construction: this file only sequences extern "C" kernels (rte_kernels.h,
 // rrtmgp_kernels.h, rrtmgp_b200_ext.h) and never dereferences an array, so the SAME source is linked
 // (a) into librte_rrtmgp_b200.so against the CUDA kernels - the product - and (b) into the oracle's
-// liboracle.so against the CPU restatement - test infrastructure / CPU baseline.  That is the
+// CPU shared library, against the C restatement - test infrastructure / CPU baseline.  That is the
 // reference's own RTE_KERNEL_MODE idea (one frontend, interchangeable kernel providers).
 //
 // Differences from the Fortran frontend, all deliberate:
