@@ -120,12 +120,27 @@ struct TauAbsParams {
   int accumulate;  // 1: tau += (reference contract, caller pre-zeroes); 0: tau = (fused frontend)
 };
 
+// Table strides.  The k-distribution tables of rrtmgp-data all have ntemp = 14, neta = 9, npres+1 = 60;
+// with those as compile-time constants every one of the 16 x (gpts per band) table loads of a cell is
+// `base pointer + immediate` (no per-load 64-bit address arithmetic - the first version of this kernel spent
+// 55% of its issue slots on IMAD/LEA/IADD3, profiles/r1_prof_v1_tile_kernels.txt).  <0,0,0> = runtime dims.
+template <int NT, int NE, int NP1>
+struct TableDims {
+  int nt, ne, np1;
+  __device__ __forceinline__ TableDims(int ntemp, int neta, int npres) : nt(NT ? NT : ntemp), ne(NE ? NE : neta), np1(NP1 ? NP1 : npres + 1) {}
+  __device__ __forceinline__ int s_eta() const { return NT ? NT : nt; }
+  __device__ __forceinline__ int s_p() const { return (NT && NE) ? NT * NE : nt * ne; }
+  __device__ __forceinline__ int s_g() const { return (NT && NE && NP1) ? NT * NE * NP1 : nt * ne * np1; }
+};
+
+template <int NT, int NE, int NP1>
 __device__ __forceinline__ void minor_contrib(const MinorTables& m, const int itropo, const TauAbsParams& p,
-                                              size_t c, size_t ncl, int gS, int gE, Float (&acc)[kMaxG]) {
+                                              const TableDims<NT, NE, NP1>& td, size_t c, size_t ncl, int gS,
+                                              int gE, Float (&acc)[kMaxG]) {
   // chunk covers 1-based g-points gS..gE
   const Float play = p.play[c], tlay = p.tlay[c];
   const int jtemp = p.jtemp[c];
-  const size_t s_eta = (size_t)p.ntemp, s_k = (size_t)p.ntemp * p.neta;
+  const int s_eta = td.s_eta(), s_k = td.s_p();
   for (int imnr = 0; imnr < m.nminor; ++imnr) {
     const int mS = __ldg(m.limits_gpt + 2 * imnr), mE = __ldg(m.limits_gpt + 2 * imnr + 1);
     if (mE < gS || mS > gE) continue;
@@ -148,14 +163,15 @@ __device__ __forceinline__ void minor_contrib(const MinorTables& m, const int it
     const Float2 f01 = reinterpret_cast<const Float2*>(p.fminor)[2 * cf];
     const Float2 f23 = reinterpret_cast<const Float2*>(p.fminor)[2 * cf + 1];
     const int2 je = reinterpret_cast<const int2*>(p.jeta)[cf];
-    const int kstart = __ldg(m.kminor_start + imnr);
-    const Float* k0 = m.kminor + (size_t)(jtemp - 1) + s_eta * (size_t)(je.x - 1);
-    const Float* k1 = m.kminor + (size_t)jtemp + s_eta * (size_t)(je.y - 1);
+    // table column of chunk slot i is kstart + (gS + i - mS) - 1 = kcol0 + i
+    const long long kcol0 = (long long)__ldg(m.kminor_start + imnr) + (gS - mS) - 1;
+    const Float* k0 = m.kminor + (jtemp - 1) + s_eta * (je.x - 1) + (long long)s_k * kcol0;
+    const Float* k1 = m.kminor + jtemp + s_eta * (je.y - 1) + (long long)s_k * kcol0;
 #pragma unroll
     for (int i = 0; i < kMaxG; ++i) {
       const int g = gS + i;
       if (g >= mS && g <= mE && g <= gE) {
-        const size_t ko = s_k * (size_t)(kstart + (g - mS) - 1);
+        const int ko = s_k * i;
         const Float kint = f01.x * __ldg(k0 + ko) + f01.y * __ldg(k0 + ko + s_eta) +
                            f23.x * __ldg(k1 + ko) + f23.y * __ldg(k1 + ko + s_eta);          // :757-760
         acc[i] = acc[i] + scaling * kint;                                                   // :493
@@ -164,10 +180,13 @@ __device__ __forceinline__ void minor_contrib(const MinorTables& m, const int it
   }
 }
 
+template <int NT, int NE, int NP1>
 __global__ void __launch_bounds__(kCellThreads, 4) tau_absorption_kernel(const TauAbsParams p) {
   const size_t ncl = (size_t)p.ncol * p.nlay;
   const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncl) return;
+  const TableDims<NT, NE, NP1> td(p.ntemp, p.neta, p.npres);
+  const int s_eta = td.s_eta(), s_p = td.s_p(), s_g = td.s_g();
   const int ibnd = blockIdx.y;
   const int bS = __ldg(p.band_lims_gpt + 2 * ibnd), bE = __ldg(p.band_lims_gpt + 2 * ibnd + 1);
   const bool tropo = p.tropo[c];
@@ -180,35 +199,34 @@ __global__ void __launch_bounds__(kCellThreads, 4) tau_absorption_kernel(const T
   const int2 je = reinterpret_cast<const int2*>(p.jeta)[cf];
   const int jtemp = p.jtemp[c];
   const int jpress = p.jpress[c] + itropo + 1;  // :390 jpress + itropo (itropo 1/2 in the reference)
-  const size_t s_eta = (size_t)p.ntemp, s_p = (size_t)p.ntemp * p.neta, s_g = s_p * (size_t)(p.npres + 1);
-  // k(jtemp, jeta1, jpress-1, g) and k(jtemp+1, jeta2, jpress-1, g)
-  const Float* k0 = p.kmajor + (size_t)(jtemp - 1) + s_eta * (size_t)(je.x - 1) + s_p * (size_t)(jpress - 2);
-  const Float* k1 = p.kmajor + (size_t)jtemp + s_eta * (size_t)(je.y - 1) + s_p * (size_t)(jpress - 2);
   for (int gS = bS; gS <= bE; gS += kMaxG) {
     const int gE = min(bE, gS + kMaxG - 1);
+    // k(jtemp, jeta1, jpress-1, gS) and k(jtemp+1, jeta2, jpress-1, gS): everything else is an immediate
+    const Float* k0 = p.kmajor + (jtemp - 1) + s_eta * (je.x - 1) + s_p * (jpress - 2) + (long long)s_g * (gS - 1);
+    const Float* k1 = p.kmajor + jtemp + s_eta * (je.y - 1) + s_p * (jpress - 2) + (long long)s_g * (gS - 1);
+    Float* tau_c = p.tau + c + ncl * (size_t)(gS - 1);
     Float acc[kMaxG];
 #pragma unroll
     for (int i = 0; i < kMaxG; ++i) {
-      const int g = gS + i;
-      if (g <= gE) {
-        const size_t go = s_g * (size_t)(g - 1);
+      if (gS + i <= gE) {
+        const int go = s_g * i;
         // interpolate3D_byflav :791-801, same association
         const Float major =
             cm.x * (f0.x * __ldg(k0 + go) + f0.y * __ldg(k0 + go + s_eta) +
                     f1.x * __ldg(k0 + go + s_p) + f1.y * __ldg(k0 + go + s_p + s_eta)) +
             cm.y * (f2.x * __ldg(k1 + go) + f2.y * __ldg(k1 + go + s_eta) +
                     f3.x * __ldg(k1 + go + s_p) + f3.y * __ldg(k1 + go + s_p + s_eta));
-        const Float t0 = p.accumulate ? p.tau[c + ncl * (size_t)(g - 1)] : (Float)0;
+        const Float t0 = p.accumulate ? tau_c[ncl * i] : (Float)0;
         acc[i] = t0 + major;                                                                 // :391
       } else {
         acc[i] = 0;
       }
     }
-    if (tropo) minor_contrib(p.lower, 0, p, c, ncl, gS, gE, acc);
-    else       minor_contrib(p.upper, 1, p, c, ncl, gS, gE, acc);
+    if (tropo) minor_contrib(p.lower, 0, p, td, c, ncl, gS, gE, acc);
+    else       minor_contrib(p.upper, 1, p, td, c, ncl, gS, gE, acc);
 #pragma unroll
     for (int i = 0; i < kMaxG; ++i)
-      if (gS + i <= gE) p.tau[c + ncl * (size_t)(gS + i - 1)] = acc[i];
+      if (gS + i <= gE) tau_c[ncl * i] = acc[i];
   }
 }
 
@@ -272,15 +290,17 @@ __device__ __forceinline__ Float planck_band(const PlanckParams& p, Float T, Flo
   return t0 + frac * (t1 - t0);
 }
 
+template <int NT, int NE, int NP1>
 __global__ void __launch_bounds__(kCellThreads, 4) planck_source_kernel(const PlanckParams p) {
   const int icol = blockIdx.x * blockDim.x + threadIdx.x;
   if (icol >= p.ncol) return;
+  const TableDims<NT, NE, NP1> td(p.ntemp, p.neta, p.npres);
+  const int s_eta = td.s_eta(), s_p = td.s_p(), s_g = td.s_g();
   const int ibnd = blockIdx.y;
   const size_t ncol = p.ncol, ncl = ncol * p.nlay, nclp = ncol * (p.nlay + 1);
   const int bS = __ldg(p.band_lims_gpt + 2 * ibnd), bE = __ldg(p.band_lims_gpt + 2 * ibnd + 1);
   const Float delta_r = (Float)1.0 / p.totplnk_delta;  // :636
   const Float* tab = p.totplnk + (size_t)p.nPlanckTemp * ibnd;
-  const size_t s_eta = (size_t)p.ntemp, s_p = (size_t)p.ntemp * p.neta, s_g = s_p * (size_t)(p.npres + 1);
   for (int gS = bS; gS <= bE; gS += kMaxG) {
     const int gE = min(bE, gS + kMaxG - 1);
     Float pf_prev[kMaxG];
@@ -296,8 +316,8 @@ __global__ void __launch_bounds__(kCellThreads, 4) planck_source_kernel(const Pl
       const int2 je = reinterpret_cast<const int2*>(p.jeta)[cf];
       const int jtemp = p.jtemp[c];
       const int jpress = p.jpress[c] + itropo + 1;  // :630
-      const Float* k0 = p.pfracin + (size_t)(jtemp - 1) + s_eta * (size_t)(je.x - 1) + s_p * (size_t)(jpress - 2);
-      const Float* k1 = p.pfracin + (size_t)jtemp + s_eta * (size_t)(je.y - 1) + s_p * (size_t)(jpress - 2);
+      const Float* k0 = p.pfracin + (jtemp - 1) + s_eta * (je.x - 1) + s_p * (jpress - 2) + (long long)s_g * (gS - 1);
+      const Float* k1 = p.pfracin + jtemp + s_eta * (je.y - 1) + s_p * (jpress - 2) + (long long)s_g * (gS - 1);
       const Float B_lay = planck_band(p, p.tlay[c], delta_r, tab);          // :661
       const Float B_lev = planck_band(p, p.tlev[c], delta_r, tab);          // :683 (level ilay)
       const bool is_sfc = (ilay == p.sfc_lay - 1);
@@ -307,22 +327,22 @@ __global__ void __launch_bounds__(kCellThreads, 4) planck_source_kernel(const Pl
         B_sfc = planck_band(p, ts, delta_r, tab);
         B_sfc1 = planck_band(p, ts + (Float)1.0, delta_r, tab);
       }
+      Float* lay_c = p.lay_src + c + ncl * (size_t)(gS - 1);
+      Float* lev_c = p.lev_src + c + nclp * (size_t)(gS - 1);
 #pragma unroll
       for (int i = 0; i < kMaxG; ++i) {
-        const int g = gS + i;
-        if (g <= gE) {
-          const size_t go = s_g * (size_t)(g - 1);
+        if (gS + i <= gE) {
+          const int go = s_g * i;
           // interpolate3D_byflav with scaling = (1,1) :627-631
           const Float pf = (Float)1 * (f0.x * __ldg(k0 + go) + f0.y * __ldg(k0 + go + s_eta) +
                                        f1.x * __ldg(k0 + go + s_p) + f1.y * __ldg(k0 + go + s_p + s_eta)) +
                            (Float)1 * (f2.x * __ldg(k1 + go) + f2.y * __ldg(k1 + go + s_eta) +
                                        f3.x * __ldg(k1 + go + s_p) + f3.y * __ldg(k1 + go + s_p + s_eta));
-          p.lay_src[c + ncl * (size_t)(g - 1)] = pf * B_lay;                                  // :674
-          const Float lev = (ilay == 0) ? pf * B_lev : sqrt(pf_prev[i] * pf) * B_lev;         // :695,699
-          p.lev_src[c + nclp * (size_t)(g - 1)] = lev;
+          lay_c[ncl * i] = pf * B_lay;                                                         // :674
+          lev_c[nclp * i] = (ilay == 0) ? pf * B_lev : sqrt(pf_prev[i] * pf) * B_lev;          // :695,699
           if (is_sfc) {                                                                        // :651-653
-            p.sfc_src[icol + ncol * (size_t)(g - 1)] = pf * B_sfc;
-            p.sfc_source_Jac[icol + ncol * (size_t)(g - 1)] = pf * (B_sfc1 - B_sfc);
+            p.sfc_src[icol + ncol * (size_t)(gS + i - 1)] = pf * B_sfc;
+            p.sfc_source_Jac[icol + ncol * (size_t)(gS + i - 1)] = pf * (B_sfc1 - B_sfc);
           }
           pf_prev[i] = pf;
         }
@@ -418,7 +438,8 @@ void tau_absorption_impl(int ncol, int nlay, int nbnd, int ngpt, int ngas, int n
   p.accumulate = accumulate ? 1 : 0;
   dim3 grid(ceil_div((long long)ncl, kCellThreads), nbnd);
   KernelTimer timer("tau_absorption");
-  tau_absorption_kernel<<<grid, kCellThreads, 0, stream()>>>(p);
+  if (ntemp == 14 && neta == 9 && npres == 59) tau_absorption_kernel<14, 9, 60><<<grid, kCellThreads, 0, stream()>>>(p);
+  else tau_absorption_kernel<0, 0, 0><<<grid, kCellThreads, 0, stream()>>>(p);
   RB_LAUNCH_CHECK();
 }
 
@@ -544,7 +565,8 @@ void rrtmgp_compute_Planck_source(const int* ncol, const int* nlay, const int* n
   p.sfc_src = o_sfc; p.lay_src = o_lay; p.lev_src = o_lev; p.sfc_source_Jac = o_jac;
   dim3 grid(ceil_div(*ncol, kCellThreads), *nbnd);
   KernelTimer timer("planck_source");
-  planck_source_kernel<<<grid, kCellThreads, 0, stream()>>>(p);
+  if (*ntemp == 14 && *neta == 9 && *npres == 59) planck_source_kernel<14, 9, 60><<<grid, kCellThreads, 0, stream()>>>(p);
+  else planck_source_kernel<0, 0, 0><<<grid, kCellThreads, 0, stream()>>>(p);
   RB_LAUNCH_CHECK();
 }
 

@@ -84,8 +84,9 @@ class Context:
         return a if self.device is None else to_device(a, self.device)
 
     def get(self, a):
+        """Host copy (always a fresh array, so results of successive calls never alias)."""
         self.lib.sync()
-        return to_host(a)
+        return np.array(to_host(a), order="F", copy=True)
 
     def config_checks(self, extents=True, values=True):
         """rte_config_checks(), rte/frontend/mo_rte_config.F90:29-49"""
