@@ -55,6 +55,11 @@ def algorithmic_bytes(ncol, nlay, ngpt_lw, ngpt_sw, nbnd_lw, nbnd_sw, nflav_lw, 
     out["lw_noscat_kernel"] = P * (3 + 1.0 / L) + 4 * N * ngpt_lw * w + 2 * N * (L + 1) * w
     out["lw_noscat_reg_kernel"] = out["lw_noscat_kernel"]
     out["rte_inc_1scalar_by_1scalar_bybnd"] = 2 * P
+    # fused gas optics: charged only what the API makes externally visible
+    small_in = N * L * (4 + ngas) * w  # play, plev, tlay, vmr
+    out["gas_tau_fused[lw]"] = small_in + N * L * nbnd_lw * w + P
+    out["planck_fused"] = small_in + P * (2 + 1.0 / L) + 2 * N * ngpt_lw * w
+    out["gas_tau_fused[sw]"] = small_in + 3 * N * L * nbnd_sw * w + 3 * planes(ngpt_sw)
     P = planes(ngpt_sw)
     out["tau_rayleigh"] = N * L * (4 * nflav_sw * w + 2 * nflav_sw * i4 + i4 + b1 + (1 + S) * w) + P
     out["rrtmgpb_combine_abs_and_rayleigh"] = 5 * P

@@ -116,6 +116,41 @@ void rrtmgpb_compute_tau_absorption_assign(
     const Bool* tropo, const Float* col_mix, const Float* fmajor, const Float* fminor, const Float* play,
     const Float* tlay, const Float* col_gas, const int* jeta, const int* jtemp, const int* jpress, Float* tau);
 
+/* Whole gas_optics() call fused: col_dry, col_gas, interpolation, absorption (major +
+ * minor), Rayleigh + combination (when krayl != NULL), the by-band cloud increment (cld_kind 0 none / 1 1scl /
+ * 2 2str; cloud arrays (ncol,nlay,nbnd) on the SAME bands) and - when lay_src != NULL - the Planck sources.
+ * Only the caller-visible arrays are written: tau[,ssa,g] (op_kind 1 / 2) and the four source arrays; no
+ * intermediate of the reference sequence is materialised.  All table pointers in `t` are BACKEND memory. */
+typedef struct {
+  int ngas, nflav, neta, npres, ntemp, nbnd, ngpt;
+  int nminorlower, nminorklower, nminorupper, nminorkupper, idx_h2o;
+  const int *flavor, *gpoint_flavor, *band_lims_gpt, *gpoint_bands;
+  const Float *press_ref_log, *temp_ref, *vmr_ref;
+  Float press_ref_log_delta, temp_ref_min, temp_ref_delta, press_ref_trop_log;
+  const Float *kmajor, *kminor_lower, *kminor_upper;
+  const int *minor_limits_gpt_lower, *minor_limits_gpt_upper;
+  const Bool *minor_scales_with_density_lower, *minor_scales_with_density_upper;
+  const Bool *scale_by_complement_lower, *scale_by_complement_upper;
+  const int *idx_minor_lower, *idx_minor_upper, *idx_minor_scaling_lower, *idx_minor_scaling_upper;
+  const int *kminor_start_lower, *kminor_start_upper;
+  const Float* krayl;                  /* NULL: no Rayleigh scattering (LW) */
+  const Float *planck_frac, *totplnk;  /* NULL for SW */
+  int nPlanckTemp;
+  Float totplnk_delta;
+} rrtmgpb_gas_tables;
+
+/* 1: stage the k-distribution / Planck-fraction table boxes to shared memory with TMA (cp.async.bulk.tensor)
+ * in the fused gas-optics kernels; 0 (default): read them through the read-only global path.
+ * RRTMGPB_TMA=1 in the environment turns staging on at start-up. */
+void rrtmgpb_set_tma_staging(int on);
+
+void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, const Float* play, const Float* plev,
+                              const Float* tlay, const Float* vmr, const Float* col_dry /* or NULL */, int op_kind,
+                              Float* tau, Float* ssa, Float* g, int cld_kind, const Float* cld_tau,
+                              const Float* cld_ssa, const Float* cld_g, const Float* tlev, const Float* tsfc,
+                              int sfc_lay, Float* sfc_src, Float* lay_src /* NULL: no sources */, Float* lev_src,
+                              Float* sfc_source_Jac);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,19 @@ int rrtmgpb_gas_optics_ext(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, c
                            const Float* tlay, const Float* vmr, rrtmgpb_optical_props* optical_props,
                            Float* toa_src, const Float* col_dry, char* errmsg);
 
+/* Fused fast path (not in the reference API): gas_optics() followed by clouds%increment(optical_props) in ONE
+ * pass that writes only the caller-visible arrays.  `clouds` (by-band, same bands; 1scl or 2str; already
+ * delta-scaled if the caller wants that) may be NULL.  Results equal the two separate calls to rounding. */
+int rrtmgpb_gas_optics_int_fused(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play,
+                                 const Float* plev, const Float* tlay, const Float* tsfc, const Float* vmr,
+                                 rrtmgpb_optical_props* optical_props, rrtmgpb_source_func_lw* sources,
+                                 const Float* col_dry, const Float* tlev, const rrtmgpb_optical_props* clouds,
+                                 char* errmsg);
+int rrtmgpb_gas_optics_ext_fused(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play,
+                                 const Float* plev, const Float* tlay, const Float* vmr,
+                                 rrtmgpb_optical_props* optical_props, Float* toa_src, const Float* col_dry,
+                                 const rrtmgpb_optical_props* clouds, char* errmsg);
+
 /* ---------------- ty_cloud_optics_rrtmgp (LUT form) ---------------- */
 typedef struct {
   int nbnd, nsize_liq, nsize_ice, nrghice, icergh;

@@ -25,6 +25,7 @@ void rrtmgpb_set_device(int d) { (void)d; }
 void rrtmgpb_sync(void) {}
 long long rrtmgpb_launch_count(int reset) { (void)reset; return 0; }
 void rrtmgpb_set_solver_variant(int v) { (void)v; }
+void rrtmgpb_set_tma_staging(int on) { (void)on; }
 void rrtmgpb_profile_enable(int on) { (void)on; }
 int rrtmgpb_profile_report(char* buf, size_t n) { if (buf && n) buf[0] = 0; return 0; }
 void rrtmgpb_set_lw_2stream_lev_source_per_gpt(int on) { oracle_set_lw_2stream_lev_source_per_gpt(on); }
@@ -158,4 +159,57 @@ void rrtmgpb_compute_tau_absorption_assign(
                                 idx_minor_upper, idx_minor_scaling_lower, idx_minor_scaling_upper,
                                 kminor_start_lower, kminor_start_upper, tropo, col_mix, fmajor, fminor, play,
                                 tlay, col_gas, jeta, jtemp, jpress, tau);
+}
+
+/* rrtmgpb_gas_optics_fused on the oracle = the reference's own sequence, kernel by kernel
+ * (mo_gas_optics_rrtmgp.F90:578-745,893-928 and the driver's clouds%increment(atmos)). */
+void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, const Float* play, const Float* plev,
+                              const Float* tlay, const Float* vmr, const Float* col_dry, int op_kind, Float* tau,
+                              Float* ssa, Float* g, int cld_kind, const Float* cld_tau, const Float* cld_ssa,
+                              const Float* cld_g, const Float* tlev, const Float* tsfc, int sfc_lay, Float* sfc_src,
+                              Float* lay_src, Float* lev_src, Float* sfc_source_Jac) {
+  const size_t ncl = (size_t)ncol * nlay, nf = (size_t)t->nflav;
+  const int ngpt = t->ngpt, nbnd = t->nbnd;
+  Float* cd = malloc(sizeof(Float) * ncl);
+  if (col_dry) memcpy(cd, col_dry, sizeof(Float) * ncl);
+  else rrtmgpb_get_col_dry(ncol, nlay, vmr + ncl * (size_t)(t->idx_h2o - 1), plev, cd);
+  Float* col_gas = malloc(sizeof(Float) * ncl * (t->ngas + 1));
+  rrtmgpb_col_gas_from_vmr(ncol, nlay, t->ngas, vmr, cd, col_gas);
+  int* jtemp = malloc(sizeof(int) * ncl); int* jpress = malloc(sizeof(int) * ncl);
+  int* jeta = malloc(sizeof(int) * 2 * ncl * nf); Bool* tropo = malloc(sizeof(Bool) * ncl);
+  Float* fmajor = malloc(sizeof(Float) * 8 * ncl * nf); Float* fminor = malloc(sizeof(Float) * 4 * ncl * nf);
+  Float* col_mix = malloc(sizeof(Float) * 2 * ncl * nf);
+  rrtmgp_interpolation(&ncol, &nlay, &t->ngas, &t->nflav, &t->neta, &t->npres, &t->ntemp, t->flavor, t->press_ref_log,
+                       t->temp_ref, &t->press_ref_log_delta, &t->temp_ref_min, &t->temp_ref_delta,
+                       &t->press_ref_trop_log, t->vmr_ref, play, tlay, col_gas, jtemp, fmajor, fminor, col_mix, tropo,
+                       jeta, jpress);
+  rrtmgpb_compute_tau_absorption_assign(
+      ncol, nlay, nbnd, ngpt, t->ngas, t->nflav, t->neta, t->npres, t->ntemp, t->nminorlower, t->nminorklower,
+      t->nminorupper, t->nminorkupper, t->idx_h2o, t->gpoint_flavor, t->band_lims_gpt, t->kmajor, t->kminor_lower,
+      t->kminor_upper, t->minor_limits_gpt_lower, t->minor_limits_gpt_upper, t->minor_scales_with_density_lower,
+      t->minor_scales_with_density_upper, t->scale_by_complement_lower, t->scale_by_complement_upper,
+      t->idx_minor_lower, t->idx_minor_upper, t->idx_minor_scaling_lower, t->idx_minor_scaling_upper,
+      t->kminor_start_lower, t->kminor_start_upper, tropo, col_mix, fmajor, fminor, play, tlay, col_gas, jeta, jtemp,
+      jpress, tau);
+  if (t->krayl) {
+    Float* tr = malloc(sizeof(Float) * ncl * ngpt);
+    rrtmgp_compute_tau_rayleigh(&ncol, &nlay, &nbnd, &ngpt, &t->ngas, &t->nflav, &t->neta, &t->npres, &t->ntemp,
+                                t->gpoint_flavor, t->band_lims_gpt, t->krayl, &t->idx_h2o, cd, col_gas, fminor, jeta,
+                                tropo, jtemp, tr);
+    rrtmgpb_combine_abs_and_rayleigh(ncol, nlay, ngpt, op_kind, tau, tr, tau, ssa, g);
+    free(tr);
+  } else if (op_kind == 2) {
+    zero_array_3D(&ncol, &nlay, &ngpt, ssa);
+    zero_array_3D(&ncol, &nlay, &ngpt, g);
+  }
+  if (cld_kind == 1 && op_kind == 1) rte_inc_1scalar_by_1scalar_bybnd(&ncol, &nlay, &ngpt, tau, cld_tau, &nbnd, t->band_lims_gpt);
+  if (cld_kind == 2 && op_kind == 1) rte_inc_1scalar_by_2stream_bybnd(&ncol, &nlay, &ngpt, tau, cld_tau, cld_ssa, &nbnd, t->band_lims_gpt);
+  if (cld_kind == 1 && op_kind == 2) rte_inc_2stream_by_1scalar_bybnd(&ncol, &nlay, &ngpt, tau, ssa, cld_tau, &nbnd, t->band_lims_gpt);
+  if (cld_kind == 2 && op_kind == 2) rte_inc_2stream_by_2stream_bybnd(&ncol, &nlay, &ngpt, tau, ssa, g, cld_tau, cld_ssa, cld_g, &nbnd, t->band_lims_gpt);
+  if (lay_src)
+    rrtmgp_compute_Planck_source(&ncol, &nlay, &nbnd, &ngpt, &t->nflav, &t->neta, &t->npres, &t->ntemp, &t->nPlanckTemp,
+                                 tlay, tlev, tsfc, &sfc_lay, fmajor, jeta, tropo, jtemp, jpress, t->gpoint_bands,
+                                 t->band_lims_gpt, t->planck_frac, &t->temp_ref_min, &t->totplnk_delta, t->totplnk,
+                                 t->gpoint_flavor, sfc_src, lay_src, lev_src, sfc_source_Jac);
+  free(cd); free(col_gas); free(jtemp); free(jpress); free(jeta); free(tropo); free(fmajor); free(fminor); free(col_mix);
 }

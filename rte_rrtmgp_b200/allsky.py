@@ -4,6 +4,8 @@ set up as in :193-311 (analytic RCEMIP-like profile replicated over ncol, ocean-
 clouds in 2/3 of the columns).  Backend-agnostic: `ctx` decides whether arrays are CUDA tensors driving
 the product library or numpy arrays driving the CPU oracle (tests / CPU baseline only).
 """
+import os
+
 import numpy as np
 
 from . import synthetic as syn
@@ -12,8 +14,10 @@ from .frontend import (CloudOptics, FluxesBroadband, GasOptics, OpticalProps, So
 
 class AllSky:
     def __init__(self, ctx, ncol, nlay, kd_lw=None, kd_sw=None, do_clouds=True, profiles=None, col_offset=0,
-                 mu0=0.86, sfc_alb=0.06, emis=0.98):
-        self.ctx, self.ncol, self.nlay = ctx, ncol, nlay
+                 mu0=0.86, sfc_alb=0.06, emis=0.98, fused=None):
+        if fused is None:  # the express path; off by default until it beats the kernel-by-kernel sequence
+            fused = os.environ.get("RRTMGPB_FUSED", "0") == "1"
+        self.ctx, self.ncol, self.nlay, self.fused = ctx, ncol, nlay, fused
         prof = profiles if profiles is not None else syn.compute_profiles(300.0, ncol, nlay)
         self.host_inputs = {}
         vmr = syn.allsky_gas_vmrs(prof)
@@ -70,10 +74,15 @@ class AllSky:
         lw = self.lw
         if self.do_clouds:
             lw.co.cloud_optics(self.lwp, self.iwp, self.rel, self.dei, lw.clouds)
-        lw.go.gas_optics(self.p_lay, self.p_lev, self.t_lay, self.vmr, lw.atmos, t_sfc=lw.t_sfc, sources=lw.sources,
-                         tlev=self.t_lev)
-        if self.do_clouds:
-            lw.clouds.increment(lw.atmos)
+        if self.fused:  # gas optics + clouds%increment(atmos) in one pass (same caller-visible results)
+            lw.go.gas_optics(self.p_lay, self.p_lev, self.t_lay, self.vmr, lw.atmos, t_sfc=lw.t_sfc,
+                             sources=lw.sources, tlev=self.t_lev, fused=True,
+                             increment_by=lw.clouds if self.do_clouds else None)
+        else:
+            lw.go.gas_optics(self.p_lay, self.p_lev, self.t_lay, self.vmr, lw.atmos, t_sfc=lw.t_sfc,
+                             sources=lw.sources, tlev=self.t_lev)
+            if self.do_clouds:
+                lw.clouds.increment(lw.atmos)
         rte_lw(self.ctx, lw.atmos, lw.sources, lw.emis_sfc, lw.fluxes)
 
     # -- SW branch (rrtmgp_allsky.F90:340-352,383-406)
@@ -81,10 +90,15 @@ class AllSky:
         sw = self.sw
         if self.do_clouds:
             sw.co.cloud_optics(self.lwp, self.iwp, self.rel, self.dei, sw.clouds)
-        sw.go.gas_optics(self.p_lay, self.p_lev, self.t_lay, self.vmr, sw.atmos, toa_src=sw.toa_flux)
         if self.do_clouds:
             sw.clouds.delta_scale()
-            sw.clouds.increment(sw.atmos)
+        if self.fused:
+            sw.go.gas_optics(self.p_lay, self.p_lev, self.t_lay, self.vmr, sw.atmos, toa_src=sw.toa_flux, fused=True,
+                             increment_by=sw.clouds if self.do_clouds else None)
+        else:
+            sw.go.gas_optics(self.p_lay, self.p_lev, self.t_lay, self.vmr, sw.atmos, toa_src=sw.toa_flux)
+            if self.do_clouds:
+                sw.clouds.increment(sw.atmos)
         rte_sw(self.ctx, sw.atmos, sw.mu0, sw.toa_flux, sw.sfc_alb_dir, sw.sfc_alb_dif, sw.fluxes)
 
     def step(self):

@@ -20,7 +20,7 @@ using namespace rrtmgpb;
 namespace {
 
 constexpr int kCellThreads = 128;
-constexpr int kMaxG = 16;  // g-points handled per register chunk (bands wider than this are chunked)
+constexpr int kMaxG = 8;   // g-points handled per register chunk (wider bands are walked in chunks; 8 keeps the kernels at 64 registers = 32 warps/SM)
 
 // ------------------------------------------------------------------------------------------
 // interpolation: mo_gas_optics_rrtmgp_kernels.F90:37-170
@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(kCellThreads) interpolation_kernel(const Inter
 // ------------------------------------------------------------------------------------------
 struct MinorTables {
   int nminor;
+  const int2* band_range;  // per band: [first, last] contributor whose g-point range touches the band (last < first: none)
   const Float* kminor;
   const int *limits_gpt, *idx_minor, *idx_scaling, *kminor_start;
   const Bool *scales_with_density, *scale_by_complement;
@@ -135,13 +136,16 @@ struct TableDims {
 
 template <int NT, int NE, int NP1>
 __device__ __forceinline__ void minor_contrib(const MinorTables& m, const int itropo, const TauAbsParams& p,
-                                              const TableDims<NT, NE, NP1>& td, size_t c, size_t ncl, int gS,
-                                              int gE, Float (&acc)[kMaxG]) {
+                                              const TableDims<NT, NE, NP1>& td, size_t c, size_t ncl, int ibnd,
+                                              int gS, int gE, Float (&acc)[kMaxG]) {
   // chunk covers 1-based g-points gS..gE
   const Float play = p.play[c], tlay = p.tlay[c];
   const int jtemp = p.jtemp[c];
   const int s_eta = td.s_eta(), s_k = td.s_p();
-  for (int imnr = 0; imnr < m.nminor; ++imnr) {
+  // only the contributors that touch this band (scanning all ~30-60 of them per chunk was the longest
+  // dependent-load chain of the first version of this kernel)
+  const int2 range = m.band_range[ibnd];
+  for (int imnr = range.x; imnr <= range.y; ++imnr) {
     const int mS = __ldg(m.limits_gpt + 2 * imnr), mE = __ldg(m.limits_gpt + 2 * imnr + 1);
     if (mE < gS || mS > gE) continue;
     Float scaling = p.col_gas[c + ncl * __ldg(m.idx_minor + imnr)];                       // :461
@@ -181,7 +185,7 @@ __device__ __forceinline__ void minor_contrib(const MinorTables& m, const int it
 }
 
 template <int NT, int NE, int NP1>
-__global__ void __launch_bounds__(kCellThreads, 4) tau_absorption_kernel(const TauAbsParams p) {
+__global__ void __launch_bounds__(kCellThreads, 6) tau_absorption_kernel(const TauAbsParams p) {
   const size_t ncl = (size_t)p.ncol * p.nlay;
   const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncl) return;
@@ -222,8 +226,8 @@ __global__ void __launch_bounds__(kCellThreads, 4) tau_absorption_kernel(const T
         acc[i] = 0;
       }
     }
-    if (tropo) minor_contrib(p.lower, 0, p, td, c, ncl, gS, gE, acc);
-    else       minor_contrib(p.upper, 1, p, td, c, ncl, gS, gE, acc);
+    if (tropo) minor_contrib(p.lower, 0, p, td, c, ncl, ibnd, gS, gE, acc);
+    else       minor_contrib(p.upper, 1, p, td, c, ncl, ibnd, gS, gE, acc);
 #pragma unroll
     for (int i = 0; i < kMaxG; ++i)
       if (gS + i <= gE) tau_c[ncl * i] = acc[i];
@@ -291,7 +295,7 @@ __device__ __forceinline__ Float planck_band(const PlanckParams& p, Float T, Flo
 }
 
 template <int NT, int NE, int NP1>
-__global__ void __launch_bounds__(kCellThreads, 4) planck_source_kernel(const PlanckParams p) {
+__global__ void __launch_bounds__(kCellThreads, 8) planck_source_kernel(const PlanckParams p) {
   const int icol = blockIdx.x * blockDim.x + threadIdx.x;
   if (icol >= p.ncol) return;
   const TableDims<NT, NE, NP1> td(p.ntemp, p.neta, p.npres);
@@ -396,6 +400,20 @@ __global__ void __launch_bounds__(kCellThreads) cld_from_table_kernel(const CldP
   }
 }
 
+// per band: first/last minor contributor whose g-point range intersects the band
+__global__ void minor_band_ranges_kernel(int nbnd, const int* band_lims_gpt, int nminor, const int* limits_gpt,
+                                         int2* out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbnd) return;
+  const int bS = band_lims_gpt[2 * b], bE = band_lims_gpt[2 * b + 1];
+  int first = nminor, last = -1;
+  for (int i = 0; i < nminor; ++i) {
+    const int mS = limits_gpt[2 * i], mE = limits_gpt[2 * i + 1];
+    if (mE >= bS && mS <= bE) { first = min(first, i); last = max(last, i); }
+  }
+  out[b] = make_int2(first, last);
+}
+
 void tau_absorption_impl(int ncol, int nlay, int nbnd, int ngpt, int ngas, int nflav, int neta, int npres,
                          int ntemp, int nminorlower, int nminorklower, int nminorupper, int nminorkupper,
                          int idx_h2o, const int* gpoint_flavor, const int* band_lims_gpt, const Float* kmajor,
@@ -431,8 +449,16 @@ void tau_absorption_impl(int ncol, int nlay, int nbnd, int ngpt, int ngas, int n
   p.ncol = ncol; p.nlay = nlay; p.nbnd = nbnd; p.ngpt = ngpt; p.ngas = ngas; p.nflav = nflav; p.neta = neta;
   p.npres = npres; p.ntemp = ntemp; p.idx_h2o = idx_h2o;
   p.gpoint_flavor = a_gf; p.band_lims_gpt = a_bl; p.kmajor = a_km;
-  p.lower = MinorTables{nminorlower, a_kl, a_ll, a_iml, a_isl, a_ksl, a_sdl, a_scl};
-  p.upper = MinorTables{nminorupper, a_ku, a_lu, a_imu, a_isu, a_ksu, a_sdu, a_scu};
+  int2* ranges = static_cast<int2*>(dev_alloc(sizeof(int2) * 2 * (size_t)nbnd));
+  {
+    KernelTimer timer("minor_band_ranges");
+    minor_band_ranges_kernel<<<ceil_div(nbnd, 32), 32, 0, stream()>>>(nbnd, a_bl, nminorlower, a_ll, ranges);
+    RB_LAUNCH_CHECK();
+    minor_band_ranges_kernel<<<ceil_div(nbnd, 32), 32, 0, stream()>>>(nbnd, a_bl, nminorupper, a_lu, ranges + nbnd);
+    RB_LAUNCH_CHECK();
+  }
+  p.lower = MinorTables{nminorlower, ranges, a_kl, a_ll, a_iml, a_isl, a_ksl, a_sdl, a_scl};
+  p.upper = MinorTables{nminorupper, ranges + nbnd, a_ku, a_lu, a_imu, a_isu, a_ksu, a_sdu, a_scu};
   p.tropo = a_tr; p.col_mix = a_cm; p.fmajor = a_fj; p.fminor = a_fn; p.play = a_pl; p.tlay = a_tl;
   p.col_gas = a_cg; p.jeta = a_je; p.jtemp = a_jt; p.jpress = a_jp; p.tau = a_tau;
   p.accumulate = accumulate ? 1 : 0;
@@ -441,6 +467,7 @@ void tau_absorption_impl(int ncol, int nlay, int nbnd, int ngpt, int ngas, int n
   if (ntemp == 14 && neta == 9 && npres == 59) tau_absorption_kernel<14, 9, 60><<<grid, kCellThreads, 0, stream()>>>(p);
   else tau_absorption_kernel<0, 0, 0><<<grid, kCellThreads, 0, stream()>>>(p);
   RB_LAUNCH_CHECK();
+  dev_free(ranges);
 }
 
 }  // namespace

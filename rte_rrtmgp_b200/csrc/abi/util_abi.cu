@@ -140,6 +140,7 @@ void rrtmgpb_init_constants(const Float* gravity, const Float* mol_weight_dry_ai
   if (gravity) g_const.grav = *gravity;
   if (mol_weight_dry_air) g_const.m_dry = *mol_weight_dry_air;
   if (heat_capacity_dry_air) g_const.cp_dry = *heat_capacity_dry_air;
+  fused_set_constants(g_const.grav, g_const.m_dry);
 }
 
 // ---------------- extension: frontend glue ----------------

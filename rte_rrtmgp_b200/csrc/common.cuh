@@ -58,6 +58,8 @@ struct OpName {
     ::rrtmgpb::count_launch();            \
   } while (0)
 
+void fused_set_constants(double grav, double m_dry);  // gas_optics_fused.cu
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- argument staging ----------------------------------------------------------------------

@@ -641,6 +641,109 @@ int rrtmgpb_gas_optics_ext(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused fast path: gas_optics() and the driver's clouds%increment(atmos) in one pass over the planes
+// (rrtmgpb_gas_optics_fused).  Same checks, same caller-visible results as the two reference calls.
+// ------------------------------------------------------------------------------------------------
+static rrtmgpb_gas_tables tables_of(const rrtmgpb_gas_optics_t* go) {
+  const rrtmgpb_kdist& k = go->h;
+  rrtmgpb_gas_tables t;
+  t.ngas = k.ngas; t.nflav = k.nflav; t.neta = k.neta; t.npres = k.npres; t.ntemp = k.ntemp; t.nbnd = k.nbnd;
+  t.ngpt = k.ngpt; t.nminorlower = k.nminorlower; t.nminorklower = k.nminorklower; t.nminorupper = k.nminorupper;
+  t.nminorkupper = k.nminorkupper; t.idx_h2o = k.idx_h2o;
+  t.flavor = go->flavor; t.gpoint_flavor = go->gpoint_flavor; t.band_lims_gpt = go->band_lims_gpt;
+  t.gpoint_bands = go->gpoint_bands; t.press_ref_log = go->press_ref_log; t.temp_ref = go->temp_ref;
+  t.vmr_ref = go->vmr_ref; t.press_ref_log_delta = k.press_ref_log_delta; t.temp_ref_min = k.temp_ref_min;
+  t.temp_ref_delta = k.temp_ref_delta; t.press_ref_trop_log = k.press_ref_trop_log;
+  t.kmajor = go->kmajor; t.kminor_lower = go->kminor_lower; t.kminor_upper = go->kminor_upper;
+  t.minor_limits_gpt_lower = go->mlg_l; t.minor_limits_gpt_upper = go->mlg_u;
+  t.minor_scales_with_density_lower = go->sd_l; t.minor_scales_with_density_upper = go->sd_u;
+  t.scale_by_complement_lower = go->sc_l; t.scale_by_complement_upper = go->sc_u;
+  t.idx_minor_lower = go->im_l; t.idx_minor_upper = go->im_u; t.idx_minor_scaling_lower = go->is_l;
+  t.idx_minor_scaling_upper = go->is_u; t.kminor_start_lower = go->ks_l; t.kminor_start_upper = go->ks_u;
+  t.krayl = go->krayl; t.planck_frac = go->planck_frac; t.totplnk = go->totplnk; t.nPlanckTemp = k.nPlanckTemp;
+  t.totplnk_delta = k.totplnk_delta;
+  return t;
+}
+
+static int gas_optics_fused_impl(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play,
+                                 const Float* plev, const Float* tlay, const Float* tsfc, const Float* vmr,
+                                 rrtmgpb_optical_props* op, rrtmgpb_source_func_lw* sources, Float* toa_src,
+                                 const Float* col_dry, const Float* tlev, const rrtmgpb_optical_props* clouds,
+                                 char* errmsg) {
+  const rrtmgpb_kdist& k = go->h;
+  const size_t ncl = (size_t)ncol * nlay;
+  std::string msg;
+  set_top_at_1(op, play, ncol, nlay);
+  // checks of compute_gas_taus (:491-521), gas_optics_int (:285-301) and increment (:893-905,956-961)
+  if (g_check_extents) {
+    if (op->ncol != ncol || op->nlay != nlay || op->ngpt != k.ngpt)
+      msg = "gas_optics(): optical properties have the wrong extents";
+    if (sources && (sources->ncol != ncol || sources->nlay != nlay || sources->ngpt != k.ngpt))
+      msg = "gas_optics%gas_optics: source function arrays inconsistently sized";
+  }
+  if (msg.empty() && g_check_values) {
+    if (rrtmgpb_any_vals_outside(ncl, play, nullptr, k.press_ref_min, k.press_ref_max))
+      msg = "gas_optics(): array play has values outside range";
+    if (rrtmgpb_any_vals_less_than(ncl + ncol, plev, nullptr, 0)) msg = "gas_optics(): array plev has values outside range";
+    if (rrtmgpb_any_vals_outside(ncl, tlay, nullptr, k.temp_ref_min, k.temp_ref_max))
+      msg = "gas_optics(): array tlay has values outside range";
+    if (col_dry && rrtmgpb_any_vals_less_than(ncl, col_dry, nullptr, 0))
+      msg = "gas_optics(): array col_dry has values outside range";
+    if (sources && rrtmgpb_any_vals_outside(ncol, tsfc, nullptr, k.temp_ref_min, k.temp_ref_max))
+      msg = "gas_optics(): array tsfc has values outside range";
+    if (sources && tlev && rrtmgpb_any_vals_outside(ncl + ncol, tlev, nullptr, k.temp_ref_min, k.temp_ref_max))
+      msg = "gas_optics(): array tlev has values outside range";
+  }
+  if (msg.empty() && op->kind == RRTMGPB_NSTR) msg = "gas_optics(): n-stream optical properties are not supported by this frontend";
+  int cld_kind = 0;
+  if (msg.empty() && clouds) {
+    if (clouds->ncol != ncol || clouds->nlay != nlay)
+      msg = "ty_optical_props%increment: optical properties objects have different ncol and/or nlay";
+    else if (clouds->nband != op->nband || clouds->ngpt != op->nband)
+      msg = "ty_optical_props%increment: optical properties objects have incompatible g-point structures";
+    else if (clouds->kind == RRTMGPB_NSTR)
+      msg = "ty_optical_props%increment: n-stream clouds are not supported by the fused path";
+    cld_kind = clouds->kind;
+  }
+  if (!msg.empty()) return fail(errmsg, msg);
+  Float* tlev_alloc = nullptr;
+  const Float* tlev_wk = tlev;
+  if (sources && !tlev) {
+    tlev_alloc = static_cast<Float*>(rrtmgpb_mem_alloc((ncl + ncol) * sizeof(Float)));
+    rrtmgpb_interpolate_tlev(ncol, nlay, play, plev, tlay, tlev_alloc);
+    tlev_wk = tlev_alloc;
+  }
+  const rrtmgpb_gas_tables t = tables_of(go);
+  const int sfc_lay = op->top_at_1 ? nlay : 1;
+  rrtmgpb_gas_optics_fused(&t, ncol, nlay, play, plev, tlay, vmr, col_dry, op->kind, op->tau, op->ssa, op->g, cld_kind,
+                           clouds ? clouds->tau : nullptr, clouds ? clouds->ssa : nullptr, clouds ? clouds->g : nullptr,
+                           tlev_wk, tsfc, sfc_lay, sources ? sources->sfc_source : nullptr,
+                           sources ? sources->lay_source : nullptr, sources ? sources->lev_source : nullptr,
+                           sources ? sources->sfc_source_Jac : nullptr);
+  if (toa_src) rrtmgpb_broadcast_by_gpt(ncol, k.ngpt, go->solar_source, toa_src);
+  rrtmgpb_mem_free(tlev_alloc);
+  return ok(errmsg);
+}
+
+int rrtmgpb_gas_optics_int_fused(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play,
+                                 const Float* plev, const Float* tlay, const Float* tsfc, const Float* vmr,
+                                 rrtmgpb_optical_props* op, rrtmgpb_source_func_lw* sources, const Float* col_dry,
+                                 const Float* tlev, const rrtmgpb_optical_props* clouds, char* errmsg) {
+  if (!go->totplnk) return fail(errmsg, "gas_optics(): no internal (Planck) source tables loaded");
+  return gas_optics_fused_impl(go, ncol, nlay, play, plev, tlay, tsfc, vmr, op, sources, nullptr, col_dry, tlev, clouds,
+                               errmsg);
+}
+
+int rrtmgpb_gas_optics_ext_fused(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play,
+                                 const Float* plev, const Float* tlay, const Float* vmr, rrtmgpb_optical_props* op,
+                                 Float* toa_src, const Float* col_dry, const rrtmgpb_optical_props* clouds,
+                                 char* errmsg) {
+  if (!go->solar_source) return fail(errmsg, "gas_optics(): no external (solar) source loaded");
+  return gas_optics_fused_impl(go, ncol, nlay, play, plev, tlay, nullptr, vmr, op, nullptr, toa_src, col_dry, nullptr,
+                               clouds, errmsg);
+}
+
+// ------------------------------------------------------------------------------------------------
 // ty_cloud_optics_rrtmgp (LUT)
 // ------------------------------------------------------------------------------------------------
 struct rrtmgpb_cloud_optics_t {

@@ -17,20 +17,22 @@ def kdists():
     return syn.make_kdist("lw"), syn.make_kdist("sw")
 
 
-def _run(lib, device, ncol, nlay, kd_lw, kd_sw, profiles=None, do_clouds=True):
-    a = AllSky(Context(lib, device), ncol, nlay, kd_lw, kd_sw, do_clouds=do_clouds, profiles=profiles)
+def _run(lib, device, ncol, nlay, kd_lw, kd_sw, profiles=None, do_clouds=True, fused=False):
+    """Oracle runs use the reference call sequence (fused=False); CUDA runs are parametrised over both."""
+    a = AllSky(Context(lib, device), ncol, nlay, kd_lw, kd_sw, do_clouds=do_clouds, profiles=profiles, fused=fused)
     a.step()
     return a
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("ncol,nlay", [(24, 72), (37, 60), (130, 72), (21, 78), (19, 96)])
-def test_allsky_replicated_profile(oracle_lib, cuda_lib, kdists, ncol, nlay, variant):
+def test_allsky_replicated_profile(oracle_lib, cuda_lib, kdists, ncol, nlay, variant, fused):
     """variant 0: register / warp-systolic solvers (nlay <= 80; 96 layers falls back to tiles); 1: tile solvers."""
     kd_lw, kd_sw = kdists
     cuda_lib.cdll.rrtmgpb_set_solver_variant(variant)
-    g = _run(cuda_lib, "cuda:0", ncol, nlay, kd_lw, kd_sw)
+    g = _run(cuda_lib, "cuda:0", ncol, nlay, kd_lw, kd_sw, fused=fused)
     c = _run(oracle_lib, None, ncol, nlay, kd_lw, kd_sw)
     fg, fc = g.fluxes_host(), c.fluxes_host()
     for k in fc:
@@ -46,13 +48,14 @@ def test_allsky_replicated_profile(oracle_lib, cuda_lib, kdists, ncol, nlay, var
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("top_at_1", [True, False])
-def test_allsky_distinct_columns(oracle_lib, cuda_lib, kdists, top_at_1):
+def test_allsky_distinct_columns(oracle_lib, cuda_lib, kdists, top_at_1, fused):
     """RFMIP-like stand-in: every column different (no broadcast table access), both orientations."""
     kd_lw, kd_sw = kdists
     ncol, nlay = 96, 60
     prof = syn.perturbed_profiles(ncol, nlay, seed=1234, top_at_1=top_at_1)
-    g = _run(cuda_lib, "cuda:0", ncol, nlay, kd_lw, kd_sw, profiles=prof)
+    g = _run(cuda_lib, "cuda:0", ncol, nlay, kd_lw, kd_sw, profiles=prof, fused=fused)
     c = _run(oracle_lib, None, ncol, nlay, kd_lw, kd_sw, profiles=prof)
     assert g.lw.atmos.top_at_1 == top_at_1 == c.lw.atmos.top_at_1
     fg, fc = g.fluxes_host(), c.fluxes_host()
@@ -65,11 +68,21 @@ def test_clear_sky_and_reduced_kdist(oracle_lib, cuda_lib):
     """BASELINE configs 3/4 shapes at test size: clear sky; reduced 128/112 g-point k-distributions."""
     kd_lw, kd_sw = syn.make_kdist("lw", ngpt=128), syn.make_kdist("sw", ngpt=112)
     for clouds in (False, True):
-        g = _run(cuda_lib, "cuda:0", 40, 72, kd_lw, kd_sw, do_clouds=clouds)
-        c = _run(oracle_lib, None, 40, 72, kd_lw, kd_sw, do_clouds=clouds)
-        fg, fc = g.fluxes_host(), c.fluxes_host()
-        for k in fc:
-            assert np.max(np.abs(fg[k] - fc[k])) <= FLUX_ATOL, (k, clouds)
+        for fused in (False, True):
+            g = _run(cuda_lib, "cuda:0", 40, 72, kd_lw, kd_sw, do_clouds=clouds, fused=fused)
+            c = _run(oracle_lib, None, 40, 72, kd_lw, kd_sw, do_clouds=clouds)
+            fg, fc = g.fluxes_host(), c.fluxes_host()
+            for k in fc:
+                assert np.max(np.abs(fg[k] - fc[k])) <= FLUX_ATOL, (k, clouds, fused)
+
+
+def test_oracle_fused_entry_equals_reference_sequence(oracle_lib, kdists):
+    """On the oracle the fused entry point is literally the reference sequence: results must be bit-identical."""
+    kd_lw, kd_sw = kdists
+    a = _run(oracle_lib, None, 12, 30, kd_lw, kd_sw, fused=True).fluxes_host()
+    b = _run(oracle_lib, None, 12, 30, kd_lw, kd_sw, fused=False).fluxes_host()
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
 
 
 @pytest.mark.gpu
