@@ -54,6 +54,45 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // slot v of this thread in stage s: [s][v][thread] - consecutive threads hit consecutive 8-byte words
 #define RB_SLOT(base, nslots, s, v) ((base) + ((size_t)((s) * (nslots) + (v)) * kRegThreads + threadIdx.x))
 
+
+// ---------------------------------------------------------------------------------------------------
+// Chunk-level scan.  Every layer recurrence here is a linear (affine or projective) map of the chain state,
+// so a lane can COMPOSE the CL layers of its chunk into one map with all 32 lanes busy, the 8 chunks of a
+// column are then chained with 8 cheap hand-overs (one shuffle + a couple of FMAs each), and finally every
+// lane REPLAYS its own layers from the now-known incoming state - again with all lanes busy - using the
+// reference's per-layer formulas.  Per-level results are therefore computed with exactly the reference's
+// expressions; only the state entering each chunk carries the (rounding-level) reassociation of the
+// composed map.  This replaces sweeps that ran with 4 of 32 lanes active (55% of the solver's issue slots,
+// profiles/r1_prof_v4_*).
+// ---------------------------------------------------------------------------------------------------
+// x_out = A*x_in + B, chunks chained top -> bottom (j = 0 first).  Returns the state entering this lane's chunk;
+// `out_last` receives the state leaving it.
+__device__ __forceinline__ Float affine_handoff_down(int j, Float A, Float B, Float x_top, Float& out) {
+  Float xin = x_top;
+  out = 0;
+  for (int jj = 0; jj < kRegChunks; ++jj) {
+    const Float got = __shfl_up_sync(0xffffffffu, out, 1);
+    if (j == jj) {
+      if (jj > 0) xin = got;
+      out = A * xin + B;
+    }
+  }
+  return xin;
+}
+// chunks chained bottom -> top (j = 7 first)
+__device__ __forceinline__ Float affine_handoff_up(int j, Float A, Float B, Float x_bottom, Float& out) {
+  Float xin = x_bottom;
+  out = 0;
+  for (int jj = kRegChunks - 1; jj >= 0; --jj) {
+    const Float got = __shfl_down_sync(0xffffffffu, out, 1);
+    if (j == jj) {
+      if (jj < kRegChunks - 1) xin = got;
+      out = A * xin + B;
+    }
+  }
+  return xin;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // LW no-scattering (mo_rte_solver_kernels.F90:51-240, 620-745), without Tang rescaling.
 // ---------------------------------------------------------------------------------------------------
@@ -172,42 +211,45 @@ __global__ void __launch_bounds__(kRegThreads, 3) lw_noscat_reg_kernel(const LwN
         Float* q = gflux + (size_t)col + ncol * o.lev(klev);
         *q = (imu == 0) ? piw * I : *q + piw * I;                                  // :223-224, :356-357
       };
-      // ---------------- phase B1: downward transport, :697-706 ----------------
-      Float I = inc / (pi * w);                                                    // :144
+      // ---------------- phase B1: downward transport, :697-706 (chunk-level scan) ----------------
+      const Float I_top = inc / (pi * w);                                           // :144
       if (j == 0) {
-        if (BB) acc_dn_top += w * I; else store(fdn, 0, I);
+        if (BB) acc_dn_top += w * I_top; else store(fdn, 0, I_top);
       }
-      for (int jj = 0; jj < kRegChunks; ++jj) {
-        const Float from_above = __shfl_up_sync(0xffffffffu, I, 1);
-        if (j == jj) {
-          if (jj > 0) I = from_above;
+      Float I;
+      {
+        Float A = 1, B = 0;
 #pragma unroll
-          for (int i = 0; i < CL; ++i) {
-            I = tr[i] * I + sd[i];
-            if (BB) acc_dn[BB ? i : 0] += w * I;                                   // :218 (scaled by pi at the end)
-            else store(fdn, k0 + i + 1, I);
-          }
+        for (int i = 0; i < CL; ++i) { A = tr[i] * A; B = tr[i] * B + sd[i]; }      // composed map of the chunk
+        Float out;
+        I = affine_handoff_down(j, A, B, I_top, out);
+#pragma unroll
+        for (int i = 0; i < CL; ++i) {                                              // replay: the reference's recurrence
+          I = tr[i] * I + sd[i];
+          if (BB) acc_dn[BB ? i : 0] += w * I;                                       // :218 (scaled by pi at the end)
+          else store(fdn, k0 + i + 1, I);
         }
       }
       // surface: the lane of the last chunk holds the intensity at the surface (:198-202)
       Float Iu = I * ((Float)1 - emis) + emis * ssrc;
       Float Ij = emis * sjac;
-      // ---------------- phase B2: upward transport, :729-743 ----------------
-      for (int jj = kRegChunks - 1; jj >= 0; --jj) {
-        const Float from_below = __shfl_down_sync(0xffffffffu, Iu, 1);
-        const Float jac_below = JAC ? __shfl_down_sync(0xffffffffu, Ij, 1) : (Float)0;
-        if (j == jj) {
-          if (jj < kRegChunks - 1) { Iu = from_below; Ij = jac_below; }
+      // ---------------- phase B2: upward transport, :729-743 (chunk-level scan) ----------------
+      {
+        Float A = 1, B = 0;
 #pragma unroll
-          for (int i = CL - 1; i >= 0; --i) {
-            // the incoming value sits at the level below layer k0+i: record it, then cross the layer
-            if (k0 + i < nlay) {
-              if (BB) acc_up[BB ? i : 0] += w * Iu; else store(fup, k0 + i + 1, Iu);
-              if (JAC) acc_jac[JAC ? i : 0] += w * Ij;
-            }
-            Iu = tr[i] * Iu + su[i];
-            if (JAC) Ij = tr[i] * Ij;
+        for (int i = CL - 1; i >= 0; --i) { A = tr[i] * A; B = tr[i] * B + su[i]; }
+        Float out, outj;
+        Iu = affine_handoff_up(j, A, B, Iu, out);
+        if (JAC) Ij = affine_handoff_up(j, A, (Float)0, Ij, outj);
+#pragma unroll
+        for (int i = CL - 1; i >= 0; --i) {
+          // the incoming value sits at the level below layer k0+i: record it, then cross the layer
+          if (k0 + i < nlay) {
+            if (BB) acc_up[BB ? i : 0] += w * Iu; else store(fup, k0 + i + 1, Iu);
+            if (JAC) acc_jac[JAC ? i : 0] += w * Ij;
           }
+          Iu = tr[i] * Iu + su[i];
+          if (JAC) Ij = tr[i] * Ij;
         }
       }
       if (j == 0) {
@@ -247,40 +289,62 @@ __global__ void __launch_bounds__(kRegThreads, 3) lw_noscat_reg_kernel(const LwN
 template <int CL, typename Top, typename Lev>
 __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL], Float (&SU)[CL], Float (&SD)[CL],
                                            Float albedo_sfc, Float src_sfc, Float flux_dn_top, Top top, Lev lev) {
-  Float alb = albedo_sfc, src = src_sfc;  // :1166-1168
-  for (int jj = kRegChunks - 1; jj >= 0; --jj) {
-    const Float alb_b = __shfl_down_sync(0xffffffffu, alb, 1);
-    const Float src_b = __shfl_down_sync(0xffffffffu, src, 1);
-    if (j == jj) {
-      if (jj < kRegChunks - 1) { alb = alb_b; src = src_b; }
+  // ---- upward pass (:1166-1186) as a chunk-level scan.  One layer maps the (albedo, source) below it to the
+  // pair above it projectively: with v = (alb, src, 1)^T,
+  //        [ t^2 - r^2        0   r   ]
+  //   v' ~ [ t*sdn - sup*r    t   sup ] v ,   divided by its third component (1 - r*alb),
+  //        [ -r               0   1   ]
+  // and products of such matrices keep the zero pattern, so a chunk composes into 7 numbers.
+  Float ma = 1, mb = 0, mc = 0, md = 1, me = 0, mf = 0, mg = 1;
 #pragma unroll
-      for (int i = CL - 1; i >= 0; --i) {  // :1174-1186
-        const Float r = R[i], t = T[i], sup = SU[i], sdn = SD[i];
-        const Float denom = (Float)1 / ((Float)1 - r * alb);
-        const Float a = t * denom;
-        R[i] = alb;
-        SU[i] = src;
-        T[i] = a;
-        SD[i] = (r * src + sdn) * denom;
-        const Float albn = r + t * t * alb * denom;
-        src = sup + a * (src + alb * sdn);
-        alb = albn;
+  for (int i = CL - 1; i >= 0; --i) {
+    const Float r = R[i], t = T[i], sup = SU[i], sdn = SD[i];
+    const Float xa = t * t - r * r, xc = t * sdn - sup * r;
+    const Float na = xa * ma + r * mf, nb = xa * mb + r * mg;
+    const Float nc = xc * ma + t * mc + sup * mf, ne = xc * mb + t * me + sup * mg;
+    const Float nf = mf - r * ma, ng = mg - r * mb;
+    ma = na; mb = nb; mc = nc; md = t * md; me = ne; mf = nf; mg = ng;
+  }
+  Float alb = albedo_sfc, src = src_sfc;  // state entering this lane's chunk from below (:1166-1168 for the last chunk)
+  {
+    Float alb_o = 0, src_o = 0;
+    for (int jj = kRegChunks - 1; jj >= 0; --jj) {
+      const Float alb_b = __shfl_down_sync(0xffffffffu, alb_o, 1);
+      const Float src_b = __shfl_down_sync(0xffffffffu, src_o, 1);
+      if (j == jj) {
+        if (jj < kRegChunks - 1) { alb = alb_b; src = src_b; }
+        const Float den = (Float)1 / (mf * alb + mg);
+        alb_o = (ma * alb + mb) * den;
+        src_o = (mc * alb + md * src + me) * den;
       }
     }
   }
-  // lane j == 0 now holds albedo and source at the top of the domain
-  Float fdn = flux_dn_top;
-  if (j == 0) top(fdn * alb + src, fdn);  // :1190
-  for (int jj = 0; jj < kRegChunks; ++jj) {
-    const Float from_above = __shfl_up_sync(0xffffffffu, fdn, 1);
-    if (j == jj) {
-      if (jj > 0) fdn = from_above;
+  // replay with the reference's per-layer expressions, every lane on its own chunk
 #pragma unroll
-      for (int i = 0; i < CL; ++i) {  // :1196-1202
-        fdn = T[i] * fdn + SD[i];
-        lev(i, fdn * R[i] + SU[i], fdn);
-      }
-    }
+  for (int i = CL - 1; i >= 0; --i) {  // :1174-1186
+    const Float r = R[i], t = T[i], sup = SU[i], sdn = SD[i];
+    const Float denom = (Float)1 / ((Float)1 - r * alb);
+    const Float a = t * denom;
+    R[i] = alb;
+    SU[i] = src;
+    T[i] = a;
+    SD[i] = (r * src + sdn) * denom;
+    const Float albn = r + t * t * alb * denom;
+    src = sup + a * (src + alb * sdn);
+    alb = albn;
+  }
+  // lane j == 0 now holds albedo and source at the top of the domain
+  if (j == 0) top(flux_dn_top * alb + src, flux_dn_top);  // :1190
+  // ---- downward pass (:1196-1202): fdn' = a*fdn + b per layer, an affine chain
+  Float A = 1, B = 0;
+#pragma unroll
+  for (int i = 0; i < CL; ++i) { A = T[i] * A; B = T[i] * B + SD[i]; }
+  Float out;
+  Float fdn = affine_handoff_down(j, A, B, flux_dn_top, out);
+#pragma unroll
+  for (int i = 0; i < CL; ++i) {
+    fdn = T[i] * fdn + SD[i];
+    lev(i, fdn * R[i] + SU[i], fdn);
   }
 }
 
@@ -414,22 +478,23 @@ __global__ void __launch_bounds__(kRegThreads, 3) sw_2stream_reg_kernel(const Sw
       if (BB) { acc_dir_top += dir; acc_dn_top += dir; }
       else if (col_ok) gdir[(size_t)col + ncol * o.lev(0)] = dir;
     }
-    for (int jj = 0; jj < kRegChunks; ++jj) {
-      const Float from_above = __shfl_up_sync(0xffffffffu, dir, 1);
-      if (j == jj) {
-        if (jj > 0) dir = from_above;
+    {
+      Float P = 1;
 #pragma unroll
-        for (int i = 0; i < CL; ++i) {
-          const Float s_up = A3[i] * dir, s_dn = A4[i] * dir;
-          dir = A5[i] * dir;
-          A3[i] = s_up;
-          A4[i] = s_dn;
-          if (k0 + i < nlay) {
-            if (BB) { acc_dir[BB ? i : 0] += dir; acc_dn[BB ? i : 0] += dir; }  // :604, direct part of :603
-            else if (col_ok) gdir[(size_t)col + ncol * o.lev(k0 + i + 1)] = dir;
-          }
-          A5[i] = dir;  // direct flux below layer k0+i, for the g-point totals (:606)
+      for (int i = 0; i < CL; ++i) P = A5[i] * P;
+      Float out;
+      dir = affine_handoff_down(j, P, (Float)0, dir_top_g, out);
+#pragma unroll
+      for (int i = 0; i < CL; ++i) {
+        const Float s_up = A3[i] * dir, s_dn = A4[i] * dir;
+        dir = A5[i] * dir;
+        A3[i] = s_up;
+        A4[i] = s_dn;
+        if (k0 + i < nlay) {
+          if (BB) { acc_dir[BB ? i : 0] += dir; acc_dn[BB ? i : 0] += dir; }  // :604, direct part of :603
+          else if (col_ok) gdir[(size_t)col + ncol * o.lev(k0 + i + 1)] = dir;
         }
+        A5[i] = dir;  // direct flux below layer k0+i, for the g-point totals (:606)
       }
     }
     // the lane of the last chunk holds the direct flux at the surface (:1120)
