@@ -27,6 +27,7 @@
 //   * SW broadband_dn adds the direct beam before the diffuse flux of the same g-point (:603)
 #pragma once
 #include "../common.cuh"
+#include "fastmath.cuh"
 
 namespace rrtmgpb {
 
@@ -190,9 +191,9 @@ __global__ void __launch_bounds__(kRegThreads, 3) lw_noscat_reg_kernel(const LwN
         const Float Bbot = *RB_SLOT(sm, NS, s, 2 * CL + i + 1);
         if (k0 + i < nlay) {
           const Float tau_loc = *RB_SLOT(sm, NS, s, i) * D;                        // :181
-          const Float t = exp(-tau_loc);                                           // :182
+          const Float t = rb_exp(-tau_loc);                                           // :182
           Float fact;                                                              // :652-656
-          if (tau_loc > tau_thresh) fact = ((Float)1 - t) / tau_loc - t;
+          if (tau_loc > tau_thresh) fact = rb_div((Float)1 - t, tau_loc) - t;
           else fact = tau_loc * ((Float)0.5 + tau_loc * (-(Float)1 / (Float)3 + tau_loc * (Float)1 / (Float)8));
           const Float lay = *RB_SLOT(sm, NS, s, CL + i);
           // :660-663; source_dn uses the Planck source at the layer's BOTTOM level, source_up at its TOP
@@ -313,7 +314,7 @@ __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL]
       const Float src_b = __shfl_down_sync(0xffffffffu, src_o, 1);
       if (j == jj) {
         if (jj < kRegChunks - 1) { alb = alb_b; src = src_b; }
-        const Float den = (Float)1 / (mf * alb + mg);
+        const Float den = rb_rcp(mf * alb + mg);
         alb_o = (ma * alb + mb) * den;
         src_o = (mc * alb + md * src + me) * den;
       }
@@ -323,7 +324,7 @@ __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL]
 #pragma unroll
   for (int i = CL - 1; i >= 0; --i) {  // :1174-1186
     const Float r = R[i], t = T[i], sup = SU[i], sdn = SD[i];
-    const Float denom = (Float)1 / ((Float)1 - r * alb);
+    const Float denom = rb_rcp((Float)1 - r * alb);
     const Float a = t * denom;
     R[i] = alb;
     SU[i] = src;
@@ -437,22 +438,22 @@ __global__ void __launch_bounds__(kRegThreads, 3) sw_2stream_reg_kernel(const Sw
         const Float gamma1 = ((Float)8 - w0_s * ((Float)5 + (Float)3 * g_s)) * (Float).25;
         const Float gamma2 = (Float)3 * (w0_s * ((Float)1 - g_s)) * (Float).25;
         const Float kk = sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), min_k));
-        const Float exp_minusktau = exp(-tau_s * kk);
+        const Float exp_minusktau = rb_exp(-tau_s * kk);
         const Float exp_minus2ktau = exp_minusktau * exp_minusktau;
-        Float RT_term = (Float)1 / (kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau));
+        Float RT_term = rb_rcp(kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau));
         R[i] = RT_term * gamma2 * ((Float)1 - exp_minus2ktau);
         T[i] = RT_term * (Float)2 * kk * exp_minusktau;
         const Float mu0_s = fmax(min_mu0, mu0);
         const Float k_mu = kk * mu0_s;
         const Float om = (Float)1 - k_mu * k_mu;
-        RT_term = w0_s * RT_term / (fabs(om) >= eps ? om : eps);
+        RT_term = rb_div(w0_s * RT_term, fabs(om) >= eps ? om : eps);
         const Float gamma3 = ((Float)2 - (Float)3 * mu0_s * g_s) * (Float).25;
         const Float gamma4 = (Float)1 - gamma3;
         const Float alpha1 = gamma1 * gamma4 + gamma2 * gamma3;
         const Float alpha2 = gamma1 * gamma3 + gamma2 * gamma4;
         const Float k_gamma3 = kk * gamma3;
         const Float k_gamma4 = kk * gamma4;
-        const Float Tnoscat = exp(-tau_s / mu0_s);
+        const Float Tnoscat = rb_exp(-rb_div(tau_s, mu0_s));
         Float Rdir = RT_term * (((Float)1 - k_mu) * (alpha2 + k_gamma3) -
                                 ((Float)1 + k_mu) * (alpha2 - k_gamma3) * exp_minus2ktau -
                                 (Float)2.0 * (k_gamma3 - alpha2 * k_mu) * exp_minusktau * Tnoscat);
@@ -579,15 +580,15 @@ __global__ void __launch_bounds__(kRegThreads, 4) lw_2stream_reg_kernel(const Lw
         const Float gamma1 = LW_diff_sec * ((Float)1 - (Float)0.5 * w0 * ((Float)1 + gg));   // :879
         const Float gamma2 = LW_diff_sec * (Float)0.5 * w0 * ((Float)1 - gg);                // :880
         const Float kk = sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), (Float)1.e-12));   // :885
-        const Float exp_minusktau = exp(-tau * kk);
+        const Float exp_minusktau = rb_exp(-tau * kk);
         const Float exp_minus2ktau = exp_minusktau * exp_minusktau;
-        const Float RT_term = (Float)1 / (kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau));
+        const Float RT_term = rb_rcp(kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau));
         const Float rdif = RT_term * gamma2 * ((Float)1 - exp_minus2ktau);
         const Float tdif = RT_term * (Float)2 * kk * exp_minusktau;
         const Float lev_top = Blev[i], lev_bot = Blev[i + 1];
         Float s_up = 0, s_dn = 0;
         if (tau > (Float)1.0e-8) {  // :947-957
-          const Float Z = (lev_bot - lev_top) / (tau * (gamma1 + gamma2));
+          const Float Z = rb_div(lev_bot - lev_top, tau * (gamma1 + gamma2));
           const Float Zup_top = Z + lev_top;
           const Float Zup_bottom = Z + lev_bot;
           const Float Zdn_top = -Z + lev_top;
