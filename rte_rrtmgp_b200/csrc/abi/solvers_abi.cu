@@ -17,6 +17,7 @@
 //     mo_rte_solver_kernels.F90:216-218,601-604) - deterministic, no atomics - and are written once.
 //   * `intent(out)` arrays whose controlling flag is false are decoys that may alias:
 //     they are never read or written here and no pointer is __restrict__.
+#include <cstdlib>
 #include "../kernels/elementwise.cuh"
 #include "../kernels/solver_reg.cuh"
 #include "rte_kernels.h"
@@ -554,6 +555,10 @@ inline int reg_chunk_len(int nlay) {
   if (nlay <= 80) return 10;
   return 0;
 }
+inline int reg_minb() {  // experiment switch: resident CTAs per SM the register kernels are compiled for
+  static const int v = [] { const char* e = std::getenv("RRTMGPB_REG_MINB"); return (e && e[0] == '3') ? 3 : 2; }();
+  return v;
+}
 inline int reg_gpt_groups(int ncol, int ngpt) {
   const int ctas = ceil_div(ncol, (kRegThreads / 32) * kRegCols);
   int groups = ceil_div(148 * 8, ctas);
@@ -618,7 +623,7 @@ void rte_lw_solver_noscat(const int* ncol_, const int* nlay_, const int* ngpt_, 
 #define LWREG2(CLV, BBV, JACV)                                                                              \
   {                                                                                                         \
     const size_t smem = (size_t)2 * lw_noscat_reg_slots<CLV>() * kRegThreads * sizeof(Float);               \
-    auto kern = lw_noscat_reg_kernel<CLV, BBV, JACV>;                                                       \
+    auto kern = reg_minb() == 2 ? lw_noscat_reg_kernel<CLV, BBV, JACV, 2> : lw_noscat_reg_kernel<CLV, BBV, JACV, 3>; \
     RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     kern<<<grid, kRegThreads, smem, stream()>>>(q);                                                         \
   }
@@ -730,7 +735,7 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
 #define SWREG2(CLV, BBV)                                                                                    \
   {                                                                                                         \
     const size_t smem = ((size_t)2 * sw_reg_slots<CLV>() + CLV) * kRegThreads * sizeof(Float);              \
-    auto kern = sw_2stream_reg_kernel<CLV, BBV>;                                                            \
+    auto kern = reg_minb() == 2 ? sw_2stream_reg_kernel<CLV, BBV, 2> : sw_2stream_reg_kernel<CLV, BBV, 3>;  \
     RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     kern<<<grid, kRegThreads, smem, stream()>>>(q);                                                         \
   }

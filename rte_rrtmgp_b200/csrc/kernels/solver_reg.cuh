@@ -112,8 +112,8 @@ struct LwNoscatRegParams {
 template <int CL>
 __host__ __device__ constexpr int lw_noscat_reg_slots() { return 3 * CL + 1 + 5; }  // tau, lay, lev(+1), emis, sfc_src, inc_flux, jac, D(angle 1)
 
-template <int CL, bool BB, bool JAC>
-__global__ void __launch_bounds__(kRegThreads, 3) lw_noscat_reg_kernel(const LwNoscatRegParams p) {
+template <int CL, bool BB, bool JAC, int MINB = 3>
+__global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const LwNoscatRegParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Float* sm = reinterpret_cast<Float*>(smem_raw);
   constexpr int NS = lw_noscat_reg_slots<CL>();
@@ -366,8 +366,8 @@ struct SwRegParams {
 template <int CL>
 __host__ __device__ constexpr int sw_reg_slots() { return 3 * CL + 4; }  // tau, ssa, g, alb_dir, alb_dif, inc_dir, inc_dif
 
-template <int CL, bool BB>
-__global__ void __launch_bounds__(kRegThreads, 3) sw_2stream_reg_kernel(const SwRegParams p) {
+template <int CL, bool BB, int MINB = 3>
+__global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const SwRegParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Float* sm = reinterpret_cast<Float*>(smem_raw);
   constexpr int NS = sw_reg_slots<CL>();
