@@ -96,6 +96,22 @@ void rrtmgpb_cloud_masks(int ncol, int nlay, const Float* clwp, const Float* ciw
 void rrtmgpb_cloud_combine(int ncol, int nlay, int ngpt, int kind, const Float* ltau, const Float* ltaussa,
                            const Float* ltaussag, const Float* itau, const Float* itaussa,
                            const Float* itaussag, Float* tau, Float* ssa, Float* g);
+/* replaces compute_all_from_table + the optical-property combination of ty_aerosol_optics_rrtmgp_merra%aerosol_optics,
+ * rrtmgp/frontend/mo_aerosol_optics_rrtmgp_merra.F90:436-559 and :385-418 (size-bin search, relative-humidity
+ * bracket + linear interpolation, per-type table lookup; kind 1: tau = atau - ataussa; kind 2: tau, ssa, g with
+ * epsilon() guards).  type(ncol,nlay) int: 0 none, 1 dust, 2 salt, 3 sulfate, 4 bcar_rh, 5 bcar, 6 ocar_rh, 7 ocar
+ * (:50-59); size, mass, rh (ncol,nlay); bin_lims(npair=2,nbin); aero_rh(nrh); tables as the loader holds them:
+ * dust(nval,nbin,nbnd) salt(nrh,nval,nbin,nbnd) sulf/bcar_rh/ocar_rh(nrh,nval,nbnd) bcar/ocar(nval,nbnd), nval = 3
+ * (ext, ssa, g).  Outputs (ncol,nlay,nbnd). */
+void rrtmgpb_aerosol_optics_from_table(int ncol, int nlay, int nval, int nrh, int nbin, int nbnd, int kind,
+                                       const int* type, const Float* size, const Float* mass, const Float* rh,
+                                       const Float* bin_lims, const Float* aero_rh, const Float* dust_tbl,
+                                       const Float* salt_tbl, const Float* sulf_tbl, const Float* bcar_rh_tbl,
+                                       const Float* bcar_tbl, const Float* ocar_rh_tbl, const Float* ocar_tbl,
+                                       Float* tau, Float* ssa, Float* g);
+/* aerosol mask (:343-347) and any_int_vals_outside_2D (:580-600): return 1 if any element violates */
+void rrtmgpb_aerosol_mask(int ncol, int nlay, const int* type, Bool* aeromsk);
+int rrtmgpb_any_int_vals_outside(size_t n, const int* array, int checkMin, int checkMax);
 /* value checks, rte/frontend/mo_rte_util_array_validation.F90:52-...: return 1 if any element violates.
  * mask may be NULL (no mask). */
 int rrtmgpb_any_vals_less_than(size_t n, const Float* array, const Bool* mask, Float check_value);

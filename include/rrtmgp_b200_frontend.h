@@ -160,6 +160,32 @@ int rrtmgpb_cloud_optics(const rrtmgpb_cloud_optics_t* co, int ncol, int nlay, c
                          const Float* reliq, const Float* dgice, rrtmgpb_optical_props* optical_props,
                          char* errmsg);
 
+/* ---------------- ty_aerosol_optics_rrtmgp_merra ---------------- */
+/* Tables as load_lut() receives them (mo_aerosol_optics_rrtmgp_merra.F90:99-123): the rh-dependent ones arrive
+ * as (nval,nrh,...) and are transposed to (nrh,nval,...) by load (:178-181).  All pointers HOST. */
+typedef struct {
+  int nbnd, nval, nrh, nbin;
+  const Float* band_lims_wvn;       /* (2,nbnd) */
+  const Float* merra_aero_bin_lims; /* (2,nbin) */
+  const Float* aero_rh;             /* (nrh) */
+  const Float* aero_dust_tbl;       /* (nval,nbin,nbnd) */
+  const Float* aero_salt_tbl;       /* (nval,nrh,nbin,nbnd) */
+  const Float* aero_sulf_tbl;       /* (nval,nrh,nbnd) */
+  const Float* aero_bcar_tbl;       /* (nval,nbnd) */
+  const Float* aero_bcar_rh_tbl;    /* (nval,nrh,nbnd) */
+  const Float* aero_ocar_tbl;       /* (nval,nbnd) */
+  const Float* aero_ocar_rh_tbl;    /* (nval,nrh,nbnd) */
+} rrtmgpb_aerosol_lut;
+
+typedef struct rrtmgpb_aerosol_optics_t rrtmgpb_aerosol_optics_t;
+rrtmgpb_aerosol_optics_t* rrtmgpb_aerosol_optics_load(const rrtmgpb_aerosol_lut* lut, char* errmsg);
+void rrtmgpb_aerosol_optics_free(rrtmgpb_aerosol_optics_t* ao);
+/* aerosol_optics(): mo_aerosol_optics_rrtmgp_merra.F90:233-424.  aero_type (ncol,nlay) int;
+ * aero_size, aero_mass, relhum (ncol,nlay) */
+int rrtmgpb_aerosol_optics(const rrtmgpb_aerosol_optics_t* ao, int ncol, int nlay, const int* aero_type,
+                           const Float* aero_size, const Float* aero_mass, const Float* relhum,
+                           rrtmgpb_optical_props* optical_props, char* errmsg);
+
 #ifdef __cplusplus
 }
 #endif

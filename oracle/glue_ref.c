@@ -213,3 +213,101 @@ void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, c
                                  t->gpoint_flavor, sfc_src, lay_src, lev_src, sfc_source_Jac);
   free(cd); free(col_gas); free(jtemp); free(jpress); free(jeta); free(tropo); free(fmajor); free(fminor); free(col_mix);
 }
+
+/* ---------------- aerosol optics: rrtmgp/frontend/mo_aerosol_optics_rrtmgp_merra.F90 ---------------- */
+/* aerosol mask :343-347 */
+void rrtmgpb_aerosol_mask(int ncol, int nlay, const int* type, Bool* aeromsk) {
+  const size_t n = (size_t)ncol * nlay;
+  for (size_t i = 0; i < n; ++i) aeromsk[i] = type[i] > 0;
+}
+/* any_int_vals_outside_2D :580-600 */
+int rrtmgpb_any_int_vals_outside(size_t n, const int* a, int lo, int hi) {
+  for (size_t i = 0; i < n; ++i)
+    if (a[i] < lo || a[i] > hi) return 1;
+  return 0;
+}
+/* linear_interp_aero_table :563-577 (1-based indices) */
+static Float aero_lin(const Float* table, int index1, int index2, Float weight) {
+  return table[index1 - 1] + weight * (table[index2 - 1] - table[index1 - 1]);
+}
+/* compute_all_from_table :436-559, loop order and per-band repeated searches as written */
+static void compute_all_from_table(int ncol, int nlay, int nval, int nrh, int nbin, int nbnd, const int* type,
+                                   const Float* size, const Float* mass, const Float* rh, const Float* lims,
+                                   const Float* aero_rh, const Float* dust, const Float* salt, const Float* sulf,
+                                   const Float* bcar_rh, const Float* bcar, const Float* ocar_rh, const Float* ocar,
+                                   Float* tau, Float* taussa, Float* taussag) {
+  const size_t ncl = (size_t)ncol * nlay;
+  enum { EXT = 0, SSA = 1, G = 2 };
+  int ibin = 1; /* the reference leaves ibin undefined when no bin matches; only reachable with checks off */
+  for (int ibnd = 0; ibnd < nbnd; ++ibnd)
+    for (size_t c = 0; c < ncl; ++c) {
+      for (int i = 1; i <= nbin; ++i)
+        if (size[c] >= lims[2 * (i - 1)] && size[c] <= lims[2 * (i - 1) + 1]) ibin = i;
+      const int itype = type[c];
+      int irh1 = 1, irh2 = 1;
+      Float rdrh = 0;
+      if (itype != 0) {
+        irh2 = 1;
+        while (rh[c] > aero_rh[irh2 - 1]) {
+          irh2 = irh2 + 1;
+          if (irh2 > nrh) break;
+        }
+        irh1 = (irh2 - 1 > 1) ? irh2 - 1 : 1;
+        irh2 = (irh2 < nrh) ? irh2 : nrh;
+        const Float drh0 = aero_rh[irh2 - 1] - aero_rh[irh1 - 1];
+        const Float drh1 = rh[c] - aero_rh[irh1 - 1];
+        rdrh = (irh1 == irh2) ? (Float)0 : drh1 / drh0;
+      }
+      const size_t o = c + ncl * ibnd;
+      const size_t b3 = (size_t)nrh * nval * ibnd;                          /* (nrh,nval,nbnd) */
+      const size_t b4 = (size_t)nrh * nval * ((ibin - 1) + (size_t)nbin * ibnd); /* (nrh,nval,nbin,nbnd) */
+      const Float* rt = NULL;
+      const Float* ft = NULL;
+      switch (itype) {
+        case 1: ft = dust + (size_t)nval * ((ibin - 1) + (size_t)nbin * ibnd); break;
+        case 2: rt = salt + b4; break;
+        case 3: rt = sulf + b3; break;
+        case 4: rt = bcar_rh + b3; break;
+        case 5: ft = bcar + (size_t)nval * ibnd; break;
+        case 6: rt = ocar_rh + b3; break;
+        case 7: ft = ocar + (size_t)nval * ibnd; break;
+        default: break;
+      }
+      if (rt) {
+        tau[o] = mass[c] * aero_lin(rt + (size_t)nrh * EXT, irh1, irh2, rdrh);
+        taussa[o] = tau[o] * aero_lin(rt + (size_t)nrh * SSA, irh1, irh2, rdrh);
+        taussag[o] = taussa[o] * aero_lin(rt + (size_t)nrh * G, irh1, irh2, rdrh);
+      } else if (ft) {
+        tau[o] = mass[c] * ft[EXT];
+        taussa[o] = tau[o] * ft[SSA];
+        taussag[o] = taussa[o] * ft[G];
+      } else {
+        tau[o] = 0; taussa[o] = 0; taussag[o] = 0;
+      }
+    }
+}
+/* aerosol_optics: table lookup (:370-380) then the combination (:385-418) */
+void rrtmgpb_aerosol_optics_from_table(int ncol, int nlay, int nval, int nrh, int nbin, int nbnd, int kind,
+                                       const int* type, const Float* size, const Float* mass, const Float* rh,
+                                       const Float* bin_lims, const Float* aero_rh, const Float* dust_tbl,
+                                       const Float* salt_tbl, const Float* sulf_tbl, const Float* bcar_rh_tbl,
+                                       const Float* bcar_tbl, const Float* ocar_rh_tbl, const Float* ocar_tbl,
+                                       Float* tau, Float* ssa, Float* g) {
+  const size_t n = (size_t)ncol * nlay * nbnd;
+  const Float eps = (sizeof(Float) == 8) ? (Float)DBL_EPSILON : (Float)FLT_EPSILON;
+  Float* atau = (Float*)malloc(3 * n * sizeof(Float) + 8);
+  Float *ataussa = atau + n, *ataussag = atau + 2 * n;
+  compute_all_from_table(ncol, nlay, nval, nrh, nbin, nbnd, type, size, mass, rh, bin_lims, aero_rh, dust_tbl,
+                         salt_tbl, sulf_tbl, bcar_rh_tbl, bcar_tbl, ocar_rh_tbl, ocar_tbl, atau, ataussa, ataussag);
+  if (kind == 1) {
+    for (size_t i = 0; i < n; ++i) tau[i] = atau[i] - ataussa[i];
+  } else {
+    for (size_t i = 0; i < n; ++i) {
+      const Float t = atau[i], ts = ataussa[i];
+      tau[i] = t;
+      ssa[i] = ts / MAXF(eps, t);
+      g[i] = ataussag[i] / MAXF(eps, ts);
+    }
+  }
+  free(atau);
+}

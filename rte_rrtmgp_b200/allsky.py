@@ -9,15 +9,20 @@ import os
 import numpy as np
 
 from . import synthetic as syn
-from .frontend import (CloudOptics, FluxesBroadband, GasOptics, OpticalProps, SourceFuncLW, rte_lw, rte_sw)
+from .frontend import (AerosolOptics, CloudOptics, FluxesBroadband, GasOptics, OpticalProps, SourceFuncLW, rte_lw,
+                       rte_lw_bygpoint, rte_sw)
 
 
 class AllSky:
     def __init__(self, ctx, ncol, nlay, kd_lw=None, kd_sw=None, do_clouds=True, profiles=None, col_offset=0,
-                 mu0=0.86, sfc_alb=0.06, emis=0.98, fused=None):
+                 mu0=0.86, sfc_alb=0.06, emis=0.98, fused=None, do_aerosols=False, lw_2stream=False):
+        """do_aerosols: rrtmgp_allsky.F90:233-236,664-738.  lw_2stream: LW with 2-stream optical properties and
+        rte_lw(use_2stream=.true.) (BASELINE config 5); the solver then returns g-point fluxes, which are summed
+        with rte_sum_broadband (the reference leaves the broadband arrays unfilled here)."""
         if fused is None:  # the express path; off by default until it beats the kernel-by-kernel sequence (DESIGN.md section 4)
             fused = os.environ.get("RRTMGPB_FUSED", "0") == "1"
         self.ctx, self.ncol, self.nlay, self.fused = ctx, ncol, nlay, fused
+        self.do_aerosols, self.lw_2stream = do_aerosols, lw_2stream
         prof = profiles if profiles is not None else syn.compute_profiles(300.0, ncol, nlay)
         self.host_inputs = {}
         vmr = syn.allsky_gas_vmrs(prof)
@@ -32,7 +37,8 @@ class AllSky:
         if kd_lw is not None:
             lw = type("LW", (), {})()
             lw.go = GasOptics(ctx, kd_lw)
-            lw.atmos = OpticalProps.like(ctx, "1scl", ncol, nlay, lw.go)
+            lw_kind = "2str" if lw_2stream else "1scl"
+            lw.atmos = OpticalProps.like(ctx, lw_kind, ncol, nlay, lw.go)
             lw.sources = SourceFuncLW(ctx, ncol, nlay, kd_lw.ngpt)
             lw.t_sfc = put(np.ascontiguousarray(prof["t_lev"][:, sfc]))  # rrtmgp_allsky.F90:296
             lw.emis_sfc = put(np.full((kd_lw.nbnd, ncol), emis, order="F"))
@@ -41,7 +47,14 @@ class AllSky:
             if do_clouds:
                 lw.lut = syn.make_cloud_lut(kd_lw)
                 lw.co = CloudOptics(ctx, lw.lut)
-                lw.clouds = OpticalProps.like(ctx, "1scl", ncol, nlay, lw.co)
+                lw.clouds = OpticalProps.like(ctx, lw_kind, ncol, nlay, lw.co)
+            if do_aerosols:
+                lw.alut = syn.make_aerosol_lut(kd_lw)
+                lw.ao = AerosolOptics(ctx, lw.alut)
+                lw.aerosols = OpticalProps.like(ctx, lw_kind, ncol, nlay, lw.ao)
+            if lw_2stream:
+                lw.gpt_flux_up = ctx.zeros((ncol, nlay + 1, kd_lw.ngpt))
+                lw.gpt_flux_dn = ctx.zeros((ncol, nlay + 1, kd_lw.ngpt))
             self.lw = lw
         if kd_sw is not None:
             sw = type("SW", (), {})()
@@ -57,6 +70,10 @@ class AllSky:
                 sw.lut = syn.make_cloud_lut(kd_sw)
                 sw.co = CloudOptics(ctx, sw.lut)
                 sw.clouds = OpticalProps.like(ctx, "2str", ncol, nlay, sw.co)
+            if do_aerosols:
+                sw.alut = syn.make_aerosol_lut(kd_sw)
+                sw.ao = AerosolOptics(ctx, sw.alut)
+                sw.aerosols = OpticalProps.like(ctx, "2str", ncol, nlay, sw.ao)
             self.sw = sw
         self.do_clouds = do_clouds
         if do_clouds:
@@ -68,12 +85,19 @@ class AllSky:
                 cl = _shift_cloud_columns(prof, some.lut, col_offset)
             self.lwp, self.iwp, self.rel, self.dei = put(cl["lwp"]), put(cl["iwp"]), put(cl["rel"]), put(cl["dei"])
             self.host_inputs.update(cl)
+        if do_aerosols:
+            ae = syn.compute_aerosols(prof, col_offset)
+            self.aero_type, self.aero_size = put(ae["aero_type"]), put(ae["aero_size"])
+            self.aero_mass, self.relhum = put(ae["aero_mass"]), put(ae["relhum"])
+            self.host_inputs.update(ae)
 
     # -- one iteration of the reference loop body, LW branch (rrtmgp_allsky.F90:340-381)
     def step_lw(self):
         lw = self.lw
         if self.do_clouds:
             lw.co.cloud_optics(self.lwp, self.iwp, self.rel, self.dei, lw.clouds)
+        if self.do_aerosols:
+            lw.ao.aerosol_optics(self.aero_type, self.aero_size, self.aero_mass, self.relhum, lw.aerosols)
         if self.fused:  # gas optics + clouds%increment(atmos) in one pass (same caller-visible results)
             lw.go.gas_optics(self.p_lay, self.p_lev, self.t_lay, self.vmr, lw.atmos, t_sfc=lw.t_sfc,
                              sources=lw.sources, tlev=self.t_lev, fused=True,
@@ -83,7 +107,15 @@ class AllSky:
                              sources=lw.sources, tlev=self.t_lev)
             if self.do_clouds:
                 lw.clouds.increment(lw.atmos)
-        rte_lw(self.ctx, lw.atmos, lw.sources, lw.emis_sfc, lw.fluxes)
+        if self.do_aerosols:
+            lw.aerosols.increment(lw.atmos)
+        if self.lw_2stream:
+            rte_lw_bygpoint(self.ctx, lw.atmos, lw.sources, lw.emis_sfc, lw.gpt_flux_up, lw.gpt_flux_dn, use_2stream=1)
+            ngpt, nlev = lw.go.ngpt, self.nlay + 1
+            self.ctx.lib.rte_sum_broadband(self.ncol, nlev, ngpt, lw.gpt_flux_up, lw.flux_up)
+            self.ctx.lib.rte_sum_broadband(self.ncol, nlev, ngpt, lw.gpt_flux_dn, lw.flux_dn)
+        else:
+            rte_lw(self.ctx, lw.atmos, lw.sources, lw.emis_sfc, lw.fluxes)
 
     # -- SW branch (rrtmgp_allsky.F90:340-352,383-406)
     def step_sw(self):
@@ -92,6 +124,8 @@ class AllSky:
             sw.co.cloud_optics(self.lwp, self.iwp, self.rel, self.dei, sw.clouds)
         if self.do_clouds:
             sw.clouds.delta_scale()
+        if self.do_aerosols:
+            sw.ao.aerosol_optics(self.aero_type, self.aero_size, self.aero_mass, self.relhum, sw.aerosols)
         if self.fused:
             sw.go.gas_optics(self.p_lay, self.p_lev, self.t_lay, self.vmr, sw.atmos, toa_src=sw.toa_flux, fused=True,
                              increment_by=sw.clouds if self.do_clouds else None)
@@ -99,6 +133,9 @@ class AllSky:
             sw.go.gas_optics(self.p_lay, self.p_lev, self.t_lay, self.vmr, sw.atmos, toa_src=sw.toa_flux)
             if self.do_clouds:
                 sw.clouds.increment(sw.atmos)
+        if self.do_aerosols:
+            sw.aerosols.delta_scale()
+            sw.aerosols.increment(sw.atmos)
         rte_sw(self.ctx, sw.atmos, sw.mu0, sw.toa_flux, sw.sfc_alb_dir, sw.sfc_alb_dif, sw.fluxes)
 
     def step(self):

@@ -323,4 +323,111 @@ int rrtmgpb_any_vals_outside(size_t n, const Float* array, const Bool* mask, Flo
   return any_flag(n, array, mask, checkMin, checkMax, true);
 }
 
+// ---------------- aerosol optics (mo_aerosol_optics_rrtmgp_merra.F90) ----------------
+void rrtmgpb_aerosol_mask(int ncol, int nlay, const int* type, Bool* aeromsk) {  // :343-347
+  OpName op_name__(__func__);
+  const size_t n = (size_t)ncol * nlay;
+  DevArg<int> t(type, n, Dir::In);
+  DevArg<Bool> m(aeromsk, n, Dir::Out);
+  const int* pt = t; Bool* pm = m;
+  launch_elementwise(n, [=] __device__(size_t k) { pm[k] = pt[k] > 0; });
+}
+
+int rrtmgpb_any_int_vals_outside(size_t n, const int* array, int checkMin, int checkMax) {  // :580-600
+  OpName op_name__(__func__);
+  DevArg<int> a(array, n, Dir::In);
+  int* flag = static_cast<int*>(dev_alloc(sizeof(int)));
+  RB_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), stream()));
+  const int* pa = a;
+  launch_elementwise(n, [=] __device__(size_t i) {
+    const int v = pa[i];
+    if (v < checkMin || v > checkMax) *flag = 1;
+  });
+  int h = 0;
+  RB_CUDA_CHECK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+  RB_CUDA_CHECK(cudaStreamSynchronize(stream()));
+  dev_free(flag);
+  return h;
+}
+
+// compute_all_from_table (:436-559) fused with the optical-property combination (:385-418): one thread per
+// (column, layer) finds its size bin and relative-humidity bracket ONCE (the reference repeats both searches for
+// every band), then walks the bands; the three (ncol,nlay,nbnd) temporaries of the reference never exist.
+void rrtmgpb_aerosol_optics_from_table(int ncol, int nlay, int nval, int nrh, int nbin, int nbnd, int kind,
+                                       const int* type, const Float* size, const Float* mass, const Float* rh,
+                                       const Float* bin_lims, const Float* aero_rh, const Float* dust_tbl,
+                                       const Float* salt_tbl, const Float* sulf_tbl, const Float* bcar_rh_tbl,
+                                       const Float* bcar_tbl, const Float* ocar_rh_tbl, const Float* ocar_tbl,
+                                       Float* tau, Float* ssa, Float* g) {
+  OpName op_name__(__func__);
+  const size_t ncl = (size_t)ncol * nlay, n = ncl * nbnd;
+  DevArg<int> a_type(type, ncl, Dir::In);
+  DevArg<Float> a_size(size, ncl, Dir::In), a_mass(mass, ncl, Dir::In), a_rh(rh, ncl, Dir::In);
+  DevArg<Float> a_lims(bin_lims, 2 * (size_t)nbin, Dir::In), a_arh(aero_rh, (size_t)nrh, Dir::In);
+  DevArg<Float> a_dust(dust_tbl, (size_t)nval * nbin * nbnd, Dir::In), a_salt(salt_tbl, (size_t)nrh * nval * nbin * nbnd, Dir::In);
+  DevArg<Float> a_sulf(sulf_tbl, (size_t)nrh * nval * nbnd, Dir::In), a_bcrh(bcar_rh_tbl, (size_t)nrh * nval * nbnd, Dir::In);
+  DevArg<Float> a_bcar(bcar_tbl, (size_t)nval * nbnd, Dir::In), a_ocrh(ocar_rh_tbl, (size_t)nrh * nval * nbnd, Dir::In);
+  DevArg<Float> a_ocar(ocar_tbl, (size_t)nval * nbnd, Dir::In);
+  DevArg<Float> o_tau(tau, n, Dir::Out), o_ssa(ssa, n, Dir::Out, kind == 2), o_g(g, n, Dir::Out, kind == 2);
+  const int* p_type = a_type;
+  const Float *p_size = a_size, *p_mass = a_mass, *p_rh = a_rh, *p_lims = a_lims, *p_arh = a_arh;
+  const Float *t_dust = a_dust, *t_salt = a_salt, *t_sulf = a_sulf, *t_bcrh = a_bcrh, *t_bcar = a_bcar,
+              *t_ocrh = a_ocrh, *t_ocar = a_ocar;
+  Float *p_tau = o_tau, *p_ssa = o_ssa, *p_g = o_g;
+  launch_elementwise(ncl, [=] __device__(size_t c) {
+    const int itype = p_type[c];
+    int ibin = 0;  // 0-based; the LAST bin whose limits bracket the size wins (:457-462)
+    int irh1 = 0, irh2 = 0;
+    Float rdrh = 0, m = 0;
+    if (itype != 0) {
+      const Float sz = p_size[c];
+      for (int i = 0; i < nbin; ++i)
+        if (sz >= __ldg(p_lims + 2 * i) && sz <= __ldg(p_lims + 2 * i + 1)) ibin = i;
+      const Float r = p_rh[c];
+      int i2 = 1;  // 1-based as in the reference (:466-478)
+      while (r > __ldg(p_arh + i2 - 1)) {
+        ++i2;
+        if (i2 > nrh) break;
+      }
+      const int i1 = max(1, i2 - 1);
+      i2 = min(nrh, i2);
+      const Float drh0 = __ldg(p_arh + i2 - 1) - __ldg(p_arh + i1 - 1);
+      const Float drh1 = r - __ldg(p_arh + i1 - 1);
+      rdrh = (i1 == i2) ? (Float)0 : drh1 / drh0;
+      irh1 = i1 - 1; irh2 = i2 - 1;
+      m = p_mass[c];
+    }
+    for (int ibnd = 0; ibnd < nbnd; ++ibnd) {
+      Float e = 0, w = 0, asy = 0;  // ext, ssa, g of this (type, bin, rh, band)
+      auto lin = [&](const Float* tab) {  // linear_interp_aero_table :571-575 on tab(nrh)
+        const Float t1 = __ldg(tab + irh1);
+        return t1 + rdrh * (__ldg(tab + irh2) - t1);
+      };
+      const Float* rh_tab = nullptr;  // (nrh,nval) slice of an rh-dependent table
+      const Float* fix_tab = nullptr; // (nval) slice of an rh-independent table
+      switch (itype) {
+        case 1: fix_tab = t_dust + (size_t)nval * (ibin + (size_t)nbin * ibnd); break;
+        case 2: rh_tab = t_salt + (size_t)nrh * nval * (ibin + (size_t)nbin * ibnd); break;
+        case 3: rh_tab = t_sulf + (size_t)nrh * nval * ibnd; break;
+        case 4: rh_tab = t_bcrh + (size_t)nrh * nval * ibnd; break;
+        case 5: fix_tab = t_bcar + (size_t)nval * ibnd; break;
+        case 6: rh_tab = t_ocrh + (size_t)nrh * nval * ibnd; break;
+        case 7: fix_tab = t_ocar + (size_t)nval * ibnd; break;
+        default: break;
+      }
+      if (rh_tab) { e = lin(rh_tab); w = lin(rh_tab + nrh); asy = lin(rh_tab + 2 * nrh); }
+      else if (fix_tab) { e = __ldg(fix_tab); w = __ldg(fix_tab + 1); asy = __ldg(fix_tab + 2); }
+      const Float t = m * e, ts = t * w, tsg = ts * asy;  // :502-504
+      const size_t o = c + ncl * ibnd;
+      if (kind == 1) {
+        p_tau[o] = t - ts;                                // :392
+      } else {
+        p_tau[o] = t;                                     // :405-409
+        p_ssa[o] = ts / fmax((Float)RB_EPS, t);
+        p_g[o] = tsg / fmax((Float)RB_EPS, ts);
+      }
+    }
+  });
+}
+
 }  // extern "C"

@@ -7,6 +7,7 @@
 //   rte/frontend/mo_rte_sw.F90:56-422               rte_sw (mu0 by column)
 //   rrtmgp/frontend/mo_gas_optics_rrtmgp.F90:220-414,419-745,840-928  gas_optics_int/ext, compute_gas_taus, source
 //   rrtmgp/frontend/mo_cloud_optics_rrtmgp.F90:256-431            cloud_optics (LUT)
+//   rrtmgp/frontend/mo_aerosol_optics_rrtmgp_merra.F90:99-424     aerosol load_lut, aerosol_optics
 //
 // Backend-agnostic by construction: this file only sequences extern "C" kernels (rte_kernels.h,
 // rrtmgp_kernels.h, rrtmgp_b200_ext.h) and never dereferences an array, so the SAME source is linked
@@ -821,6 +822,106 @@ int rrtmgpb_cloud_optics(const rrtmgpb_cloud_optics_t* co, int ncol, int nlay, c
                                 &h.diamice_lwr, co->extice, co->ssaice, co->asyice, itau, itaussa, itaussag);  // :380
   rrtmgpb_cloud_combine(ncol, nlay, ngpt, op->kind, ltau, ltaussa, ltaussag, itau, itaussa, itaussag, op->tau, op->ssa,
                         op->g);  // :399-424
+  return ok(errmsg);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ty_aerosol_optics_rrtmgp_merra (LUT): rrtmgp/frontend/mo_aerosol_optics_rrtmgp_merra.F90
+// ------------------------------------------------------------------------------------------------
+struct rrtmgpb_aerosol_optics_t {
+  int nbnd, nval, nrh, nbin;
+  std::vector<Float> band_lims_wvn_h;
+  Float min_size, max_size;  // merra_aero_bin_lims(1,1), (2,nbin), :291-292
+  Float *bin_lims, *aero_rh, *dust, *salt, *sulf, *bcar, *bcar_rh, *ocar, *ocar_rh;  // backend memory
+};
+
+// reshape(tbl, shape=(/nrh,nval,.../), order=(/2,1,.../)): swap the first two dimensions (:178-181)
+static std::vector<Float> swap_first_two(const Float* src, int nval, int nrh, size_t nrest) {
+  std::vector<Float> out((size_t)nval * nrh * nrest);
+  for (size_t r = 0; r < nrest; ++r)
+    for (int irh = 0; irh < nrh; ++irh)
+      for (int iv = 0; iv < nval; ++iv)
+        out[irh + (size_t)nrh * (iv + (size_t)nval * r)] = src[iv + (size_t)nval * (irh + (size_t)nrh * r)];
+  return out;
+}
+
+rrtmgpb_aerosol_optics_t* rrtmgpb_aerosol_optics_load(const rrtmgpb_aerosol_lut* lut, char* errmsg) {
+  if (!lut || !lut->aero_dust_tbl || !lut->aero_salt_tbl || !lut->aero_sulf_tbl || !lut->aero_bcar_tbl ||
+      !lut->aero_bcar_rh_tbl || !lut->aero_ocar_tbl || !lut->aero_ocar_rh_tbl || !lut->merra_aero_bin_lims ||
+      !lut->aero_rh) {
+    fail(errmsg, "aerosol optics: no data has been initialized");
+    return nullptr;
+  }
+  if (lut->nval != 3 || lut->nrh < 1 || lut->nbin < 1 || lut->nbnd < 1) {
+    fail(errmsg, "aerosol_optics%load_lut(): array aero_salt_tbl isn't consistently sized");
+    return nullptr;
+  }
+  rrtmgpb_aerosol_optics_t* ao = new rrtmgpb_aerosol_optics_t();
+  ao->nbnd = lut->nbnd; ao->nval = lut->nval; ao->nrh = lut->nrh; ao->nbin = lut->nbin;
+  if (lut->band_lims_wvn) ao->band_lims_wvn_h.assign(lut->band_lims_wvn, lut->band_lims_wvn + 2 * lut->nbnd);
+  ao->min_size = lut->merra_aero_bin_lims[0];
+  ao->max_size = lut->merra_aero_bin_lims[2 * (lut->nbin - 1) + 1];
+  const int nval = lut->nval, nrh = lut->nrh, nbin = lut->nbin, nbnd = lut->nbnd;
+  ao->bin_lims = upload(lut->merra_aero_bin_lims, 2 * (size_t)nbin);
+  ao->aero_rh = upload(lut->aero_rh, (size_t)nrh);
+  ao->dust = upload(lut->aero_dust_tbl, (size_t)nval * nbin * nbnd);
+  ao->bcar = upload(lut->aero_bcar_tbl, (size_t)nval * nbnd);
+  ao->ocar = upload(lut->aero_ocar_tbl, (size_t)nval * nbnd);
+  {
+    const std::vector<Float> salt = swap_first_two(lut->aero_salt_tbl, nval, nrh, (size_t)nbin * nbnd);
+    const std::vector<Float> sulf = swap_first_two(lut->aero_sulf_tbl, nval, nrh, (size_t)nbnd);
+    const std::vector<Float> bcrh = swap_first_two(lut->aero_bcar_rh_tbl, nval, nrh, (size_t)nbnd);
+    const std::vector<Float> ocrh = swap_first_two(lut->aero_ocar_rh_tbl, nval, nrh, (size_t)nbnd);
+    ao->salt = upload(salt.data(), salt.size());
+    ao->sulf = upload(sulf.data(), sulf.size());
+    ao->bcar_rh = upload(bcrh.data(), bcrh.size());
+    ao->ocar_rh = upload(ocrh.data(), ocrh.size());
+    rrtmgpb_sync();  // the host staging vectors die at the end of this scope
+  }
+  ok(errmsg);
+  return ao;
+}
+
+void rrtmgpb_aerosol_optics_free(rrtmgpb_aerosol_optics_t* ao) {
+  if (!ao) return;
+  void* ptrs[] = {ao->bin_lims, ao->aero_rh, ao->dust, ao->salt, ao->sulf, ao->bcar, ao->bcar_rh, ao->ocar, ao->ocar_rh};
+  for (void* p : ptrs) rrtmgpb_mem_free(p);
+  delete ao;
+}
+
+int rrtmgpb_aerosol_optics(const rrtmgpb_aerosol_optics_t* ao, int ncol, int nlay, const int* aero_type,
+                           const Float* aero_size, const Float* aero_mass, const Float* relhum,
+                           rrtmgpb_optical_props* op, char* errmsg) {
+  if (!ao) return fail(errmsg, "aerosol optics: no data has been initialized");  // :278-281
+  const size_t ncl = (size_t)ncol * nlay;
+  std::string msg;
+  if (g_check_extents) {  // :297-310 (the 2-D inputs carry no extents across a C interface)
+    if (op->ncol != ncol || op->nlay != nlay) msg = "aerosol optics: optical_props have wrong extents";
+    if (!msg.empty()) return fail(errmsg, msg);
+  }
+  if (g_check_values) {  // :315-323
+    if (op->nband != ao->nbnd) msg = "aerosol optics: optical properties don't have the same band structure";
+    if (op->band_lims_wvn && !ao->band_lims_wvn_h.empty()) {
+      rrtmgpb_optical_props self = *op;
+      self.band_lims_wvn = ao->band_lims_wvn_h.data();
+      self.nband = ao->nbnd;
+      if (!bands_are_equal(&self, op)) msg = "aerosol optics: optical properties don't have the same band structure";
+    }
+    if (op->nband != op->ngpt) msg = "aerosol optics: optical properties must be requested by band not g-points";
+    if (rrtmgpb_any_int_vals_outside(ncl, aero_type, 0, 7)) msg = "aerosol optics: aerosol type is out of bounds";
+    if (!msg.empty()) return fail(errmsg, msg);
+    Scratch<Bool> aeromsk(ncl);  // :343-347
+    rrtmgpb_aerosol_mask(ncol, nlay, aero_type, aeromsk);
+    if (rrtmgpb_any_vals_outside(ncl, aero_size, aeromsk, ao->min_size, ao->max_size))  // :352-357
+      msg = "aerosol optics: requested aerosol size is out of bounds";
+    if (rrtmgpb_any_vals_outside(ncl, relhum, aeromsk, 0, 1))
+      msg = "aerosol optics: relative humidity fraction is out of bounds";
+    if (!msg.empty()) return fail(errmsg, msg);
+  }
+  if (op->kind == RRTMGPB_NSTR) return fail(errmsg, "aerosol optics: n-stream calculations not yet supported");  // :419
+  rrtmgpb_aerosol_optics_from_table(ncol, nlay, ao->nval, ao->nrh, ao->nbin, ao->nbnd, op->kind, aero_type, aero_size,
+                                    aero_mass, relhum, ao->bin_lims, ao->aero_rh, ao->dust, ao->salt, ao->sulf,
+                                    ao->bcar_rh, ao->bcar, ao->ocar_rh, ao->ocar, op->tau, op->ssa, op->g);
   return ok(errmsg);
 }
 

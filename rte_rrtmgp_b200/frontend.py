@@ -59,6 +59,13 @@ class _CloudLutStruct(C.Structure):
                 + [(n, C.c_void_p) for n in ("extliq", "ssaliq", "asyliq", "extice", "ssaice", "asyice")])
 
 
+class _AerosolLutStruct(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("nbnd", "nval", "nrh", "nbin")]
+                + [(n, C.c_void_p) for n in ("band_lims_wvn", "merra_aero_bin_lims", "aero_rh", "aero_dust_tbl",
+                                             "aero_salt_tbl", "aero_sulf_tbl", "aero_bcar_tbl", "aero_bcar_rh_tbl",
+                                             "aero_ocar_tbl", "aero_ocar_rh_tbl")])
+
+
 def _addr(x):
     return None if x is None else _ptr(x).value
 
@@ -73,7 +80,7 @@ class Context:
 
     def __init__(self, lib, device=None):
         self.lib, self.device, self.c = lib, device, lib.cdll
-        for fn in ("rrtmgpb_gas_optics_load", "rrtmgpb_cloud_optics_load"):
+        for fn in ("rrtmgpb_gas_optics_load", "rrtmgpb_cloud_optics_load", "rrtmgpb_aerosol_optics_load"):
             getattr(self.c, fn).restype = C.c_void_p
 
     def zeros(self, shape, dtype=np.float64):
@@ -336,5 +343,45 @@ class CloudOptics:
     def __del__(self):
         try:
             self.ctx.c.rrtmgpb_cloud_optics_free(C.c_void_p(self.handle))
+        except Exception:
+            pass
+
+
+class AerosolOptics:
+    """ty_aerosol_optics_rrtmgp_merra (mo_aerosol_optics_rrtmgp_merra.F90:62,99,233)."""
+
+    def __init__(self, ctx, lut):
+        self.ctx, self.lut, self._keep = ctx, lut, []
+
+        def h(a):
+            a = np.asfortranarray(a, dtype=np.float64)
+            self._keep.append(a)
+            return a.ctypes.data
+
+        s = _AerosolLutStruct()
+        s.nbnd, s.nval, s.nrh, s.nbin = lut.nbnd, lut.nval, lut.nrh, lut.nbin
+        for n in ("band_lims_wvn", "merra_aero_bin_lims", "aero_rh", "aero_dust_tbl", "aero_salt_tbl", "aero_sulf_tbl",
+                  "aero_bcar_tbl", "aero_bcar_rh_tbl", "aero_ocar_tbl", "aero_ocar_rh_tbl"):
+            setattr(s, n, h(getattr(lut, n)))
+        err = C.create_string_buffer(ERRLEN)
+        self.handle = ctx.c.rrtmgpb_aerosol_optics_load(C.byref(s), err)
+        if not self.handle:
+            raise RuntimeError(err.value.decode())
+        nb = lut.nbnd
+        self.band_lims_gpt = np.asfortranarray(np.stack([np.arange(1, nb + 1), np.arange(1, nb + 1)]), dtype=np.int32)
+        self.band_lims_wvn = lut.band_lims_wvn
+
+    def aerosol_optics(self, aero_type, aero_size, aero_mass, relhum, optical_props):
+        err = C.create_string_buffer(ERRLEN)
+        o = optical_props.struct()
+        P = lambda x: C.c_void_p(_addr(x))
+        ncol, nlay = aero_type.shape  # ncol = size(aero_type,1), nlay = size(aero_type,2), :284-285
+        _check(self.ctx.c.rrtmgpb_aerosol_optics(C.c_void_p(self.handle), int(ncol), int(nlay),
+                                                 P(aero_type), P(aero_size), P(aero_mass), P(relhum), C.byref(o),
+                                                 err), err)
+
+    def __del__(self):
+        try:
+            self.ctx.c.rrtmgpb_aerosol_optics_free(C.c_void_p(self.handle))
         except Exception:
             pass

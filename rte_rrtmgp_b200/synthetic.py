@@ -315,6 +315,70 @@ def compute_clouds(prof, lut):
     return dict(lwp=_f(lwp), iwp=_f(iwp), rel=_f(rel), dei=_f(dei))
 
 
+# ----------------------------------------------------------------------------------------------
+class AerosolLUT:
+    """MERRA aerosol LUT with the loader's schema (mo_optics_utils_rrtmgp.F90:364-397): tables as load_lut()
+    receives them, i.e. the rh-dependent ones shaped (nval, nrh, ...)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def make_aerosol_lut(kdist, seed=11, nrh=36, nbin=5):
+    rng = np.random.default_rng(seed + (0 if kdist.is_lw else 1))
+    nb, nval = kdist.nbnd, 3
+    lims = np.array([[0.1, 1.0], [1.0, 1.8], [1.8, 3.0], [3.0, 6.0], [6.0, 10.0]][:nbin]).T  # (pair, nbin), microns
+    rh = np.concatenate([np.linspace(0.0, 0.8, nrh - 10, endpoint=False), np.linspace(0.8, 0.99, 10)])
+    ssa_hi = 0.5 if kdist.is_lw else 0.99
+
+    def tbl(*shape):
+        t = np.empty((nval,) + shape)
+        t[0] = rng.uniform(50.0, 5000.0, shape)   # mass extinction coefficient (m2/kg)
+        t[1] = rng.uniform(0.2, ssa_hi, shape)    # single-scattering albedo
+        t[2] = rng.uniform(0.3, 0.85, shape)      # asymmetry
+        return _f(t)
+
+    def tbl_rh(*shape):  # smooth growth with humidity so interpolation is exercised
+        base = tbl(*shape)  # (nval, ...)
+        growth = 1.0 + np.array([1.5, 0.02, 0.1])[:, None] * rh[None, :] ** 2  # (nval, nrh)
+        out = base[:, None, ...] * growth.reshape((nval, nrh) + (1,) * len(shape))
+        out[1] = np.minimum(out[1], 0.999)
+        return _f(out)
+
+    return AerosolLUT(nbnd=nb, nval=nval, nrh=nrh, nbin=nbin, band_lims_wvn=kdist.band_lims_wvn,
+                      merra_aero_bin_lims=_f(lims), aero_rh=_f(rh), aero_dust_tbl=tbl(nbin, nb),
+                      aero_salt_tbl=tbl_rh(nbin, nb), aero_sulf_tbl=tbl_rh(nb), aero_bcar_tbl=tbl(nb),
+                      aero_bcar_rh_tbl=tbl_rh(nb), aero_ocar_tbl=tbl(nb), aero_ocar_rh_tbl=tbl_rh(nb))
+
+
+def get_relhum(p_lay, t_lay, vmr_h2o):
+    """rrtmgp_allsky.F90:744-784 (m_h2o, m_dry from mo_gas_optics_constants.F90)."""
+    m_h2o, m_dry = 0.018016, 0.028964
+    mwd, t_ref, q_lay_min = m_h2o / m_dry, 273.16, 1.0e-7
+    mmr = vmr_h2o * mwd
+    q_lay = mmr / (1 + mmr)
+    q_tmp = np.maximum(q_lay_min, q_lay)
+    es_tmp = np.exp((17.67 * (t_lay - t_ref)) / (t_lay - 29.65))
+    rh = (0.263 * p_lay * q_tmp) / es_tmp
+    return _f(0.01 * rh)
+
+
+def compute_aerosols(prof, col_offset=0):
+    """rrtmgp_allsky.F90:664-738: sulfate (type 3) at 50-100 hPa, dust (type 1) at 700-900 hPa, in the columns
+    with odd 1-based index (the reference's `is_even_column = mod(icol,2) /= 0`)."""
+    p_lay = prof["p_lay"]
+    ncol, nlay = p_lay.shape
+    icol = np.arange(1 + col_offset, ncol + 1 + col_offset)[:, None]
+    sel = icol % 2 != 0
+    is_sulf = (p_lay > 50.0 * 100.0) & (p_lay < 100.0 * 100.0) & sel
+    is_dust = (p_lay > 700.0 * 100.0) & (p_lay < 900.0 * 100.0) & sel & ~is_sulf
+    aero_type = np.where(is_sulf, 3, np.where(is_dust, 1, 0)).astype(np.int32)
+    aero_size = np.where(is_sulf, 0.2, np.where(is_dust, 0.5, 0.0))
+    aero_mass = np.where(is_sulf, 1.0e-6, np.where(is_dust, 3.0e-5, 0.0))
+    relhum = get_relhum(p_lay, prof["t_lay"], prof["q"])
+    return dict(aero_type=np.asfortranarray(aero_type), aero_size=_f(aero_size), aero_mass=_f(aero_mass), relhum=relhum)
+
+
 def perturbed_profiles(ncol, nlay, seed=1234, top_at_1=True):
     """RFMIP-like stand-in: `ncol` DISTINCT columns = the analytic profile with per-column
     SST in [285,310] K and humidity/ozone scaled by 0.5-2x, so neighbouring columns hit different table
