@@ -19,8 +19,8 @@ class AllSky:
         """do_aerosols: rrtmgp_allsky.F90:233-236,664-738.  lw_2stream: LW with 2-stream optical properties and
         rte_lw(use_2stream=.true.) (BASELINE config 5); the solver then returns g-point fluxes, which are summed
         with rte_sum_broadband (the reference leaves the broadband arrays unfilled here)."""
-        if fused is None:  # the express path; off by default until it beats the kernel-by-kernel sequence (DESIGN.md section 4)
-            fused = os.environ.get("RRTMGPB_FUSED", "0") == "1"
+        if fused is None:  # fused gas optics (+ cloud increment) by default; RRTMGPB_FUSED=0: the reference's kernel-by-kernel sequence
+            fused = os.environ.get("RRTMGPB_FUSED", "1") == "1"
         self.ctx, self.ncol, self.nlay, self.fused = ctx, ncol, nlay, fused
         self.do_aerosols, self.lw_2stream = do_aerosols, lw_2stream
         prof = profiles if profiles is not None else syn.compute_profiles(300.0, ncol, nlay)

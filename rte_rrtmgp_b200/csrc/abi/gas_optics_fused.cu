@@ -19,6 +19,10 @@
 #include <cuda.h>
 #include <cstdint>
 #include "../kernels/elementwise.cuh"
+#include "../kernels/gas_optics_gfast.cuh"
+#include <map>
+#include <mutex>
+#include <vector>
 #include "rrtmgp_b200_ext.h"
 
 using namespace rrtmgpb;
@@ -27,26 +31,6 @@ namespace {
 
 constexpr int kFThreads = 128;
 constexpr int kFG = 8;  // g-points per register chunk
-
-struct CellState {  // struct-of-arrays over cells
-  Float *col_dry, *ftemp, *fpress;
-  int *jtemp, *jpress;
-  Bool* tropo;
-};
-
-struct FusedParams {
-  rrtmgpb_gas_tables t;
-  int ncol, nlay;
-  const Float *play, *plev, *tlay, *vmr, *col_dry_in;
-  CellState cs;
-  const int2 *range_lower, *range_upper;
-  // outputs
-  int op_kind;  // 1: tau ; 2: tau, ssa, g
-  Float *tau, *ssa, *g;
-  // optional by-band cloud increment (kind 0 = none; 1 = 1scl tau ; 2 = 2str tau, ssa, g)
-  int cld_kind;
-  const Float *cld_tau, *cld_ssa, *cld_g;
-};
 
 // ---- per-cell state: mo_gas_optics_utils.F90:143-150 (col_dry), mo_gas_optics_rrtmgp_kernels.F90:99-118 ----
 __global__ void __launch_bounds__(kFThreads) cell_state_kernel(const FusedParams p, Float m_dry, Float m_h2o,
@@ -82,43 +66,6 @@ __global__ void __launch_bounds__(kFThreads) cell_state_kernel(const FusedParams
   p.cs.tropo[c] = pl > press_ref_trop;
 }
 
-// ---- weights of one flavour for one cell: mo_gas_optics_rrtmgp_kernels.F90:121-168 ----
-struct FlavW {
-  Float cm[2], fmn[4], fmj[8];
-  int je[2];
-};
-
-// col_gas(igas) = igas == 0 ? col_dry : vmr(igas)*col_dry   (mo_gas_optics_rrtmgp.F90:594-609)
-__device__ __forceinline__ Float col_gas_of(const FusedParams& p, size_t c, size_t ncl, int igas, Float col_dry) {
-  return igas == 0 ? col_dry : p.vmr[c + ncl * (size_t)(igas - 1)] * col_dry;
-}
-
-__device__ __forceinline__ void flavor_weights(const FusedParams& p, size_t c, size_t ncl, int iflav, int itropo,
-                                               int jtemp, Float ftemp, Float fpress, Float col_dry, FlavW& w) {
-  const rrtmgpb_gas_tables& t = p.t;
-  const int igas_1 = __ldg(t.flavor + 2 * iflav), igas_2 = __ldg(t.flavor + 2 * iflav + 1);
-  const Float cg1 = col_gas_of(p, c, ncl, igas_1, col_dry), cg2 = col_gas_of(p, c, ncl, igas_2, col_dry);
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const int jt = jtemp + it;
-    const Float ratio_eta_half = __ldg(t.vmr_ref + itropo + 2 * (igas_1 + (t.ngas + 1) * (jt - 1))) /
-                                 __ldg(t.vmr_ref + itropo + 2 * (igas_2 + (t.ngas + 1) * (jt - 1)));
-    const Float colmix = cg1 + ratio_eta_half * cg2;
-    const Float eta = (colmix > (Float)2 * (Float)RB_TINY) ? cg1 / colmix : (Float)0.5;
-    const Float loceta = eta * (Float)(t.neta - 1);
-    w.je[it] = min((int)loceta + 1, t.neta - 1);
-    const Float feta = loceta - trunc(loceta);
-    const Float ftemp_term = ((Float)(1 - it) + (Float)(2 * it - 1) * ftemp);
-    w.cm[it] = colmix;
-    w.fmn[2 * it + 0] = ((Float)1 - feta) * ftemp_term;
-    w.fmn[2 * it + 1] = feta * ftemp_term;
-    w.fmj[4 * it + 0] = ((Float)1 - fpress) * w.fmn[2 * it + 0];
-    w.fmj[4 * it + 1] = ((Float)1 - fpress) * w.fmn[2 * it + 1];
-    w.fmj[4 * it + 2] = fpress * w.fmn[2 * it + 0];
-    w.fmj[4 * it + 3] = fpress * w.fmn[2 * it + 1];
-  }
-}
-
 template <int NT, int NE, int NP1>
 struct FDims {
   int nt, ne, np1;
@@ -128,7 +75,7 @@ struct FDims {
   __device__ __forceinline__ int s_g() const { return (NT && NE && NP1) ? NT * NE * NP1 : nt * ne * np1; }
 };
 
-struct MinorSet {
+struct MinorSetO {  // loader-layout tables (legacy kernels)
   int n;
   const int2* band_range;
   const Float* kminor;
@@ -150,10 +97,10 @@ __global__ void __launch_bounds__(kFThreads, 4) gas_tau_fused_kernel(const Fused
   const int itropo = tropo ? 0 : 1;
   const int jpress = jpress0 + itropo + 1;  // :390
   const Float play = p.play[c], tlay = p.tlay[c];
-  const MinorSet ms = tropo ? MinorSet{t.nminorlower, p.range_lower, t.kminor_lower, t.minor_limits_gpt_lower,
+  const MinorSetO ms = tropo ? MinorSetO{t.nminorlower, p.range_lower, t.kminor_lower, t.minor_limits_gpt_lower,
                                        t.idx_minor_lower, t.idx_minor_scaling_lower, t.kminor_start_lower,
                                        t.minor_scales_with_density_lower, t.scale_by_complement_lower}
-                            : MinorSet{t.nminorupper, p.range_upper, t.kminor_upper, t.minor_limits_gpt_upper,
+                            : MinorSetO{t.nminorupper, p.range_upper, t.kminor_upper, t.minor_limits_gpt_upper,
                                        t.idx_minor_upper, t.idx_minor_scaling_upper, t.kminor_start_upper,
                                        t.minor_scales_with_density_upper, t.scale_by_complement_upper};
   const Float amount_rayl = SW ? col_gas_of(p, c, ncl, t.idx_h2o, col_dry) + col_dry : (Float)0;  // :559
@@ -281,21 +228,6 @@ __global__ void __launch_bounds__(kFThreads, 4) gas_tau_fused_kernel(const Fused
 }
 
 // ---- Planck sources: compute_Planck_source :568-710 with weights recomputed per (cell, band) ----
-struct PlanckFusedParams {
-  FusedParams f;
-  const Float *tlev, *tsfc;
-  int sfc_lay;
-  Float *sfc_src, *lay_src, *lev_src, *sfc_source_Jac;
-};
-
-__device__ __forceinline__ Float planck_band_f(const rrtmgpb_gas_tables& t, Float T, Float delta_r, const Float* tab) {
-  const Float val0 = (T - t.temp_ref_min) * delta_r;  // interpolate1D :731-735
-  const Float frac = val0 - trunc(val0);
-  const int index = min(t.nPlanckTemp - 1, max(1, (int)val0 + 1));
-  const Float t0 = __ldg(tab + index - 1), t1 = __ldg(tab + index);
-  return t0 + frac * (t1 - t0);
-}
-
 template <int NT, int NE, int NP1>
 __global__ void __launch_bounds__(kFThreads, 4) planck_fused_kernel(const PlanckFusedParams q) {
   const FusedParams& p = q.f;
@@ -445,10 +377,10 @@ __global__ void __launch_bounds__(kFThreads, 3) gas_tau_tma_kernel(const FusedPa
   const int s_eta_g = t.ntemp, s_p_g = t.ntemp * t.neta;
   const long long s_g_g = (long long)s_p_g * (t.npres + 1);
   const Float play = p.play[c], tlay = p.tlay[c];
-  const MinorSet ms = tropo ? MinorSet{t.nminorlower, p.range_lower, t.kminor_lower, t.minor_limits_gpt_lower,
+  const MinorSetO ms = tropo ? MinorSetO{t.nminorlower, p.range_lower, t.kminor_lower, t.minor_limits_gpt_lower,
                                        t.idx_minor_lower, t.idx_minor_scaling_lower, t.kminor_start_lower,
                                        t.minor_scales_with_density_lower, t.scale_by_complement_lower}
-                            : MinorSet{t.nminorupper, p.range_upper, t.kminor_upper, t.minor_limits_gpt_upper,
+                            : MinorSetO{t.nminorupper, p.range_upper, t.kminor_upper, t.minor_limits_gpt_upper,
                                        t.idx_minor_upper, t.idx_minor_scaling_upper, t.kminor_start_upper,
                                        t.minor_scales_with_density_upper, t.scale_by_complement_upper};
   const Float amount_rayl = SW ? col_gas_of(p, c, ncl, t.idx_h2o, col_dry) + col_dry : (Float)0;
@@ -711,9 +643,106 @@ bool make_table_tmap(CUtensorMap* tm, const Float* base, const rrtmgpb_gas_table
   return r == CUDA_SUCCESS;
 }
 
+
+// ---- g-point-fastest table copies, built once per k-distribution (kernels/gas_optics_gfast.cuh) ----
+struct TableCacheEntry {
+  TablesT tt;
+  std::vector<void*> owned;
+  int ntemp, neta, npres, ngpt, nkl, nku;
+};
+std::mutex g_tc_mutex;
+std::map<const void*, TableCacheEntry> g_table_cache;  // key: the loader-layout kmajor pointer
+
+Float* transposed(const Float* in, int nrow, int ng, int pitch, std::vector<void*>& owned) {
+  if (!in || nrow <= 0 || ng <= 0) return nullptr;
+  Float* out = static_cast<Float*>(dev_alloc((size_t)nrow * pitch * sizeof(Float)));
+  RB_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)nrow * pitch * sizeof(Float), stream()));
+  dim3 grid(ceil_div(nrow, 32), ceil_div(ng, 32)), block(32, 8);
+  transpose_table_kernel<<<grid, block, 0, stream()>>>(in, out, nrow, ng, pitch);
+  RB_LAUNCH_CHECK();
+  owned.push_back(out);
+  return out;
+}
+
+std::vector<int> host_ints(const int* dev, size_t n) {
+  std::vector<int> h(n);
+  if (n) RB_CUDA_CHECK(cudaMemcpyAsync(h.data(), dev, n * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+  RB_CUDA_CHECK(cudaStreamSynchronize(stream()));
+  return h;
+}
+
+// 128-bit table loads need every band and every minor-contributor interval to start on an even 0-based
+// column and to have even length (true for the rrtmgp-data k-distributions: 16 g-points per band)
+bool intervals_even(const std::vector<int>& lims, const std::vector<int>* start) {
+  for (size_t i = 0; i + 1 < lims.size(); i += 2) {
+    if ((lims[i] & 1) == 0 || ((lims[i + 1] - lims[i] + 1) & 1)) return false;
+    if (start && ((*start)[i / 2] & 1) == 0) return false;
+  }
+  return true;
+}
+
+TablesT tables_gfast(const rrtmgpb_gas_tables& t) {
+  std::lock_guard<std::mutex> lock(g_tc_mutex);
+  auto it = g_table_cache.find(t.kmajor);
+  if (it != g_table_cache.end()) {
+    const TableCacheEntry& e = it->second;
+    if (e.ntemp == t.ntemp && e.neta == t.neta && e.npres == t.npres && e.ngpt == t.ngpt && e.nkl == t.nminorklower &&
+        e.nku == t.nminorkupper)
+      return e.tt;
+    for (void* q : e.owned) dev_free(q);
+    g_table_cache.erase(it);
+  }
+  TableCacheEntry e;
+  e.ntemp = t.ntemp; e.neta = t.neta; e.npres = t.npres; e.ngpt = t.ngpt; e.nkl = t.nminorklower; e.nku = t.nminorkupper;
+  const int tn = t.ntemp * t.neta, rows = tn * (t.npres + 1);
+  TablesT& tt = e.tt;
+  tt.gp = (t.ngpt + 1) & ~1;
+  tt.nkl = (t.nminorklower + 1) & ~1;
+  tt.nku = (t.nminorkupper + 1) & ~1;
+  tt.kmajor = transposed(t.kmajor, rows, t.ngpt, tt.gp, e.owned);
+  tt.pfrac = transposed(t.planck_frac, rows, t.ngpt, tt.gp, e.owned);
+  tt.kminor_lower = transposed(t.kminor_lower, tn, t.nminorklower, tt.nkl, e.owned);
+  tt.kminor_upper = transposed(t.kminor_upper, tn, t.nminorkupper, tt.nku, e.owned);
+  tt.krayl = nullptr;  // (ntemp, neta, ngpt, 2): the two tropo slices are transposed separately
+  if (t.krayl) {
+    Float* kr = static_cast<Float*>(dev_alloc((size_t)2 * tn * tt.gp * sizeof(Float)));
+    RB_CUDA_CHECK(cudaMemsetAsync(kr, 0, (size_t)2 * tn * tt.gp * sizeof(Float), stream()));
+    for (int itropo = 0; itropo < 2; ++itropo) {
+      dim3 grid(ceil_div(tn, 32), ceil_div(t.ngpt, 32)), block(32, 8);
+      transpose_table_kernel<<<grid, block, 0, stream()>>>(t.krayl + (size_t)tn * t.ngpt * itropo,
+                                                           kr + (size_t)tn * tt.gp * itropo, tn, t.ngpt, tt.gp);
+      RB_LAUNCH_CHECK();
+    }
+    e.owned.push_back(kr);
+    tt.krayl = kr;
+  }
+  const std::vector<int> bl = host_ints(t.band_lims_gpt, 2 * (size_t)t.nbnd);
+  const std::vector<int> ll = host_ints(t.minor_limits_gpt_lower, 2 * (size_t)t.nminorlower);
+  const std::vector<int> lu = host_ints(t.minor_limits_gpt_upper, 2 * (size_t)t.nminorupper);
+  const std::vector<int> sl = host_ints(t.kminor_start_lower, (size_t)t.nminorlower);
+  const std::vector<int> su = host_ints(t.kminor_start_upper, (size_t)t.nminorupper);
+  tt.vec = (sizeof(Float) == 8 && intervals_even(bl, nullptr) && intervals_even(ll, &sl) && intervals_even(lu, &su)) ? 2 : 1;
+  g_table_cache[t.kmajor] = e;
+  return e.tt;
+}
+
+int g_gas_kernels = -1;  // 0: legacy loader-layout kernels, 1: g-point-fastest kernels (default)
+bool gfast_enabled() {
+  if (g_gas_kernels < 0) { const char* v = std::getenv("RRTMGPB_GAS_KERNELS"); g_gas_kernels = (v && v[0] == '0') ? 0 : 1; }
+  return g_gas_kernels == 1;
+}
+
 }  // namespace
 
 namespace rrtmgpb {
+// called by rrtmgpb_mem_free(): a k-distribution that is being released takes its transposed copies with it
+void table_cache_release(const void* key) {
+  std::lock_guard<std::mutex> lock(g_tc_mutex);
+  auto it = g_table_cache.find(key);
+  if (it == g_table_cache.end()) return;
+  for (void* q : it->second.owned) dev_free(q);
+  g_table_cache.erase(it);
+}
 void fused_set_constants(double grav, double m_dry) { g_grav = grav; g_m_dry = m_dry; }
 }
 
@@ -738,7 +767,17 @@ void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, c
     KernelTimer timer(sw ? "gas_tau_fused[sw]" : "gas_tau_fused[lw]");
     const int grid = ceil_div((long long)ncl, kFThreads);
     CUtensorMap tm;
-    if (make_table_tmap(&tm, t->kmajor, *t)) {
+    if (gfast_enabled() && !tma_enabled()) {
+      const TablesT tt = tables_gfast(*t);
+      dim3 g2(grid, t->nbnd);
+      if (sw) {
+        if (tt.vec == 2) gas_tau_g_kernel<true, 2><<<g2, kGThreads, 0, stream()>>>(p, tt);
+        else gas_tau_g_kernel<true, 1><<<g2, kGThreads, 0, stream()>>>(p, tt);
+      } else {
+        if (tt.vec == 2) gas_tau_g_kernel<false, 2><<<g2, kGThreads, 0, stream()>>>(p, tt);
+        else gas_tau_g_kernel<false, 1><<<g2, kGThreads, 0, stream()>>>(p, tt);
+      }
+    } else if (make_table_tmap(&tm, t->kmajor, *t)) {
       // TMA-staged major-absorber table (box of kTB x 9 x kPB x kGB doubles per band, double-buffered)
       const size_t smem = (size_t)2 * kGB * kPB * 9 * kTB * sizeof(Float);
       if (sw) {
@@ -763,7 +802,13 @@ void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, c
     q.sfc_src = sfc_src; q.lay_src = lay_src; q.lev_src = lev_src; q.sfc_source_Jac = sfc_source_Jac;
     KernelTimer timer("planck_fused");
     dim3 grid(ceil_div(ncol, kFThreads), t->nbnd);
-    if (std_dims(*t)) planck_fused_kernel<14, 9, 60><<<grid, kFThreads, 0, stream()>>>(q);
+    if (gfast_enabled()) {
+      const TablesT tt = tables_gfast(*t);
+      const int lay_per_chunk = 9, nchunk = ceil_div(nlay, lay_per_chunk);
+      dim3 g3(ceil_div(ncol, kGThreads), t->nbnd, nchunk);
+      if (tt.vec == 2) planck_g_kernel<2><<<g3, kGThreads, 0, stream()>>>(q, tt, lay_per_chunk);
+      else planck_g_kernel<1><<<g3, kGThreads, 0, stream()>>>(q, tt, lay_per_chunk);
+    } else if (std_dims(*t)) planck_fused_kernel<14, 9, 60><<<grid, kFThreads, 0, stream()>>>(q);
     else planck_fused_kernel<0, 0, 0><<<grid, kFThreads, 0, stream()>>>(q);
     RB_LAUNCH_CHECK();
   }

@@ -59,6 +59,7 @@ struct OpName {
   } while (0)
 
 void fused_set_constants(double grav, double m_dry);  // gas_optics_fused.cu
+void table_cache_release(const void* key);            // gas_optics_fused.cu: drops the g-fastest copies keyed by a table
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -103,13 +103,18 @@ def _smooth_table(rng, ntemp, neta, npres1, ngpt, lo, hi):
     return _f(10.0 ** (a + bt * t + be * e * e + bp * np.sin(3.0 * p) + noise))
 
 
-def _minor(rng, nbnd, band_lims_gpt, ngas, ntemp, neta, max_per_band, lo, hi):
+def _minor(rng, nbnd, band_lims_gpt, ngas, ntemp, neta, max_per_band, lo, hi, partial=False):
+    """partial=True: contributor intervals cover a random sub-range of their band (the kernels allow it;
+    rrtmgp-data intervals always cover whole bands)."""
     lims, dens, comp, idx, idxs, start = [], [], [], [], [], []
     k = 1
     for b in range(nbnd):
         n = int(rng.integers(0, max_per_band + 1))
         for _ in range(n):
             gs, ge = int(band_lims_gpt[0, b]), int(band_lims_gpt[1, b])
+            if partial and ge > gs:
+                a, c = sorted(int(v) for v in rng.integers(gs, ge + 1, 2))
+                gs, ge = a, c
             lims.append((gs, ge))
             d = bool(rng.integers(0, 2))
             dens.append(d)
@@ -136,21 +141,25 @@ def _minor(rng, nbnd, band_lims_gpt, ngas, ntemp, neta, max_per_band, lo, hi):
     )
 
 
-def make_kdist(kind="lw", ngpt=None, seed=42, gpt_per_band=None, nminor_per_band=4):
+def make_kdist(kind="lw", ngpt=None, seed=42, gpt_per_band=None, nminor_per_band=4, band_sizes=None):
     """Synthetic k-distribution.  kind 'lw': 16 bands (256 or 128 g-points), Planck tables;
     kind 'sw': 14 bands (224 or 112 g-points), Rayleigh + solar source.  `gpt_per_band` shrinks it
-    for unit tests."""
+    for unit tests; `band_sizes` (one entry per band) makes the bands ragged and the minor-contributor
+    intervals partial."""
     rng = np.random.default_rng(seed + (0 if kind == "lw" else 1000))
     is_lw = kind == "lw"
     nbnd = 16 if is_lw else 14
     if gpt_per_band is None:
         gpt_per_band = 16 if ngpt is None else ngpt // nbnd
-    ngpt = nbnd * gpt_per_band
+    sizes = np.full(nbnd, gpt_per_band) if band_sizes is None else np.asarray(band_sizes, dtype=int)
+    assert sizes.shape == (nbnd,) and sizes.min() >= 1
+    ngpt = int(sizes.sum())
     ngas, ntemp, npres, neta = len(GAS_NAMES), 14, 59, 9
-    band_lims_gpt = _f(np.array([[b * gpt_per_band + 1, (b + 1) * gpt_per_band] for b in range(nbnd)]).T, np.int32)
+    ends = np.cumsum(sizes)
+    band_lims_gpt = _f(np.stack([ends - sizes + 1, ends]), np.int32)
     edges = np.linspace(10.0, 3250.0, nbnd + 1) if is_lw else np.linspace(820.0, 50000.0, nbnd + 1)
     band_lims_wvn = _f(np.stack([edges[:-1], edges[1:]]))
-    gpoint_bands = np.repeat(np.arange(1, nbnd + 1), gpt_per_band).astype(np.int32)
+    gpoint_bands = np.repeat(np.arange(1, nbnd + 1), sizes).astype(np.int32)
     # key species per (pair, atmos layer, band); (0,0) is rewritten to (2,2) by create_flavor
     # (mo_gas_optics_rrtmgp.F90:1568-1576)
     choices = [(1, 2), (1, 3), (1, 4), (1, 6), (1, 0), (2, 3), (2, 0), (3, 0), (6, 2), (7, 0), (0, 0)]
@@ -179,8 +188,9 @@ def make_kdist(kind="lw", ngpt=None, seed=42, gpt_per_band=None, nminor_per_band
             vmr_ref[a, :, it] = base * rng.uniform(0.5, 1.5, ngas + 1)
     vmr_ref[:, 0, :] = 1.0
     kmajor = _smooth_table(rng, ntemp, neta, npres + 1, ngpt, -26.0, -21.5)
-    lo = _minor(rng, nbnd, band_lims_gpt, ngas, ntemp, neta, nminor_per_band, -27.0, -23.0)
-    up = _minor(rng, nbnd, band_lims_gpt, ngas, ntemp, neta, max(nminor_per_band // 2, 1), -27.0, -23.0)
+    partial = band_sizes is not None
+    lo = _minor(rng, nbnd, band_lims_gpt, ngas, ntemp, neta, nminor_per_band, -27.0, -23.0, partial)
+    up = _minor(rng, nbnd, band_lims_gpt, ngas, ntemp, neta, max(nminor_per_band // 2, 1), -27.0, -23.0, partial)
     kd = KDist(
         is_lw=is_lw, gas_names=list(GAS_NAMES), ngas=ngas, nflav=flavor.shape[1], neta=neta, npres=npres,
         ntemp=ntemp, nbnd=nbnd, ngpt=ngpt, flavor=flavor, gpoint_flavor=gpoint_flavor,
@@ -202,9 +212,10 @@ def make_kdist(kind="lw", ngpt=None, seed=42, gpt_per_band=None, nminor_per_band
     kd.extra["nminorlower"], kd.extra["nminorupper"] = lo["n"], up["n"]
     if is_lw:
         pf = rng.uniform(0.2, 1.0, (ntemp, neta, npres + 1, ngpt))
-        pf *= np.linspace(1.5, 0.5, gpt_per_band)[None, None, None, :].repeat(nbnd, axis=3).reshape(1, 1, 1, ngpt)
+        if band_sizes is None:
+            pf *= np.linspace(1.5, 0.5, gpt_per_band)[None, None, None, :].repeat(nbnd, axis=3).reshape(1, 1, 1, ngpt)
         for b in range(nbnd):
-            s = slice(b * gpt_per_band, (b + 1) * gpt_per_band)
+            s = slice(int(ends[b] - sizes[b]), int(ends[b]))
             pf[..., s] /= pf[..., s].sum(axis=3, keepdims=True)
         kd.planck_frac = _f(pf)
         tgrid = 160.0 + np.arange(196.0)

@@ -76,6 +76,27 @@ def test_clear_sky_and_reduced_kdist(oracle_lib, cuda_lib):
                 assert np.max(np.abs(fg[k] - fc[k])) <= FLUX_ATOL, (k, clouds, fused)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("distinct", [False, True])
+def test_ragged_bands_and_partial_minor_intervals(oracle_lib, cuda_lib, distinct):
+    """Bands of 1..37 g-points (odd sizes -> 64-bit table loads; > 16 -> several register chunks) and minor
+    contributors covering part of a band: the layouts the g-point-fastest gas-optics kernels must not assume away."""
+    kd_lw = syn.make_kdist("lw", band_sizes=[3, 17, 16, 20, 1, 2, 37, 5, 16, 16, 7, 8, 9, 10, 11, 12], seed=5)
+    kd_sw = syn.make_kdist("sw", band_sizes=[16, 1, 33, 4, 6, 16, 18, 2, 3, 5, 7, 16, 16, 9], seed=6)
+    ncol, nlay = 70, 60
+    prof = syn.perturbed_profiles(ncol, nlay, seed=99, top_at_1=True) if distinct else None
+    c = _run(oracle_lib, None, ncol, nlay, kd_lw, kd_sw, profiles=prof)
+    for fused in (False, True):
+        g = _run(cuda_lib, "cuda:0", ncol, nlay, kd_lw, kd_sw, profiles=prof, fused=fused)
+        fg, fc = g.fluxes_host(), c.fluxes_host()
+        for k in fc:
+            assert np.max(np.abs(fg[k] - fc[k])) <= FLUX_ATOL, (k, fused)
+        for name, ga, ca in (("lw tau", g.lw.atmos.tau, c.lw.atmos.tau), ("lev_source", g.lw.sources.lev_source, c.lw.sources.lev_source),
+                             ("sfc_source", g.lw.sources.sfc_source, c.lw.sources.sfc_source),
+                             ("sw tau", g.sw.atmos.tau, c.sw.atmos.tau), ("sw ssa", g.sw.atmos.ssa, c.sw.atmos.ssa)):
+            np.testing.assert_allclose(g.ctx.get(ga), c.ctx.get(ca), rtol=1e-12, atol=1e-300, err_msg=f"{name} fused={fused}")
+
+
 def test_oracle_fused_entry_equals_reference_sequence(oracle_lib, kdists):
     """On the oracle the fused entry point is literally the reference sequence: results must be bit-identical."""
     kd_lw, kd_sw = kdists
