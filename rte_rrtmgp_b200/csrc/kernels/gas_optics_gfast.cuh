@@ -19,18 +19,44 @@
 //                      mo_gas_optics_rrtmgp_kernels.F90:613, never exists)
 // Arithmetic is the reference's, expression by expression (lines cited inline).
 #pragma once
+#include <type_traits>
 #include "../common.cuh"
 #include "rrtmgp_b200_ext.h"
 
 namespace rrtmgpb {
 
 constexpr int kGThreads = 128;
-constexpr int kGG = 16;  // g-points per register super-chunk (one band of the standard k-distributions)
+constexpr int kGG = 8;  // g-points per register chunk (a 16-g-point band of the standard k-distributions = 2 chunks)
 
-struct CellState {  // struct-of-arrays over cells
+// per-cell state, struct-of-arrays (cell_state_kernel): everything that does not depend on the band
+struct CellState {
   Float *col_dry, *ftemp, *fpress;
+  Float *pt_scale;   // 0.01*play/tlay                      (:467)
+  Float *vmr_fact;   // 1/col_gas(0)                        (:470)
+  Float *dry_fact;   // 1/(1 + col_gas(h2o)*vmr_fact)       (:471)
   int *jtemp, *jpress;
   Bool* tropo;
+};
+
+// Small per-band / per-contributor records, resolved once per k-distribution on the host (table cache) so that the
+// kernels' prologue is not a chain of dependent index loads (band_lims -> gpoint_flavor -> flavor -> vmr_ref ...).
+struct BandInfo {
+  int bS, bE;                   // 1-based g-point limits
+  int iflav[2];                 // 0-based flavour of the band's first g-point, [itropo]   (:384)
+  int igas1[2], igas2[2];       // the flavour's two gases, [itropo]                       (:121-122)
+  int mfirst[2], mlast[2];      // minor contributors overlapping the band, [itropo] (lower / upper set)
+};
+struct MinorInfo {
+  int mS, mE;                   // 1-based g-point limits of the contributor
+  int igas, isc;                // idx_minor, idx_minor_scaling (0: none)
+  int dens, comp;               // minor_scales_with_density, scale_by_complement
+  int kstart;                   // kminor_start (1-based table column of g-point mS)
+  int iflav, igas1, igas2;      // flavour of g-point mS in this contributor's atmosphere half (:487)
+};
+struct GasAux {
+  const BandInfo* band;
+  const MinorInfo *minor_lower, *minor_upper;
+  const Float* ratio;           // vmr_ref(itropo,igas1,jt)/vmr_ref(itropo,igas2,jt) as [itropo][iflav][jt]  (:127-128)
 };
 
 struct FusedParams {
@@ -38,7 +64,6 @@ struct FusedParams {
   int ncol, nlay;
   const Float *play, *plev, *tlay, *vmr, *col_dry_in;
   CellState cs;
-  const int2 *range_lower, *range_upper;
   // outputs
   int op_kind;  // 1: tau ; 2: tau, ssa, g
   Float *tau, *ssa, *g;
@@ -60,6 +85,7 @@ struct TablesT {
   int gp;        // row pitch of kmajor / pfrac / krayl (ngpt rounded up to a multiple of 2)
   int nkl, nku;  // row pitch of kminor_lower / kminor_upper
   int vec;       // 2: every band / minor interval starts on an even 0-based column and has even length
+  GasAux aux;
 };
 
 // ---- weights of one flavour for one cell: mo_gas_optics_rrtmgp_kernels.F90:121-168 ----
@@ -73,16 +99,16 @@ __device__ __forceinline__ Float col_gas_of(const FusedParams& p, size_t c, size
   return igas == 0 ? col_dry : p.vmr[c + ncl * (size_t)(igas - 1)] * col_dry;
 }
 
-__device__ __forceinline__ void flavor_weights(const FusedParams& p, size_t c, size_t ncl, int iflav, int itropo,
-                                               int jtemp, Float ftemp, Float fpress, Float col_dry, FlavW& w) {
+// ratio: the flavour's ratio_eta_half row, indexed by 0-based temperature
+__device__ __forceinline__ void flavor_weights_g(const FusedParams& p, size_t c, size_t ncl, int igas_1, int igas_2,
+                                                 const Float* __restrict__ ratio, int jtemp, Float ftemp, Float fpress,
+                                                 Float col_dry, FlavW& w) {
   const rrtmgpb_gas_tables& t = p.t;
-  const int igas_1 = __ldg(t.flavor + 2 * iflav), igas_2 = __ldg(t.flavor + 2 * iflav + 1);
   const Float cg1 = col_gas_of(p, c, ncl, igas_1, col_dry), cg2 = col_gas_of(p, c, ncl, igas_2, col_dry);
+  const Float rt0 = __ldg(ratio + jtemp - 1), rt1 = __ldg(ratio + jtemp);
 #pragma unroll
   for (int it = 0; it < 2; ++it) {
-    const int jt = jtemp + it;
-    const Float ratio_eta_half = __ldg(t.vmr_ref + itropo + 2 * (igas_1 + (t.ngas + 1) * (jt - 1))) /
-                                 __ldg(t.vmr_ref + itropo + 2 * (igas_2 + (t.ngas + 1) * (jt - 1)));
+    const Float ratio_eta_half = it ? rt1 : rt0;
     const Float colmix = cg1 + ratio_eta_half * cg2;
     const Float eta = (colmix > (Float)2 * (Float)RB_TINY) ? cg1 / colmix : (Float)0.5;
     const Float loceta = eta * (Float)(t.neta - 1);
@@ -98,15 +124,6 @@ __device__ __forceinline__ void flavor_weights(const FusedParams& p, size_t c, s
     w.fmj[4 * it + 3] = fpress * w.fmn[2 * it + 1];
   }
 }
-
-struct MinorSet {
-  int n;
-  const int2* band_range;
-  const Float* kminor;  // g-fastest copy
-  int pitch;
-  const int *limits_gpt, *idx_minor, *idx_scaling, *kminor_start;
-  const Bool *scales_with_density, *scale_by_complement;
-};
 
 // VEC consecutive table entries starting at p (16-byte aligned when VEC == 2)
 template <int VEC>
@@ -126,23 +143,19 @@ struct GLoad<2> {
 };
 
 // 3-D interpolation (interpolate3D_byflav :791-801) of n <= kGG consecutive g-points starting at 0-based
-// table column g0: out[i] = scale0*(4 terms of row set 0) + scale1*(4 terms of row set 1)
-template <int VEC>
+// table column g0: out[i] = scale0*(4 terms of row set 0) + scale1*(4 terms of row set 1).  FULL: n == kGG.
+template <int VEC, bool FULL>
 __device__ __forceinline__ void interp3d_g(const Float* __restrict__ tab, int gp, int row0, int row1, int s_eta, int s_p,
                                            int g0, int n, const Float (&f)[8], Float scale0, Float scale1,
                                            Float (&out)[kGG]) {
+  const size_t d_eta = (size_t)s_eta * gp, d_p = (size_t)s_p * gp;
   const Float* a0 = tab + (size_t)row0 * gp + g0;
-  const Float* a1 = a0 + (size_t)s_eta * gp;
-  const Float* a2 = a0 + (size_t)s_p * gp;
-  const Float* a3 = a2 + (size_t)s_eta * gp;
   const Float* b0 = tab + (size_t)row1 * gp + g0;
-  const Float* b1 = b0 + (size_t)s_eta * gp;
-  const Float* b2 = b0 + (size_t)s_p * gp;
-  const Float* b3 = b2 + (size_t)s_eta * gp;
 #pragma unroll
   for (int i = 0; i < kGG; i += VEC) {
-    if (i < n) {
-      const GLoad<VEC> x0(a0 + i), x1(a1 + i), x2(a2 + i), x3(a3 + i), y0(b0 + i), y1(b1 + i), y2(b2 + i), y3(b3 + i);
+    if (FULL || i < n) {
+      const GLoad<VEC> x0(a0 + i), x1(a0 + d_eta + i), x2(a0 + d_p + i), x3(a0 + d_p + d_eta + i);
+      const GLoad<VEC> y0(b0 + i), y1(b0 + d_eta + i), y2(b0 + d_p + i), y3(b0 + d_p + d_eta + i);
 #pragma unroll
       for (int v = 0; v < VEC; ++v)
         out[i + v] = scale0 * (f[0] * x0.v[v] + f[1] * x1.v[v] + f[2] * x2.v[v] + f[3] * x3.v[v]) +
@@ -153,24 +166,28 @@ __device__ __forceinline__ void interp3d_g(const Float* __restrict__ tab, int gp
 
 // ---------------------------------------------------------------------------------------------------
 // tau (+ ssa, g): compute_tau_absorption :176-338, compute_tau_rayleigh :506-565, combine_abs_and_rayleigh
-// (mo_gas_optics_rrtmgp.F90:1954-2002) and the by-band increment (mo_optical_props_kernels.F90:366-477)
+// (mo_gas_optics_rrtmgp.F90:1954-2002) and the by-band increment (mo_optical_props_kernels.F90:366-477).
+// Grid: 1-D, block = (128 consecutive cells, band) with the BAND fastest, so the blocks that share a cell range
+// (and its per-cell state, vmr and cloud inputs) are resident together and those inputs come from DRAM once.
 // ---------------------------------------------------------------------------------------------------
 template <bool SW, int VEC>
 __global__ void __launch_bounds__(kGThreads, 4) gas_tau_g_kernel(const FusedParams p, const TablesT tt) {
-  const size_t ncl = (size_t)p.ncol * p.nlay;
-  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncl) return;
   const rrtmgpb_gas_tables& t = p.t;
-  const int ibnd = blockIdx.y;
-  const int bS = __ldg(t.band_lims_gpt + 2 * ibnd), bE = __ldg(t.band_lims_gpt + 2 * ibnd + 1);
+  const size_t ncl = (size_t)p.ncol * p.nlay;
+  const int ibnd = blockIdx.x % t.nbnd;
+  const size_t c = (size_t)(blockIdx.x / t.nbnd) * blockDim.x + threadIdx.x;
+  if (c >= ncl) return;
+  const BandInfo bi = tt.aux.band[ibnd];
   const Float col_dry = p.cs.col_dry[c], ftemp = p.cs.ftemp[c], fpress = p.cs.fpress[c];
   const int jtemp = p.cs.jtemp[c], jpress0 = p.cs.jpress[c];
   const bool tropo = p.cs.tropo[c];
   const int itropo = tropo ? 0 : 1;
   const int jpress = jpress0 + itropo + 1;  // :390
-  const int iflav = __ldg(t.gpoint_flavor + itropo + 2 * (bS - 1)) - 1;  // :384 band's first g-point
+  // (explicit selects: indexing the register copy of BandInfo with a run-time itropo would push it to local memory)
+  const int iflav = tropo ? bi.iflav[0] : bi.iflav[1];
   FlavW w;
-  flavor_weights(p, c, ncl, iflav, itropo, jtemp, ftemp, fpress, col_dry, w);
+  flavor_weights_g(p, c, ncl, tropo ? bi.igas1[0] : bi.igas1[1], tropo ? bi.igas2[0] : bi.igas2[1],
+                   tt.aux.ratio + (size_t)(itropo * t.nflav + iflav) * t.ntemp, jtemp, ftemp, fpress, col_dry, w);
   const int s_eta = t.ntemp, s_p = t.ntemp * t.neta;
   const int row0 = (jtemp - 1) + s_eta * (w.je[0] - 1) + s_p * (jpress - 2);
   const int row1 = jtemp + s_eta * (w.je[1] - 1) + s_p * (jpress - 2);
@@ -181,60 +198,53 @@ __global__ void __launch_bounds__(kGThreads, 4) gas_tau_g_kernel(const FusedPara
     ct = p.cld_tau[cb];
     if (p.cld_kind == 2) { cw = p.cld_ssa[cb]; cg = p.cld_g[cb]; }
   }
-  const MinorSet ms = tropo ? MinorSet{t.nminorlower, p.range_lower, tt.kminor_lower, tt.nkl, t.minor_limits_gpt_lower,
-                                       t.idx_minor_lower, t.idx_minor_scaling_lower, t.kminor_start_lower,
-                                       t.minor_scales_with_density_lower, t.scale_by_complement_lower}
-                            : MinorSet{t.nminorupper, p.range_upper, tt.kminor_upper, tt.nku, t.minor_limits_gpt_upper,
-                                       t.idx_minor_upper, t.idx_minor_scaling_upper, t.kminor_start_upper,
-                                       t.minor_scales_with_density_upper, t.scale_by_complement_upper};
-  const int2 range = ms.band_range[ibnd];
-  const Float play = p.play[c], tlay = p.tlay[c];
+  const MinorInfo* minfo = tropo ? tt.aux.minor_lower : tt.aux.minor_upper;
+  const Float* kminor = tropo ? tt.kminor_lower : tt.kminor_upper;
+  const int mpitch = tropo ? tt.nkl : tt.nku;
+  const int mfirst = tropo ? bi.mfirst[0] : bi.mfirst[1], mlast = tropo ? bi.mlast[0] : bi.mlast[1];
   const Float amount_rayl = SW ? col_gas_of(p, c, ncl, t.idx_h2o, col_dry) + col_dry : (Float)0;  // :559
+  const Float eps3 = (Float)3.0 * (Float)RB_TINY;  // mo_optical_props_kernels.F90:38
 
-  for (int gS = bS; gS <= bE; gS += kGG) {
-    const int n = min(kGG, bE - gS + 1);
+  auto chunk = [&](int gS, int n, auto full_tag) {
+    constexpr bool FULL = decltype(full_tag)::value;
     Float acc[kGG];
     // ---- major absorbers: tau = 0 + major (:391 on a zeroed tau) ----
-    interp3d_g<VEC>(tt.kmajor, tt.gp, row0, row1, s_eta, s_p, gS - 1, n, w.fmj, w.cm[0], w.cm[1], acc);
+    interp3d_g<VEC, FULL>(tt.kmajor, tt.gp, row0, row1, s_eta, s_p, gS - 1, n, w.fmj, w.cm[0], w.cm[1], acc);
     // ---- minor absorbers touching this chunk (:451-498) ----
-    for (int imnr = range.x; imnr <= range.y; ++imnr) {
-      const int mS = __ldg(ms.limits_gpt + 2 * imnr), mE = __ldg(ms.limits_gpt + 2 * imnr + 1);
-      if (mE < gS || mS > gS + n - 1) continue;
-      Float scaling = col_gas_of(p, c, ncl, __ldg(ms.idx_minor + imnr), col_dry);
-      if (ms.scales_with_density[imnr]) {
-        scaling = scaling * ((Float)0.01 * play / tlay);
-        const int isc = __ldg(ms.idx_scaling + imnr);
-        if (isc > 0) {
-          const Float vmr_fact = (Float)1 / col_dry;
-          const Float dry_fact = (Float)1 / ((Float)1 + col_gas_of(p, c, ncl, t.idx_h2o, col_dry) * vmr_fact);
-          if (ms.scale_by_complement[imnr])
-            scaling = scaling * ((Float)1 - col_gas_of(p, c, ncl, isc, col_dry) * vmr_fact * dry_fact);
-          else
-            scaling = scaling * (col_gas_of(p, c, ncl, isc, col_dry) * vmr_fact * dry_fact);
+    for (int imnr = mfirst; imnr <= mlast; ++imnr) {
+      const MinorInfo mi = minfo[imnr];
+      if (mi.mE < gS || mi.mS > gS + n - 1) continue;
+      Float scaling = col_gas_of(p, c, ncl, mi.igas, col_dry);
+      if (mi.dens) {
+        scaling = scaling * p.cs.pt_scale[c];
+        if (mi.isc > 0) {
+          const Float vmr_fact = p.cs.vmr_fact[c], dry_fact = p.cs.dry_fact[c];
+          if (mi.comp) scaling = scaling * ((Float)1 - col_gas_of(p, c, ncl, mi.isc, col_dry) * vmr_fact * dry_fact);
+          else scaling = scaling * (col_gas_of(p, c, ncl, mi.isc, col_dry) * vmr_fact * dry_fact);
         }
       }
-      const int iflav_m = __ldg(t.gpoint_flavor + itropo + 2 * (mS - 1)) - 1;  // :487
       // the contributor's flavour is the band's flavour for rrtmgp-data (a contributor lives inside one band);
       // otherwise recompute its eta weights
       Float a0 = w.fmn[0], a1 = w.fmn[1], a2 = w.fmn[2], a3 = w.fmn[3];
       int je0 = w.je[0], je1 = w.je[1];
-      if (iflav_m != iflav) {
+      if (mi.iflav != iflav) {
         FlavW wm;
-        flavor_weights(p, c, ncl, iflav_m, itropo, jtemp, ftemp, fpress, col_dry, wm);
+        flavor_weights_g(p, c, ncl, mi.igas1, mi.igas2, tt.aux.ratio + (size_t)(itropo * t.nflav + mi.iflav) * t.ntemp, jtemp,
+                         ftemp, fpress, col_dry, wm);
         a0 = wm.fmn[0]; a1 = wm.fmn[1]; a2 = wm.fmn[2]; a3 = wm.fmn[3];
         je0 = wm.je[0]; je1 = wm.je[1];
       }
       // table column of g-point gS+i: kminor_start + (gS+i - mS) - 1
-      const int kcol0 = __ldg(ms.kminor_start + imnr) + (gS - mS) - 1;
-      const Float* m0 = ms.kminor + (size_t)((jtemp - 1) + s_eta * (je0 - 1)) * ms.pitch + kcol0;
-      const Float* m1 = ms.kminor + (size_t)(jtemp + s_eta * (je1 - 1)) * ms.pitch + kcol0;
-      const Float* m0e = m0 + (size_t)s_eta * ms.pitch;
-      const Float* m1e = m1 + (size_t)s_eta * ms.pitch;
-      const int iS = mS - gS, iE = min(mE - gS, n - 1);  // chunk positions covered by this contributor
+      const int kcol0 = mi.kstart + (gS - mi.mS) - 1;
+      const size_t d_eta = (size_t)s_eta * mpitch;
+      const Float* m0 = kminor + (size_t)((jtemp - 1) + s_eta * (je0 - 1)) * mpitch + kcol0;
+      const Float* m1 = kminor + (size_t)(jtemp + s_eta * (je1 - 1)) * mpitch + kcol0;
+      const int iS = mi.mS - gS, iE = min(mi.mE - gS, n - 1);  // chunk positions covered by this contributor
+      const bool whole = FULL && iS <= 0 && iE == kGG - 1;
 #pragma unroll
       for (int i = 0; i < kGG; i += VEC) {
-        if (i >= iS && i <= iE) {  // VEC == 2: intervals start even and have even length (TablesT::vec)
-          const GLoad<VEC> x0(m0 + i), x1(m0e + i), y0(m1 + i), y1(m1e + i);
+        if (whole || (i >= iS && i <= iE)) {  // VEC == 2: intervals start even and have even length (TablesT::vec)
+          const GLoad<VEC> x0(m0 + i), x1(m0 + d_eta + i), y0(m1 + i), y1(m1 + d_eta + i);
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
             const Float kint = a0 * x0.v[v] + a1 * x1.v[v] + a2 * y0.v[v] + a3 * y1.v[v];  // :757-760
@@ -244,19 +254,19 @@ __global__ void __launch_bounds__(kGThreads, 4) gas_tau_g_kernel(const FusedPara
       }
     }
     // ---- Rayleigh (:554-559), combination, cloud increment, store ----
+    const size_t dr_eta = (size_t)s_eta * tt.gp;
     const Float* kr = SW ? tt.krayl + (size_t)s_p * tt.gp * itropo + (gS - 1) : nullptr;
     const Float* r0 = SW ? kr + (size_t)((jtemp - 1) + s_eta * (w.je[0] - 1)) * tt.gp : nullptr;
     const Float* r1 = SW ? kr + (size_t)(jtemp + s_eta * (w.je[1] - 1)) * tt.gp : nullptr;
-    const Float* r0e = SW ? r0 + (size_t)s_eta * tt.gp : nullptr;
-    const Float* r1e = SW ? r1 + (size_t)s_eta * tt.gp : nullptr;
-    const size_t o0 = c + ncl * (size_t)(gS - 1);
-    const Float eps3 = (Float)3.0 * (Float)RB_TINY;  // mo_optical_props_kernels.F90:38
+    Float* tau_o = p.tau + c + ncl * (size_t)(gS - 1);
+    Float* ssa_o = p.op_kind == 2 ? p.ssa + c + ncl * (size_t)(gS - 1) : nullptr;
+    Float* g_o = p.op_kind == 2 ? p.g + c + ncl * (size_t)(gS - 1) : nullptr;
 #pragma unroll
     for (int i0 = 0; i0 < kGG; i0 += VEC) {
-      if (i0 >= n) continue;
+      if (!FULL && i0 >= n) continue;
       Float ray[VEC];
       if (SW) {
-        const GLoad<VEC> x0(r0 + i0), x1(r0e + i0), y0(r1 + i0), y1(r1e + i0);
+        const GLoad<VEC> x0(r0 + i0), x1(r0 + dr_eta + i0), y0(r1 + i0), y1(r1 + dr_eta + i0);
 #pragma unroll
         for (int v = 0; v < VEC; ++v)
           ray[v] = (w.fmn[0] * x0.v[v] + w.fmn[1] * x1.v[v] + w.fmn[2] * y0.v[v] + w.fmn[3] * y1.v[v]) * amount_rayl;
@@ -286,13 +296,20 @@ __global__ void __launch_bounds__(kGThreads, 4) gas_tau_g_kernel(const FusedPara
             tt_ = tau12;
           }
         }
-        p.tau[o0 + ncl * i] = tt_;
+        *tau_o = tt_;
+        tau_o += ncl;
         if (p.op_kind == 2) {
-          p.ssa[o0 + ncl * i] = ss;
-          p.g[o0 + ncl * i] = gg;
+          *ssa_o = ss; *g_o = gg;
+          ssa_o += ncl; g_o += ncl;
         }
       }
     }
+  };
+
+  for (int gS = bi.bS; gS <= bi.bE; gS += kGG) {
+    const int n = min(kGG, bi.bE - gS + 1);
+    if (n == kGG) chunk(gS, n, std::true_type{});
+    else chunk(gS, n, std::false_type{});
   }
 }
 
@@ -307,43 +324,50 @@ __device__ __forceinline__ Float planck_band_f(const rrtmgpb_gas_tables& t, Floa
   return t0 + frac * (t1 - t0);
 }
 
-// Planck fractions of n g-points (from 0-based column g0) of the band whose first g-point is bS, at cell c (:627-631)
-template <int VEC>
-__device__ __forceinline__ void pfrac_of_cell(const FusedParams& p, const TablesT& tt, size_t c, size_t ncl, int bS, int g0,
-                                              int n, Float (&pf)[kGG]) {
+// Planck fractions of n g-points (from 0-based column g0) of band `bi` at cell c (:627-631)
+template <int VEC, bool FULL>
+__device__ __forceinline__ void pfrac_of_cell(const FusedParams& p, const TablesT& tt, const BandInfo& bi, size_t c, size_t ncl,
+                                              int g0, int n, Float (&pf)[kGG]) {
   const rrtmgpb_gas_tables& t = p.t;
-  const int itropo = p.cs.tropo[c] ? 0 : 1;
-  const int iflav = __ldg(t.gpoint_flavor + itropo + 2 * (bS - 1)) - 1;
+  const bool tropo = p.cs.tropo[c];
+  const int itropo = tropo ? 0 : 1;
   const int jtemp = p.cs.jtemp[c];
   const int jpress = p.cs.jpress[c] + itropo + 1;
   FlavW w;
-  flavor_weights(p, c, ncl, iflav, itropo, jtemp, p.cs.ftemp[c], p.cs.fpress[c], p.cs.col_dry[c], w);
+  flavor_weights_g(p, c, ncl, tropo ? bi.igas1[0] : bi.igas1[1], tropo ? bi.igas2[0] : bi.igas2[1],
+                   tt.aux.ratio + (size_t)(itropo * t.nflav + (tropo ? bi.iflav[0] : bi.iflav[1])) * t.ntemp, jtemp,
+                   p.cs.ftemp[c], p.cs.fpress[c], p.cs.col_dry[c], w);
   const int s_eta = t.ntemp, s_p = t.ntemp * t.neta;
   const int row0 = (jtemp - 1) + s_eta * (w.je[0] - 1) + s_p * (jpress - 2);
   const int row1 = jtemp + s_eta * (w.je[1] - 1) + s_p * (jpress - 2);
-  interp3d_g<VEC>(tt.pfrac, tt.gp, row0, row1, s_eta, s_p, g0, n, w.fmj, (Float)1, (Float)1, pf);
+  interp3d_g<VEC, FULL>(tt.pfrac, tt.gp, row0, row1, s_eta, s_p, g0, n, w.fmj, (Float)1, (Float)1, pf);
 }
 
+// Grid: 1-D, block = (128 consecutive columns, chunk of layers, band), band fastest.
 template <int VEC>
-__global__ void __launch_bounds__(kGThreads, 4) planck_g_kernel(const PlanckFusedParams q, const TablesT tt, int lay_per_chunk) {
+__global__ void __launch_bounds__(kGThreads, 4) planck_g_kernel(const PlanckFusedParams q, const TablesT tt, int lay_per_chunk,
+                                                                int nchunk) {
   const FusedParams& p = q.f;
   const rrtmgpb_gas_tables& t = p.t;
-  const int icol = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ibnd = blockIdx.x % t.nbnd;
+  const int rest = blockIdx.x / t.nbnd;
+  const int ichunk = rest % nchunk;
+  const int icol = (rest / nchunk) * blockDim.x + threadIdx.x;
   if (icol >= p.ncol) return;
-  const int ibnd = blockIdx.y;
-  const int l0 = blockIdx.z * lay_per_chunk, l1 = min(p.nlay, l0 + lay_per_chunk);
+  const int l0 = ichunk * lay_per_chunk, l1 = min(p.nlay, l0 + lay_per_chunk);
   const size_t ncol = p.ncol, ncl = ncol * p.nlay, nclp = ncol * (p.nlay + 1);
-  const int bS = __ldg(t.band_lims_gpt + 2 * ibnd), bE = __ldg(t.band_lims_gpt + 2 * ibnd + 1);
+  const BandInfo bi = tt.aux.band[ibnd];
   const Float delta_r = (Float)1.0 / t.totplnk_delta;
   const Float* tab = t.totplnk + (size_t)t.nPlanckTemp * ibnd;
-  for (int gS = bS; gS <= bE; gS += kGG) {
-    const int n = min(kGG, bE - gS + 1);
+
+  auto chunk = [&](int gS, int n, auto full_tag) {
+    constexpr bool FULL = decltype(full_tag)::value;
     Float pf_prev[kGG];
-    if (l0 > 0) pfrac_of_cell<VEC>(p, tt, icol + ncol * (size_t)(l0 - 1), ncl, bS, gS - 1, n, pf_prev);
+    if (l0 > 0) pfrac_of_cell<VEC, FULL>(p, tt, bi, icol + ncol * (size_t)(l0 - 1), ncl, gS - 1, n, pf_prev);
     for (int ilay = l0; ilay < l1; ++ilay) {
       const size_t c = icol + ncol * ilay;
       Float pf[kGG];
-      pfrac_of_cell<VEC>(p, tt, c, ncl, bS, gS - 1, n, pf);
+      pfrac_of_cell<VEC, FULL>(p, tt, bi, c, ncl, gS - 1, n, pf);
       const Float B_lay = planck_band_f(t, p.tlay[c], delta_r, tab);
       const Float B_lev = planck_band_f(t, q.tlev[c], delta_r, tab);
       const bool is_sfc = (ilay == q.sfc_lay - 1);
@@ -357,11 +381,12 @@ __global__ void __launch_bounds__(kGThreads, 4) planck_g_kernel(const PlanckFuse
       Float* lev_c = q.lev_src + c + nclp * (size_t)(gS - 1);
 #pragma unroll
       for (int i = 0; i < kGG; ++i) {
-        if (i < n) {
-          lay_c[ncl * i] = pf[i] * B_lay;                                                  // :640
-          lev_c[nclp * i] = (ilay == 0) ? pf[i] * B_lev : sqrt(pf_prev[i] * pf[i]) * B_lev;  // :695-701
+        if (FULL || i < n) {
+          *lay_c = pf[i] * B_lay;                                                         // :640
+          *lev_c = (ilay == 0) ? pf[i] * B_lev : sqrt(pf_prev[i] * pf[i]) * B_lev;        // :695-701
+          lay_c += ncl; lev_c += nclp;
           if (is_sfc) {
-            q.sfc_src[icol + ncol * (size_t)(gS + i - 1)] = pf[i] * B_sfc;                  // :650-653
+            q.sfc_src[icol + ncol * (size_t)(gS + i - 1)] = pf[i] * B_sfc;                 // :650-653
             q.sfc_source_Jac[icol + ncol * (size_t)(gS + i - 1)] = pf[i] * (B_sfc1 - B_sfc);
           }
           pf_prev[i] = pf[i];
@@ -372,8 +397,14 @@ __global__ void __launch_bounds__(kGThreads, 4) planck_g_kernel(const PlanckFuse
       const Float B_top = planck_band_f(t, q.tlev[icol + ncol * p.nlay], delta_r, tab);
 #pragma unroll
       for (int i = 0; i < kGG; ++i)
-        if (i < n) q.lev_src[icol + ncol * p.nlay + nclp * (size_t)(gS + i - 1)] = pf_prev[i] * B_top;
+        if (FULL || i < n) q.lev_src[icol + ncol * p.nlay + nclp * (size_t)(gS + i - 1)] = pf_prev[i] * B_top;
     }
+  };
+
+  for (int gS = bi.bS; gS <= bi.bE; gS += kGG) {
+    const int n = min(kGG, bi.bE - gS + 1);
+    if (n == kGG) chunk(gS, n, std::true_type{});
+    else chunk(gS, n, std::false_type{});
   }
 }
 
