@@ -324,26 +324,35 @@ __device__ __forceinline__ Float planck_band_f(const rrtmgpb_gas_tables& t, Floa
   return t0 + frac * (t1 - t0);
 }
 
-// Planck fractions of n g-points (from 0-based column g0) of band `bi` at cell c (:627-631)
-template <int VEC, bool FULL>
-__device__ __forceinline__ void pfrac_of_cell(const FusedParams& p, const TablesT& tt, const BandInfo& bi, size_t c, size_t ncl,
-                                              int g0, int n, Float (&pf)[kGG]) {
+constexpr int kPG = 2 * kGG;  // g-points per pass of the Planck kernel (previous layer's fractions stay in registers)
+
+// interpolation weights and table rows of band `bi` at cell c (:121-168, :390)
+__device__ __forceinline__ void planck_cell_weights(const FusedParams& p, const TablesT& tt, const BandInfo& bi, size_t c,
+                                                    size_t ncl, FlavW& w, int& row0, int& row1) {
   const rrtmgpb_gas_tables& t = p.t;
   const bool tropo = p.cs.tropo[c];
   const int itropo = tropo ? 0 : 1;
   const int jtemp = p.cs.jtemp[c];
   const int jpress = p.cs.jpress[c] + itropo + 1;
-  FlavW w;
   flavor_weights_g(p, c, ncl, tropo ? bi.igas1[0] : bi.igas1[1], tropo ? bi.igas2[0] : bi.igas2[1],
                    tt.aux.ratio + (size_t)(itropo * t.nflav + (tropo ? bi.iflav[0] : bi.iflav[1])) * t.ntemp, jtemp,
                    p.cs.ftemp[c], p.cs.fpress[c], p.cs.col_dry[c], w);
   const int s_eta = t.ntemp, s_p = t.ntemp * t.neta;
-  const int row0 = (jtemp - 1) + s_eta * (w.je[0] - 1) + s_p * (jpress - 2);
-  const int row1 = jtemp + s_eta * (w.je[1] - 1) + s_p * (jpress - 2);
-  interp3d_g<VEC, FULL>(tt.pfrac, tt.gp, row0, row1, s_eta, s_p, g0, n, w.fmj, (Float)1, (Float)1, pf);
+  row0 = (jtemp - 1) + s_eta * (w.je[0] - 1) + s_p * (jpress - 2);
+  row1 = jtemp + s_eta * (w.je[1] - 1) + s_p * (jpress - 2);
 }
 
-// Grid: 1-D, block = (128 consecutive columns, chunk of layers, band), band fastest.
+// Planck fractions (:627-631) of the n <= kGG g-points from 0-based table column g0
+template <int VEC>
+__device__ __forceinline__ void planck_fractions(const FusedParams& p, const TablesT& tt, const FlavW& w, int row0, int row1,
+                                                 int g0, int n, Float (&pf)[kGG]) {
+  const int s_eta = p.t.ntemp, s_p = p.t.ntemp * p.t.neta;
+  if (n == kGG) interp3d_g<VEC, true>(tt.pfrac, tt.gp, row0, row1, s_eta, s_p, g0, n, w.fmj, (Float)1, (Float)1, pf);
+  else interp3d_g<VEC, false>(tt.pfrac, tt.gp, row0, row1, s_eta, s_p, g0, n, w.fmj, (Float)1, (Float)1, pf);
+}
+
+// Grid: 1-D, block = (128 consecutive columns, chunk of layers, band), band fastest.  A thread marches down its
+// layers; per layer the weights are computed once and the band's g-points are produced kGG at a time.
 template <int VEC>
 __global__ void __launch_bounds__(kGThreads, 4) planck_g_kernel(const PlanckFusedParams q, const TablesT tt, int lay_per_chunk,
                                                                 int nchunk) {
@@ -360,14 +369,28 @@ __global__ void __launch_bounds__(kGThreads, 4) planck_g_kernel(const PlanckFuse
   const Float delta_r = (Float)1.0 / t.totplnk_delta;
   const Float* tab = t.totplnk + (size_t)t.nPlanckTemp * ibnd;
 
-  auto chunk = [&](int gS, int n, auto full_tag) {
-    constexpr bool FULL = decltype(full_tag)::value;
-    Float pf_prev[kGG];
-    if (l0 > 0) pfrac_of_cell<VEC, FULL>(p, tt, bi, icol + ncol * (size_t)(l0 - 1), ncl, gS - 1, n, pf_prev);
+  for (int gS = bi.bS; gS <= bi.bE; gS += kPG) {
+    const int n = min(kPG, bi.bE - gS + 1);
+    Float pf_prev[kPG];
+    if (l0 > 0) {  // the chunk's first level also needs the layer above it
+      FlavW w;
+      int row0, row1;
+      planck_cell_weights(p, tt, bi, icol + ncol * (size_t)(l0 - 1), ncl, w, row0, row1);
+#pragma unroll
+      for (int sub = 0; sub < kPG; sub += kGG) {
+        if (sub < n) {
+          Float pf[kGG];
+          planck_fractions<VEC>(p, tt, w, row0, row1, gS - 1 + sub, min(kGG, n - sub), pf);
+#pragma unroll
+          for (int i = 0; i < kGG; ++i) pf_prev[sub + i] = pf[i];
+        }
+      }
+    }
     for (int ilay = l0; ilay < l1; ++ilay) {
       const size_t c = icol + ncol * ilay;
-      Float pf[kGG];
-      pfrac_of_cell<VEC, FULL>(p, tt, bi, c, ncl, gS - 1, n, pf);
+      FlavW w;
+      int row0, row1;
+      planck_cell_weights(p, tt, bi, c, ncl, w, row0, row1);
       const Float B_lay = planck_band_f(t, p.tlay[c], delta_r, tab);
       const Float B_lev = planck_band_f(t, q.tlev[c], delta_r, tab);
       const bool is_sfc = (ilay == q.sfc_lay - 1);
@@ -380,31 +403,33 @@ __global__ void __launch_bounds__(kGThreads, 4) planck_g_kernel(const PlanckFuse
       Float* lay_c = q.lay_src + c + ncl * (size_t)(gS - 1);
       Float* lev_c = q.lev_src + c + nclp * (size_t)(gS - 1);
 #pragma unroll
-      for (int i = 0; i < kGG; ++i) {
-        if (FULL || i < n) {
-          *lay_c = pf[i] * B_lay;                                                         // :640
-          *lev_c = (ilay == 0) ? pf[i] * B_lev : sqrt(pf_prev[i] * pf[i]) * B_lev;        // :695-701
-          lay_c += ncl; lev_c += nclp;
-          if (is_sfc) {
-            q.sfc_src[icol + ncol * (size_t)(gS + i - 1)] = pf[i] * B_sfc;                 // :650-653
-            q.sfc_source_Jac[icol + ncol * (size_t)(gS + i - 1)] = pf[i] * (B_sfc1 - B_sfc);
+      for (int sub = 0; sub < kPG; sub += kGG) {
+        if (sub < n) {
+          const int ns = min(kGG, n - sub);
+          Float pf[kGG];
+          planck_fractions<VEC>(p, tt, w, row0, row1, gS - 1 + sub, ns, pf);
+#pragma unroll
+          for (int i = 0; i < kGG; ++i) {
+            if (i < ns) {
+              *lay_c = pf[i] * B_lay;                                                          // :640
+              *lev_c = (ilay == 0) ? pf[i] * B_lev : sqrt(pf_prev[sub + i] * pf[i]) * B_lev;   // :695-701
+              lay_c += ncl; lev_c += nclp;
+              if (is_sfc) {
+                q.sfc_src[icol + ncol * (size_t)(gS + sub + i - 1)] = pf[i] * B_sfc;            // :650-653
+                q.sfc_source_Jac[icol + ncol * (size_t)(gS + sub + i - 1)] = pf[i] * (B_sfc1 - B_sfc);
+              }
+              pf_prev[sub + i] = pf[i];
+            }
           }
-          pf_prev[i] = pf[i];
         }
       }
     }
     if (l1 == p.nlay) {  // :703-705
       const Float B_top = planck_band_f(t, q.tlev[icol + ncol * p.nlay], delta_r, tab);
 #pragma unroll
-      for (int i = 0; i < kGG; ++i)
-        if (FULL || i < n) q.lev_src[icol + ncol * p.nlay + nclp * (size_t)(gS + i - 1)] = pf_prev[i] * B_top;
+      for (int i = 0; i < kPG; ++i)
+        if (i < n) q.lev_src[icol + ncol * p.nlay + nclp * (size_t)(gS + i - 1)] = pf_prev[i] * B_top;
     }
-  };
-
-  for (int gS = bi.bS; gS <= bi.bE; gS += kGG) {
-    const int n = min(kGG, bi.bE - gS + 1);
-    if (n == kGG) chunk(gS, n, std::true_type{});
-    else chunk(gS, n, std::false_type{});
   }
 }
 
