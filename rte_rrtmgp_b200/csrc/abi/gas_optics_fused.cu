@@ -211,7 +211,7 @@ TablesT tables_gfast(const rrtmgpb_gas_tables& t) {
       int first = nminor[a], last = -1;
       for (int i = 0; i < nminor[a]; ++i)
         if (mh[a].lim[2 * i + 1] >= bi.bS && mh[a].lim[2 * i] <= bi.bE) { first = std::min(first, i); last = std::max(last, i); }
-      bi.mfirst[a] = first; bi.mlast[a] = last;
+      bi.mfirst[a] = first; bi.mlast[a] = last; bi.mdiff[a] = 0;
     }
   }
   std::vector<MinorInfo> minfo[2];
@@ -225,6 +225,8 @@ TablesT tables_gfast(const rrtmgpb_gas_tables& t) {
       mi.kstart = mh[a].ks[i];
       mi.iflav = (mi.mS >= 1 && mi.mS <= t.ngpt) ? gf[a + 2 * (mi.mS - 1)] - 1 : 0;
       mi.igas1 = fl[2 * mi.iflav]; mi.igas2 = fl[2 * mi.iflav + 1];
+      for (int b = 0; b < t.nbnd; ++b)
+        if (i >= bands[b].mfirst[a] && i <= bands[b].mlast[a] && mi.iflav != bands[b].iflav[a]) bands[b].mdiff[a] = 1;
     }
   }
   // ratio_eta_half = vmr_ref(itropo,igas_1,jt) / vmr_ref(itropo,igas_2,jt), mo_gas_optics_rrtmgp_kernels.F90:127-128
@@ -281,7 +283,7 @@ void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, c
   const bool sw = t->krayl != nullptr;
   {
     KernelTimer timer(sw ? "gas_tau_fused[sw]" : "gas_tau_fused[lw]");
-    const unsigned grid = (unsigned)((long long)ceil_div((long long)ncl, kGThreads) * t->nbnd);
+    const unsigned grid = (unsigned)((long long)ceil_div((long long)ncl, kTauCells * kGThreads) * t->nbnd);
     if (sw) {
       if (tt.vec == 2) gas_tau_g_kernel<true, 2><<<grid, kGThreads, 0, stream()>>>(p, tt);
       else gas_tau_g_kernel<true, 1><<<grid, kGThreads, 0, stream()>>>(p, tt);

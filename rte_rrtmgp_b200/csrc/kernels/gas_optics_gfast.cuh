@@ -21,6 +21,7 @@
 #pragma once
 #include <type_traits>
 #include "../common.cuh"
+#include "fastmath.cuh"
 #include "rrtmgp_b200_ext.h"
 
 namespace rrtmgpb {
@@ -45,6 +46,7 @@ struct BandInfo {
   int iflav[2];                 // 0-based flavour of the band's first g-point, [itropo]   (:384)
   int igas1[2], igas2[2];       // the flavour's two gases, [itropo]                       (:121-122)
   int mfirst[2], mlast[2];      // minor contributors overlapping the band, [itropo] (lower / upper set)
+  int mdiff[2];                 // 1: some of them has a flavour other than the band's
 };
 struct MinorInfo {
   int mS, mE;                   // 1-based g-point limits of the contributor
@@ -167,149 +169,248 @@ __device__ __forceinline__ void interp3d_g(const Float* __restrict__ tab, int gp
 // ---------------------------------------------------------------------------------------------------
 // tau (+ ssa, g): compute_tau_absorption :176-338, compute_tau_rayleigh :506-565, combine_abs_and_rayleigh
 // (mo_gas_optics_rrtmgp.F90:1954-2002) and the by-band increment (mo_optical_props_kernels.F90:366-477).
-// Grid: 1-D, block = (128 consecutive cells, band) with the BAND fastest, so the blocks that share a cell range
-// (and its per-cell state, vmr and cloud inputs) are resident together and those inputs come from DRAM once.
+//
+// Grid: 1-D, block = (kTauCells x 128 consecutive cells, band) with the BAND fastest, so the blocks that share a
+// cell range (and its per-cell state, vmr and cloud inputs) are resident together and those inputs come from DRAM
+// once.  A thread owns kTauCells cells 128 apart (same layer, neighbouring columns).  When they interpolate between
+// the same table rows - the rule for neighbouring columns - every table entry is loaded ONCE and applied to all of
+// them: the kernel is bound by L1 -> register bandwidth (8..18 table values per output value), and sharing the
+// loads divides that traffic, and the latency waited for per output, by kTauCells.  Otherwise each cell is processed
+// on its own.
 // ---------------------------------------------------------------------------------------------------
-template <bool SW, int VEC>
-__global__ void __launch_bounds__(kGThreads, 4) gas_tau_g_kernel(const FusedParams p, const TablesT tt) {
+constexpr int kTauCells = 2;
+constexpr int kTG = 4;  // g-points per register chunk of the tau kernel
+
+struct TauCell {
+  size_t c;       // cell index (clamped into range; `valid` says whether it may be stored)
+  bool valid;
+  Float col_dry, ct, cw, cg, amount_rayl;
+  FlavW w;
+};
+
+// NC cells that share tropo, jtemp and the table rows (row0, row1 => je[0], je[1]) of band `bi`
+template <bool SW, int VEC, int NC>
+__device__ __forceinline__ void tau_band_cells(const FusedParams& p, const TablesT& tt, const BandInfo& bi, bool tropo,
+                                               int jtemp, int row0, int row1, TauCell (&cell)[NC]) {
   const rrtmgpb_gas_tables& t = p.t;
   const size_t ncl = (size_t)p.ncol * p.nlay;
-  const int ibnd = blockIdx.x % t.nbnd;
-  const size_t c = (size_t)(blockIdx.x / t.nbnd) * blockDim.x + threadIdx.x;
-  if (c >= ncl) return;
-  const BandInfo bi = tt.aux.band[ibnd];
-  const Float col_dry = p.cs.col_dry[c], ftemp = p.cs.ftemp[c], fpress = p.cs.fpress[c];
-  const int jtemp = p.cs.jtemp[c], jpress0 = p.cs.jpress[c];
-  const bool tropo = p.cs.tropo[c];
   const int itropo = tropo ? 0 : 1;
-  const int jpress = jpress0 + itropo + 1;  // :390
-  // (explicit selects: indexing the register copy of BandInfo with a run-time itropo would push it to local memory)
   const int iflav = tropo ? bi.iflav[0] : bi.iflav[1];
-  FlavW w;
-  flavor_weights_g(p, c, ncl, tropo ? bi.igas1[0] : bi.igas1[1], tropo ? bi.igas2[0] : bi.igas2[1],
-                   tt.aux.ratio + (size_t)(itropo * t.nflav + iflav) * t.ntemp, jtemp, ftemp, fpress, col_dry, w);
   const int s_eta = t.ntemp, s_p = t.ntemp * t.neta;
-  const int row0 = (jtemp - 1) + s_eta * (w.je[0] - 1) + s_p * (jpress - 2);
-  const int row1 = jtemp + s_eta * (w.je[1] - 1) + s_p * (jpress - 2);
-  // cloud properties of this (cell, band), if the caller wants them added (mo_optical_props.F90:956-1000)
-  Float ct = 0, cw = 0, cg = 0;
-  if (p.cld_kind) {
-    const size_t cb = c + ncl * (size_t)ibnd;
-    ct = p.cld_tau[cb];
-    if (p.cld_kind == 2) { cw = p.cld_ssa[cb]; cg = p.cld_g[cb]; }
-  }
+  const int je0 = cell[0].w.je[0], je1 = cell[0].w.je[1];
   const MinorInfo* minfo = tropo ? tt.aux.minor_lower : tt.aux.minor_upper;
   const Float* kminor = tropo ? tt.kminor_lower : tt.kminor_upper;
   const int mpitch = tropo ? tt.nkl : tt.nku;
   const int mfirst = tropo ? bi.mfirst[0] : bi.mfirst[1], mlast = tropo ? bi.mlast[0] : bi.mlast[1];
-  const Float amount_rayl = SW ? col_gas_of(p, c, ncl, t.idx_h2o, col_dry) + col_dry : (Float)0;  // :559
   const Float eps3 = (Float)3.0 * (Float)RB_TINY;  // mo_optical_props_kernels.F90:38
 
   auto chunk = [&](int gS, int n, auto full_tag) {
     constexpr bool FULL = decltype(full_tag)::value;
-    Float acc[kGG];
-    // ---- major absorbers: tau = 0 + major (:391 on a zeroed tau) ----
-    interp3d_g<VEC, FULL>(tt.kmajor, tt.gp, row0, row1, s_eta, s_p, gS - 1, n, w.fmj, w.cm[0], w.cm[1], acc);
+    Float acc[NC][kTG];
+    // ---- major absorbers: tau = 0 + major (:391 on a zeroed tau); interpolate3D_byflav :791-801 ----
+    {
+      const size_t d_eta = (size_t)s_eta * tt.gp, d_p = (size_t)s_p * tt.gp;
+      const Float* a0 = tt.kmajor + (size_t)row0 * tt.gp + (gS - 1);
+      const Float* b0 = tt.kmajor + (size_t)row1 * tt.gp + (gS - 1);
+#pragma unroll
+      for (int i = 0; i < kTG; i += VEC) {
+        if (FULL || i < n) {
+          const GLoad<VEC> x0(a0 + i), x1(a0 + d_eta + i), x2(a0 + d_p + i), x3(a0 + d_p + d_eta + i);
+          const GLoad<VEC> y0(b0 + i), y1(b0 + d_eta + i), y2(b0 + d_p + i), y3(b0 + d_p + d_eta + i);
+#pragma unroll
+          for (int k = 0; k < NC; ++k) {
+            const Float(&f)[8] = cell[k].w.fmj;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+              acc[k][i + v] = cell[k].w.cm[0] * (f[0] * x0.v[v] + f[1] * x1.v[v] + f[2] * x2.v[v] + f[3] * x3.v[v]) +
+                              cell[k].w.cm[1] * (f[4] * y0.v[v] + f[5] * y1.v[v] + f[6] * y2.v[v] + f[7] * y3.v[v]);
+          }
+        }
+      }
+    }
     // ---- minor absorbers touching this chunk (:451-498) ----
     for (int imnr = mfirst; imnr <= mlast; ++imnr) {
       const MinorInfo mi = minfo[imnr];
       if (mi.mE < gS || mi.mS > gS + n - 1) continue;
-      Float scaling = col_gas_of(p, c, ncl, mi.igas, col_dry);
-      if (mi.dens) {
-        scaling = scaling * p.cs.pt_scale[c];
-        if (mi.isc > 0) {
-          const Float vmr_fact = p.cs.vmr_fact[c], dry_fact = p.cs.dry_fact[c];
-          if (mi.comp) scaling = scaling * ((Float)1 - col_gas_of(p, c, ncl, mi.isc, col_dry) * vmr_fact * dry_fact);
-          else scaling = scaling * (col_gas_of(p, c, ncl, mi.isc, col_dry) * vmr_fact * dry_fact);
-        }
-      }
-      // the contributor's flavour is the band's flavour for rrtmgp-data (a contributor lives inside one band);
-      // otherwise recompute its eta weights
-      Float a0 = w.fmn[0], a1 = w.fmn[1], a2 = w.fmn[2], a3 = w.fmn[3];
-      int je0 = w.je[0], je1 = w.je[1];
-      if (mi.iflav != iflav) {
-        FlavW wm;
-        flavor_weights_g(p, c, ncl, mi.igas1, mi.igas2, tt.aux.ratio + (size_t)(itropo * t.nflav + mi.iflav) * t.ntemp, jtemp,
-                         ftemp, fpress, col_dry, wm);
-        a0 = wm.fmn[0]; a1 = wm.fmn[1]; a2 = wm.fmn[2]; a3 = wm.fmn[3];
-        je0 = wm.je[0]; je1 = wm.je[1];
-      }
-      // table column of g-point gS+i: kminor_start + (gS+i - mS) - 1
-      const int kcol0 = mi.kstart + (gS - mi.mS) - 1;
-      const size_t d_eta = (size_t)s_eta * mpitch;
-      const Float* m0 = kminor + (size_t)((jtemp - 1) + s_eta * (je0 - 1)) * mpitch + kcol0;
-      const Float* m1 = kminor + (size_t)(jtemp + s_eta * (je1 - 1)) * mpitch + kcol0;
-      const int iS = mi.mS - gS, iE = min(mi.mE - gS, n - 1);  // chunk positions covered by this contributor
-      const bool whole = FULL && iS <= 0 && iE == kGG - 1;
+      Float scaling[NC];
 #pragma unroll
-      for (int i = 0; i < kGG; i += VEC) {
+      for (int k = 0; k < NC; ++k) {
+        const size_t c = cell[k].c;
+        const Float col_dry = cell[k].col_dry;
+        Float sc = col_gas_of(p, c, ncl, mi.igas, col_dry);
+        if (mi.dens) {
+          sc = sc * p.cs.pt_scale[c];
+          if (mi.isc > 0) {
+            const Float vmr_fact = p.cs.vmr_fact[c], dry_fact = p.cs.dry_fact[c];
+            if (mi.comp) sc = sc * ((Float)1 - col_gas_of(p, c, ncl, mi.isc, col_dry) * vmr_fact * dry_fact);
+            else sc = sc * (col_gas_of(p, c, ncl, mi.isc, col_dry) * vmr_fact * dry_fact);
+          }
+        }
+        scaling[k] = sc;
+      }
+      // The contributor's flavour is the band's flavour for rrtmgp-data (a contributor lives inside one band);
+      // otherwise its eta weights are recomputed - single-cell path only, the caller does not share rows
+      // across cells for such bands (BandInfo::mdiff).
+      Float am[NC][4];
+      int jm0 = je0, jm1 = je1;
+#pragma unroll
+      for (int k = 0; k < NC; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) am[k][q] = cell[k].w.fmn[q];
+      if (NC == 1 && mi.iflav != iflav) {
+        FlavW wm;
+        const size_t c = cell[0].c;
+        flavor_weights_g(p, c, ncl, mi.igas1, mi.igas2, tt.aux.ratio + (size_t)(itropo * t.nflav + mi.iflav) * t.ntemp, jtemp,
+                         p.cs.ftemp[c], p.cs.fpress[c], cell[0].col_dry, wm);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) am[0][q] = wm.fmn[q];
+        jm0 = wm.je[0]; jm1 = wm.je[1];
+      }
+      const int kcol0 = mi.kstart + (gS - mi.mS) - 1;  // table column of g-point gS+i: kminor_start + (gS+i - mS) - 1
+      const size_t d_eta = (size_t)s_eta * mpitch;
+      const Float* m0 = kminor + (size_t)((jtemp - 1) + s_eta * (jm0 - 1)) * mpitch + kcol0;
+      const Float* m1 = kminor + (size_t)(jtemp + s_eta * (jm1 - 1)) * mpitch + kcol0;
+      const int iS = mi.mS - gS, iE = min(mi.mE - gS, n - 1);  // chunk positions covered by this contributor
+      const bool whole = FULL && iS <= 0 && iE == kTG - 1;
+#pragma unroll
+      for (int i = 0; i < kTG; i += VEC) {
         if (whole || (i >= iS && i <= iE)) {  // VEC == 2: intervals start even and have even length (TablesT::vec)
           const GLoad<VEC> x0(m0 + i), x1(m0 + d_eta + i), y0(m1 + i), y1(m1 + d_eta + i);
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) {
-            const Float kint = a0 * x0.v[v] + a1 * x1.v[v] + a2 * y0.v[v] + a3 * y1.v[v];  // :757-760
-            acc[i + v] = acc[i + v] + scaling * kint;                                      // :493
+          for (int k = 0; k < NC; ++k) {
+            const Float(&a)[4] = am[k];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              const Float kint = a[0] * x0.v[v] + a[1] * x1.v[v] + a[2] * y0.v[v] + a[3] * y1.v[v];  // :757-760
+              acc[k][i + v] = acc[k][i + v] + scaling[k] * kint;                                     // :493
+            }
           }
         }
       }
     }
-    // ---- Rayleigh (:554-559), combination, cloud increment, store ----
+    // ---- Rayleigh (:554-559), combination (:1986-1994), cloud increment, store ----
     const size_t dr_eta = (size_t)s_eta * tt.gp;
     const Float* kr = SW ? tt.krayl + (size_t)s_p * tt.gp * itropo + (gS - 1) : nullptr;
-    const Float* r0 = SW ? kr + (size_t)((jtemp - 1) + s_eta * (w.je[0] - 1)) * tt.gp : nullptr;
-    const Float* r1 = SW ? kr + (size_t)(jtemp + s_eta * (w.je[1] - 1)) * tt.gp : nullptr;
-    Float* tau_o = p.tau + c + ncl * (size_t)(gS - 1);
-    Float* ssa_o = p.op_kind == 2 ? p.ssa + c + ncl * (size_t)(gS - 1) : nullptr;
-    Float* g_o = p.op_kind == 2 ? p.g + c + ncl * (size_t)(gS - 1) : nullptr;
+    const Float* r0 = SW ? kr + (size_t)((jtemp - 1) + s_eta * (je0 - 1)) * tt.gp : nullptr;
+    const Float* r1 = SW ? kr + (size_t)(jtemp + s_eta * (je1 - 1)) * tt.gp : nullptr;
+    const size_t goff = ncl * (size_t)(gS - 1);
+    // one output value: absorption tabs, Rayleigh tray (0 without scattering) of cell k at chunk position i
+    auto finish = [&](int k, int i, Float tabs, Float tray) {
+      Float to = tabs, ss = 0, gg = 0;
+      if (SW) {
+        to = tabs + tray;
+        // rb_div: <= 1 ulp, no special-case code (the denominators below are >= 2*tiny, finite and normal); the IEEE
+        // division sequence made up half of this kernel's instructions (profiles/r1_v8_gas_tau_sw.txt)
+        ss = (to > (Float)2 * (Float)RB_TINY) ? rb_div(tray, to) : (Float)0;
+      }
+      const Float ct = cell[k].ct, cw = cell[k].cw, cg = cell[k].cg;
+      const size_t o = cell[k].c + goff + ncl * (size_t)i;
+      if (p.op_kind == 1) {
+        if (p.cld_kind == 1) to = to + ct;                         // inc_1scalar_by_1scalar_bybnd :379
+        else if (p.cld_kind == 2) to = to + ct * ((Float)1 - cw);  // inc_1scalar_by_2stream_bybnd :398
+        if (cell[k].valid) p.tau[o] = to;
+      } else {
+        if (p.cld_kind == 1) {                                     // inc_2stream_by_1scalar_bybnd :440-442
+          const Float tau12 = to + ct;
+          ss = rb_div(to * ss, fmax(eps3, tau12));
+          to = tau12;
+        } else if (p.cld_kind == 2) {                              // inc_2stream_by_2stream_bybnd :468-477
+          const Float tau12 = to + ct;
+          const Float tauscat12 = to * ss + ct * cw;
+          gg = rb_div(to * ss * gg + ct * cw * cg, fmax(eps3, tauscat12));
+          ss = rb_div(tauscat12, fmax(eps3, tau12));
+          to = tau12;
+        }
+        if (cell[k].valid) {
+          p.tau[o] = to;
+          p.ssa[o] = ss;
+          p.g[o] = gg;
+        }
+      }
+    };
 #pragma unroll
-    for (int i0 = 0; i0 < kGG; i0 += VEC) {
+    for (int i0 = 0; i0 < kTG; i0 += VEC) {
       if (!FULL && i0 >= n) continue;
-      Float ray[VEC];
       if (SW) {
         const GLoad<VEC> x0(r0 + i0), x1(r0 + dr_eta + i0), y0(r1 + i0), y1(r1 + dr_eta + i0);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v)
-          ray[v] = (w.fmn[0] * x0.v[v] + w.fmn[1] * x1.v[v] + w.fmn[2] * y0.v[v] + w.fmn[3] * y1.v[v]) * amount_rayl;
-      }
+        for (int k = 0; k < NC; ++k) {
+          const Float(&a)[4] = cell[k].w.fmn;
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const int i = i0 + v;
-        Float tt_ = acc[i], ss = 0, gg = 0;
-        if (SW) {
-          const Float tray = ray[v];
-          tt_ = acc[i] + tray;  // combine :1986-1994
-          ss = (tt_ > (Float)2 * (Float)RB_TINY) ? tray / tt_ : (Float)0;
+          for (int v = 0; v < VEC; ++v)
+            finish(k, i0 + v, acc[k][i0 + v],
+                   (a[0] * x0.v[v] + a[1] * x1.v[v] + a[2] * y0.v[v] + a[3] * y1.v[v]) * cell[k].amount_rayl);
         }
-        if (p.op_kind == 1) {
-          if (p.cld_kind == 1) tt_ = tt_ + ct;                         // inc_1scalar_by_1scalar_bybnd :379
-          else if (p.cld_kind == 2) tt_ = tt_ + ct * ((Float)1 - cw);  // inc_1scalar_by_2stream_bybnd :398
-        } else {
-          if (p.cld_kind == 1) {                                       // inc_2stream_by_1scalar_bybnd :440-442
-            const Float tau12 = tt_ + ct;
-            ss = tt_ * ss / fmax(eps3, tau12);
-            tt_ = tau12;
-          } else if (p.cld_kind == 2) {                                // inc_2stream_by_2stream_bybnd :468-477
-            const Float tau12 = tt_ + ct;
-            const Float tauscat12 = tt_ * ss + ct * cw;
-            gg = (tt_ * ss * gg + ct * cw * cg) / fmax(eps3, tauscat12);
-            ss = tauscat12 / fmax(eps3, tau12);
-            tt_ = tau12;
-          }
-        }
-        *tau_o = tt_;
-        tau_o += ncl;
-        if (p.op_kind == 2) {
-          *ssa_o = ss; *g_o = gg;
-          ssa_o += ncl; g_o += ncl;
-        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < NC; ++k)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) finish(k, i0 + v, acc[k][i0 + v], (Float)0);
       }
     }
   };
 
-  for (int gS = bi.bS; gS <= bi.bE; gS += kGG) {
-    const int n = min(kGG, bi.bE - gS + 1);
-    if (n == kGG) chunk(gS, n, std::true_type{});
+  for (int gS = bi.bS; gS <= bi.bE; gS += kTG) {
+    const int n = min(kTG, bi.bE - gS + 1);
+    if (n == kTG) chunk(gS, n, std::true_type{});
     else chunk(gS, n, std::false_type{});
+  }
+}
+
+template <bool SW, int VEC>
+__global__ void __launch_bounds__(kGThreads, 3) gas_tau_g_kernel(const FusedParams p, const TablesT tt) {
+  const rrtmgpb_gas_tables& t = p.t;
+  const size_t ncl = (size_t)p.ncol * p.nlay;
+  const int ibnd = blockIdx.x % t.nbnd;
+  const size_t cbase = (size_t)(blockIdx.x / t.nbnd) * (kTauCells * kGThreads) + threadIdx.x;
+  if (cbase >= ncl) return;
+  const BandInfo bi = tt.aux.band[ibnd];
+  const int s_eta = t.ntemp, s_p = t.ntemp * t.neta;
+  TauCell cell[kTauCells];
+  bool tropo[kTauCells];
+  int jtemp[kTauCells], row0[kTauCells], row1[kTauCells];
+#pragma unroll
+  for (int k = 0; k < kTauCells; ++k) {
+    const size_t craw = cbase + (size_t)k * kGThreads;
+    TauCell& ce = cell[k];
+    ce.valid = craw < ncl;
+    const size_t c = ce.valid ? craw : cbase;  // out-of-range slots shadow the thread's first cell, never store
+    ce.c = c;
+    ce.col_dry = p.cs.col_dry[c];
+    const Float ftemp = p.cs.ftemp[c], fpress = p.cs.fpress[c];
+    jtemp[k] = p.cs.jtemp[c];
+    tropo[k] = p.cs.tropo[c];
+    const int itropo = tropo[k] ? 0 : 1;
+    const int jpress = p.cs.jpress[c] + itropo + 1;  // :390
+    // (explicit selects: indexing the register copy of BandInfo with a run-time itropo would push it to local memory)
+    const int iflav = tropo[k] ? bi.iflav[0] : bi.iflav[1];
+    flavor_weights_g(p, c, ncl, tropo[k] ? bi.igas1[0] : bi.igas1[1], tropo[k] ? bi.igas2[0] : bi.igas2[1],
+                     tt.aux.ratio + (size_t)(itropo * t.nflav + iflav) * t.ntemp, jtemp[k], ftemp, fpress, ce.col_dry, ce.w);
+    row0[k] = (jtemp[k] - 1) + s_eta * (ce.w.je[0] - 1) + s_p * (jpress - 2);
+    row1[k] = jtemp[k] + s_eta * (ce.w.je[1] - 1) + s_p * (jpress - 2);
+    // cloud properties of this (cell, band), if the caller wants them added (mo_optical_props.F90:956-1000)
+    ce.ct = 0; ce.cw = 0; ce.cg = 0;
+    if (p.cld_kind) {
+      const size_t cb = c + ncl * (size_t)ibnd;
+      ce.ct = p.cld_tau[cb];
+      if (p.cld_kind == 2) { ce.cw = p.cld_ssa[cb]; ce.cg = p.cld_g[cb]; }
+    }
+    ce.amount_rayl = SW ? col_gas_of(p, c, ncl, t.idx_h2o, ce.col_dry) + ce.col_dry : (Float)0;  // :559
+  }
+  bool shared_rows = true;
+#pragma unroll
+  for (int k = 1; k < kTauCells; ++k)
+    shared_rows = shared_rows && tropo[k] == tropo[0] && row0[k] == row0[0] && row1[k] == row1[0];
+  if (tropo[0] ? bi.mdiff[0] : bi.mdiff[1]) shared_rows = false;
+  if (shared_rows) {
+    tau_band_cells<SW, VEC, kTauCells>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell);
+  } else {
+#pragma unroll
+    for (int k = 0; k < kTauCells; ++k) {
+      if (!cell[k].valid) continue;
+      TauCell one[1] = {cell[k]};
+      tau_band_cells<SW, VEC, 1>(p, tt, bi, tropo[k], jtemp[k], row0[k], row1[k], one);
+    }
   }
 }
 

@@ -3,7 +3,7 @@ TAG=$1; shift
 mkdir -p gpurun_out
 NCOL=${NCOL:-16384}
 for k in "$@"; do
-  timeout 600 ncu --set full --import-source on --clock-control none -k regex:$k -c 1 -f -o gpurun_out/${TAG}_ncu_$k \
+  timeout 600 ncu --set full --import-source on --clock-control none -k regex:$k -s ${SKIP:-0} -c 1 -f -o gpurun_out/${TAG}_ncu_$k \
     python bench.py --steps 1 --warmup 3 --no-cpu --ncol $NCOL > gpurun_out/${TAG}_ncu_$k.log 2>&1
   ncu -i gpurun_out/${TAG}_ncu_$k.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_${k}_raw.csv 2>/dev/null
   ncu -i gpurun_out/${TAG}_ncu_$k.ncu-rep --page source --csv > gpurun_out/${TAG}_ncu_${k}_src.csv 2>/dev/null
