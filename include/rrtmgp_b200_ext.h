@@ -60,6 +60,11 @@ void rrtmgpb_set_lw_2stream_lev_source_per_gpt(int on);
 /* Solver kernel family: 0 (default) = register-resident warp-systolic kernels when nlay <= 80 (shared-memory
  * tile kernels otherwise, and for Tang rescaling); 1 = always the shared-memory tile kernels. */
 void rrtmgpb_set_solver_variant(int variant);
+int rrtmgpb_get_solver_variant(void);
+
+/* Test hook for the lean fp64 exp / sqrt / reciprocal / division the solver kernels use (csrc/kernels/fastmath.cuh):
+ * e = exp(x), s = sqrt(|x|), r = 1/x, d = (x*x+1)/x, element-wise on n host or device doubles. */
+void rrtmgpb_fastmath_probe(int n, const double* x, double* e, double* s, double* r, double* d);
 
 /* ---------------- frontend-resident loops as kernels (SURVEY 8a') ---------------- */
 /* replaces the Fortran function get_layer_number / get_col_dry, rte/kernels/mo_gas_optics_utils.F90:127-152

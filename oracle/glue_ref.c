@@ -9,6 +9,7 @@
 #include <float.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include "oracle_ext.h"
 
 #define MAXF(a, b) (((a) > (b)) ? (a) : (b))
@@ -25,7 +26,12 @@ void rrtmgpb_set_device(int d) { (void)d; }
 void rrtmgpb_sync(void) {}
 long long rrtmgpb_launch_count(int reset) { (void)reset; return 0; }
 void rrtmgpb_set_solver_variant(int v) { (void)v; }
+int rrtmgpb_get_solver_variant(void) { return 0; }
 void rrtmgpb_set_tma_staging(int on) { (void)on; }
+/* the checker's side of the fast-math probe: plain libm / IEEE arithmetic */
+void rrtmgpb_fastmath_probe(int n, const double* x, double* e, double* s, double* r, double* d) {
+  for (int i = 0; i < n; ++i) { e[i] = exp(x[i]); s[i] = sqrt(fabs(x[i])); r[i] = 1.0 / x[i]; d[i] = (x[i] * x[i] + 1.0) / x[i]; }
+}
 void rrtmgpb_profile_enable(int on) { (void)on; }
 int rrtmgpb_profile_report(char* buf, size_t n) { if (buf && n) buf[0] = 0; return 0; }
 void rrtmgpb_set_lw_2stream_lev_source_per_gpt(int on) { oracle_set_lw_2stream_lev_source_per_gpt(on); }

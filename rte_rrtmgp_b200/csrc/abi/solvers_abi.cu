@@ -579,9 +579,27 @@ inline int reg_gpt_groups(int ncol, int ngpt) {
 
 }  // namespace
 
+// test hook for kernels/fastmath.cuh: out = (exp(x), sqrt(|x|), 1/x, 1/(x*x+1) / x) per element
+__global__ void fastmath_probe_kernel(int n, const double* x, double* e, double* s, double* r, double* d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  e[i] = rb_exp<true>(x[i]);
+  s[i] = rb_sqrt(fabs(x[i]));
+  r[i] = rb_rcp(x[i]);
+  d[i] = rb_div(x[i] * x[i] + 1.0, x[i]);
+}
+
 extern "C" {
 
+void rrtmgpb_fastmath_probe(int n, const double* x, double* e, double* s, double* r, double* d) {
+  DevArg<double> ax(x, n, Dir::In);
+  DevArg<double> ae(e, n, Dir::Out), as(s, n, Dir::Out), ar(r, n, Dir::Out), ad(d, n, Dir::Out);
+  fastmath_probe_kernel<<<ceil_div(n, 256), 256, 0, stream()>>>(n, ax, ae, as, ar, ad);
+  RB_LAUNCH_CHECK();
+}
+
 void rrtmgpb_set_solver_variant(int v) { g_solver_variant = v; }
+int rrtmgpb_get_solver_variant(void) { return g_solver_variant; }
 
 void rrtmgpb_set_lw_2stream_lev_source_per_gpt(int on) { g_lw2s_lev_per_gpt = on ? 1 : 0; }
 
@@ -734,8 +752,10 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
       KernelTimer timer("sw_2stream_reg_kernel");
 #define SWREG2(CLV, BBV)                                                                                    \
   {                                                                                                         \
-    const size_t smem = ((size_t)2 * sw_reg_slots<CLV>() + CLV) * kRegThreads * sizeof(Float);              \
-    auto kern = reg_minb() == 2 ? sw_2stream_reg_kernel<CLV, BBV, 2> : sw_2stream_reg_kernel<CLV, BBV, 3>;  \
+    const bool lean = BBV && reg_minb() == 3;                                                               \
+    const size_t smem = (size_t)(lean ? sw_reg_smem_slots<CLV, true>() : sw_reg_smem_slots<CLV, false>()) * \
+                        kRegThreads * sizeof(Float);                                                        \
+    auto kern = lean ? sw_2stream_reg_kernel<CLV, BBV, 3, BBV> : sw_2stream_reg_kernel<CLV, BBV, 2, false>; \
     RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     kern<<<grid, kRegThreads, smem, stream()>>>(q);                                                         \
   }

@@ -189,20 +189,22 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
 #pragma unroll
       for (int i = 0; i < CL; ++i) {
         const Float Bbot = *RB_SLOT(sm, NS, s, 2 * CL + i + 1);
-        if (k0 + i < nlay) {
+        {  // straight-line (see the SW kernel): padding cells become pass-through cells by selects
+          const bool live = k0 + i < nlay;
           const Float tau_loc = *RB_SLOT(sm, NS, s, i) * D;                        // :181
           const Float t = rb_exp(-tau_loc);                                           // :182
-          Float fact;                                                              // :652-656
-          if (tau_loc > tau_thresh) fact = rb_div((Float)1 - t, tau_loc) - t;
-          else fact = tau_loc * ((Float)0.5 + tau_loc * (-(Float)1 / (Float)3 + tau_loc * (Float)1 / (Float)8));
+          // :652-656, both branches evaluated (the divisor is clamped where the series is selected anyway)
+          const Float fact_big = rb_div((Float)1 - t, fmax(tau_loc, tau_thresh)) - t;
+          const Float fact_small = tau_loc * ((Float)0.5 + tau_loc * (-(Float)1 / (Float)3 + tau_loc * (Float)1 / (Float)8));
+          const Float fact = (tau_loc > tau_thresh) ? fact_big : fact_small;
           const Float lay = *RB_SLOT(sm, NS, s, CL + i);
           // :660-663; source_dn uses the Planck source at the layer's BOTTOM level, source_up at its TOP
           // level in either orientation (:638-644)
-          sd[i] = ((Float)1 - t) * Bbot + (Float)2 * fact * (lay - Bbot);
-          su[i] = ((Float)1 - t) * Btop + (Float)2 * fact * (lay - Btop);
-          tr[i] = t;
-        } else {
-          tr[i] = 1; sd[i] = 0; su[i] = 0;
+          const Float sdn = ((Float)1 - t) * Bbot + (Float)2 * fact * (lay - Bbot);
+          const Float sup = ((Float)1 - t) * Btop + (Float)2 * fact * (lay - Btop);
+          sd[i] = live ? sdn : (Float)0;
+          su[i] = live ? sup : (Float)0;
+          tr[i] = live ? t : (Float)1;
         }
         Btop = Bbot;
       }
@@ -366,12 +368,21 @@ struct SwRegParams {
 template <int CL>
 __host__ __device__ constexpr int sw_reg_slots() { return 3 * CL + 4; }  // tau, ssa, g, alb_dir, alb_dif, inc_dir, inc_dif
 
-template <int CL, bool BB, int MINB = 3>
+// LEAN (broadband only): the per-level broadband accumulators live in lane-private shared-memory slots instead
+// of registers and the input prefetch is single-stage (issued when phase A has consumed the slots), so that the
+// kernel fits 168 registers and 68 KB of shared memory: 3 resident CTAs (12 warps) per SM instead of 2.
+template <int CL, bool LEAN>
+__host__ __device__ constexpr int sw_reg_smem_slots() { return (LEAN ? 1 : 2) * sw_reg_slots<CL>() + CL + (LEAN ? 3 * CL : 0); }
+
+template <int CL, bool BB, int MINB = 3, bool LEAN = false>
 __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const SwRegParams p) {
+  static_assert(!LEAN || BB, "LEAN is a broadband-only variant");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Float* sm = reinterpret_cast<Float*>(smem_raw);
   constexpr int NS = sw_reg_slots<CL>();
-  Float* sm_mu0 = sm + (size_t)2 * NS * kRegThreads;  // [CL][thread], loaded once
+  constexpr int NSTAGE = LEAN ? 1 : 2;
+  Float* sm_mu0 = sm + (size_t)NSTAGE * NS * kRegThreads;  // [CL][thread], loaded once
+  Float* sm_acc = sm_mu0 + (size_t)CL * kRegThreads + threadIdx.x;  // LEAN: [3][CL][thread]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = lane >> 3, j = lane & 7;
   const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
@@ -406,10 +417,22 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
     if (p.has_dif_bc) cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 3), p.inc_flux_dif + gi);
   };
 
-  Float acc_up[BB ? CL : 1], acc_dn[BB ? CL : 1], acc_dir[BB ? CL : 1];
+  constexpr int NACC = (BB && !LEAN) ? CL : 1;
+  Float acc_up[NACC], acc_dn[NACC], acc_dir[NACC];
   Float acc_up_top = 0, acc_dn_top = 0, acc_dir_top = 0;
 #pragma unroll
-  for (int i = 0; i < (BB ? CL : 1); ++i) { acc_up[i] = 0; acc_dn[i] = 0; acc_dir[i] = 0; }
+  for (int i = 0; i < NACC; ++i) { acc_up[i] = 0; acc_dn[i] = 0; acc_dir[i] = 0; }
+  if (LEAN) {
+#pragma unroll
+    for (int i = 0; i < 3 * CL; ++i) sm_acc[i * kRegThreads] = 0;
+  }
+  // broadband accumulation of level slot i (compile-time constant): which = 0 up, 1 dn, 2 dir
+  auto acc_add = [&](int which, int i, Float v) {
+    if (LEAN) sm_acc[(which * CL + i) * kRegThreads] += v;
+    else if (which == 0) acc_up[NACC > 1 ? i : 0] += v;
+    else if (which == 1) acc_dn[NACC > 1 ? i : 0] += v;
+    else acc_dir[NACC > 1 ? i : 0] += v;
+  };
 
   if (gb < ge) prefetch(gb, 0);
   cp_async_commit();
@@ -420,59 +443,69 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
   const Float mu0_sfc = p.mu0[(size_t)col + ncol * o.lay(nlay - 1)];
 
   for (int g = gb; g < ge; ++g) {
-    const int s = (g - gb) & 1;
-    if (g + 1 < ge) prefetch(g + 1, s ^ 1);
-    cp_async_commit();
-    cp_async_wait<1>();
+    const int s = LEAN ? 0 : (g - gb) & 1;
+    if (!LEAN) {
+      if (g + 1 < ge) prefetch(g + 1, s ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     Float* gup = p.flux_up + nclp * g;
     Float* gdn = p.flux_dn + nclp * g;
     Float* gdir = p.flux_dir + nclp * g;
     // ---------------- phase A: two-stream layer properties (:1027-1108) ----------------
     Float R[CL], T[CL], A3[CL], A4[CL], A5[CL];  // Rdif, Tdif, Rdir->src_up, Tdir->src_dn, Tnoscat->direct flux
+    // Straight-line per cell (no branches, no calls): padding cells beyond nlay compute on the clamped inputs the
+    // prefetch gave them and are turned into pass-through cells by selects at the end, so that the compiler can
+    // interleave the CL independent cells of a lane.
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
-      if (k0 + i < nlay) {
-        const Float tau_s = *RB_SLOT(sm, NS, s, i), w0_s = *RB_SLOT(sm, NS, s, CL + i),
-                    g_s = *RB_SLOT(sm, NS, s, 2 * CL + i);
-        const Float mu0 = sm_mu0[i * kRegThreads + threadIdx.x];
-        const Float gamma1 = ((Float)8 - w0_s * ((Float)5 + (Float)3 * g_s)) * (Float).25;
-        const Float gamma2 = (Float)3 * (w0_s * ((Float)1 - g_s)) * (Float).25;
-        const Float kk = sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), min_k));
-        const Float exp_minusktau = rb_exp(-tau_s * kk);
-        const Float exp_minus2ktau = exp_minusktau * exp_minusktau;
-        Float RT_term = rb_rcp(kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau));
-        R[i] = RT_term * gamma2 * ((Float)1 - exp_minus2ktau);
-        T[i] = RT_term * (Float)2 * kk * exp_minusktau;
-        const Float mu0_s = fmax(min_mu0, mu0);
-        const Float k_mu = kk * mu0_s;
-        const Float om = (Float)1 - k_mu * k_mu;
-        RT_term = rb_div(w0_s * RT_term, fabs(om) >= eps ? om : eps);
-        const Float gamma3 = ((Float)2 - (Float)3 * mu0_s * g_s) * (Float).25;
-        const Float gamma4 = (Float)1 - gamma3;
-        const Float alpha1 = gamma1 * gamma4 + gamma2 * gamma3;
-        const Float alpha2 = gamma1 * gamma3 + gamma2 * gamma4;
-        const Float k_gamma3 = kk * gamma3;
-        const Float k_gamma4 = kk * gamma4;
-        const Float Tnoscat = rb_exp(-rb_div(tau_s, mu0_s));
-        Float Rdir = RT_term * (((Float)1 - k_mu) * (alpha2 + k_gamma3) -
-                                ((Float)1 + k_mu) * (alpha2 - k_gamma3) * exp_minus2ktau -
-                                (Float)2.0 * (k_gamma3 - alpha2 * k_mu) * exp_minusktau * Tnoscat);
-        Float Tdir = -RT_term * (((Float)1 + k_mu) * (alpha1 + k_gamma4) * Tnoscat -
-                                 ((Float)1 - k_mu) * (alpha1 - k_gamma4) * exp_minus2ktau * Tnoscat -
-                                 (Float)2.0 * (k_gamma4 + alpha1 * k_mu) * exp_minusktau);
-        Rdir = fmax((Float)0, fmin(Rdir, ((Float)1 - Tnoscat)));         // :1107
-        Tdir = fmax((Float)0, fmin(Tdir, ((Float)1 - Tnoscat - Rdir)));  // :1108
-        const bool night = !(mu0 > (Float)0);  // :1122-1125: no source for diffuse light where mu0 <= 0
-        A3[i] = night ? (Float)0 : Rdir;
-        A4[i] = night ? (Float)0 : Tdir;
-        A5[i] = Tnoscat;
-      } else {
-        R[i] = 0; T[i] = 1; A3[i] = 0; A4[i] = 0; A5[i] = 1;
-      }
+      const bool live = k0 + i < nlay;
+      const Float tau_s = *RB_SLOT(sm, NS, s, i), w0_s = *RB_SLOT(sm, NS, s, CL + i),
+                  g_s = *RB_SLOT(sm, NS, s, 2 * CL + i);
+      const Float mu0 = sm_mu0[i * kRegThreads + threadIdx.x];
+      const Float gamma1 = ((Float)8 - w0_s * ((Float)5 + (Float)3 * g_s)) * (Float).25;
+      const Float gamma2 = (Float)3 * (w0_s * ((Float)1 - g_s)) * (Float).25;
+      const Float kk = rb_sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), min_k));
+      const Float exp_minusktau = rb_exp(-tau_s * kk);
+      const Float exp_minus2ktau = exp_minusktau * exp_minusktau;
+      Float RT_term = rb_rcp(kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau));
+      const Float Rdif = RT_term * gamma2 * ((Float)1 - exp_minus2ktau);
+      const Float Tdif = RT_term * (Float)2 * kk * exp_minusktau;
+      const Float mu0_s = fmax(min_mu0, mu0);
+      const Float k_mu = kk * mu0_s;
+      const Float om = (Float)1 - k_mu * k_mu;
+      RT_term = rb_div(w0_s * RT_term, fabs(om) >= eps ? om : eps);
+      const Float gamma3 = ((Float)2 - (Float)3 * mu0_s * g_s) * (Float).25;
+      const Float gamma4 = (Float)1 - gamma3;
+      const Float alpha1 = gamma1 * gamma4 + gamma2 * gamma3;
+      const Float alpha2 = gamma1 * gamma3 + gamma2 * gamma4;
+      const Float k_gamma3 = kk * gamma3;
+      const Float k_gamma4 = kk * gamma4;
+      const Float Tnoscat = rb_exp<true>(-rb_div(tau_s, mu0_s));  // flushes to 0 (night columns, mu0_s = sqrt(eps))
+      Float Rdir = RT_term * (((Float)1 - k_mu) * (alpha2 + k_gamma3) -
+                              ((Float)1 + k_mu) * (alpha2 - k_gamma3) * exp_minus2ktau -
+                              (Float)2.0 * (k_gamma3 - alpha2 * k_mu) * exp_minusktau * Tnoscat);
+      Float Tdir = -RT_term * (((Float)1 + k_mu) * (alpha1 + k_gamma4) * Tnoscat -
+                               ((Float)1 - k_mu) * (alpha1 - k_gamma4) * exp_minus2ktau * Tnoscat -
+                               (Float)2.0 * (k_gamma4 + alpha1 * k_mu) * exp_minusktau);
+      Rdir = fmax((Float)0, fmin(Rdir, ((Float)1 - Tnoscat)));         // :1107
+      Tdir = fmax((Float)0, fmin(Tdir, ((Float)1 - Tnoscat - Rdir)));  // :1108
+      const bool lit = live && (mu0 > (Float)0);  // :1122-1125: no source for diffuse light where mu0 <= 0
+      R[i] = live ? Rdif : (Float)0;
+      T[i] = live ? Tdif : (Float)1;
+      A3[i] = lit ? Rdir : (Float)0;
+      A4[i] = lit ? Tdir : (Float)0;
+      A5[i] = live ? Tnoscat : (Float)1;
     }
     const Float alb_dir = *RB_SLOT(sm, NS, s, 3 * CL + 0), alb_dif = *RB_SLOT(sm, NS, s, 3 * CL + 1);
     const Float dir_top_g = *RB_SLOT(sm, NS, s, 3 * CL + 2) * mu0_top;                  // :575
     const Float dn_top = p.has_dif_bc ? *RB_SLOT(sm, NS, s, 3 * CL + 3) : (Float)0;     // :579-583
+    if (LEAN) {  // every slot of the (single) stage has been consumed: refill it while phase B runs
+      if (g + 1 < ge) prefetch(g + 1, 0);
+      cp_async_commit();
+    }
     // ---------------- phase B1: direct beam and its sources, :1110-1112 ----------------
     Float dir = dir_top_g;
     if (j == 0) {
@@ -492,7 +525,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
         A3[i] = s_up;
         A4[i] = s_dn;
         if (k0 + i < nlay) {
-          if (BB) { acc_dir[BB ? i : 0] += dir; acc_dn[BB ? i : 0] += dir; }  // :604, direct part of :603
+          if (BB) { acc_add(2, i, dir); acc_add(1, i, dir); }  // :604, direct part of :603
           else if (col_ok) gdir[(size_t)col + ncol * o.lev(k0 + i + 1)] = dir;
         }
         A5[i] = dir;  // direct flux below layer k0+i, for the g-point totals (:606)
@@ -510,7 +543,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
     };
     auto lev = [&](int i, Float fup, Float fdn) {
       if (k0 + i >= nlay) return;
-      if (BB) { acc_up[BB ? i : 0] += fup; acc_dn[BB ? i : 0] += fdn; }
+      if (BB) { acc_add(0, i, fup); acc_add(1, i, fdn); }
       else if (col_ok) {
         const size_t q = (size_t)col + ncol * o.lev(k0 + i + 1);
         gup[q] = fup;
@@ -525,7 +558,12 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
       const int klev = k0 + i + 1;
       if (klev <= nlay) {
         const size_t o2 = (size_t)col + ncol * o.lev(klev);
-        p.bb_up[o2] = acc_up[BB ? i : 0]; p.bb_dn[o2] = acc_dn[BB ? i : 0]; p.bb_dir[o2] = acc_dir[BB ? i : 0];
+        if (LEAN) {
+          p.bb_up[o2] = sm_acc[i * kRegThreads]; p.bb_dn[o2] = sm_acc[(CL + i) * kRegThreads];
+          p.bb_dir[o2] = sm_acc[(2 * CL + i) * kRegThreads];
+        } else {
+          p.bb_up[o2] = acc_up[NACC > 1 ? i : 0]; p.bb_dn[o2] = acc_dn[NACC > 1 ? i : 0]; p.bb_dir[o2] = acc_dir[NACC > 1 ? i : 0];
+        }
       }
     }
     if (j == 0) {
@@ -579,7 +617,7 @@ __global__ void __launch_bounds__(kRegThreads, 4) lw_2stream_reg_kernel(const Lw
         const Float tau = p.tau[i3], w0 = p.ssa[i3], gg = p.g[i3];
         const Float gamma1 = LW_diff_sec * ((Float)1 - (Float)0.5 * w0 * ((Float)1 + gg));   // :879
         const Float gamma2 = LW_diff_sec * (Float)0.5 * w0 * ((Float)1 - gg);                // :880
-        const Float kk = sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), (Float)1.e-12));   // :885
+        const Float kk = rb_sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), (Float)1.e-12));   // :885
         const Float exp_minusktau = rb_exp(-tau * kk);
         const Float exp_minus2ktau = exp_minusktau * exp_minusktau;
         const Float RT_term = rb_rcp(kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau));

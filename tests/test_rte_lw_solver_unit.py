@@ -78,7 +78,20 @@ def test_rescaling_with_zero_ssa_matches_noscat(backend):
     ref_up, ref_dn = rc.lw_noscat_broadband(lib, device, prob, SFC_EMIS_GPT)
     zeros = np.zeros_like(prob["tau"])
     up, dn, _ = rc.lw_noscat_broadband(lib, device, prob, SFC_EMIS_GPT, do_jacobians=True, rescale=(zeros, zeros))
-    assert rc.allclose(up, ref_up) and rc.allclose(dn, ref_dn)
+    if device is None:
+        assert rc.allclose(up, ref_up) and rc.allclose(dn, ref_dn)
+        return
+    # CUDA: Tang rescaling always runs in the shared-memory tile kernels.  The reference's 2-spacing tolerance holds
+    # like for like (tile kernels for both runs); against the register kernels - another exp() implementation and
+    # the chunk-level scan's reassociation - the stated tolerance is 16 spacings.
+    variant = lib.cdll.rrtmgpb_get_solver_variant()
+    lib.cdll.rrtmgpb_set_solver_variant(1)
+    try:
+        tile_up, tile_dn = rc.lw_noscat_broadband(lib, device, prob, SFC_EMIS_GPT)
+    finally:
+        lib.cdll.rrtmgpb_set_solver_variant(variant)
+    assert rc.allclose(up, tile_up) and rc.allclose(dn, tile_dn)
+    assert rc.max_spacings(up, ref_up) <= 16 and rc.max_spacings(dn, ref_dn) <= 16
 
 
 def test_specified_transport_angle(backend):
