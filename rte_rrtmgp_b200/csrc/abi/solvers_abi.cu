@@ -559,6 +559,10 @@ inline int reg_minb() {  // experiment switch: resident CTAs per SM the register
   static const int v = [] { const char* e = std::getenv("RRTMGPB_REG_MINB"); return (e && e[0] == '3') ? 3 : 2; }();
   return v;
 }
+inline bool solver_tma_enabled() {  // RRTMGPB_SOLVER_TMA=0: lane-private cp.async staging instead (A/B switch)
+  static const bool v = [] { const char* e = std::getenv("RRTMGPB_SOLVER_TMA"); return !(e && e[0] == '0'); }();
+  return v;
+}
 inline int reg_gpt_groups(int ncol, int ngpt) {
   const int ctas = ceil_div(ncol, (kRegThreads / 32) * kRegCols);
   int groups = ceil_div(148 * 8, ctas);
@@ -748,16 +752,27 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
     const int groups = bb ? 1 : reg_gpt_groups(ncol, ngpt);
     q.gpt_per_block = ceil_div(ngpt, groups);
     dim3 grid(ceil_div(ncol, (kRegThreads / 32) * kRegCols), ceil_div(ngpt, q.gpt_per_block));
+    // TMA tile staging of tau / ssa / g (kernels/tma.cuh) whenever the planes can be described
+    SwTmaMaps maps;
+    const bool use_tma = solver_tma_enabled() && make_plane_tmap(&maps.tau, q.tau, ncol, nlay, ngpt) &&
+                         make_plane_tmap(&maps.ssa, q.ssa, ncol, nlay, ngpt) && make_plane_tmap(&maps.g, q.g, ncol, nlay, ngpt);
     {
       KernelTimer timer("sw_2stream_reg_kernel");
 #define SWREG2(CLV, BBV)                                                                                    \
   {                                                                                                         \
     const bool lean = BBV && reg_minb() == 3;                                                               \
-    const size_t smem = (size_t)(lean ? sw_reg_smem_slots<CLV, true>() : sw_reg_smem_slots<CLV, false>()) * \
-                        kRegThreads * sizeof(Float);                                                        \
-    auto kern = lean ? sw_2stream_reg_kernel<CLV, BBV, 3, BBV> : sw_2stream_reg_kernel<CLV, BBV, 2, false>; \
-    RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    kern<<<grid, kRegThreads, smem, stream()>>>(q);                                                         \
+    if (use_tma && !lean) {                                                                                 \
+      const size_t smem = sw_reg_tma_smem<CLV>(nlay);                                                       \
+      auto kern = sw_2stream_reg_kernel<CLV, BBV, 2, false, true>;                                          \
+      RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+      kern<<<grid, kRegThreads, smem, stream()>>>(q, maps);                                                 \
+    } else {                                                                                                \
+      const size_t smem = (size_t)(lean ? sw_reg_smem_slots<CLV, true>() : sw_reg_smem_slots<CLV, false>()) * \
+                          kRegThreads * sizeof(Float);                                                      \
+      auto kern = lean ? sw_2stream_reg_kernel<CLV, BBV, 3, BBV, false> : sw_2stream_reg_kernel<CLV, BBV, 2, false, false>; \
+      RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+      kern<<<grid, kRegThreads, smem, stream()>>>(q, maps);                                                 \
+    }                                                                                                       \
   }
 #define SWREG(CLV) \
   if (bb) SWREG2(CLV, true) else SWREG2(CLV, false)

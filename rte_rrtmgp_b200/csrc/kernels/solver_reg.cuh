@@ -28,6 +28,7 @@
 #pragma once
 #include "../common.cuh"
 #include "fastmath.cuh"
+#include "tma.cuh"
 
 namespace rrtmgpb {
 
@@ -374,15 +375,31 @@ __host__ __device__ constexpr int sw_reg_slots() { return 3 * CL + 4; }  // tau,
 template <int CL, bool LEAN>
 __host__ __device__ constexpr int sw_reg_smem_slots() { return (LEAN ? 1 : 2) * sw_reg_slots<CL>() + CL + (LEAN ? 3 * CL : 0); }
 
-template <int CL, bool BB, int MINB = 3, bool LEAN = false>
-__global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const SwRegParams p) {
+// TMA variant: the three (16 columns x nlay) input tiles of a g-point arrive by cp.async.bulk.tensor (kernels/tma.cuh),
+// two stages; the four per-(column, g-point) boundary values keep their lane-private cp.async slots.
+struct SwTmaMaps { CUtensorMap tau, ssa, g; };
+template <int CL>
+__host__ __device__ inline size_t sw_reg_tma_smem(int nlay) {
+  return 2 * 3 * tile_bytes(nlay) + (size_t)(2 * 4 + CL) * kRegThreads * sizeof(Float) + 2 * sizeof(uint64_t);
+}
+
+template <int CL, bool BB, int MINB = 3, bool LEAN = false, bool TMA = false>
+__global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const SwRegParams p,
+                                                                            const __grid_constant__ SwTmaMaps tm) {
   static_assert(!LEAN || BB, "LEAN is a broadband-only variant");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Float* sm = reinterpret_cast<Float*>(smem_raw);
-  constexpr int NS = sw_reg_slots<CL>();
+  static_assert(!(LEAN && TMA), "LEAN and TMA are separate variants");
+  // no static shared memory in this kernel: the swizzled TMA tiles need the dynamic window to start 1024-byte aligned
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const size_t tileb = TMA ? tile_bytes(p.nlay) : 0;           // bytes of one tile
+  const int tile_elems = (int)(tileb / sizeof(Float));
+  const Float* tiles = reinterpret_cast<const Float*>(smem_raw);   // TMA: [stage][plane][row][16]
+  Float* sm = reinterpret_cast<Float*>(smem_raw + 2 * 3 * tileb);  // cp.async slots
+  constexpr int NS = TMA ? 4 : sw_reg_slots<CL>();                // slots per stage
+  constexpr int BC0 = TMA ? 0 : 3 * CL;                           // first boundary-value slot
   constexpr int NSTAGE = LEAN ? 1 : 2;
   Float* sm_mu0 = sm + (size_t)NSTAGE * NS * kRegThreads;  // [CL][thread], loaded once
   Float* sm_acc = sm_mu0 + (size_t)CL * kRegThreads + threadIdx.x;  // LEAN: [3][CL][thread]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm_mu0 + (size_t)CL * kRegThreads);  // TMA: [2] mbarriers
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = lane >> 3, j = lane & 7;
   const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
@@ -399,22 +416,34 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
   const int lay_step = p.top_at_1 ? p.ncol : -p.ncol;
   const int off_lay0 = col + p.ncol * o.lay(min(k0, nlay - 1));
 
+  const int cta_col0 = blockIdx.x * (kRegThreads / 32) * kRegCols;  // first column of this CTA (= tile origin)
+  const int cw = warp * kRegCols + c;                                // this lane's column inside the tile
   auto prefetch = [&](int g, int s) {
-    const Float* tau_g = p.tau + ncl * g;
-    const Float* ssa_g = p.ssa + ncl * g;
-    const Float* g_g = p.g + ncl * g;
+    if (TMA) {
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(&full_bar[s], (uint32_t)(3 * nlay * kTmaCols * sizeof(Float)));
+        unsigned char* dst = smem_raw + (size_t)s * 3 * tileb;
+        tma_load_tile(dst, &tm.tau, &full_bar[s], cta_col0, 0, g);
+        tma_load_tile(dst + tileb, &tm.ssa, &full_bar[s], cta_col0, 0, g);
+        tma_load_tile(dst + 2 * tileb, &tm.g, &full_bar[s], cta_col0, 0, g);
+      }
+    } else {
+      const Float* tau_g = p.tau + ncl * g;
+      const Float* ssa_g = p.ssa + ncl * g;
+      const Float* g_g = p.g + ncl * g;
 #pragma unroll
-    for (int i = 0; i < CL; ++i) {
-      const int off = (k0 + i < nlay) ? off_lay0 + lay_step * i : off_lay0;
-      cp_async_f(RB_SLOT(sm, NS, s, i), tau_g + off);
-      cp_async_f(RB_SLOT(sm, NS, s, CL + i), ssa_g + off);
-      cp_async_f(RB_SLOT(sm, NS, s, 2 * CL + i), g_g + off);
+      for (int i = 0; i < CL; ++i) {
+        const int off = (k0 + i < nlay) ? off_lay0 + lay_step * i : off_lay0;
+        cp_async_f(RB_SLOT(sm, NS, s, i), tau_g + off);
+        cp_async_f(RB_SLOT(sm, NS, s, CL + i), ssa_g + off);
+        cp_async_f(RB_SLOT(sm, NS, s, 2 * CL + i), g_g + off);
+      }
     }
     const size_t gi = (size_t)col + ncol * g;
-    cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 0), p.sfc_alb_dir + gi);
-    cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 1), p.sfc_alb_dif + gi);
-    cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 2), p.inc_flux_dir + gi);
-    if (p.has_dif_bc) cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 3), p.inc_flux_dif + gi);
+    cp_async_f(RB_SLOT(sm, NS, s, BC0 + 0), p.sfc_alb_dir + gi);
+    cp_async_f(RB_SLOT(sm, NS, s, BC0 + 1), p.sfc_alb_dif + gi);
+    cp_async_f(RB_SLOT(sm, NS, s, BC0 + 2), p.inc_flux_dir + gi);
+    if (p.has_dif_bc) cp_async_f(RB_SLOT(sm, NS, s, BC0 + 3), p.inc_flux_dif + gi);
   };
 
   constexpr int NACC = (BB && !LEAN) ? CL : 1;
@@ -434,8 +463,20 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
     else acc_dir[NACC > 1 ? i : 0] += v;
   };
 
+  if (TMA) {
+    if (threadIdx.x == 0) {
+      mbar_init(&full_bar[0], 1);
+      mbar_init(&full_bar[1], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
   if (gb < ge) prefetch(gb, 0);
   cp_async_commit();
+  if (TMA) {  // TMA keeps two g-points in flight: the stage of g is refilled for g+2 once every warp has read it
+    if (gb + 1 < ge) prefetch(gb + 1, 1);
+    cp_async_commit();
+  }
 #pragma unroll
   for (int i = 0; i < CL; ++i)
     sm_mu0[i * kRegThreads + threadIdx.x] = p.mu0[(k0 + i < nlay) ? off_lay0 + lay_step * i : off_lay0];
@@ -444,13 +485,17 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
 
   for (int g = gb; g < ge; ++g) {
     const int s = LEAN ? 0 : (g - gb) & 1;
-    if (!LEAN) {
+    if (TMA) {
+      cp_async_wait<1>();                                         // boundary values of g (groups g, g+1 outstanding)
+      mbar_wait(&full_bar[s], (uint32_t)(((g - gb) >> 1) & 1));   // tiles of g
+    } else if (!LEAN) {
       if (g + 1 < ge) prefetch(g + 1, s ^ 1);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
+    const Float* tile_s = tiles + (size_t)s * 3 * tile_elems;
     Float* gup = p.flux_up + nclp * g;
     Float* gdn = p.flux_dn + nclp * g;
     Float* gdir = p.flux_dir + nclp * g;
@@ -462,8 +507,13 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
       const bool live = k0 + i < nlay;
-      const Float tau_s = *RB_SLOT(sm, NS, s, i), w0_s = *RB_SLOT(sm, NS, s, CL + i),
-                  g_s = *RB_SLOT(sm, NS, s, 2 * CL + i);
+      Float tau_s, w0_s, g_s;
+      if (TMA) {
+        const Float* e = tile_at(tile_s, o.lay(min(k0 + i, nlay - 1)), cw);
+        tau_s = e[0]; w0_s = e[tile_elems]; g_s = e[2 * tile_elems];
+      } else {
+        tau_s = *RB_SLOT(sm, NS, s, i); w0_s = *RB_SLOT(sm, NS, s, CL + i); g_s = *RB_SLOT(sm, NS, s, 2 * CL + i);
+      }
       const Float mu0 = sm_mu0[i * kRegThreads + threadIdx.x];
       const Float gamma1 = ((Float)8 - w0_s * ((Float)5 + (Float)3 * g_s)) * (Float).25;
       const Float gamma2 = (Float)3 * (w0_s * ((Float)1 - g_s)) * (Float).25;
@@ -499,11 +549,16 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
       A4[i] = lit ? Tdir : (Float)0;
       A5[i] = live ? Tnoscat : (Float)1;
     }
-    const Float alb_dir = *RB_SLOT(sm, NS, s, 3 * CL + 0), alb_dif = *RB_SLOT(sm, NS, s, 3 * CL + 1);
-    const Float dir_top_g = *RB_SLOT(sm, NS, s, 3 * CL + 2) * mu0_top;                  // :575
-    const Float dn_top = p.has_dif_bc ? *RB_SLOT(sm, NS, s, 3 * CL + 3) : (Float)0;     // :579-583
+    const Float alb_dir = *RB_SLOT(sm, NS, s, BC0 + 0), alb_dif = *RB_SLOT(sm, NS, s, BC0 + 1);
+    const Float dir_top_g = *RB_SLOT(sm, NS, s, BC0 + 2) * mu0_top;                  // :575
+    const Float dn_top = p.has_dif_bc ? *RB_SLOT(sm, NS, s, BC0 + 3) : (Float)0;     // :579-583
     if (LEAN) {  // every slot of the (single) stage has been consumed: refill it while phase B runs
       if (g + 1 < ge) prefetch(g + 1, 0);
+      cp_async_commit();
+    }
+    if (TMA) {  // every warp of the CTA has read stage s into registers: hand it back to the TMA for g+2
+      __syncthreads();
+      if (g + 2 < ge) prefetch(g + 2, s);
       cp_async_commit();
     }
     // ---------------- phase B1: direct beam and its sources, :1110-1112 ----------------
