@@ -640,14 +640,26 @@ void rte_lw_solver_noscat(const int* ncol_, const int* nlay_, const int* ngpt_, 
     const int groups = (bb || jac) ? 1 : reg_gpt_groups(ncol, ngpt);
     q.gpt_per_block = ceil_div(ngpt, groups);
     dim3 grid(ceil_div(ncol, (kRegThreads / 32) * kRegCols), ceil_div(ngpt, q.gpt_per_block));
+    // TMA tile staging of tau / lay_source / lev_source (kernels/tma.cuh) whenever the planes can be described
+    LwTmaMaps maps;
+    const bool use_tma = solver_tma_enabled() && make_plane_tmap(&maps.tau, q.tau, ncol, nlay, ngpt) &&
+                         make_plane_tmap(&maps.lay, q.lay_source, ncol, nlay, ngpt) &&
+                         make_plane_tmap(&maps.lev, q.lev_source, ncol, nlay + 1, ngpt);
     {
       KernelTimer timer("lw_noscat_reg_kernel");
 #define LWREG2(CLV, BBV, JACV)                                                                              \
   {                                                                                                         \
-    const size_t smem = (size_t)2 * lw_noscat_reg_slots<CLV>() * kRegThreads * sizeof(Float);               \
-    auto kern = reg_minb() == 2 ? lw_noscat_reg_kernel<CLV, BBV, JACV, 2> : lw_noscat_reg_kernel<CLV, BBV, JACV, 3>; \
-    RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    kern<<<grid, kRegThreads, smem, stream()>>>(q);                                                         \
+    if (use_tma && reg_minb() == 2) {                                                                       \
+      const size_t smem = lw_noscat_reg_tma_smem(nlay);                                                     \
+      auto kern = lw_noscat_reg_kernel<CLV, BBV, JACV, 2, true>;                                            \
+      RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+      kern<<<grid, kRegThreads, smem, stream()>>>(q, maps);                                                 \
+    } else {                                                                                                \
+      const size_t smem = (size_t)2 * lw_noscat_reg_slots<CLV>() * kRegThreads * sizeof(Float);             \
+      auto kern = reg_minb() == 2 ? lw_noscat_reg_kernel<CLV, BBV, JACV, 2, false> : lw_noscat_reg_kernel<CLV, BBV, JACV, 3, false>; \
+      RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+      kern<<<grid, kRegThreads, smem, stream()>>>(q, maps);                                                 \
+    }                                                                                                       \
   }
 #define LWREG(CLV)                                    \
   if (bb && jac) LWREG2(CLV, true, true)              \

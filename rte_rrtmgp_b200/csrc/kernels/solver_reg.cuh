@@ -113,11 +113,25 @@ struct LwNoscatRegParams {
 template <int CL>
 __host__ __device__ constexpr int lw_noscat_reg_slots() { return 3 * CL + 1 + 5; }  // tau, lay, lev(+1), emis, sfc_src, inc_flux, jac, D(angle 1)
 
-template <int CL, bool BB, bool JAC, int MINB = 3>
-__global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const LwNoscatRegParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Float* sm = reinterpret_cast<Float*>(smem_raw);
-  constexpr int NS = lw_noscat_reg_slots<CL>();
+// TMA variant (see the SW kernel and kernels/tma.cuh): tau, lay_source (nlay rows) and lev_source (nlay+1 rows) tiles
+// by cp.async.bulk.tensor, two stages; the five per-(column, g-point) values keep their lane-private cp.async slots.
+struct LwTmaMaps { CUtensorMap tau, lay, lev; };
+__host__ __device__ inline size_t lw_noscat_reg_tma_smem(int nlay) {
+  return 2 * (2 * tile_bytes(nlay) + tile_bytes(nlay + 1)) + (size_t)(2 * 5) * kRegThreads * sizeof(Float) + 2 * sizeof(uint64_t);
+}
+
+template <int CL, bool BB, bool JAC, int MINB = 3, bool TMA = false>
+__global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const LwNoscatRegParams p,
+                                                                           const __grid_constant__ LwTmaMaps tm) {
+  // no static shared memory: the swizzled TMA tiles need the dynamic window to start 1024-byte aligned
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const size_t tb_lay = TMA ? tile_bytes(p.nlay) : 0, tb_lev = TMA ? tile_bytes(p.nlay + 1) : 0;
+  const size_t stageb = 2 * tb_lay + tb_lev;
+  const int te_lay = (int)(tb_lay / sizeof(Float));
+  Float* sm = reinterpret_cast<Float*>(smem_raw + 2 * stageb);  // cp.async slots
+  constexpr int NS = TMA ? 5 : lw_noscat_reg_slots<CL>();
+  constexpr int BC0 = TMA ? -1 : 3 * CL;                          // boundary-value slots are BC0+1 .. BC0+5
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm + (size_t)2 * NS * kRegThreads);  // TMA: [2] mbarriers
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = lane >> 3, j = lane & 7;
   const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
@@ -135,27 +149,39 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
   const int off_lay0 = col + p.ncol * o.lay(min(k0, nlay - 1));  // layer k0
   const int off_lev0 = col + p.ncol * o.lev(min(k0, nlay));      // level k0
 
+  const int cta_col0 = blockIdx.x * (kRegThreads / 32) * kRegCols;  // first column of this CTA (= tile origin)
+  const int cw = warp * kRegCols + c;                                // this lane's column inside the tile
   auto prefetch = [&](int g, int s) {
-    const Float* tau_g = p.tau + ncl * g;
-    const Float* lay_g = p.lay_source + ncl * g;
-    const Float* lev_g = p.lev_source + nclp * g;
+    if (TMA) {
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(&full_bar[s], (uint32_t)((2 * nlay + nlev) * kTmaCols * sizeof(Float)));
+        unsigned char* dst = smem_raw + (size_t)s * stageb;
+        tma_load_tile(dst, &tm.tau, &full_bar[s], cta_col0, 0, g);
+        tma_load_tile(dst + tb_lay, &tm.lay, &full_bar[s], cta_col0, 0, g);
+        tma_load_tile(dst + 2 * tb_lay, &tm.lev, &full_bar[s], cta_col0, 0, g);
+      }
+    } else {
+      const Float* tau_g = p.tau + ncl * g;
+      const Float* lay_g = p.lay_source + ncl * g;
+      const Float* lev_g = p.lev_source + nclp * g;
 #pragma unroll
-    for (int i = 0; i < CL; ++i) {
-      const int off = (k0 + i < nlay) ? off_lay0 + lay_step * i : off_lay0;
-      cp_async_f(RB_SLOT(sm, NS, s, i), tau_g + off);
-      cp_async_f(RB_SLOT(sm, NS, s, CL + i), lay_g + off);
-    }
+      for (int i = 0; i < CL; ++i) {
+        const int off = (k0 + i < nlay) ? off_lay0 + lay_step * i : off_lay0;
+        cp_async_f(RB_SLOT(sm, NS, s, i), tau_g + off);
+        cp_async_f(RB_SLOT(sm, NS, s, CL + i), lay_g + off);
+      }
 #pragma unroll
-    for (int i = 0; i <= CL; ++i) {
-      const int off = (k0 + i <= nlay) ? off_lev0 + lay_step * i : off_lev0;
-      cp_async_f(RB_SLOT(sm, NS, s, 2 * CL + i), lev_g + off);
+      for (int i = 0; i <= CL; ++i) {
+        const int off = (k0 + i <= nlay) ? off_lev0 + lay_step * i : off_lev0;
+        cp_async_f(RB_SLOT(sm, NS, s, 2 * CL + i), lev_g + off);
+      }
     }
     const size_t gi = (size_t)col + ncol * g;
-    cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 1), p.sfc_emis + gi);
-    cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 2), p.sfc_src + gi);
-    cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 3), p.inc_flux + gi);
-    if (JAC) cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 4), p.sfc_srcJac + gi);
-    cp_async_f(RB_SLOT(sm, NS, s, 3 * CL + 5), p.Ds + gi);
+    cp_async_f(RB_SLOT(sm, NS, s, BC0 + 1), p.sfc_emis + gi);
+    cp_async_f(RB_SLOT(sm, NS, s, BC0 + 2), p.sfc_src + gi);
+    cp_async_f(RB_SLOT(sm, NS, s, BC0 + 3), p.inc_flux + gi);
+    if (JAC) cp_async_f(RB_SLOT(sm, NS, s, BC0 + 4), p.sfc_srcJac + gi);
+    cp_async_f(RB_SLOT(sm, NS, s, BC0 + 5), p.Ds + gi);
   };
 
   // broadband accumulators: slot i <-> level k0+i+1 (below layer k0+i); *_top <-> level 0 (lane j == 0)
@@ -167,38 +193,58 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
     if (JAC) acc_jac[JAC ? i : 0] = 0;
   }
 
+  if (TMA) {
+    if (threadIdx.x == 0) {
+      mbar_init(&full_bar[0], 1);
+      mbar_init(&full_bar[1], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
   if (gb < ge) prefetch(gb, 0);
   cp_async_commit();
+  if (TMA) {  // two g-points in flight; the stage of g is refilled for g+2 at the end of iteration g
+    if (gb + 1 < ge) prefetch(gb + 1, 1);
+    cp_async_commit();
+  }
   for (int g = gb; g < ge; ++g) {
     const int s = (g - gb) & 1;
-    if (g + 1 < ge) prefetch(g + 1, s ^ 1);
-    cp_async_commit();
-    cp_async_wait<1>();  // everything but the newest group (stage s^1) has landed; slots are lane-private
-    const Float emis = *RB_SLOT(sm, NS, s, 3 * CL + 1), ssrc = *RB_SLOT(sm, NS, s, 3 * CL + 2),
-                inc = *RB_SLOT(sm, NS, s, 3 * CL + 3);
-    const Float sjac = JAC ? *RB_SLOT(sm, NS, s, 3 * CL + 4) : (Float)0;
+    if (TMA) {
+      cp_async_wait<1>();                                         // boundary values of g (groups g, g+1 outstanding)
+      mbar_wait(&full_bar[s], (uint32_t)(((g - gb) >> 1) & 1));   // tiles of g
+    } else {
+      if (g + 1 < ge) prefetch(g + 1, s ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();  // everything but the newest group (stage s^1) has landed; slots are lane-private
+    }
+    const Float* tile_tau = reinterpret_cast<const Float*>(smem_raw + (size_t)s * stageb);
+    const Float* tile_lev = tile_tau + 2 * te_lay;
+    const Float emis = *RB_SLOT(sm, NS, s, BC0 + 1), ssrc = *RB_SLOT(sm, NS, s, BC0 + 2),
+                inc = *RB_SLOT(sm, NS, s, BC0 + 3);
+    const Float sjac = JAC ? *RB_SLOT(sm, NS, s, BC0 + 4) : (Float)0;
     Float* fup = p.flux_up + nclp * g;
     Float* fdn = p.flux_dn + nclp * g;
     for (int imu = 0; imu < p.nmus; ++imu) {
       const Float w = p.weights[imu];
       const Float piw = pi * w;
-      const Float D = (imu == 0) ? *RB_SLOT(sm, NS, s, 3 * CL + 5)
+      const Float D = (imu == 0) ? *RB_SLOT(sm, NS, s, BC0 + 5)
                                : p.Ds[(size_t)col + ncol * ((size_t)g + (size_t)p.ngpt * imu)];
       // ---------------- phase A: CL cells per lane, in registers ----------------
       Float tr[CL], sd[CL], su[CL];
-      Float Btop = *RB_SLOT(sm, NS, s, 2 * CL);
+      Float Btop = TMA ? *tile_at(tile_lev, o.lev(min(k0, nlay)), cw) : *RB_SLOT(sm, NS, s, 2 * CL);
 #pragma unroll
       for (int i = 0; i < CL; ++i) {
-        const Float Bbot = *RB_SLOT(sm, NS, s, 2 * CL + i + 1);
+        const Float Bbot = TMA ? *tile_at(tile_lev, o.lev(min(k0 + i + 1, nlay)), cw) : *RB_SLOT(sm, NS, s, 2 * CL + i + 1);
         {  // straight-line (see the SW kernel): padding cells become pass-through cells by selects
           const bool live = k0 + i < nlay;
-          const Float tau_loc = *RB_SLOT(sm, NS, s, i) * D;                        // :181
+          const Float* e_lay = TMA ? tile_at(tile_tau, o.lay(min(k0 + i, nlay - 1)), cw) : nullptr;
+          const Float tau_loc = (TMA ? e_lay[0] : *RB_SLOT(sm, NS, s, i)) * D;     // :181
           const Float t = rb_exp(-tau_loc);                                           // :182
           // :652-656, both branches evaluated (the divisor is clamped where the series is selected anyway)
           const Float fact_big = rb_div((Float)1 - t, fmax(tau_loc, tau_thresh)) - t;
           const Float fact_small = tau_loc * ((Float)0.5 + tau_loc * (-(Float)1 / (Float)3 + tau_loc * (Float)1 / (Float)8));
           const Float fact = (tau_loc > tau_thresh) ? fact_big : fact_small;
-          const Float lay = *RB_SLOT(sm, NS, s, CL + i);
+          const Float lay = TMA ? e_lay[te_lay] : *RB_SLOT(sm, NS, s, CL + i);
           // :660-663; source_dn uses the Planck source at the layer's BOTTOM level, source_up at its TOP
           // level in either orientation (:638-644)
           const Float sdn = ((Float)1 - t) * Bbot + (Float)2 * fact * (lay - Bbot);
@@ -260,6 +306,11 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
         if (BB) acc_up_top += w * Iu; else store(fup, 0, Iu);
         if (JAC) acc_jac_top += w * Ij;
       }
+    }
+    if (TMA) {  // every warp of the CTA is done with stage s (all angles): hand it back to the TMA for g+2
+      __syncthreads();
+      if (g + 2 < ge) prefetch(g + 2, s);
+      cp_async_commit();
     }
   }
   // ---------------- epilogue: spectrally integrated outputs (:233-238) ----------------
