@@ -559,6 +559,10 @@ inline int reg_minb() {  // experiment switch: resident CTAs per SM the register
   static const int v = [] { const char* e = std::getenv("RRTMGPB_REG_MINB"); return (e && e[0] == '3') ? 3 : 2; }();
   return v;
 }
+inline bool reg_sacc() {  // experiment switch: SW broadband accumulators in shared memory (frees 54 registers)
+  static const bool v = [] { const char* e = std::getenv("RRTMGPB_REG_SACC"); return e && e[0] == '1'; }();
+  return v;
+}
 inline bool solver_tma_enabled() {  // RRTMGPB_SOLVER_TMA=0: lane-private cp.async staging instead (A/B switch)
   static const bool v = [] { const char* e = std::getenv("RRTMGPB_SOLVER_TMA"); return !(e && e[0] == '0'); }();
   return v;
@@ -773,9 +777,10 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
 #define SWREG2(CLV, BBV)                                                                                    \
   {                                                                                                         \
     const bool lean = BBV && reg_minb() == 3;                                                               \
+    const bool sacc = BBV && reg_sacc();                                                                    \
     if (use_tma && !lean) {                                                                                 \
-      const size_t smem = sw_reg_tma_smem<CLV>(nlay);                                                       \
-      auto kern = sw_2stream_reg_kernel<CLV, BBV, 2, false, true>;                                          \
+      const size_t smem = sacc ? sw_reg_tma_smem<CLV, true>(nlay) : sw_reg_tma_smem<CLV, false>(nlay);      \
+      auto kern = sacc ? sw_2stream_reg_kernel<CLV, BBV, 2, BBV, true> : sw_2stream_reg_kernel<CLV, BBV, 2, false, true>; \
       RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
       kern<<<grid, kRegThreads, smem, stream()>>>(q, maps);                                                 \
     } else {                                                                                                \

@@ -429,16 +429,15 @@ __host__ __device__ constexpr int sw_reg_smem_slots() { return (LEAN ? 1 : 2) * 
 // TMA variant: the three (16 columns x nlay) input tiles of a g-point arrive by cp.async.bulk.tensor (kernels/tma.cuh),
 // two stages; the four per-(column, g-point) boundary values keep their lane-private cp.async slots.
 struct SwTmaMaps { CUtensorMap tau, ssa, g; };
-template <int CL>
+template <int CL, bool LEAN>
 __host__ __device__ inline size_t sw_reg_tma_smem(int nlay) {
-  return 2 * 3 * tile_bytes(nlay) + (size_t)(2 * 4 + CL) * kRegThreads * sizeof(Float) + 2 * sizeof(uint64_t);
+  return 2 * 3 * tile_bytes(nlay) + (size_t)(2 * 4 + CL + (LEAN ? 3 * CL : 0)) * kRegThreads * sizeof(Float) + 2 * sizeof(uint64_t);
 }
 
 template <int CL, bool BB, int MINB = 3, bool LEAN = false, bool TMA = false>
 __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const SwRegParams p,
                                                                             const __grid_constant__ SwTmaMaps tm) {
   static_assert(!LEAN || BB, "LEAN is a broadband-only variant");
-  static_assert(!(LEAN && TMA), "LEAN and TMA are separate variants");
   // no static shared memory in this kernel: the swizzled TMA tiles need the dynamic window to start 1024-byte aligned
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const size_t tileb = TMA ? tile_bytes(p.nlay) : 0;           // bytes of one tile
@@ -447,10 +446,10 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
   Float* sm = reinterpret_cast<Float*>(smem_raw + 2 * 3 * tileb);  // cp.async slots
   constexpr int NS = TMA ? 4 : sw_reg_slots<CL>();                // slots per stage
   constexpr int BC0 = TMA ? 0 : 3 * CL;                           // first boundary-value slot
-  constexpr int NSTAGE = LEAN ? 1 : 2;
+  constexpr int NSTAGE = (LEAN && !TMA) ? 1 : 2;
   Float* sm_mu0 = sm + (size_t)NSTAGE * NS * kRegThreads;  // [CL][thread], loaded once
   Float* sm_acc = sm_mu0 + (size_t)CL * kRegThreads + threadIdx.x;  // LEAN: [3][CL][thread]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm_mu0 + (size_t)CL * kRegThreads);  // TMA: [2] mbarriers
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm_mu0 + (size_t)(CL + (LEAN ? 3 * CL : 0)) * kRegThreads);  // TMA: [2] mbarriers
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = lane >> 3, j = lane & 7;
   const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
@@ -535,7 +534,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
   const Float mu0_sfc = p.mu0[(size_t)col + ncol * o.lay(nlay - 1)];
 
   for (int g = gb; g < ge; ++g) {
-    const int s = LEAN ? 0 : (g - gb) & 1;
+    const int s = (LEAN && !TMA) ? 0 : (g - gb) & 1;
     if (TMA) {
       cp_async_wait<1>();                                         // boundary values of g (groups g, g+1 outstanding)
       mbar_wait(&full_bar[s], (uint32_t)(((g - gb) >> 1) & 1));   // tiles of g
@@ -603,7 +602,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
     const Float alb_dir = *RB_SLOT(sm, NS, s, BC0 + 0), alb_dif = *RB_SLOT(sm, NS, s, BC0 + 1);
     const Float dir_top_g = *RB_SLOT(sm, NS, s, BC0 + 2) * mu0_top;                  // :575
     const Float dn_top = p.has_dif_bc ? *RB_SLOT(sm, NS, s, BC0 + 3) : (Float)0;     // :579-583
-    if (LEAN) {  // every slot of the (single) stage has been consumed: refill it while phase B runs
+    if (LEAN && !TMA) {  // every slot of the (single) stage has been consumed: refill it while phase B runs
       if (g + 1 < ge) prefetch(g + 1, 0);
       cp_async_commit();
     }
