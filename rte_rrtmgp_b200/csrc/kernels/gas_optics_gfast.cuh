@@ -512,8 +512,9 @@ __global__ void __launch_bounds__(kGThreads, 4) planck_g_kernel(const PlanckFuse
 #pragma unroll
           for (int i = 0; i < kGG; ++i) {
             if (i < ns) {
-              *lay_c = pf[i] * B_lay;                                                          // :640
-              *lev_c = (ilay == 0) ? pf[i] * B_lev : sqrt(pf_prev[sub + i] * pf[i]) * B_lev;   // :695-701
+              // streaming stores: the source planes are next read by the solver, long after they left the caches
+              __stcs(lay_c, pf[i] * B_lay);                                                    // :640
+              __stcs(lev_c, (ilay == 0) ? pf[i] * B_lev : sqrt(pf_prev[sub + i] * pf[i]) * B_lev);   // :695-701
               lay_c += ncl; lev_c += nclp;
               if (is_sfc) {
                 q.sfc_src[icol + ncol * (size_t)(gS + sub + i - 1)] = pf[i] * B_sfc;            // :650-653
