@@ -7,5 +7,6 @@ for k in "$@"; do
     python bench.py --steps 1 --warmup 3 --no-cpu --ncol $NCOL > gpurun_out/${TAG}_ncu_$k.log 2>&1
   ncu -i gpurun_out/${TAG}_ncu_$k.ncu-rep --page raw --csv > gpurun_out/${TAG}_ncu_${k}_raw.csv 2>/dev/null
   ncu -i gpurun_out/${TAG}_ncu_$k.ncu-rep --page source --csv > gpurun_out/${TAG}_ncu_${k}_src.csv 2>/dev/null
+  [ -n "$KEEP_REP" ] || rm -f gpurun_out/${TAG}_ncu_$k.ncu-rep   # gpurun copies back at most 64 MiB
 done
 ls -la gpurun_out | grep ${TAG}_ncu
