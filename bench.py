@@ -360,6 +360,26 @@ def run_product(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * ncol / (float(t.item()) / args.steps * 1e-3)
 
+    # ---- the same step driven as the reference's call sequence, kernel by kernel through the 45 extern-ABI symbols
+    # (what a stock Fortran frontend linked against this library executes); reported beside the headline
+    seq_value = None
+    if not args.no_seq:
+        sky.fused = False
+        sky.step()
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(max(args.steps // 2, 1)):
+            sky.step()
+        q1.record()
+        barrier()
+        sky.fused = True
+        sky.step()  # leave the headline path's results in the flux arrays for the parity spot check below
+        t = torch.tensor([q0.elapsed_time(q1) / max(args.steps // 2, 1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        seq_value = world * ncol / (float(t.item()) * 1e-3)
+
     # ---- parity spot check inside the bench: first 32 columns vs the CPU oracle (checker only)
     cpu_base, parity = None, None
     if rank == 0:
@@ -384,6 +404,7 @@ def run_product(args):
                        "l2_policy": "inputs larger than L2 (each (col,lay,gpt) plane is 9.7 GB)"},
             "e2e": {"value": e2e_value, "unit": "columns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
+            "value_reference_call_sequence": seq_value,
             "roofline": roofline,
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "frac_of_hbm_peak": step_frac,
                               "bytes_per_column": step_bytes / ncol},
@@ -406,6 +427,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ncol", type=int, default=NCOL_PER_GPU, help="columns per GPU (default: the BASELINE config)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-seq", action="store_true", help="skip the kernel-by-kernel (reference call sequence) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     if args.impl == "reference":

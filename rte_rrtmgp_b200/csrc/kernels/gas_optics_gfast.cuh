@@ -178,7 +178,13 @@ __device__ __forceinline__ void interp3d_g(const Float* __restrict__ tab, int gp
 // loads divides that traffic, and the latency waited for per output, by kTauCells.  Otherwise each cell is processed
 // on its own.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kTauCells = 2;
+#ifndef RB_TAU_CELLS
+#define RB_TAU_CELLS 2
+#endif
+#ifndef RB_TAU_MINB
+#define RB_TAU_MINB 3
+#endif
+constexpr int kTauCells = RB_TAU_CELLS;
 constexpr int kTG = 4;  // g-points per register chunk of the tau kernel
 
 struct TauCell {
@@ -358,7 +364,7 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
 }
 
 template <bool SW, int VEC>
-__global__ void __launch_bounds__(kGThreads, 3) gas_tau_g_kernel(const FusedParams p, const TablesT tt) {
+__global__ void __launch_bounds__(kGThreads, RB_TAU_MINB) gas_tau_g_kernel(const FusedParams p, const TablesT tt) {
   const rrtmgpb_gas_tables& t = p.t;
   const size_t ncl = (size_t)p.ncol * p.nlay;
   const int ibnd = blockIdx.x % t.nbnd;

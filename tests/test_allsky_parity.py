@@ -111,3 +111,31 @@ def test_smoke_entry():
     from rte_rrtmgp_b200 import smoke_check
 
     assert smoke_check.run(ncol=24, nlay=72) <= FLUX_ATOL
+
+
+@pytest.mark.gpu
+def test_full_size_replicated_profile_properties(oracle_lib, cuda_lib, kdists):
+    """BASELINE config 2 at its full size (65,536 columns x 72 layers, 256 + 224 g-points), checked through properties
+    that do not need a CPU run of that size: (1) the profile is replicated and clouds repeat with period 3 in the
+    column index (rrtmgp_allsky.F90:636-656), so every column must equal - bit for bit - the column of its class
+    among the first three; (2) the first 48 columns match the oracle run on 48 columns within the flux tolerance."""
+    import torch
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100 * 2**30:
+        pytest.skip("needs ~80 GB of device memory")
+    kd_lw, kd_sw = kdists
+    ncol, nlay = 65536, 72
+    g = _run(cuda_lib, "cuda:0", ncol, nlay, kd_lw, kd_sw, fused=True)
+    fg = g.fluxes_host()
+    for k, v in fg.items():
+        assert np.all(np.isfinite(v)), k
+        for cls in range(3):
+            same = v[cls::3]
+            assert np.array_equal(same, np.broadcast_to(same[0], same.shape)), (k, cls)
+    c = _run(oracle_lib, None, 48, nlay, kd_lw, kd_sw)
+    fc = c.fluxes_host()
+    for k in fc:
+        assert np.max(np.abs(fg[k][:48] - fc[k])) <= FLUX_ATOL, k
+    del g
+    torch.cuda.empty_cache()

@@ -1,7 +1,7 @@
 # usage: ab_env.sh VAR val1 val2 ... : quick A/B of the all-sky step under an environment switch
 VAR=$1; shift
 for v in "$@"; do
-env $VAR=$v timeout 280 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ab_$v.json 2>gpurun_out/ab.err; tail -2 gpurun_out/ab.err
+env $VAR=$v timeout 280 python bench.py --steps 3 --warmup 3 --no-cpu --no-seq > gpurun_out/ab_$v.json 2>gpurun_out/ab.err; tail -2 gpurun_out/ab.err
 python -c "
 import json
 d=json.loads(open('gpurun_out/ab_$v.json').read().strip().splitlines()[-1])

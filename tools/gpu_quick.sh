@@ -1,7 +1,7 @@
 # quick GPU check: parity tests touching the changed path + a 3-step bench; usage: gpu_quick.sh [pytest -k expr]
 mkdir -p gpurun_out
 python -m pytest tests -x -q -m gpu ${1:+-k "$1"} 2>&1 | tail -8
-python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/quick_bench.json 2>gpurun_out/quick_bench.err; tail -3 gpurun_out/quick_bench.err
+python bench.py --steps 3 --warmup 3 --no-cpu --no-seq > gpurun_out/quick_bench.json 2>gpurun_out/quick_bench.err; tail -3 gpurun_out/quick_bench.err
 python - <<PY
 import json
 d=json.loads(open('gpurun_out/quick_bench.json').read().strip().splitlines()[-1])

@@ -15,6 +15,6 @@ PY
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>>gpurun_out/${TAG}_bench.err; cut -c1-300 gpurun_out/${TAG}_bench_reference.json
 # launch list (same command as the bench; times under ncu are cold-cache and serialised: shares only)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
-  python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${TAG}_launches.log 2>&1
+  python bench.py --steps 2 --warmup 3 --no-cpu --no-seq > gpurun_out/${TAG}_launches.log 2>&1
 bash tools/gpu_ncu.sh ${TAG} sw_2stream_reg_kernel lw_noscat_reg_kernel gas_tau_g_kernel planck_g_kernel
 SKIP=1 bash tools/gpu_ncu.sh ${TAG}sw gas_tau_g_kernel
