@@ -101,6 +101,14 @@ void rrtmgpb_cloud_masks(int ncol, int nlay, const Float* clwp, const Float* ciw
 void rrtmgpb_cloud_combine(int ncol, int nlay, int ngpt, int kind, const Float* ltau, const Float* ltaussa,
                            const Float* ltaussag, const Float* itau, const Float* itaussa,
                            const Float* itaussag, Float* tau, Float* ssa, Float* g);
+/* The compute part of ty_cloud_optics_rrtmgp%cloud_optics in one pass: the masks (mo_cloud_optics_rrtmgp.F90:334-341),
+ * both compute_cld_from_table calls (:373, :380; ice tables = the icergh slice) and the liquid+ice combination
+ * (:399-424), without materialising the six (ncol,nlay,nbnd) intermediates.  kind 1: tau ; kind 2: tau, ssa, g. */
+void rrtmgpb_cloud_optics_from_tables(int ncol, int nlay, int nbnd, int kind, const Float* clwp, const Float* ciwp,
+                                      const Float* reliq, const Float* dgice, int liq_nsteps, Float liq_step_size,
+                                      Float liq_offset, const Float* extliq, const Float* ssaliq, const Float* asyliq,
+                                      int ice_nsteps, Float ice_step_size, Float ice_offset, const Float* extice,
+                                      const Float* ssaice, const Float* asyice, Float* tau, Float* ssa, Float* g);
 /* replaces compute_all_from_table + the optical-property combination of ty_aerosol_optics_rrtmgp_merra%aerosol_optics,
  * rrtmgp/frontend/mo_aerosol_optics_rrtmgp_merra.F90:436-559 and :385-418 (size-bin search, relative-humidity
  * bracket + linear interpolation, per-type table lookup; kind 1: tau = atau - ataussa; kind 2: tau, ssa, g with

@@ -159,6 +159,9 @@ void rrtmgpb_cloud_optics_free(rrtmgpb_cloud_optics_t* co);
 int rrtmgpb_cloud_optics(const rrtmgpb_cloud_optics_t* co, int ncol, int nlay, const Float* clwp, const Float* ciwp,
                          const Float* reliq, const Float* dgice, rrtmgpb_optical_props* optical_props,
                          char* errmsg);
+/* 1 (default): cloud_optics() computes masks, table lookups and the liquid+ice combination in one kernel
+ * (rrtmgpb_cloud_optics_from_tables); 0: the reference's kernel-by-kernel sequence with its six intermediates. */
+void rrtmgpb_cloud_optics_one_pass(int on);
 
 /* ---------------- ty_aerosol_optics_rrtmgp_merra ---------------- */
 /* Tables as load_lut() receives them (mo_aerosol_optics_rrtmgp_merra.F90:99-123): the rh-dependent ones arrive

@@ -317,3 +317,22 @@ void rrtmgpb_aerosol_optics_from_table(int ncol, int nlay, int nval, int nrh, in
   }
   free(atau);
 }
+
+/* The checker's side of the one-pass cloud optics: literally the reference sequence (mo_cloud_optics_rrtmgp.F90:334-424). */
+void rrtmgpb_cloud_optics_from_tables(int ncol, int nlay, int nbnd, int kind, const Float* clwp, const Float* ciwp,
+                                      const Float* reliq, const Float* dgice, int liq_nsteps, Float liq_step_size,
+                                      Float liq_offset, const Float* extliq, const Float* ssaliq, const Float* asyliq,
+                                      int ice_nsteps, Float ice_step_size, Float ice_offset, const Float* extice,
+                                      const Float* ssaice, const Float* asyice, Float* tau, Float* ssa, Float* g) {
+  const size_t ncl = (size_t)ncol * nlay, n = ncl * nbnd;
+  Bool* liqmsk = (Bool*)malloc(ncl ? ncl : 1);
+  Bool* icemsk = (Bool*)malloc(ncl ? ncl : 1);
+  Float* w = (Float*)malloc((n ? n : 1) * 6 * sizeof(Float));
+  rrtmgpb_cloud_masks(ncol, nlay, clwp, ciwp, liqmsk, icemsk);
+  rrtmgp_compute_cld_from_table(&ncol, &nlay, &nbnd, liqmsk, clwp, reliq, &liq_nsteps, &liq_step_size, &liq_offset, extliq,
+                                ssaliq, asyliq, w, w + n, w + 2 * n);
+  rrtmgp_compute_cld_from_table(&ncol, &nlay, &nbnd, icemsk, ciwp, dgice, &ice_nsteps, &ice_step_size, &ice_offset, extice,
+                                ssaice, asyice, w + 3 * n, w + 4 * n, w + 5 * n);
+  rrtmgpb_cloud_combine(ncol, nlay, nbnd, kind, w, w + n, w + 2 * n, w + 3 * n, w + 4 * n, w + 5 * n, tau, ssa, g);
+  free(w); free(icemsk); free(liqmsk);
+}

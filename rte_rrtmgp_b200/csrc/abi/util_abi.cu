@@ -297,6 +297,89 @@ void rrtmgpb_cloud_combine(int ncol, int nlay, int ngpt, int kind, const Float* 
   }
 }
 
+// Whole cloud_optics() body in one pass (mo_cloud_optics_rrtmgp.F90:334-341 masks, :373/:380 table lookups through
+// mo_cloud_optics_rrtmgp_kernels.F90:24-65, :399-424 combination): thread = cell looping over bands; the six
+// (ncol,nlay,nbnd) intermediates ltau..itaussag are never materialised.
+struct CloudFusedParams {
+  int ncol, nlay, nbnd, kind;
+  const Float *clwp, *ciwp, *reliq, *dgice;
+  int liq_nsteps, ice_nsteps;
+  Float liq_step, liq_offset, ice_step, ice_offset;
+  const Float *extliq, *ssaliq, *asyliq, *extice, *ssaice, *asyice;
+  Float *tau, *ssa, *g;
+};
+__global__ void __launch_bounds__(256) cloud_optics_fused_kernel(const CloudFusedParams p) {
+  const size_t ncl = (size_t)p.ncol * p.nlay;
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncl) return;
+  const Float lwp = p.clwp[c], iwp = p.ciwp[c];
+  const bool lm = lwp > (Float)0, im = iwp > (Float)0;  // :334-341
+  int li = 1, ii = 1;
+  Float lf = 0, fi = 0;
+  if (lm) {
+    const Float re = p.reliq[c];
+    li = min((int)floor((re - p.liq_offset) / p.liq_step) + 1, p.liq_nsteps - 1);  // kernels :46
+    lf = (re - p.liq_offset) / p.liq_step - (Float)(li - 1);                        // kernels :47
+  }
+  if (im) {
+    const Float de = p.dgice[c];
+    ii = min((int)floor((de - p.ice_offset) / p.ice_step) + 1, p.ice_nsteps - 1);
+    fi = (de - p.ice_offset) / p.ice_step - (Float)(ii - 1);
+  }
+  for (int b = 0; b < p.nbnd; ++b) {
+    Float lt = 0, lts = 0, ltg = 0, it = 0, its = 0, itg = 0;
+    if (lm) {  // kernels :52-60
+      const Float* tt = p.extliq + (size_t)p.liq_nsteps * b + (li - 1);
+      const Float* st = p.ssaliq + (size_t)p.liq_nsteps * b + (li - 1);
+      const Float* at = p.asyliq + (size_t)p.liq_nsteps * b + (li - 1);
+      lt = lwp * (__ldg(tt) + lf * (__ldg(tt + 1) - __ldg(tt)));
+      lts = lt * (__ldg(st) + lf * (__ldg(st + 1) - __ldg(st)));
+      ltg = lts * (__ldg(at) + lf * (__ldg(at + 1) - __ldg(at)));
+    }
+    if (im) {
+      const Float* tt = p.extice + (size_t)p.ice_nsteps * b + (ii - 1);
+      const Float* st = p.ssaice + (size_t)p.ice_nsteps * b + (ii - 1);
+      const Float* at = p.asyice + (size_t)p.ice_nsteps * b + (ii - 1);
+      it = iwp * (__ldg(tt) + fi * (__ldg(tt + 1) - __ldg(tt)));
+      its = it * (__ldg(st) + fi * (__ldg(st + 1) - __ldg(st)));
+      itg = its * (__ldg(at) + fi * (__ldg(at + 1) - __ldg(at)));
+    }
+    const size_t o = c + ncl * b;
+    if (p.kind == 1) {
+      p.tau[o] = (lt - lts) + (it - its);  // :402-405
+    } else {                               // :412-422
+      const Float tt_ = lt + it;
+      const Float ts = lts + its;
+      p.g[o] = (ltg + itg) / fmax((Float)RB_EPS, ts);
+      p.ssa[o] = ts / fmax((Float)RB_EPS, tt_);
+      p.tau[o] = tt_;
+    }
+  }
+}
+
+void rrtmgpb_cloud_optics_from_tables(int ncol, int nlay, int nbnd, int kind, const Float* clwp, const Float* ciwp,
+                                      const Float* reliq, const Float* dgice, int liq_nsteps, Float liq_step_size,
+                                      Float liq_offset, const Float* extliq, const Float* ssaliq, const Float* asyliq,
+                                      int ice_nsteps, Float ice_step_size, Float ice_offset, const Float* extice,
+                                      const Float* ssaice, const Float* asyice, Float* tau, Float* ssa, Float* g) {
+  const size_t ncl = (size_t)ncol * nlay, n = ncl * nbnd;
+  const size_t nl = (size_t)liq_nsteps * nbnd, ni = (size_t)ice_nsteps * nbnd;
+  DevArg<Float> a_lwp(clwp, ncl, Dir::In), a_iwp(ciwp, ncl, Dir::In), a_re(reliq, ncl, Dir::In), a_de(dgice, ncl, Dir::In);
+  DevArg<Float> a_el(extliq, nl, Dir::In), a_sl(ssaliq, nl, Dir::In), a_al(asyliq, nl, Dir::In);
+  DevArg<Float> a_ei(extice, ni, Dir::In), a_si(ssaice, ni, Dir::In), a_ai(asyice, ni, Dir::In);
+  DevArg<Float> o_t(tau, n, Dir::Out), o_s(ssa, n, Dir::Out, kind == 2), o_g(g, n, Dir::Out, kind == 2);
+  CloudFusedParams p;
+  p.ncol = ncol; p.nlay = nlay; p.nbnd = nbnd; p.kind = kind;
+  p.clwp = a_lwp; p.ciwp = a_iwp; p.reliq = a_re; p.dgice = a_de;
+  p.liq_nsteps = liq_nsteps; p.ice_nsteps = ice_nsteps; p.liq_step = liq_step_size; p.liq_offset = liq_offset;
+  p.ice_step = ice_step_size; p.ice_offset = ice_offset;
+  p.extliq = a_el; p.ssaliq = a_sl; p.asyliq = a_al; p.extice = a_ei; p.ssaice = a_si; p.asyice = a_ai;
+  p.tau = o_t; p.ssa = o_s; p.g = o_g;
+  KernelTimer timer("cloud_optics_fused");
+  cloud_optics_fused_kernel<<<ceil_div((long long)ncl, 256), 256, 0, stream()>>>(p);
+  RB_LAUNCH_CHECK();
+}
+
 static int any_flag(size_t n, const Float* array, const Bool* mask, Float lo, Float hi, bool use_hi) {
   DevArg<Float> a(array, n, Dir::In);
   DevArg<Bool> m(mask, n, Dir::In, mask != nullptr);

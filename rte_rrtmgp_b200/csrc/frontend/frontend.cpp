@@ -789,6 +789,8 @@ void rrtmgpb_cloud_optics_free(rrtmgpb_cloud_optics_t* co) {
   delete co;
 }
 
+static int g_cloud_optics_one_pass = 1;  // 0: the reference's kernel-by-kernel sequence (rrtmgpb_cloud_optics_one_pass)
+
 int rrtmgpb_cloud_optics(const rrtmgpb_cloud_optics_t* co, int ncol, int nlay, const Float* clwp, const Float* ciwp,
                          const Float* reliq, const Float* dgice, rrtmgpb_optical_props* op, char* errmsg) {
   const rrtmgpb_cloud_lut& h = co->h;
@@ -803,9 +805,9 @@ int rrtmgpb_cloud_optics(const rrtmgpb_cloud_optics_t* co, int ncol, int nlay, c
       msg = "cloud optics: optical properties don't have the same band structure";
   }
   if (!msg.empty()) return fail(errmsg, msg);
-  Scratch<Bool> liqmsk(ncl), icemsk(ncl);
-  rrtmgpb_cloud_masks(ncol, nlay, clwp, ciwp, liqmsk, icemsk);  // :334-341
-  if (g_check_values) {  // :346-353
+  if (g_check_values) {  // :334-353: the masks are only needed here when the value checks are on
+    Scratch<Bool> liqmsk(ncl), icemsk(ncl);
+    rrtmgpb_cloud_masks(ncol, nlay, clwp, ciwp, liqmsk, icemsk);
     if (rrtmgpb_any_vals_outside(ncl, reliq, liqmsk, h.radliq_lwr, h.radliq_upr))
       msg = "cloud optics: liquid effective radius is out of bounds";
     if (rrtmgpb_any_vals_outside(ncl, dgice, icemsk, h.diamice_lwr, h.diamice_upr))
@@ -815,6 +817,14 @@ int rrtmgpb_cloud_optics(const rrtmgpb_cloud_optics_t* co, int ncol, int nlay, c
   }
   if (!msg.empty()) return fail(errmsg, msg);
   if (op->kind == RRTMGPB_NSTR) return fail(errmsg, "cloud optics: n-stream calculations not yet supported");
+  if (g_cloud_optics_one_pass) {  // masks + both table lookups (:373, :380) + combination (:399-424) in one kernel
+    rrtmgpb_cloud_optics_from_tables(ncol, nlay, ngpt, op->kind, clwp, ciwp, reliq, dgice, co->liq_nsteps, co->liq_step_size,
+                                     h.radliq_lwr, co->extliq, co->ssaliq, co->asyliq, co->ice_nsteps, co->ice_step_size,
+                                     h.diamice_lwr, co->extice, co->ssaice, co->asyice, op->tau, op->ssa, op->g);
+    return ok(errmsg);
+  }
+  Scratch<Bool> liqmsk(ncl), icemsk(ncl);
+  rrtmgpb_cloud_masks(ncol, nlay, clwp, ciwp, liqmsk, icemsk);  // :334-341
   Scratch<Float> ltau(n), ltaussa(n), ltaussag(n), itau(n), itaussa(n), itaussag(n);
   rrtmgp_compute_cld_from_table(&ncol, &nlay, &ngpt, liqmsk, clwp, reliq, &co->liq_nsteps, &co->liq_step_size,
                                 &h.radliq_lwr, co->extliq, co->ssaliq, co->asyliq, ltau, ltaussa, ltaussag);  // :373
@@ -824,6 +834,8 @@ int rrtmgpb_cloud_optics(const rrtmgpb_cloud_optics_t* co, int ncol, int nlay, c
                         op->g);  // :399-424
   return ok(errmsg);
 }
+
+void rrtmgpb_cloud_optics_one_pass(int on) { g_cloud_optics_one_pass = on ? 1 : 0; }
 
 // ------------------------------------------------------------------------------------------------
 // ty_aerosol_optics_rrtmgp_merra (LUT): rrtmgp/frontend/mo_aerosol_optics_rrtmgp_merra.F90
