@@ -130,6 +130,25 @@ int rrtmgpb_any_int_vals_outside(size_t n, const int* array, int checkMin, int c
 int rrtmgpb_any_vals_less_than(size_t n, const Float* array, const Bool* mask, Float check_value);
 int rrtmgpb_any_vals_outside(size_t n, const Float* array, const Bool* mask, Float checkMin, Float checkMax);
 
+/* ---------------- flux diagnostics beside the broadband reductions ---------------- */
+/* The reference compiles these in place (rte/extensions/mo_fluxes_byband.F90:159,184,210: bind(C) names rte_sum_byband,
+ * rte_net_byband_full, net_byband_precalc); same by-reference convention as the 45 extern-mode symbols.
+ * band_lims(2,nbnd): 1-based g-point limits; spectral_flux(ncol,nlev,ngpt) -> byband_flux(ncol,nlev,nbnd). */
+void rte_sum_byband(const int* ncol, const int* nlev, const int* ngpt, const int* nbnd, const int* band_lims,
+                    const Float* spectral_flux, Float* byband_flux);
+void rte_net_byband_full(const int* ncol, const int* nlev, const int* ngpt, const int* nbnd, const int* band_lims,
+                         const Float* spectral_flux_dn, const Float* spectral_flux_up, Float* byband_flux_net);
+void net_byband_precalc(const int* ncol, const int* nlev, const int* nbnd, const Float* byband_flux_dn,
+                        const Float* byband_flux_up, Float* byband_flux_net);
+/* replaces compute_heating_rate_general, rte/extensions/mo_heating_rates.F90:34-64: heating rate [K/s] of every layer
+ * from the flux divergence, H = (dF_up - dF_dn) * grav / (cp_dry * dp); fluxes, p_lev (ncol,nlay+1) -> (ncol,nlay) */
+void rrtmgpb_heating_rate(int ncol, int nlay, const Float* flux_up, const Float* flux_dn, const Float* p_lev,
+                          Float* heating_rate);
+/* replaces compute_heating_rate_solar_varmu0 (:66-117): as above, then the layer in which mu0(ncol,nlay) goes from
+ * positive to zero is recomputed from the diffuse (total minus direct) net flux */
+void rrtmgpb_heating_rate_solar_varmu0(int ncol, int nlay, const Float* flux_up, const Float* flux_dn,
+                                       const Float* flux_dir, const Float* p_lev, const Float* mu0, Float* heating_rate);
+
 /* ---------------- fused variants used by the device-resident frontend ---------------- */
 /* As rrtmgp_compute_tau_absorption but ASSIGNS tau instead of accumulating into a pre-zeroed array:
  * saves the zero_array_3D plane write and the plane read (mo_gas_optics_rrtmgp.F90:637-665,679-706). */

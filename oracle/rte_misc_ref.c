@@ -9,6 +9,7 @@
  * Pinned by the flux-reduction checks in the restated solver unit tests (net = dn - up).
  */
 #include <math.h>
+#include <float.h>
 #include <stddef.h>
 #include "rte_kernels.h"
 #include "oracle_ext.h"
@@ -130,4 +131,81 @@ void rrtmgpb_get_col_dry(int ncol, int nlay, const Float* vmr_h2o, const Float* 
       col_dry[k] = (Float)10 * delta_plev * (Float)avogad * fact /
                    ((Float)1000 * m_air * (Float)100 * (Float)g_grav);
     }
+}
+
+/* ---- rte/extensions/mo_fluxes_byband.F90:159-218 ---- */
+/* sum_byband :159-178 */
+void rte_sum_byband(const int* ncol, const int* nlev, const int* ngpt, const int* nbnd, const int* band_lims,
+                    const Float* spectral_flux, Float* byband_flux) {
+  const size_t n2 = (size_t)*ncol * *nlev;
+  (void)ngpt;
+  for (int ib = 0; ib < *nbnd; ++ib)
+    for (size_t c = 0; c < n2; ++c) {
+      Float s = spectral_flux[c + n2 * (size_t)(band_lims[2 * ib] - 1)];
+      for (int ig = band_lims[2 * ib] + 1; ig <= band_lims[2 * ib + 1]; ++ig) s = s + spectral_flux[c + n2 * (size_t)(ig - 1)];
+      byband_flux[c + n2 * ib] = s;
+    }
+}
+/* net_byband_full :184-208: net = net + dn - up, evaluated left to right */
+void rte_net_byband_full(const int* ncol, const int* nlev, const int* ngpt, const int* nbnd, const int* band_lims,
+                         const Float* spectral_flux_dn, const Float* spectral_flux_up, Float* byband_flux_net) {
+  const size_t n2 = (size_t)*ncol * *nlev;
+  (void)ngpt;
+  for (int ib = 0; ib < *nbnd; ++ib)
+    for (size_t c = 0; c < n2; ++c) {
+      size_t o = c + n2 * (size_t)(band_lims[2 * ib] - 1);
+      Float s = spectral_flux_dn[o] - spectral_flux_up[o];
+      for (int ig = band_lims[2 * ib] + 1; ig <= band_lims[2 * ib + 1]; ++ig) {
+        o = c + n2 * (size_t)(ig - 1);
+        s = s + spectral_flux_dn[o] - spectral_flux_up[o];
+      }
+      byband_flux_net[c + n2 * ib] = s;
+    }
+}
+/* net_byband_precalc :210-217 */
+void net_byband_precalc(const int* ncol, const int* nlev, const int* nbnd, const Float* byband_flux_dn,
+                        const Float* byband_flux_up, Float* byband_flux_net) {
+  const size_t n = (size_t)*ncol * *nlev * *nbnd;
+  for (size_t i = 0; i < n; ++i) byband_flux_net[i] = byband_flux_dn[i] - byband_flux_up[i];
+}
+
+/* ---- rte/extensions/mo_heating_rates.F90 ---- */
+/* compute_heating_rate_general :34-64 */
+void rrtmgpb_heating_rate(int ncol, int nlay, const Float* flux_up, const Float* flux_dn, const Float* p_lev,
+                          Float* heating_rate) {
+  const size_t nc = (size_t)ncol;
+  const Float grav = (Float)g_grav, cp_dry = (Float)g_cp_dry;
+  for (int l = 0; l < nlay; ++l)
+    for (size_t c = 0; c < nc; ++c) {
+      const size_t i = c + nc * l;
+      heating_rate[i] = (flux_up[i + nc] - flux_up[i] - flux_dn[i + nc] + flux_dn[i]) * grav /
+                        (cp_dry * (p_lev[i + nc] - p_lev[i]));
+    }
+}
+/* compute_heating_rate_solar_varmu0 :66-117 */
+void rrtmgpb_heating_rate_solar_varmu0(int ncol, int nlay, const Float* flux_up, const Float* flux_dn,
+                                       const Float* flux_dir, const Float* p_lev, const Float* mu0, Float* heating_rate) {
+  const size_t nc = (size_t)ncol, ncl = nc * nlay;
+  const Float grav = (Float)g_grav, cp_dry = (Float)g_cp_dry;
+  const Float eps = sizeof(Float) == 8 ? (Float)DBL_EPSILON : (Float)FLT_EPSILON;
+  int any = 0, any_last = 0;
+  rrtmgpb_heating_rate(ncol, nlay, flux_up, flux_dn, p_lev, heating_rate);
+  for (size_t i = 0; i < ncl; ++i)
+    if (mu0[i] < eps) { any = 1; if (i >= ncl - nc) any_last = 1; }
+  if (!any) return; /* :85-86 */
+  for (size_t c = 0; c < nc; ++c) {
+    int loc = 0, ilay;
+    Float best = 0;
+    for (int l = 0; l < nlay; ++l) { /* minloc / maxloc over mu0 > 0, first occurrence, 1-based, 0 if none */
+      const Float v = mu0[c + nc * l];
+      if (!(v > (Float)0)) continue;
+      if (loc == 0 || (any_last ? v < best : v > best)) { loc = l + 1; best = v; }
+    }
+    ilay = any_last ? loc + 1 : loc - 1; /* :102, :104 */
+    if (ilay > 1 && ilay < nlay) {       /* :108 */
+      const size_t i = c + nc * (size_t)(ilay - 1);
+      heating_rate[i] = (flux_up[i + nc] - flux_up[i] - flux_dn[i + nc] + flux_dn[i] + flux_dir[i + nc] - flux_dir[i]) *
+                        grav / (cp_dry * (p_lev[i + nc] - p_lev[i]));
+    }
+  }
 }

@@ -87,6 +87,106 @@ void rte_sum_broadband(const int* ncol, const int* nlev, const int* ngpt, const 
   });
 }
 
+// ---------------- by-band reductions (rte/extensions/mo_fluxes_byband.F90:159-218) ----------------
+// One thread per (col,lev,band); sequential sum over the band's g-points in the reference's order.
+void rte_sum_byband(const int* ncol, const int* nlev, const int* ngpt, const int* nbnd, const int* band_lims,
+                    const Float* spectral_flux, Float* byband_flux) {
+  OpName op_name__(__func__);
+  const size_t n2 = (size_t)*ncol * *nlev;
+  const int nb = *nbnd;
+  DevArg<int> lims(band_lims, 2 * (size_t)nb, Dir::In);
+  DevArg<Float> in(spectral_flux, n2 * *ngpt, Dir::In), out(byband_flux, n2 * nb, Dir::Out);
+  const int* bl = lims; const Float* s = in; Float* b = out;
+  launch_elementwise(n2 * nb, [=] __device__(size_t i) {
+    const size_t c = i % n2;
+    const int ib = (int)(i / n2);
+    const int g0 = bl[2 * ib] - 1, g1 = bl[2 * ib + 1] - 1;
+    Float acc = s[c + n2 * g0];                                   // :170
+    for (int ig = g0 + 1; ig <= g1; ++ig) acc = acc + s[c + n2 * ig];  // :171-174
+    b[i] = acc;
+  });
+}
+
+void rte_net_byband_full(const int* ncol, const int* nlev, const int* ngpt, const int* nbnd, const int* band_lims,
+                         const Float* spectral_flux_dn, const Float* spectral_flux_up, Float* byband_flux_net) {
+  OpName op_name__(__func__);
+  const size_t n2 = (size_t)*ncol * *nlev;
+  const int nb = *nbnd;
+  DevArg<int> lims(band_lims, 2 * (size_t)nb, Dir::In);
+  DevArg<Float> dn(spectral_flux_dn, n2 * *ngpt, Dir::In), up(spectral_flux_up, n2 * *ngpt, Dir::In),
+      out(byband_flux_net, n2 * nb, Dir::Out);
+  const int* bl = lims; const Float *d = dn, *u = up; Float* b = out;
+  launch_elementwise(n2 * nb, [=] __device__(size_t i) {
+    const size_t c = i % n2;
+    const int ib = (int)(i / n2);
+    const int g0 = bl[2 * ib] - 1, g1 = bl[2 * ib + 1] - 1;
+    Float acc = d[c + n2 * g0] - u[c + n2 * g0];                  // :196-198
+    for (int ig = g0 + 1; ig <= g1; ++ig) acc = acc + d[c + n2 * ig] - u[c + n2 * ig];  // :199-203, left to right
+    b[i] = acc;
+  });
+}
+
+void net_byband_precalc(const int* ncol, const int* nlev, const int* nbnd, const Float* byband_flux_dn,
+                        const Float* byband_flux_up, Float* byband_flux_net) {
+  OpName op_name__(__func__);
+  const size_t n = (size_t)*ncol * *nlev * *nbnd;
+  DevArg<Float> dn(byband_flux_dn, n, Dir::In), up(byband_flux_up, n, Dir::In), out(byband_flux_net, n, Dir::Out);
+  const Float *d = dn, *u = up; Float* b = out;
+  launch_elementwise(n, [=] __device__(size_t i) { b[i] = d[i] - u[i]; });  // :216
+}
+
+// ---------------- heating rates (rte/extensions/mo_heating_rates.F90:34-117) ----------------
+void rrtmgpb_heating_rate(int ncol, int nlay, const Float* flux_up, const Float* flux_dn, const Float* p_lev,
+                          Float* heating_rate) {
+  OpName op_name__(__func__);
+  const size_t nc = ncol, ncl = nc * nlay, nclp = nc * (nlay + 1);
+  DevArg<Float> fu(flux_up, nclp, Dir::In), fd(flux_dn, nclp, Dir::In), pl(p_lev, nclp, Dir::In), hr(heating_rate, ncl, Dir::Out);
+  const Float *u = fu, *d = fd, *pp = pl; Float* h = hr;
+  const Float grav = (Float)g_const.grav, cp_dry = (Float)g_const.cp_dry;
+  launch_elementwise(ncl, [=] __device__(size_t i) {  // :56-62; level below layer i is i + ncol
+    h[i] = (u[i + nc] - u[i] - d[i + nc] + d[i]) * grav / (cp_dry * (pp[i + nc] - pp[i]));
+  });
+}
+
+void rrtmgpb_heating_rate_solar_varmu0(int ncol, int nlay, const Float* flux_up, const Float* flux_dn,
+                                       const Float* flux_dir, const Float* p_lev, const Float* mu0, Float* heating_rate) {
+  rrtmgpb_heating_rate(ncol, nlay, flux_up, flux_dn, p_lev, heating_rate);  // :81
+  OpName op_name__(__func__);
+  const size_t nc = ncol, ncl = nc * nlay, nclp = nc * (nlay + 1);
+  DevArg<Float> fu(flux_up, nclp, Dir::In), fd(flux_dn, nclp, Dir::In), fr(flux_dir, nclp, Dir::In), pl(p_lev, nclp, Dir::In),
+      m0(mu0, ncl, Dir::In), hr(heating_rate, ncl, Dir::InOut);
+  const Float *u = fu, *d = fd, *r = fr, *pp = pl, *mu = m0; Float* h = hr;
+  const Float grav = (Float)g_const.grav, cp_dry = (Float)g_const.cp_dry;
+  const Float eps = (Float)RB_EPS;
+  // one thread per column: the serial searches of :85-104 (any sun below the horizon?  orientation from the last
+  // layer of column 1..ncol is a global property in the reference: any(mu0(:,nlay) < eps))
+  int* flags = static_cast<int*>(dev_alloc(2 * sizeof(int)));
+  RB_CUDA_CHECK(cudaMemsetAsync(flags, 0, 2 * sizeof(int), stream()));
+  launch_elementwise(ncl, [=] __device__(size_t i) {
+    if (mu[i] < eps) {
+      flags[0] = 1;                                   // any_vals_less_than(mu0, epsilon(mu0)), :85-86
+      if (i >= ncl - nc) flags[1] = 1;                // any_vals_less_than(mu0(:,nlay), epsilon(mu0)), :100
+    }
+  });
+  launch_elementwise(nc, [=] __device__(size_t icol) {
+    if (!flags[0]) return;
+    // minloc / maxloc of mu0 over the layers where mu0 > 0 (first occurrence), 1-based; 0 if the mask is empty
+    int loc = 0;
+    Float best = 0;
+    for (int l = 0; l < nlay; ++l) {
+      const Float v = mu[icol + nc * l];
+      if (!(v > (Float)0)) continue;
+      if (loc == 0 || (flags[1] ? v < best : v > best)) { loc = l + 1; best = v; }
+    }
+    const int ilay = flags[1] ? loc + 1 : loc - 1;      // :102, :104
+    if (ilay > 1 && ilay < nlay) {                      // :108
+      const size_t i = icol + nc * (size_t)(ilay - 1);
+      h[i] = (u[i + nc] - u[i] - d[i + nc] + d[i] + r[i + nc] - r[i]) * grav / (cp_dry * (pp[i + nc] - pp[i]));  // :112-115
+    }
+  });
+  dev_free(flags);
+}
+
 void rte_net_broadband_full(const int* ncol, const int* nlev, const int* ngpt, const Float* spectral_flux_dn,
                             const Float* spectral_flux_up, Float* broadband_flux_net) {
   OpName op_name__(__func__);
