@@ -670,8 +670,13 @@ void rte_lw_solver_noscat(const int* ncol_, const int* nlay_, const int* ngpt_, 
   else if (bb) LWREG2(CLV, true, false)               \
   else if (jac) LWREG2(CLV, false, true)              \
   else LWREG2(CLV, false, false)
+      // TMA tiles have 128-byte rows: with CL = 8 the eight chunk lanes of a column read rows 8 apart - the same
+      // swizzle phase, an 8-way bank conflict (measured: LW 1.6x slower at 60 layers) - so nlay <= 64 runs CL = 9
+      // too (rows 9 apart: conflict free; the extra cells are pass-through padding).  The chunk length fixes the
+      // association of the chunk-level scan, so it must not depend on whether TMA is usable (odd ncol):
+      // results are bit-identical under column subsetting (tests/test_rte_lw_solver_unit.py).
       switch (cl) {
-        case 8: LWREG(8); break;
+        case 8:
         case 9: LWREG(9); break;
         default: LWREG(10); break;
       }
@@ -793,6 +798,8 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
   }
 #define SWREG(CLV) \
   if (bb) SWREG2(CLV, true) else SWREG2(CLV, false)
+      // (CL = 8 conflicts on the TMA tiles as in rte_lw_solver_noscat, but this kernel is fp64-bound: the padding of
+      // CL = 9 costs more than the conflicts - measured 39.2 vs 37.7 ms at 131,072 x 60)
       switch (cl) {
         case 8: SWREG(8); break;
         case 9: SWREG(9); break;
