@@ -719,7 +719,32 @@ void rte_lw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
     q.flux_dn = p.flux_dn;
     q.gpt_per_block = ceil_div(ngpt, reg_gpt_groups(ncol, ngpt));
     dim3 grid(ceil_div(ncol, (kRegThreads / 32) * kRegCols), ceil_div(ngpt, q.gpt_per_block));
-    DISPATCH_CL(cl, lw_2stream_reg_kernel, q, grid);
+    Lw2sTmaMaps maps;
+    const bool use_tma = solver_tma_enabled() && make_plane_tmap(&maps.tau, q.tau, ncol, nlay, ngpt) &&
+                         make_plane_tmap(&maps.ssa, q.ssa, ncol, nlay, ngpt) && make_plane_tmap(&maps.g, q.g, ncol, nlay, ngpt) &&
+                         make_plane_tmap(&maps.lay, q.lay_source, ncol, nlay, ngpt) &&
+                         make_plane_tmap(&maps.lev, q.lev_source, ncol, nlay + 1, ngpt);
+    {
+      KernelTimer timer("lw_2stream_reg_kernel");
+#define LW2S(CLV)                                                                                          \
+  if (use_tma) {                                                                                           \
+    const size_t smem = lw_2stream_reg_tma_smem(nlay);                                                     \
+    auto kern = lw_2stream_reg_kernel<CLV, true>;                                                          \
+    RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    kern<<<grid, kRegThreads, smem, stream()>>>(q, maps);                                                  \
+  } else {                                                                                                 \
+    lw_2stream_reg_kernel<CLV, false><<<grid, kRegThreads, 0, stream()>>>(q, maps);                        \
+  }
+      // the chunk length fixes the association of the chunk-level scan: it must not depend on use_tma (see
+      // rte_lw_solver_noscat); CL = 8 conflicts on the TMA tiles, so nlay <= 64 runs CL = 9 as well
+      switch (cl) {
+        case 8:
+        case 9: LW2S(9); break;
+        default: LW2S(10); break;
+      }
+#undef LW2S
+      RB_LAUNCH_CHECK();
+    }
     return;
   }
   const size_t per_col = (size_t)6 * nlay;

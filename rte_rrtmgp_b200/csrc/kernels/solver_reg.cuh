@@ -688,8 +688,21 @@ struct Lw2sRegParams {
   int gpt_per_block;
 };
 
-template <int CL>
-__global__ void __launch_bounds__(kRegThreads, 4) lw_2stream_reg_kernel(const Lw2sRegParams p) {
+// TMA variant: tau, ssa, g, lay_source (nlay rows) and lev_source (nlay+1 rows) tiles per g-point, two stages.
+struct Lw2sTmaMaps { CUtensorMap tau, ssa, g, lay, lev; };
+__host__ __device__ inline size_t lw_2stream_reg_tma_smem(int nlay) {
+  return 2 * (4 * tile_bytes(nlay) + tile_bytes(nlay + 1)) + 2 * sizeof(uint64_t);
+}
+
+template <int CL, bool TMA = false>
+__global__ void __launch_bounds__(kRegThreads, TMA ? 2 : 3) lw_2stream_reg_kernel(const Lw2sRegParams p,
+                                                                                  const __grid_constant__ Lw2sTmaMaps tm) {
+  // no static shared memory: the swizzled TMA tiles need the dynamic window to start 1024-byte aligned
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const size_t tb_lay = TMA ? tile_bytes(p.nlay) : 0, tb_lev = TMA ? tile_bytes(p.nlay + 1) : 0;
+  const size_t stageb = 4 * tb_lay + tb_lev;
+  const int te_lay = (int)(tb_lay / sizeof(Float));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * stageb);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = lane >> 3, j = lane & 7;
   const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
@@ -702,47 +715,85 @@ __global__ void __launch_bounds__(kRegThreads, 4) lw_2stream_reg_kernel(const Lw
   const Float LW_diff_sec = (Float)1.66f;  // :870 single-precision literal widened to wp
   const int k0 = j * CL;
   const int gb = blockIdx.y * p.gpt_per_block, ge = min(p.ngpt, gb + p.gpt_per_block);
+  const int cta_col0 = blockIdx.x * (kRegThreads / 32) * kRegCols;
+  const int cw = warp * kRegCols + c;
+
+  auto issue = [&](int g, int s) {  // TMA only
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&full_bar[s], (uint32_t)((4 * nlay + nlev) * kTmaCols * sizeof(Float)));
+      unsigned char* dst = smem_raw + (size_t)s * stageb;
+      tma_load_tile(dst, &tm.tau, &full_bar[s], cta_col0, 0, g);
+      tma_load_tile(dst + tb_lay, &tm.ssa, &full_bar[s], cta_col0, 0, g);
+      tma_load_tile(dst + 2 * tb_lay, &tm.g, &full_bar[s], cta_col0, 0, g);
+      tma_load_tile(dst + 3 * tb_lay, &tm.lay, &full_bar[s], cta_col0, 0, g);
+      tma_load_tile(dst + 4 * tb_lay, &tm.lev, &full_bar[s], cta_col0, 0, p.lev_per_gpt ? g : 0);  // quirk :422
+    }
+  };
+  if (TMA) {
+    if (threadIdx.x == 0) {
+      mbar_init(&full_bar[0], 1);
+      mbar_init(&full_bar[1], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (gb < ge) issue(gb, 0);
+    if (gb + 1 < ge) issue(gb + 1, 1);
+  }
 
   for (int g = gb; g < ge; ++g) {
+    const int s = (g - gb) & 1;
     const size_t gi = col + ncol * g;
     const size_t gsrc = p.lev_per_gpt ? g : 0;  // reference default-kernel quirk (:422), see the ABI header
     Float* gup = p.flux_up + nclp * g;
     Float* gdn = p.flux_dn + nclp * g;
+    const Float* tile_tau = reinterpret_cast<const Float*>(smem_raw + (size_t)s * stageb);
+    const Float* tile_lev = tile_tau + 4 * te_lay;
+    if (TMA) mbar_wait(&full_bar[s], (uint32_t)(((g - gb) >> 1) & 1));
     Float R[CL], T[CL], SU[CL], SD[CL], Blev[CL + 1];
 #pragma unroll
     for (int i = 0; i <= CL; ++i) {
       const int kk = min(k0 + i, nlay);
-      Blev[i] = p.lev_source[col + ncol * o.lev(kk) + nclp * gsrc];
+      Blev[i] = TMA ? *tile_at(tile_lev, o.lev(kk), cw) : p.lev_source[col + ncol * o.lev(kk) + nclp * gsrc];
     }
+    // straight-line per cell (see sw_2stream_reg_kernel): padding cells become pass-through cells by selects
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
-      const int k = k0 + i;
-      if (k < nlay) {
-        const size_t i3 = col + ncol * o.lay(k) + ncl * g;
-        const Float tau = p.tau[i3], w0 = p.ssa[i3], gg = p.g[i3];
-        const Float gamma1 = LW_diff_sec * ((Float)1 - (Float)0.5 * w0 * ((Float)1 + gg));   // :879
-        const Float gamma2 = LW_diff_sec * (Float)0.5 * w0 * ((Float)1 - gg);                // :880
-        const Float kk = rb_sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), (Float)1.e-12));   // :885
-        const Float exp_minusktau = rb_exp(-tau * kk);
-        const Float exp_minus2ktau = exp_minusktau * exp_minusktau;
-        const Float RT_term = rb_rcp(kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau));
-        const Float rdif = RT_term * gamma2 * ((Float)1 - exp_minus2ktau);
-        const Float tdif = RT_term * (Float)2 * kk * exp_minusktau;
-        const Float lev_top = Blev[i], lev_bot = Blev[i + 1];
-        Float s_up = 0, s_dn = 0;
-        if (tau > (Float)1.0e-8) {  // :947-957
-          const Float Z = rb_div(lev_bot - lev_top, tau * (gamma1 + gamma2));
-          const Float Zup_top = Z + lev_top;
-          const Float Zup_bottom = Z + lev_bot;
-          const Float Zdn_top = -Z + lev_top;
-          const Float Zdn_bottom = -Z + lev_bot;
-          s_up = pi * (Zup_top - rdif * Zdn_top - tdif * Zup_bottom);
-          s_dn = pi * (Zdn_bottom - rdif * Zup_bottom - tdif * Zdn_top);
-        }
-        R[i] = rdif; T[i] = tdif; SU[i] = s_up; SD[i] = s_dn;
+      const bool live = k0 + i < nlay;
+      const int lay = o.lay(min(k0 + i, nlay - 1));
+      Float tau, w0, gg;
+      if (TMA) {
+        const Float* e = tile_at(tile_tau, lay, cw);
+        tau = e[0]; w0 = e[te_lay]; gg = e[2 * te_lay];
       } else {
-        R[i] = 0; T[i] = 1; SU[i] = 0; SD[i] = 0;
+        const size_t i3 = col + ncol * lay + ncl * g;
+        tau = p.tau[i3]; w0 = p.ssa[i3]; gg = p.g[i3];
       }
+      const Float gamma1 = LW_diff_sec * ((Float)1 - (Float)0.5 * w0 * ((Float)1 + gg));   // :879
+      const Float gamma2 = LW_diff_sec * (Float)0.5 * w0 * ((Float)1 - gg);                // :880
+      const Float kk = rb_sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), (Float)1.e-12));   // :885
+      const Float exp_minusktau = rb_exp(-tau * kk);
+      const Float exp_minus2ktau = exp_minusktau * exp_minusktau;
+      const Float RT_term = rb_rcp(kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau));
+      const Float rdif = RT_term * gamma2 * ((Float)1 - exp_minus2ktau);
+      const Float tdif = RT_term * (Float)2 * kk * exp_minusktau;
+      const Float lev_top = Blev[i], lev_bot = Blev[i + 1];
+      // :947-957; the divisor is clamped where the source is switched off anyway (tau <= 1e-8)
+      const bool has_src = live && tau > (Float)1.0e-8;
+      const Float Z = rb_div(lev_bot - lev_top, fmax(tau, (Float)1.0e-8) * (gamma1 + gamma2));
+      const Float Zup_top = Z + lev_top;
+      const Float Zup_bottom = Z + lev_bot;
+      const Float Zdn_top = -Z + lev_top;
+      const Float Zdn_bottom = -Z + lev_bot;
+      const Float s_up = pi * (Zup_top - rdif * Zdn_top - tdif * Zup_bottom);
+      const Float s_dn = pi * (Zdn_bottom - rdif * Zup_bottom - tdif * Zdn_top);
+      R[i] = live ? rdif : (Float)0;
+      T[i] = live ? tdif : (Float)1;
+      SU[i] = has_src ? s_up : (Float)0;
+      SD[i] = has_src ? s_dn : (Float)0;
+    }
+    if (TMA) {  // every warp of the CTA has read stage s into registers: hand it back to the TMA for g+2
+      __syncthreads();
+      if (g + 2 < ge) issue(g + 2, s);
     }
     const Float emis = p.sfc_emis[gi];
     auto top = [&](Float fup, Float fdn) {
