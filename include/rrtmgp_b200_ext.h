@@ -192,10 +192,13 @@ typedef struct {
  * RRTMGPB_TMA=1 in the environment turns staging on at start-up. */
 void rrtmgpb_set_tma_staging(int on);
 
+/* aer_*: a second by-band increment applied after the cloud one (the driver's aerosols%increment(atmos),
+ * examples/all-sky/rrtmgp_allsky.F90:377,398), same kinds. */
 void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, const Float* play, const Float* plev,
                               const Float* tlay, const Float* vmr, const Float* col_dry /* or NULL */, int op_kind,
                               Float* tau, Float* ssa, Float* g, int cld_kind, const Float* cld_tau,
-                              const Float* cld_ssa, const Float* cld_g, const Float* tlev, const Float* tsfc,
+                              const Float* cld_ssa, const Float* cld_g, int aer_kind, const Float* aer_tau,
+                              const Float* aer_ssa, const Float* aer_g, const Float* tlev, const Float* tsfc,
                               int sfc_lay, Float* sfc_src, Float* lay_src /* NULL: no sources */, Float* lev_src,
                               Float* sfc_source_Jac);
 

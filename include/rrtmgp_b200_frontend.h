@@ -136,11 +136,13 @@ int rrtmgpb_gas_optics_int_fused(const rrtmgpb_gas_optics_t* go, int ncol, int n
                                  const Float* plev, const Float* tlay, const Float* tsfc, const Float* vmr,
                                  rrtmgpb_optical_props* optical_props, rrtmgpb_source_func_lw* sources,
                                  const Float* col_dry, const Float* tlev, const rrtmgpb_optical_props* clouds,
+                                 const rrtmgpb_optical_props* aerosols /* second increment, after clouds; or NULL */,
                                  char* errmsg);
 int rrtmgpb_gas_optics_ext_fused(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play,
                                  const Float* plev, const Float* tlay, const Float* vmr,
                                  rrtmgpb_optical_props* optical_props, Float* toa_src, const Float* col_dry,
-                                 const rrtmgpb_optical_props* clouds, char* errmsg);
+                                 const rrtmgpb_optical_props* clouds, const rrtmgpb_optical_props* aerosols,
+                                 char* errmsg);
 
 /* ---------------- ty_cloud_optics_rrtmgp (LUT form) ---------------- */
 typedef struct {

@@ -172,7 +172,8 @@ void rrtmgpb_compute_tau_absorption_assign(
 void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, const Float* play, const Float* plev,
                               const Float* tlay, const Float* vmr, const Float* col_dry, int op_kind, Float* tau,
                               Float* ssa, Float* g, int cld_kind, const Float* cld_tau, const Float* cld_ssa,
-                              const Float* cld_g, const Float* tlev, const Float* tsfc, int sfc_lay, Float* sfc_src,
+                              const Float* cld_g, int aer_kind, const Float* aer_tau, const Float* aer_ssa,
+                              const Float* aer_g, const Float* tlev, const Float* tsfc, int sfc_lay, Float* sfc_src,
                               Float* lay_src, Float* lev_src, Float* sfc_source_Jac) {
   const size_t ncl = (size_t)ncol * nlay, nf = (size_t)t->nflav;
   const int ngpt = t->ngpt, nbnd = t->nbnd;
@@ -212,6 +213,10 @@ void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, c
   if (cld_kind == 2 && op_kind == 1) rte_inc_1scalar_by_2stream_bybnd(&ncol, &nlay, &ngpt, tau, cld_tau, cld_ssa, &nbnd, t->band_lims_gpt);
   if (cld_kind == 1 && op_kind == 2) rte_inc_2stream_by_1scalar_bybnd(&ncol, &nlay, &ngpt, tau, ssa, cld_tau, &nbnd, t->band_lims_gpt);
   if (cld_kind == 2 && op_kind == 2) rte_inc_2stream_by_2stream_bybnd(&ncol, &nlay, &ngpt, tau, ssa, g, cld_tau, cld_ssa, cld_g, &nbnd, t->band_lims_gpt);
+  if (aer_kind == 1 && op_kind == 1) rte_inc_1scalar_by_1scalar_bybnd(&ncol, &nlay, &ngpt, tau, aer_tau, &nbnd, t->band_lims_gpt);
+  if (aer_kind == 2 && op_kind == 1) rte_inc_1scalar_by_2stream_bybnd(&ncol, &nlay, &ngpt, tau, aer_tau, aer_ssa, &nbnd, t->band_lims_gpt);
+  if (aer_kind == 1 && op_kind == 2) rte_inc_2stream_by_1scalar_bybnd(&ncol, &nlay, &ngpt, tau, ssa, aer_tau, &nbnd, t->band_lims_gpt);
+  if (aer_kind == 2 && op_kind == 2) rte_inc_2stream_by_2stream_bybnd(&ncol, &nlay, &ngpt, tau, ssa, g, aer_tau, aer_ssa, aer_g, &nbnd, t->band_lims_gpt);
   if (lay_src)
     rrtmgp_compute_Planck_source(&ncol, &nlay, &nbnd, &ngpt, &t->nflav, &t->neta, &t->npres, &t->ntemp, &t->nPlanckTemp,
                                  tlay, tlev, tsfc, &sfc_lay, fmajor, jeta, tropo, jtemp, jpress, t->gpoint_bands,

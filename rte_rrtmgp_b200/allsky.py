@@ -98,17 +98,18 @@ class AllSky:
             lw.co.cloud_optics(self.lwp, self.iwp, self.rel, self.dei, lw.clouds)
         if self.do_aerosols:
             lw.ao.aerosol_optics(self.aero_type, self.aero_size, self.aero_mass, self.relhum, lw.aerosols)
-        if self.fused:  # gas optics + clouds%increment(atmos) in one pass (same caller-visible results)
+        if self.fused:  # gas optics + clouds%increment(atmos) [+ aerosols%increment(atmos)] in one pass
             lw.go.gas_optics(self.p_lay, self.p_lev, self.t_lay, self.vmr, lw.atmos, t_sfc=lw.t_sfc,
                              sources=lw.sources, tlev=self.t_lev, fused=True,
-                             increment_by=lw.clouds if self.do_clouds else None)
+                             increment_by=lw.clouds if self.do_clouds else None,
+                             increment_by2=lw.aerosols if self.do_aerosols else None)
         else:
             lw.go.gas_optics(self.p_lay, self.p_lev, self.t_lay, self.vmr, lw.atmos, t_sfc=lw.t_sfc,
                              sources=lw.sources, tlev=self.t_lev)
             if self.do_clouds:
                 lw.clouds.increment(lw.atmos)
-        if self.do_aerosols:
-            lw.aerosols.increment(lw.atmos)
+            if self.do_aerosols:
+                lw.aerosols.increment(lw.atmos)
         if self.lw_2stream:
             rte_lw_bygpoint(self.ctx, lw.atmos, lw.sources, lw.emis_sfc, lw.gpt_flux_up, lw.gpt_flux_dn, use_2stream=1)
             ngpt, nlev = lw.go.ngpt, self.nlay + 1
@@ -126,16 +127,19 @@ class AllSky:
             sw.clouds.delta_scale()
         if self.do_aerosols:
             sw.ao.aerosol_optics(self.aero_type, self.aero_size, self.aero_mass, self.relhum, sw.aerosols)
-        if self.fused:
+        if self.fused:  # aerosols%delta_scale() does not depend on the gas optics: it moves in front of the fused pass
+            if self.do_aerosols:
+                sw.aerosols.delta_scale()
             sw.go.gas_optics(self.p_lay, self.p_lev, self.t_lay, self.vmr, sw.atmos, toa_src=sw.toa_flux, fused=True,
-                             increment_by=sw.clouds if self.do_clouds else None)
+                             increment_by=sw.clouds if self.do_clouds else None,
+                             increment_by2=sw.aerosols if self.do_aerosols else None)
         else:
             sw.go.gas_optics(self.p_lay, self.p_lev, self.t_lay, self.vmr, sw.atmos, toa_src=sw.toa_flux)
             if self.do_clouds:
                 sw.clouds.increment(sw.atmos)
-        if self.do_aerosols:
-            sw.aerosols.delta_scale()
-            sw.aerosols.increment(sw.atmos)
+            if self.do_aerosols:
+                sw.aerosols.delta_scale()
+                sw.aerosols.increment(sw.atmos)
         rte_sw(self.ctx, sw.atmos, sw.mu0, sw.toa_flux, sw.sfc_alb_dir, sw.sfc_alb_dif, sw.fluxes)
 
     def step(self):

@@ -270,7 +270,8 @@ void rrtmgpb_set_tma_staging(int on) { (void)on; }
 void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, const Float* play, const Float* plev,
                               const Float* tlay, const Float* vmr, const Float* col_dry, int op_kind, Float* tau,
                               Float* ssa, Float* g, int cld_kind, const Float* cld_tau, const Float* cld_ssa,
-                              const Float* cld_g, const Float* tlev, const Float* tsfc, int sfc_lay, Float* sfc_src,
+                              const Float* cld_g, int aer_kind, const Float* aer_tau, const Float* aer_ssa,
+                              const Float* aer_g, const Float* tlev, const Float* tsfc, int sfc_lay, Float* sfc_src,
                               Float* lay_src, Float* lev_src, Float* sfc_source_Jac) {
   const size_t ncl = (size_t)ncol * nlay;
   FusedParams p;
@@ -278,19 +279,22 @@ void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, c
   p.ncol = ncol; p.nlay = nlay; p.play = play; p.plev = plev; p.tlay = tlay; p.vmr = vmr; p.col_dry_in = col_dry;
   p.op_kind = op_kind; p.tau = tau; p.ssa = ssa; p.g = g;
   p.cld_kind = cld_kind; p.cld_tau = cld_tau; p.cld_ssa = cld_ssa; p.cld_g = cld_g;
+  p.aer_kind = aer_kind; p.aer_tau = aer_tau; p.aer_ssa = aer_ssa; p.aer_g = aer_g;
   const TablesT tt = tables_gfast(*t);
   Workspace w = prepare(p);
   const bool sw = t->krayl != nullptr;
   {
     KernelTimer timer(sw ? "gas_tau_fused[sw]" : "gas_tau_fused[lw]");
     const unsigned grid = (unsigned)((long long)ceil_div((long long)ncl, kTauCells * kGThreads) * t->nbnd);
+#define GAS_TAU_LAUNCH(SWV, VECV)                                                                 \
+  if (aer_kind) gas_tau_g_kernel<SWV, VECV, true><<<grid, kGThreads, 0, stream()>>>(p, tt);       \
+  else gas_tau_g_kernel<SWV, VECV, false><<<grid, kGThreads, 0, stream()>>>(p, tt)
     if (sw) {
-      if (tt.vec == 2) gas_tau_g_kernel<true, 2><<<grid, kGThreads, 0, stream()>>>(p, tt);
-      else gas_tau_g_kernel<true, 1><<<grid, kGThreads, 0, stream()>>>(p, tt);
+      if (tt.vec == 2) { GAS_TAU_LAUNCH(true, 2); } else { GAS_TAU_LAUNCH(true, 1); }
     } else {
-      if (tt.vec == 2) gas_tau_g_kernel<false, 2><<<grid, kGThreads, 0, stream()>>>(p, tt);
-      else gas_tau_g_kernel<false, 1><<<grid, kGThreads, 0, stream()>>>(p, tt);
+      if (tt.vec == 2) { GAS_TAU_LAUNCH(false, 2); } else { GAS_TAU_LAUNCH(false, 1); }
     }
+#undef GAS_TAU_LAUNCH
     RB_LAUNCH_CHECK();
   }
   if (lay_src) {

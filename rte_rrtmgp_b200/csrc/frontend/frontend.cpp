@@ -670,7 +670,7 @@ static int gas_optics_fused_impl(const rrtmgpb_gas_optics_t* go, int ncol, int n
                                  const Float* plev, const Float* tlay, const Float* tsfc, const Float* vmr,
                                  rrtmgpb_optical_props* op, rrtmgpb_source_func_lw* sources, Float* toa_src,
                                  const Float* col_dry, const Float* tlev, const rrtmgpb_optical_props* clouds,
-                                 char* errmsg) {
+                                 const rrtmgpb_optical_props* aerosols, char* errmsg) {
   const rrtmgpb_kdist& k = go->h;
   const size_t ncl = (size_t)ncol * nlay;
   std::string msg;
@@ -696,15 +696,17 @@ static int gas_optics_fused_impl(const rrtmgpb_gas_optics_t* go, int ncol, int n
       msg = "gas_optics(): array tlev has values outside range";
   }
   if (msg.empty() && op->kind == RRTMGPB_NSTR) msg = "gas_optics(): n-stream optical properties are not supported by this frontend";
-  int cld_kind = 0;
-  if (msg.empty() && clouds) {
-    if (clouds->ncol != ncol || clouds->nlay != nlay)
+  int cld_kind = 0, aer_kind = 0;
+  for (int which = 0; which < 2 && msg.empty(); ++which) {  // the checks of increment() (:893-905,956-961) for both
+    const rrtmgpb_optical_props* inc = which ? aerosols : clouds;
+    if (!inc) continue;
+    if (inc->ncol != ncol || inc->nlay != nlay)
       msg = "ty_optical_props%increment: optical properties objects have different ncol and/or nlay";
-    else if (clouds->nband != op->nband || clouds->ngpt != op->nband)
+    else if (inc->nband != op->nband || inc->ngpt != op->nband)
       msg = "ty_optical_props%increment: optical properties objects have incompatible g-point structures";
-    else if (clouds->kind == RRTMGPB_NSTR)
-      msg = "ty_optical_props%increment: n-stream clouds are not supported by the fused path";
-    cld_kind = clouds->kind;
+    else if (inc->kind == RRTMGPB_NSTR)
+      msg = "ty_optical_props%increment: n-stream properties are not supported by the fused path";
+    (which ? aer_kind : cld_kind) = inc->kind;
   }
   if (!msg.empty()) return fail(errmsg, msg);
   Float* tlev_alloc = nullptr;
@@ -718,7 +720,8 @@ static int gas_optics_fused_impl(const rrtmgpb_gas_optics_t* go, int ncol, int n
   const int sfc_lay = op->top_at_1 ? nlay : 1;
   rrtmgpb_gas_optics_fused(&t, ncol, nlay, play, plev, tlay, vmr, col_dry, op->kind, op->tau, op->ssa, op->g, cld_kind,
                            clouds ? clouds->tau : nullptr, clouds ? clouds->ssa : nullptr, clouds ? clouds->g : nullptr,
-                           tlev_wk, tsfc, sfc_lay, sources ? sources->sfc_source : nullptr,
+                           aer_kind, aerosols ? aerosols->tau : nullptr, aerosols ? aerosols->ssa : nullptr,
+                           aerosols ? aerosols->g : nullptr, tlev_wk, tsfc, sfc_lay, sources ? sources->sfc_source : nullptr,
                            sources ? sources->lay_source : nullptr, sources ? sources->lev_source : nullptr,
                            sources ? sources->sfc_source_Jac : nullptr);
   if (toa_src) rrtmgpb_broadcast_by_gpt(ncol, k.ngpt, go->solar_source, toa_src);
@@ -729,19 +732,20 @@ static int gas_optics_fused_impl(const rrtmgpb_gas_optics_t* go, int ncol, int n
 int rrtmgpb_gas_optics_int_fused(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play,
                                  const Float* plev, const Float* tlay, const Float* tsfc, const Float* vmr,
                                  rrtmgpb_optical_props* op, rrtmgpb_source_func_lw* sources, const Float* col_dry,
-                                 const Float* tlev, const rrtmgpb_optical_props* clouds, char* errmsg) {
+                                 const Float* tlev, const rrtmgpb_optical_props* clouds,
+                                 const rrtmgpb_optical_props* aerosols, char* errmsg) {
   if (!go->totplnk) return fail(errmsg, "gas_optics(): no internal (Planck) source tables loaded");
   return gas_optics_fused_impl(go, ncol, nlay, play, plev, tlay, tsfc, vmr, op, sources, nullptr, col_dry, tlev, clouds,
-                               errmsg);
+                               aerosols, errmsg);
 }
 
 int rrtmgpb_gas_optics_ext_fused(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play,
                                  const Float* plev, const Float* tlay, const Float* vmr, rrtmgpb_optical_props* op,
                                  Float* toa_src, const Float* col_dry, const rrtmgpb_optical_props* clouds,
-                                 char* errmsg) {
+                                 const rrtmgpb_optical_props* aerosols, char* errmsg) {
   if (!go->solar_source) return fail(errmsg, "gas_optics(): no external (solar) source loaded");
   return gas_optics_fused_impl(go, ncol, nlay, play, plev, tlay, nullptr, vmr, op, nullptr, toa_src, col_dry, nullptr,
-                               clouds, errmsg);
+                               clouds, aerosols, errmsg);
 }
 
 // ------------------------------------------------------------------------------------------------

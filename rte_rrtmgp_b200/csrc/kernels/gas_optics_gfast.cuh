@@ -72,6 +72,9 @@ struct FusedParams {
   // optional by-band cloud increment (kind 0 = none; 1 = 1scl tau ; 2 = 2str tau, ssa, g)
   int cld_kind;
   const Float *cld_tau, *cld_ssa, *cld_g;
+  // optional second by-band increment applied after the cloud one (aerosols), same kinds
+  int aer_kind;
+  const Float *aer_tau, *aer_ssa, *aer_g;
 };
 
 struct PlanckFusedParams {
@@ -191,11 +194,12 @@ struct TauCell {
   size_t c;       // cell index (clamped into range; `valid` says whether it may be stored)
   bool valid;
   Float col_dry, ct, cw, cg, amount_rayl;
+  Float at, aw, ag;  // second increment (only touched by the AER instantiations)
   FlavW w;
 };
 
 // NC cells that share tropo, jtemp and the table rows (row0, row1 => je[0], je[1]) of band `bi`
-template <bool SW, int VEC, int NC>
+template <bool SW, int VEC, int NC, bool AER>
 __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const TablesT& tt, const BandInfo& bi, bool tropo,
                                                int jtemp, int row0, int row1, TauCell (&cell)[NC]) {
   const rrtmgpb_gas_tables& t = p.t;
@@ -309,24 +313,33 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
         // division sequence made up half of this kernel's instructions (profiles/r1_v8_gas_tau_sw.txt)
         ss = (to > (Float)2 * (Float)RB_TINY) ? rb_div(tray, to) : (Float)0;
       }
-      const Float ct = cell[k].ct, cw = cell[k].cw, cg = cell[k].cg;
       const size_t o = cell[k].c + goff + ncl * (size_t)i;
+      // by-band increments of (to[, ss, gg]) by (ct, cw, cg): mo_optical_props_kernels.F90:366-477; the cloud one
+      // first, then (AER instantiations) the aerosol one
       if (p.op_kind == 1) {
-        if (p.cld_kind == 1) to = to + ct;                         // inc_1scalar_by_1scalar_bybnd :379
-        else if (p.cld_kind == 2) to = to + ct * ((Float)1 - cw);  // inc_1scalar_by_2stream_bybnd :398
+        auto inc1 = [&](int kind, Float ct, Float cw) {
+          if (kind == 1) to = to + ct;                         // inc_1scalar_by_1scalar_bybnd :379
+          else if (kind == 2) to = to + ct * ((Float)1 - cw);  // inc_1scalar_by_2stream_bybnd :398
+        };
+        inc1(p.cld_kind, cell[k].ct, cell[k].cw);
+        if (AER) inc1(p.aer_kind, cell[k].at, cell[k].aw);
         if (cell[k].valid) p.tau[o] = to;
       } else {
-        if (p.cld_kind == 1) {                                     // inc_2stream_by_1scalar_bybnd :440-442
-          const Float tau12 = to + ct;
-          ss = rb_div(to * ss, fmax(eps3, tau12));
-          to = tau12;
-        } else if (p.cld_kind == 2) {                              // inc_2stream_by_2stream_bybnd :468-477
-          const Float tau12 = to + ct;
-          const Float tauscat12 = to * ss + ct * cw;
-          gg = rb_div(to * ss * gg + ct * cw * cg, fmax(eps3, tauscat12));
-          ss = rb_div(tauscat12, fmax(eps3, tau12));
-          to = tau12;
-        }
+        auto inc2 = [&](int kind, Float ct, Float cw, Float cg) {
+          if (kind == 1) {                                     // inc_2stream_by_1scalar_bybnd :440-442
+            const Float tau12 = to + ct;
+            ss = rb_div(to * ss, fmax(eps3, tau12));
+            to = tau12;
+          } else if (kind == 2) {                              // inc_2stream_by_2stream_bybnd :468-477
+            const Float tau12 = to + ct;
+            const Float tauscat12 = to * ss + ct * cw;
+            gg = rb_div(to * ss * gg + ct * cw * cg, fmax(eps3, tauscat12));
+            ss = rb_div(tauscat12, fmax(eps3, tau12));
+            to = tau12;
+          }
+        };
+        inc2(p.cld_kind, cell[k].ct, cell[k].cw, cell[k].cg);
+        if (AER) inc2(p.aer_kind, cell[k].at, cell[k].aw, cell[k].ag);
         if (cell[k].valid) {
           p.tau[o] = to;
           p.ssa[o] = ss;
@@ -363,7 +376,7 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
   }
 }
 
-template <bool SW, int VEC>
+template <bool SW, int VEC, bool AER>
 __global__ void __launch_bounds__(kGThreads, RB_TAU_MINB) gas_tau_g_kernel(const FusedParams p, const TablesT tt) {
   const rrtmgpb_gas_tables& t = p.t;
   const size_t ncl = (size_t)p.ncol * p.nlay;
@@ -401,6 +414,12 @@ __global__ void __launch_bounds__(kGThreads, RB_TAU_MINB) gas_tau_g_kernel(const
       ce.ct = p.cld_tau[cb];
       if (p.cld_kind == 2) { ce.cw = p.cld_ssa[cb]; ce.cg = p.cld_g[cb]; }
     }
+    ce.at = 0; ce.aw = 0; ce.ag = 0;
+    if (AER && p.aer_kind) {
+      const size_t cb = c + ncl * (size_t)ibnd;
+      ce.at = p.aer_tau[cb];
+      if (p.aer_kind == 2) { ce.aw = p.aer_ssa[cb]; ce.ag = p.aer_g[cb]; }
+    }
     ce.amount_rayl = SW ? col_gas_of(p, c, ncl, t.idx_h2o, ce.col_dry) + ce.col_dry : (Float)0;  // :559
   }
   bool shared_rows = true;
@@ -409,13 +428,13 @@ __global__ void __launch_bounds__(kGThreads, RB_TAU_MINB) gas_tau_g_kernel(const
     shared_rows = shared_rows && tropo[k] == tropo[0] && row0[k] == row0[0] && row1[k] == row1[0];
   if (tropo[0] ? bi.mdiff[0] : bi.mdiff[1]) shared_rows = false;
   if (shared_rows) {
-    tau_band_cells<SW, VEC, kTauCells>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell);
+    tau_band_cells<SW, VEC, kTauCells, AER>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell);
   } else {
 #pragma unroll
     for (int k = 0; k < kTauCells; ++k) {
       if (!cell[k].valid) continue;
       TauCell one[1] = {cell[k]};
-      tau_band_cells<SW, VEC, 1>(p, tt, bi, tropo[k], jtemp[k], row0[k], row1[k], one);
+      tau_band_cells<SW, VEC, 1, AER>(p, tt, bi, tropo[k], jtemp[k], row0[k], row1[k], one);
     }
   }
 }

@@ -266,9 +266,10 @@ class GasOptics:
         return not self.kd.is_lw
 
     def gas_optics(self, p_lay, p_lev, t_lay, vmr, optical_props, t_sfc=None, sources=None, toa_src=None,
-                   col_dry=None, tlev=None, fused=False, increment_by=None):
+                   col_dry=None, tlev=None, fused=False, increment_by=None, increment_by2=None):
         """fused=False: the reference call sequence, kernel by kernel.  fused=True: one fused pass
-        (rrtmgpb_gas_optics_*_fused) that can also fold in `increment_by%increment(optical_props)`."""
+        (rrtmgpb_gas_optics_*_fused) that can also fold in `increment_by%increment(optical_props)` and then
+        `increment_by2%increment(optical_props)` (clouds, aerosols: rrtmgp_allsky.F90:376-377,392-399)."""
         ncol, nlay = optical_props.ncol, optical_props.nlay
         err = C.create_string_buffer(ERRLEN)
         o = optical_props.struct()
@@ -276,19 +277,21 @@ class GasOptics:
         if fused:
             cl = increment_by.struct() if increment_by is not None else None
             clp = C.byref(cl) if cl is not None else None
+            ae = increment_by2.struct() if increment_by2 is not None else None
+            aep = C.byref(ae) if ae is not None else None
             if self.kd.is_lw:
                 s = sources.struct()
                 rc = self.ctx.c.rrtmgpb_gas_optics_int_fused(C.c_void_p(self.handle), ncol, nlay, P(p_lay), P(p_lev),
                                                              P(t_lay), P(t_sfc), P(vmr), C.byref(o), C.byref(s),
-                                                             P(col_dry), P(tlev), clp, err)
+                                                             P(col_dry), P(tlev), clp, aep, err)
             else:
                 rc = self.ctx.c.rrtmgpb_gas_optics_ext_fused(C.c_void_p(self.handle), ncol, nlay, P(p_lay), P(p_lev),
                                                              P(t_lay), P(vmr), C.byref(o), P(toa_src), P(col_dry),
-                                                             clp, err)
+                                                             clp, aep, err)
             _check(rc, err)
             optical_props._sync_back(o)
             return
-        if increment_by is not None:
+        if increment_by is not None or increment_by2 is not None:
             raise ValueError("increment_by needs fused=True")
         if self.kd.is_lw:
             s = sources.struct()

@@ -164,3 +164,36 @@ def test_allsky_with_aerosols(oracle_lib, cuda_lib, ncol, nlay, lw_2stream):
     if lw_2stream:
         x, y = g.ctx.get(g.lw.gpt_flux_up), c.ctx.get(c.lw.gpt_flux_up)
         assert np.max(np.abs(x - y)) <= FLUX_ATOL
+
+
+@pytest.mark.parametrize("lw_2stream", [False, True])
+def test_oracle_fused_with_aerosols_equals_reference_sequence(oracle_lib, lw_2stream):
+    """gas_optics(..., increment_by=clouds, increment_by2=aerosols) on the oracle is literally the reference sequence
+    (gas optics, clouds%increment, aerosols%increment): bit-identical fluxes."""
+    kd_lw, kd_sw = syn.make_kdist("lw", ngpt=32), syn.make_kdist("sw", ngpt=28)
+    ctx = Context(oracle_lib, None)
+    res = []
+    for fused in (True, False):
+        a = AllSky(ctx, 9, 40, kd_lw, kd_sw, do_aerosols=True, lw_2stream=lw_2stream, fused=fused)
+        a.step()
+        res.append(a.fluxes_host())
+    for k in res[0]:
+        np.testing.assert_array_equal(res[0][k], res[1][k], err_msg=k)
+
+
+@pytest.mark.gpu
+def test_cuda_fused_and_sequence_with_aerosols(oracle_lib, cuda_lib):
+    """CUDA: the fused pass with both increments and the kernel-by-kernel sequence both match the oracle."""
+    kd_lw, kd_sw = syn.make_kdist("lw"), syn.make_kdist("sw")
+    c = AllSky(Context(oracle_lib, None), 30, 72, kd_lw, kd_sw, do_aerosols=True, fused=False)
+    c.step()
+    fc = c.fluxes_host()
+    for fused in (True, False):
+        g = AllSky(Context(cuda_lib, "cuda:0"), 30, 72, kd_lw, kd_sw, do_aerosols=True, fused=fused)
+        g.step()
+        fg = g.fluxes_host()
+        for k in fc:
+            assert np.max(np.abs(fg[k] - fc[k])) <= FLUX_ATOL, (k, fused)
+        for name, ga, ca in (("lw tau", g.lw.atmos.tau, c.lw.atmos.tau), ("sw tau", g.sw.atmos.tau, c.sw.atmos.tau),
+                             ("sw ssa", g.sw.atmos.ssa, c.sw.atmos.ssa), ("sw g", g.sw.atmos.g, c.sw.atmos.g)):
+            np.testing.assert_allclose(g.ctx.get(ga), c.ctx.get(ca), rtol=1e-12, atol=1e-300, err_msg=f"{name} fused={fused}")
