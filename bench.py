@@ -360,6 +360,27 @@ def run_product(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * ncol / (float(t.item()) / args.steps * 1e-3)
 
+    # ---- N > 1: the optional epilogue of SURVEY 8(e) - broadband fluxes gathered to rank 0 over NCCL after every step
+    gather_value = None
+    if world > 1:
+        from rte_rrtmgp_b200.sharding import gather_fluxes_device
+        flux_t = [sky.lw.flux_up, sky.lw.flux_dn, sky.sw.flux_up, sky.sw.flux_dn, sky.sw.flux_dir]
+        recv = ([[torch.empty(tuple(reversed(t.shape)), dtype=t.dtype, device=t.device) for _ in range(world)] for t in flux_t]
+                if rank == 0 else None)
+        sky.step()
+        gather_fluxes_device(flux_t, rank, world, recv)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            sky.step()
+            gather_fluxes_device(flux_t, rank, world, recv)
+        g1.record()
+        barrier()
+        t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gather_value = world * ncol / (float(t.item()) / args.steps * 1e-3)
+
     # ---- the same step driven as the reference's call sequence, kernel by kernel through the 45 extern-ABI symbols
     # (what a stock Fortran frontend linked against this library executes); reported beside the headline
     seq_value = None
@@ -405,6 +426,7 @@ def run_product(args):
             "e2e": {"value": e2e_value, "unit": "columns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "value_reference_call_sequence": seq_value,
+            "value_with_flux_gather_to_rank0": gather_value,
             "roofline": roofline,
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "frac_of_hbm_peak": step_frac,
                               "bytes_per_column": step_bytes / ncol},

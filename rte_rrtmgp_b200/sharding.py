@@ -37,3 +37,22 @@ def gather_fluxes(fluxes, ncol, rank, world, device=None):
                 parts.append(b[: hi - lo].cpu().numpy())
             out[name] = np.asfortranarray(np.concatenate(parts, axis=0))
     return out if rank == 0 else None
+
+
+def gather_fluxes_device(tensors, rank, world, out=None):
+    """Device-resident variant for equal shards: gathers each (nlev, ncol_local) torch tensor (the Fortran (ncol, nlev)
+    array seen row-major) to rank 0 with one NCCL gather per array, no host staging.  `out`: optional list of per-array
+    lists of receive buffers to reuse on rank 0.  Returns the receive buffers on rank 0 (column order = rank order)."""
+    if world == 1:
+        return [[t] for t in tensors]
+    res = []
+    for i, t in enumerate(tensors):
+        # Fortran-ordered arrays are transposed views of contiguous storage: gather that storage
+        tc = t if t.is_contiguous() else t.permute(*reversed(range(t.dim())))
+        assert tc.is_contiguous()
+        bufs = None
+        if rank == 0:
+            bufs = out[i] if out is not None else [torch.empty_like(tc) for _ in range(world)]
+        dist.gather(tc, bufs, dst=0)
+        res.append(bufs)
+    return res if rank == 0 else None

@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 from rte_rrtmgp_b200 import synthetic as syn
 from rte_rrtmgp_b200.allsky import AllSky
 from rte_rrtmgp_b200.frontend import Context
-from rte_rrtmgp_b200.sharding import column_shard, gather_fluxes
+from rte_rrtmgp_b200.sharding import column_shard, gather_fluxes, gather_fluxes_device
 
 NCOL, NLAY = 22, 24
 
@@ -37,8 +37,17 @@ def _worker(rank, world, port, q):
     mine = {k: np.asfortranarray(v[lo:hi]) for k, v in prof.items()}
     sky = AllSky(Context(oracle.lib(), None), hi - lo, NLAY, kd_lw, kd_sw, profiles=mine, col_offset=lo)
     sky.step()
-    gathered = gather_fluxes(sky.fluxes_host(), NCOL, rank, world)
+    local = sky.fluxes_host()
+    gathered = gather_fluxes(local, NCOL, rank, world)
+    # the device-resident variant bench.py uses for N > 1 (here on CPU tensors over gloo): Fortran-ordered arrays
+    # as transposed views of contiguous storage, equal shards
+    names = sorted(local)
+    tens = [torch.from_numpy(np.ascontiguousarray(local[k].T)).T for k in names]
+    bufs = gather_fluxes_device(tens, rank, world)
     if rank == 0:
+        for k, per_rank in zip(names, bufs):
+            glued = np.concatenate([b.numpy().T for b in per_rank], axis=0)
+            assert np.array_equal(glued, gathered[k]), k
         q.put(gathered)
     dist.barrier()
     dist.destroy_process_group()
