@@ -78,6 +78,7 @@ inline EncodeTiledFn encode_tiled_fn() {
 // Tensor map of a Fortran-ordered (ncol, nrows, ngpt) plane with box (kTmaCols, nrows, 1).  Returns false when the
 // plane cannot be described (odd ncol -> strides not multiples of 16 B, misaligned base, more than 256 rows, no driver).
 inline bool make_plane_tmap(CUtensorMap* tm, const Float* base, int ncol, int nrows, int ngpt) {
+  if (sizeof(Float) != 8) return false;  // single-precision builds (untested tile layout) use the cp.async staging
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc || !base || nrows > 256 || ((size_t)ncol * sizeof(Float)) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) % 16) != 0)
     return false;
