@@ -45,6 +45,12 @@ long long rrtmgpb_launch_count(int reset);
 void rrtmgpb_profile_enable(int on);
 int rrtmgpb_profile_report(char* buf, size_t buflen);
 
+/* 1: the kernel-by-kernel entry points (rrtmgp_compute_tau_absorption) may keep g-point-fastest copies of the
+ * k-distribution tables, keyed by the kmajor pointer.  Only for callers that never change a table in place while its
+ * allocation lives and release it through rrtmgpb_mem_free (the C++ frontend mirror switches it on around its own
+ * calls); per host thread, default 0. */
+void rrtmgpb_abi_table_cache(int on);
+
 /* ---------------- physical constants ---------------- */
 /* replaces mo_gas_optics_constants.F90:42-51 init_constants(); NULL keeps the current value */
 void rrtmgpb_init_constants(const Float* gravity, const Float* mol_weight_dry_air,

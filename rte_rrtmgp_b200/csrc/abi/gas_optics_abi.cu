@@ -119,6 +119,8 @@ struct TauAbsParams {
   const int *jeta, *jtemp, *jpress;
   Float* tau;
   int accumulate;  // 1: tau += (reference contract, caller pre-zeroes); 0: tau = (fused frontend)
+  // GF kernels: kmajor / kminor point at g-point-fastest copies (kernels/gas_optics_gfast.cuh) with these row pitches
+  int gp, pitch_lower, pitch_upper;
 };
 
 // Table strides.  The k-distribution tables of rrtmgp-data all have ntemp = 14, neta = 9, npres+1 = 60;
@@ -134,7 +136,7 @@ struct TableDims {
   __device__ __forceinline__ int s_g() const { return (NT && NE && NP1) ? NT * NE * NP1 : nt * ne * np1; }
 };
 
-template <int NT, int NE, int NP1>
+template <int NT, int NE, int NP1, bool GF>
 __device__ __forceinline__ void minor_contrib(const MinorTables& m, const int itropo, const TauAbsParams& p,
                                               const TableDims<NT, NE, NP1>& td, size_t c, size_t ncl, int ibnd,
                                               int gS, int gE, Float (&acc)[kMaxG]) {
@@ -169,6 +171,22 @@ __device__ __forceinline__ void minor_contrib(const MinorTables& m, const int it
     const int2 je = reinterpret_cast<const int2*>(p.jeta)[cf];
     // table column of chunk slot i is kstart + (gS + i - mS) - 1 = kcol0 + i
     const long long kcol0 = (long long)__ldg(m.kminor_start + imnr) + (gS - mS) - 1;
+    if (GF) {  // g-point-fastest copy: row (jt + ntemp*je), consecutive g-points are consecutive addresses
+      const int pitch = itropo ? p.pitch_upper : p.pitch_lower;
+      const Float* k0 = m.kminor + (size_t)((jtemp - 1) + s_eta * (je.x - 1)) * pitch + kcol0;
+      const Float* k1 = m.kminor + (size_t)(jtemp + s_eta * (je.y - 1)) * pitch + kcol0;
+      const size_t de = (size_t)s_eta * pitch;
+#pragma unroll
+      for (int i = 0; i < kMaxG; ++i) {
+        const int g = gS + i;
+        if (g >= mS && g <= mE && g <= gE) {
+          const Float kint = f01.x * __ldg(k0 + i) + f01.y * __ldg(k0 + de + i) +
+                             f23.x * __ldg(k1 + i) + f23.y * __ldg(k1 + de + i);              // :757-760
+          acc[i] = acc[i] + scaling * kint;                                                   // :493
+        }
+      }
+      continue;
+    }
     const Float* k0 = m.kminor + (jtemp - 1) + s_eta * (je.x - 1) + (long long)s_k * kcol0;
     const Float* k1 = m.kminor + jtemp + s_eta * (je.y - 1) + (long long)s_k * kcol0;
 #pragma unroll
@@ -184,7 +202,7 @@ __device__ __forceinline__ void minor_contrib(const MinorTables& m, const int it
   }
 }
 
-template <int NT, int NE, int NP1>
+template <int NT, int NE, int NP1, bool GF = false>
 __global__ void __launch_bounds__(kCellThreads, 6) tau_absorption_kernel(const TauAbsParams p) {
   const size_t ncl = (size_t)p.ncol * p.nlay;
   const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -206,28 +224,48 @@ __global__ void __launch_bounds__(kCellThreads, 6) tau_absorption_kernel(const T
   for (int gS = bS; gS <= bE; gS += kMaxG) {
     const int gE = min(bE, gS + kMaxG - 1);
     // k(jtemp, jeta1, jpress-1, gS) and k(jtemp+1, jeta2, jpress-1, gS): everything else is an immediate
-    const Float* k0 = p.kmajor + (jtemp - 1) + s_eta * (je.x - 1) + s_p * (jpress - 2) + (long long)s_g * (gS - 1);
-    const Float* k1 = p.kmajor + jtemp + s_eta * (je.y - 1) + s_p * (jpress - 2) + (long long)s_g * (gS - 1);
     Float* tau_c = p.tau + c + ncl * (size_t)(gS - 1);
     Float acc[kMaxG];
+    if (GF) {
+      // g-point-fastest copy: row = jt + ntemp*(je + neta*jp); the chunk's g-points are consecutive addresses of a
+      // row, so neighbouring g-points share sectors and neighbouring columns share lines
+      const size_t gp = (size_t)p.gp, de = (size_t)s_eta * gp, dp = (size_t)s_p * gp;
+      const Float* k0 = p.kmajor + (size_t)((jtemp - 1) + s_eta * (je.x - 1) + s_p * (jpress - 2)) * gp + (gS - 1);
+      const Float* k1 = p.kmajor + (size_t)(jtemp + s_eta * (je.y - 1) + s_p * (jpress - 2)) * gp + (gS - 1);
 #pragma unroll
-    for (int i = 0; i < kMaxG; ++i) {
-      if (gS + i <= gE) {
-        const int go = s_g * i;
-        // interpolate3D_byflav :791-801, same association
-        const Float major =
-            cm.x * (f0.x * __ldg(k0 + go) + f0.y * __ldg(k0 + go + s_eta) +
-                    f1.x * __ldg(k0 + go + s_p) + f1.y * __ldg(k0 + go + s_p + s_eta)) +
-            cm.y * (f2.x * __ldg(k1 + go) + f2.y * __ldg(k1 + go + s_eta) +
-                    f3.x * __ldg(k1 + go + s_p) + f3.y * __ldg(k1 + go + s_p + s_eta));
-        const Float t0 = p.accumulate ? tau_c[ncl * i] : (Float)0;
-        acc[i] = t0 + major;                                                                 // :391
-      } else {
-        acc[i] = 0;
+      for (int i = 0; i < kMaxG; ++i) {
+        if (gS + i <= gE) {
+          const Float major =  // interpolate3D_byflav :791-801, same association
+              cm.x * (f0.x * __ldg(k0 + i) + f0.y * __ldg(k0 + de + i) + f1.x * __ldg(k0 + dp + i) + f1.y * __ldg(k0 + dp + de + i)) +
+              cm.y * (f2.x * __ldg(k1 + i) + f2.y * __ldg(k1 + de + i) + f3.x * __ldg(k1 + dp + i) + f3.y * __ldg(k1 + dp + de + i));
+          const Float t0 = p.accumulate ? tau_c[ncl * i] : (Float)0;
+          acc[i] = t0 + major;                                                               // :391
+        } else {
+          acc[i] = 0;
+        }
+      }
+    } else {
+      const Float* k0 = p.kmajor + (jtemp - 1) + s_eta * (je.x - 1) + s_p * (jpress - 2) + (long long)s_g * (gS - 1);
+      const Float* k1 = p.kmajor + jtemp + s_eta * (je.y - 1) + s_p * (jpress - 2) + (long long)s_g * (gS - 1);
+#pragma unroll
+      for (int i = 0; i < kMaxG; ++i) {
+        if (gS + i <= gE) {
+          const int go = s_g * i;
+          // interpolate3D_byflav :791-801, same association
+          const Float major =
+              cm.x * (f0.x * __ldg(k0 + go) + f0.y * __ldg(k0 + go + s_eta) +
+                      f1.x * __ldg(k0 + go + s_p) + f1.y * __ldg(k0 + go + s_p + s_eta)) +
+              cm.y * (f2.x * __ldg(k1 + go) + f2.y * __ldg(k1 + go + s_eta) +
+                      f3.x * __ldg(k1 + go + s_p) + f3.y * __ldg(k1 + go + s_p + s_eta));
+          const Float t0 = p.accumulate ? tau_c[ncl * i] : (Float)0;
+          acc[i] = t0 + major;                                                                 // :391
+        } else {
+          acc[i] = 0;
+        }
       }
     }
-    if (tropo) minor_contrib(p.lower, 0, p, td, c, ncl, ibnd, gS, gE, acc);
-    else       minor_contrib(p.upper, 1, p, td, c, ncl, ibnd, gS, gE, acc);
+    if (tropo) minor_contrib<NT, NE, NP1, GF>(p.lower, 0, p, td, c, ncl, ibnd, gS, gE, acc);
+    else       minor_contrib<NT, NE, NP1, GF>(p.upper, 1, p, td, c, ncl, ibnd, gS, gE, acc);
 #pragma unroll
     for (int i = 0; i < kMaxG; ++i)
       if (gS + i <= gE) tau_c[ncl * i] = acc[i];
@@ -463,8 +501,18 @@ void tau_absorption_impl(int ncol, int nlay, int nbnd, int ngpt, int ngas, int n
   p.col_gas = a_cg; p.jeta = a_je; p.jtemp = a_jt; p.jpress = a_jp; p.tau = a_tau;
   p.accumulate = accumulate ? 1 : 0;
   dim3 grid(ceil_div((long long)ncl, kCellThreads), nbnd);
+  // g-point-fastest table copies when the caller allows caching them (device-resident tables only: a staged host
+  // table gets a fresh device address on every call)
+  const Float *kmT = nullptr, *klT = nullptr, *kuT = nullptr;
+  p.gp = p.pitch_lower = p.pitch_upper = 0;
+  const bool gf = !a_km.staged() && !a_kl.staged() && !a_ku.staged() &&
+                  tables_gfast_abi(a_km, a_kl, a_ku, ntemp, neta, npres, ngpt, nminorklower, nminorkupper, &kmT, &klT, &kuT,
+                                   &p.gp, &p.pitch_lower, &p.pitch_upper);
   KernelTimer timer("tau_absorption");
-  if (ntemp == 14 && neta == 9 && npres == 59) tau_absorption_kernel<14, 9, 60><<<grid, kCellThreads, 0, stream()>>>(p);
+  if (gf) {
+    p.kmajor = kmT; p.lower.kminor = klT; p.upper.kminor = kuT;
+    tau_absorption_kernel<0, 0, 0, true><<<grid, kCellThreads, 0, stream()>>>(p);
+  } else if (ntemp == 14 && neta == 9 && npres == 59) tau_absorption_kernel<14, 9, 60><<<grid, kCellThreads, 0, stream()>>>(p);
   else tau_absorption_kernel<0, 0, 0><<<grid, kCellThreads, 0, stream()>>>(p);
   RB_LAUNCH_CHECK();
   dev_free(ranges);

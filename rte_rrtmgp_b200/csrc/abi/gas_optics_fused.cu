@@ -248,6 +248,53 @@ TablesT tables_gfast(const rrtmgpb_gas_tables& t) {
   return e.tt;
 }
 
+// ---- the same g-point-fastest copies for the kernel-by-kernel ABI entry points (gas_optics_abi.cu) ----
+// Only kmajor / kminor_* are needed there (the interpolation weights arrive as arguments).  Keyed by the kmajor
+// pointer like the fused path's cache, so it is only valid for callers that keep a table immutable while its
+// allocation lives: off unless rrtmgpb_abi_table_cache(1) was called (the C++ frontend mirror does, its tables are
+// released through rrtmgpb_mem_free which drops the copies).
+struct AbiCacheEntry {
+  TablesT tt;
+  std::vector<void*> owned;
+  int ntemp, neta, npres, ngpt, nkl, nku;
+};
+std::map<const void*, AbiCacheEntry> g_abi_cache;
+thread_local int g_abi_cache_on = 0;
+}  // namespace
+
+namespace rrtmgpb {
+bool tables_gfast_abi(const Float* kmajor, const Float* kminor_lower, const Float* kminor_upper, int ntemp, int neta,
+                      int npres, int ngpt, int nkl, int nku, const Float** kmajorT, const Float** kminorT_lower,
+                      const Float** kminorT_upper, int* gp, int* pitch_lower, int* pitch_upper) {
+  if (!g_abi_cache_on) return false;
+  std::lock_guard<std::mutex> lock(g_tc_mutex);
+  auto it = g_abi_cache.find(kmajor);
+  if (it != g_abi_cache.end()) {
+    const AbiCacheEntry& e = it->second;
+    if (!(e.ntemp == ntemp && e.neta == neta && e.npres == npres && e.ngpt == ngpt && e.nkl == nkl && e.nku == nku)) {
+      for (void* q : e.owned) dev_free(q);
+      g_abi_cache.erase(it);
+      it = g_abi_cache.end();
+    }
+  }
+  if (it == g_abi_cache.end()) {
+    AbiCacheEntry e;
+    e.ntemp = ntemp; e.neta = neta; e.npres = npres; e.ngpt = ngpt; e.nkl = nkl; e.nku = nku;
+    const int tn = ntemp * neta;
+    e.tt.gp = (ngpt + 1) & ~1; e.tt.nkl = (nkl + 1) & ~1; e.tt.nku = (nku + 1) & ~1;
+    e.tt.kmajor = transposed(kmajor, 1, tn * (npres + 1), ngpt, e.tt.gp, e.owned);
+    e.tt.kminor_lower = transposed(kminor_lower, 1, tn, nkl, e.tt.nkl, e.owned);
+    e.tt.kminor_upper = transposed(kminor_upper, 1, tn, nku, e.tt.nku, e.owned);
+    it = g_abi_cache.emplace(kmajor, e).first;
+  }
+  const TablesT& tt = it->second.tt;
+  *kmajorT = tt.kmajor; *kminorT_lower = tt.kminor_lower; *kminorT_upper = tt.kminor_upper;
+  *gp = tt.gp; *pitch_lower = tt.nkl; *pitch_upper = tt.nku;
+  return tt.kmajor != nullptr;
+}
+}  // namespace rrtmgpb
+
+namespace {
 }  // namespace
 
 namespace rrtmgpb {
@@ -259,10 +306,19 @@ void table_cache_release(const void* key) {
   for (void* q : it->second.owned) dev_free(q);
   g_table_cache.erase(it);
 }
+void table_cache_release_abi(const void* key) {
+  std::lock_guard<std::mutex> lock(g_tc_mutex);
+  auto it = g_abi_cache.find(key);
+  if (it == g_abi_cache.end()) return;
+  for (void* q : it->second.owned) dev_free(q);
+  g_abi_cache.erase(it);
+}
 void fused_set_constants(double grav, double m_dry) { g_grav = grav; g_m_dry = m_dry; }
 }
 
 extern "C" {
+
+void rrtmgpb_abi_table_cache(int on) { g_abi_cache_on = on ? 1 : 0; }
 
 /* kept so that programs linked against earlier builds still resolve it: table staging is no longer selectable */
 void rrtmgpb_set_tma_staging(int on) { (void)on; }

@@ -60,6 +60,12 @@ struct OpName {
 
 void fused_set_constants(double grav, double m_dry);  // gas_optics_fused.cu
 void table_cache_release(const void* key);            // gas_optics_fused.cu: drops the g-fastest copies keyed by a table
+void table_cache_release_abi(const void* key);
+// g-point-fastest copies of kmajor / kminor_* for the kernel-by-kernel ABI entry points; false: not available
+// (cache switched off, see rrtmgpb_abi_table_cache)
+bool tables_gfast_abi(const Float* kmajor, const Float* kminor_lower, const Float* kminor_upper, int ntemp, int neta,
+                      int npres, int ngpt, int nkl, int nku, const Float** kmajorT, const Float** kminorT_lower,
+                      const Float** kminorT_upper, int* gp, int* pitch_lower, int* pitch_upper);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -548,11 +548,15 @@ static int compute_gas_taus(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, 
                        &k.press_ref_trop_log, go->vmr_ref, play, tlay, s.col_gas, s.jtemp, s.fmajor, s.fminor,
                        s.col_mix, s.tropo, s.jeta, s.jpress);
   auto tau_abs = [&](Float* tau) {  // :637-665 / :679-706 (zero_array + accumulate == assign)
+    // this frontend's tables are immutable and released through rrtmgpb_mem_free: the kernel may keep
+    // g-point-fastest copies of them for the duration of this call's lookup (scoped switch, thread-local)
+    rrtmgpb_abi_table_cache(1);
     rrtmgpb_compute_tau_absorption_assign(
         ncol, nlay, nband, ngpt, ngas, nflav, k.neta, k.npres, k.ntemp, k.nminorlower, k.nminorklower, k.nminorupper,
         k.nminorkupper, k.idx_h2o, go->gpoint_flavor, go->band_lims_gpt, go->kmajor, go->kminor_lower, go->kminor_upper,
         go->mlg_l, go->mlg_u, go->sd_l, go->sd_u, go->sc_l, go->sc_u, go->im_l, go->im_u, go->is_l, go->is_u, go->ks_l,
         go->ks_u, s.tropo, s.col_mix, s.fmajor, s.fminor, play, tlay, s.col_gas, s.jeta, s.jtemp, s.jpress, tau);
+    rrtmgpb_abi_table_cache(0);
   };
   if (go->krayl) {  // :634-677
     Scratch<Float> tau_rayleigh(ncl * ngpt);

@@ -75,6 +75,7 @@ const char* rrtmgpb_backend_name(void) { return "cuda-sm_100a"; }
 void* rrtmgpb_mem_alloc(size_t bytes) { return dev_alloc(bytes); }
 void rrtmgpb_mem_free(void* p) {
   table_cache_release(p);  // no-op unless p is a k-distribution table with transposed copies
+  table_cache_release_abi(p);
   dev_free(p);
 }
 void rrtmgpb_mem_to_backend(void* d, const void* s, size_t n) {
