@@ -155,6 +155,18 @@ void rrtmgpb_heating_rate(int ncol, int nlay, const Float* flux_up, const Float*
 void rrtmgpb_heating_rate_solar_varmu0(int ncol, int nlay, const Float* flux_up, const Float* flux_dn,
                                        const Float* flux_dir, const Float* p_lev, const Float* mu0, Float* heating_rate);
 
+/* ---------------- simple spectral model gas optics ---------------- */
+/* The kernels of the reference's second, data-file-free gas-optics provider (ssm/mo_optics_ssm_kernels.F90:29,83;
+ * bind(C) names as there; by-reference convention).  absorption_coeffs(ngas,nnu), play(ncol,nlay),
+ * layer_mass(ngas,ncol,nlay) -> tau(ncol,nlay,nnu), pressure broadening play/pref when pref > 0;
+ * vmr(ngas,ncol,nlay), plev(ncol,nlay+1), mol_weights(ngas) -> layer_mass(ngas,ncol,nlay).  Its Planck sources use
+ * rte_compute_Planck_source_1D/_2D of rte_kernels.h. */
+void ssm_compute_tau_absorption(const int* ncol, const int* nlay, const int* nnu, const int* ngas,
+                                const Float* absorption_coeffs, const Float* play, const Float* pref,
+                                const Float* layer_mass, Float* tau);
+void ssm_compute_layer_mass(const int* ncol, const int* nlay, const int* ngas, const Float* vmr, const Float* plev,
+                            const Float* mol_weights, const Float* m_dry, Float* layer_mass);
+
 /* ---------------- fused variants used by the device-resident frontend ---------------- */
 /* As rrtmgp_compute_tau_absorption but ASSIGNS tau instead of accumulating into a pre-zeroed array:
  * saves the zero_array_3D plane write and the plane read (mo_gas_optics_rrtmgp.F90:637-665,679-706). */

@@ -209,3 +209,26 @@ void rrtmgpb_heating_rate_solar_varmu0(int ncol, int nlay, const Float* flux_up,
     }
   }
 }
+
+/* ---- ssm/mo_optics_ssm_kernels.F90 ---- */
+/* compute_tau :29-81 */
+void ssm_compute_tau_absorption(const int* ncol, const int* nlay, const int* nnu, const int* ngas,
+                                const Float* absorption_coeffs, const Float* play, const Float* pref,
+                                const Float* layer_mass, Float* tau) {
+  const size_t ncl = (size_t)*ncol * *nlay;
+  for (int inu = 0; inu < *nnu; ++inu)
+    for (size_t c = 0; c < ncl; ++c) {
+      Float s = 0;
+      for (int ig = 0; ig < *ngas; ++ig) s = s + layer_mass[ig + (size_t)*ngas * c] * absorption_coeffs[ig + (size_t)*ngas * inu];
+      tau[c + ncl * inu] = (*pref > (Float)0) ? s * play[c] / *pref : s;
+    }
+}
+/* compute_layer_mass :83-106 */
+void ssm_compute_layer_mass(const int* ncol, const int* nlay, const int* ngas, const Float* vmr, const Float* plev,
+                            const Float* mol_weights, const Float* m_dry, Float* layer_mass) {
+  const size_t nc = (size_t)*ncol, ncl = nc * *nlay;
+  for (size_t c = 0; c < ncl; ++c)
+    for (int ig = 0; ig < *ngas; ++ig)
+      layer_mass[ig + (size_t)*ngas * c] = vmr[ig + (size_t)*ngas * c] * (mol_weights[ig] / *m_dry) *
+                                           fabs(plev[c + nc] - plev[c]) / (Float)g_grav;
+}

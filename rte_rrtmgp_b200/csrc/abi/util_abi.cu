@@ -87,6 +87,55 @@ void rte_sum_broadband(const int* ncol, const int* nlev, const int* ngpt, const 
   });
 }
 
+// ---------------- simple spectral model gas optics (ssm/mo_optics_ssm_kernels.F90:29-108) ----------------
+// compute_tau :29-81: tau(icol,ilay,inu) = sum_igas layer_mass(igas,icol,ilay) * absorption_coeffs(igas,inu)
+// [* play/pref when pref > 0].  Thread = cell looping over nu: the cell's ngas masses stay in registers (ngas <= 8;
+// more gases re-read them), each tau plane element written once, coalesced.
+void ssm_compute_tau_absorption(const int* ncol_, const int* nlay_, const int* nnu_, const int* ngas_,
+                                const Float* absorption_coeffs, const Float* play, const Float* pref_,
+                                const Float* layer_mass, Float* tau) {
+  OpName op_name__(__func__);
+  const int nnu = *nnu_, ngas = *ngas_;
+  const size_t ncl = (size_t)*ncol_ * *nlay_;
+  const Float pref = *pref_;
+  DevArg<Float> a_k(absorption_coeffs, (size_t)ngas * nnu, Dir::In), a_p(play, ncl, Dir::In),
+      a_m(layer_mass, ncl * ngas, Dir::In), a_t(tau, ncl * nnu, Dir::Out);
+  const Float *k = a_k, *pl = a_p, *lm = a_m; Float* t = a_t;
+  launch_elementwise(ncl, [=] __device__(size_t c) {
+    constexpr int kMaxReg = 8;
+    Float m[kMaxReg];
+#pragma unroll
+    for (int ig = 0; ig < kMaxReg; ++ig) m[ig] = ig < ngas ? lm[ig + (size_t)ngas * c] : (Float)0;
+    const Float scale = pref > (Float)0 ? pl[c] : (Float)1;
+    for (int inu = 0; inu < nnu; ++inu) {
+      const Float* kk = k + (size_t)ngas * inu;
+      Float s = 0;  // sum() of the array constructor: left to right from zero
+#pragma unroll
+      for (int ig = 0; ig < kMaxReg; ++ig)
+        if (ig < ngas) s = s + m[ig] * __ldg(kk + ig);
+      for (int ig = kMaxReg; ig < ngas; ++ig) s = s + lm[ig + (size_t)ngas * c] * __ldg(kk + ig);
+      t[c + ncl * inu] = pref > (Float)0 ? s * scale / pref : s;   // :58-61, :71-72
+    }
+  });
+}
+
+// compute_layer_mass :83-106: layer_mass(igas,icol,ilay) = vmr * (mol_weights(igas)/m_dry) * |dp| / grav
+void ssm_compute_layer_mass(const int* ncol_, const int* nlay_, const int* ngas_, const Float* vmr, const Float* plev,
+                            const Float* mol_weights, const Float* m_dry_, Float* layer_mass) {
+  OpName op_name__(__func__);
+  const int ncol = *ncol_, ngas = *ngas_;
+  const size_t ncl = (size_t)ncol * *nlay_;
+  const Float m_dry = *m_dry_, grav = (Float)g_const.grav;
+  DevArg<Float> a_v(vmr, ncl * ngas, Dir::In), a_p(plev, ncl + ncol, Dir::In), a_w(mol_weights, ngas, Dir::In),
+      a_o(layer_mass, ncl * ngas, Dir::Out);
+  const Float *v = a_v, *pp = a_p, *w = a_w; Float* o = a_o;
+  launch_elementwise(ncl * ngas, [=] __device__(size_t i) {
+    const int ig = (int)(i % ngas);
+    const size_t c = i / ngas;
+    o[i] = v[i] * (w[ig] / m_dry) * fabs(pp[c + ncol] - pp[c]) / grav;
+  });
+}
+
 // ---------------- by-band reductions (rte/extensions/mo_fluxes_byband.F90:159-218) ----------------
 // One thread per (col,lev,band); sequential sum over the band's g-points in the reference's order.
 void rte_sum_byband(const int* ncol, const int* nlev, const int* ngpt, const int* nbnd, const int* band_lims,
