@@ -655,7 +655,8 @@ void rte_lw_solver_noscat(const int* ncol_, const int* nlay_, const int* ngpt_, 
   {                                                                                                         \
     if (use_tma && reg_minb() == 2) {                                                                       \
       const size_t smem = lw_noscat_reg_tma_smem(nlay);                                                     \
-      auto kern = lw_noscat_reg_kernel<CLV, BBV, JACV, 2, true>;                                            \
+      auto kern = nlay == 8 * CLV ? lw_noscat_reg_kernel<CLV, BBV, JACV, 2, true, true>                     \
+                                  : lw_noscat_reg_kernel<CLV, BBV, JACV, 2, true, false>;                   \
       RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
       kern<<<grid, kRegThreads, smem, stream()>>>(q, maps);                                                 \
     } else {                                                                                                \
@@ -729,11 +730,11 @@ void rte_lw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
 #define LW2S(CLV)                                                                                          \
   if (use_tma) {                                                                                           \
     const size_t smem = lw_2stream_reg_tma_smem(nlay);                                                     \
-    auto kern = lw_2stream_reg_kernel<CLV, true>;                                                          \
+    auto kern = nlay == 8 * CLV ? lw_2stream_reg_kernel<CLV, true, true> : lw_2stream_reg_kernel<CLV, true, false>; \
     RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
     kern<<<grid, kRegThreads, smem, stream()>>>(q, maps);                                                  \
   } else {                                                                                                 \
-    lw_2stream_reg_kernel<CLV, false><<<grid, kRegThreads, 0, stream()>>>(q, maps);                        \
+    lw_2stream_reg_kernel<CLV, false, false><<<grid, kRegThreads, 0, stream()>>>(q, maps);                        \
   }
       // the chunk length fixes the association of the chunk-level scan: it must not depend on use_tma (see
       // rte_lw_solver_noscat); CL = 8 conflicts on the TMA tiles, so nlay <= 64 runs CL = 9 as well
@@ -810,7 +811,9 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
     const bool sacc = BBV && reg_sacc();                                                                    \
     if (use_tma && !lean) {                                                                                 \
       const size_t smem = sacc ? sw_reg_tma_smem<CLV, true>(nlay) : sw_reg_tma_smem<CLV, false>(nlay);      \
-      auto kern = sacc ? sw_2stream_reg_kernel<CLV, BBV, 2, BBV, true> : sw_2stream_reg_kernel<CLV, BBV, 2, false, true>; \
+      auto kern = sacc ? sw_2stream_reg_kernel<CLV, BBV, 2, BBV, true>                                      \
+                       : (nlay == 8 * CLV ? sw_2stream_reg_kernel<CLV, BBV, 2, false, true, true>           \
+                                          : sw_2stream_reg_kernel<CLV, BBV, 2, false, true, false>);        \
       RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
       kern<<<grid, kRegThreads, smem, stream()>>>(q, maps);                                                 \
     } else {                                                                                                \

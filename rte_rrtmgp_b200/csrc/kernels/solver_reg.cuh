@@ -120,7 +120,8 @@ __host__ __device__ inline size_t lw_noscat_reg_tma_smem(int nlay) {
   return 2 * (2 * tile_bytes(nlay) + tile_bytes(nlay + 1)) + (size_t)(2 * 5) * kRegThreads * sizeof(Float) + 2 * sizeof(uint64_t);
 }
 
-template <int CL, bool BB, bool JAC, int MINB = 3, bool TMA = false>
+// FULL: nlay == 8*CL, every lane's cells are real layers - the padding selects and tests fold away at compile time.
+template <int CL, bool BB, bool JAC, int MINB = 3, bool TMA = false, bool FULL = false>
 __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const LwNoscatRegParams p,
                                                                            const __grid_constant__ LwTmaMaps tm) {
   // no static shared memory: the swizzled TMA tiles need the dynamic window to start 1024-byte aligned
@@ -231,13 +232,13 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
                                : p.Ds[(size_t)col + ncol * ((size_t)g + (size_t)p.ngpt * imu)];
       // ---------------- phase A: CL cells per lane, in registers ----------------
       Float tr[CL], sd[CL], su[CL];
-      Float Btop = TMA ? *tile_at(tile_lev, o.lev(min(k0, nlay)), cw) : *RB_SLOT(sm, NS, s, 2 * CL);
+      Float Btop = TMA ? *tile_at(tile_lev, o.lev(FULL ? k0 : min(k0, nlay)), cw) : *RB_SLOT(sm, NS, s, 2 * CL);
 #pragma unroll
       for (int i = 0; i < CL; ++i) {
-        const Float Bbot = TMA ? *tile_at(tile_lev, o.lev(min(k0 + i + 1, nlay)), cw) : *RB_SLOT(sm, NS, s, 2 * CL + i + 1);
+        const Float Bbot = TMA ? *tile_at(tile_lev, o.lev(FULL ? k0 + i + 1 : min(k0 + i + 1, nlay)), cw) : *RB_SLOT(sm, NS, s, 2 * CL + i + 1);
         {  // straight-line (see the SW kernel): padding cells become pass-through cells by selects
-          const bool live = k0 + i < nlay;
-          const Float* e_lay = TMA ? tile_at(tile_tau, o.lay(min(k0 + i, nlay - 1)), cw) : nullptr;
+          const bool live = FULL || k0 + i < nlay;
+          const Float* e_lay = TMA ? tile_at(tile_tau, o.lay(FULL ? k0 + i : min(k0 + i, nlay - 1)), cw) : nullptr;
           const Float tau_loc = (TMA ? e_lay[0] : *RB_SLOT(sm, NS, s, i)) * D;     // :181
           const Float t = rb_exp(-tau_loc);                                           // :182
           // :652-656, both branches evaluated (the divisor is clamped where the series is selected anyway)
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
       }
       // g-point flux of one level (only when spectrally resolved output is requested)
       auto store = [&](Float* gflux, int klev, Float I) {
-        if (klev > nlay || !col_ok) return;
+        if ((!FULL && klev > nlay) || !col_ok) return;
         Float* q = gflux + (size_t)col + ncol * o.lev(klev);
         *q = (imu == 0) ? piw * I : *q + piw * I;                                  // :223-224, :356-357
       };
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
 #pragma unroll
         for (int i = CL - 1; i >= 0; --i) {
           // the incoming value sits at the level below layer k0+i: record it, then cross the layer
-          if (k0 + i < nlay) {
+          if (FULL || k0 + i < nlay) {
             if (BB) acc_up[BB ? i : 0] += w * Iu; else store(fup, k0 + i + 1, Iu);
             if (JAC) acc_jac[JAC ? i : 0] += w * Ij;
           }
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
       const int klev = k0 + i + 1;
-      if (klev <= nlay) {
+      if (FULL || klev <= nlay) {
         const size_t o2 = (size_t)col + ncol * o.lev(klev);
         if (BB) { p.bb_up[o2] = pi * acc_up[BB ? i : 0]; p.bb_dn[o2] = pi * acc_dn[BB ? i : 0]; }
         if (JAC) p.flux_upJac[o2] = pi * acc_jac[JAC ? i : 0];
@@ -434,7 +435,8 @@ __host__ __device__ inline size_t sw_reg_tma_smem(int nlay) {
   return 2 * 3 * tile_bytes(nlay) + (size_t)(2 * 4 + CL + (LEAN ? 3 * CL : 0)) * kRegThreads * sizeof(Float) + 2 * sizeof(uint64_t);
 }
 
-template <int CL, bool BB, int MINB = 3, bool LEAN = false, bool TMA = false>
+// FULL: nlay == 8*CL, every lane's cells are real layers - the padding selects and tests fold away at compile time.
+template <int CL, bool BB, int MINB = 3, bool LEAN = false, bool TMA = false, bool FULL = false>
 __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const SwRegParams p,
                                                                             const __grid_constant__ SwTmaMaps tm) {
   static_assert(!LEAN || BB, "LEAN is a broadband-only variant");
@@ -556,10 +558,10 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
     // interleave the CL independent cells of a lane.
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
-      const bool live = k0 + i < nlay;
+      const bool live = FULL || k0 + i < nlay;
       Float tau_s, w0_s, g_s;
       if (TMA) {
-        const Float* e = tile_at(tile_s, o.lay(min(k0 + i, nlay - 1)), cw);
+        const Float* e = tile_at(tile_s, o.lay(FULL ? k0 + i : min(k0 + i, nlay - 1)), cw);
         tau_s = e[0]; w0_s = e[tile_elems]; g_s = e[2 * tile_elems];
       } else {
         tau_s = *RB_SLOT(sm, NS, s, i); w0_s = *RB_SLOT(sm, NS, s, CL + i); g_s = *RB_SLOT(sm, NS, s, 2 * CL + i);
@@ -629,7 +631,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
         dir = A5[i] * dir;
         A3[i] = s_up;
         A4[i] = s_dn;
-        if (k0 + i < nlay) {
+        if (FULL || k0 + i < nlay) {
           if (BB) { acc_add(2, i, dir); acc_add(1, i, dir); }  // :604, direct part of :603
           else if (col_ok) gdir[(size_t)col + ncol * o.lev(k0 + i + 1)] = dir;
         }
@@ -647,7 +649,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
       }
     };
     auto lev = [&](int i, Float fup, Float fdn) {
-      if (k0 + i >= nlay) return;
+      if (!FULL && k0 + i >= nlay) return;
       if (BB) { acc_add(0, i, fup); acc_add(1, i, fdn); }
       else if (col_ok) {
         const size_t q = (size_t)col + ncol * o.lev(k0 + i + 1);
@@ -661,7 +663,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
       const int klev = k0 + i + 1;
-      if (klev <= nlay) {
+      if (FULL || klev <= nlay) {
         const size_t o2 = (size_t)col + ncol * o.lev(klev);
         if (LEAN) {
           p.bb_up[o2] = sm_acc[i * kRegThreads]; p.bb_dn[o2] = sm_acc[(CL + i) * kRegThreads];
@@ -694,7 +696,7 @@ __host__ __device__ inline size_t lw_2stream_reg_tma_smem(int nlay) {
   return 2 * (4 * tile_bytes(nlay) + tile_bytes(nlay + 1)) + 2 * sizeof(uint64_t);
 }
 
-template <int CL, bool TMA = false>
+template <int CL, bool TMA = false, bool FULL = false>
 __global__ void __launch_bounds__(kRegThreads, TMA ? 2 : 3) lw_2stream_reg_kernel(const Lw2sRegParams p,
                                                                                   const __grid_constant__ Lw2sTmaMaps tm) {
   // no static shared memory: the swizzled TMA tiles need the dynamic window to start 1024-byte aligned
@@ -752,14 +754,14 @@ __global__ void __launch_bounds__(kRegThreads, TMA ? 2 : 3) lw_2stream_reg_kerne
     Float R[CL], T[CL], SU[CL], SD[CL], Blev[CL + 1];
 #pragma unroll
     for (int i = 0; i <= CL; ++i) {
-      const int kk = min(k0 + i, nlay);
+      const int kk = FULL ? k0 + i : min(k0 + i, nlay);
       Blev[i] = TMA ? *tile_at(tile_lev, o.lev(kk), cw) : p.lev_source[col + ncol * o.lev(kk) + nclp * gsrc];
     }
     // straight-line per cell (see sw_2stream_reg_kernel): padding cells become pass-through cells by selects
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
-      const bool live = k0 + i < nlay;
-      const int lay = o.lay(min(k0 + i, nlay - 1));
+      const bool live = FULL || k0 + i < nlay;
+      const int lay = o.lay(FULL ? k0 + i : min(k0 + i, nlay - 1));
       Float tau, w0, gg;
       if (TMA) {
         const Float* e = tile_at(tile_tau, lay, cw);
@@ -803,7 +805,7 @@ __global__ void __launch_bounds__(kRegThreads, TMA ? 2 : 3) lw_2stream_reg_kerne
       gdn[q] = fdn;
     };
     auto lev = [&](int i, Float fup, Float fdn) {
-      if (k0 + i >= nlay || !col_ok) return;
+      if ((!FULL && k0 + i >= nlay) || !col_ok) return;
       const size_t q = col + ncol * o.lev(k0 + i + 1);
       gup[q] = fup;
       gdn[q] = fdn;
