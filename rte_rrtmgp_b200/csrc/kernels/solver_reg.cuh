@@ -295,10 +295,10 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
 #pragma unroll
         for (int i = CL - 1; i >= 0; --i) {
           // the incoming value sits at the level below layer k0+i: record it, then cross the layer
-          if (FULL || k0 + i < nlay) {
-            if (BB) acc_up[BB ? i : 0] += w * Iu; else store(fup, k0 + i + 1, Iu);
-            if (JAC) acc_jac[JAC ? i : 0] += w * Ij;
-          }
+          // (accumulator slots of padding cells are never written out, so the sums need no guard: branch-free)
+          if (BB) acc_up[BB ? i : 0] += w * Iu;
+          else if (FULL || k0 + i < nlay) store(fup, k0 + i + 1, Iu);
+          if (JAC) acc_jac[JAC ? i : 0] += w * Ij;
           Iu = tr[i] * Iu + su[i];
           if (JAC) Ij = tr[i] * Ij;
         }
@@ -631,10 +631,9 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
         dir = A5[i] * dir;
         A3[i] = s_up;
         A4[i] = s_dn;
-        if (FULL || k0 + i < nlay) {
-          if (BB) { acc_add(2, i, dir); acc_add(1, i, dir); }  // :604, direct part of :603
-          else if (col_ok) gdir[(size_t)col + ncol * o.lev(k0 + i + 1)] = dir;
-        }
+        // (accumulator slots of padding cells are never written out, so the sums need no guard: branch-free)
+        if (BB) { acc_add(2, i, dir); acc_add(1, i, dir); }  // :604, direct part of :603
+        else if ((FULL || k0 + i < nlay) && col_ok) gdir[(size_t)col + ncol * o.lev(k0 + i + 1)] = dir;
         A5[i] = dir;  // direct flux below layer k0+i, for the g-point totals (:606)
       }
     }
@@ -649,9 +648,8 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
       }
     };
     auto lev = [&](int i, Float fup, Float fdn) {
-      if (!FULL && k0 + i >= nlay) return;
       if (BB) { acc_add(0, i, fup); acc_add(1, i, fdn); }
-      else if (col_ok) {
+      else if ((FULL || k0 + i < nlay) && col_ok) {
         const size_t q = (size_t)col + ncol * o.lev(k0 + i + 1);
         gup[q] = fup;
         gdn[q] = fdn + A5[i];                                                 // :606
