@@ -228,6 +228,13 @@ TablesT tables_gfast(const rrtmgpb_gas_tables& t) {
       for (int b = 0; b < t.nbnd; ++b)
         if (i >= bands[b].mfirst[a] && i <= bands[b].mlast[a] && mi.iflav != bands[b].iflav[a]) bands[b].mdiff[a] = 1;
     }
+    for (int b = 0; b < t.nbnd; ++b) {  // regular band: 4*kTG g-points, every contributor covers exactly the band
+      BandInfo& bi = bands[b];
+      bool reg = (bi.bE - bi.bS + 1 == 4 * kTG) && !bi.mdiff[a];
+      for (int i = bi.mfirst[a]; reg && i <= bi.mlast[a]; ++i)
+        reg = minfo[a][i].mS == bi.bS && minfo[a][i].mE == bi.bE;
+      bi.regular[a] = reg ? 1 : 0;
+    }
   }
   // ratio_eta_half = vmr_ref(itropo,igas_1,jt) / vmr_ref(itropo,igas_2,jt), mo_gas_optics_rrtmgp_kernels.F90:127-128
   std::vector<Float> ratio((size_t)2 * t.nflav * t.ntemp);

@@ -47,6 +47,8 @@ struct BandInfo {
   int igas1[2], igas2[2];       // the flavour's two gases, [itropo]                       (:121-122)
   int mfirst[2], mlast[2];      // minor contributors overlapping the band, [itropo] (lower / upper set)
   int mdiff[2];                 // 1: some of them has a flavour other than the band's
+  int regular[2];               // 1: the band has 4*kTG g-points and every contributor covers exactly the band with the
+                                //    band's flavour (all rrtmgp-data bands): the kernel's range tests fold away
 };
 struct MinorInfo {
   int mS, mE;                   // 1-based g-point limits of the contributor
@@ -214,8 +216,9 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
   const int mfirst = tropo ? bi.mfirst[0] : bi.mfirst[1], mlast = tropo ? bi.mlast[0] : bi.mlast[1];
   const Float eps3 = (Float)3.0 * (Float)RB_TINY;  // mo_optical_props_kernels.F90:38
 
-  auto chunk = [&](int gS, int n, auto full_tag) {
+  auto chunk = [&](int gS, int n, auto full_tag, auto reg_tag) {
     constexpr bool FULL = decltype(full_tag)::value;
+    constexpr bool REG = decltype(reg_tag)::value;  // regular band: every contributor covers the whole chunk
     Float acc[NC][kTG];
     // ---- major absorbers: tau = 0 + major (:391 on a zeroed tau); interpolate3D_byflav :791-801 ----
     {
@@ -241,7 +244,7 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
     // ---- minor absorbers touching this chunk (:451-498) ----
     for (int imnr = mfirst; imnr <= mlast; ++imnr) {
       const MinorInfo mi = minfo[imnr];
-      if (mi.mE < gS || mi.mS > gS + n - 1) continue;
+      if (!REG && (mi.mE < gS || mi.mS > gS + n - 1)) continue;
       Float scaling[NC];
 #pragma unroll
       for (int k = 0; k < NC; ++k) {
@@ -267,7 +270,7 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
       for (int k = 0; k < NC; ++k)
 #pragma unroll
         for (int q = 0; q < 4; ++q) am[k][q] = cell[k].w.fmn[q];
-      if (NC == 1 && mi.iflav != iflav) {
+      if (!REG && NC == 1 && mi.iflav != iflav) {
         FlavW wm;
         const size_t c = cell[0].c;
         flavor_weights_g(p, c, ncl, mi.igas1, mi.igas2, tt.aux.ratio + (size_t)(itropo * t.nflav + mi.iflav) * t.ntemp, jtemp,
@@ -281,7 +284,7 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
       const Float* m0 = kminor + (size_t)((jtemp - 1) + s_eta * (jm0 - 1)) * mpitch + kcol0;
       const Float* m1 = kminor + (size_t)(jtemp + s_eta * (jm1 - 1)) * mpitch + kcol0;
       const int iS = mi.mS - gS, iE = min(mi.mE - gS, n - 1);  // chunk positions covered by this contributor
-      const bool whole = FULL && iS <= 0 && iE == kTG - 1;
+      const bool whole = REG || (FULL && iS <= 0 && iE == kTG - 1);
 #pragma unroll
       for (int i = 0; i < kTG; i += VEC) {
         if (whole || (i >= iS && i <= iE)) {  // VEC == 2: intervals start even and have even length (TablesT::vec)
@@ -369,10 +372,14 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
     }
   };
 
-  for (int gS = bi.bS; gS <= bi.bE; gS += kTG) {
-    const int n = min(kTG, bi.bE - gS + 1);
-    if (n == kTG) chunk(gS, n, std::true_type{});
-    else chunk(gS, n, std::false_type{});
+  if (tropo ? bi.regular[0] : bi.regular[1]) {
+    for (int q = 0; q < 4; ++q) chunk(bi.bS + q * kTG, kTG, std::true_type{}, std::true_type{});
+  } else {
+    for (int gS = bi.bS; gS <= bi.bE; gS += kTG) {
+      const int n = min(kTG, bi.bE - gS + 1);
+      if (n == kTG) chunk(gS, n, std::true_type{}, std::false_type{});
+      else chunk(gS, n, std::false_type{}, std::false_type{});
+    }
   }
 }
 
@@ -534,20 +541,25 @@ __global__ void __launch_bounds__(kGThreads, 4) planck_g_kernel(const PlanckFuse
           const int ns = min(kGG, n - sub);
           Float pf[kGG];
           planck_fractions<VEC>(p, tt, w, row0, row1, gS - 1 + sub, ns, pf);
+          auto emit = [&](auto full_tag) {  // full chunk: no per-g-point guards
+            constexpr bool FULLC = decltype(full_tag)::value;
 #pragma unroll
-          for (int i = 0; i < kGG; ++i) {
-            if (i < ns) {
-              // streaming stores: the source planes are next read by the solver, long after they left the caches
-              __stcs(lay_c, pf[i] * B_lay);                                                    // :640
-              __stcs(lev_c, (ilay == 0) ? pf[i] * B_lev : sqrt(pf_prev[sub + i] * pf[i]) * B_lev);   // :695-701
-              lay_c += ncl; lev_c += nclp;
-              if (is_sfc) {
-                q.sfc_src[icol + ncol * (size_t)(gS + sub + i - 1)] = pf[i] * B_sfc;            // :650-653
-                q.sfc_source_Jac[icol + ncol * (size_t)(gS + sub + i - 1)] = pf[i] * (B_sfc1 - B_sfc);
+            for (int i = 0; i < kGG; ++i) {
+              if (FULLC || i < ns) {
+                // streaming stores: the source planes are next read by the solver, long after they left the caches
+                __stcs(lay_c, pf[i] * B_lay);                                                    // :640
+                __stcs(lev_c, (ilay == 0) ? pf[i] * B_lev : sqrt(pf_prev[sub + i] * pf[i]) * B_lev);   // :695-701
+                lay_c += ncl; lev_c += nclp;
+                if (is_sfc) {
+                  q.sfc_src[icol + ncol * (size_t)(gS + sub + i - 1)] = pf[i] * B_sfc;            // :650-653
+                  q.sfc_source_Jac[icol + ncol * (size_t)(gS + sub + i - 1)] = pf[i] * (B_sfc1 - B_sfc);
+                }
+                pf_prev[sub + i] = pf[i];
               }
-              pf_prev[sub + i] = pf[i];
             }
-          }
+          };
+          if (ns == kGG) emit(std::true_type{});
+          else emit(std::false_type{});
         }
       }
     }

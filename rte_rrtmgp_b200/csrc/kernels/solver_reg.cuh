@@ -4,21 +4,23 @@
 //     lane = c*8 + j      c in 0..3  : one of the warp's 4 consecutive columns
 //                         j in 0..7  : a CHUNK of CL consecutive layers, counted from the top
 // so a warp owns 4 (column, g-point) recurrences at a time and every lane owns CL cells of one of them.
-//   prefetch every lane copies the inputs of its CL cells for g-point g+1 from global memory into its own
-//            shared-memory slots with cp.async (LDGSTS) while g-point g is being processed: two stages,
-//            lane-private slots, so completion is a per-thread cp.async.wait_group - no block barrier;
+//   inputs   TMA (kernels/tma.cuh): one thread issues one cp.async.bulk.tensor per input plane - the (16 columns x
+//            nlay) tile of a g-point - into a two-stage, 128B-swizzled shared-memory ring, completion on an
+//            mbarrier; the stage is handed back for g+2 after a __syncthreads() once every warp has read it.
+//            Fallback (odd ncol, single precision): every lane copies the inputs of its CL cells for g+1 into its
+//            own shared-memory slots with cp.async (LDGSTS), lane-private, completion by cp.async.wait_group;
 //   phase A  every lane computes its CL cells (the exp / sqrt / divide-heavy two-stream or Planck-source
-//            algebra) into REGISTERS: CL independent cells per lane give the instruction-level
-//            parallelism that hides the fp64 latencies;
-//   phase B  the layer-serial recurrences (transport / direct beam / adding) run chunk by chunk: the lane
-//            holding chunk j advances the chain through its CL layers out of registers and hands the chain
-//            state (intensity, or (albedo, source), or flux) to the lane of the next chunk with ONE warp
-//            shuffle.  Eight hand-overs per sweep replace the per-layer shared/global traffic of a
-//            thread-per-column design.
+//            algebra) into REGISTERS as STRAIGHT-LINE code (branch-free math from fastmath.cuh, padding cells by
+//            selects): CL independent cells per lane give the instruction-level parallelism that hides the fp64
+//            latencies.  FULL instantiations (nlay == 8*CL) drop the padding selects, clamps and guards;
+//   phase B  the layer-serial recurrences (transport / direct beam / adding) as a chunk-level scan: every lane
+//            composes the CL layers of its chunk into one map, the 8 chunks of a column are chained with 8
+//            hand-overs (one warp shuffle each), and every lane replays its own layers from the incoming state
+//            with the reference's per-layer expressions.
 //   Broadband sums live in registers of the lane that owns the level, accumulated in g-point order (the
 //   reference's order, mo_rte_solver_kernels.F90:216-218,601-604): deterministic, no atomics.
 // Layers beyond nlay (padding of the last chunk) are exact pass-through cells (T = 1, R = 0, no source).
-// Every input plane is read from HBM once (32-byte sectors: 4 consecutive columns x 8 layers per request).
+// Every input plane is read from HBM once (TMA: 128-byte rows of 16 consecutive columns).
 //
 // Numerics follow rte/kernels/mo_rte_solver_kernels.F90 (line numbers cited inline).  Two documented
 // reassociations w.r.t. the reference (results differ by ~1 ulp of the affected term):
