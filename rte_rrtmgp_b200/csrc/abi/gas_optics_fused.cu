@@ -349,9 +349,12 @@ void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, c
   {
     KernelTimer timer(sw ? "gas_tau_fused[sw]" : "gas_tau_fused[lw]");
     const unsigned grid = (unsigned)((long long)ceil_div((long long)ncl, kTauCells * kGThreads) * t->nbnd);
-#define GAS_TAU_LAUNCH(SWV, VECV)                                                                 \
-  if (aer_kind) gas_tau_g_kernel<SWV, VECV, true><<<grid, kGThreads, 0, stream()>>>(p, tt);       \
-  else gas_tau_g_kernel<SWV, VECV, false><<<grid, kGThreads, 0, stream()>>>(p, tt)
+// KIND 1: the common kinds as compile-time constants (LW 1scl += 1scl clouds, SW 2str += 2str clouds, no aerosols)
+#define GAS_TAU_LAUNCH(SWV, VECV)                                                                     \
+  if (aer_kind) gas_tau_g_kernel<SWV, VECV, true, 0><<<grid, kGThreads, 0, stream()>>>(p, tt);        \
+  else if (op_kind == (SWV ? 2 : 1) && cld_kind == (SWV ? 2 : 1))                                     \
+    gas_tau_g_kernel<SWV, VECV, false, 1><<<grid, kGThreads, 0, stream()>>>(p, tt);                   \
+  else gas_tau_g_kernel<SWV, VECV, false, 0><<<grid, kGThreads, 0, stream()>>>(p, tt)
     if (sw) {
       if (tt.vec == 2) { GAS_TAU_LAUNCH(true, 2); } else { GAS_TAU_LAUNCH(true, 1); }
     } else {

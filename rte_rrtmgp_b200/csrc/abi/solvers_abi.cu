@@ -655,8 +655,9 @@ void rte_lw_solver_noscat(const int* ncol_, const int* nlay_, const int* ngpt_, 
   {                                                                                                         \
     if (use_tma && reg_minb() == 2) {                                                                       \
       const size_t smem = lw_noscat_reg_tma_smem(nlay);                                                     \
-      auto kern = nlay == 8 * CLV ? lw_noscat_reg_kernel<CLV, BBV, JACV, 2, true, true>                     \
-                                  : lw_noscat_reg_kernel<CLV, BBV, JACV, 2, true, false>;                   \
+      auto kern = nlay == 8 * CLV ? (nmus == 1 ? lw_noscat_reg_kernel<CLV, BBV, JACV, 2, true, true, true>  \
+                                               : lw_noscat_reg_kernel<CLV, BBV, JACV, 2, true, true, false>) \
+                                  : lw_noscat_reg_kernel<CLV, BBV, JACV, 2, true, false, false>;            \
       RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
       kern<<<grid, kRegThreads, smem, stream()>>>(q, maps);                                                 \
     } else {                                                                                                \

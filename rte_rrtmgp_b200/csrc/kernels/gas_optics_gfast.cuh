@@ -201,7 +201,9 @@ struct TauCell {
 };
 
 // NC cells that share tropo, jtemp and the table rows (row0, row1 => je[0], je[1]) of band `bi`
-template <bool SW, int VEC, int NC, bool AER>
+// KIND: 0 = optical-property kind and cloud kind read at run time; 1 = the common combination as compile-time constants
+// (LW: 1scl tau += 1scl clouds; SW: 2str incremented by 2str clouds), so the epilogue's kind tests fold away.
+template <bool SW, int VEC, int NC, bool AER, int KIND>
 __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const TablesT& tt, const BandInfo& bi, bool tropo,
                                                int jtemp, int row0, int row1, TauCell (&cell)[NC]) {
   const rrtmgpb_gas_tables& t = p.t;
@@ -319,12 +321,14 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
       const size_t o = cell[k].c + goff + ncl * (size_t)i;
       // by-band increments of (to[, ss, gg]) by (ct, cw, cg): mo_optical_props_kernels.F90:366-477; the cloud one
       // first, then (AER instantiations) the aerosol one
-      if (p.op_kind == 1) {
+      const int op_kind = KIND ? (SW ? 2 : 1) : p.op_kind;
+      const int cld_kind = KIND ? (SW ? 2 : 1) : p.cld_kind;
+      if (op_kind == 1) {
         auto inc1 = [&](int kind, Float ct, Float cw) {
           if (kind == 1) to = to + ct;                         // inc_1scalar_by_1scalar_bybnd :379
           else if (kind == 2) to = to + ct * ((Float)1 - cw);  // inc_1scalar_by_2stream_bybnd :398
         };
-        inc1(p.cld_kind, cell[k].ct, cell[k].cw);
+        inc1(cld_kind, cell[k].ct, cell[k].cw);
         if (AER) inc1(p.aer_kind, cell[k].at, cell[k].aw);
         if (cell[k].valid) p.tau[o] = to;
       } else {
@@ -341,7 +345,7 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
             to = tau12;
           }
         };
-        inc2(p.cld_kind, cell[k].ct, cell[k].cw, cell[k].cg);
+        inc2(cld_kind, cell[k].ct, cell[k].cw, cell[k].cg);
         if (AER) inc2(p.aer_kind, cell[k].at, cell[k].aw, cell[k].ag);
         if (cell[k].valid) {
           p.tau[o] = to;
@@ -383,7 +387,7 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
   }
 }
 
-template <bool SW, int VEC, bool AER>
+template <bool SW, int VEC, bool AER, int KIND>
 __global__ void __launch_bounds__(kGThreads, RB_TAU_MINB) gas_tau_g_kernel(const FusedParams p, const TablesT tt) {
   const rrtmgpb_gas_tables& t = p.t;
   const size_t ncl = (size_t)p.ncol * p.nlay;
@@ -416,10 +420,11 @@ __global__ void __launch_bounds__(kGThreads, RB_TAU_MINB) gas_tau_g_kernel(const
     row1[k] = jtemp[k] + s_eta * (ce.w.je[1] - 1) + s_p * (jpress - 2);
     // cloud properties of this (cell, band), if the caller wants them added (mo_optical_props.F90:956-1000)
     ce.ct = 0; ce.cw = 0; ce.cg = 0;
-    if (p.cld_kind) {
+    const int cld_kind = KIND ? (SW ? 2 : 1) : p.cld_kind;
+    if (cld_kind) {
       const size_t cb = c + ncl * (size_t)ibnd;
       ce.ct = p.cld_tau[cb];
-      if (p.cld_kind == 2) { ce.cw = p.cld_ssa[cb]; ce.cg = p.cld_g[cb]; }
+      if (cld_kind == 2) { ce.cw = p.cld_ssa[cb]; ce.cg = p.cld_g[cb]; }
     }
     ce.at = 0; ce.aw = 0; ce.ag = 0;
     if (AER && p.aer_kind) {
@@ -435,13 +440,13 @@ __global__ void __launch_bounds__(kGThreads, RB_TAU_MINB) gas_tau_g_kernel(const
     shared_rows = shared_rows && tropo[k] == tropo[0] && row0[k] == row0[0] && row1[k] == row1[0];
   if (tropo[0] ? bi.mdiff[0] : bi.mdiff[1]) shared_rows = false;
   if (shared_rows) {
-    tau_band_cells<SW, VEC, kTauCells, AER>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell);
+    tau_band_cells<SW, VEC, kTauCells, AER, KIND>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell);
   } else {
 #pragma unroll
     for (int k = 0; k < kTauCells; ++k) {
       if (!cell[k].valid) continue;
       TauCell one[1] = {cell[k]};
-      tau_band_cells<SW, VEC, 1, AER>(p, tt, bi, tropo[k], jtemp[k], row0[k], row1[k], one);
+      tau_band_cells<SW, VEC, 1, AER, KIND>(p, tt, bi, tropo[k], jtemp[k], row0[k], row1[k], one);
     }
   }
 }

@@ -123,7 +123,8 @@ __host__ __device__ inline size_t lw_noscat_reg_tma_smem(int nlay) {
 }
 
 // FULL: nlay == 8*CL, every lane's cells are real layers - the padding selects and tests fold away at compile time.
-template <int CL, bool BB, bool JAC, int MINB = 3, bool TMA = false, bool FULL = false>
+// ONEMU: a single quadrature angle (the default of rte_lw): the loop over angles folds away.
+template <int CL, bool BB, bool JAC, int MINB = 3, bool TMA = false, bool FULL = false, bool ONEMU = false>
 __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const LwNoscatRegParams p,
                                                                            const __grid_constant__ LwTmaMaps tm) {
   // no static shared memory: the swizzled TMA tiles need the dynamic window to start 1024-byte aligned
@@ -227,7 +228,8 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
     const Float sjac = JAC ? *RB_SLOT(sm, NS, s, BC0 + 4) : (Float)0;
     Float* fup = p.flux_up + nclp * g;
     Float* fdn = p.flux_dn + nclp * g;
-    for (int imu = 0; imu < p.nmus; ++imu) {
+    const int nmus = ONEMU ? 1 : p.nmus;
+    for (int imu = 0; imu < nmus; ++imu) {
       const Float w = p.weights[imu];
       const Float piw = pi * w;
       const Float D = (imu == 0) ? *RB_SLOT(sm, NS, s, BC0 + 5)
