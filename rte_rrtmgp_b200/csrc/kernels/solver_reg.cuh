@@ -365,19 +365,28 @@ __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL]
     const Float nf = mf - r * ma, ng = mg - r * mb;
     ma = na; mb = nb; mc = nc; md = t * md; me = ne; mf = nf; mg = ng;
   }
-  Float alb = albedo_sfc, src = src_sfc;  // state entering this lane's chunk from below (:1166-1168 for the last chunk)
+  // State entering this lane's chunk from below (:1166-1168 for the last chunk).  The hand-over carries the pair in
+  // HOMOGENEOUS form (a, s, d) with albedo = a/d, source = s/d: applying a chunk's matrix is then 7 multiply-adds with
+  // no division inside the 8-step serial chain (the reciprocal used to be its longest link); every lane normalises
+  // the state it received once, in parallel with the others.
+  Float alb = albedo_sfc, src = src_sfc;
   {
-    Float alb_o = 0, src_o = 0;
+    Float ha = 0, hs = 0, hd = 0;
+    Float ia = albedo_sfc, is = src_sfc, id = 1;  // incoming state of this lane, homogeneous
     for (int jj = kRegChunks - 1; jj >= 0; --jj) {
-      const Float alb_b = __shfl_down_sync(0xffffffffu, alb_o, 1);
-      const Float src_b = __shfl_down_sync(0xffffffffu, src_o, 1);
+      const Float a_b = __shfl_down_sync(0xffffffffu, ha, 1);
+      const Float s_b = __shfl_down_sync(0xffffffffu, hs, 1);
+      const Float d_b = __shfl_down_sync(0xffffffffu, hd, 1);
       if (j == jj) {
-        if (jj < kRegChunks - 1) { alb = alb_b; src = src_b; }
-        const Float den = rb_rcp(mf * alb + mg);
-        alb_o = (ma * alb + mb) * den;
-        src_o = (mc * alb + md * src + me) * den;
+        if (jj < kRegChunks - 1) { ia = a_b; is = s_b; id = d_b; }
+        ha = ma * ia + mb * id;
+        hs = mc * ia + md * is + me * id;
+        hd = mf * ia + mg * id;
       }
     }
+    const Float inv = rb_rcp(id);  // id = 1 for the last chunk: alb, src are then exactly the surface values
+    alb = ia * inv;
+    src = is * inv;
   }
   // replay with the reference's per-layer expressions, every lane on its own chunk
 #pragma unroll
