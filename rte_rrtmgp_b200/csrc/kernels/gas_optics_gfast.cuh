@@ -117,7 +117,10 @@ __device__ __forceinline__ void flavor_weights_g(const FusedParams& p, size_t c,
   for (int it = 0; it < 2; ++it) {
     const Float ratio_eta_half = it ? rt1 : rt0;
     const Float colmix = cg1 + ratio_eta_half * cg2;
-    const Float eta = (colmix > (Float)2 * (Float)RB_TINY) ? cg1 / colmix : (Float)0.5;
+    // rb_div (branch-free, 0 ulp from IEEE on the 50,000-argument probe of tests/test_fastmath.py): the compiler's
+    // division carries a slow-path branch that splits this prologue into basic blocks.  A last-bit difference could
+    // only move eta across a table node, where the piecewise-linear interpolation is continuous.
+    const Float eta = (colmix > (Float)2 * (Float)RB_TINY) ? rb_div(cg1, colmix) : (Float)0.5;
     const Float loceta = eta * (Float)(t.neta - 1);
     w.je[it] = min((int)loceta + 1, t.neta - 1);
     const Float feta = loceta - trunc(loceta);
