@@ -297,7 +297,9 @@ def run_product(args):
     # every step's inputs cross PCIe and every step's five flux arrays come back, all inside the timed region).
     hin = sky.host_inputs
     pinned = {k: torch.from_numpy(np.ascontiguousarray(v.T)).pin_memory() for k, v in hin.items()}
-    names = ["p_lay", "p_lev", "t_lay", "t_lev", "vmr", "lwp", "iwp", "rel", "dei"]
+    # gas concentrations cross PCIe the way the reference driver holds them (rrtmgp_allsky.F90:195-203): the h2o and
+    # o3 fields; the six well-mixed gases are scalars in gas_concs and are broadcast on the device every step
+    names = ["p_lay", "p_lev", "t_lay", "t_lev", "h2o", "o3", "lwp", "iwp", "rel", "dei"]
     set_a = {k: getattr(sky, k) for k in names}
     set_b = {k: torch.empty_like(v) for k, v in set_a.items()}
     sets = [set_a, set_b]

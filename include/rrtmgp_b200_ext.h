@@ -99,6 +99,10 @@ void rrtmgpb_expand_and_transpose(int ncol, int nband, int ngpt, const int* band
                                   const Float* arr_in, Float* arr_out);
 /* replaces mo_rte_sw.F90:87-93: mu0_bylay(icol,ilay) = mu0(icol) */
 void rrtmgpb_broadcast_by_lay(int ncol, int nlay, const Float* per_col, Float* out);
+/* replaces ty_gas_concs%get_vmr_2d, rte/frontend/gas-optics-template/mo_gas_concentrations.F90:433-504 (called once per
+ * gas by gas_optics, rrtmgp/frontend/mo_gas_optics_rrtmgp.F90:540-545): a concentration stored as (ncol,nlay), (1,nlay)
+ * or (1,1) - conc(nc_conc, nl_conc) - is broadcast into array(ncol,nlay) */
+void rrtmgpb_gas_concs_get_vmr(int ncol, int nlay, int nc_conc, int nl_conc, const Float* conc, Float* array);
 /* replaces the cloud masks mo_cloud_optics_rrtmgp.F90:334-341 */
 void rrtmgpb_cloud_masks(int ncol, int nlay, const Float* clwp, const Float* ciwp, Bool* liqmsk,
                          Bool* icemsk);

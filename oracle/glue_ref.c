@@ -104,6 +104,18 @@ void rrtmgpb_broadcast_by_lay(int ncol, int nlay, const Float* per_col, Float* o
     for (int i = 0; i < ncol; ++i) out[(size_t)i + (size_t)ncol * l] = per_col[i];
 }
 
+/* ty_gas_concs%get_vmr_2d, rte/frontend/gas-optics-template/mo_gas_concentrations.F90:464-501 */
+void rrtmgpb_gas_concs_get_vmr(int ncol, int nlay, int nc_conc, int nl_conc, const Float* conc, Float* array) {
+  for (int l = 0; l < nlay; ++l)
+    for (int i = 0; i < ncol; ++i) {
+      Float v;
+      if (nc_conc > 1) v = conc[(size_t)i + (size_t)ncol * l];  /* stored as 2D */
+      else if (nl_conc > 1) v = conc[l];                        /* stored as 1D */
+      else v = conc[0];                                         /* stored as scalar */
+      array[(size_t)i + (size_t)ncol * l] = v;
+    }
+}
+
 /* mo_cloud_optics_rrtmgp.F90:334-341 */
 void rrtmgpb_cloud_masks(int ncol, int nlay, const Float* clwp, const Float* ciwp, Bool* liqmsk, Bool* icemsk) {
   const size_t ncl = (size_t)ncol * nlay;

@@ -9,8 +9,8 @@ import os
 import numpy as np
 
 from . import synthetic as syn
-from .frontend import (AerosolOptics, CloudOptics, FluxesBroadband, GasOptics, OpticalProps, SourceFuncLW, rte_lw,
-                       rte_lw_bygpoint, rte_sw)
+from .frontend import (AerosolOptics, CloudOptics, FluxesBroadband, GasConcs, GasOptics, OpticalProps, SourceFuncLW,
+                       rte_lw, rte_lw_bygpoint, rte_sw)
 
 
 class AllSky:
@@ -25,14 +25,21 @@ class AllSky:
         self.do_aerosols, self.lw_2stream = do_aerosols, lw_2stream
         prof = profiles if profiles is not None else syn.compute_profiles(300.0, ncol, nlay)
         self.host_inputs = {}
-        vmr = syn.allsky_gas_vmrs(prof)
         put = ctx.put
         self.p_lay, self.p_lev = put(prof["p_lay"]), put(prof["p_lev"])
         self.t_lay, self.t_lev = put(prof["t_lay"]), put(prof["t_lev"])
-        self.vmr = put(vmr)
+        # gas_concs as the reference driver sets it up (rrtmgp_allsky.F90:195-203, 275-276): h2o and o3 are
+        # (ncol,nlay) fields, the well-mixed gases scalars.  gas_optics expands it to vmr(ncol,nlay,ngas) on every
+        # call (mo_gas_optics_rrtmgp.F90:540-545); here the expansion runs once per step, shared by LW and SW.
+        self.h2o, self.o3 = put(prof["q"]), put(prof["o3"])
+        self.gas_concs = GasConcs(ctx, syn.GAS_NAMES)
+        for name, w in syn.ALLSKY_WELL_MIXED.items():
+            self.gas_concs.set_vmr(name, w)
+        self.vmr = ctx.zeros((ncol, nlay, len(syn.GAS_NAMES)))
+        self.update_vmr()
         top_at_1 = bool(prof["p_lay"][0, 0] < prof["p_lay"][0, nlay - 1])
         sfc = nlay if top_at_1 else 0
-        self.host_inputs.update(p_lay=prof["p_lay"], p_lev=prof["p_lev"], t_lay=prof["t_lay"], t_lev=prof["t_lev"], vmr=vmr)
+        self.host_inputs.update(p_lay=prof["p_lay"], p_lev=prof["p_lev"], t_lay=prof["t_lay"], t_lev=prof["t_lev"], h2o=prof["q"], o3=prof["o3"])
         self.lw = self.sw = None
         if kd_lw is not None:
             lw = type("LW", (), {})()
@@ -91,6 +98,12 @@ class AllSky:
             self.aero_mass, self.relhum = put(ae["aero_mass"]), put(ae["relhum"])
             self.host_inputs.update(ae)
 
+    def update_vmr(self):
+        """gas_concs -> vmr(ncol,nlay,ngas): the get_vmr loop of gas_optics (mo_gas_optics_rrtmgp.F90:540-545)."""
+        self.gas_concs.set_vmr("h2o", self.h2o)
+        self.gas_concs.set_vmr("o3", self.o3)
+        self.gas_concs.fill_vmr(syn.GAS_NAMES, self.vmr)
+
     # -- one iteration of the reference loop body, LW branch (rrtmgp_allsky.F90:340-381)
     def step_lw(self):
         lw = self.lw
@@ -143,6 +156,7 @@ class AllSky:
         rte_sw(self.ctx, sw.atmos, sw.mu0, sw.toa_flux, sw.sfc_alb_dir, sw.sfc_alb_dif, sw.fluxes)
 
     def step(self):
+        self.update_vmr()
         if self.lw is not None:
             self.step_lw()
         if self.sw is not None:

@@ -181,6 +181,7 @@ TablesT tables_gfast(const rrtmgpb_gas_tables& t) {
   e.nbnd = t.nbnd; e.nflav = t.nflav;
   const int tn = t.ntemp * t.neta, rows = tn * (t.npres + 1);
   TablesT& tt = e.tt;
+  tt.maxm = 1;
   tt.gp = (t.ngpt + 1) & ~1;
   tt.nkl = (t.nminorklower + 1) & ~1;
   tt.nku = (t.nminorkupper + 1) & ~1;
@@ -212,6 +213,7 @@ TablesT tables_gfast(const rrtmgpb_gas_tables& t) {
       for (int i = 0; i < nminor[a]; ++i)
         if (mh[a].lim[2 * i + 1] >= bi.bS && mh[a].lim[2 * i] <= bi.bE) { first = std::min(first, i); last = std::max(last, i); }
       bi.mfirst[a] = first; bi.mlast[a] = last; bi.mdiff[a] = 0;
+      tt.maxm = std::max(tt.maxm, last - first + 1);
     }
   }
   std::vector<MinorInfo> minfo[2];
@@ -228,9 +230,9 @@ TablesT tables_gfast(const rrtmgpb_gas_tables& t) {
       for (int b = 0; b < t.nbnd; ++b)
         if (i >= bands[b].mfirst[a] && i <= bands[b].mlast[a] && mi.iflav != bands[b].iflav[a]) bands[b].mdiff[a] = 1;
     }
-    for (int b = 0; b < t.nbnd; ++b) {  // regular band: 4*kTG g-points, every contributor covers exactly the band
+    for (int b = 0; b < t.nbnd; ++b) {  // regular band: 16 g-points, every contributor covers exactly the band
       BandInfo& bi = bands[b];
-      bool reg = (bi.bE - bi.bS + 1 == 4 * kTG) && !bi.mdiff[a];
+      bool reg = (bi.bE - bi.bS + 1 == kTauRegChunks * kTG) && !bi.mdiff[a];
       for (int i = bi.mfirst[a]; reg && i <= bi.mlast[a]; ++i)
         reg = minfo[a][i].mS == bi.bS && minfo[a][i].mE == bi.bE;
       bi.regular[a] = reg ? 1 : 0;
@@ -349,18 +351,26 @@ void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, c
   {
     KernelTimer timer(sw ? "gas_tau_fused[sw]" : "gas_tau_fused[lw]");
     const unsigned grid = (unsigned)((long long)ceil_div((long long)ncl, kTauCells * kGThreads) * t->nbnd);
+    // lane-private slots for the per-(cell, band) minor scalings: [contributor][cell slot][thread]
+    const size_t smem = (size_t)tt.maxm * kTauCells * kGThreads * sizeof(Float);
 // KIND 1: the common kinds as compile-time constants (LW 1scl += 1scl clouds, SW 2str += 2str clouds, no aerosols)
+#define GAS_TAU_LAUNCH1(SWV, VECV, AERV, KINDV)                                                                   \
+  do {                                                                                                            \
+    auto kern = gas_tau_g_kernel<SWV, VECV, AERV, KINDV>;                                                         \
+    if (smem > 48 * 1024) RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, kGThreads, smem, stream()>>>(p, tt);                                                             \
+  } while (0)
 #define GAS_TAU_LAUNCH(SWV, VECV)                                                                     \
-  if (aer_kind) gas_tau_g_kernel<SWV, VECV, true, 0><<<grid, kGThreads, 0, stream()>>>(p, tt);        \
-  else if (op_kind == (SWV ? 2 : 1) && cld_kind == (SWV ? 2 : 1))                                     \
-    gas_tau_g_kernel<SWV, VECV, false, 1><<<grid, kGThreads, 0, stream()>>>(p, tt);                   \
-  else gas_tau_g_kernel<SWV, VECV, false, 0><<<grid, kGThreads, 0, stream()>>>(p, tt)
+  if (aer_kind) GAS_TAU_LAUNCH1(SWV, VECV, true, 0);                                                  \
+  else if (op_kind == (SWV ? 2 : 1) && cld_kind == (SWV ? 2 : 1)) GAS_TAU_LAUNCH1(SWV, VECV, false, 1); \
+  else GAS_TAU_LAUNCH1(SWV, VECV, false, 0)
     if (sw) {
       if (tt.vec == 2) { GAS_TAU_LAUNCH(true, 2); } else { GAS_TAU_LAUNCH(true, 1); }
     } else {
       if (tt.vec == 2) { GAS_TAU_LAUNCH(false, 2); } else { GAS_TAU_LAUNCH(false, 1); }
     }
 #undef GAS_TAU_LAUNCH
+#undef GAS_TAU_LAUNCH1
     RB_LAUNCH_CHECK();
   }
   if (lay_src) {

@@ -399,6 +399,17 @@ void rrtmgpb_broadcast_by_lay(int ncol, int nlay, const Float* per_col, Float* o
   launch_elementwise(n, [=] __device__(size_t k) { po[k] = pi[k % ncol]; });
 }
 
+void rrtmgpb_gas_concs_get_vmr(int ncol, int nlay, int nc_conc, int nl_conc, const Float* conc, Float* array) {
+  OpName op_name__(__func__);
+  const size_t n = (size_t)ncol * nlay;
+  DevArg<Float> in(conc, (size_t)nc_conc * nl_conc, Dir::In), o(array, n, Dir::Out);
+  const Float* pi = in; Float* po = o;
+  // mo_gas_concentrations.F90:464-501: stored as 2D (ncol,nlay), 1D (1,nlay) or scalar (1,1)
+  if (nc_conc > 1) launch_elementwise(n, [=] __device__(size_t k) { po[k] = pi[k]; });
+  else if (nl_conc > 1) launch_elementwise(n, [=] __device__(size_t k) { po[k] = pi[k / ncol]; });
+  else launch_elementwise(n, [=] __device__(size_t k) { po[k] = pi[0]; });
+}
+
 void rrtmgpb_expand_and_transpose(int ncol, int nband, int ngpt, const int* band_lims_gpt,
                                   const Float* arr_in, Float* arr_out) {
   OpName op_name__(__func__);

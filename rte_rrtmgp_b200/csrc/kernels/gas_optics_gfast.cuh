@@ -47,7 +47,7 @@ struct BandInfo {
   int igas1[2], igas2[2];       // the flavour's two gases, [itropo]                       (:121-122)
   int mfirst[2], mlast[2];      // minor contributors overlapping the band, [itropo] (lower / upper set)
   int mdiff[2];                 // 1: some of them has a flavour other than the band's
-  int regular[2];               // 1: the band has 4*kTG g-points and every contributor covers exactly the band with the
+  int regular[2];               // 1: the band has kTauRegChunks*kTG = 16 g-points and every contributor covers exactly the band with the
                                 //    band's flavour (all rrtmgp-data bands): the kernel's range tests fold away
 };
 struct MinorInfo {
@@ -92,6 +92,7 @@ struct TablesT {
   int gp;        // row pitch of kmajor / pfrac / krayl (ngpt rounded up to a multiple of 2)
   int nkl, nku;  // row pitch of kminor_lower / kminor_upper
   int vec;       // 2: every band / minor interval starts on an even 0-based column and has even length
+  int maxm;      // most minor contributors any band has in one atmosphere half (sizes the tau kernel's scaling slots)
   GasAux aux;
 };
 
@@ -193,22 +194,42 @@ __device__ __forceinline__ void interp3d_g(const Float* __restrict__ tab, int gp
 #define RB_TAU_MINB 3
 #endif
 constexpr int kTauCells = RB_TAU_CELLS;
-constexpr int kTG = 4;  // g-points per register chunk of the tau kernel
+#ifndef RB_TAU_TG
+#define RB_TAU_TG 4
+#endif
+constexpr int kTG = RB_TAU_TG;          // g-points per register chunk of the tau kernel
+constexpr int kTauRegChunks = 16 / kTG;  // chunks of a regular band (16 g-points, all rrtmgp-data bands)
 
 struct TauCell {
   size_t c;       // cell index (clamped into range; `valid` says whether it may be stored)
   bool valid;
+  int slot;       // which of the thread's kTauCells cells this is (selects its precomputed minor scalings)
   Float col_dry, ct, cw, cg, amount_rayl;
   Float at, aw, ag;  // second increment (only touched by the AER instantiations)
   FlavW w;
 };
+
+// scaling of one minor contributor at cell c (:461-480): col_gas(minor) [* 0.01 p/T [* vmr of the scaling gas or its
+// complement]]
+__device__ __forceinline__ Float minor_scaling(const FusedParams& p, const MinorInfo& mi, size_t c, size_t ncl, Float col_dry) {
+  Float sc = col_gas_of(p, c, ncl, mi.igas, col_dry);
+  if (mi.dens) {
+    sc = sc * p.cs.pt_scale[c];
+    if (mi.isc > 0) {
+      const Float vmr_fact = p.cs.vmr_fact[c], dry_fact = p.cs.dry_fact[c];
+      if (mi.comp) sc = sc * ((Float)1 - col_gas_of(p, c, ncl, mi.isc, col_dry) * vmr_fact * dry_fact);
+      else sc = sc * (col_gas_of(p, c, ncl, mi.isc, col_dry) * vmr_fact * dry_fact);
+    }
+  }
+  return sc;
+}
 
 // NC cells that share tropo, jtemp and the table rows (row0, row1 => je[0], je[1]) of band `bi`
 // KIND: 0 = optical-property kind and cloud kind read at run time; 1 = the common combination as compile-time constants
 // (LW: 1scl tau += 1scl clouds; SW: 2str incremented by 2str clouds), so the epilogue's kind tests fold away.
 template <bool SW, int VEC, int NC, bool AER, int KIND>
 __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const TablesT& tt, const BandInfo& bi, bool tropo,
-                                               int jtemp, int row0, int row1, TauCell (&cell)[NC]) {
+                                               int jtemp, int row0, int row1, TauCell (&cell)[NC], const Float* scal) {
   const rrtmgpb_gas_tables& t = p.t;
   const size_t ncl = (size_t)p.ncol * p.nlay;
   const int itropo = tropo ? 0 : 1;
@@ -250,22 +271,11 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
     for (int imnr = mfirst; imnr <= mlast; ++imnr) {
       const MinorInfo mi = minfo[imnr];
       if (!REG && (mi.mE < gS || mi.mS > gS + n - 1)) continue;
+      // scaling of this contributor for every cell: computed once per (cell, band) by the kernel's prologue
+      // (minor_scaling) into the thread's own shared-memory slots, not once per chunk
       Float scaling[NC];
 #pragma unroll
-      for (int k = 0; k < NC; ++k) {
-        const size_t c = cell[k].c;
-        const Float col_dry = cell[k].col_dry;
-        Float sc = col_gas_of(p, c, ncl, mi.igas, col_dry);
-        if (mi.dens) {
-          sc = sc * p.cs.pt_scale[c];
-          if (mi.isc > 0) {
-            const Float vmr_fact = p.cs.vmr_fact[c], dry_fact = p.cs.dry_fact[c];
-            if (mi.comp) sc = sc * ((Float)1 - col_gas_of(p, c, ncl, mi.isc, col_dry) * vmr_fact * dry_fact);
-            else sc = sc * (col_gas_of(p, c, ncl, mi.isc, col_dry) * vmr_fact * dry_fact);
-          }
-        }
-        scaling[k] = sc;
-      }
+      for (int k = 0; k < NC; ++k) scaling[k] = scal[((imnr - mfirst) * kTauCells + cell[k].slot) * kGThreads];
       // The contributor's flavour is the band's flavour for rrtmgp-data (a contributor lives inside one band);
       // otherwise its eta weights are recomputed - single-cell path only, the caller does not share rows
       // across cells for such bands (BandInfo::mdiff).
@@ -380,7 +390,7 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
   };
 
   if (tropo ? bi.regular[0] : bi.regular[1]) {
-    for (int q = 0; q < 4; ++q) chunk(bi.bS + q * kTG, kTG, std::true_type{}, std::true_type{});
+    for (int q = 0; q < kTauRegChunks; ++q) chunk(bi.bS + q * kTG, kTG, std::true_type{}, std::true_type{});
   } else {
     for (int gS = bi.bS; gS <= bi.bE; gS += kTG) {
       const int n = min(kTG, bi.bE - gS + 1);
@@ -397,6 +407,10 @@ __global__ void __launch_bounds__(kGThreads, RB_TAU_MINB) gas_tau_g_kernel(const
   const int ibnd = blockIdx.x % t.nbnd;
   const size_t cbase = (size_t)(blockIdx.x / t.nbnd) * (kTauCells * kGThreads) + threadIdx.x;
   if (cbase >= ncl) return;
+  // minor-contributor scalings of this thread's cells: [contributor of the band][cell slot][thread], lane-private
+  // (no barrier: a thread only reads what it wrote); tt.maxm contributors at most
+  extern __shared__ __align__(16) unsigned char tau_smem_raw[];
+  Float* scal = reinterpret_cast<Float*>(tau_smem_raw) + threadIdx.x;
   const BandInfo bi = tt.aux.band[ibnd];
   const int s_eta = t.ntemp, s_p = t.ntemp * t.neta;
   TauCell cell[kTauCells];
@@ -407,6 +421,7 @@ __global__ void __launch_bounds__(kGThreads, RB_TAU_MINB) gas_tau_g_kernel(const
     const size_t craw = cbase + (size_t)k * kGThreads;
     TauCell& ce = cell[k];
     ce.valid = craw < ncl;
+    ce.slot = k;
     const size_t c = ce.valid ? craw : cbase;  // out-of-range slots shadow the thread's first cell, never store
     ce.c = c;
     ce.col_dry = p.cs.col_dry[c];
@@ -436,6 +451,12 @@ __global__ void __launch_bounds__(kGThreads, RB_TAU_MINB) gas_tau_g_kernel(const
       if (p.aer_kind == 2) { ce.aw = p.aer_ssa[cb]; ce.ag = p.aer_g[cb]; }
     }
     ce.amount_rayl = SW ? col_gas_of(p, c, ncl, t.idx_h2o, ce.col_dry) + ce.col_dry : (Float)0;  // :559
+    {
+      const MinorInfo* minfo = tropo[k] ? tt.aux.minor_lower : tt.aux.minor_upper;
+      const int mfirst = tropo[k] ? bi.mfirst[0] : bi.mfirst[1], mlast = tropo[k] ? bi.mlast[0] : bi.mlast[1];
+      for (int imnr = mfirst; imnr <= mlast; ++imnr)
+        scal[((imnr - mfirst) * kTauCells + k) * kGThreads] = minor_scaling(p, minfo[imnr], c, ncl, ce.col_dry);
+    }
   }
   bool shared_rows = true;
 #pragma unroll
@@ -443,13 +464,13 @@ __global__ void __launch_bounds__(kGThreads, RB_TAU_MINB) gas_tau_g_kernel(const
     shared_rows = shared_rows && tropo[k] == tropo[0] && row0[k] == row0[0] && row1[k] == row1[0];
   if (tropo[0] ? bi.mdiff[0] : bi.mdiff[1]) shared_rows = false;
   if (shared_rows) {
-    tau_band_cells<SW, VEC, kTauCells, AER, KIND>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell);
+    tau_band_cells<SW, VEC, kTauCells, AER, KIND>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell, scal);
   } else {
 #pragma unroll
     for (int k = 0; k < kTauCells; ++k) {
       if (!cell[k].valid) continue;
       TauCell one[1] = {cell[k]};
-      tau_band_cells<SW, VEC, 1, AER, KIND>(p, tt, bi, tropo[k], jtemp[k], row0[k], row1[k], one);
+      tau_band_cells<SW, VEC, 1, AER, KIND>(p, tt, bi, tropo[k], jtemp[k], row0[k], row1[k], one, scal);
     }
   }
 }

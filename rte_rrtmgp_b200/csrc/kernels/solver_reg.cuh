@@ -70,8 +70,29 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // profiles/r1_prof_v4_*).
 // ---------------------------------------------------------------------------------------------------
 // x_out = A*x_in + B, chunks chained top -> bottom (j = 0 first).  Returns the state entering this lane's chunk;
-// `out_last` receives the state leaving it.
+// `out` receives the state leaving it.  x_top must hold the boundary value on every lane of the column.
+//
+// The chain is a prefix scan of affine maps over the 8 chunk lanes of a column (Hillis-Steele, 3 steps of
+// 2 shuffles + 2 multiply-adds, then one shuffle to pass the result on) instead of 8 dependent
+// shuffle + multiply-add steps: the hand-overs were the longest serial sections of a g-point (three of them per
+// g-point in the SW kernel), during which a warp issues next to nothing.  Composition order differs from the serial
+// chain only in the association of the products and sums (rounding level, like the chunk composition itself).
+#ifndef RB_HANDOFF_SCAN
+#define RB_HANDOFF_SCAN 1
+#endif
 __device__ __forceinline__ Float affine_handoff_down(int j, Float A, Float B, Float x_top, Float& out) {
+#if RB_HANDOFF_SCAN
+  Float PA = A, PB = B;  // composed map of chunks (j-d+1 .. j): x -> PA*x + PB
+#pragma unroll
+  for (int d = 1; d < kRegChunks; d <<= 1) {
+    const Float qa = __shfl_up_sync(0xffffffffu, PA, d, kRegChunks);
+    const Float qb = __shfl_up_sync(0xffffffffu, PB, d, kRegChunks);
+    if (j >= d) { PB = PA * qb + PB; PA = PA * qa; }  // this map after the d chunks above it
+  }
+  out = PA * x_top + PB;
+  const Float got = __shfl_up_sync(0xffffffffu, out, 1, kRegChunks);
+  return j == 0 ? x_top : got;
+#else
   Float xin = x_top;
   out = 0;
   for (int jj = 0; jj < kRegChunks; ++jj) {
@@ -82,9 +103,39 @@ __device__ __forceinline__ Float affine_handoff_down(int j, Float A, Float B, Fl
     }
   }
   return xin;
+#endif
 }
-// chunks chained bottom -> top (j = 7 first)
+// direct beam: B == 0, the scan carries the products only
+__device__ __forceinline__ Float product_handoff_down(int j, Float A, Float x_top, Float& out) {
+#if RB_HANDOFF_SCAN
+  Float PA = A;
+#pragma unroll
+  for (int d = 1; d < kRegChunks; d <<= 1) {
+    const Float qa = __shfl_up_sync(0xffffffffu, PA, d, kRegChunks);
+    if (j >= d) PA = PA * qa;
+  }
+  out = PA * x_top;
+  const Float got = __shfl_up_sync(0xffffffffu, out, 1, kRegChunks);
+  return j == 0 ? x_top : got;
+#else
+  return affine_handoff_down(j, A, (Float)0, x_top, out);
+#endif
+}
+// chunks chained bottom -> top (j = 7 first); x_bottom needs to be valid on the lane of the last chunk only
 __device__ __forceinline__ Float affine_handoff_up(int j, Float A, Float B, Float x_bottom, Float& out) {
+#if RB_HANDOFF_SCAN
+  const Float xb = __shfl_sync(0xffffffffu, x_bottom, kRegChunks - 1, kRegChunks);
+  Float PA = A, PB = B;  // composed map of chunks (j+d-1 .. j), applied bottom first
+#pragma unroll
+  for (int d = 1; d < kRegChunks; d <<= 1) {
+    const Float qa = __shfl_down_sync(0xffffffffu, PA, d, kRegChunks);
+    const Float qb = __shfl_down_sync(0xffffffffu, PB, d, kRegChunks);
+    if (j + d < kRegChunks) { PB = PA * qb + PB; PA = PA * qa; }
+  }
+  out = PA * xb + PB;
+  const Float got = __shfl_down_sync(0xffffffffu, out, 1, kRegChunks);
+  return j == kRegChunks - 1 ? xb : got;
+#else
   Float xin = x_bottom;
   out = 0;
   for (int jj = kRegChunks - 1; jj >= 0; --jj) {
@@ -95,6 +146,7 @@ __device__ __forceinline__ Float affine_handoff_up(int j, Float A, Float B, Floa
     }
   }
   return xin;
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -370,6 +422,41 @@ __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL]
   // no division inside the 8-step serial chain (the reciprocal used to be its longest link); every lane normalises
   // the state it received once, in parallel with the others.
   Float alb = albedo_sfc, src = src_sfc;
+#if RB_HANDOFF_SCAN
+  {
+    // prefix scan of the chunk matrices from the bottom (3 steps; see affine_handoff_down): after it lane j holds the
+    // product of the matrices of chunks j .. 7, bottom one applied first
+#pragma unroll
+    for (int d = 1; d < kRegChunks; d <<= 1) {
+      const Float la = __shfl_down_sync(0xffffffffu, ma, d, kRegChunks), lb = __shfl_down_sync(0xffffffffu, mb, d, kRegChunks);
+      const Float lc = __shfl_down_sync(0xffffffffu, mc, d, kRegChunks), ld = __shfl_down_sync(0xffffffffu, md, d, kRegChunks);
+      const Float le = __shfl_down_sync(0xffffffffu, me, d, kRegChunks), lf = __shfl_down_sync(0xffffffffu, mf, d, kRegChunks);
+      const Float lg = __shfl_down_sync(0xffffffffu, mg, d, kRegChunks);
+      if (j + d < kRegChunks) {  // (this lane's chunks) after (the d chunk groups below them)
+        const Float na = ma * la + mb * lf, nb = ma * lb + mb * lg;
+        const Float nc = mc * la + md * lc + me * lf, ne = mc * lb + md * le + me * lg;
+        const Float nf = mf * la + mg * lf, ng = mf * lb + mg * lg;
+        ma = na; mb = nb; mc = nc; md = md * ld; me = ne; mf = nf; mg = ng;
+      }
+    }
+    // the surface state lives on the lane of the last chunk (src_sfc comes from its direct beam)
+    const Float a_s = __shfl_sync(0xffffffffu, albedo_sfc, kRegChunks - 1, kRegChunks);
+    const Float s_s = __shfl_sync(0xffffffffu, src_sfc, kRegChunks - 1, kRegChunks);
+    // state leaving this lane's chunk upwards, homogeneous; the lane above takes it over
+    const Float ha = ma * a_s + mb, hs = mc * a_s + md * s_s + me, hd = mf * a_s + mg;
+    const Float ia = __shfl_down_sync(0xffffffffu, ha, 1, kRegChunks);
+    const Float is = __shfl_down_sync(0xffffffffu, hs, 1, kRegChunks);
+    const Float id = __shfl_down_sync(0xffffffffu, hd, 1, kRegChunks);
+    if (j < kRegChunks - 1) {
+      const Float inv = rb_rcp(id);
+      alb = ia * inv;
+      src = is * inv;
+    } else {
+      alb = a_s;  // exactly the surface values (:1166-1168)
+      src = s_s;
+    }
+  }
+#else
   {
     Float ha = 0, hs = 0, hd = 0;
     Float ia = albedo_sfc, is = src_sfc, id = 1;  // incoming state of this lane, homogeneous
@@ -388,6 +475,7 @@ __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL]
     alb = ia * inv;
     src = is * inv;
   }
+#endif
   // replay with the reference's per-layer expressions, every lane on its own chunk
 #pragma unroll
   for (int i = CL - 1; i >= 0; --i) {  // :1174-1186
@@ -431,6 +519,10 @@ struct SwRegParams {
   int gpt_per_block;
 };
 
+// per-(column, layer) quantities derived from mu0, computed once per CTA and kept in lane-private shared-memory slots
+// for all g-points: mu0_s = max(sqrt(eps), mu0) (:1065), 3*mu0_s (first factor of :1079) and 1/mu0_s (for tau/mu0_s, :1092)
+constexpr int kSwMu0Planes = 3;
+
 template <int CL>
 __host__ __device__ constexpr int sw_reg_slots() { return 3 * CL + 4; }  // tau, ssa, g, alb_dir, alb_dif, inc_dir, inc_dif
 
@@ -438,14 +530,14 @@ __host__ __device__ constexpr int sw_reg_slots() { return 3 * CL + 4; }  // tau,
 // of registers and the input prefetch is single-stage (issued when phase A has consumed the slots), so that the
 // kernel fits 168 registers and 68 KB of shared memory: 3 resident CTAs (12 warps) per SM instead of 2.
 template <int CL, bool LEAN>
-__host__ __device__ constexpr int sw_reg_smem_slots() { return (LEAN ? 1 : 2) * sw_reg_slots<CL>() + CL + (LEAN ? 3 * CL : 0); }
+__host__ __device__ constexpr int sw_reg_smem_slots() { return (LEAN ? 1 : 2) * sw_reg_slots<CL>() + kSwMu0Planes * CL + (LEAN ? 3 * CL : 0); }
 
 // TMA variant: the three (16 columns x nlay) input tiles of a g-point arrive by cp.async.bulk.tensor (kernels/tma.cuh),
 // two stages; the four per-(column, g-point) boundary values keep their lane-private cp.async slots.
 struct SwTmaMaps { CUtensorMap tau, ssa, g; };
 template <int CL, bool LEAN>
 __host__ __device__ inline size_t sw_reg_tma_smem(int nlay) {
-  return 2 * 3 * tile_bytes(nlay) + (size_t)(2 * 4 + CL + (LEAN ? 3 * CL : 0)) * kRegThreads * sizeof(Float) + 2 * sizeof(uint64_t);
+  return 2 * 3 * tile_bytes(nlay) + (size_t)(2 * 4 + kSwMu0Planes * CL + (LEAN ? 3 * CL : 0)) * kRegThreads * sizeof(Float) + 2 * sizeof(uint64_t);
 }
 
 // FULL: nlay == 8*CL, every lane's cells are real layers - the padding selects and tests fold away at compile time.
@@ -462,9 +554,9 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
   constexpr int NS = TMA ? 4 : sw_reg_slots<CL>();                // slots per stage
   constexpr int BC0 = TMA ? 0 : 3 * CL;                           // first boundary-value slot
   constexpr int NSTAGE = (LEAN && !TMA) ? 1 : 2;
-  Float* sm_mu0 = sm + (size_t)NSTAGE * NS * kRegThreads;  // [CL][thread], loaded once
-  Float* sm_acc = sm_mu0 + (size_t)CL * kRegThreads + threadIdx.x;  // LEAN: [3][CL][thread]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm_mu0 + (size_t)(CL + (LEAN ? 3 * CL : 0)) * kRegThreads);  // TMA: [2] mbarriers
+  Float* sm_mu0 = sm + (size_t)NSTAGE * NS * kRegThreads;  // [3][CL][thread]: mu0_s, 3*mu0_s, 1/mu0_s; filled once
+  Float* sm_acc = sm_mu0 + (size_t)kSwMu0Planes * CL * kRegThreads + threadIdx.x;  // LEAN: [3][CL][thread]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm_mu0 + (size_t)(kSwMu0Planes * CL + (LEAN ? 3 * CL : 0)) * kRegThreads);  // TMA: [2] mbarriers
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = lane >> 3, j = lane & 7;
   const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
@@ -542,9 +634,18 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
     if (gb + 1 < ge) prefetch(gb + 1, 1);
     cp_async_commit();
   }
+  // mu0 does not depend on the g-point: its clamped value, 3*mu0_s and the reciprocal are computed once, and
+  // "mu0 > 0" (:1122) becomes one bit per cell
+  unsigned lit_mask = 0;
 #pragma unroll
-  for (int i = 0; i < CL; ++i)
-    sm_mu0[i * kRegThreads + threadIdx.x] = p.mu0[(k0 + i < nlay) ? off_lay0 + lay_step * i : off_lay0];
+  for (int i = 0; i < CL; ++i) {
+    const Float mu0 = p.mu0[(k0 + i < nlay) ? off_lay0 + lay_step * i : off_lay0];
+    const Float mu0_s = fmax(min_mu0, mu0);  // :1065
+    sm_mu0[i * kRegThreads + threadIdx.x] = mu0_s;
+    sm_mu0[(CL + i) * kRegThreads + threadIdx.x] = (Float)3 * mu0_s;
+    sm_mu0[(2 * CL + i) * kRegThreads + threadIdx.x] = rb_rcp(mu0_s);
+    if (mu0 > (Float)0) lit_mask |= 1u << i;
+  }
   const Float mu0_top = p.mu0[(size_t)col + ncol * o.lay(0)];
   const Float mu0_sfc = p.mu0[(size_t)col + ncol * o.lay(nlay - 1)];
 
@@ -579,7 +680,9 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
       } else {
         tau_s = *RB_SLOT(sm, NS, s, i); w0_s = *RB_SLOT(sm, NS, s, CL + i); g_s = *RB_SLOT(sm, NS, s, 2 * CL + i);
       }
-      const Float mu0 = sm_mu0[i * kRegThreads + threadIdx.x];
+      const Float mu0_s = sm_mu0[i * kRegThreads + threadIdx.x];
+      const Float mu0_3 = sm_mu0[(CL + i) * kRegThreads + threadIdx.x];
+      const Float mu0_r = sm_mu0[(2 * CL + i) * kRegThreads + threadIdx.x];
       const Float gamma1 = ((Float)8 - w0_s * ((Float)5 + (Float)3 * g_s)) * (Float).25;
       const Float gamma2 = (Float)3 * (w0_s * ((Float)1 - g_s)) * (Float).25;
       const Float kk = rb_sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), min_k));
@@ -588,17 +691,18 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
       Float RT_term = rb_rcp(kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau));
       const Float Rdif = RT_term * gamma2 * ((Float)1 - exp_minus2ktau);
       const Float Tdif = RT_term * (Float)2 * kk * exp_minusktau;
-      const Float mu0_s = fmax(min_mu0, mu0);
       const Float k_mu = kk * mu0_s;
       const Float om = (Float)1 - k_mu * k_mu;
       RT_term = rb_div(w0_s * RT_term, fabs(om) >= eps ? om : eps);
-      const Float gamma3 = ((Float)2 - (Float)3 * mu0_s * g_s) * (Float).25;
+      const Float gamma3 = ((Float)2 - mu0_3 * g_s) * (Float).25;
       const Float gamma4 = (Float)1 - gamma3;
       const Float alpha1 = gamma1 * gamma4 + gamma2 * gamma3;
       const Float alpha2 = gamma1 * gamma3 + gamma2 * gamma4;
       const Float k_gamma3 = kk * gamma3;
       const Float k_gamma4 = kk * gamma4;
-      const Float Tnoscat = rb_exp<true>(-rb_div(tau_s, mu0_s));  // flushes to 0 (night columns, mu0_s = sqrt(eps))
+      // tau/mu0_s from the stored reciprocal with the residual correction of rb_div (<= 1 ulp)
+      const Float tq = tau_s * mu0_r;
+      const Float Tnoscat = rb_exp<true>(-fma(fma(-mu0_s, tq, tau_s), mu0_r, tq));  // flushes to 0 (night columns, mu0_s = sqrt(eps))
       Float Rdir = RT_term * (((Float)1 - k_mu) * (alpha2 + k_gamma3) -
                               ((Float)1 + k_mu) * (alpha2 - k_gamma3) * exp_minus2ktau -
                               (Float)2.0 * (k_gamma3 - alpha2 * k_mu) * exp_minusktau * Tnoscat);
@@ -607,7 +711,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
                                (Float)2.0 * (k_gamma4 + alpha1 * k_mu) * exp_minusktau);
       Rdir = fmax((Float)0, fmin(Rdir, ((Float)1 - Tnoscat)));         // :1107
       Tdir = fmax((Float)0, fmin(Tdir, ((Float)1 - Tnoscat - Rdir)));  // :1108
-      const bool lit = live && (mu0 > (Float)0);  // :1122-1125: no source for diffuse light where mu0 <= 0
+      const bool lit = live && ((lit_mask >> i) & 1u);  // :1122-1125: no source for diffuse light where mu0 <= 0
       R[i] = live ? Rdif : (Float)0;
       T[i] = live ? Tdif : (Float)1;
       A3[i] = lit ? Rdir : (Float)0;
@@ -637,7 +741,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
 #pragma unroll
       for (int i = 0; i < CL; ++i) P = A5[i] * P;
       Float out;
-      dir = affine_handoff_down(j, P, (Float)0, dir_top_g, out);
+      dir = product_handoff_down(j, P, dir_top_g, out);
 #pragma unroll
       for (int i = 0; i < CL; ++i) {
         const Float s_up = A3[i] * dir, s_dn = A4[i] * dir;

@@ -296,11 +296,15 @@ def compute_profiles(SST, ncol, nlay):
     return dict(p_lay=rep(p_l), t_lay=rep(T_l), p_lev=rep(p_v), t_lev=rep(T_v), q=rep(q_l), o3=rep(o3))
 
 
+# rrtmgp_allsky.F90:195-203: the well-mixed gases are scalars in gas_concs
+ALLSKY_WELL_MIXED = {"co2": 348.0e-6, "ch4": 1650.0e-9, "n2o": 306.0e-9, "n2": 0.7808, "o2": 0.2095, "co": 0.0}
+
+
 def allsky_gas_vmrs(prof):
     """rrtmgp_allsky.F90:195-203: vmr(ncol,nlay,ngas) in GAS_NAMES order."""
     ncol, nlay = prof["p_lay"].shape
     vmr = np.zeros((ncol, nlay, len(GAS_NAMES)), order="F")
-    const = {"co2": 348.0e-6, "ch4": 1650.0e-9, "n2o": 306.0e-9, "n2": 0.7808, "o2": 0.2095, "co": 0.0}
+    const = ALLSKY_WELL_MIXED
     for i, name in enumerate(GAS_NAMES):
         if name == "h2o":
             vmr[:, :, i] = prof["q"]
