@@ -103,6 +103,11 @@ void rrtmgpb_broadcast_by_lay(int ncol, int nlay, const Float* per_col, Float* o
  * gas by gas_optics, rrtmgp/frontend/mo_gas_optics_rrtmgp.F90:540-545): a concentration stored as (ncol,nlay), (1,nlay)
  * or (1,1) - conc(nc_conc, nl_conc) - is broadcast into array(ncol,nlay) */
 void rrtmgpb_gas_concs_get_vmr(int ncol, int nlay, int nc_conc, int nl_conc, const Float* conc, Float* array);
+/* replaces the loop of ty_gas_optics_rrtmgp%compute_optimal_angles, rrtmgp/frontend/mo_gas_optics_rrtmgp.F90:1544-1562
+ * (SURVEY 8f rank 3): optimal_angles(icol,igpt) = fit(1,band)*exp(-sum_lay tau(icol,:,igpt)) + fit(2,band);
+ * tau(ncol,nlay,ngpt), optimal_angle_fit(2,nband) -> optimal_angles(ncol,ngpt), the lw_Ds argument of rte_lw */
+void rrtmgpb_compute_optimal_angles(int ncol, int nlay, int ngpt, int nband, const int* band_lims_gpt, const Float* tau,
+                                    const Float* optimal_angle_fit, Float* optimal_angles);
 /* replaces the cloud masks mo_cloud_optics_rrtmgp.F90:334-341 */
 void rrtmgpb_cloud_masks(int ncol, int nlay, const Float* clwp, const Float* ciwp, Bool* liqmsk,
                          Bool* icemsk);

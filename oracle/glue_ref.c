@@ -116,6 +116,22 @@ void rrtmgpb_gas_concs_get_vmr(int ncol, int nlay, int nc_conc, int nl_conc, con
     }
 }
 
+/* ty_gas_optics_rrtmgp%compute_optimal_angles, rrtmgp/frontend/mo_gas_optics_rrtmgp.F90:1540-1562 */
+void rrtmgpb_compute_optimal_angles(int ncol, int nlay, int ngpt, int nband, const int* band_lims_gpt, const Float* tau,
+                                    const Float* optimal_angle_fit, Float* optimal_angles) {
+  const size_t ncl = (size_t)ncol * nlay;
+  for (int i = 0; i < ncol; ++i)
+    for (int g = 1; g <= ngpt; ++g) {
+      int b = 0;
+      while (b < nband - 1 && g > band_lims_gpt[2 * b + 1]) ++b; /* convert_gpt2band :1540-1542 */
+      Float t = 0;
+      for (int l = 0; l < nlay; ++l) t = t + tau[(size_t)i + (size_t)ncol * l + ncl * (size_t)(g - 1)]; /* :1552-1554 */
+      const Float trans_total = exp(-t);                                                               /* :1555 */
+      optimal_angles[(size_t)i + (size_t)ncol * (g - 1)] =
+          optimal_angle_fit[2 * b] * trans_total + optimal_angle_fit[2 * b + 1];                       /* :1559-1560 */
+    }
+}
+
 /* mo_cloud_optics_rrtmgp.F90:334-341 */
 void rrtmgpb_cloud_masks(int ncol, int nlay, const Float* clwp, const Float* ciwp, Bool* liqmsk, Bool* icemsk) {
   const size_t ncl = (size_t)ncol * nlay;

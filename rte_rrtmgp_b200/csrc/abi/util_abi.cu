@@ -410,6 +410,26 @@ void rrtmgpb_gas_concs_get_vmr(int ncol, int nlay, int nc_conc, int nl_conc, con
   else launch_elementwise(n, [=] __device__(size_t k) { po[k] = pi[0]; });
 }
 
+void rrtmgpb_compute_optimal_angles(int ncol, int nlay, int ngpt, int nband, const int* band_lims_gpt, const Float* tau,
+                                    const Float* optimal_angle_fit, Float* optimal_angles) {
+  OpName op_name__(__func__);
+  const size_t n = (size_t)ncol * ngpt, ncl = (size_t)ncol * nlay;
+  DevArg<int> lims(band_lims_gpt, 2 * (size_t)nband, Dir::In);
+  DevArg<Float> t(tau, ncl * ngpt, Dir::In), fit(optimal_angle_fit, 2 * (size_t)nband, Dir::In), o(optimal_angles, n, Dir::Out);
+  const int* pl = lims; const Float* pt = t; const Float* pf = fit; Float* po = o;
+  // thread = (column, g-point), columns fastest: every layer's read is one coalesced row of the tau plane
+  launch_elementwise(n, [=] __device__(size_t k) {
+    const int g = (int)(k / ncol) + 1; const size_t i = k % ncol;
+    int b = 0;
+    while (b < nband - 1 && g > pl[2 * b + 1]) ++b;            // convert_gpt2band
+    const Float* tg = pt + i + ncl * (size_t)(g - 1);
+    Float tsum = 0;
+    for (int l = 0; l < nlay; ++l) tsum = tsum + tg[(size_t)ncol * l];  // mo_gas_optics_rrtmgp.F90:1552-1554, layer order
+    const Float trans_total = exp(-tsum);                               // :1555
+    po[k] = pf[2 * b] * trans_total + pf[2 * b + 1];                    // :1559-1560
+  });
+}
+
 void rrtmgpb_expand_and_transpose(int ncol, int nband, int ngpt, const int* band_lims_gpt,
                                   const Float* arr_in, Float* arr_out) {
   OpName op_name__(__func__);

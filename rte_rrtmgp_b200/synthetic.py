@@ -221,6 +221,10 @@ def make_kdist(kind="lw", ngpt=None, seed=42, gpt_per_band=None, nminor_per_band
         tgrid = 160.0 + np.arange(196.0)
         kd.totplnk = _f(_planck_band_integrals(tgrid, band_lims_wvn))
         kd.totplnk_delta = 1.0
+        # optimal_angle_fit(2,nbnd) (mo_gas_optics_rrtmgp.F90:1503-1562): secant = fit1*T_column + fit2 >= 1; own generator,
+        # so that the tables above keep their values
+        r2 = np.random.default_rng(seed + 7700)
+        kd.extra["optimal_angle_fit"] = _f(np.stack([r2.uniform(0.0, 0.3, nbnd), r2.uniform(1.4, 1.7, nbnd)]))
     else:
         kd.krayl = _f(10.0 ** rng.uniform(-27.5, -26.0, (ntemp, neta, ngpt, 2)))
         ss = rng.uniform(0.2, 1.0, ngpt)
