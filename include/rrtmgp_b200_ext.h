@@ -108,6 +108,17 @@ void rrtmgpb_gas_concs_get_vmr(int ncol, int nlay, int nc_conc, int nl_conc, con
  * tau(ncol,nlay,ngpt), optimal_angle_fit(2,nband) -> optimal_angles(ncol,ngpt), the lw_Ds argument of rte_lw */
 void rrtmgpb_compute_optimal_angles(int ncol, int nlay, int ngpt, int nband, const int* band_lims_gpt, const Float* tau,
                                     const Float* optimal_angle_fit, Float* optimal_angles);
+/* McICA cloud sampling, rte/extensions/mo_cloud_sampling.F90.  randoms(ngpt,nlay,ncol) in [0,1),
+ * cloud_frac(ncol,nlay), overlap_param(ncol,nlay-1) -> cloud_mask(ncol,nlay,ngpt).
+ * replaces the column loops of sampled_mask_max_ran (:160-190) and sampled_mask_exp_ran (:250-290) */
+void rrtmgpb_sampled_mask_max_ran(int ncol, int nlay, int ngpt, const Float* randoms, const Float* cloud_frac,
+                                  Bool* cloud_mask);
+void rrtmgpb_sampled_mask_exp_ran(int ncol, int nlay, int ngpt, const Float* randoms, const Float* cloud_frac,
+                                  const Float* overlap_param, Bool* cloud_mask);
+/* replaces apply_cloud_mask (:298-314), the body of draw_samples: input_field(ncol,nlay,nbnd) by band ->
+ * sampled_field(ncol,nlay,ngpt), zero where the mask is false */
+void rrtmgpb_apply_cloud_mask(int ncol, int nlay, int nbnd, int ngpt, const int* band_lims_gpt, const Bool* cloud_mask,
+                              const Float* input_field, Float* sampled_field);
 /* replaces the cloud masks mo_cloud_optics_rrtmgp.F90:334-341 */
 void rrtmgpb_cloud_masks(int ncol, int nlay, const Float* clwp, const Float* ciwp, Bool* liqmsk,
                          Bool* icemsk);

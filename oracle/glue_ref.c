@@ -132,6 +132,56 @@ void rrtmgpb_compute_optimal_angles(int ncol, int nlay, int ngpt, int nband, con
     }
 }
 
+/* rte/extensions/mo_cloud_sampling.F90:160-190 (max-random) and :250-290 (exponential-random), one column at a time */
+static void sampled_mask_ref(int exp_ran, int ncol, int nlay, int ngpt, const Float* randoms, const Float* cloud_frac,
+                             const Float* overlap_param, Bool* cloud_mask) {
+  const size_t ncl = (size_t)ncol * nlay;
+  Float* local_rands = (Float*)malloc(sizeof(Float) * (size_t)(ngpt > 0 ? ngpt : 1));
+  for (int icol = 0; icol < ncol; ++icol) {
+    int fst = -1, lst = -1;
+    for (int l = 0; l < nlay; ++l)
+      if (cloud_frac[(size_t)icol + (size_t)ncol * l] > 0) { if (fst < 0) fst = l; lst = l; }
+    for (int l = 0; l < nlay; ++l)
+      for (int g = 0; g < ngpt; ++g) cloud_mask[(size_t)icol + (size_t)ncol * l + ncl * g] = 0;
+    if (fst < 0) continue;
+    for (int l = fst; l <= lst; ++l) {
+      const Float frac = cloud_frac[(size_t)icol + (size_t)ncol * l];
+      if (!(frac > 0)) continue;
+      const Float* r = randoms + (size_t)ngpt * ((size_t)l + (size_t)nlay * icol);
+      const int prev_cloudy = l > fst && cloud_frac[(size_t)icol + (size_t)ncol * (l - 1)] > 0;
+      if (l == fst || !prev_cloudy) {
+        for (int g = 0; g < ngpt; ++g) local_rands[g] = r[g];
+      } else if (exp_ran) {
+        const Float rho = overlap_param[(size_t)icol + (size_t)ncol * (l - 1)];
+        const Float sq = sqrt((Float)1 - rho * rho);
+        for (int g = 0; g < ngpt; ++g)
+          local_rands[g] = rho * (local_rands[g] - (Float)0.5) + sq * (r[g] - (Float)0.5) + (Float)0.5;
+      } /* max-random: same deviates as the cloudy layer above */
+      for (int g = 0; g < ngpt; ++g)
+        cloud_mask[(size_t)icol + (size_t)ncol * l + ncl * g] = local_rands[g] > ((Float)1 - frac);
+    }
+  }
+  free(local_rands);
+}
+void rrtmgpb_sampled_mask_max_ran(int ncol, int nlay, int ngpt, const Float* randoms, const Float* cloud_frac,
+                                  Bool* cloud_mask) {
+  sampled_mask_ref(0, ncol, nlay, ngpt, randoms, cloud_frac, 0, cloud_mask);
+}
+void rrtmgpb_sampled_mask_exp_ran(int ncol, int nlay, int ngpt, const Float* randoms, const Float* cloud_frac,
+                                  const Float* overlap_param, Bool* cloud_mask) {
+  sampled_mask_ref(1, ncol, nlay, ngpt, randoms, cloud_frac, overlap_param, cloud_mask);
+}
+/* apply_cloud_mask, mo_cloud_sampling.F90:298-314 */
+void rrtmgpb_apply_cloud_mask(int ncol, int nlay, int nbnd, int ngpt, const int* band_lims_gpt, const Bool* cloud_mask,
+                              const Float* input_field, Float* sampled_field) {
+  const size_t ncl = (size_t)ncol * nlay;
+  (void)ngpt;
+  for (int b = 0; b < nbnd; ++b)
+    for (int g = band_lims_gpt[2 * b]; g <= band_lims_gpt[2 * b + 1]; ++g)
+      for (size_t c = 0; c < ncl; ++c)
+        sampled_field[c + ncl * (size_t)(g - 1)] = cloud_mask[c + ncl * (size_t)(g - 1)] ? input_field[c + ncl * (size_t)b] : (Float)0;
+}
+
 /* mo_cloud_optics_rrtmgp.F90:334-341 */
 void rrtmgpb_cloud_masks(int ncol, int nlay, const Float* clwp, const Float* ciwp, Bool* liqmsk, Bool* icemsk) {
   const size_t ncl = (size_t)ncol * nlay;

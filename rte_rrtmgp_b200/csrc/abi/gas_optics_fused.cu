@@ -19,6 +19,7 @@
 // rrtmgpb_mem_free().
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -378,7 +379,10 @@ void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, c
     q.f = p; q.tlev = tlev; q.tsfc = tsfc; q.sfc_lay = sfc_lay;
     q.sfc_src = sfc_src; q.lay_src = lay_src; q.lev_src = lev_src; q.sfc_source_Jac = sfc_source_Jac;
     KernelTimer timer("planck_fused");
-    const int lay_per_chunk = 9, nchunk = ceil_div(nlay, lay_per_chunk);
+    // layers a thread marches through (its first level needs the Planck fractions of the layer above: 1/lay_per_chunk
+    // redundant work); RRTMGPB_PLANCK_CHUNK overrides for experiments
+    static const int chunk_env = [] { const char* e = std::getenv("RRTMGPB_PLANCK_CHUNK"); return e ? std::atoi(e) : 0; }();
+    const int lay_per_chunk = chunk_env > 0 ? chunk_env : 9, nchunk = ceil_div(nlay, lay_per_chunk);
     const unsigned grid = (unsigned)((long long)ceil_div(ncol, kGThreads) * nchunk * t->nbnd);
     if (tt.vec == 2) planck_g_kernel<2><<<grid, kGThreads, 0, stream()>>>(q, tt, lay_per_chunk, nchunk);
     else planck_g_kernel<1><<<grid, kGThreads, 0, stream()>>>(q, tt, lay_per_chunk, nchunk);

@@ -586,6 +586,91 @@ int rrtmgpb_any_vals_outside(size_t n, const Float* array, const Bool* mask, Flo
   return any_flag(n, array, mask, checkMin, checkMax, true);
 }
 
+// ---------------- McICA cloud sampling (rte/extensions/mo_cloud_sampling.F90) ----------------
+}  // extern "C"
+namespace {
+// One thread = (column, group of 4 consecutive g-points) marching down the layers with its random deviates in
+// registers: the 4 deviates of a layer are one 32-byte sector of randoms(ngpt,nlay,ncol); the mask is written
+// column-fastest (coalesced 1-byte stores).  EXP: exponential-random overlap (:205-292), else maximum-random (:125-192).
+// The correlated deviate is evaluated without FMA contraction so that the mask equals the CPU result bit for bit.
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+
+template <bool EXP>
+void sampled_mask(int ncol, int nlay, int ngpt, const Float* randoms, const Float* cloud_frac, const Float* overlap_param,
+                  Bool* cloud_mask) {
+  const size_t ncl = (size_t)ncol * nlay;
+  DevArg<Float> r(randoms, ncl * ngpt, Dir::In), cf(cloud_frac, ncl, Dir::In);
+  DevArg<Float> op(overlap_param, EXP ? (size_t)ncol * (nlay - 1) : 0, Dir::In, EXP);
+  DevArg<Bool> m(cloud_mask, ncl * ngpt, Dir::Out);
+  const Float* pr = r; const Float* pc = cf; const Float* po = op; Bool* pm = m;
+  constexpr int GQ = 4;
+  const int ngrp = (ngpt + GQ - 1) / GQ;
+  launch_elementwise((size_t)ncol * ngrp, [=] __device__(size_t k) {
+    const size_t icol = k % ncol;
+    const int g0 = (int)(k / ncol) * GQ, ng = min(GQ, ngpt - g0);
+    Float lr[GQ];
+    bool prev_cloudy = false, started = false;
+    for (int ilay = 0; ilay < nlay; ++ilay) {
+      const Float frac = pc[icol + (size_t)ncol * ilay];
+      const bool cloudy = frac > (Float)0;  // cloud_mask_layer, :161
+      const Float* rl = pr + g0 + (size_t)ngpt * (ilay + (size_t)nlay * icol);
+      if (cloudy) {
+        Float rho = 0, sq = 0;
+        const bool corr = EXP && started && prev_cloudy;
+        if (corr) { rho = po[icol + (size_t)ncol * (ilay - 1)]; sq = sqrt(add_rn((Float)1, -mul_rn(rho, rho))); }  // :274-276
+#pragma unroll
+        for (int q = 0; q < GQ; ++q) {
+          if (q < ng) {
+            if (corr)  // :275-276, left to right
+              lr[q] = add_rn(add_rn(mul_rn(rho, lr[q] - (Float)0.5), mul_rn(sq, rl[q] - (Float)0.5)), (Float)0.5);
+            else if (EXP || !(started && prev_cloudy)) lr[q] = rl[q];  // new deviates (:172,:180 / :264,:278)
+            pm[icol + (size_t)ncol * ilay + ncl * (size_t)(g0 + q)] = lr[q] > ((Float)1 - frac);  // :173,:181
+          }
+        }
+        started = true;
+      } else {
+#pragma unroll
+        for (int q = 0; q < GQ; ++q)
+          if (q < ng) pm[icol + (size_t)ncol * ilay + ncl * (size_t)(g0 + q)] = false;
+      }
+      prev_cloudy = cloudy;
+    }
+  });
+}
+}  // namespace
+extern "C" {
+
+void rrtmgpb_sampled_mask_max_ran(int ncol, int nlay, int ngpt, const Float* randoms, const Float* cloud_frac,
+                                  Bool* cloud_mask) {
+  OpName op_name__(__func__);
+  sampled_mask<false>(ncol, nlay, ngpt, randoms, cloud_frac, nullptr, cloud_mask);
+}
+
+void rrtmgpb_sampled_mask_exp_ran(int ncol, int nlay, int ngpt, const Float* randoms, const Float* cloud_frac,
+                                  const Float* overlap_param, Bool* cloud_mask) {
+  OpName op_name__(__func__);
+  sampled_mask<true>(ncol, nlay, ngpt, randoms, cloud_frac, overlap_param, cloud_mask);
+}
+
+void rrtmgpb_apply_cloud_mask(int ncol, int nlay, int nbnd, int ngpt, const int* band_lims_gpt, const Bool* cloud_mask,
+                              const Float* input_field, Float* sampled_field) {
+  OpName op_name__(__func__);
+  const size_t ncl = (size_t)ncol * nlay, n = ncl * ngpt;
+  DevArg<int> lims(band_lims_gpt, 2 * (size_t)nbnd, Dir::In);
+  DevArg<Bool> m(cloud_mask, n, Dir::In);
+  DevArg<Float> in(input_field, ncl * nbnd, Dir::In), o(sampled_field, n, Dir::Out);
+  const int* pl = lims; const Bool* pm = m; const Float* pi = in; Float* po = o;
+  launch_elementwise(n, [=] __device__(size_t k) {  // :304-312
+    const int g = (int)(k / ncl) + 1; const size_t c = k % ncl;
+    int b = 0;
+    while (b < nbnd - 1 && g > pl[2 * b + 1]) ++b;
+    if (g >= pl[2 * b] && g <= pl[2 * b + 1]) po[k] = pm[k] ? pi[c + ncl * (size_t)b] : (Float)0;
+  });
+}
+
 // ---------------- aerosol optics (mo_aerosol_optics_rrtmgp_merra.F90) ----------------
 void rrtmgpb_aerosol_mask(int ncol, int nlay, const int* type, Bool* aeromsk) {  // :343-347
   OpName op_name__(__func__);

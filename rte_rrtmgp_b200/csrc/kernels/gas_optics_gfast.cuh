@@ -190,8 +190,13 @@ __device__ __forceinline__ void interp3d_g(const Float* __restrict__ tab, int gp
 #ifndef RB_TAU_CELLS
 #define RB_TAU_CELLS 2
 #endif
-#ifndef RB_TAU_MINB
-#define RB_TAU_MINB 3
+// resident blocks per SM the register budget is set for: the LW instantiations (tau only) run best at 4 (128
+// registers; 5.5 -> 5.2 ms at 65,536 x 72 x 256 on B200), the SW ones (tau, ssa, g + Rayleigh + divisions) at 3 (8.4 vs 8.6 ms)
+#ifndef RB_TAU_MINB_LW
+#define RB_TAU_MINB_LW 4
+#endif
+#ifndef RB_TAU_MINB_SW
+#define RB_TAU_MINB_SW 3
 #endif
 constexpr int kTauCells = RB_TAU_CELLS;
 #ifndef RB_TAU_TG
@@ -401,7 +406,7 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
 }
 
 template <bool SW, int VEC, bool AER, int KIND>
-__global__ void __launch_bounds__(kGThreads, RB_TAU_MINB) gas_tau_g_kernel(const FusedParams p, const TablesT tt) {
+__global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_LW) gas_tau_g_kernel(const FusedParams p, const TablesT tt) {
   const rrtmgpb_gas_tables& t = p.t;
   const size_t ncl = (size_t)p.ncol * p.nlay;
   const int ibnd = blockIdx.x % t.nbnd;
@@ -515,8 +520,11 @@ __device__ __forceinline__ void planck_fractions(const FusedParams& p, const Tab
 
 // Grid: 1-D, block = (128 consecutive columns, chunk of layers, band), band fastest.  A thread marches down its
 // layers; per layer the weights are computed once and the band's g-points are produced kGG at a time.
+#ifndef RB_PLANCK_MINB
+#define RB_PLANCK_MINB 4
+#endif
 template <int VEC>
-__global__ void __launch_bounds__(kGThreads, 4) planck_g_kernel(const PlanckFusedParams q, const TablesT tt, int lay_per_chunk,
+__global__ void __launch_bounds__(kGThreads, RB_PLANCK_MINB) planck_g_kernel(const PlanckFusedParams q, const TablesT tt, int lay_per_chunk,
                                                                 int nchunk) {
   const FusedParams& p = q.f;
   const rrtmgpb_gas_tables& t = p.t;

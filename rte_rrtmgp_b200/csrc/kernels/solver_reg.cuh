@@ -519,10 +519,6 @@ struct SwRegParams {
   int gpt_per_block;
 };
 
-// per-(column, layer) quantities derived from mu0, computed once per CTA and kept in lane-private shared-memory slots
-// for all g-points: mu0_s = max(sqrt(eps), mu0) (:1065), 3*mu0_s (first factor of :1079) and 1/mu0_s (for tau/mu0_s, :1092)
-constexpr int kSwMu0Planes = 3;
-
 template <int CL>
 __host__ __device__ constexpr int sw_reg_slots() { return 3 * CL + 4; }  // tau, ssa, g, alb_dir, alb_dif, inc_dir, inc_dif
 
@@ -530,14 +526,14 @@ __host__ __device__ constexpr int sw_reg_slots() { return 3 * CL + 4; }  // tau,
 // of registers and the input prefetch is single-stage (issued when phase A has consumed the slots), so that the
 // kernel fits 168 registers and 68 KB of shared memory: 3 resident CTAs (12 warps) per SM instead of 2.
 template <int CL, bool LEAN>
-__host__ __device__ constexpr int sw_reg_smem_slots() { return (LEAN ? 1 : 2) * sw_reg_slots<CL>() + kSwMu0Planes * CL + (LEAN ? 3 * CL : 0); }
+__host__ __device__ constexpr int sw_reg_smem_slots() { return (LEAN ? 1 : 2) * sw_reg_slots<CL>() + CL + (LEAN ? 3 * CL : 0); }
 
 // TMA variant: the three (16 columns x nlay) input tiles of a g-point arrive by cp.async.bulk.tensor (kernels/tma.cuh),
 // two stages; the four per-(column, g-point) boundary values keep their lane-private cp.async slots.
 struct SwTmaMaps { CUtensorMap tau, ssa, g; };
 template <int CL, bool LEAN>
 __host__ __device__ inline size_t sw_reg_tma_smem(int nlay) {
-  return 2 * 3 * tile_bytes(nlay) + (size_t)(2 * 4 + kSwMu0Planes * CL + (LEAN ? 3 * CL : 0)) * kRegThreads * sizeof(Float) + 2 * sizeof(uint64_t);
+  return 2 * 3 * tile_bytes(nlay) + (size_t)(2 * 4 + CL + (LEAN ? 3 * CL : 0)) * kRegThreads * sizeof(Float) + 2 * sizeof(uint64_t);
 }
 
 // FULL: nlay == 8*CL, every lane's cells are real layers - the padding selects and tests fold away at compile time.
@@ -554,9 +550,9 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
   constexpr int NS = TMA ? 4 : sw_reg_slots<CL>();                // slots per stage
   constexpr int BC0 = TMA ? 0 : 3 * CL;                           // first boundary-value slot
   constexpr int NSTAGE = (LEAN && !TMA) ? 1 : 2;
-  Float* sm_mu0 = sm + (size_t)NSTAGE * NS * kRegThreads;  // [3][CL][thread]: mu0_s, 3*mu0_s, 1/mu0_s; filled once
-  Float* sm_acc = sm_mu0 + (size_t)kSwMu0Planes * CL * kRegThreads + threadIdx.x;  // LEAN: [3][CL][thread]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm_mu0 + (size_t)(kSwMu0Planes * CL + (LEAN ? 3 * CL : 0)) * kRegThreads);  // TMA: [2] mbarriers
+  Float* sm_mu0 = sm + (size_t)NSTAGE * NS * kRegThreads;  // [CL][thread], loaded once
+  Float* sm_acc = sm_mu0 + (size_t)CL * kRegThreads + threadIdx.x;  // LEAN: [3][CL][thread]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm_mu0 + (size_t)(CL + (LEAN ? 3 * CL : 0)) * kRegThreads);  // TMA: [2] mbarriers
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = lane >> 3, j = lane & 7;
   const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
@@ -634,18 +630,11 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
     if (gb + 1 < ge) prefetch(gb + 1, 1);
     cp_async_commit();
   }
-  // mu0 does not depend on the g-point: its clamped value, 3*mu0_s and the reciprocal are computed once, and
-  // "mu0 > 0" (:1122) becomes one bit per cell
-  unsigned lit_mask = 0;
+  // (Tried: mu0_s, 3*mu0_s and 1/mu0_s precomputed per (column, layer) in three shared-memory planes - five fp64
+  // instructions fewer per cell, but 255 registers and two more LDS per cell: 14.3 -> 16.9 ms on B200.)
 #pragma unroll
-  for (int i = 0; i < CL; ++i) {
-    const Float mu0 = p.mu0[(k0 + i < nlay) ? off_lay0 + lay_step * i : off_lay0];
-    const Float mu0_s = fmax(min_mu0, mu0);  // :1065
-    sm_mu0[i * kRegThreads + threadIdx.x] = mu0_s;
-    sm_mu0[(CL + i) * kRegThreads + threadIdx.x] = (Float)3 * mu0_s;
-    sm_mu0[(2 * CL + i) * kRegThreads + threadIdx.x] = rb_rcp(mu0_s);
-    if (mu0 > (Float)0) lit_mask |= 1u << i;
-  }
+  for (int i = 0; i < CL; ++i)
+    sm_mu0[i * kRegThreads + threadIdx.x] = p.mu0[(k0 + i < nlay) ? off_lay0 + lay_step * i : off_lay0];
   const Float mu0_top = p.mu0[(size_t)col + ncol * o.lay(0)];
   const Float mu0_sfc = p.mu0[(size_t)col + ncol * o.lay(nlay - 1)];
 
@@ -680,9 +669,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
       } else {
         tau_s = *RB_SLOT(sm, NS, s, i); w0_s = *RB_SLOT(sm, NS, s, CL + i); g_s = *RB_SLOT(sm, NS, s, 2 * CL + i);
       }
-      const Float mu0_s = sm_mu0[i * kRegThreads + threadIdx.x];
-      const Float mu0_3 = sm_mu0[(CL + i) * kRegThreads + threadIdx.x];
-      const Float mu0_r = sm_mu0[(2 * CL + i) * kRegThreads + threadIdx.x];
+      const Float mu0 = sm_mu0[i * kRegThreads + threadIdx.x];
       const Float gamma1 = ((Float)8 - w0_s * ((Float)5 + (Float)3 * g_s)) * (Float).25;
       const Float gamma2 = (Float)3 * (w0_s * ((Float)1 - g_s)) * (Float).25;
       const Float kk = rb_sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), min_k));
@@ -691,18 +678,17 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
       Float RT_term = rb_rcp(kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau));
       const Float Rdif = RT_term * gamma2 * ((Float)1 - exp_minus2ktau);
       const Float Tdif = RT_term * (Float)2 * kk * exp_minusktau;
+      const Float mu0_s = fmax(min_mu0, mu0);
       const Float k_mu = kk * mu0_s;
       const Float om = (Float)1 - k_mu * k_mu;
       RT_term = rb_div(w0_s * RT_term, fabs(om) >= eps ? om : eps);
-      const Float gamma3 = ((Float)2 - mu0_3 * g_s) * (Float).25;
+      const Float gamma3 = ((Float)2 - (Float)3 * mu0_s * g_s) * (Float).25;
       const Float gamma4 = (Float)1 - gamma3;
       const Float alpha1 = gamma1 * gamma4 + gamma2 * gamma3;
       const Float alpha2 = gamma1 * gamma3 + gamma2 * gamma4;
       const Float k_gamma3 = kk * gamma3;
       const Float k_gamma4 = kk * gamma4;
-      // tau/mu0_s from the stored reciprocal with the residual correction of rb_div (<= 1 ulp)
-      const Float tq = tau_s * mu0_r;
-      const Float Tnoscat = rb_exp<true>(-fma(fma(-mu0_s, tq, tau_s), mu0_r, tq));  // flushes to 0 (night columns, mu0_s = sqrt(eps))
+      const Float Tnoscat = rb_exp<true>(-rb_div(tau_s, mu0_s));  // flushes to 0 (night columns, mu0_s = sqrt(eps))
       Float Rdir = RT_term * (((Float)1 - k_mu) * (alpha2 + k_gamma3) -
                               ((Float)1 + k_mu) * (alpha2 - k_gamma3) * exp_minus2ktau -
                               (Float)2.0 * (k_gamma3 - alpha2 * k_mu) * exp_minusktau * Tnoscat);
@@ -711,7 +697,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
                                (Float)2.0 * (k_gamma4 + alpha1 * k_mu) * exp_minusktau);
       Rdir = fmax((Float)0, fmin(Rdir, ((Float)1 - Tnoscat)));         // :1107
       Tdir = fmax((Float)0, fmin(Tdir, ((Float)1 - Tnoscat - Rdir)));  // :1108
-      const bool lit = live && ((lit_mask >> i) & 1u);  // :1122-1125: no source for diffuse light where mu0 <= 0
+      const bool lit = live && (mu0 > (Float)0);  // :1122-1125: no source for diffuse light where mu0 <= 0
       R[i] = live ? Rdif : (Float)0;
       T[i] = live ? Tdif : (Float)1;
       A3[i] = lit ? Rdir : (Float)0;
