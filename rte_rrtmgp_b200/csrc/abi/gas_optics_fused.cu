@@ -380,9 +380,9 @@ void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, c
     q.sfc_src = sfc_src; q.lay_src = lay_src; q.lev_src = lev_src; q.sfc_source_Jac = sfc_source_Jac;
     KernelTimer timer("planck_fused");
     // layers a thread marches through (its first level needs the Planck fractions of the layer above: 1/lay_per_chunk
-    // redundant work); RRTMGPB_PLANCK_CHUNK overrides for experiments
+    // redundant work; B200, 65,536 x 72: 9 -> 5.40 ms, 12 -> 5.31, 18 -> 5.24, 36 -> 5.22); RRTMGPB_PLANCK_CHUNK overrides
     static const int chunk_env = [] { const char* e = std::getenv("RRTMGPB_PLANCK_CHUNK"); return e ? std::atoi(e) : 0; }();
-    const int lay_per_chunk = chunk_env > 0 ? chunk_env : 9, nchunk = ceil_div(nlay, lay_per_chunk);
+    const int lay_per_chunk = chunk_env > 0 ? chunk_env : 18, nchunk = ceil_div(nlay, lay_per_chunk);
     const unsigned grid = (unsigned)((long long)ceil_div(ncol, kGThreads) * nchunk * t->nbnd);
     if (tt.vec == 2) planck_g_kernel<2><<<grid, kGThreads, 0, stream()>>>(q, tt, lay_per_chunk, nchunk);
     else planck_g_kernel<1><<<grid, kGThreads, 0, stream()>>>(q, tt, lay_per_chunk, nchunk);

@@ -232,7 +232,10 @@ __device__ __forceinline__ Float minor_scaling(const FusedParams& p, const Minor
 // NC cells that share tropo, jtemp and the table rows (row0, row1 => je[0], je[1]) of band `bi`
 // KIND: 0 = optical-property kind and cloud kind read at run time; 1 = the common combination as compile-time constants
 // (LW: 1scl tau += 1scl clouds; SW: 2str incremented by 2str clouds), so the epilogue's kind tests fold away.
-template <bool SW, int VEC, int NC, bool AER, int KIND>
+// CLD (KIND 1 only): false = no cell of the WARP has cloud in this band (ct == 0 in every lane, a warp-uniform fact): the
+// by-band increment then reduces, with identical arithmetic, to ssa = (tau*ssa)/max(eps, tau), g = 0 (its numerator
+// tau*ssa*0 + 0*cw*cg is exactly 0), tau unchanged - one division per value instead of three.
+template <bool SW, int VEC, int NC, bool AER, int KIND, bool CLD = true>
 __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const TablesT& tt, const BandInfo& bi, bool tropo,
                                                int jtemp, int row0, int row1, TauCell (&cell)[NC], const Float* scal) {
   const rrtmgpb_gas_tables& t = p.t;
@@ -351,7 +354,9 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
         if (cell[k].valid) p.tau[o] = to;
       } else {
         auto inc2 = [&](int kind, Float ct, Float cw, Float cg) {
-          if (kind == 1) {                                     // inc_2stream_by_1scalar_bybnd :440-442
+          if (KIND == 1 && !CLD && !AER) {                     // ct == 0: tau12 = to, tauscat12 = to*ss, g stays 0
+            ss = rb_div(to * ss, fmax(eps3, to));
+          } else if (kind == 1) {                                     // inc_2stream_by_1scalar_bybnd :440-442
             const Float tau12 = to + ct;
             ss = rb_div(to * ss, fmax(eps3, tau12));
             to = tau12;
@@ -468,7 +473,18 @@ __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_L
   for (int k = 1; k < kTauCells; ++k)
     shared_rows = shared_rows && tropo[k] == tropo[0] && row0[k] == row0[0] && row1[k] == row1[0];
   if (tropo[0] ? bi.mdiff[0] : bi.mdiff[1]) shared_rows = false;
-  if (shared_rows) {
+  // cloud-free warps (layers above / below the cloud deck, clear regions) take the reduced increment; the test is
+  // warp-uniform, so it costs no divergence
+  bool cloudy = false;
+  if (SW && KIND == 1 && !AER) {
+    bool mine = false;
+#pragma unroll
+    for (int k = 0; k < kTauCells; ++k) mine = mine || cell[k].ct != (Float)0;
+    cloudy = __any_sync(__activemask(), mine);
+  }
+  if (shared_rows && SW && KIND == 1 && !AER && !cloudy) {
+    tau_band_cells<SW, VEC, kTauCells, AER, KIND, false>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell, scal);
+  } else if (shared_rows) {
     tau_band_cells<SW, VEC, kTauCells, AER, KIND>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell, scal);
   } else {
 #pragma unroll
