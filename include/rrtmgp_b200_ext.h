@@ -135,6 +135,15 @@ void rrtmgpb_cloud_optics_from_tables(int ncol, int nlay, int nbnd, int kind, co
                                       Float liq_offset, const Float* extliq, const Float* ssaliq, const Float* asyliq,
                                       int ice_nsteps, Float ice_step_size, Float ice_offset, const Float* extice,
                                       const Float* ssaice, const Float* asyice, Float* tau, Float* ssa, Float* g);
+/* the same, optionally followed in the same pass by clouds%delta_scale() (rte/frontend/mo_optical_props.F90:565-612 ->
+ * delta_scale_2str_k, mo_optical_props_kernels.F90:89-93; 2-stream only), the SW driver's next call
+ * (examples/all-sky/rrtmgp_allsky.F90:350-352): saves one read-modify-write pass over the by-band cloud arrays */
+void rrtmgpb_cloud_optics_from_tables_ds(int ncol, int nlay, int nbnd, int kind, const Float* clwp, const Float* ciwp,
+                                         const Float* reliq, const Float* dgice, int liq_nsteps, Float liq_step_size,
+                                         Float liq_offset, const Float* extliq, const Float* ssaliq, const Float* asyliq,
+                                         int ice_nsteps, Float ice_step_size, Float ice_offset, const Float* extice,
+                                         const Float* ssaice, const Float* asyice, Float* tau, Float* ssa, Float* g,
+                                         int delta_scale);
 /* replaces compute_all_from_table + the optical-property combination of ty_aerosol_optics_rrtmgp_merra%aerosol_optics,
  * rrtmgp/frontend/mo_aerosol_optics_rrtmgp_merra.F90:436-559 and :385-418 (size-bin search, relative-humidity
  * bracket + linear interpolation, per-type table lookup; kind 1: tau = atau - ataussa; kind 2: tau, ssa, g with

@@ -161,6 +161,11 @@ void rrtmgpb_cloud_optics_free(rrtmgpb_cloud_optics_t* co);
 int rrtmgpb_cloud_optics(const rrtmgpb_cloud_optics_t* co, int ncol, int nlay, const Float* clwp, const Float* ciwp,
                          const Float* reliq, const Float* dgice, rrtmgpb_optical_props* optical_props,
                          char* errmsg);
+/* cloud_optics() followed by optical_props%delta_scale() (the SW driver's two calls, rrtmgp_allsky.F90:350-352); with the
+ * one-pass kernel the scaling is applied before the by-band arrays are stored (no second pass over them) */
+int rrtmgpb_cloud_optics_delta_scaled(const rrtmgpb_cloud_optics_t* co, int ncol, int nlay, const Float* clwp,
+                                      const Float* ciwp, const Float* reliq, const Float* dgice,
+                                      rrtmgpb_optical_props* optical_props, int delta_scale, char* errmsg);
 /* 1 (default): cloud_optics() computes masks, table lookups and the liquid+ice combination in one kernel
  * (rrtmgpb_cloud_optics_from_tables); 0: the reference's kernel-by-kernel sequence with its six intermediates. */
 void rrtmgpb_cloud_optics_one_pass(int on);

@@ -420,3 +420,16 @@ void rrtmgpb_cloud_optics_from_tables(int ncol, int nlay, int nbnd, int kind, co
   rrtmgpb_cloud_combine(ncol, nlay, nbnd, kind, w, w + n, w + 2 * n, w + 3 * n, w + 4 * n, w + 5 * n, tau, ssa, g);
   free(w); free(icemsk); free(liqmsk);
 }
+/* ... followed by clouds%delta_scale(): literally the two calls of the reference driver (rrtmgp_allsky.F90:350-352) */
+void rte_delta_scale_2str_k(const int* ncol, const int* nlay, const int* ngpt, Float* tau, Float* ssa, Float* g);
+void rrtmgpb_cloud_optics_from_tables_ds(int ncol, int nlay, int nbnd, int kind, const Float* clwp, const Float* ciwp,
+                                         const Float* reliq, const Float* dgice, int liq_nsteps, Float liq_step_size,
+                                         Float liq_offset, const Float* extliq, const Float* ssaliq, const Float* asyliq,
+                                         int ice_nsteps, Float ice_step_size, Float ice_offset, const Float* extice,
+                                         const Float* ssaice, const Float* asyice, Float* tau, Float* ssa, Float* g,
+                                         int delta_scale) {
+  rrtmgpb_cloud_optics_from_tables(ncol, nlay, nbnd, kind, clwp, ciwp, reliq, dgice, liq_nsteps, liq_step_size, liq_offset,
+                                   extliq, ssaliq, asyliq, ice_nsteps, ice_step_size, ice_offset, extice, ssaice, asyice, tau,
+                                   ssa, g);
+  if (delta_scale && kind == 2) rte_delta_scale_2str_k(&ncol, &nlay, &nbnd, tau, ssa, g);
+}

@@ -134,9 +134,10 @@ class AllSky:
     # -- SW branch (rrtmgp_allsky.F90:340-352,383-406)
     def step_sw(self):
         sw = self.sw
-        if self.do_clouds:
+        if self.do_clouds and self.fused:  # cloud_optics + clouds%delta_scale() in one pass over the by-band arrays
+            sw.co.cloud_optics(self.lwp, self.iwp, self.rel, self.dei, sw.clouds, delta_scale=True)
+        elif self.do_clouds:
             sw.co.cloud_optics(self.lwp, self.iwp, self.rel, self.dei, sw.clouds)
-        if self.do_clouds:
             sw.clouds.delta_scale()
         if self.do_aerosols:
             sw.ao.aerosol_optics(self.aero_type, self.aero_size, self.aero_mass, self.relhum, sw.aerosols)

@@ -6,6 +6,7 @@
 //   rte/kernels/api/mo_gas_optics_utils.F90:7-36          rte_compute_Planck_source_1D/_2D
 // and the frontend loops listed in include/rrtmgp_b200_ext.h (SURVEY.md section 8a').
 // All pure-bandwidth: one coalesced pass, grid-stride, columns innermost.
+#include "../kernels/fastmath.cuh"
 #include "../kernels/elementwise.cuh"
 #include "rte_kernels.h"
 #include "rrtmgp_b200_ext.h"
@@ -487,6 +488,7 @@ struct CloudFusedParams {
   Float liq_step, liq_offset, ice_step, ice_offset;
   const Float *extliq, *ssaliq, *asyliq, *extice, *ssaice, *asyice;
   Float *tau, *ssa, *g;
+  int delta_scale;  // 2-stream only: apply delta_scale_2str_k (mo_optical_props_kernels.F90:89-93) before the store
 };
 __global__ void __launch_bounds__(256) cloud_optics_fused_kernel(const CloudFusedParams p) {
   const size_t ncl = (size_t)p.ncol * p.nlay;
@@ -530,9 +532,22 @@ __global__ void __launch_bounds__(256) cloud_optics_fused_kernel(const CloudFuse
     } else {                               // :412-422
       const Float tt_ = lt + it;
       const Float ts = lts + its;
-      p.g[o] = (ltg + itg) / fmax((Float)RB_EPS, ts);
-      p.ssa[o] = ts / fmax((Float)RB_EPS, tt_);
-      p.tau[o] = tt_;
+      // rb_div (kernels/fastmath.cuh): branch-free, <= 1 ulp; the denominators are >= epsilon resp. 3*tiny, finite, normal.
+      // The compiler's IEEE division sequence made this HBM-bound kernel compute-bound once the delta scaling was added.
+      Float gq = rb_div(ltg + itg, fmax((Float)RB_EPS, ts));
+      Float sq = rb_div(ts, fmax((Float)RB_EPS, tt_));
+      Float tq = tt_;
+      if (p.delta_scale) {  // clouds%delta_scale() (rrtmgp_allsky.F90:352) on the values just computed
+        const Float eps3 = (Float)3.0 * (Float)RB_TINY;
+        const Float fi = gq * gq;
+        const Float wf = sq * fi;
+        tq = ((Float)1 - wf) * tq;
+        sq = rb_div(sq - wf, fmax(eps3, ((Float)1 - wf)));
+        gq = rb_div(gq - fi, fmax(eps3, ((Float)1 - fi)));
+      }
+      p.g[o] = gq;
+      p.ssa[o] = sq;
+      p.tau[o] = tq;
     }
   }
 }
@@ -542,6 +557,17 @@ void rrtmgpb_cloud_optics_from_tables(int ncol, int nlay, int nbnd, int kind, co
                                       Float liq_offset, const Float* extliq, const Float* ssaliq, const Float* asyliq,
                                       int ice_nsteps, Float ice_step_size, Float ice_offset, const Float* extice,
                                       const Float* ssaice, const Float* asyice, Float* tau, Float* ssa, Float* g) {
+  rrtmgpb_cloud_optics_from_tables_ds(ncol, nlay, nbnd, kind, clwp, ciwp, reliq, dgice, liq_nsteps, liq_step_size, liq_offset,
+                                      extliq, ssaliq, asyliq, ice_nsteps, ice_step_size, ice_offset, extice, ssaice, asyice,
+                                      tau, ssa, g, 0);
+}
+
+void rrtmgpb_cloud_optics_from_tables_ds(int ncol, int nlay, int nbnd, int kind, const Float* clwp, const Float* ciwp,
+                                         const Float* reliq, const Float* dgice, int liq_nsteps, Float liq_step_size,
+                                         Float liq_offset, const Float* extliq, const Float* ssaliq, const Float* asyliq,
+                                         int ice_nsteps, Float ice_step_size, Float ice_offset, const Float* extice,
+                                         const Float* ssaice, const Float* asyice, Float* tau, Float* ssa, Float* g,
+                                         int delta_scale) {
   const size_t ncl = (size_t)ncol * nlay, n = ncl * nbnd;
   const size_t nl = (size_t)liq_nsteps * nbnd, ni = (size_t)ice_nsteps * nbnd;
   DevArg<Float> a_lwp(clwp, ncl, Dir::In), a_iwp(ciwp, ncl, Dir::In), a_re(reliq, ncl, Dir::In), a_de(dgice, ncl, Dir::In);
@@ -555,6 +581,7 @@ void rrtmgpb_cloud_optics_from_tables(int ncol, int nlay, int nbnd, int kind, co
   p.ice_step = ice_step_size; p.ice_offset = ice_offset;
   p.extliq = a_el; p.ssaliq = a_sl; p.asyliq = a_al; p.extice = a_ei; p.ssaice = a_si; p.asyice = a_ai;
   p.tau = o_t; p.ssa = o_s; p.g = o_g;
+  p.delta_scale = (delta_scale && kind == 2) ? 1 : 0;
   KernelTimer timer("cloud_optics_fused");
   cloud_optics_fused_kernel<<<ceil_div((long long)ncl, 256), 256, 0, stream()>>>(p);
   RB_LAUNCH_CHECK();

@@ -801,6 +801,12 @@ static int g_cloud_optics_one_pass = 1;  // 0: the reference's kernel-by-kernel 
 
 int rrtmgpb_cloud_optics(const rrtmgpb_cloud_optics_t* co, int ncol, int nlay, const Float* clwp, const Float* ciwp,
                          const Float* reliq, const Float* dgice, rrtmgpb_optical_props* op, char* errmsg) {
+  return rrtmgpb_cloud_optics_delta_scaled(co, ncol, nlay, clwp, ciwp, reliq, dgice, op, 0, errmsg);
+}
+
+int rrtmgpb_cloud_optics_delta_scaled(const rrtmgpb_cloud_optics_t* co, int ncol, int nlay, const Float* clwp,
+                                      const Float* ciwp, const Float* reliq, const Float* dgice, rrtmgpb_optical_props* op,
+                                      int delta_scale, char* errmsg) {
   const rrtmgpb_cloud_lut& h = co->h;
   const int ngpt = h.nbnd;  // by-band tables: ngpt == nbnd
   const size_t ncl = (size_t)ncol * nlay, n = ncl * ngpt;
@@ -826,9 +832,10 @@ int rrtmgpb_cloud_optics(const rrtmgpb_cloud_optics_t* co, int ncol, int nlay, c
   if (!msg.empty()) return fail(errmsg, msg);
   if (op->kind == RRTMGPB_NSTR) return fail(errmsg, "cloud optics: n-stream calculations not yet supported");
   if (g_cloud_optics_one_pass) {  // masks + both table lookups (:373, :380) + combination (:399-424) in one kernel
-    rrtmgpb_cloud_optics_from_tables(ncol, nlay, ngpt, op->kind, clwp, ciwp, reliq, dgice, co->liq_nsteps, co->liq_step_size,
-                                     h.radliq_lwr, co->extliq, co->ssaliq, co->asyliq, co->ice_nsteps, co->ice_step_size,
-                                     h.diamice_lwr, co->extice, co->ssaice, co->asyice, op->tau, op->ssa, op->g);
+    rrtmgpb_cloud_optics_from_tables_ds(ncol, nlay, ngpt, op->kind, clwp, ciwp, reliq, dgice, co->liq_nsteps,
+                                        co->liq_step_size, h.radliq_lwr, co->extliq, co->ssaliq, co->asyliq, co->ice_nsteps,
+                                        co->ice_step_size, h.diamice_lwr, co->extice, co->ssaice, co->asyice, op->tau, op->ssa,
+                                        op->g, delta_scale);
     return ok(errmsg);
   }
   Scratch<Bool> liqmsk(ncl), icemsk(ncl);
@@ -840,6 +847,7 @@ int rrtmgpb_cloud_optics(const rrtmgpb_cloud_optics_t* co, int ncol, int nlay, c
                                 &h.diamice_lwr, co->extice, co->ssaice, co->asyice, itau, itaussa, itaussag);  // :380
   rrtmgpb_cloud_combine(ncol, nlay, ngpt, op->kind, ltau, ltaussa, ltaussag, itau, itaussa, itaussag, op->tau, op->ssa,
                         op->g);  // :399-424
+  if (delta_scale) return rrtmgpb_op_delta_scale(op, nullptr, errmsg);
   return ok(errmsg);
 }
 

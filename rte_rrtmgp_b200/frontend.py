@@ -476,12 +476,14 @@ class CloudOptics:
         self.band_lims_gpt = np.asfortranarray(np.stack([np.arange(1, nb + 1), np.arange(1, nb + 1)]), dtype=np.int32)
         self.band_lims_wvn = lut.band_lims_wvn
 
-    def cloud_optics(self, clwp, ciwp, reliq, dgice, optical_props):
+    def cloud_optics(self, clwp, ciwp, reliq, dgice, optical_props, delta_scale=False):
+        """delta_scale=True: cloud_optics() and optical_props%delta_scale() (rrtmgp_allsky.F90:350-352) in one pass."""
         err = C.create_string_buffer(ERRLEN)
         o = optical_props.struct()
         P = lambda x: C.c_void_p(_addr(x))
-        _check(self.ctx.c.rrtmgpb_cloud_optics(C.c_void_p(self.handle), optical_props.ncol, optical_props.nlay,
-                                               P(clwp), P(ciwp), P(reliq), P(dgice), C.byref(o), err), err)
+        _check(self.ctx.c.rrtmgpb_cloud_optics_delta_scaled(C.c_void_p(self.handle), optical_props.ncol,
+                                                            optical_props.nlay, P(clwp), P(ciwp), P(reliq), P(dgice),
+                                                            C.byref(o), int(bool(delta_scale)), err), err)
 
     def __del__(self):
         try:

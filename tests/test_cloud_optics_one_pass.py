@@ -8,7 +8,7 @@ from rte_rrtmgp_b200 import synthetic as syn
 from rte_rrtmgp_b200.frontend import CloudOptics, Context, OpticalProps
 
 
-def _clouds(lib, device, kind, one_pass, ncol=37, nlay=60, lw=True):
+def _clouds(lib, device, kind, one_pass, ncol=37, nlay=60, lw=True, delta_scale=None):
     ctx = Context(lib, device)
     kd = syn.make_kdist("lw" if lw else "sw", gpt_per_band=2)
     prof = syn.perturbed_profiles(ncol, nlay, seed=21, top_at_1=True)
@@ -21,7 +21,13 @@ def _clouds(lib, device, kind, one_pass, ncol=37, nlay=60, lw=True):
     op = OpticalProps.like(ctx, kind, ncol, nlay, co)
     ctx.c.rrtmgpb_cloud_optics_one_pass(1 if one_pass else 0)
     try:
-        co.cloud_optics(ctx.put(cl["lwp"]), ctx.put(cl["iwp"]), ctx.put(np.asfortranarray(rel)), ctx.put(np.asfortranarray(dei)), op)
+        args = (ctx.put(cl["lwp"]), ctx.put(cl["iwp"]), ctx.put(np.asfortranarray(rel)), ctx.put(np.asfortranarray(dei)), op)
+        if delta_scale == "fused":      # cloud_optics + delta_scale in one call
+            co.cloud_optics(*args, delta_scale=True)
+        else:
+            co.cloud_optics(*args)
+            if delta_scale == "separate":  # the reference driver's two calls (rrtmgp_allsky.F90:350-352)
+                op.delta_scale()
     finally:
         ctx.c.rrtmgpb_cloud_optics_one_pass(1)
     out = {"tau": ctx.get(op.tau)}
@@ -47,3 +53,21 @@ def test_cuda_one_pass_and_sequence_match_oracle(oracle_lib, cuda_lib, kind, lw)
         got = _clouds(cuda_lib, "cuda:0", kind, one_pass, lw=lw)
         for k in ref:
             np.testing.assert_allclose(got[k], ref[k], rtol=1e-13, atol=1e-300, err_msg=f"{k} one_pass={one_pass}")
+
+
+def test_oracle_delta_scaled_is_the_two_calls(oracle_lib):
+    a = _clouds(oracle_lib, None, "2str", True, lw=False, delta_scale="fused")
+    b = _clouds(oracle_lib, None, "2str", False, lw=False, delta_scale="separate")
+    plain = _clouds(oracle_lib, None, "2str", True, lw=False)
+    assert np.any(a["tau"] != plain["tau"])  # the scaling did something
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("one_pass", [True, False])
+def test_cuda_delta_scaled_matches_oracle(oracle_lib, cuda_lib, one_pass):
+    ref = _clouds(oracle_lib, None, "2str", False, lw=False, delta_scale="separate")
+    got = _clouds(cuda_lib, "cuda:0", "2str", one_pass, lw=False, delta_scale="fused")
+    for k in ref:
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-13, atol=1e-300, err_msg=k)
