@@ -431,19 +431,53 @@ void rrtmgpb_compute_optimal_angles(int ncol, int nlay, int ngpt, int nband, con
   });
 }
 
+}  // extern "C"
+namespace {
+// arr_in(nband,ncol) -> arr_out(ncol,ngpt): a block stages the bands of 32 columns (one contiguous run of arr_in) in shared
+// memory, then every warp writes whole 256-byte rows of arr_out (lane = column).  The straightforward mapping read
+// arr_in with a stride of nband words per lane: 0.10 ms per call at 65,536 x 256 on B200, 5x its roofline.
+__global__ void __launch_bounds__(256) expand_transpose_kernel(int ncol, int nband, int ngpt, const int* __restrict__ lims,
+                                                               const Float* __restrict__ in, Float* __restrict__ out) {
+  extern __shared__ Float et_tile[];  // [nband][33]
+  const int col0 = blockIdx.x * 32;
+  const int ncols = min(32, ncol - col0);
+  const Float* src = in + (size_t)nband * col0;
+  for (int k = threadIdx.x; k < nband * ncols; k += blockDim.x) et_tile[(k % nband) * 33 + k / nband] = src[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane >= ncols) return;
+  for (int g = w + 1; g <= ngpt; g += nw) {  // mo_rte_lw.F90:490-500
+    int b = 0;
+    while (b < nband - 1 && g > lims[2 * b + 1]) ++b;
+    if (g >= lims[2 * b] && g <= lims[2 * b + 1]) out[(size_t)(col0 + lane) + (size_t)ncol * (g - 1)] = et_tile[b * 33 + lane];
+  }
+}
+}  // namespace
+extern "C" {
+
 void rrtmgpb_expand_and_transpose(int ncol, int nband, int ngpt, const int* band_lims_gpt,
                                   const Float* arr_in, Float* arr_out) {
   OpName op_name__(__func__);
   const size_t n = (size_t)ncol * ngpt;
+  if (n == 0) return;
   DevArg<int> lims(band_lims_gpt, 2 * (size_t)nband, Dir::In);
   DevArg<Float> in(arr_in, (size_t)nband * ncol, Dir::In), o(arr_out, n, Dir::Out);
-  const int* pl = lims; const Float* pi = in; Float* po = o;
-  launch_elementwise(n, [=] __device__(size_t k) {  // mo_rte_lw.F90:490-500
-    const int g = (int)(k / ncol) + 1; const size_t i = k % ncol;
-    int b = 0;
-    while (b < nband - 1 && g > pl[2 * b + 1]) ++b;
-    if (g >= pl[2 * b] && g <= pl[2 * b + 1]) po[k] = pi[(size_t)b + (size_t)nband * i];
-  });
+  const size_t smem = (size_t)nband * 33 * sizeof(Float);
+  if (smem > 160 * 1024) {  // (hundreds of bands: the plain mapping)
+    const int* pl = lims; const Float* pi = in; Float* po = o;
+    launch_elementwise(n, [=] __device__(size_t k) {
+      const int g = (int)(k / ncol) + 1; const size_t i = k % ncol;
+      int b = 0;
+      while (b < nband - 1 && g > pl[2 * b + 1]) ++b;
+      if (g >= pl[2 * b] && g <= pl[2 * b + 1]) po[k] = pi[(size_t)b + (size_t)nband * i];
+    });
+    return;
+  }
+  KernelTimer timer("rrtmgpb_expand_and_transpose");
+  if (smem > 48 * 1024)
+    RB_CUDA_CHECK(cudaFuncSetAttribute(expand_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  expand_transpose_kernel<<<ceil_div(ncol, 32), 256, smem, stream()>>>(ncol, nband, ngpt, lims, in, o);
+  RB_LAUNCH_CHECK();
 }
 
 void rrtmgpb_cloud_masks(int ncol, int nlay, const Float* clwp, const Float* ciwp, Bool* liqmsk, Bool* icemsk) {
