@@ -507,7 +507,10 @@ __device__ __forceinline__ Float planck_band_f(const rrtmgpb_gas_tables& t, Floa
   return t0 + frac * (t1 - t0);
 }
 
-constexpr int kPG = 2 * kGG;  // g-points per pass of the Planck kernel (previous layer's fractions stay in registers)
+#ifndef RB_PLANCK_PG
+#define RB_PLANCK_PG 2
+#endif
+constexpr int kPG = RB_PLANCK_PG * kGG;  // g-points per pass of the Planck kernel (previous layer's fractions stay in registers)
 
 // interpolation weights and table rows of band `bi` at cell c (:121-168, :390)
 __device__ __forceinline__ void planck_cell_weights(const FusedParams& p, const TablesT& tt, const BandInfo& bi, size_t c,
