@@ -170,6 +170,20 @@ int rrtmgpb_cloud_optics_delta_scaled(const rrtmgpb_cloud_optics_t* co, int ncol
  * (rrtmgpb_cloud_optics_from_tables); 0: the reference's kernel-by-kernel sequence with its six intermediates. */
 void rrtmgpb_cloud_optics_one_pass(int on);
 
+/* ---------------- ty_gas_concs (rte/frontend/gas-optics-template/mo_gas_concentrations.F90) ----------------
+ * Concentrations by gas name, stored as a scalar, a profile (nlay) or a field (ncol,nlay) and broadcast on demand;
+ * set_vmr copies its argument as the reference does.  Array arguments live in BACKEND memory (device pointers for the
+ * CUDA library - like the reference's OpenACC build, which expects device-resident arrays), scalars are passed by value. */
+typedef struct rrtmgpb_gas_concs_t rrtmgpb_gas_concs_t;
+rrtmgpb_gas_concs_t* rrtmgpb_gc_init(int ngas, const char* const* gas_names, char* errmsg);            /* init :96-124 */
+void rrtmgpb_gc_free(rrtmgpb_gas_concs_t* gc);
+int rrtmgpb_gc_set_vmr_scalar(rrtmgpb_gas_concs_t* gc, const char* gas, Float w, char* errmsg);          /* :129-191 */
+int rrtmgpb_gc_set_vmr_1d(rrtmgpb_gas_concs_t* gc, const char* gas, int nlay, const Float* w, char* errmsg); /* :194-246 */
+int rrtmgpb_gc_set_vmr_2d(rrtmgpb_gas_concs_t* gc, const char* gas, int ncol, int nlay, const Float* w,
+                          char* errmsg);                                                              /* :249-305 */
+/* get_vmr_2d :433-504: array(ncol,nlay) <- the stored concentration, broadcast (rrtmgpb_gas_concs_get_vmr) */
+int rrtmgpb_gc_get_vmr(const rrtmgpb_gas_concs_t* gc, const char* gas, int ncol, int nlay, Float* array, char* errmsg);
+
 /* ---------------- ty_aerosol_optics_rrtmgp_merra ---------------- */
 /* Tables as load_lut() receives them (mo_aerosol_optics_rrtmgp_merra.F90:99-123): the rh-dependent ones arrive
  * as (nval,nrh,...) and are transposed to (nrh,nval,...) by load (:178-181).  All pointers HOST. */

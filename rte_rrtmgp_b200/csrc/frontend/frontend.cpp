@@ -854,6 +854,115 @@ int rrtmgpb_cloud_optics_delta_scaled(const rrtmgpb_cloud_optics_t* co, int ncol
 void rrtmgpb_cloud_optics_one_pass(int on) { g_cloud_optics_one_pass = on ? 1 : 0; }
 
 // ------------------------------------------------------------------------------------------------
+// ty_gas_concs: rte/frontend/gas-optics-template/mo_gas_concentrations.F90
+// ------------------------------------------------------------------------------------------------
+struct rrtmgpb_gas_concs_t {
+  struct Conc { int nc = 0, nl = 0; Float* data = nullptr; };  // conc(nc,nl): (1,1), (1,nlay) or (ncol,nlay), backend memory
+  std::vector<std::string> names;
+  std::vector<Conc> concs;
+  int ncol = 0, nlay = 0;
+};
+
+static std::string gc_lower_trim(const char* s) {  // lower_case(trim(gas)), :100,:366
+  std::string r(s ? s : "");
+  while (!r.empty() && r.back() == ' ') r.pop_back();
+  size_t b = 0;
+  while (b < r.size() && r[b] == ' ') ++b;
+  r = r.substr(b);
+  for (char& c : r) if (c >= 'A' && c <= 'Z') c = (char)(c - 'A' + 'a');
+  return r;
+}
+static std::string gc_trim(const char* s) {  // trim(gas), as the reference's messages print it
+  std::string r(s ? s : "");
+  while (!r.empty() && r.back() == ' ') r.pop_back();
+  return r;
+}
+static int gc_find(const rrtmgpb_gas_concs_t* gc, const std::string& name) {  // find_gas, :577-590
+  for (size_t i = 0; i < gc->names.size(); ++i) if (gc->names[i] == name) return (int)i;
+  return -1;
+}
+// (re)allocate the storage of gas igas as conc(nc,nl) and fill it from w (backend memory) or from the scalar
+static void gc_store(rrtmgpb_gas_concs_t* gc, int igas, int nc, int nl, const Float* w, Float scalar) {
+  rrtmgpb_gas_concs_t::Conc& c = gc->concs[igas];
+  if (c.data && (c.nc != nc || c.nl != nl)) { rrtmgpb_mem_free(c.data); c.data = nullptr; }  // :154-161
+  const size_t n = (size_t)nc * nl;
+  if (!c.data) c.data = static_cast<Float*>(rrtmgpb_mem_alloc(n * sizeof(Float)));
+  c.nc = nc; c.nl = nl;
+  if (w) rrtmgpb_mem_copy(c.data, w, n * sizeof(Float));
+  else rrtmgpb_mem_to_backend(c.data, &scalar, sizeof(Float));
+}
+
+rrtmgpb_gas_concs_t* rrtmgpb_gc_init(int ngas, const char* const* gas_names, char* errmsg) {  // init(), :96-124
+  std::vector<std::string> names;
+  for (int i = 0; i < ngas; ++i) {
+    const std::string n = gc_lower_trim(gas_names[i]);
+    if (n.empty()) { fail(errmsg, "ty_gas_concs%init(): must provide non-empty gas names"); return nullptr; }
+    for (const std::string& m : names)
+      if (m == n) { fail(errmsg, "ty_gas_concs%init(): duplicate gas names aren't allowed"); return nullptr; }
+    names.push_back(n);
+  }
+  rrtmgpb_gas_concs_t* gc = new rrtmgpb_gas_concs_t;
+  gc->names = names;
+  gc->concs.resize(names.size());
+  ok(errmsg);
+  return gc;
+}
+
+void rrtmgpb_gc_free(rrtmgpb_gas_concs_t* gc) {
+  if (!gc) return;
+  for (auto& c : gc->concs) rrtmgpb_mem_free(c.data);
+  delete gc;
+}
+
+int rrtmgpb_gc_set_vmr_scalar(rrtmgpb_gas_concs_t* gc, const char* gas, Float w, char* errmsg) {  // :129-191
+  if (w < 0 || w > 1) return fail(errmsg, "ty_gas_concs%set_vmr(): concentrations should be >= 0, <= 1");
+  const int igas = gc_find(gc, gc_lower_trim(gas));
+  if (igas < 0)
+    return fail(errmsg, "ty_gas_concs%set_vmr(): trying to set " + gc_trim(gas) + " but name not provided at initialization");
+  gc_store(gc, igas, 1, 1, nullptr, w);
+  return ok(errmsg);
+}
+
+int rrtmgpb_gc_set_vmr_1d(rrtmgpb_gas_concs_t* gc, const char* gas, int nlay, const Float* w, char* errmsg) {  // :194-246
+  if (g_check_values && rrtmgpb_any_vals_outside((size_t)nlay, w, nullptr, 0, 1))
+    return fail(errmsg, "ty_gas_concs%set_vmr: concentrations should be >= 0, <= 1");
+  if (gc->nlay > 0 && nlay != gc->nlay) return fail(errmsg, "ty_gas_concs%set_vmr: different dimension (nlay)");
+  const int igas = gc_find(gc, gc_lower_trim(gas));
+  if (igas < 0)
+    return fail(errmsg, "ty_gas_concs%set_vmr(): trying to set " + gc_trim(gas) + " but name not provided at initialization");
+  gc->nlay = nlay;
+  gc_store(gc, igas, 1, nlay, w, 0);
+  return ok(errmsg);
+}
+
+int rrtmgpb_gc_set_vmr_2d(rrtmgpb_gas_concs_t* gc, const char* gas, int ncol, int nlay, const Float* w, char* errmsg) {  // :249-305
+  if (g_check_values && rrtmgpb_any_vals_outside((size_t)ncol * nlay, w, nullptr, 0, 1))
+    return fail(errmsg, "ty_gas_concs%set_vmr: concentrations should be >= 0, <= 1");
+  if (gc->ncol > 0 && ncol != gc->ncol) return fail(errmsg, "ty_gas_concs%set_vmr: different dimension (ncol)");
+  if (gc->nlay > 0 && nlay != gc->nlay) return fail(errmsg, "ty_gas_concs%set_vmr: different dimension (nlay)");
+  const int igas = gc_find(gc, gc_lower_trim(gas));
+  if (igas < 0)
+    return fail(errmsg, "ty_gas_concs%set_vmr(): trying to set " + gc_trim(gas) + " but name not provided at initialization");
+  gc->ncol = ncol; gc->nlay = nlay;
+  gc_store(gc, igas, ncol, nlay, w, 0);
+  return ok(errmsg);
+}
+
+int rrtmgpb_gc_get_vmr(const rrtmgpb_gas_concs_t* gc, const char* gas, int ncol, int nlay, Float* array, char* errmsg) {  // :433-504
+  const int igas = gc_find(gc, gc_lower_trim(gas));
+  const std::string name = gc_trim(gas);
+  std::string msg;
+  if (igas < 0) msg = "ty_gas_concs%get_vmr; gas " + name + " not found";
+  else if (!gc->concs[igas].data) msg = "ty_gas_concs%get_vmr; gas " + name + " concentration hasn't been set";
+  if (gc->ncol > 0 && gc->ncol != ncol) msg = "ty_gas_concs%get_vmr; gas " + name + " array is wrong size (ncol)";
+  if (gc->nlay > 0 && gc->nlay != nlay) msg = "ty_gas_concs%get_vmr; gas " + name + " array is wrong size (nlay)";
+  if (!msg.empty()) return fail(errmsg, msg);
+  const rrtmgpb_gas_concs_t::Conc& c = gc->concs[igas];
+  rrtmgpb_gas_concs_get_vmr(ncol, nlay, c.nc, c.nl, c.data, array);
+  return ok(errmsg);
+}
+
+// ------------------------------------------------------------------------------------------------
 // ty_aerosol_optics_rrtmgp_merra (LUT): rrtmgp/frontend/mo_aerosol_optics_rrtmgp_merra.F90
 // ------------------------------------------------------------------------------------------------
 struct rrtmgpb_aerosol_optics_t {

@@ -274,62 +274,56 @@ def draw_samples(ctx, cloud_mask, clouds, clouds_sampled):
 
 
 class GasConcs:
-    """ty_gas_concs (rte/frontend/gas-optics-template/mo_gas_concentrations.F90): concentrations by gas name, each
-    stored as a scalar (1,1), a profile (1,nlay) or a field (ncol,nlay) - set_vmr_scalar/_1d/_2d :129-305 - and
-    broadcast on demand by get_vmr (:433-504).  A host model that keeps its well-mixed gases as scalars (the all-sky
-    example: rrtmgp_allsky.F90:195-203) only ever hands the fields of h2o and o3 to the device."""
+    """ty_gas_concs (rte/frontend/gas-optics-template/mo_gas_concentrations.F90) through its C++ mirror
+    (rrtmgpb_gc_*, include/rrtmgp_b200_frontend.h): concentrations by gas name, each stored as a scalar (1,1), a
+    profile (1,nlay) or a field (ncol,nlay) - set_vmr_scalar/_1d/_2d :129-305 - and broadcast on demand by get_vmr
+    (:433-504).  A host model that keeps its well-mixed gases as scalars (the all-sky example:
+    rrtmgp_allsky.F90:195-203) only ever hands the fields of h2o and o3 to the device."""
 
     def __init__(self, ctx, gas_names):
         self.ctx = ctx
-        self.gas_names = [g.strip().lower() for g in gas_names]  # init(), :96-124
-        self.concs = {}
-        self.ncol = self.nlay = 0
+        ctx.c.rrtmgpb_gc_init.restype = C.c_void_p
+        ctx.c.rrtmgpb_gc_set_vmr_scalar.argtypes = [C.c_void_p, C.c_char_p, FLOAT, C.c_char_p]
+        names = (C.c_char_p * len(gas_names))(*[g.encode() for g in gas_names])
+        err = C.create_string_buffer(ERRLEN)
+        self.handle = ctx.c.rrtmgpb_gc_init(len(gas_names), names, err)
+        if not self.handle:
+            raise RuntimeError(err.value.decode())
 
     def set_vmr(self, gas, w):
-        name = gas.strip().lower()
-        if name not in self.gas_names:
-            raise RuntimeError("ty_gas_concs%set_vmr(): trying to set " + gas.strip() +
-                               " but name not provided at initialization")
+        err = C.create_string_buffer(ERRLEN)
+        h, name = C.c_void_p(self.handle), gas.encode()
         if np.isscalar(w):
-            if w < 0.0 or w > 1.0:  # :140-143
-                raise RuntimeError("ty_gas_concs%set_vmr(): concentrations should be >= 0, <= 1")
-            self.concs[name] = (1, 1, self.ctx.put(np.full((1, 1), float(w))))
+            _check(self.ctx.c.rrtmgpb_gc_set_vmr_scalar(h, name, FLOAT(float(w)), err), err)
             return
+        temporary = isinstance(w, np.ndarray) and self.ctx.device is not None
+        if isinstance(w, np.ndarray):
+            w = self.ctx.put(np.asfortranarray(w, dtype=np.float64))  # backend memory
         nd = w.ndim if isinstance(w, np.ndarray) else w.dim()
-        if nd == 1:  # set_vmr_1d, :194-246
-            nlay = int(w.shape[0])
-            if self.nlay > 0 and nlay != self.nlay:
-                raise RuntimeError("ty_gas_concs%set_vmr: different dimension (nlay)")
-            self.nlay = nlay
-            self.concs[name] = (1, nlay, self.ctx.put(w) if isinstance(w, np.ndarray) else w)
-        else:        # set_vmr_2d, :249-305
-            ncol, nlay = int(w.shape[0]), int(w.shape[1])
-            if self.ncol > 0 and ncol != self.ncol:
-                raise RuntimeError("ty_gas_concs%set_vmr: different dimension (ncol)")
-            if self.nlay > 0 and nlay != self.nlay:
-                raise RuntimeError("ty_gas_concs%set_vmr: different dimension (nlay)")
-            self.ncol, self.nlay = ncol, nlay
-            self.concs[name] = (ncol, nlay, self.ctx.put(w) if isinstance(w, np.ndarray) else w)
+        if nd == 1:
+            _check(self.ctx.c.rrtmgpb_gc_set_vmr_1d(h, name, int(w.shape[0]), C.c_void_p(_addr(w)), err), err)
+        else:
+            _check(self.ctx.c.rrtmgpb_gc_set_vmr_2d(h, name, int(w.shape[0]), int(w.shape[1]), C.c_void_p(_addr(w)), err), err)
+        if temporary:  # the device copy of a host array dies here: the (stream-ordered) copy out of it has to be complete
+            self.ctx.lib.sync()
 
     def get_vmr(self, gas, array, ncol, nlay):
         """get_vmr_2d, :433-504: array(ncol,nlay) <- the stored concentration, broadcast."""
-        name = gas.strip().lower()
-        if name not in self.gas_names:
-            raise RuntimeError("ty_gas_concs%get_vmr; gas " + gas.strip() + " not found")
-        if name not in self.concs:
-            raise RuntimeError("ty_gas_concs%get_vmr; gas " + gas.strip() + " concentration hasn't been set")
-        if self.ncol > 0 and self.ncol != ncol:
-            raise RuntimeError("ty_gas_concs%get_vmr; gas " + gas.strip() + " array is wrong size (ncol)")
-        if self.nlay > 0 and self.nlay != nlay:
-            raise RuntimeError("ty_gas_concs%get_vmr; gas " + gas.strip() + " array is wrong size (nlay)")
-        nc, nl, conc = self.concs[name]
-        self.ctx.c.rrtmgpb_gas_concs_get_vmr(ncol, nlay, nc, nl, C.c_void_p(_addr(conc)), C.c_void_p(_addr(array)))
+        err = C.create_string_buffer(ERRLEN)
+        _check(self.ctx.c.rrtmgpb_gc_get_vmr(C.c_void_p(self.handle), gas.encode(), ncol, nlay, C.c_void_p(_addr(array)), err),
+               err)
 
     def fill_vmr(self, gas_names, vmr):
         """The loop of gas_optics over its gases, mo_gas_optics_rrtmgp.F90:540-545: vmr(:,:,igas) <- get_vmr(name)."""
         ncol, nlay = int(vmr.shape[0]), int(vmr.shape[1])
         for igas, name in enumerate(gas_names):
             self.get_vmr(name, vmr[:, :, igas], ncol, nlay)
+
+    def __del__(self):
+        try:
+            self.ctx.c.rrtmgpb_gc_free(C.c_void_p(self.handle))
+        except Exception:
+            pass
 
 
 class GasOptics:
