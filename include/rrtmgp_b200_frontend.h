@@ -170,6 +170,13 @@ int rrtmgpb_cloud_optics_delta_scaled(const rrtmgpb_cloud_optics_t* co, int ncol
  * (rrtmgpb_cloud_optics_from_tables); 0: the reference's kernel-by-kernel sequence with its six intermediates. */
 void rrtmgpb_cloud_optics_one_pass(int on);
 
+/* compute_optimal_angles (mo_gas_optics_rrtmgp.F90:1503-1562): secant of the LW transport angle per (column, g-point) from
+ * the column transmissivity, the lw_Ds argument of rrtmgpb_rte_lw.  optimal_angle_fit(2,nbnd) comes with the LW
+ * k-distribution (load_int :1040-1045; HOST pointer); optimal_angles(ncol_out, ngpt_out) in backend memory. */
+int rrtmgpb_gas_optics_set_optimal_angle_fit(rrtmgpb_gas_optics_t* go, const Float* optimal_angle_fit, char* errmsg);
+int rrtmgpb_gas_optics_compute_optimal_angles(const rrtmgpb_gas_optics_t* go, const rrtmgpb_optical_props* optical_props,
+                                              int ncol_out, int ngpt_out, Float* optimal_angles, char* errmsg);
+
 /* ---------------- ty_gas_concs (rte/frontend/gas-optics-template/mo_gas_concentrations.F90) ----------------
  * Concentrations by gas name, stored as a scalar, a profile (nlay) or a field (ncol,nlay) and broadcast on demand;
  * set_vmr copies its argument as the reference does.  Array arguments live in BACKEND memory (device pointers for the

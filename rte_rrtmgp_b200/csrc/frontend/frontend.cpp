@@ -442,6 +442,7 @@ struct rrtmgpb_gas_optics_t {
   int *mlg_l, *mlg_u, *im_l, *im_u, *is_l, *is_u, *ks_l, *ks_u;
   Bool *sd_l, *sd_u, *sc_l, *sc_u;
   Float *planck_frac, *totplnk, *krayl, *solar_source;
+  Float* optimal_angle_fit = nullptr;  // (2,nbnd), backend; set by rrtmgpb_gas_optics_set_optimal_angle_fit
 };
 
 rrtmgpb_gas_optics_t* rrtmgpb_gas_optics_load(const rrtmgpb_kdist* t, char* errmsg) {
@@ -494,7 +495,33 @@ void rrtmgpb_gas_optics_free(rrtmgpb_gas_optics_t* go) {
                   go->is_l, go->is_u, go->ks_l, go->ks_u, go->sd_l, go->sd_u, go->sc_l, go->sc_u, go->planck_frac,
                   go->totplnk, go->krayl, go->solar_source};
   for (void* p : ptrs) rrtmgpb_mem_free(p);
+  rrtmgpb_mem_free(go->optimal_angle_fit);
   delete go;
+}
+
+// optimal_angle_fit(2,nbnd) is part of the LW k-distribution files (load_int, mo_gas_optics_rrtmgp.F90:1040-1045); HOST pointer
+int rrtmgpb_gas_optics_set_optimal_angle_fit(rrtmgpb_gas_optics_t* go, const Float* fit, char* errmsg) {
+  if (!go || !fit) return fail(errmsg, "gas_optics%load: optimal_angle_fit missing");
+  const size_t bytes = 2 * (size_t)go->h.nbnd * sizeof(Float);
+  if (!go->optimal_angle_fit) go->optimal_angle_fit = static_cast<Float*>(rrtmgpb_mem_alloc(bytes));
+  rrtmgpb_mem_to_backend(go->optimal_angle_fit, fit, bytes);
+  return ok(errmsg);
+}
+
+// compute_optimal_angles, mo_gas_optics_rrtmgp.F90:1503-1562
+int rrtmgpb_gas_optics_compute_optimal_angles(const rrtmgpb_gas_optics_t* go, const rrtmgpb_optical_props* op, int ncol_out,
+                                              int ngpt_out, Float* optimal_angles, char* errmsg) {
+  const rrtmgpb_kdist& k = go->h;
+  if (!go->optimal_angle_fit) return fail(errmsg, "gas_optics%compute_optimal_angles: no optimal_angle_fit in this k-distribution");
+  bool same = op->ngpt == k.ngpt && op->nband == k.nbnd;  // gpoints_are_equal, :1532
+  for (int i = 0; same && i < 2 * k.nbnd; ++i) same = op->band_lims_gpt[i] == go->band_lims_gpt_h[i];
+  if (!same)
+    return fail(errmsg, "gas_optics%compute_optimal_angles: optical_props has different spectral discretization than gas_optics");
+  if (ncol_out != op->ncol || ngpt_out != op->ngpt)  // :1534-1535
+    return fail(errmsg, "gas_optics%compute_optimal_angles: optimal_angles different dimension (ncol)");
+  rrtmgpb_compute_optimal_angles(op->ncol, op->nlay, op->ngpt, k.nbnd, go->band_lims_gpt, op->tau, go->optimal_angle_fit,
+                                 optimal_angles);
+  return ok(errmsg);
 }
 
 int rrtmgpb_gas_optics_source_is_internal(const rrtmgpb_gas_optics_t* go) { return go->totplnk != nullptr; }

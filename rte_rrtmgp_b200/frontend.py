@@ -418,23 +418,19 @@ class GasOptics:
     def compute_optimal_angles(self, optical_props, optimal_angles=None):
         """ty_gas_optics_rrtmgp%compute_optimal_angles (mo_gas_optics_rrtmgp.F90:1503-1562): secant of the transport
         angle per (column, g-point) from the column transmissivity; feed it to rte_lw(..., lw_Ds=)."""
+        err = C.create_string_buffer(ERRLEN)
         fit = self.kd.extra.get("optimal_angle_fit")
-        if fit is None:
-            raise RuntimeError("gas_optics%compute_optimal_angles: no optimal_angle_fit in this k-distribution")
-        ncol, nlay, ngpt = optical_props.ncol, optical_props.nlay, optical_props.ngpt
-        if ngpt != self.ngpt or not np.array_equal(optical_props.band_lims_gpt, self.band_lims_gpt):  # :1532-1533
-            raise RuntimeError("gas_optics%compute_optimal_angles: optical_props has different spectral "
-                               "discretization than gas_optics")
+        if fit is not None and not getattr(self, "_oa_set", False):
+            fit = np.asfortranarray(fit, dtype=np.float64)
+            _check(self.ctx.c.rrtmgpb_gas_optics_set_optimal_angle_fit(C.c_void_p(self.handle),
+                                                                       C.c_void_p(fit.ctypes.data), err), err)
+            self._oa_set = True
         if optimal_angles is None:
-            optimal_angles = self.ctx.zeros((ncol, ngpt))
-        elif tuple(optimal_angles.shape) != (ncol, ngpt):                                             # :1534-1535
-            raise RuntimeError("gas_optics%compute_optimal_angles: optimal_angles different dimension (ncol)")
-        if not hasattr(self, "_oa_fit"):
-            self._oa_fit = self.ctx.put(np.asfortranarray(fit, dtype=np.float64))
-            self._oa_lims = self.ctx.put(np.asfortranarray(self.band_lims_gpt, dtype=np.int32))
-        self.ctx.c.rrtmgpb_compute_optimal_angles(ncol, nlay, ngpt, self.nband, C.c_void_p(_addr(self._oa_lims)),
-                                                  C.c_void_p(_addr(optical_props.tau)), C.c_void_p(_addr(self._oa_fit)),
-                                                  C.c_void_p(_addr(optimal_angles)))
+            optimal_angles = self.ctx.zeros((optical_props.ncol, optical_props.ngpt))
+        o = optical_props.struct()
+        _check(self.ctx.c.rrtmgpb_gas_optics_compute_optimal_angles(
+            C.c_void_p(self.handle), C.byref(o), int(optimal_angles.shape[0]), int(optimal_angles.shape[1]),
+            C.c_void_p(_addr(optimal_angles)), err), err)
         return optimal_angles
 
     def __del__(self):
