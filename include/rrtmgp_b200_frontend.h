@@ -177,6 +177,20 @@ int rrtmgpb_gas_optics_set_optimal_angle_fit(rrtmgpb_gas_optics_t* go, const Flo
 int rrtmgpb_gas_optics_compute_optimal_angles(const rrtmgpb_gas_optics_t* go, const rrtmgpb_optical_props* optical_props,
                                               int ncol_out, int ngpt_out, Float* optimal_angles, char* errmsg);
 
+/* ---------------- McICA cloud sampling (rte/extensions/mo_cloud_sampling.F90) ----------------
+ * sampled_mask_max_ran (:125-192), sampled_mask_exp_ran (:205-292), draw_samples (:36-120) with their extent and range
+ * checks; every array's extents are passed (C has no size()).  randoms(ngpt,nlay,ncol), cloud_frac(cf_ncol,cf_nlay),
+ * overlap_param(op_ncol,op_nlay), cloud_mask(m_ncol,m_nlay,m_ngpt); arrays in backend memory. */
+int rrtmgpb_cloud_sampling_mask_max_ran(int ngpt, int nlay, int ncol, const Float* randoms, int cf_ncol, int cf_nlay,
+                                        const Float* cloud_frac, int m_ncol, int m_nlay, int m_ngpt, Bool* cloud_mask,
+                                        char* errmsg);
+int rrtmgpb_cloud_sampling_mask_exp_ran(int ngpt, int nlay, int ncol, const Float* randoms, int cf_ncol, int cf_nlay,
+                                        const Float* cloud_frac, int op_ncol, int op_nlay, const Float* overlap_param,
+                                        int m_ncol, int m_nlay, int m_ngpt, Bool* cloud_mask, char* errmsg);
+int rrtmgpb_cloud_sampling_draw_samples(int m_ncol, int m_nlay, int m_ngpt, const Bool* cloud_mask,
+                                        const rrtmgpb_optical_props* clouds, rrtmgpb_optical_props* clouds_sampled,
+                                        char* errmsg);
+
 /* ---------------- ty_gas_concs (rte/frontend/gas-optics-template/mo_gas_concentrations.F90) ----------------
  * Concentrations by gas name, stored as a scalar, a profile (nlay) or a field (ncol,nlay) and broadcast on demand;
  * set_vmr copies its argument as the reference does.  Array arguments live in BACKEND memory (device pointers for the

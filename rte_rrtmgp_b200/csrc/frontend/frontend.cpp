@@ -881,6 +881,72 @@ int rrtmgpb_cloud_optics_delta_scaled(const rrtmgpb_cloud_optics_t* co, int ncol
 void rrtmgpb_cloud_optics_one_pass(int on) { g_cloud_optics_one_pass = on ? 1 : 0; }
 
 // ------------------------------------------------------------------------------------------------
+// McICA cloud sampling: rte/extensions/mo_cloud_sampling.F90 (extents are passed explicitly: C has no size())
+// ------------------------------------------------------------------------------------------------
+static int sampled_mask_checks(const char* who, int ngpt, int nlay, int ncol, int cf_ncol, int cf_nlay, const Float* cloud_frac,
+                               bool exp_ran, int op_ncol, int op_nlay, const Float* overlap_param, int m_ncol, int m_nlay,
+                               int m_ngpt, char* errmsg) {
+  const std::string w(who);
+  if (ncol != cf_ncol || nlay != cf_nlay)  // :142-145 / :224-227
+    return fail(errmsg, w + ": sizes of randoms(ngpt,nlay,ncol) and cloud_frac(ncol,nlay) are inconsistent");
+  if (exp_ran && (ncol != op_ncol || nlay - 1 != op_nlay))  // :228-231
+    return fail(errmsg, w + ": sizes of randoms(ngpt,nlay,ncol) and overlap_param(ncol,nlay-1) are inconsistent");
+  if (ncol != m_ncol || nlay != m_nlay || ngpt != m_ngpt)  // :146-149 / :232-235
+    return fail(errmsg, w + ": sizes of randoms(ngpt,nlay,ncol) and cloud_mask(ncol,nlay,ngpt) are inconsistent");
+  if (rrtmgpb_any_vals_outside((size_t)ncol * nlay, cloud_frac, nullptr, 0, 1))  // :150-153 / :237-240
+    return fail(errmsg, w + ": cloud fraction values out of range [0,1]");
+  if (exp_ran && rrtmgpb_any_vals_outside((size_t)ncol * (nlay - 1), overlap_param, nullptr, -1, 1))  // :241-244
+    return fail(errmsg, w + ": overlap_param values out of range [-1,1]");
+  return ok(errmsg);
+}
+
+int rrtmgpb_cloud_sampling_mask_max_ran(int ngpt, int nlay, int ncol, const Float* randoms, int cf_ncol, int cf_nlay,
+                                        const Float* cloud_frac, int m_ncol, int m_nlay, int m_ngpt, Bool* cloud_mask,
+                                        char* errmsg) {  // sampled_mask_max_ran, :125-192
+  if (sampled_mask_checks("sampled_mask_max_ran", ngpt, nlay, ncol, cf_ncol, cf_nlay, cloud_frac, false, 0, 0, nullptr, m_ncol,
+                          m_nlay, m_ngpt, errmsg))
+    return 1;
+  rrtmgpb_sampled_mask_max_ran(ncol, nlay, ngpt, randoms, cloud_frac, cloud_mask);
+  return ok(errmsg);
+}
+
+int rrtmgpb_cloud_sampling_mask_exp_ran(int ngpt, int nlay, int ncol, const Float* randoms, int cf_ncol, int cf_nlay,
+                                        const Float* cloud_frac, int op_ncol, int op_nlay, const Float* overlap_param,
+                                        int m_ncol, int m_nlay, int m_ngpt, Bool* cloud_mask, char* errmsg) {  // :205-292
+  if (sampled_mask_checks("sampled_mask_exp_ran", ngpt, nlay, ncol, cf_ncol, cf_nlay, cloud_frac, true, op_ncol, op_nlay,
+                          overlap_param, m_ncol, m_nlay, m_ngpt, errmsg))
+    return 1;
+  rrtmgpb_sampled_mask_exp_ran(ncol, nlay, ngpt, randoms, cloud_frac, overlap_param, cloud_mask);
+  return ok(errmsg);
+}
+
+int rrtmgpb_cloud_sampling_draw_samples(int m_ncol, int m_nlay, int m_ngpt, const Bool* cloud_mask,
+                                        const rrtmgpb_optical_props* clouds, rrtmgpb_optical_props* clouds_sampled,
+                                        char* errmsg) {  // draw_samples, :36-120
+  if (!clouds->tau) return fail(errmsg, "draw_samples: cloud optical properties are not initialized");
+  if (!clouds_sampled->tau) return fail(errmsg, "draw_samples: sampled cloud optical properties are not initialized");
+  if (clouds->kind == RRTMGPB_NSTR) return fail(errmsg, "draw_samples: sampling isn't implemented yet for ty_optical_props_nstr");
+  if (clouds->kind != clouds_sampled->kind)
+    return fail(errmsg, "draw_samples: by-band and sampled cloud properties need to be the same variable type");
+  if (!bands_are_equal(clouds, clouds_sampled))
+    return fail(errmsg, "draw_samples: by-band and sampled cloud properties spectral structure is different");
+  const int ncol = clouds->ncol, nlay = clouds->nlay, nbnd = clouds->nband, ngpt = clouds_sampled->ngpt;
+  if (m_ncol != ncol || m_nlay != nlay || m_ngpt != ngpt)
+    return fail(errmsg, "draw_samples: cloud mask and cloud optical properties have different ncol, nlay and/or ngpt");
+  if (clouds_sampled->ncol != ncol || clouds_sampled->nlay != nlay)
+    return fail(errmsg, "draw_samples: sampled/unsampled cloud optical properties have different ncol and/or nlay");
+  // band limits of the sampled object live on the host: stage them once for the three calls
+  Scratch<int> lims(2 * (size_t)nbnd);
+  rrtmgpb_mem_to_backend(lims, clouds_sampled->band_lims_gpt, 2 * (size_t)nbnd * sizeof(int));
+  rrtmgpb_apply_cloud_mask(ncol, nlay, nbnd, ngpt, lims, cloud_mask, clouds->tau, clouds_sampled->tau);  // :104
+  if (clouds->kind == RRTMGPB_2STR) {                                                                     // :108-118
+    rrtmgpb_apply_cloud_mask(ncol, nlay, nbnd, ngpt, lims, cloud_mask, clouds->ssa, clouds_sampled->ssa);
+    rrtmgpb_apply_cloud_mask(ncol, nlay, nbnd, ngpt, lims, cloud_mask, clouds->g, clouds_sampled->g);
+  }
+  return ok(errmsg);
+}
+
+// ------------------------------------------------------------------------------------------------
 // ty_gas_concs: rte/frontend/gas-optics-template/mo_gas_concentrations.F90
 // ------------------------------------------------------------------------------------------------
 struct rrtmgpb_gas_concs_t {

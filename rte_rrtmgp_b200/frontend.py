@@ -214,63 +214,42 @@ def rte_sw_bygpoint(ctx, atmos, mu0, inc_flux, sfc_alb_dir, sfc_alb_dif, gpt_up,
                                          C.c_void_p(_addr(gpt_dir)), C.c_void_p(_addr(inc_flux_dif)), err), err)
 
 
-# ---- McICA cloud sampling: rte/extensions/mo_cloud_sampling.F90 -------------------------------------------------------
-def _sampled_mask(ctx, which, randoms, cloud_frac, overlap_param, cloud_mask):
+# ---- McICA cloud sampling: rte/extensions/mo_cloud_sampling.F90 (C++ mirror: rrtmgpb_cloud_sampling_*) ----------------
+def _sampled_mask(ctx, randoms, cloud_frac, overlap_param, cloud_mask):
     ngpt, nlay, ncol = (int(v) for v in randoms.shape)
-    if (ncol, nlay) != tuple(int(v) for v in cloud_frac.shape):
-        raise RuntimeError(f"sampled_mask_{which}: sizes of randoms(ngpt,nlay,ncol) and cloud_frac(ncol,nlay) are inconsistent")
-    if overlap_param is not None and (ncol, nlay - 1) != tuple(int(v) for v in overlap_param.shape):
-        raise RuntimeError(f"sampled_mask_{which}: sizes of randoms(ngpt,nlay,ncol) and overlap_param(ncol,nlay-1) "
-                           "are inconsistent")
     if cloud_mask is None:
         cloud_mask = ctx.zeros((ncol, nlay, ngpt), dtype=np.bool_)
-    elif (ncol, nlay, ngpt) != tuple(int(v) for v in cloud_mask.shape):
-        raise RuntimeError(f"sampled_mask_{which}: sizes of randoms(ngpt,nlay,ncol) and cloud_mask(ncol,nlay,ngpt) "
-                           "are inconsistent")
     P = lambda x: C.c_void_p(_addr(x))
-    if ctx.c.rrtmgpb_any_vals_outside(C.c_size_t(ncol * nlay), P(cloud_frac), None, FLOAT(0.0), FLOAT(1.0)):
-        raise RuntimeError(f"sampled_mask_{which}: cloud fraction values out of range [0,1]")
-    if overlap_param is not None:
-        if ctx.c.rrtmgpb_any_vals_outside(C.c_size_t(ncol * (nlay - 1)), P(overlap_param), None, FLOAT(-1.0), FLOAT(1.0)):
-            raise RuntimeError(f"sampled_mask_{which}: overlap_param values out of range [-1,1]")
-        ctx.c.rrtmgpb_sampled_mask_exp_ran(ncol, nlay, ngpt, P(randoms), P(cloud_frac), P(overlap_param), P(cloud_mask))
+    err = C.create_string_buffer(ERRLEN)
+    cf, m = [int(v) for v in cloud_frac.shape], [int(v) for v in cloud_mask.shape]
+    if overlap_param is None:
+        rc = ctx.c.rrtmgpb_cloud_sampling_mask_max_ran(ngpt, nlay, ncol, P(randoms), cf[0], cf[1], P(cloud_frac), m[0], m[1],
+                                                       m[2], P(cloud_mask), err)
     else:
-        ctx.c.rrtmgpb_sampled_mask_max_ran(ncol, nlay, ngpt, P(randoms), P(cloud_frac), P(cloud_mask))
+        op = [int(v) for v in overlap_param.shape]
+        rc = ctx.c.rrtmgpb_cloud_sampling_mask_exp_ran(ngpt, nlay, ncol, P(randoms), cf[0], cf[1], P(cloud_frac), op[0], op[1],
+                                                       P(overlap_param), m[0], m[1], m[2], P(cloud_mask), err)
+    _check(rc, err)
     return cloud_mask
 
 
 def sampled_mask_max_ran(ctx, randoms, cloud_frac, cloud_mask=None):
     """mo_cloud_sampling.F90:125-192: McICA mask for maximum-random overlap.  randoms(ngpt,nlay,ncol)."""
-    return _sampled_mask(ctx, "max_ran", randoms, cloud_frac, None, cloud_mask)
+    return _sampled_mask(ctx, randoms, cloud_frac, None, cloud_mask)
 
 
 def sampled_mask_exp_ran(ctx, randoms, cloud_frac, overlap_param, cloud_mask=None):
     """mo_cloud_sampling.F90:205-292: McICA mask for exponential-random overlap; overlap_param(ncol,nlay-1)."""
-    return _sampled_mask(ctx, "exp_ran", randoms, cloud_frac, overlap_param, cloud_mask)
+    return _sampled_mask(ctx, randoms, cloud_frac, overlap_param, cloud_mask)
 
 
 def draw_samples(ctx, cloud_mask, clouds, clouds_sampled):
     """mo_cloud_sampling.F90:36-120: by-band cloud properties -> by-g-point properties, zero where the mask is false."""
-    if clouds.kind == KNSTR:
-        raise RuntimeError("draw_samples: sampling isn't implemented yet for ty_optical_props_nstr")
-    if clouds.kind != clouds_sampled.kind:
-        raise RuntimeError("draw_samples: by-band and sampled cloud properties need to be the same variable type")
-    if clouds.nband != clouds_sampled.nband or (
-            clouds.band_lims_wvn is not None and clouds_sampled.band_lims_wvn is not None
-            and not np.array_equal(clouds.band_lims_wvn, clouds_sampled.band_lims_wvn)):
-        raise RuntimeError("draw_samples: by-band and sampled cloud properties spectral structure is different")
-    ncol, nlay, nbnd, ngpt = clouds.ncol, clouds.nlay, clouds.nband, clouds_sampled.ngpt
-    if tuple(int(v) for v in cloud_mask.shape) != (ncol, nlay, ngpt):
-        raise RuntimeError("draw_samples: cloud mask and cloud optical properties have different ncol, nlay and/or ngpt")
-    if (clouds_sampled.ncol, clouds_sampled.nlay) != (ncol, nlay):
-        raise RuntimeError("draw_samples: sampled/unsampled cloud optical properties have different ncol and/or nlay")
-    lims = ctx.put(np.asfortranarray(clouds_sampled.band_lims_gpt, dtype=np.int32))
-    P = lambda x: C.c_void_p(_addr(x))
-    fields = [("tau",)] if clouds.kind == K1SCL else [("tau",), ("ssa",), ("g",)]
-    for (name,) in fields:
-        ctx.c.rrtmgpb_apply_cloud_mask(ncol, nlay, nbnd, ngpt, P(lims), P(cloud_mask), P(getattr(clouds, name)),
-                                       P(getattr(clouds_sampled, name)))
-    ctx.lib.sync()  # `lims` is a temporary
+    err = C.create_string_buffer(ERRLEN)
+    a, b = clouds.struct(), clouds_sampled.struct()
+    m = [int(v) for v in cloud_mask.shape]
+    _check(ctx.c.rrtmgpb_cloud_sampling_draw_samples(m[0], m[1], m[2], C.c_void_p(_addr(cloud_mask)), C.byref(a), C.byref(b),
+                                                     err), err)
 
 
 class GasConcs:
