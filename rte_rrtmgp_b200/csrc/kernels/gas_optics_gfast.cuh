@@ -191,7 +191,8 @@ __device__ __forceinline__ void interp3d_g(const Float* __restrict__ tab, int gp
 #define RB_TAU_CELLS 2
 #endif
 // resident blocks per SM the register budget is set for: the LW instantiations (tau only) run best at 4 (128
-// registers; 5.5 -> 5.2 ms at 65,536 x 72 x 256 on B200), the SW ones (tau, ssa, g + Rayleigh + divisions) at 3 (8.4 vs 8.6 ms)
+// registers; 5.5 -> 5.2 ms at 65,536 x 72 x 256 on B200; 5 blocks: 5.7, 6 blocks: 6.4 - spills), the SW ones (tau, ssa, g +
+// Rayleigh + divisions) at 3 (8.4 vs 8.6 ms)
 #ifndef RB_TAU_MINB_LW
 #define RB_TAU_MINB_LW 4
 #endif
