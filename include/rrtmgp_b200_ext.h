@@ -32,7 +32,9 @@ void rrtmgpb_mem_free(void* p);
 void rrtmgpb_mem_to_backend(void* dst_backend, const void* src_host, size_t bytes);
 void rrtmgpb_mem_to_host(void* dst_host, const void* src_backend, size_t bytes);
 void rrtmgpb_mem_copy(void* dst_backend, const void* src_backend, size_t bytes);
-/* CUDA: all kernels are launched on this stream (default: the legacy default stream). */
+/* CUDA: the launch stream of the CALLING HOST THREAD (every thread has its own; default cudaStreamPerThread, which
+ * orders itself against the legacy default stream).  Entry points may be called concurrently from several host
+ * threads on disjoint arrays; each thread's work is ordered on its own stream. */
 void rrtmgpb_set_stream(void* cuda_stream);
 void* rrtmgpb_get_stream(void);
 void rrtmgpb_set_device(int device);
@@ -50,6 +52,13 @@ int rrtmgpb_profile_report(char* buf, size_t buflen);
  * allocation lives and release it through rrtmgpb_mem_free (the C++ frontend mirror switches it on around its own
  * calls); per host thread, default 0. */
 void rrtmgpb_abi_table_cache(int on);
+/* Lifetime contract of the g-point-fastest table copies (fused gas optics, and the kernel-by-kernel entry points while
+ * rrtmgpb_abi_table_cache(1) is in effect): they are derived from the k-distribution arrays on first use, keyed by the
+ * kmajor pointer and reused while every table pointer and dimension is unchanged.  A host that REFILLS a table in
+ * place, or frees tables with anything other than rrtmgpb_mem_free() and allocates a new k-distribution of the same
+ * shape, must call this before the next gas-optics call: kmajor = that k-distribution's kmajor array, or NULL to drop
+ * every cached copy. */
+void rrtmgpb_tables_changed(const void* kmajor);
 
 /* ---------------- physical constants ---------------- */
 /* replaces mo_gas_optics_constants.F90:42-51 init_constants(); NULL keeps the current value */
@@ -57,10 +66,10 @@ void rrtmgpb_init_constants(const Float* gravity, const Float* mol_weight_dry_ai
                             const Float* heat_capacity_dry_air);
 
 /* ---------------- solver options ---------------- */
-/* lw_solver_2stream level-source selection.  0 (default): reference DEFAULT-kernel behaviour,
- * every g-point uses g-point 1's level source (mo_rte_solver_kernels.F90:422 passes the rank-3
- * array to a rank-2 dummy); 1: per-g-point level source as in the reference's accel kernels
- * (accel/mo_rte_solver_kernels.F90:958-962). */
+/* lw_solver_2stream level-source selection.  1 (default of the CUDA library): per-g-point level source as in the
+ * reference's accelerator kernels (accel/mo_rte_solver_kernels.F90:958-962); 0 (default of the oracle): the serial
+ * DEFAULT kernel's behaviour, every g-point uses g-point 1's level source (mo_rte_solver_kernels.F90:422 passes the
+ * rank-3 array to a rank-2 dummy) - kept for bit-parity tests against the serial kernels only. */
 void rrtmgpb_set_lw_2stream_lev_source_per_gpt(int on);
 
 /* Solver kernel family: 0 (default) = register-resident warp-systolic kernels when nlay <= 80 (shared-memory

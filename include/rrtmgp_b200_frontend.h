@@ -115,6 +115,9 @@ typedef struct {
 typedef struct rrtmgpb_gas_optics_t rrtmgpb_gas_optics_t;
 rrtmgpb_gas_optics_t* rrtmgpb_gas_optics_load(const rrtmgpb_kdist* tables, char* errmsg);
 void rrtmgpb_gas_optics_free(rrtmgpb_gas_optics_t* go);
+/* Backend address of the loaded kmajor(ntemp,neta,npres+1,ngpt) table.  A host that overwrites the loaded coefficients
+ * in place (rrtmgpb_mem_to_backend) passes it to rrtmgpb_tables_changed() afterwards (rrtmgp_b200_ext.h). */
+Float* rrtmgpb_gas_optics_kmajor(const rrtmgpb_gas_optics_t* go);
 int rrtmgpb_gas_optics_source_is_internal(const rrtmgpb_gas_optics_t* go);
 
 /* gas_optics_int(): mo_gas_optics_rrtmgp.F90:220-330.  play,tlay (ncol,nlay); plev (ncol,nlay+1);

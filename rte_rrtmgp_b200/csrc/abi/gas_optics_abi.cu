@@ -478,10 +478,11 @@ void tau_absorption_impl(int ncol, int nlay, int nbnd, int ngpt, int ngas, int n
       a_isl(idx_minor_scaling_lower, nminorlower, Dir::In), a_isu(idx_minor_scaling_upper, nminorupper, Dir::In),
       a_ksl(kminor_start_lower, nminorlower, Dir::In), a_ksu(kminor_start_upper, nminorupper, Dir::In);
   DevArg<Bool> a_tr(tropo, ncl, Dir::In);
-  DevArg<Float> a_cm(col_mix, 2 * ncl * nflav, Dir::In), a_fj(fmajor, 8 * ncl * nflav, Dir::In),
-      a_fn(fminor, 4 * ncl * nflav, Dir::In), a_pl(play, ncl, Dir::In), a_tl(tlay, ncl, Dir::In),
+  // (16- / 8-byte alignment: the kernels read these with 128- / 64-bit loads; see DevArg)
+  DevArg<Float> a_cm(col_mix, 2 * ncl * nflav, Dir::In, true, 16), a_fj(fmajor, 8 * ncl * nflav, Dir::In, true, 16),
+      a_fn(fminor, 4 * ncl * nflav, Dir::In, true, 16), a_pl(play, ncl, Dir::In), a_tl(tlay, ncl, Dir::In),
       a_cg(col_gas, ncl * (ngas + 1), Dir::In);
-  DevArg<int> a_je(jeta, 2 * ncl * nflav, Dir::In), a_jt(jtemp, ncl, Dir::In), a_jp(jpress, ncl, Dir::In);
+  DevArg<int> a_je(jeta, 2 * ncl * nflav, Dir::In, true, 8), a_jt(jtemp, ncl, Dir::In), a_jp(jpress, ncl, Dir::In);
   DevArg<Float> a_tau(tau, ncl * ngpt, accumulate ? Dir::InOut : Dir::Out);
   TauAbsParams p;
   p.ncol = ncol; p.nlay = nlay; p.nbnd = nbnd; p.ngpt = ngpt; p.ngas = ngas; p.nflav = nflav; p.neta = neta;
@@ -533,9 +534,9 @@ void rrtmgp_interpolation(const int* ncol, const int* nlay, const int* ngas, con
   DevArg<Float> a_prl(press_ref_log, *npres, Dir::In), a_tr(temp_ref, *ntemp, Dir::In),
       a_vr(vmr_ref, 2 * (size_t)(*ngas + 1) * *ntemp, Dir::In), a_pl(play, ncl, Dir::In), a_tl(tlay, ncl, Dir::In),
       a_cg(col_gas, ncl * (*ngas + 1), Dir::In);
-  DevArg<int> a_jt(jtemp, ncl, Dir::Out), a_je(jeta, 2 * ncl * nf, Dir::Out), a_jp(jpress, ncl, Dir::Out);
-  DevArg<Float> a_fj(fmajor, 8 * ncl * nf, Dir::Out), a_fn(fminor, 4 * ncl * nf, Dir::Out),
-      a_cm(col_mix, 2 * ncl * nf, Dir::Out);
+  DevArg<int> a_jt(jtemp, ncl, Dir::Out), a_je(jeta, 2 * ncl * nf, Dir::Out, true, 8), a_jp(jpress, ncl, Dir::Out);
+  DevArg<Float> a_fj(fmajor, 8 * ncl * nf, Dir::Out, true, 16), a_fn(fminor, 4 * ncl * nf, Dir::Out, true, 16),
+      a_cm(col_mix, 2 * ncl * nf, Dir::Out, true, 16);
   DevArg<Bool> a_tp(tropo, ncl, Dir::Out);
   InterpParams p;
   p.ncol = *ncol; p.nlay = *nlay; p.ngas = *ngas; p.nflav = *nflav; p.neta = *neta; p.npres = *npres; p.ntemp = *ntemp;
@@ -598,8 +599,8 @@ void rrtmgp_compute_tau_rayleigh(const int* ncol, const int* nlay, const int* nb
   const size_t ncl = (size_t)*ncol * *nlay, nf = (size_t)*nflav;
   DevArg<int> a_gf(gpoint_flavor, 2 * (size_t)*ngpt, Dir::In), a_bl(band_lims_gpt, 2 * (size_t)*nbnd, Dir::In);
   DevArg<Float> a_kr(krayl, (size_t)*ntemp * *neta * *ngpt * 2, Dir::In), a_cd(col_dry, ncl, Dir::In),
-      a_cg(col_gas, ncl * (*ngas + 1), Dir::In), a_fn(fminor, 4 * ncl * nf, Dir::In);
-  DevArg<int> a_je(jeta, 2 * ncl * nf, Dir::In), a_jt(jtemp, ncl, Dir::In);
+      a_cg(col_gas, ncl * (*ngas + 1), Dir::In), a_fn(fminor, 4 * ncl * nf, Dir::In, true, 16);
+  DevArg<int> a_je(jeta, 2 * ncl * nf, Dir::In, true, 8), a_jt(jtemp, ncl, Dir::In);
   DevArg<Bool> a_tp(tropo, ncl, Dir::In);
   DevArg<Float> a_out(tau_rayleigh, ncl * *ngpt, Dir::Out);
   RaylParams p;
@@ -624,9 +625,9 @@ void rrtmgp_compute_Planck_source(const int* ncol, const int* nlay, const int* n
   (void)gpoint_bands;
   const size_t nc = (size_t)*ncol, ncl = nc * *nlay, nclp = nc * (*nlay + 1), nf = (size_t)*nflav, ng = (size_t)*ngpt;
   DevArg<Float> a_tl(tlay, ncl, Dir::In), a_tv(tlev, nclp, Dir::In), a_ts(tsfc, nc, Dir::In),
-      a_fj(fmajor, 8 * ncl * nf, Dir::In), a_pf(pfracin, (size_t)*ntemp * *neta * (*npres + 1) * ng, Dir::In),
+      a_fj(fmajor, 8 * ncl * nf, Dir::In, true, 16), a_pf(pfracin, (size_t)*ntemp * *neta * (*npres + 1) * ng, Dir::In),
       a_tp(totplnk, (size_t)*nPlanckTemp * *nbnd, Dir::In);
-  DevArg<int> a_je(jeta, 2 * ncl * nf, Dir::In), a_jt(jtemp, ncl, Dir::In), a_jp(jpress, ncl, Dir::In),
+  DevArg<int> a_je(jeta, 2 * ncl * nf, Dir::In, true, 8), a_jt(jtemp, ncl, Dir::In), a_jp(jpress, ncl, Dir::In),
       a_bl(band_lims_gpt, 2 * (size_t)*nbnd, Dir::In), a_gf(gpoint_flavor, 2 * ng, Dir::In);
   DevArg<Bool> a_tr(tropo, ncl, Dir::In);
   DevArg<Float> o_sfc(sfc_src, nc * ng, Dir::Out), o_lay(lay_src, ncl * ng, Dir::Out),

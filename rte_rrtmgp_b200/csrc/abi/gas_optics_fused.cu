@@ -108,7 +108,17 @@ struct TableCacheEntry {
   TablesT tt;
   std::vector<void*> owned;
   int ntemp, neta, npres, ngpt, nkl, nku, nbnd, nflav;
+  // every array the copies and the host-resolved records were derived from: an entry is only reused when ALL of them
+  // are the same allocations (a new k-distribution that happens to reuse the kmajor address does not match unless
+  // it reuses all of them - and then rrtmgpb_tables_changed() is the caller's explicit invalidation)
+  const void* src[16];
 };
+void table_sources(const rrtmgpb_gas_tables& t, const void* (&src)[16]) {
+  const void* v[16] = {t.kmajor, t.planck_frac, t.kminor_lower, t.kminor_upper, t.krayl, t.band_lims_gpt, t.gpoint_flavor,
+                       t.flavor, t.vmr_ref, t.minor_limits_gpt_lower, t.minor_limits_gpt_upper, t.kminor_start_lower,
+                       t.kminor_start_upper, t.idx_minor_lower, t.idx_minor_upper, t.totplnk};
+  for (int i = 0; i < 16; ++i) src[i] = v[i];
+}
 std::mutex g_tc_mutex;
 std::map<const void*, TableCacheEntry> g_table_cache;  // key: the loader-layout kmajor pointer
 
@@ -171,8 +181,10 @@ TablesT tables_gfast(const rrtmgpb_gas_tables& t) {
   auto it = g_table_cache.find(t.kmajor);
   if (it != g_table_cache.end()) {
     const TableCacheEntry& e = it->second;
+    const void* src[16];
+    table_sources(t, src);
     if (e.ntemp == t.ntemp && e.neta == t.neta && e.npres == t.npres && e.ngpt == t.ngpt && e.nkl == t.nminorklower &&
-        e.nku == t.nminorkupper && e.nbnd == t.nbnd && e.nflav == t.nflav)
+        e.nku == t.nminorkupper && e.nbnd == t.nbnd && e.nflav == t.nflav && std::equal(src, src + 16, e.src))
       return e.tt;
     for (void* q : e.owned) dev_free(q);
     g_table_cache.erase(it);
@@ -180,6 +192,7 @@ TablesT tables_gfast(const rrtmgpb_gas_tables& t) {
   TableCacheEntry e;
   e.ntemp = t.ntemp; e.neta = t.neta; e.npres = t.npres; e.ngpt = t.ngpt; e.nkl = t.nminorklower; e.nku = t.nminorkupper;
   e.nbnd = t.nbnd; e.nflav = t.nflav;
+  table_sources(t, e.src);
   const int tn = t.ntemp * t.neta, rows = tn * (t.npres + 1);
   TablesT& tt = e.tt;
   tt.maxm = 1;
@@ -295,6 +308,7 @@ bool tables_gfast_abi(const Float* kmajor, const Float* kminor_lower, const Floa
     e.tt.kmajor = transposed(kmajor, 1, tn * (npres + 1), ngpt, e.tt.gp, e.owned);
     e.tt.kminor_lower = transposed(kminor_lower, 1, tn, nkl, e.tt.nkl, e.owned);
     e.tt.kminor_upper = transposed(kminor_upper, 1, tn, nku, e.tt.nku, e.owned);
+    RB_CUDA_CHECK(cudaStreamSynchronize(stream()));  // other host threads (other streams) may use the copies next
     it = g_abi_cache.emplace(kmajor, e).first;
   }
   const TablesT& tt = it->second.tt;
@@ -324,6 +338,19 @@ void table_cache_release_abi(const void* key) {
   g_abi_cache.erase(it);
 }
 void fused_set_constants(double grav, double m_dry) { g_grav = grav; g_m_dry = m_dry; }
+}
+
+extern "C" void rrtmgpb_tables_changed(const void* kmajor) {
+  if (kmajor) {
+    table_cache_release(kmajor);
+    table_cache_release_abi(kmajor);
+    return;
+  }
+  std::lock_guard<std::mutex> lock(g_tc_mutex);
+  for (auto& kv : g_table_cache) for (void* q : kv.second.owned) dev_free(q);
+  for (auto& kv : g_abi_cache) for (void* q : kv.second.owned) dev_free(q);
+  g_table_cache.clear();
+  g_abi_cache.clear();
 }
 
 extern "C" {

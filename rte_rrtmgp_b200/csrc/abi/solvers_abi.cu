@@ -17,6 +17,8 @@
 //     mo_rte_solver_kernels.F90:216-218,601-604) - deterministic, no atomics - and are written once.
 //   * `intent(out)` arrays whose controlling flag is false are decoys that may alias:
 //     they are never read or written here and no pointer is __restrict__.
+#include <atomic>
+#include <climits>
 #include <cstdlib>
 #include "../kernels/elementwise.cuh"
 #include "../kernels/solver_reg.cuh"
@@ -28,8 +30,12 @@ using namespace rrtmgpb;
 namespace {
 
 constexpr int kSolverThreads = 256;
-static int g_lw2s_lev_per_gpt = 0;
-static int g_solver_variant = 0;  // 0: register/warp-systolic kernels when nlay <= 80, else tiles; 1: always tiles
+// process-wide switches, set once at start-up (atomics: safe to read from concurrently calling host threads)
+// lev_source per g-point is the DEFAULT: an accelerator backend should reproduce the reference's accelerator kernels
+// (accel/mo_rte_solver_kernels.F90:958-962), not the sequence-association slip of the serial CPU kernel
+// (mo_rte_solver_kernels.F90:422), which stays reachable with rrtmgpb_set_lw_2stream_lev_source_per_gpt(0)
+static std::atomic<int> g_lw2s_lev_per_gpt{1};
+static std::atomic<int> g_solver_variant{0};  // 0: register/warp-systolic kernels when nlay <= 80, else tiles; 1: always tiles
 
 struct Orient {
   int nlay;
@@ -548,8 +554,11 @@ void launch_tile(K kern, const P& p, dim3 grid, size_t smem, const char* name) {
 
 
 // register-resident kernels: chunk length CL = ceil(nlay/8) in {8,9,10}
-inline int reg_chunk_len(int nlay) {
-  if (g_solver_variant != 0) return 0;
+inline int reg_chunk_len(int nlay, int ncol) {
+  if (g_solver_variant.load(std::memory_order_relaxed) != 0) return 0;
+  // the register kernels use 32-bit in-plane offsets (kernels/solver_reg.cuh): planes of 2^31 elements or more go to
+  // the tile kernels, whose indices are 64-bit
+  if ((long long)ncol * (nlay + 1) > (long long)INT_MAX) return 0;
   if (nlay <= 64) return 8;
   if (nlay <= 72) return 9;
   if (nlay <= 80) return 10;
@@ -606,10 +615,10 @@ void rrtmgpb_fastmath_probe(int n, const double* x, double* e, double* s, double
   RB_LAUNCH_CHECK();
 }
 
-void rrtmgpb_set_solver_variant(int v) { g_solver_variant = v; }
-int rrtmgpb_get_solver_variant(void) { return g_solver_variant; }
+void rrtmgpb_set_solver_variant(int v) { g_solver_variant.store(v); }
+int rrtmgpb_get_solver_variant(void) { return g_solver_variant.load(); }
 
-void rrtmgpb_set_lw_2stream_lev_source_per_gpt(int on) { g_lw2s_lev_per_gpt = on ? 1 : 0; }
+void rrtmgpb_set_lw_2stream_lev_source_per_gpt(int on) { g_lw2s_lev_per_gpt.store(on ? 1 : 0); }
 
 void rte_lw_solver_noscat(const int* ncol_, const int* nlay_, const int* ngpt_, const Bool* top_at_1,
                           const int* nmus_, const Float* Ds, const Float* weights, const Float* tau,
@@ -634,7 +643,7 @@ void rte_lw_solver_noscat(const int* ncol_, const int* nlay_, const int* ngpt_, 
   p.sfc_src = a_ss; p.inc_flux = a_inc; p.flux_up = a_fu; p.flux_dn = a_fd; p.do_broadband = bb; p.bb_up = a_bu;
   p.bb_dn = a_bd; p.do_jac = jac; p.sfc_srcJac = a_sj; p.flux_upJac = a_fj; p.do_rescaling = resc; p.ssa = a_ssa;
   p.g = a_g;
-  if (const int cl = resc ? 0 : reg_chunk_len(nlay)) {
+  if (const int cl = resc ? 0 : reg_chunk_len(nlay, ncol)) {
     LwNoscatRegParams q;
     q.ncol = ncol; q.nlay = nlay; q.ngpt = ngpt; q.top_at_1 = p.top_at_1; q.nmus = nmus; q.Ds = p.Ds;
     q.weights = p.weights; q.tau = p.tau; q.lay_source = p.lay_source; q.lev_source = p.lev_source;
@@ -710,10 +719,10 @@ void rte_lw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
       a_ss(sfc_src, ncg, Dir::In), a_inc(inc_flux, ncg, Dir::In);
   DevArg<Float> a_fu(flux_up, nclp * ngpt, Dir::Out), a_fd(flux_dn, nclp * ngpt, Dir::Out);
   Lw2sParams p;
-  p.ncol = ncol; p.nlay = nlay; p.ngpt = ngpt; p.top_at_1 = *top_at_1 ? 1 : 0; p.lev_per_gpt = g_lw2s_lev_per_gpt;
+  p.ncol = ncol; p.nlay = nlay; p.ngpt = ngpt; p.top_at_1 = *top_at_1 ? 1 : 0; p.lev_per_gpt = g_lw2s_lev_per_gpt.load();
   p.tau = a_tau; p.ssa = a_ssa; p.g = a_g; p.lay_source = a_lay; p.lev_source = a_lev; p.sfc_emis = a_em;
   p.sfc_src = a_ss; p.inc_flux = a_inc; p.flux_up = a_fu; p.flux_dn = a_fd;
-  if (const int cl = reg_chunk_len(nlay)) {
+  if (const int cl = reg_chunk_len(nlay, ncol)) {
     Lw2sRegParams q;
     q.ncol = ncol; q.nlay = nlay; q.ngpt = ngpt; q.top_at_1 = p.top_at_1; q.lev_per_gpt = p.lev_per_gpt;
     q.tau = p.tau; q.ssa = p.ssa; q.g = p.g; q.lay_source = p.lay_source; q.lev_source = p.lev_source;
@@ -791,7 +800,7 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
   p.tau = a_tau; p.ssa = a_ssa; p.g = a_g; p.mu0 = a_mu; p.sfc_alb_dir = a_ad; p.sfc_alb_dif = a_af;
   p.inc_flux_dir = a_inc; p.flux_up = a_fu; p.flux_dn = a_fd; p.flux_dir = a_fr; p.has_dif_bc = bc;
   p.inc_flux_dif = a_dif; p.do_broadband = bb; p.bb_up = a_bu; p.bb_dn = a_bd; p.bb_dir = a_br;
-  if (const int cl = reg_chunk_len(nlay)) {
+  if (const int cl = reg_chunk_len(nlay, ncol)) {
     SwRegParams q;
     q.ncol = ncol; q.nlay = nlay; q.ngpt = ngpt; q.top_at_1 = p.top_at_1; q.tau = p.tau; q.ssa = p.ssa; q.g = p.g;
     q.mu0 = p.mu0; q.sfc_alb_dir = p.sfc_alb_dir; q.sfc_alb_dif = p.sfc_alb_dif; q.inc_flux_dir = p.inc_flux_dir;

@@ -1,6 +1,7 @@
 // common.cuh - runtime plumbing shared by every kernel file of librte_rrtmgp_b200.so
 //
-// * one launch stream (set by the host program, e.g. torch's current stream)
+// * one launch stream PER HOST THREAD (cudaStreamPerThread until the thread calls rrtmgpb_set_stream, e.g. with
+//   torch's current stream): the entry points are re-entrant across host threads (runtime.cu)
 // * CUDA errors abort: the reference kernels are `subroutine`s with no error path
 //   (SURVEY.md section 8b "Errors"), so a failed launch must never be silently ignored
 // * DevIn/DevOut/DevInOut: pointer provenance at the ABI.  The Fortran frontend hands the
@@ -13,6 +14,7 @@
 #include <cstdlib>
 #include <cstddef>
 #include <cfloat>
+#include <cstdint>
 #include "rte_types.h"
 
 namespace rrtmgpb {
@@ -42,6 +44,7 @@ struct KernelTimer {
   KernelTimer(const KernelTimer&) = delete;
   KernelTimer& operator=(const KernelTimer&) = delete;
   int slot;
+  void* b_;  // the closing event (cudaEvent_t)
 };
 
 // Name of the ABI entry point currently executing (labels its elementwise launches in the profiler).
@@ -75,19 +78,26 @@ enum class Dir { In, Out, InOut };
 template <typename T>
 class DevArg {
  public:
-  DevArg(const T* p, size_t count, Dir dir, bool used = true) : host_(const_cast<T*>(p)), n_(count), dir_(dir) {
+  // align: byte alignment the kernel's vector loads / stores assume for this array (0: element alignment).  A Fortran
+  // host may pass array sections or arrays at their natural 4- / 8-byte alignment: a DEVICE pointer that does not meet
+  // `align` is staged through an aligned scratch copy as well (device-to-device), instead of faulting in the kernel.
+  DevArg(const T* p, size_t count, Dir dir, bool used = true, size_t align = 0)
+      : host_(const_cast<T*>(p)), n_(count), dir_(dir), on_device_(false) {
     if (!used || p == nullptr || count == 0) { dev_ = const_cast<T*>(p); staged_ = false; return; }
-    if (is_device_ptr(p)) { dev_ = const_cast<T*>(p); staged_ = false; return; }
+    on_device_ = is_device_ptr(p);
+    if (on_device_ && (align == 0 || reinterpret_cast<uintptr_t>(p) % align == 0)) {
+      dev_ = const_cast<T*>(p); staged_ = false; return;
+    }
     staged_ = true;
     dev_ = static_cast<T*>(dev_alloc(n_ * sizeof(T)));
     if (dir_ != Dir::Out)
-      RB_CUDA_CHECK(cudaMemcpyAsync(dev_, host_, n_ * sizeof(T), cudaMemcpyHostToDevice, stream()));
+      RB_CUDA_CHECK(cudaMemcpyAsync(dev_, host_, n_ * sizeof(T), cudaMemcpyDefault, stream()));
   }
   ~DevArg() {
     if (!staged_) return;
     if (dir_ != Dir::In) {
-      RB_CUDA_CHECK(cudaMemcpyAsync(host_, dev_, n_ * sizeof(T), cudaMemcpyDeviceToHost, stream()));
-      RB_CUDA_CHECK(cudaStreamSynchronize(stream()));
+      RB_CUDA_CHECK(cudaMemcpyAsync(host_, dev_, n_ * sizeof(T), cudaMemcpyDefault, stream()));
+      if (!on_device_) RB_CUDA_CHECK(cudaStreamSynchronize(stream()));  // host results are valid at return
     }
     dev_free(dev_);
   }
@@ -103,6 +113,7 @@ class DevArg {
   size_t n_;
   Dir dir_;
   bool staged_;
+  bool on_device_;
 };
 
 template <typename T> using In = DevArg<T>;

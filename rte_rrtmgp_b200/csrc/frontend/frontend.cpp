@@ -20,6 +20,7 @@
 //     a ty_gas_concs object;
 //   * when the caller wants broadband fluxes the absorption kernel ASSIGNS tau (extension symbol) instead
 //     of zero_array + accumulate, saving two plane passes; results are identical.
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -32,8 +33,9 @@
 
 namespace {
 
-bool g_check_extents = true;  // mo_rte_config.F90:25-26
-bool g_check_values = true;
+// process-wide like the module variables of mo_rte_config.F90:25-26; atomics, so host threads may read them concurrently
+std::atomic<bool> g_check_extents{true};
+std::atomic<bool> g_check_values{true};
 
 int fail(char* errmsg, const std::string& msg) {
   if (errmsg) {
@@ -524,6 +526,8 @@ int rrtmgpb_gas_optics_compute_optimal_angles(const rrtmgpb_gas_optics_t* go, co
   return ok(errmsg);
 }
 
+/* backend address of the loaded kmajor table: the key of the g-point-fastest copies (rrtmgpb_tables_changed) */
+Float* rrtmgpb_gas_optics_kmajor(const rrtmgpb_gas_optics_t* go) { return go ? go->kmajor : nullptr; }
 int rrtmgpb_gas_optics_source_is_internal(const rrtmgpb_gas_optics_t* go) { return go->totplnk != nullptr; }
 
 // Interpolation intermediates shared by compute_gas_taus and source (frontend locals in the reference,
@@ -824,7 +828,7 @@ void rrtmgpb_cloud_optics_free(rrtmgpb_cloud_optics_t* co) {
   delete co;
 }
 
-static int g_cloud_optics_one_pass = 1;  // 0: the reference's kernel-by-kernel sequence (rrtmgpb_cloud_optics_one_pass)
+static std::atomic<int> g_cloud_optics_one_pass{1};  // 0: the reference's kernel-by-kernel sequence (rrtmgpb_cloud_optics_one_pass)
 
 int rrtmgpb_cloud_optics(const rrtmgpb_cloud_optics_t* co, int ncol, int nlay, const Float* clwp, const Float* ciwp,
                          const Float* reliq, const Float* dgice, rrtmgpb_optical_props* op, char* errmsg) {

@@ -1,4 +1,11 @@
 // runtime.cu - backend plumbing of the CUDA library (include/rrtmgp_b200_ext.h, first section)
+//
+// Threading contract (SURVEY 8b "Threading / re-entrancy"): the reference kernels are serial and stateless, so a host
+// may call them concurrently from many threads on disjoint column blocks (its own OpenMP-over-blocks idiom,
+// examples/rfmip-clear-sky/rrtmgp_rfmip_lw.F90:177-178).  Here every HOST THREAD has its own launch stream
+// (thread_local; cudaStreamPerThread until the thread calls rrtmgpb_set_stream), scratch is allocated and freed
+// stream-ordered on that stream, the profiler's records are guarded by a mutex, table caches by theirs, and the
+// process-wide switches (solver variant, checks, ...) are atomics that are meant to be set once at start-up.
 #include <algorithm>
 #include <atomic>
 #include <mutex>
@@ -12,25 +19,33 @@
 namespace rrtmgpb {
 
 thread_local const char* tl_op_name = nullptr;
-static cudaStream_t g_stream = nullptr;  // legacy default stream until the host sets one
+// cudaStreamPerThread is a blocking stream: it orders itself against the legacy default stream, so hosts that mix this
+// library with legacy-stream work (torch's default stream, plain cudaMemcpy) keep the ordering they had
+static thread_local cudaStream_t tl_stream = cudaStreamPerThread;
 static std::atomic<long long> g_launches{0};
 
-cudaStream_t stream() { return g_stream; }
+cudaStream_t stream() { return tl_stream; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-static std::once_flag g_pool_once;
+// keep freed scratch in the pool instead of returning it to the driver after every sync - once per DEVICE
+static std::atomic<unsigned long long> g_pool_ready{0};  // bit d: device d's default pool is configured
+static std::mutex g_pool_mutex;
 static void init_pool() {
-  // keep freed scratch in the pool instead of returning it to the driver after every sync
   int dev = 0;
   RB_CUDA_CHECK(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (g_pool_ready.load(std::memory_order_acquire) & bit) return;
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  if (g_pool_ready.load(std::memory_order_relaxed) & bit) return;
   cudaMemPool_t pool;
   RB_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
   unsigned long long thresh = ~0ull;
   RB_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  g_pool_ready.fetch_or(bit, std::memory_order_release);
 }
 
 void* dev_alloc(size_t bytes) {
-  std::call_once(g_pool_once, init_pool);
+  init_pool();
   void* p = nullptr;
   RB_CUDA_CHECK(cudaMallocAsync(&p, bytes ? bytes : 16, stream()));
   return p;
@@ -39,24 +54,27 @@ void dev_free(void* p) {
   if (p) RB_CUDA_CHECK(cudaFreeAsync(p, stream()));
 }
 
-// ---- per-kernel event timing -----------------------------------------------------------------
+// ---- per-kernel event timing (records of all threads in one list, guarded by a mutex) -----------
 struct TimerRec { const char* name; cudaEvent_t a, b; };
-static bool g_profile = false;
+static std::atomic<bool> g_profile{false};
+static std::mutex g_prof_mutex;
 static std::vector<TimerRec> g_recs;
 static std::vector<cudaEvent_t> g_free_events;
-static cudaEvent_t get_event() {
+static cudaEvent_t get_event() {  // g_prof_mutex held
   if (!g_free_events.empty()) { cudaEvent_t e = g_free_events.back(); g_free_events.pop_back(); return e; }
   cudaEvent_t e; RB_CUDA_CHECK(cudaEventCreate(&e)); return e;
 }
-KernelTimer::KernelTimer(const char* name) : slot(-1) {
-  if (!g_profile) return;
+KernelTimer::KernelTimer(const char* name) : slot(-1), b_(nullptr) {
+  if (!g_profile.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   TimerRec r{name, get_event(), get_event()};
   RB_CUDA_CHECK(cudaEventRecord(r.a, stream()));
   g_recs.push_back(r);
   slot = (int)g_recs.size() - 1;
+  b_ = r.b;
 }
 KernelTimer::~KernelTimer() {
-  if (slot >= 0) RB_CUDA_CHECK(cudaEventRecord(g_recs[slot].b, stream()));
+  if (slot >= 0) RB_CUDA_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(b_), stream()));
 }
 
 bool is_device_ptr(const void* p) {
@@ -88,17 +106,20 @@ void rrtmgpb_mem_to_host(void* d, const void* s, size_t n) {
 void rrtmgpb_mem_copy(void* d, const void* s, size_t n) {
   RB_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, stream()));
 }
-void rrtmgpb_set_stream(void* s) { g_stream = static_cast<cudaStream_t>(s); }
-void* rrtmgpb_get_stream(void) { return g_stream; }
+/* the CALLING THREAD's launch stream (every host thread has its own; default cudaStreamPerThread) */
+void rrtmgpb_set_stream(void* s) { tl_stream = static_cast<cudaStream_t>(s); }
+void* rrtmgpb_get_stream(void) { return tl_stream; }
 void rrtmgpb_set_device(int d) { RB_CUDA_CHECK(cudaSetDevice(d)); }
 void rrtmgpb_sync(void) { RB_CUDA_CHECK(cudaStreamSynchronize(stream())); }
-void rrtmgpb_profile_enable(int on) { g_profile = on != 0; }
+void rrtmgpb_profile_enable(int on) { g_profile.store(on != 0); }
 // Writes "name count total_ms\n" per kernel (sorted by time) into buf; clears the records.
 int rrtmgpb_profile_report(char* buf, size_t buflen) {
   RB_CUDA_CHECK(cudaStreamSynchronize(stream()));
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   std::map<std::string, std::pair<int, double>> agg;
   for (auto& r : g_recs) {
     float ms = 0;
+    RB_CUDA_CHECK(cudaEventSynchronize(r.b));  // records of other host threads' streams
     RB_CUDA_CHECK(cudaEventElapsedTime(&ms, r.a, r.b));
     auto& e = agg[r.name];
     e.first += 1; e.second += ms;

@@ -145,17 +145,26 @@ def test_cuda_aerosol_optics_vs_oracle(oracle_lib, cuda_lib, kind):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("lw_2stream", [False, True])
+@pytest.mark.parametrize("lw_2stream", [False, True, "quirk"])
 @pytest.mark.parametrize("ncol,nlay", [(26, 72), (35, 60)])
 def test_allsky_with_aerosols(oracle_lib, cuda_lib, ncol, nlay, lw_2stream):
     """BASELINE config 5 at test size: clouds + aerosols; LW either no-scattering or two-stream (g-point fluxes
-    summed with rte_sum_broadband).  The LW two-stream default keeps the reference default kernels' level-source
-    quirk (mo_rte_solver_kernels.F90:422) on both sides."""
+    summed with rte_sum_broadband).  LW two-stream is compared in both level-source modes: per g-point (the CUDA
+    library's default = the reference's accelerator kernels, accel/mo_rte_solver_kernels.F90:958-962; the oracle is
+    switched to it) and "quirk" (the serial default kernels' sequence association, mo_rte_solver_kernels.F90:422 = the
+    oracle's default; the CUDA library is switched to it)."""
     kd_lw, kd_sw = syn.make_kdist("lw"), syn.make_kdist("sw")
     runs = []
+    per_gpt = 0 if lw_2stream == "quirk" else 1
+    lw_2stream = bool(lw_2stream)
     for lib, dev in ((oracle_lib, None), (cuda_lib, "cuda:0")):
-        a = AllSky(Context(lib, dev), ncol, nlay, kd_lw, kd_sw, do_aerosols=True, lw_2stream=lw_2stream)
-        a.step()
+        lib.cdll.rrtmgpb_set_lw_2stream_lev_source_per_gpt(per_gpt)
+        try:
+            a = AllSky(Context(lib, dev), ncol, nlay, kd_lw, kd_sw, do_aerosols=True, lw_2stream=lw_2stream)
+            a.step()
+            lib.sync()
+        finally:  # defaults: oracle = the serial reference kernels' behaviour, CUDA = per g-point
+            lib.cdll.rrtmgpb_set_lw_2stream_lev_source_per_gpt(0 if dev is None else 1)
         runs.append(a)
     c, g = runs
     fc, fg = c.fluxes_host(), g.fluxes_host()

@@ -23,6 +23,7 @@ def _inputs():
         -np.abs(rng.standard_cauchy(20000)) * 3.0,        # the solvers' exp arguments: -tau*k, -tau/mu0
         -10.0 ** rng.uniform(-300, 2.8, 20000),           # tiny ... -630
         10.0 ** rng.uniform(-12, 2.8, 10000),             # positive (sqrt / rcp / div operands)
+        np.array([-2.0e9, -3.0e9, -1.0e15, -1.0e200, -746.0, -709.0]),  # |x*log2(e)| beyond the int range: must still flush to 0
         np.array([-708.0, -707.9, -1e-320 - 1e-300, -0.0 - 1e-17, -1.0, -0.5, 1e-12, 2.220446049250313e-12, 1.0, 4.0]),
     ])
     return np.ascontiguousarray(x[(np.abs(x) > 1e-300) & (np.abs(x) < 1e300)])
@@ -46,6 +47,7 @@ def test_fastmath_within_2ulp(oracle_lib, cuda_lib):
     ref = _probe(oracle_lib, x)
     got = _probe(cuda_lib, x)
     sel = x >= -708.0  # below: flushed to 0 by design (true values are subnormal)
+    assert np.all(got[0][x < -708.001] == 0.0)  # however negative (the power of two must not wrap around)
     for name, g, r, m in (("exp", got[0], ref[0], sel), ("sqrt", got[1], ref[1], np.ones_like(sel)),
                           ("rcp", got[2], ref[2], np.ones_like(sel)), ("div", got[3], ref[3], np.ones_like(sel))):
         u = _ulps(g[m], r[m])

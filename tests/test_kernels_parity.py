@@ -71,8 +71,9 @@ def test_lw_solver_noscat(oracle_lib, cuda_lib, variant, top_at_1, nmus, bb, jac
 @pytest.mark.parametrize("top_at_1", [True, False])
 @pytest.mark.parametrize("per_gpt", [0, 1])
 def test_lw_solver_2stream(oracle_lib, cuda_lib, variant, top_at_1, per_gpt):
-    """per_gpt = 0: the reference DEFAULT kernels' behaviour (every g-point uses g-point 1's level source,
-    mo_rte_solver_kernels.F90:422); 1: per-g-point level sources as in the reference's accel kernels."""
+    """per_gpt = 0: the reference's serial DEFAULT kernels' behaviour (every g-point uses g-point 1's level source,
+    mo_rte_solver_kernels.F90:422; the oracle's default); 1: per-g-point level sources as in the reference's accel
+    kernels (the CUDA library's default)."""
     x = _lw_inputs(19, 33, 4, seed=5, scattering=True)
     ncol, nlay, ngpt = x["tau"].shape
 
@@ -83,7 +84,7 @@ def test_lw_solver_2stream(oracle_lib, cuda_lib, variant, top_at_1, per_gpt):
         lib.rte_lw_solver_2stream(ncol, nlay, ngpt, top_at_1, d(x["tau"]), d(x["ssa"]), d(x["g"]), d(x["lay"]),
                                   d(x["lev"]), d(x["emis"]), d(x["sfc"]), d(x["inc"]), gup, gdn)
         lib.sync()
-        lib.cdll.rrtmgpb_set_lw_2stream_lev_source_per_gpt(0)
+        lib.cdll.rrtmgpb_set_lw_2stream_lev_source_per_gpt(0 if device is None else 1)  # each library's default
         return rc.host(gup), rc.host(gdn)
 
     cuda_lib.cdll.rrtmgpb_set_solver_variant(variant)
@@ -93,6 +94,63 @@ def test_lw_solver_2stream(oracle_lib, cuda_lib, variant, top_at_1, per_gpt):
     # cancellation amplifies last-bit differences (FMA contraction) to ~1e-10 relative
     _close(got[0], ref[0], "flux_up", rtol=2e-9)
     _close(got[1], ref[1], "flux_dn", rtol=2e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [0, 1])
+def test_solvers_with_opaque_layers(oracle_lib, cuda_lib, variant):
+    """Optical depths of 1e9 .. 1e13: -tau*D, -tau*k and -tau/mu0 times log2(e) exceed the int range of the lean exp's
+    power-of-two extraction - the transmittance must still be 0 (libm underflows), not a wrapped-around huge value."""
+    cuda_lib.cdll.rrtmgpb_set_solver_variant(variant)
+    try:
+        x = _lw_inputs(21, 37, 5, seed=12)
+        x["tau"][3, 5, :] = 1.0e13
+        x["tau"][7, 20, 2] = 3.0e9
+        ref = _run_lw_noscat(oracle_lib, None, x, True, 1, True, False, False)
+        got = _run_lw_noscat(cuda_lib, "cuda:0", x, True, 1, True, False, False)
+        for k in ref:
+            assert np.all(np.isfinite(got[k]))
+            _close(got[k], ref[k], k)
+        y = _sw_inputs(23, 41, 6, seed=4)
+        y["tau"][2, 11, :] = 1.0e13
+        y["tau"][9, 30, 1] = 5.0e9
+        ncol, nlay, ngpt = y["tau"].shape
+        res = {}
+        for name, lib, device in (("ref", oracle_lib, None), ("gpu", cuda_lib, "cuda:0")):
+            d = lambda a: rc.dev(a, device)
+            decoy = fzeros((ncol, nlay + 1, ngpt), device=device)
+            bup, bdn, bdr = (fzeros((ncol, nlay + 1), device=device) for _ in range(3))
+            lib.rte_sw_solver_2stream(ncol, nlay, ngpt, True, d(y["tau"]), d(y["ssa"]), d(y["g"]), d(y["mu0"]), d(y["adir"]),
+                                      d(y["adif"]), d(y["inc"]), decoy, decoy, decoy, False, d(y["dif"]), True, bup, bdn, bdr)
+            lib.sync()
+            res[name] = [rc.host(o) for o in (bup, bdn, bdr)]
+        for a, b, n in zip(res["gpu"], res["ref"], ("up", "dn", "dir")):
+            assert np.all(np.isfinite(a))
+            _close(a, b, n)
+    finally:
+        cuda_lib.cdll.rrtmgpb_set_solver_variant(0)
+
+
+@pytest.mark.gpu
+def test_lw_solver_2stream_default_is_per_gpoint_level_source(oracle_lib, cuda_lib):
+    """Out of the box the CUDA library indexes lev_source per g-point like the reference's accelerator kernels
+    (accel/mo_rte_solver_kernels.F90:958-962); the serial kernel's g-point-1 quirk is opt-in."""
+    x = _lw_inputs(19, 33, 4, seed=6, scattering=True)
+    ncol, nlay, ngpt = x["tau"].shape
+    out = {}
+    for name, lib, device in (("ref", oracle_lib, None), ("gpu", cuda_lib, "cuda:0")):
+        if device is None:
+            lib.cdll.rrtmgpb_set_lw_2stream_lev_source_per_gpt(1)
+        d = lambda a: rc.dev(a, device)
+        gup, gdn = fzeros((ncol, nlay + 1, ngpt), device=device), fzeros((ncol, nlay + 1, ngpt), device=device)
+        lib.rte_lw_solver_2stream(ncol, nlay, ngpt, True, d(x["tau"]), d(x["ssa"]), d(x["g"]), d(x["lay"]),
+                                  d(x["lev"]), d(x["emis"]), d(x["sfc"]), d(x["inc"]), gup, gdn)
+        lib.sync()
+        if device is None:
+            lib.cdll.rrtmgpb_set_lw_2stream_lev_source_per_gpt(0)
+        out[name] = (rc.host(gup), rc.host(gdn))
+    _close(out["gpu"][0], out["ref"][0], "flux_up", rtol=2e-9)
+    _close(out["gpu"][1], out["ref"][1], "flux_dn", rtol=2e-9)
 
 
 def _sw_inputs(ncol, nlay, ngpt, seed):
