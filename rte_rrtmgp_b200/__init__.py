@@ -21,6 +21,10 @@ def lib():
     CPU fallback."""
     global _LIB
     if _LIB is None:
+        path = os.environ.get("RRTMGPB_LIB", LIB_PATH)  # A/B measurements of build variants (tools/build_variant.py)
+        if path != LIB_PATH:
+            _LIB = KernelLib(path)
+            return _LIB
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -80,14 +80,35 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #ifndef RB_HANDOFF_SCAN
 #define RB_HANDOFF_SCAN 1
 #endif
+// 1: the scan steps are branch-free - lanes without a partner d chunks away combine with the IDENTITY map (selected on
+// the integer pipe) instead of skipping the step under a divergent branch (BRA/BSYNC pairs and partially active fp64
+// instructions in round 1's SASS: the fp64 pipe is busy for the whole warp either way)
+#ifndef RB_SCAN_SELECT
+#define RB_SCAN_SELECT 1
+#endif
+// 1: adding's upward replay carries (albedo, source) in homogeneous form through the lane's layers, so the per-layer
+// reciprocal leaves the 9-step dependent chain: the chain is 2 multiply-adds deep per layer, the reciprocals of all
+// levels are then independent of each other (see adding_reg)
+#ifndef RB_ADD_HOMOG
+#define RB_ADD_HOMOG 1
+#endif
+// 1: Rdir/Tdir's RT_term*w0/(1 - k^2 mu0^2) shares ONE reciprocal with RT_term itself (see sw cell)
+#ifndef RB_SW_MERGED_DIV
+#define RB_SW_MERGED_DIV 1
+#endif
 __device__ __forceinline__ Float affine_handoff_down(int j, Float A, Float B, Float x_top, Float& out) {
 #if RB_HANDOFF_SCAN
   Float PA = A, PB = B;  // composed map of chunks (j-d+1 .. j): x -> PA*x + PB
 #pragma unroll
   for (int d = 1; d < kRegChunks; d <<= 1) {
-    const Float qa = __shfl_up_sync(0xffffffffu, PA, d, kRegChunks);
-    const Float qb = __shfl_up_sync(0xffffffffu, PB, d, kRegChunks);
+    Float qa = __shfl_up_sync(0xffffffffu, PA, d, kRegChunks);
+    Float qb = __shfl_up_sync(0xffffffffu, PB, d, kRegChunks);
+#if RB_SCAN_SELECT
+    qa = (j >= d) ? qa : (Float)1; qb = (j >= d) ? qb : (Float)0;
+    PB = PA * qb + PB; PA = PA * qa;
+#else
     if (j >= d) { PB = PA * qb + PB; PA = PA * qa; }  // this map after the d chunks above it
+#endif
   }
   out = PA * x_top + PB;
   const Float got = __shfl_up_sync(0xffffffffu, out, 1, kRegChunks);
@@ -111,8 +132,13 @@ __device__ __forceinline__ Float product_handoff_down(int j, Float A, Float x_to
   Float PA = A;
 #pragma unroll
   for (int d = 1; d < kRegChunks; d <<= 1) {
-    const Float qa = __shfl_up_sync(0xffffffffu, PA, d, kRegChunks);
+    Float qa = __shfl_up_sync(0xffffffffu, PA, d, kRegChunks);
+#if RB_SCAN_SELECT
+    qa = (j >= d) ? qa : (Float)1;
+    PA = PA * qa;
+#else
     if (j >= d) PA = PA * qa;
+#endif
   }
   out = PA * x_top;
   const Float got = __shfl_up_sync(0xffffffffu, out, 1, kRegChunks);
@@ -128,9 +154,14 @@ __device__ __forceinline__ Float affine_handoff_up(int j, Float A, Float B, Floa
   Float PA = A, PB = B;  // composed map of chunks (j+d-1 .. j), applied bottom first
 #pragma unroll
   for (int d = 1; d < kRegChunks; d <<= 1) {
-    const Float qa = __shfl_down_sync(0xffffffffu, PA, d, kRegChunks);
-    const Float qb = __shfl_down_sync(0xffffffffu, PB, d, kRegChunks);
+    Float qa = __shfl_down_sync(0xffffffffu, PA, d, kRegChunks);
+    Float qb = __shfl_down_sync(0xffffffffu, PB, d, kRegChunks);
+#if RB_SCAN_SELECT
+    qa = (j + d < kRegChunks) ? qa : (Float)1; qb = (j + d < kRegChunks) ? qb : (Float)0;
+    PB = PA * qb + PB; PA = PA * qa;
+#else
     if (j + d < kRegChunks) { PB = PA * qb + PB; PA = PA * qa; }
+#endif
   }
   out = PA * xb + PB;
   const Float got = __shfl_down_sync(0xffffffffu, out, 1, kRegChunks);
@@ -428,11 +459,18 @@ __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL]
     // product of the matrices of chunks j .. 7, bottom one applied first
 #pragma unroll
     for (int d = 1; d < kRegChunks; d <<= 1) {
-      const Float la = __shfl_down_sync(0xffffffffu, ma, d, kRegChunks), lb = __shfl_down_sync(0xffffffffu, mb, d, kRegChunks);
-      const Float lc = __shfl_down_sync(0xffffffffu, mc, d, kRegChunks), ld = __shfl_down_sync(0xffffffffu, md, d, kRegChunks);
-      const Float le = __shfl_down_sync(0xffffffffu, me, d, kRegChunks), lf = __shfl_down_sync(0xffffffffu, mf, d, kRegChunks);
-      const Float lg = __shfl_down_sync(0xffffffffu, mg, d, kRegChunks);
+      Float la = __shfl_down_sync(0xffffffffu, ma, d, kRegChunks), lb = __shfl_down_sync(0xffffffffu, mb, d, kRegChunks);
+      Float lc = __shfl_down_sync(0xffffffffu, mc, d, kRegChunks), ld = __shfl_down_sync(0xffffffffu, md, d, kRegChunks);
+      Float le = __shfl_down_sync(0xffffffffu, me, d, kRegChunks), lf = __shfl_down_sync(0xffffffffu, mf, d, kRegChunks);
+      Float lg = __shfl_down_sync(0xffffffffu, mg, d, kRegChunks);
+#if RB_SCAN_SELECT
+      const bool on = j + d < kRegChunks;  // lanes without a partner combine with the identity matrix
+      la = on ? la : (Float)1; lb = on ? lb : (Float)0; lc = on ? lc : (Float)0; ld = on ? ld : (Float)1;
+      le = on ? le : (Float)0; lf = on ? lf : (Float)0; lg = on ? lg : (Float)1;
+      {
+#else
       if (j + d < kRegChunks) {  // (this lane's chunks) after (the d chunk groups below them)
+#endif
         const Float na = ma * la + mb * lf, nb = ma * lb + mb * lg;
         const Float nc = mc * la + md * lc + me * lf, ne = mc * lb + md * le + me * lg;
         const Float nf = mf * la + mg * lf, ng = mf * lb + mg * lg;
@@ -476,6 +514,45 @@ __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL]
     src = is * inv;
   }
 #endif
+#if RB_ADD_HOMOG
+  // Upward replay in HOMOGENEOUS form.  With alb = A/D, src = S/D the layer step (:1174-1186) reads
+  //     D' = D - r*A            (= D*(1 - r*alb))
+  //     A' = r*D' + t^2*A       (albedo above  = r + t^2*alb/(1 - r*alb))
+  //     S' = sup*D' + t*(S + A*sdn)
+  // - two dependent multiply-adds per layer and no reciprocal inside the chain (the per-layer form's chain carries a
+  // reciprocal, ~5 dependent operations, per layer: the longest serial stretch of the kernel, during which a warp
+  // issues next to nothing).  The reciprocals 1/D of the CL+1 levels are then independent of one another, and
+  // denom = 1/(1 - r*alb) = D/D' needs no reciprocal of its own.  Per-level albedo and source carry the rounding of
+  // CL <= 10 homogeneous steps (a few ulp) instead of the reference's level-by-level quotient.
+  {
+    Float hA[CL + 1], hS[CL + 1], hD[CL + 1];  // state BELOW layer i (slot i), slot CL... see below: slot k = below layer k-1
+    // slot CL = below the lane's last layer (incoming), slot i = above layer i = below layer i-1
+    hA[CL] = alb; hS[CL] = src; hD[CL] = (Float)1;
+#pragma unroll
+    for (int i = CL - 1; i >= 0; --i) {
+      const Float r = R[i], t = T[i];
+      hD[i] = hD[i + 1] - r * hA[i + 1];
+      hA[i] = r * hD[i] + (t * t) * hA[i + 1];
+      hS[i] = SU[i] * hD[i] + t * (hS[i + 1] + hA[i + 1] * SD[i]);
+    }
+    Float inv[CL + 1];
+    inv[CL] = (Float)1;
+#pragma unroll
+    for (int i = 0; i < CL; ++i) inv[i] = rb_rcp(hD[i]);
+#pragma unroll
+    for (int i = CL - 1; i >= 0; --i) {
+      const Float r = R[i], t = T[i], sdn = SD[i];
+      const Float alb_i = hA[i + 1] * inv[i + 1], src_i = hS[i + 1] * inv[i + 1];  // below layer i
+      const Float denom = hD[i + 1] * inv[i];                                        // 1/(1 - r*alb_i)
+      R[i] = alb_i;
+      SU[i] = src_i;
+      T[i] = t * denom;
+      SD[i] = (r * src_i + sdn) * denom;
+    }
+    alb = hA[0] * inv[0];
+    src = hS[0] * inv[0];
+  }
+#else
   // replay with the reference's per-layer expressions, every lane on its own chunk
 #pragma unroll
   for (int i = CL - 1; i >= 0; --i) {  // :1174-1186
@@ -490,6 +567,7 @@ __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL]
     src = sup + a * (src + alb * sdn);
     alb = albn;
   }
+#endif
   // lane j == 0 now holds albedo and source at the top of the domain
   if (j == 0) top(flux_dn_top * alb + src, flux_dn_top);  // :1190
   // ---- downward pass (:1196-1202): fdn' = a*fdn + b per layer, an affine chain
@@ -675,13 +753,27 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
       const Float kk = rb_sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), min_k));
       const Float exp_minusktau = rb_exp(-tau_s * kk);
       const Float exp_minus2ktau = exp_minusktau * exp_minusktau;
-      Float RT_term = rb_rcp(kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau));
-      const Float Rdif = RT_term * gamma2 * ((Float)1 - exp_minus2ktau);
-      const Float Tdif = RT_term * (Float)2 * kk * exp_minusktau;
       const Float mu0_s = fmax(min_mu0, mu0);
       const Float k_mu = kk * mu0_s;
       const Float om = (Float)1 - k_mu * k_mu;
-      RT_term = rb_div(w0_s * RT_term, fabs(om) >= eps ? om : eps);
+      const Float om_s = fabs(om) >= eps ? om : eps;                                  // :1071-1073
+      const Float rt_den = kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau);
+#if RB_SW_MERGED_DIV
+      // RT_term = 1/rt_den (:1052) and RT_term*w0/om_s (:1071) from ONE reciprocal, 1/(rt_den*om_s): a multiplication
+      // each instead of a second division sequence (9 fp64 instructions); rt_den in [k, 2*max(k, gamma1)] and
+      // |om_s| >= eps keep the product finite and normal; both quotients stay within 2 ulp of the reference's
+      const Float rt_inv = rb_rcp(rt_den * om_s);
+      Float RT_term = om_s * rt_inv;
+#else
+      Float RT_term = rb_rcp(rt_den);
+#endif
+      const Float Rdif = RT_term * gamma2 * ((Float)1 - exp_minus2ktau);
+      const Float Tdif = RT_term * (Float)2 * kk * exp_minusktau;
+#if RB_SW_MERGED_DIV
+      RT_term = w0_s * rt_inv;
+#else
+      RT_term = rb_div(w0_s * RT_term, om_s);
+#endif
       const Float gamma3 = ((Float)2 - (Float)3 * mu0_s * g_s) * (Float).25;
       const Float gamma4 = (Float)1 - gamma3;
       const Float alpha1 = gamma1 * gamma4 + gamma2 * gamma3;

@@ -499,3 +499,154 @@ class AerosolOptics:
             self.ctx.c.rrtmgpb_aerosol_optics_free(C.c_void_p(self.handle))
         except Exception:
             pass
+
+
+# ----------------------------------------------------------------------------------------------------
+# k-distribution ingestion (include/rrtmgp_b200_kdist.h): on-disk variable set -> kernel tables.  The reduction runs in
+# C++ (csrc/frontend/kdist_load.cpp); this is marshalling only.
+# ----------------------------------------------------------------------------------------------------
+_RAW_INT = ("ntemp", "npres", "nabsorbers", "nminorabsorbers", "nextabsorbers", "nmixingfracs", "nlayers", "nbnd", "ngpt",
+            "nminor_absorber_intervals_lower", "nminor_absorber_intervals_upper", "ncontributors_lower",
+            "ncontributors_upper", "ntemp_planck", "nfit_coeffs")
+
+
+class _KDistRawStruct(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in _RAW_INT]
+                + [(n, C.c_void_p) for n in ("gas_names", "key_species", "bnd_limits_wavenumber", "bnd_limits_gpt",
+                                             "press_ref", "temp_ref")]
+                + [(n, FLOAT) for n in ("absorption_coefficient_ref_P", "absorption_coefficient_ref_T", "press_ref_trop")]
+                + [(n, C.c_void_p) for n in ("kminor_lower", "kminor_upper", "gas_minor", "identifier_minor",
+                                             "minor_gases_lower", "minor_gases_upper", "minor_limits_gpt_lower",
+                                             "minor_limits_gpt_upper", "minor_scales_with_density_lower",
+                                             "minor_scales_with_density_upper", "scale_by_complement_lower",
+                                             "scale_by_complement_upper", "scaling_gas_lower", "scaling_gas_upper",
+                                             "kminor_start_lower", "kminor_start_upper", "vmr_ref", "kmajor", "rayl_lower",
+                                             "rayl_upper", "totplnk", "plank_fraction", "optimal_angle_fit",
+                                             "solar_source_quiet", "solar_source_facular", "solar_source_sunspot")]
+                + [(n, FLOAT) for n in ("tsi_default", "mg_default", "sb_default")])
+
+
+def load_kdist_raw(lib, raw, available_gases, mg_index=None, sb_index=None, tsi=None):
+    """ty_gas_optics_rrtmgp%load on the on-disk variable set `raw` (dict, see synthetic.make_kdist_raw /
+    mo_optics_utils_rrtmgp.F90:102-183) for the gases the host provides.  Returns a synthetic.KDist holding numpy copies
+    of the reduced kernel-layout tables (feed it to GasOptics) - raises RuntimeError with the reference's message."""
+    from .synthetic import KDist
+
+    c = lib.cdll
+    c.rrtmgpb_kdist_reduce.restype = C.c_void_p
+    c.rrtmgpb_kdist_loaded_tables.restype = C.POINTER(_KDistStruct)
+    c.rrtmgpb_kdist_loaded_gas_name.restype = C.c_char_p
+    c.rrtmgpb_kdist_loaded_optimal_angle_fit.restype = C.c_void_p
+    for fn in ("rrtmgpb_kdist_loaded_tables", "rrtmgpb_kdist_loaded_free", "rrtmgpb_kdist_loaded_optimal_angle_fit"):
+        getattr(c, fn).argtypes = [C.c_void_p]
+    c.rrtmgpb_kdist_loaded_gas_name.argtypes = [C.c_void_p, C.c_int]
+    c.rrtmgpb_kdist_loaded_is_key.argtypes = [C.c_void_p, C.c_int]
+    keep = []
+
+    def arr(a, dt):
+        a = np.asfortranarray(a, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    def strs(lst):
+        bufs = [C.create_string_buffer(s.encode()) for s in lst]
+        tab = (C.c_char_p * max(len(lst), 1))(*[C.cast(b, C.c_char_p) for b in bufs])
+        keep.extend([bufs, tab])
+        return C.cast(tab, C.c_void_p)
+
+    i32, f64, b8 = np.int32, np.float64, np.bool_
+    s = _KDistRawStruct()
+    km = np.asarray(raw["kmajor"])
+    s.ngpt, s.nmixingfracs, s.npres, s.ntemp = km.shape[0], km.shape[1], km.shape[2] - 1, km.shape[3]
+    s.nabsorbers, s.nextabsorbers = len(raw["gas_names"]), np.asarray(raw["vmr_ref"]).shape[1]
+    s.nminorabsorbers, s.nlayers, s.nbnd = len(raw["gas_minor"]), 2, np.asarray(raw["bnd_limits_gpt"]).shape[1]
+    s.nminor_absorber_intervals_lower, s.nminor_absorber_intervals_upper = len(raw["minor_gases_lower"]), len(raw["minor_gases_upper"])
+    s.ncontributors_lower, s.ncontributors_upper = np.asarray(raw["kminor_lower"]).shape[0], np.asarray(raw["kminor_upper"]).shape[0]
+    for n in ("gas_names", "gas_minor", "identifier_minor", "minor_gases_lower", "minor_gases_upper", "scaling_gas_lower",
+              "scaling_gas_upper"):
+        setattr(s, n, strs(raw[n]))
+    for n, dt in (("key_species", i32), ("bnd_limits_wavenumber", f64), ("bnd_limits_gpt", i32), ("press_ref", f64),
+                  ("temp_ref", f64), ("kminor_lower", f64), ("kminor_upper", f64), ("minor_limits_gpt_lower", i32),
+                  ("minor_limits_gpt_upper", i32), ("minor_scales_with_density_lower", b8),
+                  ("minor_scales_with_density_upper", b8), ("scale_by_complement_lower", b8),
+                  ("scale_by_complement_upper", b8), ("kminor_start_lower", i32), ("kminor_start_upper", i32),
+                  ("vmr_ref", f64), ("kmajor", f64)):
+        setattr(s, n, arr(raw[n], dt))
+    for n in ("absorption_coefficient_ref_P", "absorption_coefficient_ref_T", "press_ref_trop"):
+        setattr(s, n, float(raw[n]))
+    if raw.get("rayl_lower") is not None:
+        s.rayl_lower = arr(raw["rayl_lower"], f64)
+    if raw.get("rayl_upper") is not None:
+        s.rayl_upper = arr(raw["rayl_upper"], f64)
+    is_lw = "totplnk" in raw
+    if is_lw:
+        s.totplnk, s.plank_fraction = arr(raw["totplnk"], f64), arr(raw["plank_fraction"], f64)
+        s.optimal_angle_fit = arr(raw["optimal_angle_fit"], f64)
+        s.ntemp_planck, s.nfit_coeffs = np.asarray(raw["totplnk"]).shape[0], np.asarray(raw["optimal_angle_fit"]).shape[0]
+    else:
+        for n in ("solar_source_quiet", "solar_source_facular", "solar_source_sunspot"):
+            setattr(s, n, arr(raw[n], f64))
+        s.tsi_default, s.mg_default, s.sb_default = float(raw["tsi_default"]), float(raw["mg_default"]), float(raw["sb_default"])
+    err = C.create_string_buffer(ERRLEN)
+    avail = strs(list(available_gases))
+    h = c.rrtmgpb_kdist_reduce(C.byref(s), len(available_gases), avail, err)
+    if not h:
+        raise RuntimeError(err.value.decode())
+    try:
+        if not is_lw and (mg_index is not None or sb_index is not None):   # set_solar_variability(mg, sb) :760-798
+            c.rrtmgpb_kdist_set_solar_variability.argtypes = [C.c_void_p, FLOAT, FLOAT, FLOAT, C.c_char_p]
+            _check(c.rrtmgpb_kdist_set_solar_variability(h, raw["mg_default"] if mg_index is None else mg_index,
+                                                         raw["sb_default"] if sb_index is None else sb_index, -1.0, err), err)
+        if not is_lw and tsi is not None:                                  # set_tsi(tsi) :800-835
+            c.rrtmgpb_kdist_set_tsi.argtypes = [C.c_void_p, FLOAT, C.c_char_p]
+            _check(c.rrtmgpb_kdist_set_tsi(h, tsi, err), err)
+        t = c.rrtmgpb_kdist_loaded_tables(h).contents
+
+        def get(ptr, shape, dt):
+            n = int(np.prod(shape))
+            if not ptr or n == 0:
+                return np.zeros(shape, dtype=dt, order="F")
+            buf = (C.c_byte * (n * np.dtype(dt).itemsize)).from_address(ptr)
+            return np.asfortranarray(np.frombuffer(buf, dtype=dt).reshape(shape, order="F").copy(order="F"))
+
+        nl, nu = t.nminorlower, t.nminorupper
+        gas_names = [c.rrtmgpb_kdist_loaded_gas_name(h, i).decode() for i in range(t.ngas)]
+        kd = KDist(
+            is_lw=is_lw, gas_names=gas_names, ngas=t.ngas, nflav=t.nflav, neta=t.neta, npres=t.npres, ntemp=t.ntemp,
+            nbnd=t.nbnd, ngpt=t.ngpt, flavor=get(t.flavor, (2, t.nflav), i32), gpoint_flavor=get(t.gpoint_flavor, (2, t.ngpt), i32),
+            band_lims_gpt=get(t.band_lims_gpt, (2, t.nbnd), i32), band_lims_wvn=get(t.band_lims_wvn, (2, t.nbnd), f64),
+            gpoint_bands=get(t.gpoint_bands, (t.ngpt,), i32), press_ref=np.array(raw["press_ref"], dtype=f64),
+            press_ref_log=get(t.press_ref_log, (t.npres,), f64), temp_ref=get(t.temp_ref, (t.ntemp,), f64),
+            press_ref_log_delta=t.press_ref_log_delta, temp_ref_min=t.temp_ref_min, temp_ref_max=t.temp_ref_max,
+            temp_ref_delta=t.temp_ref_delta, press_ref_min=t.press_ref_min, press_ref_max=t.press_ref_max,
+            press_ref_trop_log=t.press_ref_trop_log, vmr_ref=get(t.vmr_ref, (2, t.ngas + 1, t.ntemp), f64),
+            kmajor=get(t.kmajor, (t.ntemp, t.neta, t.npres + 1, t.ngpt), f64),
+            kminor_lower=get(t.kminor_lower, (t.ntemp, t.neta, max(t.nminorklower, 1)), f64),
+            kminor_upper=get(t.kminor_upper, (t.ntemp, t.neta, max(t.nminorkupper, 1)), f64),
+            minor_limits_gpt_lower=get(t.minor_limits_gpt_lower, (2, max(nl, 1)), i32),
+            minor_limits_gpt_upper=get(t.minor_limits_gpt_upper, (2, max(nu, 1)), i32),
+            minor_scales_with_density_lower=get(t.minor_scales_with_density_lower, (max(nl, 1),), b8),
+            minor_scales_with_density_upper=get(t.minor_scales_with_density_upper, (max(nu, 1),), b8),
+            scale_by_complement_lower=get(t.scale_by_complement_lower, (max(nl, 1),), b8),
+            scale_by_complement_upper=get(t.scale_by_complement_upper, (max(nu, 1),), b8),
+            idx_minor_lower=get(t.idx_minor_lower, (max(nl, 1),), i32), idx_minor_upper=get(t.idx_minor_upper, (max(nu, 1),), i32),
+            idx_minor_scaling_lower=get(t.idx_minor_scaling_lower, (max(nl, 1),), i32),
+            idx_minor_scaling_upper=get(t.idx_minor_scaling_upper, (max(nu, 1),), i32),
+            kminor_start_lower=get(t.kminor_start_lower, (max(nl, 1),), i32),
+            kminor_start_upper=get(t.kminor_start_upper, (max(nu, 1),), i32), idx_h2o=t.idx_h2o,
+        )
+        kd.extra["nminorlower"], kd.extra["nminorupper"] = nl, nu
+        kd.extra["is_key"] = [bool(c.rrtmgpb_kdist_loaded_is_key(h, i)) for i in range(t.ngas)]
+        if is_lw:
+            kd.planck_frac = get(t.planck_frac, (t.ntemp, t.neta, t.npres + 1, t.ngpt), f64)
+            kd.totplnk = get(t.totplnk, (t.nPlanckTemp, t.nbnd), f64)
+            kd.totplnk_delta = t.totplnk_delta
+            oaf = c.rrtmgpb_kdist_loaded_optimal_angle_fit(h)
+            if oaf:
+                kd.extra["optimal_angle_fit"] = get(oaf, (s.nfit_coeffs, t.nbnd), f64)
+        else:
+            kd.krayl = get(t.krayl, (t.ntemp, t.neta, t.ngpt, 2), f64) if t.krayl else None
+            kd.solar_source = get(t.solar_source, (t.ngpt,), f64)
+        return kd
+    finally:
+        c.rrtmgpb_kdist_loaded_free(h)

@@ -420,3 +420,112 @@ def perturbed_profiles(ncol, nlay, seed=1234, top_at_1=True):
     if top_at_1:
         out = {k: _f(v[:, ::-1]) for k, v in out.items()}
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Raw ("on-disk") k-distribution: the variable set of an rrtmgp-data file before ty_gas_optics_rrtmgp%load
+# (rrtmgp/data-loading-examples/mo_optics_utils_rrtmgp.F90:102-183), synthesised so that load() restricted to the
+# host's gases gives back exactly the tables of a KDist built by make_kdist().
+# ----------------------------------------------------------------------------------------------
+RAW_EXTRA_GASES = ["ccl4", "cfc11", "cfc12", "cfc22", "hfc143a", "hfc125", "hfc23", "hfc32", "hfc134a", "cf4", "no2"]
+
+
+def make_kdist_raw(kd, seed=11):
+    """dict of numpy arrays / string lists with the on-disk names and Fortran shapes (first index fastest):
+    19 absorbers (the 8 of `kd` in their order, 11 others interleaved), key_species indexing THAT list, minor-contributor
+    intervals of absent gases interleaved with kd's, string-valued minor_gases / scaling_gas, kmajor / plank_fraction as
+    (gpt, mixing_fraction, pressure+1, temperature), rayl_lower/upper (gpt, mixing_fraction, temperature)."""
+    rng = np.random.default_rng(seed)
+    ngas = kd.ngas
+    # --- absorber list: kd's gases keep their relative order (the reduced list must come out as kd.gas_names)
+    slots = sorted(rng.choice(ngas + len(RAW_EXTRA_GASES), ngas, replace=False).tolist())
+    names, host_pos, extra = [], {}, iter(RAW_EXTRA_GASES)
+    for i in range(ngas + len(RAW_EXTRA_GASES)):
+        if i in slots:
+            g = kd.gas_names[slots.index(i)]
+            host_pos[g] = len(names) + 1
+            names.append(g.upper() if len(names) % 3 == 0 else g + "  ")   # case and blank padding must not matter
+        else:
+            names.append(next(extra))
+    nabs = len(names)
+    raw_of_host = [0] + [host_pos[g] for g in kd.gas_names]   # reduced index -> raw index
+    # --- key_species(2, atmos_layer, bnd): kd's flavours; (2,2) is what load() makes of an on-disk (0,0)
+    key_species = np.zeros((2, 2, kd.nbnd), dtype=np.int32, order="F")
+    for b in range(kd.nbnd):
+        g1 = int(kd.band_lims_gpt[0, b]) - 1
+        for a in range(2):
+            pr = kd.flavor[:, int(kd.gpoint_flavor[a, g1]) - 1]
+            key_species[:, a, b] = (0, 0) if tuple(pr) == (2, 2) else [raw_of_host[int(v)] for v in pr]
+    vmr_ref = np.asfortranarray(rng.uniform(1e-9, 1e-3, (2, nabs + 1, kd.ntemp)))
+    for i in range(ngas + 1):
+        vmr_ref[:, raw_of_host[i], :] = kd.vmr_ref[:, i, :]
+    # --- minor contributors
+    ident = [g if g != "h2o" else "h2o_frgn" for g in kd.gas_names] + ["h2o_self"] + RAW_EXTRA_GASES
+    gas_minor = list(kd.gas_names) + ["h2o"] + RAW_EXTRA_GASES
+
+    def minor(which):
+        lims = getattr(kd, f"minor_limits_gpt_{which}")
+        n = kd.extra[f"nminor{which}"]
+        kmin = getattr(kd, f"kminor_{which}")          # (ntemp, neta, nk)
+        out = dict(gases=[], scaling=[], lims=[], dens=[], comp=[], start=[], cols=[])
+        k = 1
+
+        def add(gas_ident, scal, gs, ge, dens, comp, cols):
+            nonlocal k
+            out["gases"].append(gas_ident); out["scaling"].append(scal); out["lims"].append((gs, ge))
+            out["dens"].append(dens); out["comp"].append(comp); out["start"].append(k); out["cols"].append(cols)
+            k += ge - gs + 1
+
+        def absent():
+            b = int(rng.integers(0, kd.nbnd))
+            gs, ge = int(kd.band_lims_gpt[0, b]), int(kd.band_lims_gpt[1, b])
+            add(RAW_EXTRA_GASES[int(rng.integers(0, len(RAW_EXTRA_GASES)))], "", gs, ge, bool(rng.integers(0, 2)), False,
+                10.0 ** rng.uniform(-27, -23, (kd.ntemp, kd.neta, ge - gs + 1)))
+
+        for i in range(n):
+            while rng.random() < 0.35:
+                absent()
+            gs, ge = int(lims[0, i]), int(lims[1, i])
+            g = kd.gas_names[int(getattr(kd, f"idx_minor_{which}")[i]) - 1]
+            idn = g if g != "h2o" else ("h2o_self" if rng.random() < 0.5 else "h2o_frgn")
+            isc = int(getattr(kd, f"idx_minor_scaling_{which}")[i])
+            ks = int(getattr(kd, f"kminor_start_{which}")[i])
+            add(idn.upper() if i % 4 == 0 else idn, kd.gas_names[isc - 1] if isc > 0 else "",
+                gs, ge, bool(getattr(kd, f"minor_scales_with_density_{which}")[i]),
+                bool(getattr(kd, f"scale_by_complement_{which}")[i]), kmin[:, :, ks - 1:ks - 1 + ge - gs + 1])
+        absent()
+        ncontrib = k - 1
+        kraw = np.zeros((ncontrib, kd.neta, kd.ntemp), order="F")
+        for s, c in zip(out["start"], out["cols"]):
+            kraw[s - 1:s - 1 + c.shape[2]] = np.transpose(c, (2, 1, 0))
+        return dict(kminor=kraw, gases=out["gases"], scaling=out["scaling"],
+                    limits=_f(np.array(out["lims"]).T.reshape(2, -1), np.int32), dens=np.array(out["dens"], dtype=np.bool_),
+                    comp=np.array(out["comp"], dtype=np.bool_), start=np.array(out["start"], dtype=np.int32))
+
+    lo, up = minor("lower"), minor("upper")
+    raw = dict(
+        gas_names=names, key_species=key_species, bnd_limits_wavenumber=_f(kd.band_lims_wvn),
+        bnd_limits_gpt=_f(kd.band_lims_gpt, np.int32), press_ref=np.array(kd.press_ref), temp_ref=np.array(kd.temp_ref),
+        absorption_coefficient_ref_P=101325.0, absorption_coefficient_ref_T=296.0,
+        press_ref_trop=float(np.exp(kd.press_ref_trop_log)), kminor_lower=lo["kminor"], kminor_upper=up["kminor"],
+        gas_minor=gas_minor, identifier_minor=ident, minor_gases_lower=lo["gases"], minor_gases_upper=up["gases"],
+        minor_limits_gpt_lower=lo["limits"], minor_limits_gpt_upper=up["limits"],
+        minor_scales_with_density_lower=lo["dens"], minor_scales_with_density_upper=up["dens"],
+        scale_by_complement_lower=lo["comp"], scale_by_complement_upper=up["comp"],
+        scaling_gas_lower=lo["scaling"], scaling_gas_upper=up["scaling"],
+        kminor_start_lower=lo["start"], kminor_start_upper=up["start"], vmr_ref=vmr_ref,
+        kmajor=_f(np.transpose(kd.kmajor, (3, 1, 2, 0))),
+    )
+    if kd.is_lw:
+        raw.update(totplnk=_f(kd.totplnk), plank_fraction=_f(np.transpose(kd.planck_frac, (3, 1, 2, 0))),
+                   optimal_angle_fit=_f(kd.extra["optimal_angle_fit"]))
+    else:
+        raw.update(rayl_lower=_f(np.transpose(kd.krayl[:, :, :, 0], (2, 1, 0))),
+                   rayl_upper=_f(np.transpose(kd.krayl[:, :, :, 1], (2, 1, 0))))
+        # solar_source = quiet + (mg - 0.1495954) facular + (sb - 0.00066696) sunspot (mo_gas_optics_rrtmgp.F90:788-792)
+        fac, spot = rng.uniform(0.0, 0.05, kd.ngpt) * kd.solar_source, rng.uniform(-0.05, 0.0, kd.ngpt) * kd.solar_source
+        mg, sb = 0.1567652, 902.71260
+        raw.update(solar_source_quiet=kd.solar_source - (mg - 0.1495954) * fac - (sb - 0.00066696) * spot,
+                   solar_source_facular=fac, solar_source_sunspot=spot, tsi_default=1360.85767381726, mg_default=mg,
+                   sb_default=sb)
+    return raw

@@ -48,8 +48,9 @@ def test_fastmath_within_2ulp(oracle_lib, cuda_lib):
     got = _probe(cuda_lib, x)
     sel = x >= -708.0  # below: flushed to 0 by design (true values are subnormal)
     assert np.all(got[0][x < -708.001] == 0.0)  # however negative (the power of two must not wrap around)
-    for name, g, r, m in (("exp", got[0], ref[0], sel), ("sqrt", got[1], ref[1], np.ones_like(sel)),
-                          ("rcp", got[2], ref[2], np.ones_like(sel)), ("div", got[3], ref[3], np.ones_like(sel))):
+    fin = np.abs(x) < 1e100  # (x*x + 1)/x of the probe overflows beyond; those arguments are there for exp only
+    for name, g, r, m in (("exp", got[0], ref[0], sel), ("sqrt", got[1], ref[1], fin),
+                          ("rcp", got[2], ref[2], fin), ("div", got[3], ref[3], fin)):
         u = _ulps(g[m], r[m])
         print(f"fastmath {name}: max {np.max(u):.3f} ulp, mean {np.mean(u):.4f} ulp over {u.size} arguments")
         assert np.max(u) <= 2.0, (name, float(np.max(u)), x[m][np.argmax(u)])
