@@ -258,6 +258,25 @@ void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, c
                               int sfc_lay, Float* sfc_src, Float* lay_src /* NULL: no sources */, Float* lev_src,
                               Float* sfc_source_Jac);
 
+/* ---------------- express path ---------------- */
+/* Broadband fluxes straight from the atmospheric state: gas optics (+ by-band cloud increment, + Planck sources) feed
+ * the flux solver per band through a scratch that is sized to stay in L2; no (ncol, nlay, ngpt) array is allocated, the
+ * footprint is ~6 KB per column instead of ~0.9 MB.  LW when t->krayl == NULL (no-scattering solver, nmus Gauss
+ * angles: Ds_host / wts_host are HOST arrays of nmus secants and weights, mo_rte_lw.F90:146-160), else SW (two-stream).
+ * Arrays: play, tlay (ncol,nlay); plev, tlev (ncol,nlay+1); tsfc, mu0 (ncol); vmr (ncol,nlay,ngas); col_dry optional;
+ * cld_* by band (ncol,nlay,nbnd), kind 0 none / 1 tau / 2 tau,ssa[,g]; sfc_emis_or_alb_dir, sfc_alb_dif (nbnd,ncol);
+ * solar_source (ngpt); outputs (ncol,nlay+1).  The oracle's implementation is the reference call sequence on full
+ * arrays (gas optics, increment, rte_lw / rte_sw). */
+void rrtmgpb_express(const rrtmgpb_gas_tables* t, int ncol, int nlay, int top_at_1, const Float* play, const Float* plev,
+                     const Float* tlay, const Float* tlev, const Float* tsfc, const Float* vmr, const Float* col_dry,
+                     int cld_kind, const Float* cld_tau, const Float* cld_ssa, const Float* cld_g,
+                     const Float* sfc_emis_or_alb_dir, const Float* sfc_alb_dif, const Float* mu0,
+                     const Float* solar_source, int nmus, const Float* Ds_host, const Float* wts_host, Float* flux_up,
+                     Float* flux_dn, Float* flux_dir);
+/* 1: the band-staged pipeline runs (register solvers: nlay within their range); 0: rrtmgpb_express still works, one
+ * solver launch per column chunk over all bands (bounded scratch, planes through HBM) */
+int rrtmgpb_express_supported(int ncol, int nlay);
+
 #ifdef __cplusplus
 }
 #endif

@@ -147,6 +147,23 @@ int rrtmgpb_gas_optics_ext_fused(const rrtmgpb_gas_optics_t* go, int ncol, int n
                                  const rrtmgpb_optical_props* clouds, const rrtmgpb_optical_props* aerosols,
                                  char* errmsg);
 
+/* ---------------- express path: state in, broadband fluxes out ---------------- */
+/* = gas_optics(play, plev, tlay, tsfc, gas_concs, atmos, sources[, col_dry, tlev]) ; clouds%increment(atmos) ;
+ *   rte_lw(atmos, sources, sfc_emis, fluxes[, n_gauss_angles])   with ty_fluxes_broadband
+ * (examples/all-sky/rrtmgp_allsky.F90:368-381) without atmos / sources ever existing: no (ncol,nlay,ngpt) array is
+ * allocated (include/rrtmgp_b200_ext.h: rrtmgpb_express).  clouds: by-band 1scl / 2str properties or NULL;
+ * sfc_emis (nbnd,ncol); the same checks and error strings as the three calls it replaces. */
+int rrtmgpb_rte_lw_express(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play, const Float* plev,
+                           const Float* tlay, const Float* tsfc, const Float* vmr, const Float* col_dry /* or NULL */,
+                           const Float* tlev /* or NULL */, const rrtmgpb_optical_props* clouds /* or NULL */,
+                           const Float* sfc_emis, int n_gauss_angles, rrtmgpb_fluxes_broadband* fluxes, char* errmsg);
+/* = gas_optics(..., atmos, toa_flux) ; clouds%increment(atmos) ; rte_sw(atmos, mu0, toa_flux, sfc_alb_dir, sfc_alb_dif,
+ *   fluxes) (rrtmgp_allsky.F90:383-406); clouds are expected delta-scaled already, as there. */
+int rrtmgpb_rte_sw_express(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play, const Float* plev,
+                           const Float* tlay, const Float* vmr, const Float* col_dry /* or NULL */,
+                           const rrtmgpb_optical_props* clouds /* or NULL */, const Float* mu0, const Float* sfc_alb_dir,
+                           const Float* sfc_alb_dif, rrtmgpb_fluxes_broadband* fluxes, char* errmsg);
+
 /* ---------------- ty_cloud_optics_rrtmgp (LUT form) ---------------- */
 typedef struct {
   int nbnd, nsize_liq, nsize_ice, nrghice, icergh;

@@ -434,3 +434,48 @@ void rrtmgpb_cloud_optics_from_tables_ds(int ncol, int nlay, int nbnd, int kind,
                                    ssa, g);
   if (delta_scale && kind == 2) rte_delta_scale_2str_k(&ncol, &nlay, &nbnd, tau, ssa, g);
 }
+
+
+/* ---------------- express path: on the oracle, the reference call sequence on full arrays ---------------- */
+int rrtmgpb_express_supported(int ncol, int nlay) { (void)ncol; (void)nlay; return 1; }
+void rrtmgpb_express(const rrtmgpb_gas_tables* t, int ncol, int nlay, int top_at_1, const Float* play, const Float* plev,
+                     const Float* tlay, const Float* tlev, const Float* tsfc, const Float* vmr, const Float* col_dry,
+                     int cld_kind, const Float* cld_tau, const Float* cld_ssa, const Float* cld_g,
+                     const Float* sfc_emis_or_alb_dir, const Float* sfc_alb_dif, const Float* mu0,
+                     const Float* solar_source, int nmus, const Float* Ds_host, const Float* wts_host, Float* flux_up,
+                     Float* flux_dn, Float* flux_dir) {
+  const int sw = t->krayl != NULL, ngpt = t->ngpt, nbnd = t->nbnd, nlev = nlay + 1;
+  const size_t ncl = (size_t)ncol * nlay, nclp = (size_t)ncol * nlev, ncg = (size_t)ncol * ngpt;
+  const Bool top = top_at_1 != 0, yes = 1, no = 0;
+  Float* tau = malloc(sizeof(Float) * ncl * ngpt);
+  Float* decoy = malloc(sizeof(Float) * nclp);
+  Float* zero = calloc(ncg, sizeof(Float));
+  Float* bc_a = malloc(sizeof(Float) * ncg);
+  rrtmgpb_expand_and_transpose(ncol, nbnd, ngpt, t->band_lims_gpt, sfc_emis_or_alb_dir, bc_a);
+  if (sw) {
+    Float* ssa = malloc(sizeof(Float) * ncl * ngpt); Float* g = malloc(sizeof(Float) * ncl * ngpt);
+    Float* bc_b = malloc(sizeof(Float) * ncg); Float* toa = malloc(sizeof(Float) * ncg);
+    Float* mu0l = malloc(sizeof(Float) * ncl);
+    rrtmgpb_gas_optics_fused(t, ncol, nlay, play, plev, tlay, vmr, col_dry, 2, tau, ssa, g, cld_kind, cld_tau, cld_ssa,
+                             cld_g, 0, NULL, NULL, NULL, NULL, NULL, 0, NULL, NULL, NULL, NULL);
+    rrtmgpb_expand_and_transpose(ncol, nbnd, ngpt, t->band_lims_gpt, sfc_alb_dif, bc_b);
+    rrtmgpb_broadcast_by_gpt(ncol, ngpt, solar_source, toa);
+    rrtmgpb_broadcast_by_lay(ncol, nlay, mu0, mu0l);
+    rte_sw_solver_2stream(&ncol, &nlay, &ngpt, &top, tau, ssa, g, mu0l, bc_a, bc_b, toa, decoy, decoy, decoy, &no, zero,
+                          &yes, flux_up, flux_dn, flux_dir);
+    free(ssa); free(g); free(bc_b); free(toa); free(mu0l);
+  } else {
+    Float* lay = malloc(sizeof(Float) * ncl * ngpt); Float* lev = malloc(sizeof(Float) * nclp * ngpt);
+    Float* sfc = malloc(sizeof(Float) * ncg); Float* jac = malloc(sizeof(Float) * ncg);
+    Float* Ds = malloc(sizeof(Float) * ncg * nmus);
+    for (int imu = 0; imu < nmus; ++imu)
+      for (size_t i = 0; i < ncg; ++i) Ds[i + ncg * imu] = Ds_host[imu];
+    const int sfc_lay = top_at_1 ? nlay : 1;
+    rrtmgpb_gas_optics_fused(t, ncol, nlay, play, plev, tlay, vmr, col_dry, 1, tau, NULL, NULL, cld_kind, cld_tau, cld_ssa,
+                             cld_g, 0, NULL, NULL, NULL, tlev, tsfc, sfc_lay, sfc, lay, lev, jac);
+    rte_lw_solver_noscat(&ncol, &nlay, &ngpt, &top, &nmus, Ds, wts_host, tau, lay, lev, bc_a, sfc, zero, decoy, decoy, &yes,
+                         flux_up, flux_dn, &no, jac, decoy, &no, tau, tau);
+    free(lay); free(lev); free(sfc); free(jac); free(Ds);
+  }
+  free(tau); free(decoy); free(zero); free(bc_a);
+}

@@ -10,12 +10,12 @@ import numpy as np
 
 from . import synthetic as syn
 from .frontend import (AerosolOptics, CloudOptics, FluxesBroadband, GasConcs, GasOptics, OpticalProps, SourceFuncLW,
-                       rte_lw, rte_lw_bygpoint, rte_sw)
+                       rte_lw, rte_lw_bygpoint, rte_lw_express, rte_sw, rte_sw_express)
 
 
 class AllSky:
     def __init__(self, ctx, ncol, nlay, kd_lw=None, kd_sw=None, do_clouds=True, profiles=None, col_offset=0,
-                 mu0=0.86, sfc_alb=0.06, emis=0.98, fused=None, do_aerosols=False, lw_2stream=False):
+                 mu0=0.86, sfc_alb=0.06, emis=0.98, fused=None, do_aerosols=False, lw_2stream=False, express=False):
         """do_aerosols: rrtmgp_allsky.F90:233-236,664-738.  lw_2stream: LW with 2-stream optical properties and
         rte_lw(use_2stream=.true.) (BASELINE config 5); the solver then returns g-point fluxes, which are summed
         with rte_sum_broadband (the reference leaves the broadband arrays unfilled here)."""
@@ -23,6 +23,10 @@ class AllSky:
             fused = os.environ.get("RRTMGPB_FUSED", "1") == "1"
         self.ctx, self.ncol, self.nlay, self.fused = ctx, ncol, nlay, fused
         self.do_aerosols, self.lw_2stream = do_aerosols, lw_2stream
+        # express: broadband fluxes straight from the state - atmos / sources (the (ncol,nlay,ngpt) arrays)
+        # are never allocated; clouds only (no aerosols, no LW two-stream)
+        self.express = express
+        assert not (express and (do_aerosols or lw_2stream))
         prof = profiles if profiles is not None else syn.compute_profiles(300.0, ncol, nlay)
         self.host_inputs = {}
         put = ctx.put
@@ -45,8 +49,9 @@ class AllSky:
             lw = type("LW", (), {})()
             lw.go = GasOptics(ctx, kd_lw)
             lw_kind = "2str" if lw_2stream else "1scl"
-            lw.atmos = OpticalProps.like(ctx, lw_kind, ncol, nlay, lw.go)
-            lw.sources = SourceFuncLW(ctx, ncol, nlay, kd_lw.ngpt)
+            if not express:
+                lw.atmos = OpticalProps.like(ctx, lw_kind, ncol, nlay, lw.go)
+                lw.sources = SourceFuncLW(ctx, ncol, nlay, kd_lw.ngpt)
             lw.t_sfc = put(np.ascontiguousarray(prof["t_lev"][:, sfc]))  # rrtmgp_allsky.F90:296
             lw.emis_sfc = put(np.full((kd_lw.nbnd, ncol), emis, order="F"))
             lw.flux_up, lw.flux_dn = ctx.zeros((ncol, nlay + 1)), ctx.zeros((ncol, nlay + 1))
@@ -66,8 +71,9 @@ class AllSky:
         if kd_sw is not None:
             sw = type("SW", (), {})()
             sw.go = GasOptics(ctx, kd_sw)
-            sw.atmos = OpticalProps.like(ctx, "2str", ncol, nlay, sw.go)
-            sw.toa_flux = ctx.zeros((ncol, kd_sw.ngpt))
+            if not express:
+                sw.atmos = OpticalProps.like(ctx, "2str", ncol, nlay, sw.go)
+                sw.toa_flux = ctx.zeros((ncol, kd_sw.ngpt))
             sw.mu0 = put(np.full(ncol, mu0))
             sw.sfc_alb_dir = put(np.full((kd_sw.nbnd, ncol), sfc_alb, order="F"))
             sw.sfc_alb_dif = put(np.full((kd_sw.nbnd, ncol), sfc_alb, order="F"))
@@ -111,6 +117,10 @@ class AllSky:
             lw.co.cloud_optics(self.lwp, self.iwp, self.rel, self.dei, lw.clouds)
         if self.do_aerosols:
             lw.ao.aerosol_optics(self.aero_type, self.aero_size, self.aero_mass, self.relhum, lw.aerosols)
+        if self.express:
+            rte_lw_express(self.ctx, lw.go, self.p_lay, self.p_lev, self.t_lay, lw.t_sfc, self.vmr, lw.emis_sfc, lw.fluxes,
+                           clouds=lw.clouds if self.do_clouds else None, tlev=self.t_lev)
+            return
         if self.fused:  # gas optics + clouds%increment(atmos) [+ aerosols%increment(atmos)] in one pass
             lw.go.gas_optics(self.p_lay, self.p_lev, self.t_lay, self.vmr, lw.atmos, t_sfc=lw.t_sfc,
                              sources=lw.sources, tlev=self.t_lev, fused=True,
@@ -141,6 +151,10 @@ class AllSky:
             sw.clouds.delta_scale()
         if self.do_aerosols:
             sw.ao.aerosol_optics(self.aero_type, self.aero_size, self.aero_mass, self.relhum, sw.aerosols)
+        if self.express:
+            rte_sw_express(self.ctx, sw.go, self.p_lay, self.p_lev, self.t_lay, self.vmr, sw.mu0, sw.sfc_alb_dir,
+                           sw.sfc_alb_dif, sw.fluxes, clouds=sw.clouds if self.do_clouds else None)
+            return
         if self.fused:  # aerosols%delta_scale() does not depend on the gas optics: it moves in front of the fused pass
             if self.do_aerosols:
                 sw.aerosols.delta_scale()

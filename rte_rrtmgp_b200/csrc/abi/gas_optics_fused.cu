@@ -26,6 +26,7 @@
 #include "../kernels/elementwise.cuh"
 #include "../kernels/gas_optics_gfast.cuh"
 #include "rrtmgp_b200_ext.h"
+#include "rte_kernels.h"
 
 using namespace rrtmgpb;
 
@@ -353,6 +354,51 @@ extern "C" void rrtmgpb_tables_changed(const void* kmajor) {
   g_abi_cache.clear();
 }
 
+namespace {
+// gas_tau_g_kernel for the bands p.band0 .. p.band0 + p.nband_sub - 1
+void launch_tau(const FusedParams& p, const TablesT& tt) {
+  const rrtmgpb_gas_tables* t = &p.t;
+  const size_t ncl = (size_t)p.ncol * p.nlay;
+  const bool sw = t->krayl != nullptr;
+  const int op_kind = p.op_kind, cld_kind = p.cld_kind, aer_kind = p.aer_kind;
+  KernelTimer timer(sw ? "gas_tau_fused[sw]" : "gas_tau_fused[lw]");
+  const unsigned grid = (unsigned)((long long)ceil_div((long long)ncl, kTauCells * kGThreads) * p.nband_sub);
+  // lane-private slots for the per-(cell, band) minor scalings: [contributor][cell slot][thread]
+  const size_t smem = (size_t)tt.maxm * kTauCells * kGThreads * sizeof(Float);
+// KIND 1: the common kinds as compile-time constants (LW 1scl += 1scl clouds, SW 2str += 2str clouds, no aerosols)
+#define GAS_TAU_LAUNCH1(SWV, VECV, AERV, KINDV)                                                                   \
+  do {                                                                                                            \
+    auto kern = gas_tau_g_kernel<SWV, VECV, AERV, KINDV>;                                                         \
+    if (smem > 48 * 1024) RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, kGThreads, smem, stream()>>>(p, tt);                                                             \
+  } while (0)
+#define GAS_TAU_LAUNCH(SWV, VECV)                                                                     \
+  if (aer_kind) GAS_TAU_LAUNCH1(SWV, VECV, true, 0);                                                  \
+  else if (op_kind == (SWV ? 2 : 1) && cld_kind == (SWV ? 2 : 1)) GAS_TAU_LAUNCH1(SWV, VECV, false, 1); \
+  else GAS_TAU_LAUNCH1(SWV, VECV, false, 0)
+  if (sw) {
+    if (tt.vec == 2) { GAS_TAU_LAUNCH(true, 2); } else { GAS_TAU_LAUNCH(true, 1); }
+  } else {
+    if (tt.vec == 2) { GAS_TAU_LAUNCH(false, 2); } else { GAS_TAU_LAUNCH(false, 1); }
+  }
+#undef GAS_TAU_LAUNCH
+#undef GAS_TAU_LAUNCH1
+  RB_LAUNCH_CHECK();
+}
+
+void launch_planck(const PlanckFusedParams& q, const TablesT& tt) {
+  KernelTimer timer("planck_fused");
+  // layers a thread marches through (its first level needs the Planck fractions of the layer above: 1/lay_per_chunk
+  // redundant work; B200, 65,536 x 72: 9 -> 5.40 ms, 12 -> 5.31, 18 -> 5.24, 36 -> 5.22); RRTMGPB_PLANCK_CHUNK overrides
+  static const int chunk_env = [] { const char* e = std::getenv("RRTMGPB_PLANCK_CHUNK"); return e ? std::atoi(e) : 0; }();
+  const int lay_per_chunk = chunk_env > 0 ? chunk_env : 18, nchunk = ceil_div(q.f.nlay, lay_per_chunk);
+  const unsigned grid = (unsigned)((long long)ceil_div(q.f.ncol, kGThreads) * nchunk * q.f.nband_sub);
+  if (tt.vec == 2) planck_g_kernel<2><<<grid, kGThreads, 0, stream()>>>(q, tt, lay_per_chunk, nchunk);
+  else planck_g_kernel<1><<<grid, kGThreads, 0, stream()>>>(q, tt, lay_per_chunk, nchunk);
+  RB_LAUNCH_CHECK();
+}
+}  // namespace
+
 extern "C" {
 
 void rrtmgpb_abi_table_cache(int on) { g_abi_cache_on = on ? 1 : 0; }
@@ -366,56 +412,228 @@ void rrtmgpb_gas_optics_fused(const rrtmgpb_gas_tables* t, int ncol, int nlay, c
                               const Float* cld_g, int aer_kind, const Float* aer_tau, const Float* aer_ssa,
                               const Float* aer_g, const Float* tlev, const Float* tsfc, int sfc_lay, Float* sfc_src,
                               Float* lay_src, Float* lev_src, Float* sfc_source_Jac) {
-  const size_t ncl = (size_t)ncol * nlay;
   FusedParams p;
   p.t = *t;
   p.ncol = ncol; p.nlay = nlay; p.play = play; p.plev = plev; p.tlay = tlay; p.vmr = vmr; p.col_dry_in = col_dry;
+  p.band0 = 0; p.nband_sub = t->nbnd; p.gpt0 = 0;
   p.op_kind = op_kind; p.tau = tau; p.ssa = ssa; p.g = g;
   p.cld_kind = cld_kind; p.cld_tau = cld_tau; p.cld_ssa = cld_ssa; p.cld_g = cld_g;
   p.aer_kind = aer_kind; p.aer_tau = aer_tau; p.aer_ssa = aer_ssa; p.aer_g = aer_g;
   const TablesT tt = tables_gfast(*t);
   Workspace w = prepare(p);
-  const bool sw = t->krayl != nullptr;
-  {
-    KernelTimer timer(sw ? "gas_tau_fused[sw]" : "gas_tau_fused[lw]");
-    const unsigned grid = (unsigned)((long long)ceil_div((long long)ncl, kTauCells * kGThreads) * t->nbnd);
-    // lane-private slots for the per-(cell, band) minor scalings: [contributor][cell slot][thread]
-    const size_t smem = (size_t)tt.maxm * kTauCells * kGThreads * sizeof(Float);
-// KIND 1: the common kinds as compile-time constants (LW 1scl += 1scl clouds, SW 2str += 2str clouds, no aerosols)
-#define GAS_TAU_LAUNCH1(SWV, VECV, AERV, KINDV)                                                                   \
-  do {                                                                                                            \
-    auto kern = gas_tau_g_kernel<SWV, VECV, AERV, KINDV>;                                                         \
-    if (smem > 48 * 1024) RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, kGThreads, smem, stream()>>>(p, tt);                                                             \
-  } while (0)
-#define GAS_TAU_LAUNCH(SWV, VECV)                                                                     \
-  if (aer_kind) GAS_TAU_LAUNCH1(SWV, VECV, true, 0);                                                  \
-  else if (op_kind == (SWV ? 2 : 1) && cld_kind == (SWV ? 2 : 1)) GAS_TAU_LAUNCH1(SWV, VECV, false, 1); \
-  else GAS_TAU_LAUNCH1(SWV, VECV, false, 0)
-    if (sw) {
-      if (tt.vec == 2) { GAS_TAU_LAUNCH(true, 2); } else { GAS_TAU_LAUNCH(true, 1); }
-    } else {
-      if (tt.vec == 2) { GAS_TAU_LAUNCH(false, 2); } else { GAS_TAU_LAUNCH(false, 1); }
-    }
-#undef GAS_TAU_LAUNCH
-#undef GAS_TAU_LAUNCH1
-    RB_LAUNCH_CHECK();
-  }
+  launch_tau(p, tt);
   if (lay_src) {
     PlanckFusedParams q;
     q.f = p; q.tlev = tlev; q.tsfc = tsfc; q.sfc_lay = sfc_lay;
     q.sfc_src = sfc_src; q.lay_src = lay_src; q.lev_src = lev_src; q.sfc_source_Jac = sfc_source_Jac;
-    KernelTimer timer("planck_fused");
-    // layers a thread marches through (its first level needs the Planck fractions of the layer above: 1/lay_per_chunk
-    // redundant work; B200, 65,536 x 72: 9 -> 5.40 ms, 12 -> 5.31, 18 -> 5.24, 36 -> 5.22); RRTMGPB_PLANCK_CHUNK overrides
-    static const int chunk_env = [] { const char* e = std::getenv("RRTMGPB_PLANCK_CHUNK"); return e ? std::atoi(e) : 0; }();
-    const int lay_per_chunk = chunk_env > 0 ? chunk_env : 18, nchunk = ceil_div(nlay, lay_per_chunk);
-    const unsigned grid = (unsigned)((long long)ceil_div(ncol, kGThreads) * nchunk * t->nbnd);
-    if (tt.vec == 2) planck_g_kernel<2><<<grid, kGThreads, 0, stream()>>>(q, tt, lay_per_chunk, nchunk);
-    else planck_g_kernel<1><<<grid, kGThreads, 0, stream()>>>(q, tt, lay_per_chunk, nchunk);
-    RB_LAUNCH_CHECK();
+    launch_planck(q, tt);
   }
   dev_free(w.block);
+}
+
+}  // extern "C"
+
+// ====================================================================================================
+// Express path: broadband fluxes straight from the atmospheric state.  No (ncol, nlay, ngpt) array
+// exists in HBM-sized form: columns are processed in chunks and, inside a chunk, a few bands at a time - gas optics
+// (+ cloud increment, + Planck sources) write the planes of those bands into a scratch that is sized to stay in the
+// 126 MB L2, and the register solver reads them straight back (TMA) and ADDS its spectrally integrated fluxes to the
+// chunk's flux arrays (band after band, in band order: deterministic).  The chunk's g-points can be split over grid
+// rows to fill the SMs; every row owns a copy of the flux arrays, summed in a fixed order at the end of the chunk.
+// Kernels are the headline path's (gas_tau_g_kernel / planck_g_kernel on a band sub-range, *_reg_kernel with
+// accumulate): per-g-point arithmetic is identical, only the association of the broadband sums differs
+// (sum over bands of per-band sums).  What it buys: the footprint of a step drops from ~0.9 MB to ~6 KB per column
+// (millions of columns stay resident) and the HBM traffic by the same factor.
+// ====================================================================================================
+namespace {
+
+int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return (e && *e) ? std::atoi(e) : dflt;
+}
+
+// dense copy of columns [c0, c0+n) of a Fortran (ncol, nrows) array, and back
+void gather_cols(Float* dst, const Float* src, int ncol, int c0, int n, size_t nrows) {
+  RB_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)n * sizeof(Float), src + c0, (size_t)ncol * sizeof(Float),
+                                  (size_t)n * sizeof(Float), nrows, cudaMemcpyDeviceToDevice, stream()));
+}
+
+// out(c0 + i, l) = sum over the `groups` partial copies, in group order
+__global__ void reduce_groups_kernel(int n, int nlev, int ncol, int c0, int groups, size_t stride, int narr,
+                                     const Float* part, Float* o0, Float* o1, Float* o2) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t per = (size_t)n * nlev;
+  if (k >= per) return;
+  const int i = (int)(k % n), l = (int)(k / n);
+  for (int a = 0; a < narr; ++a) {
+    Float* out = a == 0 ? o0 : (a == 1 ? o1 : o2);
+    if (!out) continue;
+    const Float* q = part + (size_t)a * per + k;   // arrays of one group are contiguous: [group][array][n*nlev]
+    Float acc = q[0];
+    for (int g = 1; g < groups; ++g) acc = acc + q[(size_t)g * stride];
+    out[(size_t)c0 + i + (size_t)ncol * l] = acc;
+  }
+}
+
+struct ExpressPlan {
+  int nc, bands_per_group, rows;
+};
+// columns per chunk / bands per solver launch / grid rows: defaults keep the scratch of one launch (nc columns x the
+// g-points of one band x 3 planes) near 64 MB - L2 resident - with one 16-column CTA per SM slot pair
+ExpressPlan express_plan(int ncol, int nlay) {
+  ExpressPlan pl;
+  pl.nc = env_int("RRTMGPB_EXPRESS_NC", 148 * 16);
+  pl.bands_per_group = env_int("RRTMGPB_EXPRESS_BANDS", 1);
+  pl.rows = env_int("RRTMGPB_EXPRESS_ROWS", 2);
+  if (pl.nc > ncol) pl.nc = ncol;
+  if (pl.nc < 1) pl.nc = 1;
+  if (pl.nc % 2) pl.nc += (pl.nc < ncol) ? 1 : 0;  // even chunk widths keep the scratch planes TMA-describable (16-byte row stride)
+  (void)nlay;
+  return pl;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rrtmgpb_express_supported(int ncol, int nlay) {
+  (void)ncol;
+  return (rrtmgpb_get_solver_variant() == 0 && nlay <= 80) ? 1 : 0;   // register solvers (accumulate mode)
+}
+
+// see include/rrtmgp_b200_ext.h
+void rrtmgpb_express(const rrtmgpb_gas_tables* t, int ncol, int nlay, int top_at_1, const Float* play, const Float* plev,
+                     const Float* tlay, const Float* tlev, const Float* tsfc, const Float* vmr, const Float* col_dry,
+                     int cld_kind, const Float* cld_tau, const Float* cld_ssa, const Float* cld_g,
+                     const Float* sfc_emis_or_alb_dir, const Float* sfc_alb_dif, const Float* mu0,
+                     const Float* solar_source, int nmus, const Float* Ds_host, const Float* wts_host, Float* flux_up,
+                     Float* flux_dn, Float* flux_dir) {
+  OpName op_name__(__func__);
+  const bool sw = t->krayl != nullptr;
+  const int ngpt = t->ngpt, nbnd = t->nbnd, ngas = t->ngas, nlev = nlay + 1;
+  // the caller's arrays: used in place when they live on the device, staged once per call otherwise
+  const size_t Ncl = (size_t)ncol * nlay, Nclp = (size_t)ncol * nlev;
+  DevArg<Float> a_play(play, Ncl, Dir::In), a_plev(plev, Nclp, Dir::In), a_tlay(tlay, Ncl, Dir::In),
+      a_tlev(tlev, Nclp, Dir::In, !sw), a_tsfc(tsfc, ncol, Dir::In, !sw), a_vmr(vmr, Ncl * ngas, Dir::In),
+      a_cd(col_dry, Ncl, Dir::In, col_dry != nullptr), a_ct(cld_tau, Ncl * nbnd, Dir::In, cld_kind != 0),
+      a_cw(cld_ssa, Ncl * nbnd, Dir::In, cld_kind == 2), a_cg(cld_g, Ncl * nbnd, Dir::In, cld_kind == 2 && sw),
+      a_sa(sfc_emis_or_alb_dir, (size_t)nbnd * ncol, Dir::In), a_sb(sfc_alb_dif, (size_t)nbnd * ncol, Dir::In, sw),
+      a_mu0(mu0, ncol, Dir::In, sw), a_sol(solar_source, ngpt, Dir::In, sw);
+  DevArg<Float> a_fu(flux_up, Nclp, Dir::Out), a_fd(flux_dn, Nclp, Dir::Out), a_fr(flux_dir, Nclp, Dir::Out, sw);
+  play = a_play; plev = a_plev; tlay = a_tlay; tlev = a_tlev; tsfc = a_tsfc; vmr = a_vmr; col_dry = a_cd;
+  cld_tau = a_ct; cld_ssa = a_cw; cld_g = a_cg; sfc_emis_or_alb_dir = a_sa; sfc_alb_dif = a_sb; mu0 = a_mu0;
+  solar_source = a_sol; flux_up = a_fu; flux_dn = a_fd; flux_dir = a_fr;
+  struct Trust { Trust() { tl_trust_device_ptrs = true; } ~Trust() { tl_trust_device_ptrs = false; } } trust__;  // see DevArg
+  const TablesT tt = tables_gfast(*t);
+  const std::vector<int> bl = to_host(t->band_lims_gpt, 2 * (size_t)nbnd);
+  const bool staged = rrtmgpb_express_supported(ncol, nlay) != 0;   // else: one launch per chunk over all bands
+  ExpressPlan pl = express_plan(ncol, nlay);
+  if (!staged) { pl.bands_per_group = nbnd; pl.rows = 1; }
+  const int nc = pl.nc;
+  int ng_max = 0;
+  for (int b0 = 0; b0 < nbnd; b0 += pl.bands_per_group) {
+    const int b1 = std::min(nbnd, b0 + pl.bands_per_group);
+    ng_max = std::max(ng_max, bl[2 * (b1 - 1) + 1] - bl[2 * b0] + 1);
+  }
+  const int narr = sw ? 3 : 2;
+  const size_t ncl = (size_t)nc * nlay, nclp = (size_t)nc * nlev;
+  // ---- scratch, allocated once (stream-ordered pool)
+  const size_t nplane = sw ? 3 : 3;  // SW: tau, ssa, g ; LW: tau, lay_source, lev_source (nlev rows)
+  Float* planes = static_cast<Float*>(dev_alloc((ncl * 2 + nclp) * (size_t)ng_max * sizeof(Float)));
+  (void)nplane;
+  Float* in2d = static_cast<Float*>(dev_alloc((ncl * (3 + (size_t)ngas + 3 * (size_t)nbnd) + 2 * nclp + 4 * (size_t)nc) * sizeof(Float)));
+  Float* bnd = static_cast<Float*>(dev_alloc((size_t)nc * ngpt * 4 * sizeof(Float) + (size_t)nc * ng_max * (nmus + 2) * sizeof(Float)));
+  const size_t gstride = (size_t)narr * nclp;
+  Float* part = static_cast<Float*>(dev_alloc(gstride * pl.rows * sizeof(Float)));
+  Float* decoy = static_cast<Float*>(dev_alloc(nclp * sizeof(Float)));
+  Float* wts_dev = static_cast<Float*>(dev_alloc((size_t)std::max(nmus, 1) * sizeof(Float)));
+  if (!sw) RB_CUDA_CHECK(cudaMemcpyAsync(wts_dev, wts_host, (size_t)nmus * sizeof(Float), cudaMemcpyHostToDevice, stream()));
+  // chunk-local inputs
+  Float* c_play = in2d; Float* c_tlay = c_play + ncl; Float* c_cd = c_tlay + ncl; Float* c_vmr = c_cd + ncl;
+  Float* c_ct = c_vmr + ncl * ngas; Float* c_cw = c_ct + ncl * nbnd; Float* c_cg = c_cw + ncl * nbnd;
+  Float* c_plev = c_cg + ncl * nbnd; Float* c_tlev = c_plev + nclp;
+  // boundary arrays of the chunk on all g-points: a g-point sub-range of an (nc, ngpt) array is a contiguous slab
+  Float* b_a = bnd; Float* b_b = b_a + (size_t)nc * ngpt; Float* b_toa = b_b + (size_t)nc * ngpt; Float* b_zero = b_toa + (size_t)nc * ngpt;
+  Float* b_Ds = b_zero + (size_t)nc * ngpt; Float* b_sfc = b_Ds + (size_t)nc * ng_max * nmus; Float* b_jac = b_sfc + (size_t)nc * ng_max;
+  Float* mu0_lay = static_cast<Float*>(dev_alloc(ncl * sizeof(Float)));
+
+  for (int c0 = 0; c0 < ncol; c0 += nc) {
+    const int n = std::min(nc, ncol - c0);
+    const size_t nl = (size_t)n * nlay, nlp = (size_t)n * nlev;
+    // ---- gather the chunk's columns (dense (n, nlay[, k]) copies of the strided slices)
+    gather_cols(c_play, play, ncol, c0, n, nlay);
+    gather_cols(c_tlay, tlay, ncol, c0, n, nlay);
+    gather_cols(c_plev, plev, ncol, c0, n, nlev);
+    gather_cols(c_vmr, vmr, ncol, c0, n, (size_t)nlay * ngas);
+    if (col_dry) gather_cols(c_cd, col_dry, ncol, c0, n, nlay);
+    if (cld_kind) {
+      gather_cols(c_ct, cld_tau, ncol, c0, n, (size_t)nlay * nbnd);
+      if (cld_kind == 2) {
+        gather_cols(c_cw, cld_ssa, ncol, c0, n, (size_t)nlay * nbnd);
+        if (sw) gather_cols(c_cg, cld_g, ncol, c0, n, (size_t)nlay * nbnd);
+      }
+    }
+    if (!sw) gather_cols(c_tlev, tlev, ncol, c0, n, nlev);
+    // ---- per-cell state of the chunk
+    FusedParams p;
+    p.t = *t;
+    p.ncol = n; p.nlay = nlay; p.play = c_play; p.plev = c_plev; p.tlay = c_tlay; p.vmr = c_vmr;
+    p.col_dry_in = col_dry ? c_cd : nullptr;
+    p.op_kind = sw ? 2 : 1;
+    p.cld_kind = cld_kind; p.cld_tau = c_ct; p.cld_ssa = c_cw; p.cld_g = c_cg;
+    p.aer_kind = 0; p.aer_tau = p.aer_ssa = p.aer_g = nullptr;
+    Workspace w = prepare(p);
+    // ---- boundary conditions of the chunk (mo_rte_lw.F90:264-282, mo_rte_sw.F90:266-280)
+    rrtmgpb_expand_and_transpose(n, nbnd, ngpt, t->band_lims_gpt, sfc_emis_or_alb_dir + (size_t)nbnd * c0, b_a);
+    RB_CUDA_CHECK(cudaMemsetAsync(b_zero, 0, (size_t)n * ngpt * sizeof(Float), stream()));
+    if (sw) {
+      rrtmgpb_expand_and_transpose(n, nbnd, ngpt, t->band_lims_gpt, sfc_alb_dif + (size_t)nbnd * c0, b_b);
+      rrtmgpb_broadcast_by_gpt(n, ngpt, solar_source, b_toa);
+      rrtmgpb_broadcast_by_lay(n, nlay, mu0 + c0, mu0_lay);
+    }
+    RB_CUDA_CHECK(cudaMemsetAsync(part, 0, gstride * pl.rows * sizeof(Float), stream()));
+    int ng_last = -1;
+    for (int b0 = 0; b0 < nbnd; b0 += pl.bands_per_group) {
+      const int b1 = std::min(nbnd, b0 + pl.bands_per_group);
+      const int g0 = bl[2 * b0] - 1, ng = bl[2 * (b1 - 1) + 1] - g0;   // 0-based first g-point, count
+      p.band0 = b0; p.nband_sub = b1 - b0; p.gpt0 = g0;
+      Float* s_tau = planes; Float* s_b = s_tau + nl * ng; Float* s_c = s_b + nl * ng;
+      p.tau = s_tau; p.ssa = sw ? s_b : nullptr; p.g = sw ? s_c : nullptr;
+      launch_tau(p, tt);
+      const Bool top = top_at_1 != 0, yes = 1, no = 0;
+      tl_express.accumulate = 1; tl_express.groups = staged ? pl.rows : 1; tl_express.group_stride = gstride;
+      if (!staged) tl_express.accumulate = 0;
+      if (sw) {
+        rte_sw_solver_2stream(&n, &nlay, &ng, &top, s_tau, s_b, s_c, mu0_lay, b_a + (size_t)n * g0, b_b + (size_t)n * g0,
+                              b_toa + (size_t)n * g0, decoy, decoy, decoy, &no, b_zero, &yes, part, part + nlp, part + 2 * nlp);
+      } else {
+        PlanckFusedParams q;
+        q.f = p; q.tlev = c_tlev; q.tsfc = tsfc + c0; q.sfc_lay = top_at_1 ? nlay : 1;
+        q.sfc_src = b_sfc; q.lay_src = s_b; q.lev_src = s_c; q.sfc_source_Jac = b_jac;
+        launch_planck(q, tt);
+        if (ng != ng_last) {   // secants: the same value for every column and g-point of an angle (mo_rte_lw.F90:357-365)
+          for (int imu = 0; imu < nmus; ++imu) {
+            const int n2 = ng;
+            set_to_scalar_2D(&n, &n2, b_Ds + (size_t)n * ng * imu, &Ds_host[imu]);
+          }
+          ng_last = ng;
+        }
+        rte_lw_solver_noscat(&n, &nlay, &ng, &top, &nmus, b_Ds, wts_dev, s_tau, s_b, s_c, b_a + (size_t)n * g0, b_sfc,
+                             b_zero, decoy, decoy, &yes, part, part + nlp, &no, b_jac, decoy, &no, s_tau, s_tau);
+      }
+      tl_express = ExpressSolverMode();
+    }
+    // ---- sum the grid rows' copies (fixed order) into the caller's arrays
+    {
+      KernelTimer timer("express_reduce");
+      // partial layout per row: [array a][n*nlev]; rows are gstride apart (sized for nc columns)
+      reduce_groups_kernel<<<ceil_div((long long)nlp, 256), 256, 0, stream()>>>(
+          n, nlev, ncol, c0, staged ? pl.rows : 1, gstride, narr, part, flux_up, flux_dn, sw ? flux_dir : nullptr);
+      RB_LAUNCH_CHECK();
+    }
+    dev_free(w.block);
+  }
+  dev_free(mu0_lay); dev_free(wts_dev); dev_free(decoy); dev_free(part); dev_free(bnd); dev_free(in2d); dev_free(planes);
 }
 
 }  // extern "C"

@@ -17,6 +17,7 @@
 //     mo_rte_solver_kernels.F90:216-218,601-604) - deterministic, no atomics - and are written once.
 //   * `intent(out)` arrays whose controlling flag is false are decoys that may alias:
 //     they are never read or written here and no pointer is __restrict__.
+#include <algorithm>
 #include <atomic>
 #include <climits>
 #include <cstdlib>
@@ -650,8 +651,9 @@ void rte_lw_solver_noscat(const int* ncol_, const int* nlay_, const int* ngpt_, 
     q.sfc_emis = p.sfc_emis; q.sfc_src = p.sfc_src; q.inc_flux = p.inc_flux; q.flux_up = p.flux_up;
     q.flux_dn = p.flux_dn; q.do_broadband = bb; q.bb_up = p.bb_up; q.bb_dn = p.bb_dn; q.do_jac = jac;
     q.sfc_srcJac = p.sfc_srcJac; q.flux_upJac = p.flux_upJac;
-    const int groups = (bb || jac) ? 1 : reg_gpt_groups(ncol, ngpt);
+    const int groups = (bb || jac) ? std::min(tl_express.groups, ngpt) : reg_gpt_groups(ncol, ngpt);
     q.gpt_per_block = ceil_div(ngpt, groups);
+    q.accumulate = tl_express.accumulate; q.group_stride = tl_express.group_stride;
     dim3 grid(ceil_div(ncol, (kRegThreads / 32) * kRegCols), ceil_div(ngpt, q.gpt_per_block));
     // TMA tile staging of tau / lay_source / lev_source (kernels/tma.cuh) whenever the planes can be described
     LwTmaMaps maps;
@@ -806,8 +808,9 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
     q.mu0 = p.mu0; q.sfc_alb_dir = p.sfc_alb_dir; q.sfc_alb_dif = p.sfc_alb_dif; q.inc_flux_dir = p.inc_flux_dir;
     q.flux_up = p.flux_up; q.flux_dn = p.flux_dn; q.flux_dir = p.flux_dir; q.has_dif_bc = bc;
     q.inc_flux_dif = p.inc_flux_dif; q.do_broadband = bb; q.bb_up = p.bb_up; q.bb_dn = p.bb_dn; q.bb_dir = p.bb_dir;
-    const int groups = bb ? 1 : reg_gpt_groups(ncol, ngpt);
+    const int groups = bb ? std::min(tl_express.groups, ngpt) : reg_gpt_groups(ncol, ngpt);
     q.gpt_per_block = ceil_div(ngpt, groups);
+    q.accumulate = tl_express.accumulate; q.group_stride = tl_express.group_stride;
     dim3 grid(ceil_div(ncol, (kRegThreads / 32) * kRegCols), ceil_div(ngpt, q.gpt_per_block));
     // TMA tile staging of tau / ssa / g (kernels/tma.cuh) whenever the planes can be described
     SwTmaMaps maps;

@@ -70,6 +70,16 @@ bool tables_gfast_abi(const Float* kmajor, const Float* kminor_lower, const Floa
                       int npres, int ngpt, int nkl, int nku, const Float** kmajorT, const Float** kminorT_lower,
                       const Float** kminorT_upper, int* gp, int* pitch_lower, int* pitch_upper);
 
+// Express path (gas_optics_fused.cu -> solvers_abi.cu), per calling thread: the next broadband solver call ADDS its
+// spectrally integrated fluxes to the output arrays (accumulate) and splits its g-points over `groups` grid rows, each
+// row owning the copy of the outputs `group_stride` elements after the previous one.
+struct ExpressSolverMode { int accumulate = 0; int groups = 1; size_t group_stride = 0; };
+extern thread_local ExpressSolverMode tl_express;
+// true while a library-internal driver (the express path) calls the ABI entry points with arrays it allocated itself:
+// DevArg then skips the per-pointer provenance query (cudaPointerGetAttributes, ~1 us each, 20 per solver call -
+// as much host time as the GPU needs for one of the express path's small launches)
+extern thread_local bool tl_trust_device_ptrs;
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- argument staging ----------------------------------------------------------------------
@@ -84,7 +94,7 @@ class DevArg {
   DevArg(const T* p, size_t count, Dir dir, bool used = true, size_t align = 0)
       : host_(const_cast<T*>(p)), n_(count), dir_(dir), on_device_(false) {
     if (!used || p == nullptr || count == 0) { dev_ = const_cast<T*>(p); staged_ = false; return; }
-    on_device_ = is_device_ptr(p);
+    on_device_ = tl_trust_device_ptrs || is_device_ptr(p);
     if (on_device_ && (align == 0 || reinterpret_cast<uintptr_t>(p) % align == 0)) {
       dev_ = const_cast<T*>(p); staged_ = false; return;
     }

@@ -784,6 +784,110 @@ int rrtmgpb_gas_optics_ext_fused(const rrtmgpb_gas_optics_t* go, int ncol, int n
 }
 
 // ------------------------------------------------------------------------------------------------
+// Express path: gas_optics + clouds%increment(atmos) + rte_lw / rte_sw with ty_fluxes_broadband in ONE
+// call that never allocates a (ncol, nlay, ngpt) array.  Same checks and error strings as the calls it replaces
+// (mo_gas_optics_rrtmgp.F90:491-521,285-301; mo_optical_props.F90:893-905; mo_rte_lw.F90:170-262; mo_rte_sw.F90:176-191).
+// ------------------------------------------------------------------------------------------------
+static int express_impl(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play, const Float* plev,
+                        const Float* tlay, const Float* tsfc, const Float* vmr, const Float* col_dry, const Float* tlev,
+                        const rrtmgpb_optical_props* clouds, const Float* sfc_a, const Float* sfc_b, const Float* mu0,
+                        int n_gauss_angles, rrtmgpb_fluxes_broadband* fluxes, char* errmsg) {
+  const rrtmgpb_kdist& k = go->h;
+  const bool sw = go->solar_source != nullptr;
+  const char* who = sw ? "rte_sw" : "rte_lw";
+  const size_t ncl = (size_t)ncol * nlay, nclp = ncl + ncol;
+  std::string msg;
+  if (!fluxes || !(fluxes->flux_up || fluxes->flux_dn || fluxes->flux_net || (sw && fluxes->flux_dn_dir)))
+    return fail(errmsg, std::string(who) + ": no space allocated for fluxes");
+  if (g_check_values) {
+    if (rrtmgpb_any_vals_outside(ncl, play, nullptr, k.press_ref_min, k.press_ref_max))
+      msg = "gas_optics(): array play has values outside range";
+    if (rrtmgpb_any_vals_less_than(nclp, plev, nullptr, 0)) msg = "gas_optics(): array plev has values outside range";
+    if (rrtmgpb_any_vals_outside(ncl, tlay, nullptr, k.temp_ref_min, k.temp_ref_max))
+      msg = "gas_optics(): array tlay has values outside range";
+    if (col_dry && rrtmgpb_any_vals_less_than(ncl, col_dry, nullptr, 0))
+      msg = "gas_optics(): array col_dry has values outside range";
+    if (!sw && rrtmgpb_any_vals_outside(ncol, tsfc, nullptr, k.temp_ref_min, k.temp_ref_max))
+      msg = "gas_optics(): array tsfc has values outside range";
+    if (!sw && tlev && rrtmgpb_any_vals_outside(nclp, tlev, nullptr, k.temp_ref_min, k.temp_ref_max))
+      msg = "gas_optics(): array tlev has values outside range";
+    if (sw) {
+      if (rrtmgpb_any_vals_outside(ncol, mu0, nullptr, -1, 1)) msg = "rte_sw: one or more mu0 < -1 or > 1";
+      if (rrtmgpb_any_vals_outside((size_t)k.nbnd * ncol, sfc_a, nullptr, 0, 1)) msg = "rte_sw: sfc_alb_dir out of bounds [0,1]";
+      if (rrtmgpb_any_vals_outside((size_t)k.nbnd * ncol, sfc_b, nullptr, 0, 1)) msg = "rte_sw: sfc_alb_dif out of bounds [0,1]";
+    } else {
+      if (rrtmgpb_any_vals_outside((size_t)k.nbnd * ncol, sfc_a, nullptr, 0, 1)) msg = "rte_lw: sfc_emis has values < 0 or > 1";
+      if (n_gauss_angles > max_gauss_pts) msg = "rte_lw: asking for too many quadrature points for no-scattering calculation";
+      if (n_gauss_angles < 0) msg = "rte_lw: have to ask for at least one quadrature point for no-scattering calculation";
+    }
+  }
+  int cld_kind = 0;
+  if (msg.empty() && clouds) {
+    if (clouds->ncol != ncol || clouds->nlay != nlay)
+      msg = "ty_optical_props%increment: optical properties objects have different ncol and/or nlay";
+    else if (clouds->nband != k.nbnd || clouds->ngpt != k.nbnd)
+      msg = "ty_optical_props%increment: optical properties objects have incompatible g-point structures";
+    else if (clouds->kind == RRTMGPB_NSTR)
+      msg = "ty_optical_props%increment: n-stream properties are not supported by the fused path";
+    else if (g_check_values) {
+      char verr[RRTMGPB_ERRLEN];
+      if (rrtmgpb_op_validate(clouds, verr)) msg = verr;
+    }
+    cld_kind = clouds->kind;
+  }
+  if (!msg.empty()) return fail(errmsg, msg);
+  Float a = 0, b = 0;  // top_at_1 = play(1,1) < play(1,nlay), mo_gas_optics_rrtmgp.F90:258
+  rrtmgpb_mem_to_host(&a, play, sizeof(Float));
+  rrtmgpb_mem_to_host(&b, play + (size_t)ncol * (nlay - 1), sizeof(Float));
+  const int top_at_1 = a < b;
+  Float* tlev_alloc = nullptr;
+  const Float* tlev_wk = tlev;
+  if (!sw && !tlev) {
+    tlev_alloc = static_cast<Float*>(rrtmgpb_mem_alloc(nclp * sizeof(Float)));
+    rrtmgpb_interpolate_tlev(ncol, nlay, play, plev, tlay, tlev_alloc);
+    tlev_wk = tlev_alloc;
+  }
+  const int nmus = n_gauss_angles > 0 ? n_gauss_angles : 1;
+  Float Ds[max_gauss_pts], wts[max_gauss_pts];
+  for (int imu = 0; imu < nmus; ++imu) {  // mo_rte_lw.F90:146-160,357-365
+    Ds[imu] = (Float)1 / (Float)gauss_mus[nmus - 1][imu];
+    wts[imu] = (Float)gauss_wts[nmus - 1][imu];
+  }
+  Float *up = fluxes->flux_up, *dn = fluxes->flux_dn, *dir = fluxes->flux_dn_dir, *up_t = nullptr, *dn_t = nullptr, *dir_t = nullptr;
+  if (!up) up = up_t = static_cast<Float*>(rrtmgpb_mem_alloc(nclp * sizeof(Float)));
+  if (!dn) dn = dn_t = static_cast<Float*>(rrtmgpb_mem_alloc(nclp * sizeof(Float)));
+  if (sw && !dir) dir = dir_t = static_cast<Float*>(rrtmgpb_mem_alloc(nclp * sizeof(Float)));
+  const rrtmgpb_gas_tables t = tables_of(go);
+  rrtmgpb_express(&t, ncol, nlay, top_at_1, play, plev, tlay, tlev_wk, tsfc, vmr, col_dry, cld_kind,
+                  clouds ? clouds->tau : nullptr, clouds ? clouds->ssa : nullptr, clouds ? clouds->g : nullptr, sfc_a, sfc_b,
+                  mu0, go->solar_source, nmus, Ds, wts, up, dn, dir);
+  if (fluxes->flux_net) {
+    const int nlev = nlay + 1;
+    rte_net_broadband_precalc(&ncol, &nlev, dn, up, fluxes->flux_net);
+  }
+  rrtmgpb_mem_free(tlev_alloc); rrtmgpb_mem_free(up_t); rrtmgpb_mem_free(dn_t); rrtmgpb_mem_free(dir_t);
+  return ok(errmsg);
+}
+
+int rrtmgpb_rte_lw_express(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play, const Float* plev,
+                           const Float* tlay, const Float* tsfc, const Float* vmr, const Float* col_dry, const Float* tlev,
+                           const rrtmgpb_optical_props* clouds, const Float* sfc_emis, int n_gauss_angles,
+                           rrtmgpb_fluxes_broadband* fluxes, char* errmsg) {
+  if (!go->totplnk) return fail(errmsg, "gas_optics(): no internal (Planck) source tables loaded");
+  return express_impl(go, ncol, nlay, play, plev, tlay, tsfc, vmr, col_dry, tlev, clouds, sfc_emis, nullptr, nullptr,
+                      n_gauss_angles, fluxes, errmsg);
+}
+
+int rrtmgpb_rte_sw_express(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, const Float* play, const Float* plev,
+                           const Float* tlay, const Float* vmr, const Float* col_dry, const rrtmgpb_optical_props* clouds,
+                           const Float* mu0, const Float* sfc_alb_dir, const Float* sfc_alb_dif,
+                           rrtmgpb_fluxes_broadband* fluxes, char* errmsg) {
+  if (!go->solar_source) return fail(errmsg, "gas_optics(): no external (solar) source loaded");
+  return express_impl(go, ncol, nlay, play, plev, tlay, nullptr, vmr, col_dry, nullptr, clouds, sfc_alb_dir, sfc_alb_dif,
+                      mu0, 0, fluxes, errmsg);
+}
+
+// ------------------------------------------------------------------------------------------------
 // ty_cloud_optics_rrtmgp (LUT)
 // ------------------------------------------------------------------------------------------------
 struct rrtmgpb_cloud_optics_t {

@@ -66,6 +66,10 @@ struct GasAux {
 struct FusedParams {
   rrtmgpb_gas_tables t;
   int ncol, nlay;
+  // band sub-range of this launch (express path: the planes of a few bands at a time live in an L2-sized scratch):
+  // bands band0 .. band0+nband_sub-1; output planes are indexed from g-point gpt0 (0-based first g-point of band0), so a
+  // sub-range writes a dense (ncol, nlay, ng_sub) array.  Whole k-distribution: band0 = 0, nband_sub = nbnd, gpt0 = 0.
+  int band0, nband_sub, gpt0;
   const Float *play, *plev, *tlay, *vmr, *col_dry_in;
   CellState cs;
   // outputs
@@ -330,7 +334,7 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
     const Float* kr = SW ? tt.krayl + (size_t)s_p * tt.gp * itropo + (gS - 1) : nullptr;
     const Float* r0 = SW ? kr + (size_t)((jtemp - 1) + s_eta * (je0 - 1)) * tt.gp : nullptr;
     const Float* r1 = SW ? kr + (size_t)(jtemp + s_eta * (je1 - 1)) * tt.gp : nullptr;
-    const size_t goff = ncl * (size_t)(gS - 1);
+    const size_t goff = ncl * (size_t)(gS - 1 - p.gpt0);
     // one output value: absorption tabs, Rayleigh tray (0 without scattering) of cell k at chunk position i
     auto finish = [&](int k, int i, Float tabs, Float tray) {
       Float to = tabs, ss = 0, gg = 0;
@@ -415,8 +419,8 @@ template <bool SW, int VEC, bool AER, int KIND>
 __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_LW) gas_tau_g_kernel(const FusedParams p, const TablesT tt) {
   const rrtmgpb_gas_tables& t = p.t;
   const size_t ncl = (size_t)p.ncol * p.nlay;
-  const int ibnd = blockIdx.x % t.nbnd;
-  const size_t cbase = (size_t)(blockIdx.x / t.nbnd) * (kTauCells * kGThreads) + threadIdx.x;
+  const int ibnd = p.band0 + blockIdx.x % p.nband_sub;
+  const size_t cbase = (size_t)(blockIdx.x / p.nband_sub) * (kTauCells * kGThreads) + threadIdx.x;
   if (cbase >= ncl) return;
   // minor-contributor scalings of this thread's cells: [contributor of the band][cell slot][thread], lane-private
   // (no barrier: a thread only reads what it wrote); tt.maxm contributors at most
@@ -548,8 +552,8 @@ __global__ void __launch_bounds__(kGThreads, RB_PLANCK_MINB) planck_g_kernel(con
                                                                 int nchunk) {
   const FusedParams& p = q.f;
   const rrtmgpb_gas_tables& t = p.t;
-  const int ibnd = blockIdx.x % t.nbnd;
-  const int rest = blockIdx.x / t.nbnd;
+  const int ibnd = p.band0 + blockIdx.x % p.nband_sub;
+  const int rest = blockIdx.x / p.nband_sub;
   const int ichunk = rest % nchunk;
   const int icol = (rest / nchunk) * blockDim.x + threadIdx.x;
   if (icol >= p.ncol) return;
@@ -590,8 +594,8 @@ __global__ void __launch_bounds__(kGThreads, RB_PLANCK_MINB) planck_g_kernel(con
         B_sfc = planck_band_f(t, ts, delta_r, tab);
         B_sfc1 = planck_band_f(t, ts + (Float)1.0, delta_r, tab);
       }
-      Float* lay_c = q.lay_src + c + ncl * (size_t)(gS - 1);
-      Float* lev_c = q.lev_src + c + nclp * (size_t)(gS - 1);
+      Float* lay_c = q.lay_src + c + ncl * (size_t)(gS - 1 - p.gpt0);
+      Float* lev_c = q.lev_src + c + nclp * (size_t)(gS - 1 - p.gpt0);
 #pragma unroll
       for (int sub = 0; sub < kPG; sub += kGG) {
         if (sub < n) {
@@ -608,8 +612,8 @@ __global__ void __launch_bounds__(kGThreads, RB_PLANCK_MINB) planck_g_kernel(con
                 __stcs(lev_c, (ilay == 0) ? pf[i] * B_lev : sqrt(pf_prev[sub + i] * pf[i]) * B_lev);   // :695-701
                 lay_c += ncl; lev_c += nclp;
                 if (is_sfc) {
-                  q.sfc_src[icol + ncol * (size_t)(gS + sub + i - 1)] = pf[i] * B_sfc;            // :650-653
-                  q.sfc_source_Jac[icol + ncol * (size_t)(gS + sub + i - 1)] = pf[i] * (B_sfc1 - B_sfc);
+                  q.sfc_src[icol + ncol * (size_t)(gS + sub + i - 1 - p.gpt0)] = pf[i] * B_sfc;            // :650-653
+                  q.sfc_source_Jac[icol + ncol * (size_t)(gS + sub + i - 1 - p.gpt0)] = pf[i] * (B_sfc1 - B_sfc);
                 }
                 pf_prev[sub + i] = pf[i];
               }
@@ -624,7 +628,7 @@ __global__ void __launch_bounds__(kGThreads, RB_PLANCK_MINB) planck_g_kernel(con
       const Float B_top = planck_band_f(t, q.tlev[icol + ncol * p.nlay], delta_r, tab);
 #pragma unroll
       for (int i = 0; i < kPG; ++i)
-        if (i < n) q.lev_src[icol + ncol * p.nlay + nclp * (size_t)(gS + i - 1)] = pf_prev[i] * B_top;
+        if (i < n) q.lev_src[icol + ncol * p.nlay + nclp * (size_t)(gS + i - 1 - p.gpt0)] = pf_prev[i] * B_top;
     }
   }
 }

@@ -90,7 +90,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // reciprocal leaves the 9-step dependent chain: the chain is 2 multiply-adds deep per layer, the reciprocals of all
 // levels are then independent of each other (see adding_reg)
 #ifndef RB_ADD_HOMOG
-#define RB_ADD_HOMOG 1
+#define RB_ADD_HOMOG 0   // measured on B200: 13.56 (1) vs 13.51 ms (0) for the SW solver - no gain, so the reference's per-layer form stays
 #endif
 // 1: Rdir/Tdir's RT_term*w0/(1 - k^2 mu0^2) shares ONE reciprocal with RT_term itself (see sw cell)
 #ifndef RB_SW_MERGED_DIV
@@ -193,6 +193,11 @@ struct LwNoscatRegParams {
   const Float* sfc_srcJac;
   Float* flux_upJac;
   int gpt_per_block;
+  // express path (spectrally integrated outputs only): the g-points of a launch may be split over blockIdx.y, every
+  // group adding into its OWN copy of the outputs (bb + blockIdx.y * group_stride; summed afterwards in a fixed order:
+  // deterministic, no atomics), and a launch may add to what earlier launches (other bands) left there
+  int accumulate;
+  size_t group_stride;
 };
 
 template <int CL>
@@ -403,19 +408,22 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
   }
   // ---------------- epilogue: spectrally integrated outputs (:233-238) ----------------
   if (col_ok && (BB || JAC)) {
+    const size_t goff = p.group_stride * blockIdx.y;  // 0 unless the express path splits a launch's g-points
+    Float *bu = p.bb_up + goff, *bd = p.bb_dn + goff, *bj = p.flux_upJac + goff;
+    auto put = [&](Float* dst, size_t o2, Float v) { dst[o2] = p.accumulate ? dst[o2] + v : v; };
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
       const int klev = k0 + i + 1;
       if (FULL || klev <= nlay) {
         const size_t o2 = (size_t)col + ncol * o.lev(klev);
-        if (BB) { p.bb_up[o2] = pi * acc_up[BB ? i : 0]; p.bb_dn[o2] = pi * acc_dn[BB ? i : 0]; }
-        if (JAC) p.flux_upJac[o2] = pi * acc_jac[JAC ? i : 0];
+        if (BB) { put(bu, o2, pi * acc_up[BB ? i : 0]); put(bd, o2, pi * acc_dn[BB ? i : 0]); }
+        if (JAC) put(bj, o2, pi * acc_jac[JAC ? i : 0]);
       }
     }
     if (j == 0) {
       const size_t o2 = (size_t)col + ncol * o.lev(0);
-      if (BB) { p.bb_up[o2] = pi * acc_up_top; p.bb_dn[o2] = pi * acc_dn_top; }
-      if (JAC) p.flux_upJac[o2] = pi * acc_jac_top;
+      if (BB) { put(bu, o2, pi * acc_up_top); put(bd, o2, pi * acc_dn_top); }
+      if (JAC) put(bj, o2, pi * acc_jac_top);
     }
   }
 }
@@ -595,6 +603,8 @@ struct SwRegParams {
   int do_broadband;
   Float *bb_up, *bb_dn, *bb_dir;
   int gpt_per_block;
+  int accumulate;        // express path, see LwNoscatRegParams
+  size_t group_stride;
 };
 
 template <int CL>
@@ -853,22 +863,25 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
     adding_reg<CL>(j, R, T, A3, A4, alb_dif, src_sfc, dn_top, top, lev);
   }
   if (BB && col_ok) {
+    const size_t goff = p.group_stride * blockIdx.y;  // 0 unless the express path splits a launch's g-points
+    Float *bu = p.bb_up + goff, *bd = p.bb_dn + goff, *br = p.bb_dir + goff;
+    auto put = [&](Float* dst, size_t o2, Float v) { dst[o2] = p.accumulate ? dst[o2] + v : v; };
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
       const int klev = k0 + i + 1;
       if (FULL || klev <= nlay) {
         const size_t o2 = (size_t)col + ncol * o.lev(klev);
         if (LEAN) {
-          p.bb_up[o2] = sm_acc[i * kRegThreads]; p.bb_dn[o2] = sm_acc[(CL + i) * kRegThreads];
-          p.bb_dir[o2] = sm_acc[(2 * CL + i) * kRegThreads];
+          put(bu, o2, sm_acc[i * kRegThreads]); put(bd, o2, sm_acc[(CL + i) * kRegThreads]);
+          put(br, o2, sm_acc[(2 * CL + i) * kRegThreads]);
         } else {
-          p.bb_up[o2] = acc_up[NACC > 1 ? i : 0]; p.bb_dn[o2] = acc_dn[NACC > 1 ? i : 0]; p.bb_dir[o2] = acc_dir[NACC > 1 ? i : 0];
+          put(bu, o2, acc_up[NACC > 1 ? i : 0]); put(bd, o2, acc_dn[NACC > 1 ? i : 0]); put(br, o2, acc_dir[NACC > 1 ? i : 0]);
         }
       }
     }
     if (j == 0) {
       const size_t o2 = (size_t)col + ncol * o.lev(0);
-      p.bb_up[o2] = acc_up_top; p.bb_dn[o2] = acc_dn_top; p.bb_dir[o2] = acc_dir_top;
+      put(bu, o2, acc_up_top); put(bd, o2, acc_dn_top); put(br, o2, acc_dir_top);
     }
   }
 }

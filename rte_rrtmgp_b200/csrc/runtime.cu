@@ -19,6 +19,8 @@
 namespace rrtmgpb {
 
 thread_local const char* tl_op_name = nullptr;
+thread_local ExpressSolverMode tl_express;
+thread_local bool tl_trust_device_ptrs = false;
 // cudaStreamPerThread is a blocking stream: it orders itself against the legacy default stream, so hosts that mix this
 // library with legacy-stream work (torch's default stream, plain cudaMemcpy) keep the ordering they had
 static thread_local cudaStream_t tl_stream = cudaStreamPerThread;

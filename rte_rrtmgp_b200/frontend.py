@@ -214,6 +214,33 @@ def rte_sw_bygpoint(ctx, atmos, mu0, inc_flux, sfc_alb_dir, sfc_alb_dif, gpt_up,
                                          C.c_void_p(_addr(gpt_dir)), C.c_void_p(_addr(inc_flux_dif)), err), err)
 
 
+def rte_lw_express(ctx, gas_optics, p_lay, p_lev, t_lay, t_sfc, vmr, sfc_emis, fluxes, clouds=None, col_dry=None,
+                   tlev=None, n_gauss_angles=0):
+    """Express path: gas_optics + clouds%increment + rte_lw -> broadband fluxes, no (ncol,nlay,ngpt) array
+    (rrtmgpb_rte_lw_express, include/rrtmgp_b200_frontend.h).  vmr(ncol,nlay,ngas); sfc_emis(nband,ncol)."""
+    err = C.create_string_buffer(ERRLEN)
+    ncol, nlay = (int(v) for v in p_lay.shape)
+    P = lambda x: C.c_void_p(_addr(x))
+    f = fluxes.struct()
+    o = clouds.struct() if clouds is not None else None
+    _check(ctx.c.rrtmgpb_rte_lw_express(C.c_void_p(gas_optics.handle), ncol, nlay, P(p_lay), P(p_lev), P(t_lay), P(t_sfc),
+                                        P(vmr), P(col_dry), P(tlev), C.byref(o) if o is not None else None, P(sfc_emis),
+                                        int(n_gauss_angles), C.byref(f), err), err)
+
+
+def rte_sw_express(ctx, gas_optics, p_lay, p_lev, t_lay, vmr, mu0, sfc_alb_dir, sfc_alb_dif, fluxes, clouds=None,
+                   col_dry=None):
+    """Express path, shortwave: gas_optics + clouds%increment (clouds already delta-scaled) + rte_sw -> broadband fluxes."""
+    err = C.create_string_buffer(ERRLEN)
+    ncol, nlay = (int(v) for v in p_lay.shape)
+    P = lambda x: C.c_void_p(_addr(x))
+    f = fluxes.struct()
+    o = clouds.struct() if clouds is not None else None
+    _check(ctx.c.rrtmgpb_rte_sw_express(C.c_void_p(gas_optics.handle), ncol, nlay, P(p_lay), P(p_lev), P(t_lay), P(vmr),
+                                        P(col_dry), C.byref(o) if o is not None else None, P(mu0), P(sfc_alb_dir),
+                                        P(sfc_alb_dif), C.byref(f), err), err)
+
+
 # ---- McICA cloud sampling: rte/extensions/mo_cloud_sampling.F90 (C++ mirror: rrtmgpb_cloud_sampling_*) ----------------
 def _sampled_mask(ctx, randoms, cloud_frac, overlap_param, cloud_mask):
     ngpt, nlay, ncol = (int(v) for v in randoms.shape)

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--distinct", action="store_true", help="RFMIP-like distinct columns (clear sky) instead of the replicated all-sky profile")
     ap.add_argument("--tag", default=os.environ.get("RRTMGPB_LIB", "main"))
+    ap.add_argument("--express", action="store_true", help="the express path (no (ncol,nlay,ngpt) arrays)")
     ap.add_argument("--lw-only", action="store_true")
     ap.add_argument("--sw-only", action="store_true")
     a = ap.parse_args()
@@ -40,7 +41,7 @@ def main():
         reps = -(-a.ncol // 1800)
         import numpy as np
         prof = {k: np.asfortranarray(np.tile(v, (reps,) + (1,) * (v.ndim - 1))[:a.ncol]) for k, v in base.items()}
-    sky = AllSky(ctx, a.ncol, a.nlay, kd_lw, kd_sw, do_clouds=not a.distinct, profiles=prof)
+    sky = AllSky(ctx, a.ncol, a.nlay, kd_lw, kd_sw, do_clouds=not a.distinct, profiles=prof, express=a.express)
     sky.step()
     ctx.config_checks(False, False)
     sky.step()
@@ -59,7 +60,8 @@ def main():
     for ln in buf.value.decode().splitlines():
         name, cnt, tot = ln.rsplit(" ", 2)
         ks[name] = round(float(tot) / a.steps, 3)
-    print(json.dumps({"tag": a.tag, "ncol": a.ncol, "nlay": a.nlay, "distinct": a.distinct,
+    mem = torch.cuda.max_memory_allocated() / 2**30
+    print(json.dumps({"tag": a.tag, "express": a.express, "peak_torch_GiB": round(mem, 2), "ncol": a.ncol, "nlay": a.nlay, "distinct": a.distinct,
                       "ms_per_step": round(e0.elapsed_time(e1) / a.steps, 3), "kernels": ks}), flush=True)
 
 
