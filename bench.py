@@ -1,19 +1,28 @@
 #!/usr/bin/env python
 """bench.py - columns/sec of the all-sky LW+SW hot path (BASELINE.json metric) on N B200s.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]          product (CUDA) arm
-  python bench.py --impl reference [--steps K] [--warmup W]    reference arm: the reference's CPU kernels
-                                                               (C restatement, all host threads)
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3|c4|c5]     product (CUDA) arm
+  python bench.py --impl reference [--steps K] [--warmup W]                      reference arm: the reference's CPU
+                                                                                 kernels (C restatement, all host threads)
 
-Workload (config.workload): BASELINE.json configs[1] - one analytic RCEMIP-like profile replicated to
-65,536 columns x 72 layers per GPU, LW 256 g-points + SW 224 g-points, clouds in 2/3 of the columns:
-the loop body of the reference's own benchmark driver (examples/all-sky/rrtmgp_allsky.F90:332-409).
-A "step" = one LW iteration + one SW iteration over all columns of the rank.  Columns are independent,
-so ranks own disjoint column shards and there is NO collective on the data path ("scaling": "weak").
+Headline workload (config.workload): BASELINE.json configs[1] = "c2" - one analytic RCEMIP-like profile replicated to
+65,536 columns x 72 layers per GPU, LW 256 + SW 224 g-points, clouds in 2/3 of the columns: the loop body of the
+reference's own benchmark driver (examples/all-sky/rrtmgp_allsky.F90:332-409).  A "step" = one LW iteration + one SW
+iteration over all columns of the rank.  Columns are independent, so ranks own disjoint column shards and there is NO
+collective on the data path ("scaling": "weak").
 
-One JSON line is printed by rank 0 (see the contract in the task statement / DESIGN.md section 6).
+  value   device-timed, inputs resident in HBM, the API-visible (ncol,nlay,ngpt) arrays materialised (plane path)
+  e2e     the same step through the library's HOST-buffer entry (rrtmgpb_allsky_stream_host): state and fluxes in pinned
+          host memory, column chunks, uploads / downloads overlapped with compute inside the library
+  extras  value_express (no (ncol,nlay,ngpt) arrays), value_reference_call_sequence (the 45 extern symbols, kernel by
+          kernel), value_with_flux_gather_to_rank0 (N > 1), other_configs: c3 / c4 / c5 of BASELINE.json per GPU
+          (c4 streamed from host memory through the same host-buffer entry)
+
+--config c3|c4|c5 makes that configuration the timed headline instead (parity-test shapes; supplementary).
+One JSON line is printed by rank 0 (contract: task statement / DESIGN.md section 6).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -29,7 +38,14 @@ sys.path.insert(0, ROOT)
 NCOL_PER_GPU = 65536
 NLAY = 72
 METRIC = "columns/sec (LW+SW all-sky)"
-WORKLOAD = "all-sky LW(256 gpt)+SW(224 gpt), 1 RCEMIP-like profile replicated, 72 layers, clouds in 2/3 of columns"
+WORKLOADS = {
+    "c2": "all-sky LW(256 gpt)+SW(224 gpt), 1 RCEMIP-like profile replicated, 72 layers, clouds in 2/3 of columns",
+    "c3": "RFMIP-like clear-sky LW(256)+SW(224), 1800 distinct profiles tiled to 131,072 columns per GPU, 60 layers",
+    "c4": "all-sky LW(128 gpt)+SW(112 gpt), reduced k-distributions, 524,288 columns per GPU streamed from host memory in chunks, 72 layers",
+    "c5": "all-sky LW two-stream (256 gpt, g-point fluxes summed) + SW(224), clouds + aerosols, 131,072 columns per GPU in chunks of 32,768, 72 layers",
+}
+# roofline columns/s per B200 from the unfused-ABI algorithmic bytes at the measured HBM bandwidth
+ROOFLINE_COLS = {"c2": 1.62e6, "c3": 2.95e6, "c4": 2.71e6, "c5": 1.61e6}
 
 
 def algorithmic_bytes(ncol, nlay, ngpt_lw, ngpt_sw, nbnd_lw, nbnd_sw, nflav_lw, nflav_sw, ngas):
@@ -108,10 +124,23 @@ def summarize_clocks(samples, device_index):
 
 
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_rate(ncol_per_block, nblocks_per_thread, steps, warmup, fast=True, threads=None):
-    """columns/s of the CPU oracle (C restatement of the reference's default kernels) with all host
-    threads: independent column blocks per thread - the reference's own parallelisation idiom
-    (examples/rfmip-clear-sky/rrtmgp_rfmip_lw.F90:177-178,247)."""
+# CPU arm: the oracle (C restatement of the reference's default kernels) on the host cores
+# ----------------------------------------------------------------------------------------------------
+def _cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def cpu_rate(ncol_per_block, nblocks_per_thread, timed, warmup, fast=True, threads=None, lw_only_clear=False, nlay=NLAY,
+             distinct=False):
+    """columns/s of the CPU oracle: independent column blocks per thread - the reference's own parallelisation idiom
+    (examples/rfmip-clear-sky/rrtmgp_rfmip_lw.F90:177-178,247).  Returns (median, best) columns/s over `timed`
+    iterations after `warmup`, plus threads and columns per iteration."""
     import oracle
     from rte_rrtmgp_b200 import synthetic as syn
     from rte_rrtmgp_b200.allsky import AllSky
@@ -120,17 +149,21 @@ def cpu_reference_rate(ncol_per_block, nblocks_per_thread, steps, warmup, fast=T
     threads = threads or (os.cpu_count() or 1)
     lib = oracle.lib(fast=fast)
     ctx = Context(lib, None)
-    kd_lw, kd_sw = syn.make_kdist("lw"), syn.make_kdist("sw")
-    blocks = [AllSky(ctx, ncol_per_block, NLAY, kd_lw, kd_sw, col_offset=i * ncol_per_block) for i in range(threads)]
+    kd_lw = syn.make_kdist("lw")
+    kd_sw = None if lw_only_clear else syn.make_kdist("sw")
+    blocks = []
+    for i in range(threads):
+        prof = syn.perturbed_profiles(ncol_per_block, nlay, seed=1234 + i, top_at_1=True) if distinct else None
+        blocks.append(AllSky(ctx, ncol_per_block, nlay, kd_lw, kd_sw, col_offset=i * ncol_per_block, profiles=prof,
+                             do_clouds=not lw_only_clear))
     ctx.config_checks(False, False)  # rrtmgp_allsky.F90:334
 
-    def work(b, n):
-        for _ in range(n):
-            for _ in range(nblocks_per_thread):
-                b.step()
+    def work(b):
+        for _ in range(nblocks_per_thread):
+            b.step()
 
-    def run(n):
-        ts = [threading.Thread(target=work, args=(b, n)) for b in blocks]
+    def run_once():
+        ts = [threading.Thread(target=work, args=(b,)) for b in blocks]
         t0 = time.perf_counter()
         for t in ts:
             t.start()
@@ -138,27 +171,56 @@ def cpu_reference_rate(ncol_per_block, nblocks_per_thread, steps, warmup, fast=T
             t.join()
         return time.perf_counter() - t0
 
-    run(warmup)
-    dt = run(steps)
-    cols = threads * nblocks_per_thread * ncol_per_block * steps
-    return cols / dt, dt / steps, threads, threads * nblocks_per_thread * ncol_per_block
+    for _ in range(warmup):
+        run_once()
+    times = [run_once() for _ in range(timed)]
+    cols = threads * nblocks_per_thread * ncol_per_block
+    return cols / float(np.median(times)), cols / min(times), threads, cols
+
+
+def cpu_baseline_block():
+    """single-thread and all-thread figures, parity build and speed build, C1 in full
+    (1800 x 60 x 256 LW clear sky) and a slice of C2; >= 3 warm-up + 5 timed iterations, median and best."""
+    ncpu = os.cpu_count() or 1
+    blk = 64
+    per_thread = max(1, 4096 // (blk * ncpu))
+    med, best, th, cols = cpu_rate(blk, per_thread, 5, 3, fast=True)
+    out = {"value": med, "unit": "columns/s", "cores": th, "kind": "port", "cpu_model": _cpu_model(),
+           "sample": f"{cols} columns per iteration ({th} threads x {per_thread} blocks x {blk} columns) of the headline workload; "
+                     "3 warm-up + 5 timed iterations, median (best in value_best); oracle -O3 -march=native build of the C "
+                     "restatement of the reference's default kernels (no Fortran compiler in the image)",
+           "value_best": best}
+    m1, b1, _, c1 = cpu_rate(blk, 2, 5, 3, fast=True, threads=1)
+    out["single_thread"] = {"value": m1, "value_best": b1, "columns_per_iteration": c1}
+    mp, bp, _, cp = cpu_rate(blk, per_thread, 3, 1, fast=False)
+    out["parity_build_all_threads"] = {"value": mp, "value_best": bp, "columns_per_iteration": cp,
+                                       "flags": "-O2 -ffp-contract=off (the oracle the parity tests use)"}
+    # C1: RFMIP clear-sky LW, 1800 columns x 60 layers x 256 g-points in full, blocks over threads
+    nb = -(-1800 // ncpu)
+    mc, bc, _, cc = cpu_rate(nb, 1, 5, 3, fast=True, lw_only_clear=True, nlay=60, distinct=True)
+    m1c, b1c, _, c1c = cpu_rate(1800, 1, 3, 1, fast=True, threads=1, lw_only_clear=True, nlay=60, distinct=True)
+    out["c1_rfmip_clear_sky_lw"] = {"all_threads": {"value": mc, "value_best": bc, "columns_per_iteration": cc, "threads": ncpu},
+                                    "single_thread": {"value": m1c, "value_best": b1c, "columns_per_iteration": c1c},
+                                    "shape": "1800 distinct columns x 60 layers x 256 g-points, LW clear sky"}
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    threads = os.cpu_count() or 1
     ncb, nbt = 64, 2
-    rate, sec_per_step, threads, cols = cpu_reference_rate(ncb, nbt, args.steps, args.warmup)
+    med, best, threads, cols = cpu_rate(ncb, nbt, max(args.steps, 1), max(args.warmup, 1))
+    rate = med
     sample = (f"{cols} columns per step ({threads} threads x {nbt} blocks x {ncb} columns) of the same workload; "
-              "oracle -O3 -march=native build")
+              "median over the timed steps; oracle -O3 -march=native build")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "columns/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cols / rate * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "ncol_per_step": cols, "nlay": NLAY},
-        "cpu_baseline": {"value": rate, "unit": "columns/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOADS["c2"], "ncol_per_step": cols, "nlay": NLAY},
+        "cpu_baseline": {"value": rate, "unit": "columns/s", "cores": threads, "kind": "port", "sample": sample,
+                         "value_best": best, "cpu_model": _cpu_model()},
         "e2e": {"value": rate, "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -167,79 +229,140 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------
-def run_product(args):
-    import torch
-    import torch.distributed as dist
+# product arm
+# ----------------------------------------------------------------------------------------------------
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
 
-    import rte_rrtmgp_b200 as pkg
+        import rte_rrtmgp_b200 as pkg
+
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the product arm)")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.lib = pkg.lib()
+        self.lib.set_device(self.local)
+        self.lib.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.device = f"cuda:{self.local}"
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps):
+        """CUDA events around `steps` calls of fn on torch's current stream (= the library's stream), barriers on both
+        sides, max over ranks; ms per step."""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    def timed_host(self, fn, steps):
+        """Wall clock around host-synchronous calls (the host-buffer entry returns when the fluxes are in host memory),
+        device-synchronised and barriered on both sides, max over ranks; ms per step."""
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        self.torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        self.barrier()
+        return self.max_over_ranks(ms) / steps
+
+    def profile(self, fn, steps):
+        lib = self.lib
+        self.torch.cuda.synchronize()
+        lib.cdll.rrtmgpb_profile_enable(1)
+        for _ in range(steps):
+            fn()
+        self.torch.cuda.synchronize()
+        lib.cdll.rrtmgpb_profile_enable(0)
+        buf = ctypes.create_string_buffer(1 << 16)
+        lib.cdll.rrtmgpb_profile_report(buf, ctypes.c_size_t(len(buf)))
+        prof = []
+        for ln in buf.value.decode().splitlines():
+            name, cnt, tot = ln.rsplit(" ", 2)
+            prof.append((name, int(cnt) / steps, float(tot) / steps))
+        return prof
+
+    def free(self):
+        import gc
+
+        gc.collect()
+        self.torch.cuda.empty_cache()
+
+
+def _tile(prof, n):
+    reps = -(-n // next(iter(prof.values())).shape[0])
+    return {k: np.asfortranarray(np.tile(v, (reps,) + (1,) * (v.ndim - 1))[:n]) for k, v in prof.items()}
+
+
+def make_config(b, name, ncol=None):
+    """-> (step function, columns per step, description dict, cleanup objects) for one BASELINE.json configuration."""
     from rte_rrtmgp_b200 import synthetic as syn
     from rte_rrtmgp_b200.allsky import AllSky
     from rte_rrtmgp_b200.frontend import Context
+    from rte_rrtmgp_b200.streaming import HostAllSky
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the product arm)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib = pkg.lib()
-    lib.set_device(local)
-    lib.set_stream(torch.cuda.current_stream().cuda_stream)
-    device = f"cuda:{local}"
-    ctx = Context(lib, device)
-    ncol = args.ncol
-    kd_lw, kd_sw = syn.make_kdist("lw"), syn.make_kdist("sw")
-    sky = AllSky(ctx, ncol, NLAY, kd_lw, kd_sw, col_offset=rank * ncol)
+    ctx = Context(b.lib, b.device)
+    if name == "c3":
+        n = ncol or 131072
+        prof = _tile(syn.perturbed_profiles(1800, 60, seed=1234, top_at_1=True), n)
+        sky = AllSky(ctx, n, 60, syn.make_kdist("lw"), syn.make_kdist("sw"), profiles=prof, do_clouds=False, col_offset=b.rank * n)
+        return sky.step, n, {"ncol_per_gpu": n, "nlay": 60, "resident": True}, sky
+    if name == "c4":
+        n, chunk = ncol or 524288, 65536
+        h = HostAllSky(b.lib, n, NLAY, syn.make_kdist("lw", ngpt=128), syn.make_kdist("sw", ngpt=112), chunk, device=b.device)
+        return h.step, n, {"ncol_per_gpu": n, "nlay": NLAY, "chunk_columns": chunk, "resident": False,
+                           "h2d_bytes_per_step": h.h2d_bytes, "d2h_bytes_per_step": h.d2h_bytes,
+                           "note": "state and fluxes in pinned host memory; every chunk's inputs cross PCIe (rrtmgpb_allsky_stream_host)"}, h
+    if name == "c5":
+        n, chunk = ncol or 131072, 32768
+        sky = AllSky(ctx, chunk, NLAY, syn.make_kdist("lw"), syn.make_kdist("sw"), do_aerosols=True, lw_2stream=True,
+                     col_offset=b.rank * n)
+        nchunk = n // chunk
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+        def step():
+            for _ in range(nchunk):   # device-resident chunk (synthetic replicated profile: every chunk is the same columns)
+                sky.step()
+        return step, n, {"ncol_per_gpu": n, "nlay": NLAY, "chunk_columns": chunk, "resident": True,
+                         "note": "LW two-stream returns g-point fluxes (2 x 9.8 GB per chunk), summed with rte_sum_broadband"}, sky
+    raise ValueError(name)
 
-    # first step with the frontend's checks on (as the reference driver does), then off: rrtmgp_allsky.F90:334
-    sky.step()
-    ctx.config_checks(False, False)
-    for _ in range(max(args.warmup - 1, 0)):
-        sky.step()
-    barrier()
 
+def run_product(args):
+    b = Bench(args)
+    torch, lib, world, rank = b.torch, b.lib, b.world, b.rank
+    from rte_rrtmgp_b200 import synthetic as syn
+    from rte_rrtmgp_b200.allsky import AllSky
+    from rte_rrtmgp_b200.frontend import Context
+    from rte_rrtmgp_b200.streaming import HostAllSky
+
+    ctx = Context(lib, b.device)
+    steps, warmup = args.steps, args.warmup
     stop, samples = threading.Event(), []
     sampler = threading.Thread(target=clock_sampler, args=(stop, samples), daemon=True)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-    lib.launch_count(reset=True)
-    lib.cdll.rrtmgpb_profile_enable(1)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        sky.step()
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = lib.launch_count()
-    lib.cdll.rrtmgpb_profile_enable(0)
-    import ctypes
-    buf = ctypes.create_string_buffer(1 << 16)
-    lib.cdll.rrtmgpb_profile_report(buf, ctypes.c_size_t(len(buf)))
-    stop.set()
-    t = torch.tensor([ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    ms_per_step = ms_max / args.steps
-    value = world * ncol / (ms_per_step * 1e-3)
-
-    # ---- per-kernel shares from the event profiler (this rank) and the roofline of the dominant kernel
-    prof = []
-    for ln in buf.value.decode().splitlines():
-        name, cnt, tot = ln.rsplit(" ", 2)
-        prof.append((name, int(cnt), float(tot)))
-    alg = algorithmic_bytes(ncol, NLAY, kd_lw.ngpt, kd_sw.ngpt, kd_lw.nbnd, kd_sw.nbnd, kd_lw.nflav, kd_sw.nflav, kd_lw.ngas)
+    extras, kernels, roofline, step_roof = {}, [], None, None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -247,199 +370,205 @@ def run_product(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
-    roofline, kernels = None, []
-    total_kernel_ms = sum(p[2] for p in prof) or 1.0
-    for name, cnt, tot in prof:
-        # per STEP figures: a kernel that runs for LW and for SW (tau_absorption, interpolation,
-        # cld_from_table) is charged the sum of both launches' algorithmic bytes against the sum of both times
-        ms_step = tot / args.steps
-        if name in alg:
-            bytes_step = alg[name]
-        elif f"{name}[lw]" in alg:
-            bytes_step = alg[f"{name}[lw]"] + alg[f"{name}[sw]"]
-        else:
-            bytes_step = None
-        ent = {"kernel": name, "launches_per_step": cnt / args.steps, "ms_per_step": ms_step,
-               "share": tot / total_kernel_ms}
-        if bytes_step:
-            ent["algorithmic_bytes_per_step"] = bytes_step
-            ent["achieved_gbs"] = bytes_step / (ms_step * 1e-3) / 1e9
-            ent["frac"] = ent["achieved_gbs"] / peak
-        kernels.append(ent)
-    # DRAM traffic per launch of each kernel from the committed `ncu --set full` captures (profiles/, taken at a
-    # reduced column count; both read and written bytes scale linearly with the columns of a launch)
-    ncu = {}
-    try:
-        ncu = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))
-    except Exception:
-        pass
-    for ent in kernels:
-        rec = ncu.get(ent["kernel"])
-        if rec:
-            ent["traffic"] = rec["dram_bytes_per_column"] * ncol * ent["launches_per_step"] / max(rec.get("launches", 1), 1)
-            ent["fp64_pipe_active_pct_ncu"] = rec.get("fp64_pipe_active_pct")
-    if kernels:
-        top = kernels[0]
-        roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top.get("achieved_gbs"), "peak": peak,
-                    "unit": "GB/s", "frac": top.get("frac"), "traffic": top.get("traffic"), "peak_source": peak_src,
-                    "share_of_step": top["share"], "ms_per_step": top["ms_per_step"],
-                    "launches_per_step": top["launches_per_step"],
-                    "algorithmic_bytes_per_step": top.get("algorithmic_bytes_per_step"),
-                    # the solvers are fp64-issue bound, not HBM bound: pipe utilisation from ncu
-                    "fp64_pipe_active_pct_ncu": top.get("fp64_pipe_active_pct_ncu"),
-                    "traffic_source": "profiles/r1_ncu_summary.json (ncu --set full, dram__bytes_read+write, scaled to this launch)"}
-    step_bytes = sum(k.get("algorithmic_bytes_per_step") or 0 for k in kernels)
-    step_frac = step_bytes / (ms_per_step * 1e-3) / 1e9 / peak
 
-    # ---- end to end: host inputs (pinned) -> device every step, broadband fluxes -> host every step.
-    # As a host model would drive it: two device input sets; a copy stream uploads step n+1's inputs and downloads
-    # step n-1's fluxes while the compute stream runs step n (events order the streams; nothing is skipped:
-    # every step's inputs cross PCIe and every step's five flux arrays come back, all inside the timed region).
-    hin = sky.host_inputs
-    pinned = {k: torch.from_numpy(np.ascontiguousarray(v.T)).pin_memory() for k, v in hin.items()}
-    # gas concentrations cross PCIe the way the reference driver holds them (rrtmgp_allsky.F90:195-203): the h2o and
-    # o3 fields; the six well-mixed gases are scalars in gas_concs and are broadcast on the device every step
-    names = ["p_lay", "p_lev", "t_lay", "t_lev", "h2o", "o3", "lwp", "iwp", "rel", "dei"]
-    set_a = {k: getattr(sky, k) for k in names}
-    set_b = {k: torch.empty_like(v) for k, v in set_a.items()}
-    sets = [set_a, set_b]
-    outs = [sky.lw.flux_up, sky.lw.flux_dn, sky.sw.flux_up, sky.sw.flux_dn, sky.sw.flux_dir]
-    stage_out = [[torch.empty_like(o) for o in outs] for _ in range(2)]  # device staging so compute never waits on D2H
-    host_out = [torch.empty(tuple(reversed(o.shape)), dtype=torch.float64).pin_memory() for o in outs]
-    h2d = sum(pinned[k].numel() * 8 for k in names)
-    d2h = sum(h.numel() * 8 for h in host_out)
-    compute = torch.cuda.current_stream()
-    copy = torch.cuda.Stream()
-    ev_in = [torch.cuda.Event() for _ in range(2)]      # inputs of set i uploaded
-    ev_free = [torch.cuda.Event() for _ in range(2)]    # compute finished reading set i
-    ev_out = [torch.cuda.Event() for _ in range(2)]     # fluxes of step parity i staged
-    ev_down = [torch.cuda.Event() for _ in range(2)]    # staging buffer i downloaded
-
-    def upload(i):
-        with torch.cuda.stream(copy):
-            copy.wait_event(ev_free[i])
-            for k in names:
-                d = sets[i][k]
-                d.permute(*reversed(range(d.dim()))).copy_(pinned[k], non_blocking=True)
-            ev_in[i].record(copy)
-
-    def run_e2e(nsteps):
-        for i in range(2):
-            ev_free[i].record(compute)
-            ev_down[i].record(copy)
-        upload(0)
-        for n in range(nsteps):
-            i = n & 1
-            if n + 1 < nsteps:
-                upload(i ^ 1)
-            compute.wait_event(ev_in[i])
-            for k in names:
-                setattr(sky, k, sets[i][k])
-            sky.step()
-            ev_free[i].record(compute)
-            compute.wait_event(ev_down[i])           # staging buffer i free again
-            for o, st in zip(outs, stage_out[i]):
-                st.copy_(o, non_blocking=True)
-            ev_out[i].record(compute)
-            with torch.cuda.stream(copy):
-                copy.wait_event(ev_out[i])
-                for st, h in zip(stage_out[i], host_out):
-                    h.copy_(st.permute(*reversed(range(st.dim()))), non_blocking=True)
-                ev_down[i].record(copy)
-        compute.wait_stream(copy)                    # the timed region ends when the last fluxes are on the host
-
-    run_e2e(2)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run_e2e(args.steps)
-    e1.record()
-    barrier()
-    for k in names:
-        setattr(sky, k, set_a[k])
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * ncol / (float(t.item()) / args.steps * 1e-3)
-
-    # ---- N > 1: the optional epilogue of SURVEY 8(e) - broadband fluxes gathered to rank 0 over NCCL after every step
-    gather_value = None
-    if world > 1:
-        from rte_rrtmgp_b200.sharding import gather_fluxes_device
-        flux_t = [sky.lw.flux_up, sky.lw.flux_dn, sky.sw.flux_up, sky.sw.flux_dn, sky.sw.flux_dir]
-        recv = ([[torch.empty(tuple(reversed(t.shape)), dtype=t.dtype, device=t.device) for _ in range(world)] for t in flux_t]
-                if rank == 0 else None)
+    if args.config == "c2":
+        ncol = args.ncol
+        kd_lw, kd_sw = syn.make_kdist("lw"), syn.make_kdist("sw")
+        sky = AllSky(ctx, ncol, NLAY, kd_lw, kd_sw, col_offset=rank * ncol)
+        # first step with the frontend's checks on (as the reference driver does), then off: rrtmgp_allsky.F90:334
         sky.step()
-        gather_fluxes_device(flux_t, rank, world, recv)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(args.steps):
+        ctx.config_checks(False, False)
+        for _ in range(max(warmup - 1, 0)):
             sky.step()
-            gather_fluxes_device(flux_t, rank, world, recv)
-        g1.record()
-        barrier()
-        t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        gather_value = world * ncol / (float(t.item()) / args.steps * 1e-3)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.25)
+        lib.launch_count(reset=True)
+        ms_per_step = b.timed(sky.step, steps)        # headline: event profiler OFF
+        launches = lib.launch_count()
+        value = world * ncol / (ms_per_step * 1e-3)
+        workload, cfg = WORKLOADS["c2"], {"ncol_per_gpu": ncol, "nlay": NLAY, "ngpt_lw": kd_lw.ngpt, "ngpt_sw": kd_sw.ngpt}
 
-    # ---- the same step driven as the reference's call sequence, kernel by kernel through the 45 extern-ABI symbols
-    # (what a stock Fortran frontend linked against this library executes); reported beside the headline
-    seq_value = None
-    if not args.no_seq:
-        sky.fused = False
-        sky.step()
-        barrier()
-        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        q0.record()
-        for _ in range(max(args.steps // 2, 1)):
-            sky.step()
-        q1.record()
-        barrier()
-        sky.fused = True
-        sky.step()  # leave the headline path's results in the flux arrays for the parity spot check below
-        t = torch.tensor([q0.elapsed_time(q1) / max(args.steps // 2, 1)], dtype=torch.float64, device=device)
+        # ---- per-kernel shares (separate profiled pass) and the roofline of the dominant kernel
+        prof = b.profile(sky.step, max(steps // 2, 2))
+        alg = algorithmic_bytes(ncol, NLAY, kd_lw.ngpt, kd_sw.ngpt, kd_lw.nbnd, kd_sw.nbnd, kd_lw.nflav, kd_sw.nflav, kd_lw.ngas)
+        total_kernel_ms = sum(p[2] for p in prof) or 1.0
+        ncu = {}
+        for fn in ("r2_ncu_summary.json", "r1_ncu_summary.json"):
+            try:
+                ncu = json.load(open(os.path.join(ROOT, "profiles", fn)))
+                ncu_src = fn
+                break
+            except Exception:
+                continue
+        for name, cnt, ms in prof:
+            bytes_step = alg.get(name) or ((alg[f"{name}[lw]"] + alg[f"{name}[sw]"]) if f"{name}[lw]" in alg else None)
+            ent = {"kernel": name, "launches_per_step": cnt, "ms_per_step": ms, "share": ms / total_kernel_ms}
+            if bytes_step:
+                ent["algorithmic_bytes_per_step"] = bytes_step
+                ent["achieved_gbs"] = bytes_step / (ms * 1e-3) / 1e9
+                ent["frac"] = ent["achieved_gbs"] / peak
+            rec = ncu.get(name)
+            if rec:
+                ent["traffic"] = rec["dram_bytes_per_column"] * ncol * cnt / max(rec.get("launches", 1), 1)
+                ent["fp64_pipe_active_pct_ncu"] = rec.get("fp64_pipe_active_pct")
+            kernels.append(ent)
+        if kernels:
+            top = kernels[0]
+            roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top.get("achieved_gbs"), "peak": peak,
+                        "unit": "GB/s", "frac": top.get("frac"), "traffic": top.get("traffic"), "peak_source": peak_src,
+                        "share_of_step": top["share"], "ms_per_launch": top["ms_per_step"] / max(top["launches_per_step"], 1),
+                        "launches_per_step": top["launches_per_step"],
+                        "algorithmic_bytes_per_launch": (top.get("algorithmic_bytes_per_step") or 0) / max(top["launches_per_step"], 1),
+                        # the solvers are fp64-issue bound, not HBM bound: pipe utilisation from ncu
+                        "fp64_pipe_active_pct_ncu": top.get("fp64_pipe_active_pct_ncu"),
+                        "traffic_source": f"profiles/{ncu_src} (ncu --set full, dram__bytes_read+write, scaled to this launch)" if ncu else None}
+        step_bytes = sum(k.get("algorithmic_bytes_per_step") or 0 for k in kernels)
+        step_roof = {"algorithmic_bytes_per_step": step_bytes, "frac_of_hbm_peak": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                     "bytes_per_column": step_bytes / ncol, "frac_of_unfused_abi_roofline": value / world / ROOFLINE_COLS["c2"]}
+
+        # ---- N > 1: the optional epilogue of SURVEY 8(e) - broadband fluxes gathered to rank 0 over NCCL after every step
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        seq_value = world * ncol / (float(t.item()) * 1e-3)
+            from rte_rrtmgp_b200.sharding import gather_fluxes_device
+            flux_t = [sky.lw.flux_up, sky.lw.flux_dn, sky.sw.flux_up, sky.sw.flux_dn, sky.sw.flux_dir]
+            recv = ([[torch.empty(tuple(reversed(t.shape)), dtype=t.dtype, device=t.device) for _ in range(world)] for t in flux_t]
+                    if rank == 0 else None)
 
-    # ---- parity spot check inside the bench: first 32 columns vs the CPU oracle (checker only)
-    cpu_base, parity = None, None
+            def step_gather():
+                sky.step()
+                gather_fluxes_device(flux_t, rank, world, recv)
+            step_gather()
+            extras["value_with_flux_gather_to_rank0"] = world * ncol / (b.timed(step_gather, steps) * 1e-3)
+
+        # ---- the same step driven as the reference's call sequence, kernel by kernel through the 45 extern-ABI symbols
+        if not args.no_seq:
+            sky.fused = False
+            sky.step()
+            extras["value_reference_call_sequence"] = world * ncol / (b.timed(sky.step, max(steps // 2, 1)) * 1e-3)
+            sky.fused = True
+            sky.step()  # leave the headline path's results in the flux arrays for the parity spot check below
+        flux_gpu = sky.fluxes_host() if rank == 0 else None
+        del sky
+        b.free()
+
+        # ---- express path: no (ncol,nlay,ngpt) arrays
+        if not args.no_extras:
+            xs = AllSky(ctx, ncol, NLAY, kd_lw, kd_sw, col_offset=rank * ncol, express=True)
+            xs.step(); xs.step()
+            ms_x = b.timed(xs.step, steps)
+            extras["value_express"] = world * ncol / (ms_x * 1e-3)
+            extras["express"] = {"ms_per_step": ms_x, "peak_device_GiB_torch": round(torch.cuda.max_memory_allocated() / 2**30, 2),
+                                 "note": "rrtmgpb_rte_lw_express / _sw_express: column chunks x band groups, planes only in a reused scratch"}
+            if rank == 0 and flux_gpu is not None:
+                fx = xs.fluxes_host()
+                extras["express"]["max_abs_flux_diff_vs_plane_path_Wm2"] = max(float(np.max(np.abs(fx[k] - flux_gpu[k]))) for k in fx)
+            del xs
+            b.free()
+
+        # ---- end to end through the library's HOST-buffer entry: state and fluxes in pinned host memory
+        h = HostAllSky(lib, ncol, NLAY, kd_lw, kd_sw, args.e2e_chunk, device=b.device)
+        h.step(); h.step()
+        ms_e2e = b.timed(h.step, steps)   # events on the library's compute stream; the call returns when the fluxes are on the host
+        e2e = {"value": world * ncol / (ms_e2e * 1e-3), "unit": "columns/s", "h2d_bytes_per_step": h.h2d_bytes,
+               "d2h_bytes_per_step": h.d2h_bytes, "ms_per_step": ms_e2e, "chunk_columns": args.e2e_chunk,
+               "api": "rrtmgpb_allsky_stream_host (include/rrtmgp_b200_frontend.h): host buffers in, host fluxes out, copies inside the timed region"}
+        if rank == 0 and flux_gpu is not None:
+            fh = h.fluxes_host()
+            e2e["max_abs_flux_diff_vs_resident_Wm2"] = max(float(np.max(np.abs(fh[k] - flux_gpu[k]))) for k in fh)
+        del h
+        b.free()
+
+        # ---- a stock host (gfortran-style: HOST arrays into the 45 symbols, every call staged through PCIe), small slice
+        if not args.no_extras and world == 1:
+            try:
+                nh = 2048
+                hs = AllSky(Context(lib, None), nh, NLAY, kd_lw, kd_sw, fused=False)
+                hs.step()
+                t0 = time.perf_counter()
+                hs.step()
+                lib.sync()
+                extras["value_host_pointer_call_sequence"] = nh / (time.perf_counter() - t0)
+                extras["host_pointer_note"] = f"{nh} columns, numpy arrays handed to the 45 symbols one by one: every argument is staged to the device and back per call (PCIe-bound correctness path)"
+                del hs
+            except Exception as e:  # pragma: no cover
+                extras["value_host_pointer_call_sequence"] = None
+                extras["host_pointer_note"] = f"failed: {e}"
+
+        # ---- the other BASELINE.json configurations, per GPU, few steps (supplementary; full runs: --config c3|c4|c5)
+        if not args.no_extras:
+            other = {}
+            for name in ("c3", "c4", "c5"):
+                try:
+                    fn, n, desc, keep = make_config(b, name)
+                    fn()
+                    ctx.config_checks(False, False)
+                    fn()
+                    ms = b.timed(fn, 2)
+                    v = world * n / (ms * 1e-3)
+                    other[name] = {"value": v, "unit": "columns/s", "ms_per_step": ms, "workload": WORKLOADS[name],
+                                   "frac_of_unfused_abi_roofline": v / world / ROOFLINE_COLS[name], **desc}
+                    del fn, keep
+                except Exception as e:  # pragma: no cover
+                    other[name] = {"error": str(e)[:200]}
+                b.free()
+            extras["other_configs"] = other
+    else:
+        # ---- a non-headline configuration as the timed workload
+        fn, ncol, desc, keep = make_config(b, args.config, None if args.ncol == NCOL_PER_GPU else args.ncol)
+        fn()
+        ctx.config_checks(False, False)
+        for _ in range(max(warmup - 1, 0)):
+            fn()
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.25)
+        lib.launch_count(reset=True)
+        ms_per_step = b.timed(fn, steps)
+        launches = lib.launch_count()
+        value = world * ncol / (ms_per_step * 1e-3)
+        workload, cfg = WORKLOADS[args.config], desc
+        prof = b.profile(fn, 1)
+        tot = sum(p[2] for p in prof) or 1.0
+        kernels = [{"kernel": n_, "launches_per_step": c_, "ms_per_step": m_, "share": m_ / tot} for n_, c_, m_ in prof]
+        step_roof = {"frac_of_unfused_abi_roofline": value / world / ROOFLINE_COLS[args.config]}
+        e2e = ({"value": value, "unit": "columns/s", "h2d_bytes_per_step": desc["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": desc["d2h_bytes_per_step"], "note": "this configuration IS the host-buffer path"}
+               if args.config == "c4" else None)
+        flux_gpu, kd_lw, kd_sw = None, None, None
+
+    stop.set()
     if rank == 0:
         if sampler.is_alive():
             sampler.join(timeout=2)
-        if world == 1 and not args.no_cpu:
-            rate, sps, threads, cols = cpu_reference_rate(64, 1, 2, 1)
-            cpu_base = {"value": rate, "unit": "columns/s", "cores": threads, "kind": "port",
-                        "sample": f"{cols} columns per step ({threads} threads x 64 columns), 2 timed + 1 warm-up steps, "
-                                  "oracle -O3 -march=native build of the C restatement (no Fortran compiler in the image)"}
+        cpu_base, parity = None, None
+        if world == 1 and not args.no_cpu and args.config == "c2":
+            cpu_base = cpu_baseline_block()
             import oracle
             chk = AllSky(Context(oracle.lib(), None), 48, NLAY, kd_lw, kd_sw)
             chk.step()
-            fc, fg = chk.fluxes_host(), sky.fluxes_host()
-            parity = max(float(np.max(np.abs(fg[k][:48] - fc[k]))) for k in fc)
+            fc = chk.fluxes_host()
+            parity = max(float(np.max(np.abs(flux_gpu[k][:48] - fc[k]))) for k in fc)
         line = {
-            "metric": METRIC, "value": value, "unit": "columns/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": value, "unit": "columns/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "ncol_per_gpu": ncol, "nlay": NLAY, "ngpt_lw": kd_lw.ngpt,
-                       "ngpt_sw": kd_sw.ngpt, "sharding": f"columns x{world}, no data-path collective",
-                       "l2_policy": "inputs larger than L2 (each (col,lay,gpt) plane is 9.7 GB)"},
-            "e2e": {"value": e2e_value, "unit": "columns/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "config": {"workload": workload, **cfg, "sharding": f"columns x{world}, no data-path collective",
+                       "l2_policy": "inputs larger than L2 (each (col,lay,gpt) plane is GBs)"},
+            "e2e": e2e,
             "gpu_launches": launches,
-            "value_reference_call_sequence": seq_value,
-            "value_with_flux_gather_to_rank0": gather_value,
+            **{k: extras[k] for k in ("value_with_flux_gather_to_rank0", "value_express", "value_reference_call_sequence",
+                                      "value_host_pointer_call_sequence") if k in extras},
             "roofline": roofline,
-            "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "frac_of_hbm_peak": step_frac,
-                              "bytes_per_column": step_bytes / ncol},
-            "kernels": kernels[:14],
+            "step_roofline": step_roof,
+            "clocks": summarize_clocks(samples, b.local),
             "cpu_baseline": cpu_base,
             "max_abs_flux_err_vs_oracle_Wm2": parity,
-            "clocks": summarize_clocks(samples, local),
+            **{k: v for k, v in extras.items() if k in ("express", "other_configs", "host_pointer_note")},
+            "kernels": kernels[:14],
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        b.dist.destroy_process_group()
     return 0
 
 
@@ -449,9 +578,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"], help="BASELINE.json configuration timed as the headline (default c2)")
     ap.add_argument("--ncol", type=int, default=NCOL_PER_GPU, help="columns per GPU (default: the BASELINE config)")
+    ap.add_argument("--e2e-chunk", type=int, default=16384, help="column chunk of the host-buffer (e2e) path")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-seq", action="store_true", help="skip the kernel-by-kernel (reference call sequence) leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip express / host-pointer / other-config legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     if args.impl == "reference":

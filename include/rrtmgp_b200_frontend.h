@@ -115,6 +115,9 @@ typedef struct {
 typedef struct rrtmgpb_gas_optics_t rrtmgpb_gas_optics_t;
 rrtmgpb_gas_optics_t* rrtmgpb_gas_optics_load(const rrtmgpb_kdist* tables, char* errmsg);
 void rrtmgpb_gas_optics_free(rrtmgpb_gas_optics_t* go);
+/* Dimensions of a loaded k-distribution (any pointer may be NULL) and the HOST copy of its band_lims_gpt(2,nbnd). */
+void rrtmgpb_gas_optics_dims(const rrtmgpb_gas_optics_t* go, int* ngas, int* nbnd, int* ngpt);
+const int* rrtmgpb_gas_optics_band_lims_gpt(const rrtmgpb_gas_optics_t* go);
 /* Backend address of the loaded kmajor(ntemp,neta,npres+1,ngpt) table.  A host that overwrites the loaded coefficients
  * in place (rrtmgpb_mem_to_backend) passes it to rrtmgpb_tables_changed() afterwards (rrtmgp_b200_ext.h). */
 Float* rrtmgpb_gas_optics_kmajor(const rrtmgpb_gas_optics_t* go);
@@ -163,6 +166,37 @@ int rrtmgpb_rte_sw_express(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, c
                            const Float* tlay, const Float* vmr, const Float* col_dry /* or NULL */,
                            const rrtmgpb_optical_props* clouds /* or NULL */, const Float* mu0, const Float* sfc_alb_dir,
                            const Float* sfc_alb_dif, rrtmgpb_fluxes_broadband* fluxes, char* errmsg);
+
+/* ---------------- all-sky driver on HOST buffers (CUDA library only) ---------------- */
+/* One iteration of the reference's all-sky loop body (examples/all-sky/rrtmgp_allsky.F90:332-409: cloud optics, gas
+ * optics, clouds%increment, rte_lw / rte_sw with broadband fluxes) for `ncol` columns whose inputs and outputs live in
+ * HOST memory: the columns are processed in chunks of `chunk_cols`, chunk k+1's inputs are uploaded and chunk k-1's
+ * fluxes downloaded (separate copy streams, cudaMemcpy2DAsync on the strided column slices) while chunk k computes.
+ * Pinned host memory makes the copies asynchronous; pageable memory works, serialised.  This is the entry a host model
+ * that keeps its state on the CPU calls, and how a problem larger than device memory (BASELINE config 4) is streamed.
+ * Arrays are Fortran-ordered: p_lay, t_lay, lwp, iwp, rel, dei, vmr fields (ncol,nlay); p_lev, t_lev (ncol,nlay+1);
+ * t_sfc, mu0 (ncol); emis_sfc (nbnd_lw,ncol), sfc_alb_dir/dif (nbnd_sw,ncol); fluxes (ncol,nlay+1). */
+typedef struct {
+  int ncol, nlay;
+  const Float *p_lay, *p_lev, *t_lay, *t_lev;
+  int ngas;                        /* gases in the k-distributions' order (both k-distributions share it) */
+  const Float* const* vmr_field;   /* [ngas]: HOST (ncol,nlay) field, or NULL when the gas is well mixed ... */
+  const Float* vmr_scalar;         /* [ngas]: ... with this volume mixing ratio */
+  const Float *lwp, *iwp, *rel, *dei;   /* all NULL: clear sky */
+  const Float *t_sfc, *emis_sfc;        /* LW boundary conditions */
+  const Float *mu0, *sfc_alb_dir, *sfc_alb_dif;   /* SW boundary conditions */
+} rrtmgpb_allsky_host_inputs;
+typedef struct {
+  Float *lw_flux_up, *lw_flux_dn, *sw_flux_up, *sw_flux_dn, *sw_flux_dir;   /* HOST (ncol,nlay+1); NULL: not wanted */
+} rrtmgpb_allsky_host_fluxes;
+/* go_lw / go_sw: either may be NULL (that half is skipped); co_lw / co_sw: cloud optics for the same bands, needed when
+ * the cloud inputs are given.  express != 0: rrtmgpb_rte_lw_express / _sw_express per chunk (no (ncol,nlay,ngpt) arrays),
+ * else the fused gas optics + rte_lw / rte_sw on chunk-sized planes.  Returns 0, or 1 and the failing call's message. */
+struct rrtmgpb_cloud_optics_t;
+int rrtmgpb_allsky_stream_host(const rrtmgpb_gas_optics_t* go_lw, const rrtmgpb_gas_optics_t* go_sw,
+                               const struct rrtmgpb_cloud_optics_t* co_lw, const struct rrtmgpb_cloud_optics_t* co_sw,
+                               const rrtmgpb_allsky_host_inputs* in, const rrtmgpb_allsky_host_fluxes* out, int chunk_cols,
+                               int express, char* errmsg);
 
 /* ---------------- ty_cloud_optics_rrtmgp (LUT form) ---------------- */
 typedef struct {

@@ -2,7 +2,7 @@
 
 Python loader for the CPU restatement of the reference kernels (oracle/*.c).  Only tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
-Nothing under rte_rrtmgp_b200/ imports it.
+Nothing under rte_rrtmgp_b200/ imports it (tests/test_abi.py checks).
 """
 import os
 import subprocess

@@ -26,6 +26,8 @@ class AllSky:
         # express: broadband fluxes straight from the state - atmos / sources (the (ncol,nlay,ngpt) arrays)
         # are never allocated; clouds only (no aerosols, no LW two-stream)
         self.express = express
+        self.concurrent = os.environ.get("RRTMGPB_CONCURRENT_LW_SW", "0") == "1"
+        self._side = None
         assert not (express and (do_aerosols or lw_2stream))
         prof = profiles if profiles is not None else syn.compute_profiles(300.0, ncol, nlay)
         self.host_inputs = {}
@@ -172,6 +174,21 @@ class AllSky:
 
     def step(self):
         self.update_vmr()
+        if self.concurrent and self.lw is not None and self.sw is not None and self.ctx.device is not None:
+            # the LW and the SW halves of the iteration are independent: issue them on two streams so that the tail of
+            # one kernel overlaps the head of the other half's (the library launches on the calling thread's stream)
+            import torch
+
+            cur = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            self._side.wait_stream(cur)
+            self.ctx.lib.set_stream(self._side.cuda_stream)
+            self.step_sw()
+            self.ctx.lib.set_stream(cur.cuda_stream)
+            self.step_lw()
+            cur.wait_stream(self._side)
+            return
         if self.lw is not None:
             self.step_lw()
         if self.sw is not None:

@@ -1,0 +1,217 @@
+// allsky_stream.cu - the all-sky iteration on HOST buffers, streamed through the device in column chunks
+// (include/rrtmgp_b200_frontend.h: rrtmgpb_allsky_stream_host).
+//
+// Reference workload: the loop body of examples/all-sky/rrtmgp_allsky.F90:332-409.  What a host model that keeps its
+// state in CPU memory needs from an accelerator backend is not a kernel but this: inputs cross PCIe once, fluxes come
+// back once, and neither transfer is exposed.  Three streams:
+//     up    chunk k+1's input slices  (cudaMemcpy2DAsync: a column range of a Fortran (ncol, nlay) array is strided)
+//     comp  chunk k: gas_concs broadcast, cloud optics, gas optics, solver  (the C++ frontend's own calls)
+//     down  chunk k-1's five flux slices
+// ordered by events; two device input sets and two device flux sets.  With pinned host memory every copy is
+// asynchronous; with pageable memory CUDA stages them (correct, serialised).
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "../common.cuh"
+#include "rrtmgp_b200_ext.h"
+#include "rrtmgp_b200_frontend.h"
+#include "rte_kernels.h"
+
+using namespace rrtmgpb;
+
+namespace {
+
+struct Streams {
+  cudaStream_t up = nullptr, down = nullptr;
+  cudaEvent_t in_ready[2] = {}, in_free[2] = {}, out_ready[2] = {}, out_free[2] = {};
+};
+Streams& streams() {
+  static thread_local Streams s;
+  if (!s.up) {
+    RB_CUDA_CHECK(cudaStreamCreateWithFlags(&s.up, cudaStreamNonBlocking));
+    RB_CUDA_CHECK(cudaStreamCreateWithFlags(&s.down, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      RB_CUDA_CHECK(cudaEventCreateWithFlags(&s.in_ready[i], cudaEventDisableTiming));
+      RB_CUDA_CHECK(cudaEventCreateWithFlags(&s.in_free[i], cudaEventDisableTiming));
+      RB_CUDA_CHECK(cudaEventCreateWithFlags(&s.out_ready[i], cudaEventDisableTiming));
+      RB_CUDA_CHECK(cudaEventCreateWithFlags(&s.out_free[i], cudaEventDisableTiming));
+    }
+  }
+  return s;
+}
+
+// columns [c0, c0+n) of a HOST Fortran (ncol, nrows) array -> dense device (n, nrows), and back
+void upload_cols(Float* dst, const Float* src, int ncol, int c0, int n, size_t nrows, cudaStream_t st) {
+  RB_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)n * sizeof(Float), src + c0, (size_t)ncol * sizeof(Float),
+                                  (size_t)n * sizeof(Float), nrows, cudaMemcpyHostToDevice, st));
+}
+void download_cols(Float* dst, const Float* src, int ncol, int c0, int n, size_t nrows, cudaStream_t st) {
+  RB_CUDA_CHECK(cudaMemcpy2DAsync(dst + c0, (size_t)ncol * sizeof(Float), src, (size_t)n * sizeof(Float),
+                                  (size_t)n * sizeof(Float), nrows, cudaMemcpyDeviceToHost, st));
+}
+
+struct InSet {   // device copies of one chunk's inputs
+  Float *p_lay, *p_lev, *t_lay, *t_lev, *lwp, *iwp, *rel, *dei, *t_sfc, *emis, *mu0, *alb_dir, *alb_dif;
+  std::vector<Float*> field;   // [ngas]: uploaded field or nullptr
+};
+struct OutSet { Float* f[5]; };
+
+}  // namespace
+
+extern "C" int rrtmgpb_allsky_stream_host(const rrtmgpb_gas_optics_t* go_lw, const rrtmgpb_gas_optics_t* go_sw,
+                                          const rrtmgpb_cloud_optics_t* co_lw, const rrtmgpb_cloud_optics_t* co_sw,
+                                          const rrtmgpb_allsky_host_inputs* in, const rrtmgpb_allsky_host_fluxes* out,
+                                          int chunk_cols, int express, char* errmsg) {
+  if (errmsg) errmsg[0] = 0;
+  auto fail = [&](const std::string& m) { if (errmsg) std::snprintf(errmsg, RRTMGPB_ERRLEN, "%s", m.c_str()); return 1; };
+  if (!in || !out || (!go_lw && !go_sw)) return fail("allsky_stream_host: nothing to do");
+  const int ncol = in->ncol, nlay = in->nlay, nlev = nlay + 1, ngas = in->ngas;
+  const bool clouds = in->lwp != nullptr;
+  if (clouds && ((go_lw && !co_lw) || (go_sw && !co_sw))) return fail("allsky_stream_host: cloud inputs given without cloud optics");
+  int nbnd_lw = 0, ngpt_lw = 0, nbnd_sw = 0, ngpt_sw = 0, g1 = ngas, g2 = ngas;
+  if (go_lw) rrtmgpb_gas_optics_dims(go_lw, &g1, &nbnd_lw, &ngpt_lw);
+  if (go_sw) rrtmgpb_gas_optics_dims(go_sw, &g2, &nbnd_sw, &ngpt_sw);
+  if (g1 != ngas || g2 != ngas) return fail("allsky_stream_host: ngas differs from the k-distributions'");
+  const int nc = std::max(1, std::min(chunk_cols > 0 ? chunk_cols : ncol, ncol));
+  const size_t ncl = (size_t)nc * nlay, nclp = (size_t)nc * nlev;
+  Streams& S = streams();
+  cudaStream_t comp = stream();
+  auto dalloc = [&](size_t n) { return static_cast<Float*>(dev_alloc(std::max<size_t>(n, 1) * sizeof(Float))); };
+  // ---- device buffers (stream-ordered pool on the compute stream; the copy streams wait for `start`)
+  InSet I[2];
+  OutSet O[2];
+  std::vector<void*> owned;
+  auto take = [&](size_t n) { Float* p = dalloc(n); owned.push_back(p); return p; };
+  for (int k = 0; k < 2; ++k) {
+    I[k].p_lay = take(ncl); I[k].t_lay = take(ncl); I[k].p_lev = take(nclp); I[k].t_lev = take(nclp);
+    I[k].lwp = clouds ? take(ncl) : nullptr; I[k].iwp = clouds ? take(ncl) : nullptr;
+    I[k].rel = clouds ? take(ncl) : nullptr; I[k].dei = clouds ? take(ncl) : nullptr;
+    I[k].t_sfc = go_lw ? take(nc) : nullptr; I[k].emis = go_lw ? take((size_t)nbnd_lw * nc) : nullptr;
+    I[k].mu0 = go_sw ? take(nc) : nullptr; I[k].alb_dir = go_sw ? take((size_t)nbnd_sw * nc) : nullptr;
+    I[k].alb_dif = go_sw ? take((size_t)nbnd_sw * nc) : nullptr;
+    I[k].field.assign((size_t)ngas, nullptr);
+    for (int g = 0; g < ngas; ++g)
+      if (in->vmr_field && in->vmr_field[g]) I[k].field[(size_t)g] = take(ncl);
+    for (int a = 0; a < 5; ++a) O[k].f[a] = take(nclp);
+  }
+  Float* vmr = take(ncl * ngas);
+  // work arrays of the plane path (chunk sized); the express path needs none
+  const int* bl_lw = go_lw ? rrtmgpb_gas_optics_band_lims_gpt(go_lw) : nullptr;
+  const int* bl_sw = go_sw ? rrtmgpb_gas_optics_band_lims_gpt(go_sw) : nullptr;
+  std::vector<int> byband_lw(2 * (size_t)std::max(nbnd_lw, 1)), byband_sw(2 * (size_t)std::max(nbnd_sw, 1));
+  for (int b = 0; b < nbnd_lw; ++b) byband_lw[2 * b] = byband_lw[2 * b + 1] = b + 1;
+  for (int b = 0; b < nbnd_sw; ++b) byband_sw[2 * b] = byband_sw[2 * b + 1] = b + 1;
+  rrtmgpb_optical_props atm_lw{}, atm_sw{}, cld_lw{}, cld_sw{};
+  rrtmgpb_source_func_lw src{};
+  Float* toa = nullptr;
+  auto props = [&](rrtmgpb_optical_props& o, int kind, int ng, int nb, const int* lims, bool alloc) {
+    o.kind = kind; o.ncol = nc; o.nlay = nlay; o.ngpt = ng; o.nband = nb; o.nmom = 0; o.top_at_1 = 0;
+    o.band_lims_gpt = lims; o.band_lims_wvn = nullptr;
+    if (alloc) {
+      o.tau = take(ncl * ng);
+      o.ssa = kind == RRTMGPB_2STR ? take(ncl * ng) : nullptr;
+      o.g = kind == RRTMGPB_2STR ? take(ncl * ng) : nullptr;
+    }
+  };
+  if (go_lw && clouds) props(cld_lw, RRTMGPB_1SCL, nbnd_lw, nbnd_lw, byband_lw.data(), true);
+  if (go_sw && clouds) props(cld_sw, RRTMGPB_2STR, nbnd_sw, nbnd_sw, byband_sw.data(), true);
+  if (!express) {
+    if (go_lw) {
+      props(atm_lw, RRTMGPB_1SCL, ngpt_lw, nbnd_lw, bl_lw, true);
+      src.ncol = nc; src.nlay = nlay; src.ngpt = ngpt_lw;
+      src.lay_source = take(ncl * ngpt_lw); src.lev_source = take(nclp * ngpt_lw);
+      src.sfc_source = take((size_t)nc * ngpt_lw); src.sfc_source_Jac = take((size_t)nc * ngpt_lw);
+    }
+    if (go_sw) { props(atm_sw, RRTMGPB_2STR, ngpt_sw, nbnd_sw, bl_sw, true); toa = take((size_t)nc * ngpt_sw); }
+  }
+  cudaEvent_t start;
+  RB_CUDA_CHECK(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+  RB_CUDA_CHECK(cudaEventRecord(start, comp));
+  RB_CUDA_CHECK(cudaStreamWaitEvent(S.up, start, 0));
+  RB_CUDA_CHECK(cudaStreamWaitEvent(S.down, start, 0));
+  for (int k = 0; k < 2; ++k) {   // both sets start out free
+    RB_CUDA_CHECK(cudaEventRecord(S.in_free[k], comp));
+    RB_CUDA_CHECK(cudaEventRecord(S.out_free[k], S.down));
+  }
+
+  const int nchunk = (ncol + nc - 1) / nc;
+  auto upload = [&](int ic) {
+    const int k = ic & 1, c0 = ic * nc, n = std::min(nc, ncol - c0);
+    RB_CUDA_CHECK(cudaStreamWaitEvent(S.up, S.in_free[k], 0));
+    upload_cols(I[k].p_lay, in->p_lay, ncol, c0, n, nlay, S.up);
+    upload_cols(I[k].t_lay, in->t_lay, ncol, c0, n, nlay, S.up);
+    upload_cols(I[k].p_lev, in->p_lev, ncol, c0, n, nlev, S.up);
+    if (go_lw && in->t_lev) upload_cols(I[k].t_lev, in->t_lev, ncol, c0, n, nlev, S.up);
+    if (clouds) {
+      upload_cols(I[k].lwp, in->lwp, ncol, c0, n, nlay, S.up);
+      upload_cols(I[k].iwp, in->iwp, ncol, c0, n, nlay, S.up);
+      upload_cols(I[k].rel, in->rel, ncol, c0, n, nlay, S.up);
+      upload_cols(I[k].dei, in->dei, ncol, c0, n, nlay, S.up);
+    }
+    for (int g = 0; g < ngas; ++g)
+      if (I[k].field[(size_t)g]) upload_cols(I[k].field[(size_t)g], in->vmr_field[g], ncol, c0, n, nlay, S.up);
+    auto up1 = [&](Float* d, const Float* h, size_t per_col) {   // (k, ncol) arrays: a column range is contiguous
+      RB_CUDA_CHECK(cudaMemcpyAsync(d, h + per_col * c0, per_col * n * sizeof(Float), cudaMemcpyHostToDevice, S.up));
+    };
+    if (go_lw) { up1(I[k].t_sfc, in->t_sfc, 1); up1(I[k].emis, in->emis_sfc, nbnd_lw); }
+    if (go_sw) { up1(I[k].mu0, in->mu0, 1); up1(I[k].alb_dir, in->sfc_alb_dir, nbnd_sw); up1(I[k].alb_dif, in->sfc_alb_dif, nbnd_sw); }
+    RB_CUDA_CHECK(cudaEventRecord(S.in_ready[k], S.up));
+  };
+
+  std::string msg;
+  char err[RRTMGPB_ERRLEN];
+  upload(0);
+  for (int ic = 0; ic < nchunk && msg.empty(); ++ic) {
+    const int k = ic & 1, c0 = ic * nc, n = std::min(nc, ncol - c0);
+    if (ic + 1 < nchunk) upload(ic + 1);
+    RB_CUDA_CHECK(cudaStreamWaitEvent(comp, S.in_ready[k], 0));
+    RB_CUDA_CHECK(cudaStreamWaitEvent(comp, S.out_free[k], 0));
+    const InSet& X = I[k];
+    // gas_concs -> vmr(n, nlay, ngas): fields as uploaded, well-mixed gases broadcast (mo_gas_optics_rrtmgp.F90:540-545)
+    for (int g = 0; g < ngas; ++g) {
+      Float* plane = vmr + (size_t)n * nlay * g;
+      if (X.field[(size_t)g]) rrtmgpb_mem_copy(plane, X.field[(size_t)g], (size_t)n * nlay * sizeof(Float));
+      else set_to_scalar_2D(&n, &nlay, plane, &in->vmr_scalar[g]);
+    }
+    rrtmgpb_fluxes_broadband fl{O[k].f[0], O[k].f[1], nullptr, nullptr}, fs{O[k].f[2], O[k].f[3], nullptr, O[k].f[4]};
+    cld_lw.ncol = cld_sw.ncol = atm_lw.ncol = atm_sw.ncol = src.ncol = n;
+    if (go_lw && (out->lw_flux_up || out->lw_flux_dn)) {
+      if (clouds && rrtmgpb_cloud_optics(co_lw, n, nlay, X.lwp, X.iwp, X.rel, X.dei, &cld_lw, err)) { msg = err; break; }
+      const Float* tlev = in->t_lev ? X.t_lev : nullptr;
+      if (express) {
+        if (rrtmgpb_rte_lw_express(go_lw, n, nlay, X.p_lay, X.p_lev, X.t_lay, X.t_sfc, vmr, nullptr, tlev,
+                                   clouds ? &cld_lw : nullptr, X.emis, 0, &fl, err)) { msg = err; break; }
+      } else {
+        if (rrtmgpb_gas_optics_int_fused(go_lw, n, nlay, X.p_lay, X.p_lev, X.t_lay, X.t_sfc, vmr, &atm_lw, &src, nullptr, tlev,
+                                         clouds ? &cld_lw : nullptr, nullptr, err)) { msg = err; break; }
+        if (rrtmgpb_rte_lw(&atm_lw, &src, X.emis, &fl, nullptr, 0, -1, nullptr, nullptr, err)) { msg = err; break; }
+      }
+    }
+    if (go_sw && (out->sw_flux_up || out->sw_flux_dn || out->sw_flux_dir)) {
+      if (clouds && rrtmgpb_cloud_optics_delta_scaled(co_sw, n, nlay, X.lwp, X.iwp, X.rel, X.dei, &cld_sw, 1, err)) { msg = err; break; }
+      if (express) {
+        if (rrtmgpb_rte_sw_express(go_sw, n, nlay, X.p_lay, X.p_lev, X.t_lay, vmr, nullptr, clouds ? &cld_sw : nullptr, X.mu0,
+                                   X.alb_dir, X.alb_dif, &fs, err)) { msg = err; break; }
+      } else {
+        if (rrtmgpb_gas_optics_ext_fused(go_sw, n, nlay, X.p_lay, X.p_lev, X.t_lay, vmr, &atm_sw, toa, nullptr,
+                                         clouds ? &cld_sw : nullptr, nullptr, err)) { msg = err; break; }
+        if (rrtmgpb_rte_sw(&atm_sw, X.mu0, toa, X.alb_dir, X.alb_dif, &fs, nullptr, err)) { msg = err; break; }
+      }
+    }
+    RB_CUDA_CHECK(cudaEventRecord(S.in_free[k], comp));
+    RB_CUDA_CHECK(cudaEventRecord(S.out_ready[k], comp));
+    // ---- fluxes of this chunk -> host, behind the compute stream
+    RB_CUDA_CHECK(cudaStreamWaitEvent(S.down, S.out_ready[k], 0));
+    Float* dsts[5] = {out->lw_flux_up, out->lw_flux_dn, out->sw_flux_up, out->sw_flux_dn, out->sw_flux_dir};
+    for (int a = 0; a < 5; ++a)
+      if (dsts[a] && ((a < 2 && go_lw) || (a >= 2 && go_sw))) download_cols(dsts[a], O[k].f[a], ncol, c0, n, nlev, S.down);
+    RB_CUDA_CHECK(cudaEventRecord(S.out_free[k], S.down));
+  }
+  // the call returns when the last fluxes are on the host; the compute stream is ordered behind both copy streams
+  RB_CUDA_CHECK(cudaStreamSynchronize(S.down));
+  RB_CUDA_CHECK(cudaStreamSynchronize(S.up));
+  RB_CUDA_CHECK(cudaStreamSynchronize(comp));
+  for (void* p : owned) dev_free(p);
+  RB_CUDA_CHECK(cudaEventDestroy(start));
+  return msg.empty() ? 0 : fail(msg);
+}

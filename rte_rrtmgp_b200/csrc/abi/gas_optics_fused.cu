@@ -476,15 +476,22 @@ __global__ void reduce_groups_kernel(int n, int nlev, int ncol, int c0, int grou
 }
 
 struct ExpressPlan {
-  int nc, bands_per_group, rows;
+  int nc, bands_per_group, rows, nstreams;
 };
-// columns per chunk / bands per solver launch / grid rows: defaults keep the scratch of one launch (nc columns x the
-// g-points of one band x 3 planes) near 64 MB - L2 resident - with one 16-column CTA per SM slot pair
+// columns per chunk / bands per solver launch / grid rows / concurrent chunks.  Measured on B200 (65,536 x 72, LW+SW,
+// profiles/r2_express_sweep.jsonl; the plane path takes 39.4 ms): launches whose scratch fits L2 (2,368 columns x 1
+// band = 64 MB) leave most SMs idle - the Planck kernel has 76 blocks there - and the step takes 125 ms; 9,472 x 2
+// bands 54 ms; 16,384 x 2 bands 52.8 ms on one stream, 47.7 ms with two chunks in flight on two streams (one chunk's
+// tail overlaps the other's head); 32,768 x 4 bands on two streams 45.1 ms.  None of these kernels is HBM-bound (the
+// solvers are fp64-bound, the gas optics L1-bound), so L2 residency buys nothing and small launches cost; what the
+// express path buys is the footprint (2.9 GB instead of 54 GB at this size).  RRTMGPB_EXPRESS_NC / _BANDS / _ROWS /
+// _STREAMS override.
 ExpressPlan express_plan(int ncol, int nlay) {
   ExpressPlan pl;
-  pl.nc = env_int("RRTMGPB_EXPRESS_NC", 148 * 16);
-  pl.bands_per_group = env_int("RRTMGPB_EXPRESS_BANDS", 1);
-  pl.rows = env_int("RRTMGPB_EXPRESS_ROWS", 2);
+  pl.nc = env_int("RRTMGPB_EXPRESS_NC", 32768);
+  pl.bands_per_group = env_int("RRTMGPB_EXPRESS_BANDS", 4);
+  pl.rows = env_int("RRTMGPB_EXPRESS_ROWS", 1);
+  pl.nstreams = std::max(1, std::min(2, env_int("RRTMGPB_EXPRESS_STREAMS", 2)));
   if (pl.nc > ncol) pl.nc = ncol;
   if (pl.nc < 1) pl.nc = 1;
   if (pl.nc % 2) pl.nc += (pl.nc < ncol) ? 1 : 0;  // even chunk widths keep the scratch planes TMA-describable (16-byte row stride)
@@ -537,27 +544,49 @@ void rrtmgpb_express(const rrtmgpb_gas_tables* t, int ncol, int nlay, int top_at
   }
   const int narr = sw ? 3 : 2;
   const size_t ncl = (size_t)nc * nlay, nclp = (size_t)nc * nlev;
-  // ---- scratch, allocated once (stream-ordered pool)
-  const size_t nplane = sw ? 3 : 3;  // SW: tau, ssa, g ; LW: tau, lay_source, lev_source (nlev rows)
-  Float* planes = static_cast<Float*>(dev_alloc((ncl * 2 + nclp) * (size_t)ng_max * sizeof(Float)));
-  (void)nplane;
-  Float* in2d = static_cast<Float*>(dev_alloc((ncl * (3 + (size_t)ngas + 3 * (size_t)nbnd) + 2 * nclp + 4 * (size_t)nc) * sizeof(Float)));
-  Float* bnd = static_cast<Float*>(dev_alloc((size_t)nc * ngpt * 4 * sizeof(Float) + (size_t)nc * ng_max * (nmus + 2) * sizeof(Float)));
+  // ---- scratch, allocated once per concurrent chunk (stream-ordered pool, on the caller's stream)
   const size_t gstride = (size_t)narr * nclp;
-  Float* part = static_cast<Float*>(dev_alloc(gstride * pl.rows * sizeof(Float)));
-  Float* decoy = static_cast<Float*>(dev_alloc(nclp * sizeof(Float)));
+  const int nslots = (ncol > nc) ? pl.nstreams : 1;
+  struct Slot { Float *planes, *in2d, *bnd, *part, *decoy, *mu0_lay; } slots[2] = {};
+  for (int k = 0; k < nslots; ++k) {
+    Slot& sl = slots[k];
+    sl.planes = static_cast<Float*>(dev_alloc((ncl * 2 + nclp) * (size_t)ng_max * sizeof(Float)));  // SW tau, ssa, g; LW tau, lay, lev
+    sl.in2d = static_cast<Float*>(dev_alloc((ncl * (3 + (size_t)ngas + 3 * (size_t)nbnd) + 2 * nclp) * sizeof(Float)));
+    sl.bnd = static_cast<Float*>(dev_alloc((size_t)nc * ngpt * 4 * sizeof(Float) + (size_t)nc * ng_max * (nmus + 2) * sizeof(Float)));
+    sl.part = static_cast<Float*>(dev_alloc(gstride * pl.rows * sizeof(Float)));
+    sl.decoy = static_cast<Float*>(dev_alloc(nclp * sizeof(Float)));
+    sl.mu0_lay = static_cast<Float*>(dev_alloc(ncl * sizeof(Float)));
+  }
   Float* wts_dev = static_cast<Float*>(dev_alloc((size_t)std::max(nmus, 1) * sizeof(Float)));
   if (!sw) RB_CUDA_CHECK(cudaMemcpyAsync(wts_dev, wts_host, (size_t)nmus * sizeof(Float), cudaMemcpyHostToDevice, stream()));
-  // chunk-local inputs
-  Float* c_play = in2d; Float* c_tlay = c_play + ncl; Float* c_cd = c_tlay + ncl; Float* c_vmr = c_cd + ncl;
-  Float* c_ct = c_vmr + ncl * ngas; Float* c_cw = c_ct + ncl * nbnd; Float* c_cg = c_cw + ncl * nbnd;
-  Float* c_plev = c_cg + ncl * nbnd; Float* c_tlev = c_plev + nclp;
-  // boundary arrays of the chunk on all g-points: a g-point sub-range of an (nc, ngpt) array is a contiguous slab
-  Float* b_a = bnd; Float* b_b = b_a + (size_t)nc * ngpt; Float* b_toa = b_b + (size_t)nc * ngpt; Float* b_zero = b_toa + (size_t)nc * ngpt;
-  Float* b_Ds = b_zero + (size_t)nc * ngpt; Float* b_sfc = b_Ds + (size_t)nc * ng_max * nmus; Float* b_jac = b_sfc + (size_t)nc * ng_max;
-  Float* mu0_lay = static_cast<Float*>(dev_alloc(ncl * sizeof(Float)));
+  // ---- chunks alternate between the caller's stream and an auxiliary one (fork / join by events): the small grids at
+  // the end of one chunk's kernels overlap the next chunk's
+  cudaStream_t s_main = stream(), s_aux = s_main;
+  static thread_local cudaStream_t tl_aux = nullptr;
+  static thread_local cudaEvent_t tl_fork = nullptr, tl_join = nullptr;
+  if (nslots > 1) {
+    if (!tl_aux) {
+      RB_CUDA_CHECK(cudaStreamCreateWithFlags(&tl_aux, cudaStreamNonBlocking));
+      RB_CUDA_CHECK(cudaEventCreateWithFlags(&tl_fork, cudaEventDisableTiming));
+      RB_CUDA_CHECK(cudaEventCreateWithFlags(&tl_join, cudaEventDisableTiming));
+    }
+    s_aux = tl_aux;
+    RB_CUDA_CHECK(cudaEventRecord(tl_fork, s_main));
+    RB_CUDA_CHECK(cudaStreamWaitEvent(s_aux, tl_fork, 0));
+  }
 
-  for (int c0 = 0; c0 < ncol; c0 += nc) {
+  int ichunk = 0;
+  for (int c0 = 0; c0 < ncol; c0 += nc, ++ichunk) {
+    const Slot& sl = slots[ichunk % nslots];
+    rrtmgpb_set_stream((ichunk % nslots) ? s_aux : s_main);   // every launch below goes to this chunk's stream
+    Float *planes = sl.planes, *in2d = sl.in2d, *bnd = sl.bnd, *part = sl.part, *decoy = sl.decoy, *mu0_lay = sl.mu0_lay;
+    // chunk-local inputs
+    Float* c_play = in2d; Float* c_tlay = c_play + ncl; Float* c_cd = c_tlay + ncl; Float* c_vmr = c_cd + ncl;
+    Float* c_ct = c_vmr + ncl * ngas; Float* c_cw = c_ct + ncl * nbnd; Float* c_cg = c_cw + ncl * nbnd;
+    Float* c_plev = c_cg + ncl * nbnd; Float* c_tlev = c_plev + nclp;
+    // boundary arrays of the chunk on all g-points: a g-point sub-range of an (nc, ngpt) array is a contiguous slab
+    Float* b_a = bnd; Float* b_b = b_a + (size_t)nc * ngpt; Float* b_toa = b_b + (size_t)nc * ngpt; Float* b_zero = b_toa + (size_t)nc * ngpt;
+    Float* b_Ds = b_zero + (size_t)nc * ngpt; Float* b_sfc = b_Ds + (size_t)nc * ng_max * nmus; Float* b_jac = b_sfc + (size_t)nc * ng_max;
     const int n = std::min(nc, ncol - c0);
     const size_t nl = (size_t)n * nlay, nlp = (size_t)n * nlev;
     // ---- gather the chunk's columns (dense (n, nlay[, k]) copies of the strided slices)
@@ -633,7 +662,16 @@ void rrtmgpb_express(const rrtmgpb_gas_tables* t, int ncol, int nlay, int top_at
     }
     dev_free(w.block);
   }
-  dev_free(mu0_lay); dev_free(wts_dev); dev_free(decoy); dev_free(part); dev_free(bnd); dev_free(in2d); dev_free(planes);
+  rrtmgpb_set_stream(s_main);
+  if (nslots > 1) {   // join: the caller's stream continues after the auxiliary stream's chunks
+    RB_CUDA_CHECK(cudaEventRecord(tl_join, s_aux));
+    RB_CUDA_CHECK(cudaStreamWaitEvent(s_main, tl_join, 0));
+  }
+  dev_free(wts_dev);
+  for (int k = 0; k < nslots; ++k) {
+    dev_free(slots[k].mu0_lay); dev_free(slots[k].decoy); dev_free(slots[k].part); dev_free(slots[k].bnd);
+    dev_free(slots[k].in2d); dev_free(slots[k].planes);
+  }
 }
 
 }  // extern "C"

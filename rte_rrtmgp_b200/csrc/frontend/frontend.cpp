@@ -526,6 +526,13 @@ int rrtmgpb_gas_optics_compute_optimal_angles(const rrtmgpb_gas_optics_t* go, co
   return ok(errmsg);
 }
 
+/* table dimensions and the HOST copy of band_lims_gpt (2,nbnd) of a loaded k-distribution */
+void rrtmgpb_gas_optics_dims(const rrtmgpb_gas_optics_t* go, int* ngas, int* nbnd, int* ngpt) {
+  if (ngas) *ngas = go->h.ngas;
+  if (nbnd) *nbnd = go->h.nbnd;
+  if (ngpt) *ngpt = go->h.ngpt;
+}
+const int* rrtmgpb_gas_optics_band_lims_gpt(const rrtmgpb_gas_optics_t* go) { return go->band_lims_gpt_h.data(); }
 /* backend address of the loaded kmajor table: the key of the g-point-fastest copies (rrtmgpb_tables_changed) */
 Float* rrtmgpb_gas_optics_kmajor(const rrtmgpb_gas_optics_t* go) { return go ? go->kmajor : nullptr; }
 int rrtmgpb_gas_optics_source_is_internal(const rrtmgpb_gas_optics_t* go) { return go->totplnk != nullptr; }

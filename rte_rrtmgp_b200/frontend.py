@@ -677,3 +677,41 @@ def load_kdist_raw(lib, raw, available_gases, mg_index=None, sb_index=None, tsi=
         return kd
     finally:
         c.rrtmgpb_kdist_loaded_free(h)
+
+
+# ----------------------------------------------------------------------------------------------------
+# The all-sky iteration on HOST buffers (rrtmgpb_allsky_stream_host, csrc/abi/allsky_stream.cu): marshalling only.
+# ----------------------------------------------------------------------------------------------------
+class _AllSkyHostInputs(C.Structure):
+    _fields_ = ([("ncol", C.c_int), ("nlay", C.c_int)] + [(n, C.c_void_p) for n in ("p_lay", "p_lev", "t_lay", "t_lev")]
+                + [("ngas", C.c_int), ("vmr_field", C.c_void_p), ("vmr_scalar", C.c_void_p)]
+                + [(n, C.c_void_p) for n in ("lwp", "iwp", "rel", "dei", "t_sfc", "emis_sfc", "mu0", "sfc_alb_dir", "sfc_alb_dif")])
+
+
+class _AllSkyHostFluxes(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("lw_flux_up", "lw_flux_dn", "sw_flux_up", "sw_flux_dn", "sw_flux_dir")]
+
+
+def allsky_stream_host(lib, go_lw, go_sw, co_lw, co_sw, inputs, fluxes, gas_names, vmr_scalars, chunk_cols, express=False):
+    """inputs / fluxes: dicts of HOST arrays in Fortran order - numpy arrays or (pinned) torch CPU tensors holding the
+    transposed C-contiguous data, i.e. anything whose memory is (ncol, nlay) first-index-fastest.  Gas fields are the
+    entries of `inputs` named like a gas; the other gases of `gas_names` take vmr_scalars[name]."""
+    def addr(x):
+        return None if x is None else _addr(x)
+
+    ncol, nlay = inputs["shape"]
+    fields = (C.c_void_p * len(gas_names))(*[addr(inputs.get(g)) for g in gas_names])
+    scal = (FLOAT * len(gas_names))(*[float(vmr_scalars.get(g, 0.0)) for g in gas_names])
+    s = _AllSkyHostInputs()
+    s.ncol, s.nlay, s.ngas = int(ncol), int(nlay), len(gas_names)
+    s.vmr_field, s.vmr_scalar = C.cast(fields, C.c_void_p), C.cast(scal, C.c_void_p)
+    for n in ("p_lay", "p_lev", "t_lay", "t_lev", "lwp", "iwp", "rel", "dei", "t_sfc", "emis_sfc", "mu0", "sfc_alb_dir",
+              "sfc_alb_dif"):
+        setattr(s, n, addr(inputs.get(n)))
+    f = _AllSkyHostFluxes()
+    for n in ("lw_flux_up", "lw_flux_dn", "sw_flux_up", "sw_flux_dn", "sw_flux_dir"):
+        setattr(f, n, addr(fluxes.get(n)))
+    err = C.create_string_buffer(ERRLEN)
+    h = lambda o: C.c_void_p(o.handle) if o is not None else None
+    _check(lib.cdll.rrtmgpb_allsky_stream_host(h(go_lw), h(go_sw), h(co_lw), h(co_sw), C.byref(s), C.byref(f), int(chunk_cols),
+                                               int(bool(express)), err), err)

@@ -108,9 +108,9 @@ def test_oracle_fused_entry_equals_reference_sequence(oracle_lib, kdists):
 
 @pytest.mark.gpu
 def test_smoke_entry():
-    from rte_rrtmgp_b200 import smoke_check
+    import __graft_entry__ as entry
 
-    assert smoke_check.run(ncol=24, nlay=72) <= FLUX_ATOL
+    assert entry.smoke(ncol=24, nlay=72, verbose=False) <= FLUX_ATOL
 
 
 @pytest.mark.gpu
