@@ -478,21 +478,18 @@ def run_product(args):
         del h
         b.free()
 
-        # ---- a stock host (gfortran-style: HOST arrays into the 45 symbols, every call staged through PCIe), small slice
-        if not args.no_extras and world == 1:
+        # ---- a stock host (gfortran-style: HOST arrays into the 45 symbols, every call staged through PCIe), small slice;
+        # in a child process: a failure on this correctness path must not take the bench line with it
+        if not args.no_extras and world == 1 and rank == 0:
             try:
-                nh = 2048
-                hs = AllSky(Context(lib, None), nh, NLAY, kd_lw, kd_sw, fused=False)
-                hs.step()
-                t0 = time.perf_counter()
-                hs.step()
-                lib.sync()
-                extras["value_host_pointer_call_sequence"] = nh / (time.perf_counter() - t0)
-                extras["host_pointer_note"] = f"{nh} columns, numpy arrays handed to the 45 symbols one by one: every argument is staged to the device and back per call (PCIe-bound correctness path)"
-                del hs
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "host_pointer_bench.py")], capture_output=True,
+                                   text=True, timeout=300)
+                hp = json.loads(r.stdout.strip().splitlines()[-1])
+                extras["value_host_pointer_call_sequence"] = hp["value"]
+                extras["host_pointer_note"] = hp["note"]
             except Exception as e:  # pragma: no cover
                 extras["value_host_pointer_call_sequence"] = None
-                extras["host_pointer_note"] = f"failed: {e}"
+                extras["host_pointer_note"] = f"failed: {str(e)[:160]}"
 
         # ---- the other BASELINE.json configurations, per GPU, few steps (supplementary; full runs: --config c3|c4|c5)
         if not args.no_extras:

@@ -657,18 +657,23 @@ void rte_lw_solver_noscat(const int* ncol_, const int* nlay_, const int* ngpt_, 
     dim3 grid(ceil_div(ncol, (kRegThreads / 32) * kRegCols), ceil_div(ngpt, q.gpt_per_block));
     // TMA tile staging of tau / lay_source / lev_source (kernels/tma.cuh) whenever the planes can be described
     LwTmaMaps maps;
-    const bool use_tma = solver_tma_enabled() && make_plane_tmap(&maps.tau, q.tau, ncol, nlay, ngpt) &&
-                         make_plane_tmap(&maps.lay, q.lay_source, ncol, nlay, ngpt) &&
-                         make_plane_tmap(&maps.lev, q.lev_source, ncol, nlay + 1, ngpt);
+    // layers per lane (see the switch below) and the tile height: 8*CL rows when nlay is not a multiple of 8 - the rows
+    // beyond the plane arrive zero-filled and act as pass-through layers, so every TMA launch runs the FULL instantiation
+    const int clv = cl <= 9 ? 9 : 10, rows = 8 * clv;
+    q.tile_rows = rows; q.row0 = p.top_at_1 ? 0 : nlay - rows;
+    const bool use_tma = solver_tma_enabled() && make_plane_tmap(&maps.tau, q.tau, ncol, nlay, ngpt, rows) &&
+                         make_plane_tmap(&maps.lay, q.lay_source, ncol, nlay, ngpt, rows) &&
+                         make_plane_tmap(&maps.lev, q.lev_source, ncol, nlay + 1, ngpt, rows + 1);
     {
       KernelTimer timer("lw_noscat_reg_kernel");
 #define LWREG2(CLV, BBV, JACV)                                                                              \
   {                                                                                                         \
     if (use_tma && reg_minb() == 2) {                                                                       \
-      const size_t smem = lw_noscat_reg_tma_smem(nlay);                                                     \
-      auto kern = nlay == 8 * CLV ? (nmus == 1 ? lw_noscat_reg_kernel<CLV, BBV, JACV, 2, true, true, true>  \
-                                               : lw_noscat_reg_kernel<CLV, BBV, JACV, 2, true, true, false>) \
-                                  : lw_noscat_reg_kernel<CLV, BBV, JACV, 2, true, false, false>;            \
+      const size_t smem = lw_noscat_reg_tma_smem(rows);                                                     \
+      auto kern = rows == nlay ? (nmus == 1 ? lw_noscat_reg_kernel<CLV, BBV, JACV, 2, true, 1, true>        \
+                                            : lw_noscat_reg_kernel<CLV, BBV, JACV, 2, true, 1, false>)      \
+                               : (nmus == 1 ? lw_noscat_reg_kernel<CLV, BBV, JACV, 2, true, 2, true>        \
+                                            : lw_noscat_reg_kernel<CLV, BBV, JACV, 2, true, 2, false>);     \
       RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
       kern<<<grid, kRegThreads, smem, stream()>>>(q, maps);                                                 \
     } else {                                                                                                \
@@ -733,20 +738,22 @@ void rte_lw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
     q.gpt_per_block = ceil_div(ngpt, reg_gpt_groups(ncol, ngpt));
     dim3 grid(ceil_div(ncol, (kRegThreads / 32) * kRegCols), ceil_div(ngpt, q.gpt_per_block));
     Lw2sTmaMaps maps;
-    const bool use_tma = solver_tma_enabled() && make_plane_tmap(&maps.tau, q.tau, ncol, nlay, ngpt) &&
-                         make_plane_tmap(&maps.ssa, q.ssa, ncol, nlay, ngpt) && make_plane_tmap(&maps.g, q.g, ncol, nlay, ngpt) &&
-                         make_plane_tmap(&maps.lay, q.lay_source, ncol, nlay, ngpt) &&
-                         make_plane_tmap(&maps.lev, q.lev_source, ncol, nlay + 1, ngpt);
+    const int clv = cl <= 9 ? 9 : 10, rows = 8 * clv;   // zero-filled padded tiles, see rte_lw_solver_noscat
+    q.tile_rows = rows; q.row0 = p.top_at_1 ? 0 : nlay - rows;
+    const bool use_tma = solver_tma_enabled() && make_plane_tmap(&maps.tau, q.tau, ncol, nlay, ngpt, rows) &&
+                         make_plane_tmap(&maps.ssa, q.ssa, ncol, nlay, ngpt, rows) && make_plane_tmap(&maps.g, q.g, ncol, nlay, ngpt, rows) &&
+                         make_plane_tmap(&maps.lay, q.lay_source, ncol, nlay, ngpt, rows) &&
+                         make_plane_tmap(&maps.lev, q.lev_source, ncol, nlay + 1, ngpt, rows + 1);
     {
       KernelTimer timer("lw_2stream_reg_kernel");
 #define LW2S(CLV)                                                                                          \
   if (use_tma) {                                                                                           \
-    const size_t smem = lw_2stream_reg_tma_smem(nlay);                                                     \
-    auto kern = nlay == 8 * CLV ? lw_2stream_reg_kernel<CLV, true, true> : lw_2stream_reg_kernel<CLV, true, false>; \
+    const size_t smem = lw_2stream_reg_tma_smem(rows);                                                     \
+    auto kern = rows == nlay ? lw_2stream_reg_kernel<CLV, true, 1> : lw_2stream_reg_kernel<CLV, true, 2>;  \
     RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
     kern<<<grid, kRegThreads, smem, stream()>>>(q, maps);                                                  \
   } else {                                                                                                 \
-    lw_2stream_reg_kernel<CLV, false, false><<<grid, kRegThreads, 0, stream()>>>(q, maps);                        \
+    lw_2stream_reg_kernel<CLV, false, 0><<<grid, kRegThreads, 0, stream()>>>(q, maps);                        \
   }
       // the chunk length fixes the association of the chunk-level scan: it must not depend on use_tma (see
       // rte_lw_solver_noscat); CL = 8 conflicts on the TMA tiles, so nlay <= 64 runs CL = 9 as well
@@ -814,8 +821,10 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
     dim3 grid(ceil_div(ncol, (kRegThreads / 32) * kRegCols), ceil_div(ngpt, q.gpt_per_block));
     // TMA tile staging of tau / ssa / g (kernels/tma.cuh) whenever the planes can be described
     SwTmaMaps maps;
-    const bool use_tma = solver_tma_enabled() && make_plane_tmap(&maps.tau, q.tau, ncol, nlay, ngpt) &&
-                         make_plane_tmap(&maps.ssa, q.ssa, ncol, nlay, ngpt) && make_plane_tmap(&maps.g, q.g, ncol, nlay, ngpt);
+    const int rows = 8 * cl;   // zero-filled padded tiles, see rte_lw_solver_noscat
+    q.tile_rows = rows; q.row0 = p.top_at_1 ? 0 : nlay - rows;
+    const bool use_tma = solver_tma_enabled() && make_plane_tmap(&maps.tau, q.tau, ncol, nlay, ngpt, rows) &&
+                         make_plane_tmap(&maps.ssa, q.ssa, ncol, nlay, ngpt, rows) && make_plane_tmap(&maps.g, q.g, ncol, nlay, ngpt, rows);
     {
       KernelTimer timer("sw_2stream_reg_kernel");
 #define SWREG2(CLV, BBV)                                                                                    \
@@ -823,10 +832,10 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
     const bool lean = BBV && reg_minb() == 3;                                                               \
     const bool sacc = BBV && reg_sacc();                                                                    \
     if (use_tma && !lean) {                                                                                 \
-      const size_t smem = sacc ? sw_reg_tma_smem<CLV, true>(nlay) : sw_reg_tma_smem<CLV, false>(nlay);      \
-      auto kern = sacc ? sw_2stream_reg_kernel<CLV, BBV, 2, BBV, true>                                      \
-                       : (nlay == 8 * CLV ? sw_2stream_reg_kernel<CLV, BBV, 2, false, true, true>           \
-                                          : sw_2stream_reg_kernel<CLV, BBV, 2, false, true, false>);        \
+      const size_t smem = sacc ? sw_reg_tma_smem<CLV, true>(rows) : sw_reg_tma_smem<CLV, false>(rows);      \
+      auto kern = sacc ? sw_2stream_reg_kernel<CLV, BBV, 2, BBV, true, 2>                                   \
+                       : (rows == nlay ? sw_2stream_reg_kernel<CLV, BBV, 2, false, true, 1>                 \
+                                       : sw_2stream_reg_kernel<CLV, BBV, 2, false, true, 2>);               \
       RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
       kern<<<grid, kRegThreads, smem, stream()>>>(q, maps);                                                 \
     } else {                                                                                                \

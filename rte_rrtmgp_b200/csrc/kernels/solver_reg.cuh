@@ -198,6 +198,11 @@ struct LwNoscatRegParams {
   // deterministic, no atomics), and a launch may add to what earlier launches (other bands) left there
   int accumulate;
   size_t group_stride;
+  // FULL = 2 instantiations (TMA, nlay not a multiple of 8): the TMA box is 8*CL (+1) rows tall and starts at row0
+  // (negative for bottom-up columns); rows outside the plane arrive zero-filled, so the tile is addressed like a full
+  // one - no clamped row indices - and padding cells are turned into exact pass-through cells by selects on their
+  // RESULTS only (FSEL pairs on the integer pipe).  tile_rows = rows of a layer tile (nlay when FULL = 1).
+  int tile_rows, row0;
 };
 
 template <int CL>
@@ -210,14 +215,17 @@ __host__ __device__ inline size_t lw_noscat_reg_tma_smem(int nlay) {
   return 2 * (2 * tile_bytes(nlay) + tile_bytes(nlay + 1)) + (size_t)(2 * 5) * kRegThreads * sizeof(Float) + 2 * sizeof(uint64_t);
 }
 
-// FULL: nlay == 8*CL, every lane's cells are real layers - the padding selects and tests fold away at compile time.
+// FULL = 1: nlay == 8*CL, every lane's cells are real layers - the padding selects and tests fold away at compile time;
+// FULL = 2: zero-filled padded tiles (LwNoscatRegParams::tile_rows); 0: clamped addressing (cp.async fallback).
 // ONEMU: a single quadrature angle (the default of rte_lw): the loop over angles folds away.
-template <int CL, bool BB, bool JAC, int MINB = 3, bool TMA = false, bool FULL = false, bool ONEMU = false>
+template <int CL, bool BB, bool JAC, int MINB = 3, bool TMA = false, int FULL = 0, bool ONEMU = false>
 __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const LwNoscatRegParams p,
                                                                            const __grid_constant__ LwTmaMaps tm) {
   // no static shared memory: the swizzled TMA tiles need the dynamic window to start 1024-byte aligned
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const size_t tb_lay = TMA ? tile_bytes(p.nlay) : 0, tb_lev = TMA ? tile_bytes(p.nlay + 1) : 0;
+  constexpr bool FULLG = FULL == 1;   // no level beyond nlay exists: padding selects and store guards fold away
+  const int row0 = (FULL == 2) ? p.row0 : 0, tile_rows = (FULL == 2) ? p.tile_rows : p.nlay;
+  const size_t tb_lay = TMA ? tile_bytes(tile_rows) : 0, tb_lev = TMA ? tile_bytes(tile_rows + 1) : 0;
   const size_t stageb = 2 * tb_lay + tb_lev;
   const int te_lay = (int)(tb_lay / sizeof(Float));
   Float* sm = reinterpret_cast<Float*>(smem_raw + 2 * stageb);  // cp.async slots
@@ -246,11 +254,11 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
   auto prefetch = [&](int g, int s) {
     if (TMA) {
       if (threadIdx.x == 0) {
-        mbar_expect_tx(&full_bar[s], (uint32_t)((2 * nlay + nlev) * kTmaCols * sizeof(Float)));
+        mbar_expect_tx(&full_bar[s], (uint32_t)((3 * tile_rows + 1) * kTmaCols * sizeof(Float)));
         unsigned char* dst = smem_raw + (size_t)s * stageb;
-        tma_load_tile(dst, &tm.tau, &full_bar[s], cta_col0, 0, g);
-        tma_load_tile(dst + tb_lay, &tm.lay, &full_bar[s], cta_col0, 0, g);
-        tma_load_tile(dst + 2 * tb_lay, &tm.lev, &full_bar[s], cta_col0, 0, g);
+        tma_load_tile(dst, &tm.tau, &full_bar[s], cta_col0, row0, g);
+        tma_load_tile(dst + tb_lay, &tm.lay, &full_bar[s], cta_col0, row0, g);
+        tma_load_tile(dst + 2 * tb_lay, &tm.lev, &full_bar[s], cta_col0, row0, g);
       }
     } else {
       const Float* tau_g = p.tau + ncl * g;
@@ -324,13 +332,13 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
                                : p.Ds[(size_t)col + ncol * ((size_t)g + (size_t)p.ngpt * imu)];
       // ---------------- phase A: CL cells per lane, in registers ----------------
       Float tr[CL], sd[CL], su[CL];
-      Float Btop = TMA ? *tile_at(tile_lev, o.lev(FULL ? k0 : min(k0, nlay)), cw) : *RB_SLOT(sm, NS, s, 2 * CL);
+      Float Btop = TMA ? *tile_at(tile_lev, o.lev(FULL ? k0 : min(k0, nlay)) - row0, cw) : *RB_SLOT(sm, NS, s, 2 * CL);
 #pragma unroll
       for (int i = 0; i < CL; ++i) {
-        const Float Bbot = TMA ? *tile_at(tile_lev, o.lev(FULL ? k0 + i + 1 : min(k0 + i + 1, nlay)), cw) : *RB_SLOT(sm, NS, s, 2 * CL + i + 1);
+        const Float Bbot = TMA ? *tile_at(tile_lev, o.lev(FULL ? k0 + i + 1 : min(k0 + i + 1, nlay)) - row0, cw) : *RB_SLOT(sm, NS, s, 2 * CL + i + 1);
         {  // straight-line (see the SW kernel): padding cells become pass-through cells by selects
-          const bool live = FULL || k0 + i < nlay;
-          const Float* e_lay = TMA ? tile_at(tile_tau, o.lay(FULL ? k0 + i : min(k0 + i, nlay - 1)), cw) : nullptr;
+          const bool live = FULLG || k0 + i < nlay;
+          const Float* e_lay = TMA ? tile_at(tile_tau, o.lay(FULL ? k0 + i : min(k0 + i, nlay - 1)) - row0, cw) : nullptr;
           const Float tau_loc = (TMA ? e_lay[0] : *RB_SLOT(sm, NS, s, i)) * D;     // :181
           const Float t = rb_exp(-tau_loc);                                           // :182
           // :652-656, both branches evaluated (the divisor is clamped where the series is selected anyway)
@@ -350,7 +358,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
       }
       // g-point flux of one level (only when spectrally resolved output is requested)
       auto store = [&](Float* gflux, int klev, Float I) {
-        if ((!FULL && klev > nlay) || !col_ok) return;
+        if ((!FULLG && klev > nlay) || !col_ok) return;
         Float* q = gflux + (size_t)col + ncol * o.lev(klev);
         *q = (imu == 0) ? piw * I : *q + piw * I;                                  // :223-224, :356-357
       };
@@ -389,7 +397,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
           // the incoming value sits at the level below layer k0+i: record it, then cross the layer
           // (accumulator slots of padding cells are never written out, so the sums need no guard: branch-free)
           if (BB) acc_up[BB ? i : 0] += w * Iu;
-          else if (FULL || k0 + i < nlay) store(fup, k0 + i + 1, Iu);
+          else if (FULLG || k0 + i < nlay) store(fup, k0 + i + 1, Iu);
           if (JAC) acc_jac[JAC ? i : 0] += w * Ij;
           Iu = tr[i] * Iu + su[i];
           if (JAC) Ij = tr[i] * Ij;
@@ -414,7 +422,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
       const int klev = k0 + i + 1;
-      if (FULL || klev <= nlay) {
+      if (FULLG || klev <= nlay) {
         const size_t o2 = (size_t)col + ncol * o.lev(klev);
         if (BB) { put(bu, o2, pi * acc_up[BB ? i : 0]); put(bd, o2, pi * acc_dn[BB ? i : 0]); }
         if (JAC) put(bj, o2, pi * acc_jac[JAC ? i : 0]);
@@ -605,6 +613,7 @@ struct SwRegParams {
   int gpt_per_block;
   int accumulate;        // express path, see LwNoscatRegParams
   size_t group_stride;
+  int tile_rows, row0;   // zero-filled padded tiles, see LwNoscatRegParams
 };
 
 template <int CL>
@@ -625,13 +634,15 @@ __host__ __device__ inline size_t sw_reg_tma_smem(int nlay) {
 }
 
 // FULL: nlay == 8*CL, every lane's cells are real layers - the padding selects and tests fold away at compile time.
-template <int CL, bool BB, int MINB = 3, bool LEAN = false, bool TMA = false, bool FULL = false>
+template <int CL, bool BB, int MINB = 3, bool LEAN = false, bool TMA = false, int FULL = 0>
 __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const SwRegParams p,
                                                                             const __grid_constant__ SwTmaMaps tm) {
   static_assert(!LEAN || BB, "LEAN is a broadband-only variant");
   // no static shared memory in this kernel: the swizzled TMA tiles need the dynamic window to start 1024-byte aligned
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const size_t tileb = TMA ? tile_bytes(p.nlay) : 0;           // bytes of one tile
+  constexpr bool FULLG = FULL == 1;                             // see LwNoscatRegParams::tile_rows
+  const int row0 = (FULL == 2) ? p.row0 : 0, tile_rows = (FULL == 2) ? p.tile_rows : p.nlay;
+  const size_t tileb = TMA ? tile_bytes(tile_rows) : 0;        // bytes of one tile
   const int tile_elems = (int)(tileb / sizeof(Float));
   const Float* tiles = reinterpret_cast<const Float*>(smem_raw);   // TMA: [stage][plane][row][16]
   Float* sm = reinterpret_cast<Float*>(smem_raw + 2 * 3 * tileb);  // cp.async slots
@@ -662,11 +673,11 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
   auto prefetch = [&](int g, int s) {
     if (TMA) {
       if (threadIdx.x == 0) {
-        mbar_expect_tx(&full_bar[s], (uint32_t)(3 * nlay * kTmaCols * sizeof(Float)));
+        mbar_expect_tx(&full_bar[s], (uint32_t)(3 * tile_rows * kTmaCols * sizeof(Float)));
         unsigned char* dst = smem_raw + (size_t)s * 3 * tileb;
-        tma_load_tile(dst, &tm.tau, &full_bar[s], cta_col0, 0, g);
-        tma_load_tile(dst + tileb, &tm.ssa, &full_bar[s], cta_col0, 0, g);
-        tma_load_tile(dst + 2 * tileb, &tm.g, &full_bar[s], cta_col0, 0, g);
+        tma_load_tile(dst, &tm.tau, &full_bar[s], cta_col0, row0, g);
+        tma_load_tile(dst + tileb, &tm.ssa, &full_bar[s], cta_col0, row0, g);
+        tma_load_tile(dst + 2 * tileb, &tm.g, &full_bar[s], cta_col0, row0, g);
       }
     } else {
       const Float* tau_g = p.tau + ncl * g;
@@ -749,10 +760,10 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
     // interleave the CL independent cells of a lane.
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
-      const bool live = FULL || k0 + i < nlay;
+      const bool live = FULLG || k0 + i < nlay;
       Float tau_s, w0_s, g_s;
       if (TMA) {
-        const Float* e = tile_at(tile_s, o.lay(FULL ? k0 + i : min(k0 + i, nlay - 1)), cw);
+        const Float* e = tile_at(tile_s, o.lay(FULL ? k0 + i : min(k0 + i, nlay - 1)) - row0, cw);
         tau_s = e[0]; w0_s = e[tile_elems]; g_s = e[2 * tile_elems];
       } else {
         tau_s = *RB_SLOT(sm, NS, s, i); w0_s = *RB_SLOT(sm, NS, s, CL + i); g_s = *RB_SLOT(sm, NS, s, 2 * CL + i);
@@ -838,7 +849,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
         A4[i] = s_dn;
         // (accumulator slots of padding cells are never written out, so the sums need no guard: branch-free)
         if (BB) { acc_add(2, i, dir); acc_add(1, i, dir); }  // :604, direct part of :603
-        else if ((FULL || k0 + i < nlay) && col_ok) gdir[(size_t)col + ncol * o.lev(k0 + i + 1)] = dir;
+        else if ((FULLG || k0 + i < nlay) && col_ok) gdir[(size_t)col + ncol * o.lev(k0 + i + 1)] = dir;
         A5[i] = dir;  // direct flux below layer k0+i, for the g-point totals (:606)
       }
     }
@@ -854,7 +865,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
     };
     auto lev = [&](int i, Float fup, Float fdn) {
       if (BB) { acc_add(0, i, fup); acc_add(1, i, fdn); }
-      else if ((FULL || k0 + i < nlay) && col_ok) {
+      else if ((FULLG || k0 + i < nlay) && col_ok) {
         const size_t q = (size_t)col + ncol * o.lev(k0 + i + 1);
         gup[q] = fup;
         gdn[q] = fdn + A5[i];                                                 // :606
@@ -869,7 +880,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
       const int klev = k0 + i + 1;
-      if (FULL || klev <= nlay) {
+      if (FULLG || klev <= nlay) {
         const size_t o2 = (size_t)col + ncol * o.lev(klev);
         if (LEAN) {
           put(bu, o2, sm_acc[i * kRegThreads]); put(bd, o2, sm_acc[(CL + i) * kRegThreads]);
@@ -894,6 +905,7 @@ struct Lw2sRegParams {
   const Float *tau, *ssa, *g, *lay_source, *lev_source, *sfc_emis, *sfc_src, *inc_flux;
   Float *flux_up, *flux_dn;
   int gpt_per_block;
+  int tile_rows, row0;   // zero-filled padded tiles, see LwNoscatRegParams
 };
 
 // TMA variant: tau, ssa, g, lay_source (nlay rows) and lev_source (nlay+1 rows) tiles per g-point, two stages.
@@ -902,12 +914,14 @@ __host__ __device__ inline size_t lw_2stream_reg_tma_smem(int nlay) {
   return 2 * (4 * tile_bytes(nlay) + tile_bytes(nlay + 1)) + 2 * sizeof(uint64_t);
 }
 
-template <int CL, bool TMA = false, bool FULL = false>
+template <int CL, bool TMA = false, int FULL = 0>
 __global__ void __launch_bounds__(kRegThreads, TMA ? 2 : 3) lw_2stream_reg_kernel(const Lw2sRegParams p,
                                                                                   const __grid_constant__ Lw2sTmaMaps tm) {
   // no static shared memory: the swizzled TMA tiles need the dynamic window to start 1024-byte aligned
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const size_t tb_lay = TMA ? tile_bytes(p.nlay) : 0, tb_lev = TMA ? tile_bytes(p.nlay + 1) : 0;
+  constexpr bool FULLG = FULL == 1;    // see LwNoscatRegParams::tile_rows
+  const int row0 = (FULL == 2) ? p.row0 : 0, tile_rows = (FULL == 2) ? p.tile_rows : p.nlay;
+  const size_t tb_lay = TMA ? tile_bytes(tile_rows) : 0, tb_lev = TMA ? tile_bytes(tile_rows + 1) : 0;
   const size_t stageb = 4 * tb_lay + tb_lev;
   const int te_lay = (int)(tb_lay / sizeof(Float));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * stageb);
@@ -928,13 +942,13 @@ __global__ void __launch_bounds__(kRegThreads, TMA ? 2 : 3) lw_2stream_reg_kerne
 
   auto issue = [&](int g, int s) {  // TMA only
     if (threadIdx.x == 0) {
-      mbar_expect_tx(&full_bar[s], (uint32_t)((4 * nlay + nlev) * kTmaCols * sizeof(Float)));
+      mbar_expect_tx(&full_bar[s], (uint32_t)((5 * tile_rows + 1) * kTmaCols * sizeof(Float)));
       unsigned char* dst = smem_raw + (size_t)s * stageb;
-      tma_load_tile(dst, &tm.tau, &full_bar[s], cta_col0, 0, g);
-      tma_load_tile(dst + tb_lay, &tm.ssa, &full_bar[s], cta_col0, 0, g);
-      tma_load_tile(dst + 2 * tb_lay, &tm.g, &full_bar[s], cta_col0, 0, g);
-      tma_load_tile(dst + 3 * tb_lay, &tm.lay, &full_bar[s], cta_col0, 0, g);
-      tma_load_tile(dst + 4 * tb_lay, &tm.lev, &full_bar[s], cta_col0, 0, p.lev_per_gpt ? g : 0);  // quirk :422
+      tma_load_tile(dst, &tm.tau, &full_bar[s], cta_col0, row0, g);
+      tma_load_tile(dst + tb_lay, &tm.ssa, &full_bar[s], cta_col0, row0, g);
+      tma_load_tile(dst + 2 * tb_lay, &tm.g, &full_bar[s], cta_col0, row0, g);
+      tma_load_tile(dst + 3 * tb_lay, &tm.lay, &full_bar[s], cta_col0, row0, g);
+      tma_load_tile(dst + 4 * tb_lay, &tm.lev, &full_bar[s], cta_col0, row0, p.lev_per_gpt ? g : 0);  // quirk :422
     }
   };
   if (TMA) {
@@ -961,16 +975,16 @@ __global__ void __launch_bounds__(kRegThreads, TMA ? 2 : 3) lw_2stream_reg_kerne
 #pragma unroll
     for (int i = 0; i <= CL; ++i) {
       const int kk = FULL ? k0 + i : min(k0 + i, nlay);
-      Blev[i] = TMA ? *tile_at(tile_lev, o.lev(kk), cw) : p.lev_source[col + ncol * o.lev(kk) + nclp * gsrc];
+      Blev[i] = TMA ? *tile_at(tile_lev, o.lev(kk) - row0, cw) : p.lev_source[col + ncol * o.lev(kk) + nclp * gsrc];
     }
     // straight-line per cell (see sw_2stream_reg_kernel): padding cells become pass-through cells by selects
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
-      const bool live = FULL || k0 + i < nlay;
+      const bool live = FULLG || k0 + i < nlay;
       const int lay = o.lay(FULL ? k0 + i : min(k0 + i, nlay - 1));
       Float tau, w0, gg;
       if (TMA) {
-        const Float* e = tile_at(tile_tau, lay, cw);
+        const Float* e = tile_at(tile_tau, lay - row0, cw);
         tau = e[0]; w0 = e[te_lay]; gg = e[2 * te_lay];
       } else {
         const size_t i3 = col + ncol * lay + ncl * g;
@@ -1011,7 +1025,7 @@ __global__ void __launch_bounds__(kRegThreads, TMA ? 2 : 3) lw_2stream_reg_kerne
       gdn[q] = fdn;
     };
     auto lev = [&](int i, Float fup, Float fdn) {
-      if ((!FULL && k0 + i >= nlay) || !col_ok) return;
+      if ((!FULLG && k0 + i >= nlay) || !col_ok) return;
       const size_t q = col + ncol * o.lev(k0 + i + 1);
       gup[q] = fup;
       gdn[q] = fdn;

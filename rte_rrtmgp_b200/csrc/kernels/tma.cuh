@@ -75,16 +75,20 @@ inline EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// Tensor map of a Fortran-ordered (ncol, nrows, ngpt) plane with box (kTmaCols, nrows, 1).  Returns false when the
-// plane cannot be described (odd ncol -> strides not multiples of 16 B, misaligned base, more than 256 rows, no driver).
-inline bool make_plane_tmap(CUtensorMap* tm, const Float* base, int ncol, int nrows, int ngpt) {
+// Tensor map of a Fortran-ordered (ncol, nrows, ngpt) plane with box (kTmaCols, box_rows, 1); box_rows = 0: nrows.  A
+// box taller than the plane (or started at a negative row) is allowed: rows outside the tensor arrive as zeros
+// (CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE = zero fill), which the solvers use as exact pass-through padding layers.
+// Returns false when the plane cannot be described (odd ncol -> strides not multiples of 16 B, misaligned base, more
+// than 256 rows, no driver).
+inline bool make_plane_tmap(CUtensorMap* tm, const Float* base, int ncol, int nrows, int ngpt, int box_rows = 0) {
+  if (box_rows <= 0) box_rows = nrows;
   if (sizeof(Float) != 8) return false;  // single-precision builds (untested tile layout) use the cp.async staging
   EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc || !base || nrows > 256 || ((size_t)ncol * sizeof(Float)) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) % 16) != 0)
+  if (!enc || !base || box_rows > 256 || ((size_t)ncol * sizeof(Float)) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) % 16) != 0)
     return false;
   const cuuint64_t dims[3] = {(cuuint64_t)ncol, (cuuint64_t)nrows, (cuuint64_t)ngpt};
   const cuuint64_t strides[2] = {(cuuint64_t)ncol * sizeof(Float), (cuuint64_t)ncol * nrows * sizeof(Float)};
-  const cuuint32_t box[3] = {(cuuint32_t)kTmaCols, (cuuint32_t)nrows, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)kTmaCols, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = enc(tm, sizeof(Float) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                          const_cast<Float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

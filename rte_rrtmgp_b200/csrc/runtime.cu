@@ -98,15 +98,18 @@ void rrtmgpb_mem_free(void* p) {
   table_cache_release_abi(p);
   dev_free(p);
 }
+// (cudaMemcpyDefault: the direction follows from the pointers - a host program that hands HOST arrays to the frontend
+// mirror, as a stock Fortran host does with the extern kernels, reaches these with either kind of pointer)
 void rrtmgpb_mem_to_backend(void* d, const void* s, size_t n) {
-  RB_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream()));
+  RB_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDefault, stream()));
 }
 void rrtmgpb_mem_to_host(void* d, const void* s, size_t n) {
-  RB_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream()));
+  RB_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDefault, stream()));
   RB_CUDA_CHECK(cudaStreamSynchronize(stream()));
 }
 void rrtmgpb_mem_copy(void* d, const void* s, size_t n) {
-  RB_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, stream()));
+  RB_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDefault, stream()));
+  if (!is_device_ptr(d) || !is_device_ptr(s)) RB_CUDA_CHECK(cudaStreamSynchronize(stream()));  // pageable host memory involved
 }
 /* the CALLING THREAD's launch stream (every host thread has its own; default cudaStreamPerThread) */
 void rrtmgpb_set_stream(void* s) { tl_stream = static_cast<cudaStream_t>(s); }
