@@ -331,7 +331,7 @@ def make_config(b, name, ncol=None):
         sky = AllSky(ctx, n, 60, syn.make_kdist("lw"), syn.make_kdist("sw"), profiles=prof, do_clouds=False, col_offset=b.rank * n)
         return sky.step, n, {"ncol_per_gpu": n, "nlay": 60, "resident": True}, sky
     if name == "c4":
-        n, chunk = ncol or 524288, 65536
+        n, chunk = ncol or 524288, 37888   # 8 solver waves per chunk
         h = HostAllSky(b.lib, n, NLAY, syn.make_kdist("lw", ngpt=128), syn.make_kdist("sw", ngpt=112), chunk, device=b.device)
         return h.step, n, {"ncol_per_gpu": n, "nlay": NLAY, "chunk_columns": chunk, "resident": False,
                            "h2d_bytes_per_step": h.h2d_bytes, "d2h_bytes_per_step": h.d2h_bytes,
@@ -577,7 +577,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"], help="BASELINE.json configuration timed as the headline (default c2)")
     ap.add_argument("--ncol", type=int, default=NCOL_PER_GPU, help="columns per GPU (default: the BASELINE config)")
-    ap.add_argument("--e2e-chunk", type=int, default=16384, help="column chunk of the host-buffer (e2e) path")
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="nominal column chunk of the host-buffer (e2e) path; 0: the library's default (4 solver waves = 18,944 columns on a B200)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-seq", action="store_true", help="skip the kernel-by-kernel (reference call sequence) leg")
     ap.add_argument("--no-extras", action="store_true", help="skip express / host-pointer / other-config legs")

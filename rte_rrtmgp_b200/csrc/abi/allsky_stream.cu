@@ -72,7 +72,27 @@ extern "C" int rrtmgpb_allsky_stream_host(const rrtmgpb_gas_optics_t* go_lw, con
   if (go_lw) rrtmgpb_gas_optics_dims(go_lw, &g1, &nbnd_lw, &ngpt_lw);
   if (go_sw) rrtmgpb_gas_optics_dims(go_sw, &g2, &nbnd_sw, &ngpt_sw);
   if (g1 != ngas || g2 != ngas) return fail("allsky_stream_host: ngas differs from the k-distributions'");
-  const int nc = std::max(1, std::min(chunk_cols > 0 ? chunk_cols : ncol, ncol));
+  // Chunk schedule: a SMALL first chunk (a quarter of the nominal width) so that compute starts as soon as possible -
+  // its upload is the only one that is not hidden behind compute - then full chunks, and whatever is left at the end
+  // (the last chunk's download is the only exposed one).  Nominal width: chunk_cols, or by default four waves of the
+  // register solvers' 16-column CTAs (2 resident per SM), so that no chunk ends on a nearly empty wave.
+  int sms = 148;
+  {
+    int dev = 0;
+    RB_CUDA_CHECK(cudaGetDevice(&dev));
+    RB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int wave = 2 * sms * 16;
+  const int nc = std::max(1, std::min(chunk_cols > 0 ? chunk_cols : 4 * wave, ncol));
+  std::vector<int> starts;   // first column of every chunk, plus ncol
+  {
+    int c = 0;
+    const int first = ncol > nc ? std::max(std::min(wave, nc), nc / 4) : nc;
+    starts.push_back(0);
+    c = std::min(first, ncol);
+    while (c < ncol) { starts.push_back(c); c = std::min(c + nc, ncol); }
+    starts.push_back(ncol);
+  }
   const size_t ncl = (size_t)nc * nlay, nclp = (size_t)nc * nlev;
   Streams& S = streams();
   cudaStream_t comp = stream();
@@ -134,9 +154,9 @@ extern "C" int rrtmgpb_allsky_stream_host(const rrtmgpb_gas_optics_t* go_lw, con
     RB_CUDA_CHECK(cudaEventRecord(S.out_free[k], S.down));
   }
 
-  const int nchunk = (ncol + nc - 1) / nc;
+  const int nchunk = (int)starts.size() - 1;
   auto upload = [&](int ic) {
-    const int k = ic & 1, c0 = ic * nc, n = std::min(nc, ncol - c0);
+    const int k = ic & 1, c0 = starts[(size_t)ic], n = starts[(size_t)ic + 1] - c0;
     RB_CUDA_CHECK(cudaStreamWaitEvent(S.up, S.in_free[k], 0));
     upload_cols(I[k].p_lay, in->p_lay, ncol, c0, n, nlay, S.up);
     upload_cols(I[k].t_lay, in->t_lay, ncol, c0, n, nlay, S.up);
@@ -162,7 +182,7 @@ extern "C" int rrtmgpb_allsky_stream_host(const rrtmgpb_gas_optics_t* go_lw, con
   char err[RRTMGPB_ERRLEN];
   upload(0);
   for (int ic = 0; ic < nchunk && msg.empty(); ++ic) {
-    const int k = ic & 1, c0 = ic * nc, n = std::min(nc, ncol - c0);
+    const int k = ic & 1, c0 = starts[(size_t)ic], n = starts[(size_t)ic + 1] - c0;
     if (ic + 1 < nchunk) upload(ic + 1);
     RB_CUDA_CHECK(cudaStreamWaitEvent(comp, S.in_ready[k], 0));
     RB_CUDA_CHECK(cudaStreamWaitEvent(comp, S.out_free[k], 0));

@@ -505,7 +505,7 @@ extern "C" {
 
 int rrtmgpb_express_supported(int ncol, int nlay) {
   (void)ncol;
-  return (rrtmgpb_get_solver_variant() == 0 && nlay <= 80) ? 1 : 0;   // register solvers (accumulate mode)
+  return (rrtmgpb_get_solver_variant() == 0 && nlay <= 144) ? 1 : 0;   // register solvers (accumulate mode)
 }
 
 // see include/rrtmgp_b200_ext.h

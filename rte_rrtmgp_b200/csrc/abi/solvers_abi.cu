@@ -36,7 +36,7 @@ constexpr int kSolverThreads = 256;
 // (accel/mo_rte_solver_kernels.F90:958-962), not the sequence-association slip of the serial CPU kernel
 // (mo_rte_solver_kernels.F90:422), which stays reachable with rrtmgpb_set_lw_2stream_lev_source_per_gpt(0)
 static std::atomic<int> g_lw2s_lev_per_gpt{1};
-static std::atomic<int> g_solver_variant{0};  // 0: register/warp-systolic kernels when nlay <= 80, else tiles; 1: always tiles
+static std::atomic<int> g_solver_variant{0};  // 0: register kernels when nlay <= 144, else tiles; 1: always tiles  // 0: register/warp-systolic kernels when nlay <= 80, else tiles; 1: always tiles
 
 struct Orient {
   int nlay;
@@ -563,7 +563,16 @@ inline int reg_chunk_len(int nlay, int ncol) {
   if (nlay <= 64) return 8;
   if (nlay <= 72) return 9;
   if (nlay <= 80) return 10;
+  // 16 lanes per column (8 warps per CTA): 6, 7 or 9 layers per lane
+  if (nlay <= 96) return 6;
+  if (nlay <= 112) return 7;
+  if (nlay <= 144) return 9;
   return 0;
+}
+inline int reg_lanes(int nlay) { return nlay <= 80 ? 8 : 16; }
+inline bool sw_cl8() {  // RRTMGPB_SW_CL8=1: 8 layers per lane for nlay <= 64 in the SW kernel (A/B switch; default 9, see below)
+  static const bool v = [] { const char* e = std::getenv("RRTMGPB_SW_CL8"); return e && e[0] == '1'; }();
+  return v;
 }
 inline int reg_minb() {  // experiment switch: resident CTAs per SM the register kernels are compiled for
   static const int v = [] { const char* e = std::getenv("RRTMGPB_REG_MINB"); return (e && e[0] == '3') ? 3 : 2; }();
@@ -659,7 +668,8 @@ void rte_lw_solver_noscat(const int* ncol_, const int* nlay_, const int* ngpt_, 
     LwTmaMaps maps;
     // layers per lane (see the switch below) and the tile height: 8*CL rows when nlay is not a multiple of 8 - the rows
     // beyond the plane arrive zero-filled and act as pass-through layers, so every TMA launch runs the FULL instantiation
-    const int clv = cl <= 9 ? 9 : 10, rows = 8 * clv;
+    const int nch = reg_lanes(nlay);
+    const int clv = nch == 16 ? cl : (cl <= 9 ? 9 : 10), rows = nch * clv;
     q.tile_rows = rows; q.row0 = p.top_at_1 ? 0 : nlay - rows;
     const bool use_tma = solver_tma_enabled() && make_plane_tmap(&maps.tau, q.tau, ncol, nlay, ngpt, rows) &&
                          make_plane_tmap(&maps.lay, q.lay_source, ncol, nlay, ngpt, rows) &&
@@ -693,11 +703,39 @@ void rte_lw_solver_noscat(const int* ncol_, const int* nlay_, const int* ngpt_, 
       // too (rows 9 apart: conflict free; the extra cells are pass-through padding).  The chunk length fixes the
       // association of the chunk-level scan, so it must not depend on whether TMA is usable (odd ncol):
       // results are bit-identical under column subsetting (tests/test_rte_lw_solver_unit.py).
+#define LWREG16_2(CLV, BBV, JACV)                                                                            \
+  {                                                                                                         \
+    if (use_tma) {                                                                                          \
+      const size_t smem = lw_noscat_reg_tma_smem(rows, reg_threads(16));                                    \
+      auto kern = lw_noscat_reg_kernel<CLV, BBV, JACV, 1, true, 2, false, 16>;                              \
+      RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+      kern<<<grid, reg_threads(16), smem, stream()>>>(q, maps);                                             \
+    } else {                                                                                                \
+      const size_t smem = (size_t)2 * lw_noscat_reg_slots<CLV>() * reg_threads(16) * sizeof(Float);         \
+      auto kern = lw_noscat_reg_kernel<CLV, BBV, JACV, 1, false, 0, false, 16>;                             \
+      RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+      kern<<<grid, reg_threads(16), smem, stream()>>>(q, maps);                                             \
+    }                                                                                                       \
+  }
+#define LWREG16(CLV)                                    \
+  if (bb && jac) LWREG16_2(CLV, true, true)             \
+  else if (bb) LWREG16_2(CLV, true, false)              \
+  else if (jac) LWREG16_2(CLV, false, true)             \
+  else LWREG16_2(CLV, false, false)
+      if (nch == 16) {   // 80 < nlay <= 144: 16 lanes per column
+        switch (cl) {
+          case 6: LWREG16(6); break;
+          case 7: LWREG16(7); break;
+          default: LWREG16(9); break;
+        }
+      } else
       switch (cl) {
         case 8:
         case 9: LWREG(9); break;
         default: LWREG(10); break;
       }
+#undef LWREG16
+#undef LWREG16_2
 #undef LWREG
 #undef LWREG2
       RB_LAUNCH_CHECK();
@@ -738,7 +776,8 @@ void rte_lw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
     q.gpt_per_block = ceil_div(ngpt, reg_gpt_groups(ncol, ngpt));
     dim3 grid(ceil_div(ncol, (kRegThreads / 32) * kRegCols), ceil_div(ngpt, q.gpt_per_block));
     Lw2sTmaMaps maps;
-    const int clv = cl <= 9 ? 9 : 10, rows = 8 * clv;   // zero-filled padded tiles, see rte_lw_solver_noscat
+    const int nch = reg_lanes(nlay);
+    const int clv = nch == 16 ? cl : (cl <= 9 ? 9 : 10), rows = nch * clv;   // zero-filled padded tiles, see rte_lw_solver_noscat
     q.tile_rows = rows; q.row0 = p.top_at_1 ? 0 : nlay - rows;
     const bool use_tma = solver_tma_enabled() && make_plane_tmap(&maps.tau, q.tau, ncol, nlay, ngpt, rows) &&
                          make_plane_tmap(&maps.ssa, q.ssa, ncol, nlay, ngpt, rows) && make_plane_tmap(&maps.g, q.g, ncol, nlay, ngpt, rows) &&
@@ -757,11 +796,28 @@ void rte_lw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
   }
       // the chunk length fixes the association of the chunk-level scan: it must not depend on use_tma (see
       // rte_lw_solver_noscat); CL = 8 conflicts on the TMA tiles, so nlay <= 64 runs CL = 9 as well
+#define LW2S16(CLV)                                                                                        \
+  if (use_tma) {                                                                                           \
+    const size_t smem = lw_2stream_reg_tma_smem(rows);                                                     \
+    auto kern = lw_2stream_reg_kernel<CLV, true, 2, 16>;                                                   \
+    RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    kern<<<grid, reg_threads(16), smem, stream()>>>(q, maps);                                              \
+  } else {                                                                                                 \
+    lw_2stream_reg_kernel<CLV, false, 0, 16><<<grid, reg_threads(16), 0, stream()>>>(q, maps);             \
+  }
+      if (nch == 16) {
+        switch (cl) {
+          case 6: LW2S16(6); break;
+          case 7: LW2S16(7); break;
+          default: LW2S16(9); break;
+        }
+      } else
       switch (cl) {
         case 8:
         case 9: LW2S(9); break;
         default: LW2S(10); break;
       }
+#undef LW2S16
 #undef LW2S
       RB_LAUNCH_CHECK();
     }
@@ -821,7 +877,12 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
     dim3 grid(ceil_div(ncol, (kRegThreads / 32) * kRegCols), ceil_div(ngpt, q.gpt_per_block));
     // TMA tile staging of tau / ssa / g (kernels/tma.cuh) whenever the planes can be described
     SwTmaMaps maps;
-    const int rows = 8 * cl;   // zero-filled padded tiles, see rte_lw_solver_noscat
+    const int nch = reg_lanes(nlay);
+    // nlay <= 64 runs 9 layers per lane as well (like the LW kernels): with CL = 8 the eight lanes of a column read tile
+    // rows 8 apart - one swizzle phase, 8-way bank conflicts - and since the padding rows of the zero-filled tiles cost
+    // no clamped addressing any more, 72 slots at full speed beat 64 conflicting ones (B200, 65,536 x 60: see DESIGN.md)
+    const int cl_sw = (nch == 8 && cl == 8 && !sw_cl8()) ? 9 : cl;
+    const int rows = nch * cl_sw;   // zero-filled padded tiles, see rte_lw_solver_noscat
     q.tile_rows = rows; q.row0 = p.top_at_1 ? 0 : nlay - rows;
     const bool use_tma = solver_tma_enabled() && make_plane_tmap(&maps.tau, q.tau, ncol, nlay, ngpt, rows) &&
                          make_plane_tmap(&maps.ssa, q.ssa, ncol, nlay, ngpt, rows) && make_plane_tmap(&maps.g, q.g, ncol, nlay, ngpt, rows);
@@ -850,11 +911,36 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
   if (bb) SWREG2(CLV, true) else SWREG2(CLV, false)
       // (CL = 8 conflicts on the TMA tiles as in rte_lw_solver_noscat, but this kernel is fp64-bound: the padding of
       // CL = 9 costs more than the conflicts - measured 39.2 vs 37.7 ms at 131,072 x 60)
-      switch (cl) {
+#define SWREG16_2(CLV, BBV)                                                                                 \
+  {                                                                                                         \
+    if (use_tma) {                                                                                          \
+      const size_t smem = sw_reg_tma_smem<CLV, false>(rows, reg_threads(16));                               \
+      auto kern = sw_2stream_reg_kernel<CLV, BBV, 1, false, true, 2, 16>;                                   \
+      RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+      kern<<<grid, reg_threads(16), smem, stream()>>>(q, maps);                                             \
+    } else {                                                                                                \
+      const size_t smem = (size_t)sw_reg_smem_slots<CLV, false>() * reg_threads(16) * sizeof(Float);        \
+      auto kern = sw_2stream_reg_kernel<CLV, BBV, 1, false, false, 0, 16>;                                  \
+      RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+      kern<<<grid, reg_threads(16), smem, stream()>>>(q, maps);                                             \
+    }                                                                                                       \
+  }
+#define SWREG16(CLV) \
+  if (bb) SWREG16_2(CLV, true) else SWREG16_2(CLV, false)
+      if (nch == 16) {
+        switch (cl) {
+          case 6: SWREG16(6); break;
+          case 7: SWREG16(7); break;
+          default: SWREG16(9); break;
+        }
+      } else
+      switch (cl_sw) {
         case 8: SWREG(8); break;
         case 9: SWREG(9); break;
         default: SWREG(10); break;
       }
+#undef SWREG16
+#undef SWREG16_2
 #undef SWREG
 #undef SWREG2
       RB_LAUNCH_CHECK();

@@ -34,7 +34,12 @@
 
 namespace rrtmgpb {
 
-constexpr int kRegThreads = 128;  // 4 warps = 16 columns per CTA
+// A CTA always owns 16 consecutive columns (= one TMA tile row of 128 bytes).  NCH lanes share a column (template
+// parameter of every kernel below): 8 lanes x CL <= 10 layers for nlay <= 80 (4 warps per CTA), 16 lanes x CL <= 9
+// layers for 80 < nlay <= 144 (8 warps per CTA) - the chunk-level scans simply take one more step.
+constexpr int kRegColsPerCta = 16;
+__host__ __device__ constexpr int reg_threads(int nch) { return kRegColsPerCta * nch; }
+constexpr int kRegThreads = reg_threads(8);  // the 8-lane family (host-side defaults)
 constexpr int kRegChunks = 8;
 constexpr int kRegCols = 4;
 
@@ -96,13 +101,14 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #ifndef RB_SW_MERGED_DIV
 #define RB_SW_MERGED_DIV 1
 #endif
+template <int NCH>
 __device__ __forceinline__ Float affine_handoff_down(int j, Float A, Float B, Float x_top, Float& out) {
 #if RB_HANDOFF_SCAN
   Float PA = A, PB = B;  // composed map of chunks (j-d+1 .. j): x -> PA*x + PB
 #pragma unroll
-  for (int d = 1; d < kRegChunks; d <<= 1) {
-    Float qa = __shfl_up_sync(0xffffffffu, PA, d, kRegChunks);
-    Float qb = __shfl_up_sync(0xffffffffu, PB, d, kRegChunks);
+  for (int d = 1; d < NCH; d <<= 1) {
+    Float qa = __shfl_up_sync(0xffffffffu, PA, d, NCH);
+    Float qb = __shfl_up_sync(0xffffffffu, PB, d, NCH);
 #if RB_SCAN_SELECT
     qa = (j >= d) ? qa : (Float)1; qb = (j >= d) ? qb : (Float)0;
     PB = PA * qb + PB; PA = PA * qa;
@@ -111,12 +117,12 @@ __device__ __forceinline__ Float affine_handoff_down(int j, Float A, Float B, Fl
 #endif
   }
   out = PA * x_top + PB;
-  const Float got = __shfl_up_sync(0xffffffffu, out, 1, kRegChunks);
+  const Float got = __shfl_up_sync(0xffffffffu, out, 1, NCH);
   return j == 0 ? x_top : got;
 #else
   Float xin = x_top;
   out = 0;
-  for (int jj = 0; jj < kRegChunks; ++jj) {
+  for (int jj = 0; jj < NCH; ++jj) {
     const Float got = __shfl_up_sync(0xffffffffu, out, 1);
     if (j == jj) {
       if (jj > 0) xin = got;
@@ -127,12 +133,13 @@ __device__ __forceinline__ Float affine_handoff_down(int j, Float A, Float B, Fl
 #endif
 }
 // direct beam: B == 0, the scan carries the products only
+template <int NCH>
 __device__ __forceinline__ Float product_handoff_down(int j, Float A, Float x_top, Float& out) {
 #if RB_HANDOFF_SCAN
   Float PA = A;
 #pragma unroll
-  for (int d = 1; d < kRegChunks; d <<= 1) {
-    Float qa = __shfl_up_sync(0xffffffffu, PA, d, kRegChunks);
+  for (int d = 1; d < NCH; d <<= 1) {
+    Float qa = __shfl_up_sync(0xffffffffu, PA, d, NCH);
 #if RB_SCAN_SELECT
     qa = (j >= d) ? qa : (Float)1;
     PA = PA * qa;
@@ -141,38 +148,39 @@ __device__ __forceinline__ Float product_handoff_down(int j, Float A, Float x_to
 #endif
   }
   out = PA * x_top;
-  const Float got = __shfl_up_sync(0xffffffffu, out, 1, kRegChunks);
+  const Float got = __shfl_up_sync(0xffffffffu, out, 1, NCH);
   return j == 0 ? x_top : got;
 #else
-  return affine_handoff_down(j, A, (Float)0, x_top, out);
+  return affine_handoff_down<NCH>(j, A, (Float)0, x_top, out);
 #endif
 }
 // chunks chained bottom -> top (j = 7 first); x_bottom needs to be valid on the lane of the last chunk only
+template <int NCH>
 __device__ __forceinline__ Float affine_handoff_up(int j, Float A, Float B, Float x_bottom, Float& out) {
 #if RB_HANDOFF_SCAN
-  const Float xb = __shfl_sync(0xffffffffu, x_bottom, kRegChunks - 1, kRegChunks);
+  const Float xb = __shfl_sync(0xffffffffu, x_bottom, NCH - 1, NCH);
   Float PA = A, PB = B;  // composed map of chunks (j+d-1 .. j), applied bottom first
 #pragma unroll
-  for (int d = 1; d < kRegChunks; d <<= 1) {
-    Float qa = __shfl_down_sync(0xffffffffu, PA, d, kRegChunks);
-    Float qb = __shfl_down_sync(0xffffffffu, PB, d, kRegChunks);
+  for (int d = 1; d < NCH; d <<= 1) {
+    Float qa = __shfl_down_sync(0xffffffffu, PA, d, NCH);
+    Float qb = __shfl_down_sync(0xffffffffu, PB, d, NCH);
 #if RB_SCAN_SELECT
-    qa = (j + d < kRegChunks) ? qa : (Float)1; qb = (j + d < kRegChunks) ? qb : (Float)0;
+    qa = (j + d < NCH) ? qa : (Float)1; qb = (j + d < NCH) ? qb : (Float)0;
     PB = PA * qb + PB; PA = PA * qa;
 #else
-    if (j + d < kRegChunks) { PB = PA * qb + PB; PA = PA * qa; }
+    if (j + d < NCH) { PB = PA * qb + PB; PA = PA * qa; }
 #endif
   }
   out = PA * xb + PB;
-  const Float got = __shfl_down_sync(0xffffffffu, out, 1, kRegChunks);
-  return j == kRegChunks - 1 ? xb : got;
+  const Float got = __shfl_down_sync(0xffffffffu, out, 1, NCH);
+  return j == NCH - 1 ? xb : got;
 #else
   Float xin = x_bottom;
   out = 0;
-  for (int jj = kRegChunks - 1; jj >= 0; --jj) {
+  for (int jj = NCH - 1; jj >= 0; --jj) {
     const Float got = __shfl_down_sync(0xffffffffu, out, 1);
     if (j == jj) {
-      if (jj < kRegChunks - 1) xin = got;
+      if (jj < NCH - 1) xin = got;
       out = A * xin + B;
     }
   }
@@ -211,18 +219,19 @@ __host__ __device__ constexpr int lw_noscat_reg_slots() { return 3 * CL + 1 + 5;
 // TMA variant (see the SW kernel and kernels/tma.cuh): tau, lay_source (nlay rows) and lev_source (nlay+1 rows) tiles
 // by cp.async.bulk.tensor, two stages; the five per-(column, g-point) values keep their lane-private cp.async slots.
 struct LwTmaMaps { CUtensorMap tau, lay, lev; };
-__host__ __device__ inline size_t lw_noscat_reg_tma_smem(int nlay) {
-  return 2 * (2 * tile_bytes(nlay) + tile_bytes(nlay + 1)) + (size_t)(2 * 5) * kRegThreads * sizeof(Float) + 2 * sizeof(uint64_t);
+__host__ __device__ inline size_t lw_noscat_reg_tma_smem(int nlay, int nthreads = kRegThreads) {
+  return 2 * (2 * tile_bytes(nlay) + tile_bytes(nlay + 1)) + (size_t)(2 * 5) * nthreads * sizeof(Float) + 2 * sizeof(uint64_t);
 }
 
 // FULL = 1: nlay == 8*CL, every lane's cells are real layers - the padding selects and tests fold away at compile time;
 // FULL = 2: zero-filled padded tiles (LwNoscatRegParams::tile_rows); 0: clamped addressing (cp.async fallback).
 // ONEMU: a single quadrature angle (the default of rte_lw): the loop over angles folds away.
-template <int CL, bool BB, bool JAC, int MINB = 3, bool TMA = false, int FULL = 0, bool ONEMU = false>
-__global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const LwNoscatRegParams p,
+template <int CL, bool BB, bool JAC, int MINB = 3, bool TMA = false, int FULL = 0, bool ONEMU = false, int NCH = 8>
+__global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? MINB : 1) lw_noscat_reg_kernel(const LwNoscatRegParams p,
                                                                            const __grid_constant__ LwTmaMaps tm) {
   // no static shared memory: the swizzled TMA tiles need the dynamic window to start 1024-byte aligned
   extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int kRegChunks = NCH, kRegCols = 32 / NCH, kRegThreads = reg_threads(NCH);  // lanes per column, columns per warp, threads per CTA
   constexpr bool FULLG = FULL == 1;   // no level beyond nlay exists: padding selects and store guards fold away
   const int row0 = (FULL == 2) ? p.row0 : 0, tile_rows = (FULL == 2) ? p.tile_rows : p.nlay;
   const size_t tb_lay = TMA ? tile_bytes(tile_rows) : 0, tb_lev = TMA ? tile_bytes(tile_rows + 1) : 0;
@@ -233,7 +242,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
   constexpr int BC0 = TMA ? -1 : 3 * CL;                          // boundary-value slots are BC0+1 .. BC0+5
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm + (size_t)2 * NS * kRegThreads);  // TMA: [2] mbarriers
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = lane >> 3, j = lane & 7;
+  const int c = lane / kRegChunks, j = lane % kRegChunks;
   const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
   const bool col_ok = col_raw < p.ncol;
   const int col = col_ok ? col_raw : p.ncol - 1;  // out-of-range lanes shadow the last column, never store
@@ -373,7 +382,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
 #pragma unroll
         for (int i = 0; i < CL; ++i) { A = tr[i] * A; B = tr[i] * B + sd[i]; }      // composed map of the chunk
         Float out;
-        I = affine_handoff_down(j, A, B, I_top, out);
+        I = affine_handoff_down<kRegChunks>(j, A, B, I_top, out);
 #pragma unroll
         for (int i = 0; i < CL; ++i) {                                              // replay: the reference's recurrence
           I = tr[i] * I + sd[i];
@@ -390,8 +399,8 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
 #pragma unroll
         for (int i = CL - 1; i >= 0; --i) { A = tr[i] * A; B = tr[i] * B + su[i]; }
         Float out, outj;
-        Iu = affine_handoff_up(j, A, B, Iu, out);
-        if (JAC) Ij = affine_handoff_up(j, A, (Float)0, Ij, outj);
+        Iu = affine_handoff_up<kRegChunks>(j, A, B, Iu, out);
+        if (JAC) Ij = affine_handoff_up<kRegChunks>(j, A, (Float)0, Ij, outj);
 #pragma unroll
         for (int i = CL - 1; i >= 0; --i) {
           // the incoming value sits at the level below layer k0+i: record it, then cross the layer
@@ -445,7 +454,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) lw_noscat_reg_kernel(const 
 // top(fup, fdn): fluxes at the top level (lane j == 0); lev(i, fup, fdn): at the level below layer k0+i,
 // called with a compile-time-constant i so that callers can index register arrays with it.
 // ---------------------------------------------------------------------------------------------------
-template <int CL, typename Top, typename Lev>
+template <int CL, int NCH, typename Top, typename Lev>
 __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL], Float (&SU)[CL], Float (&SD)[CL],
                                            Float albedo_sfc, Float src_sfc, Float flux_dn_top, Top top, Lev lev) {
   // ---- upward pass (:1166-1186) as a chunk-level scan.  One layer maps the (albedo, source) below it to the
@@ -474,18 +483,18 @@ __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL]
     // prefix scan of the chunk matrices from the bottom (3 steps; see affine_handoff_down): after it lane j holds the
     // product of the matrices of chunks j .. 7, bottom one applied first
 #pragma unroll
-    for (int d = 1; d < kRegChunks; d <<= 1) {
-      Float la = __shfl_down_sync(0xffffffffu, ma, d, kRegChunks), lb = __shfl_down_sync(0xffffffffu, mb, d, kRegChunks);
-      Float lc = __shfl_down_sync(0xffffffffu, mc, d, kRegChunks), ld = __shfl_down_sync(0xffffffffu, md, d, kRegChunks);
-      Float le = __shfl_down_sync(0xffffffffu, me, d, kRegChunks), lf = __shfl_down_sync(0xffffffffu, mf, d, kRegChunks);
-      Float lg = __shfl_down_sync(0xffffffffu, mg, d, kRegChunks);
+    for (int d = 1; d < NCH; d <<= 1) {
+      Float la = __shfl_down_sync(0xffffffffu, ma, d, NCH), lb = __shfl_down_sync(0xffffffffu, mb, d, NCH);
+      Float lc = __shfl_down_sync(0xffffffffu, mc, d, NCH), ld = __shfl_down_sync(0xffffffffu, md, d, NCH);
+      Float le = __shfl_down_sync(0xffffffffu, me, d, NCH), lf = __shfl_down_sync(0xffffffffu, mf, d, NCH);
+      Float lg = __shfl_down_sync(0xffffffffu, mg, d, NCH);
 #if RB_SCAN_SELECT
-      const bool on = j + d < kRegChunks;  // lanes without a partner combine with the identity matrix
+      const bool on = j + d < NCH;  // lanes without a partner combine with the identity matrix
       la = on ? la : (Float)1; lb = on ? lb : (Float)0; lc = on ? lc : (Float)0; ld = on ? ld : (Float)1;
       le = on ? le : (Float)0; lf = on ? lf : (Float)0; lg = on ? lg : (Float)1;
       {
 #else
-      if (j + d < kRegChunks) {  // (this lane's chunks) after (the d chunk groups below them)
+      if (j + d < NCH) {  // (this lane's chunks) after (the d chunk groups below them)
 #endif
         const Float na = ma * la + mb * lf, nb = ma * lb + mb * lg;
         const Float nc = mc * la + md * lc + me * lf, ne = mc * lb + md * le + me * lg;
@@ -494,14 +503,14 @@ __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL]
       }
     }
     // the surface state lives on the lane of the last chunk (src_sfc comes from its direct beam)
-    const Float a_s = __shfl_sync(0xffffffffu, albedo_sfc, kRegChunks - 1, kRegChunks);
-    const Float s_s = __shfl_sync(0xffffffffu, src_sfc, kRegChunks - 1, kRegChunks);
+    const Float a_s = __shfl_sync(0xffffffffu, albedo_sfc, NCH - 1, NCH);
+    const Float s_s = __shfl_sync(0xffffffffu, src_sfc, NCH - 1, NCH);
     // state leaving this lane's chunk upwards, homogeneous; the lane above takes it over
     const Float ha = ma * a_s + mb, hs = mc * a_s + md * s_s + me, hd = mf * a_s + mg;
-    const Float ia = __shfl_down_sync(0xffffffffu, ha, 1, kRegChunks);
-    const Float is = __shfl_down_sync(0xffffffffu, hs, 1, kRegChunks);
-    const Float id = __shfl_down_sync(0xffffffffu, hd, 1, kRegChunks);
-    if (j < kRegChunks - 1) {
+    const Float ia = __shfl_down_sync(0xffffffffu, ha, 1, NCH);
+    const Float is = __shfl_down_sync(0xffffffffu, hs, 1, NCH);
+    const Float id = __shfl_down_sync(0xffffffffu, hd, 1, NCH);
+    if (j < NCH - 1) {
       const Float inv = rb_rcp(id);
       alb = ia * inv;
       src = is * inv;
@@ -514,12 +523,12 @@ __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL]
   {
     Float ha = 0, hs = 0, hd = 0;
     Float ia = albedo_sfc, is = src_sfc, id = 1;  // incoming state of this lane, homogeneous
-    for (int jj = kRegChunks - 1; jj >= 0; --jj) {
+    for (int jj = NCH - 1; jj >= 0; --jj) {
       const Float a_b = __shfl_down_sync(0xffffffffu, ha, 1);
       const Float s_b = __shfl_down_sync(0xffffffffu, hs, 1);
       const Float d_b = __shfl_down_sync(0xffffffffu, hd, 1);
       if (j == jj) {
-        if (jj < kRegChunks - 1) { ia = a_b; is = s_b; id = d_b; }
+        if (jj < NCH - 1) { ia = a_b; is = s_b; id = d_b; }
         ha = ma * ia + mb * id;
         hs = mc * ia + md * is + me * id;
         hd = mf * ia + mg * id;
@@ -591,7 +600,7 @@ __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL]
 #pragma unroll
   for (int i = 0; i < CL; ++i) { A = T[i] * A; B = T[i] * B + SD[i]; }
   Float out;
-  Float fdn = affine_handoff_down(j, A, B, flux_dn_top, out);
+  Float fdn = affine_handoff_down<NCH>(j, A, B, flux_dn_top, out);
 #pragma unroll
   for (int i = 0; i < CL; ++i) {
     fdn = T[i] * fdn + SD[i];
@@ -629,17 +638,18 @@ __host__ __device__ constexpr int sw_reg_smem_slots() { return (LEAN ? 1 : 2) * 
 // two stages; the four per-(column, g-point) boundary values keep their lane-private cp.async slots.
 struct SwTmaMaps { CUtensorMap tau, ssa, g; };
 template <int CL, bool LEAN>
-__host__ __device__ inline size_t sw_reg_tma_smem(int nlay) {
-  return 2 * 3 * tile_bytes(nlay) + (size_t)(2 * 4 + CL + (LEAN ? 3 * CL : 0)) * kRegThreads * sizeof(Float) + 2 * sizeof(uint64_t);
+__host__ __device__ inline size_t sw_reg_tma_smem(int nlay, int nthreads = kRegThreads) {
+  return 2 * 3 * tile_bytes(nlay) + (size_t)(2 * 4 + CL + (LEAN ? 3 * CL : 0)) * nthreads * sizeof(Float) + 2 * sizeof(uint64_t);
 }
 
 // FULL: nlay == 8*CL, every lane's cells are real layers - the padding selects and tests fold away at compile time.
-template <int CL, bool BB, int MINB = 3, bool LEAN = false, bool TMA = false, int FULL = 0>
-__global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const SwRegParams p,
+template <int CL, bool BB, int MINB = 3, bool LEAN = false, bool TMA = false, int FULL = 0, int NCH = 8>
+__global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? MINB : 1) sw_2stream_reg_kernel(const SwRegParams p,
                                                                             const __grid_constant__ SwTmaMaps tm) {
   static_assert(!LEAN || BB, "LEAN is a broadband-only variant");
   // no static shared memory in this kernel: the swizzled TMA tiles need the dynamic window to start 1024-byte aligned
   extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int kRegChunks = NCH, kRegCols = 32 / NCH, kRegThreads = reg_threads(NCH);  // lanes per column, columns per warp, threads per CTA
   constexpr bool FULLG = FULL == 1;                             // see LwNoscatRegParams::tile_rows
   const int row0 = (FULL == 2) ? p.row0 : 0, tile_rows = (FULL == 2) ? p.tile_rows : p.nlay;
   const size_t tileb = TMA ? tile_bytes(tile_rows) : 0;        // bytes of one tile
@@ -653,7 +663,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
   Float* sm_acc = sm_mu0 + (size_t)CL * kRegThreads + threadIdx.x;  // LEAN: [3][CL][thread]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm_mu0 + (size_t)(CL + (LEAN ? 3 * CL : 0)) * kRegThreads);  // TMA: [2] mbarriers
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = lane >> 3, j = lane & 7;
+  const int c = lane / kRegChunks, j = lane % kRegChunks;
   const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
   const bool col_ok = col_raw < p.ncol;
   const int col = col_ok ? col_raw : p.ncol - 1;
@@ -840,7 +850,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
 #pragma unroll
       for (int i = 0; i < CL; ++i) P = A5[i] * P;
       Float out;
-      dir = product_handoff_down(j, P, dir_top_g, out);
+      dir = product_handoff_down<kRegChunks>(j, P, dir_top_g, out);
 #pragma unroll
       for (int i = 0; i < CL; ++i) {
         const Float s_up = A3[i] * dir, s_dn = A4[i] * dir;
@@ -871,7 +881,7 @@ __global__ void __launch_bounds__(kRegThreads, MINB) sw_2stream_reg_kernel(const
         gdn[q] = fdn + A5[i];                                                 // :606
       }
     };
-    adding_reg<CL>(j, R, T, A3, A4, alb_dif, src_sfc, dn_top, top, lev);
+    adding_reg<CL, kRegChunks>(j, R, T, A3, A4, alb_dif, src_sfc, dn_top, top, lev);
   }
   if (BB && col_ok) {
     const size_t goff = p.group_stride * blockIdx.y;  // 0 unless the express path splits a launch's g-points
@@ -914,11 +924,12 @@ __host__ __device__ inline size_t lw_2stream_reg_tma_smem(int nlay) {
   return 2 * (4 * tile_bytes(nlay) + tile_bytes(nlay + 1)) + 2 * sizeof(uint64_t);
 }
 
-template <int CL, bool TMA = false, int FULL = 0>
-__global__ void __launch_bounds__(kRegThreads, TMA ? 2 : 3) lw_2stream_reg_kernel(const Lw2sRegParams p,
+template <int CL, bool TMA = false, int FULL = 0, int NCH = 8>
+__global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? (TMA ? 2 : 3) : 1) lw_2stream_reg_kernel(const Lw2sRegParams p,
                                                                                   const __grid_constant__ Lw2sTmaMaps tm) {
   // no static shared memory: the swizzled TMA tiles need the dynamic window to start 1024-byte aligned
   extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int kRegChunks = NCH, kRegCols = 32 / NCH, kRegThreads = reg_threads(NCH);  // lanes per column, columns per warp, threads per CTA
   constexpr bool FULLG = FULL == 1;    // see LwNoscatRegParams::tile_rows
   const int row0 = (FULL == 2) ? p.row0 : 0, tile_rows = (FULL == 2) ? p.tile_rows : p.nlay;
   const size_t tb_lay = TMA ? tile_bytes(tile_rows) : 0, tb_lev = TMA ? tile_bytes(tile_rows + 1) : 0;
@@ -926,7 +937,7 @@ __global__ void __launch_bounds__(kRegThreads, TMA ? 2 : 3) lw_2stream_reg_kerne
   const int te_lay = (int)(tb_lay / sizeof(Float));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * stageb);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = lane >> 3, j = lane & 7;
+  const int c = lane / kRegChunks, j = lane % kRegChunks;
   const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
   const bool col_ok = col_raw < p.ncol;
   const size_t col = col_ok ? col_raw : p.ncol - 1;
@@ -1030,7 +1041,7 @@ __global__ void __launch_bounds__(kRegThreads, TMA ? 2 : 3) lw_2stream_reg_kerne
       gup[q] = fup;
       gdn[q] = fdn;
     };
-    adding_reg<CL>(j, R, T, SU, SD, (Float)1 - emis, pi * emis * p.sfc_src[gi], p.inc_flux[gi], top, lev);
+    adding_reg<CL, kRegChunks>(j, R, T, SU, SD, (Float)1 - emis, pi * emis * p.sfc_src[gi], p.inc_flux[gi], top, lev);
   }
 }
 

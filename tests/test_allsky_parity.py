@@ -27,9 +27,10 @@ def _run(lib, device, ncol, nlay, kd_lw, kd_sw, profiles=None, do_clouds=True, f
 @pytest.mark.gpu
 @pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("ncol,nlay", [(24, 72), (37, 60), (130, 72), (21, 78), (19, 96)])
+@pytest.mark.parametrize("ncol,nlay", [(24, 72), (37, 60), (130, 72), (21, 78), (19, 96), (26, 137), (20, 150)])
 def test_allsky_replicated_profile(oracle_lib, cuda_lib, kdists, ncol, nlay, variant, fused):
-    """variant 0: register / warp-systolic solvers (nlay <= 80; 96 layers falls back to tiles); 1: tile solvers."""
+    """variant 0: register / warp-systolic solvers (8 lanes per column up to 80 layers, 16 lanes up to 144; 150 layers falls
+    back to the tile kernels); 1: tile solvers."""
     kd_lw, kd_sw = kdists
     cuda_lib.cdll.rrtmgpb_set_solver_variant(variant)
     g = _run(cuda_lib, "cuda:0", ncol, nlay, kd_lw, kd_sw, fused=fused)

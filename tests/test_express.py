@@ -53,9 +53,9 @@ def test_oracle_express_is_the_reference_sequence(oracle_lib, kdists):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("nc,bands,rows", [(2368, 1, 2), (16, 1, 1), (22, 3, 3), (64, 16, 2)])
-@pytest.mark.parametrize("ncol,nlay", [(24, 72), (37, 60), (130, 72), (21, 78), (19, 96)])
+@pytest.mark.parametrize("ncol,nlay", [(24, 72), (37, 60), (130, 72), (21, 78), (19, 96), (18, 150)])
 def test_express_replicated_profile(oracle_lib, cuda_lib, kdists, ncol, nlay, nc, bands, rows):
-    """(19, 96): beyond the register solvers' layer range - the express entry falls back to one launch per chunk."""
+    """(18, 150): beyond the register solvers' layer range (144) - the express entry falls back to one launch per chunk."""
     kd_lw, kd_sw = kdists
     ref = _run(oracle_lib, None, ncol, nlay, kd_lw, kd_sw, express=False, fused=False)
     with _Env(RRTMGPB_EXPRESS_NC=nc, RRTMGPB_EXPRESS_BANDS=bands, RRTMGPB_EXPRESS_ROWS=rows):

@@ -196,6 +196,50 @@ def test_sw_solver_2stream(oracle_lib, cuda_lib, variant, top_at_1, bb, bc):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("top_at_1", [True, False])
+@pytest.mark.parametrize("ncol,nlay", [(22, 90), (19, 90), (22, 137), (18, 144), (17, 112), (20, 81)])
+def test_register_solvers_on_tall_columns(oracle_lib, cuda_lib, ncol, nlay, top_at_1):
+    """80 < nlay <= 144 (ICON 90 layers, IFS 137): the register solvers run with 16 lanes per column (csrc/kernels/
+    solver_reg.cuh) - every solver, broadband and g-point outputs, Jacobian, even ncol (TMA tiles, zero-filled padding
+    rows) and odd ncol (cp.async fallback)."""
+    assert cuda_lib.cdll.rrtmgpb_get_solver_variant() == 0
+    x = _lw_inputs(ncol, nlay, 4, seed=21, scattering=True)
+    for nmus, bb, jac in ((1, True, False), (2, False, True), (3, True, True)):
+        ref = _run_lw_noscat(oracle_lib, None, x, top_at_1, nmus, bb, jac, False)
+        got = _run_lw_noscat(cuda_lib, "cuda:0", x, top_at_1, nmus, bb, jac, False)
+        for k in ref:
+            _close(got[k], ref[k], f"lw noscat {k} nmus={nmus}")
+    for lib, dev in ((oracle_lib, None), (cuda_lib, "cuda:0")):
+        lib.cdll.rrtmgpb_set_lw_2stream_lev_source_per_gpt(1)
+    try:
+        res = {}
+        for name, lib, device in (("ref", oracle_lib, None), ("gpu", cuda_lib, "cuda:0")):
+            d = lambda a: rc.dev(a, device)
+            gup, gdn = fzeros((ncol, nlay + 1, 4), device=device), fzeros((ncol, nlay + 1, 4), device=device)
+            lib.rte_lw_solver_2stream(ncol, nlay, 4, top_at_1, d(x["tau"]), d(x["ssa"]), d(x["g"]), d(x["lay"]), d(x["lev"]),
+                                      d(x["emis"]), d(x["sfc"]), d(x["inc"]), gup, gdn)
+            lib.sync()
+            res[name] = (rc.host(gup), rc.host(gdn))
+    finally:
+        oracle_lib.cdll.rrtmgpb_set_lw_2stream_lev_source_per_gpt(0)
+    _close(res["gpu"][0], res["ref"][0], "lw 2stream up", rtol=2e-9)
+    _close(res["gpu"][1], res["ref"][1], "lw 2stream dn", rtol=2e-9)
+    y = _sw_inputs(ncol, nlay, 5, seed=22)
+    for bb, bc in ((True, True), (False, False)):
+        out = {}
+        for name, lib, device in (("ref", oracle_lib, None), ("gpu", cuda_lib, "cuda:0")):
+            d = lambda a: rc.dev(a, device)
+            gup, gdn, gdr = (fzeros((ncol, nlay + 1, 5), device=device) for _ in range(3))
+            bup, bdn, bdr = (fzeros((ncol, nlay + 1), device=device) for _ in range(3))
+            lib.rte_sw_solver_2stream(ncol, nlay, 5, top_at_1, d(y["tau"]), d(y["ssa"]), d(y["g"]), d(y["mu0"]), d(y["adir"]),
+                                      d(y["adif"]), d(y["inc"]), gup, gdn, gdr, bc, d(y["dif"]), bb, bup, bdn, bdr)
+            lib.sync()
+            out[name] = [rc.host(o) for o in ((bup, bdn, bdr) if bb else (gup, gdn, gdr))]
+        for a, b, n in zip(out["gpu"], out["ref"], ("up", "dn", "dir")):
+            _close(a, b, f"sw {n} bb={bb}")
+
+
+@pytest.mark.gpu
 def test_sw_solver_noscat_and_reductions(oracle_lib, cuda_lib):
     x = _sw_inputs(17, 29, 5, seed=8)
     x["mu0"] = np.asfortranarray(np.abs(x["mu0"]) + 0.05)
