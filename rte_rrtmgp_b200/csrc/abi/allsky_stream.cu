@@ -10,6 +10,7 @@
 // ordered by events; two device input sets and two device flux sets.  With pinned host memory every copy is
 // asynchronous; with pageable memory CUDA stages them (correct, serialised).
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "../common.cuh"
@@ -155,9 +156,21 @@ extern "C" int rrtmgpb_allsky_stream_host(const rrtmgpb_gas_optics_t* go_lw, con
   }
 
   const int nchunk = (int)starts.size() - 1;
+  // RRTMGPB_STREAM_TRACE=1: per-chunk timeline (upload / compute / download, ms since the call started) on stderr
+  static const bool trace = [] { const char* e = std::getenv("RRTMGPB_STREAM_TRACE"); return e && e[0] == '1'; }();
+  struct Tr { cudaEvent_t u0, u1, c0, c1, d0, d1; };
+  std::vector<Tr> tr;
+  cudaEvent_t t_start = nullptr;
+  if (trace) {
+    tr.resize((size_t)nchunk);
+    for (Tr& t : tr) for (cudaEvent_t* e : {&t.u0, &t.u1, &t.c0, &t.c1, &t.d0, &t.d1}) RB_CUDA_CHECK(cudaEventCreate(e));
+    RB_CUDA_CHECK(cudaEventCreate(&t_start));
+    RB_CUDA_CHECK(cudaEventRecord(t_start, comp));
+  }
   auto upload = [&](int ic) {
     const int k = ic & 1, c0 = starts[(size_t)ic], n = starts[(size_t)ic + 1] - c0;
     RB_CUDA_CHECK(cudaStreamWaitEvent(S.up, S.in_free[k], 0));
+    if (trace) RB_CUDA_CHECK(cudaEventRecord(tr[(size_t)ic].u0, S.up));
     upload_cols(I[k].p_lay, in->p_lay, ncol, c0, n, nlay, S.up);
     upload_cols(I[k].t_lay, in->t_lay, ncol, c0, n, nlay, S.up);
     upload_cols(I[k].p_lev, in->p_lev, ncol, c0, n, nlev, S.up);
@@ -176,6 +189,7 @@ extern "C" int rrtmgpb_allsky_stream_host(const rrtmgpb_gas_optics_t* go_lw, con
     if (go_lw) { up1(I[k].t_sfc, in->t_sfc, 1); up1(I[k].emis, in->emis_sfc, nbnd_lw); }
     if (go_sw) { up1(I[k].mu0, in->mu0, 1); up1(I[k].alb_dir, in->sfc_alb_dir, nbnd_sw); up1(I[k].alb_dif, in->sfc_alb_dif, nbnd_sw); }
     RB_CUDA_CHECK(cudaEventRecord(S.in_ready[k], S.up));
+    if (trace) RB_CUDA_CHECK(cudaEventRecord(tr[(size_t)ic].u1, S.up));
   };
 
   std::string msg;
@@ -187,6 +201,7 @@ extern "C" int rrtmgpb_allsky_stream_host(const rrtmgpb_gas_optics_t* go_lw, con
     RB_CUDA_CHECK(cudaStreamWaitEvent(comp, S.in_ready[k], 0));
     RB_CUDA_CHECK(cudaStreamWaitEvent(comp, S.out_free[k], 0));
     const InSet& X = I[k];
+    if (trace) RB_CUDA_CHECK(cudaEventRecord(tr[(size_t)ic].c0, comp));
     // gas_concs -> vmr(n, nlay, ngas): fields as uploaded, well-mixed gases broadcast (mo_gas_optics_rrtmgp.F90:540-545)
     for (int g = 0; g < ngas; ++g) {
       Float* plane = vmr + (size_t)n * nlay * g;
@@ -220,17 +235,32 @@ extern "C" int rrtmgpb_allsky_stream_host(const rrtmgpb_gas_optics_t* go_lw, con
     }
     RB_CUDA_CHECK(cudaEventRecord(S.in_free[k], comp));
     RB_CUDA_CHECK(cudaEventRecord(S.out_ready[k], comp));
+    if (trace) RB_CUDA_CHECK(cudaEventRecord(tr[(size_t)ic].c1, comp));
     // ---- fluxes of this chunk -> host, behind the compute stream
     RB_CUDA_CHECK(cudaStreamWaitEvent(S.down, S.out_ready[k], 0));
+    if (trace) RB_CUDA_CHECK(cudaEventRecord(tr[(size_t)ic].d0, S.down));
     Float* dsts[5] = {out->lw_flux_up, out->lw_flux_dn, out->sw_flux_up, out->sw_flux_dn, out->sw_flux_dir};
     for (int a = 0; a < 5; ++a)
       if (dsts[a] && ((a < 2 && go_lw) || (a >= 2 && go_sw))) download_cols(dsts[a], O[k].f[a], ncol, c0, n, nlev, S.down);
     RB_CUDA_CHECK(cudaEventRecord(S.out_free[k], S.down));
+    if (trace) RB_CUDA_CHECK(cudaEventRecord(tr[(size_t)ic].d1, S.down));
   }
   // the call returns when the last fluxes are on the host; the compute stream is ordered behind both copy streams
   RB_CUDA_CHECK(cudaStreamSynchronize(S.down));
   RB_CUDA_CHECK(cudaStreamSynchronize(S.up));
   RB_CUDA_CHECK(cudaStreamSynchronize(comp));
+  if (trace && msg.empty()) {
+    auto ms = [&](cudaEvent_t e) { float v = 0; RB_CUDA_CHECK(cudaEventElapsedTime(&v, t_start, e)); return v; };
+    for (int ic = 0; ic < nchunk; ++ic) {
+      const Tr& t = tr[(size_t)ic];
+      std::fprintf(stderr, "stream trace: chunk %d cols [%d,%d)  up %.2f-%.2f  compute %.2f-%.2f  down %.2f-%.2f ms\n", ic,
+                   starts[(size_t)ic], starts[(size_t)ic + 1], ms(t.u0), ms(t.u1), ms(t.c0), ms(t.c1), ms(t.d0), ms(t.d1));
+    }
+  }
+  if (trace) {
+    for (Tr& t : tr) for (cudaEvent_t e : {t.u0, t.u1, t.c0, t.c1, t.d0, t.d1}) cudaEventDestroy(e);
+    cudaEventDestroy(t_start);
+  }
   for (void* p : owned) dev_free(p);
   RB_CUDA_CHECK(cudaEventDestroy(start));
   return msg.empty() ? 0 : fail(msg);

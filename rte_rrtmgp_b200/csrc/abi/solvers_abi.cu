@@ -653,6 +653,54 @@ void rte_lw_solver_noscat(const int* ncol_, const int* nlay_, const int* ngpt_, 
   p.sfc_src = a_ss; p.inc_flux = a_inc; p.flux_up = a_fu; p.flux_dn = a_fd; p.do_broadband = bb; p.bb_up = a_bu;
   p.bb_dn = a_bd; p.do_jac = jac; p.sfc_srcJac = a_sj; p.flux_upJac = a_fj; p.do_rescaling = resc; p.ssa = a_ssa;
   p.g = a_g;
+  // ---- Tang rescaling on the register kernels (TMA tiles of the five planes; else the tile kernel below)
+  if (const int cl = resc ? reg_chunk_len(nlay, ncol) : 0) {
+    LwNoscatRegParams q;
+    q.ncol = ncol; q.nlay = nlay; q.ngpt = ngpt; q.top_at_1 = p.top_at_1; q.nmus = nmus; q.Ds = p.Ds;
+    q.weights = p.weights; q.tau = p.tau; q.lay_source = p.lay_source; q.lev_source = p.lev_source;
+    q.sfc_emis = p.sfc_emis; q.sfc_src = p.sfc_src; q.inc_flux = p.inc_flux; q.flux_up = p.flux_up;
+    q.flux_dn = p.flux_dn; q.do_broadband = bb; q.bb_up = p.bb_up; q.bb_dn = p.bb_dn; q.do_jac = jac;
+    q.sfc_srcJac = p.sfc_srcJac; q.flux_upJac = p.flux_upJac; q.accumulate = 0; q.group_stride = 0;
+    const int groups = (bb || jac) ? 1 : reg_gpt_groups(ncol, ngpt);
+    q.gpt_per_block = ceil_div(ngpt, groups);
+    dim3 grid(ceil_div(ncol, kRegColsPerCta), ceil_div(ngpt, q.gpt_per_block));
+    const int nch = reg_lanes(nlay);
+    const int clv = nch == 16 ? cl : (cl <= 9 ? 9 : 10), rows = nch * clv;
+    q.tile_rows = rows; q.row0 = p.top_at_1 ? 0 : nlay - rows;
+    LwResclTmaMaps maps;
+    const bool use_tma = solver_tma_enabled() && make_plane_tmap(&maps.tau, q.tau, ncol, nlay, ngpt, rows) &&
+                         make_plane_tmap(&maps.ssa, p.ssa, ncol, nlay, ngpt, rows) && make_plane_tmap(&maps.g, p.g, ncol, nlay, ngpt, rows) &&
+                         make_plane_tmap(&maps.lay, q.lay_source, ncol, nlay, ngpt, rows) &&
+                         make_plane_tmap(&maps.lev, q.lev_source, ncol, nlay + 1, ngpt, rows + 1);
+    if (use_tma) {
+      KernelTimer timer("lw_rescl_reg_kernel");
+      const size_t smem = lw_rescl_reg_tma_smem(rows, reg_threads(nch));
+#define LWRS2(CLV, BBV, JACV, NCHV)                                                                       \
+  {                                                                                                       \
+    auto kern = lw_rescl_reg_kernel<CLV, BBV, JACV, NCHV>;                                                \
+    RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    kern<<<grid, reg_threads(NCHV), smem, stream()>>>(q, maps);                                           \
+  }
+#define LWRS(CLV, NCHV)                          \
+  if (bb && jac) LWRS2(CLV, true, true, NCHV)    \
+  else if (bb) LWRS2(CLV, true, false, NCHV)     \
+  else if (jac) LWRS2(CLV, false, true, NCHV)    \
+  else LWRS2(CLV, false, false, NCHV)
+      if (nch == 16) {
+        switch (clv) {
+          case 6: LWRS(6, 16); break;
+          case 7: LWRS(7, 16); break;
+          default: LWRS(9, 16); break;
+        }
+      } else {
+        if (clv == 9) { LWRS(9, 8); } else { LWRS(10, 8); }
+      }
+#undef LWRS
+#undef LWRS2
+      RB_LAUNCH_CHECK();
+      return;
+    }
+  }
   if (const int cl = resc ? 0 : reg_chunk_len(nlay, ncol)) {
     LwNoscatRegParams q;
     q.ncol = ncol; q.nlay = nlay; q.ngpt = ngpt; q.top_at_1 = p.top_at_1; q.nmus = nmus; q.Ds = p.Ds;

@@ -446,6 +446,220 @@ __global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? MINB : 1) lw_nosc
 }
 
 // ---------------------------------------------------------------------------------------------------
+// LW no-scattering with Tang rescaling (mo_rte_solver_kernels.F90:148-178, 206-210, 753-844): the default LW path for
+// scattering (2-stream) optical properties when use_2stream is false (mo_rte_lw.F90:395-423).  TMA tiles only (five
+// planes: tau, ssa, g, lay_source, lev_source; zero-filled padded tiles as in FULL = 2 above).
+// Three sweeps, each an affine chain solved as a chunk-level scan:
+//   1. plain downward transport                     I_dn1(l+1) = t*I_dn1(l) + S_dn                              (:697-706)
+//   2. upward transport with the adjustment term    I_up(top)  = t*I_up(bot) + S_up + Cn*(An*I_dn1(top) - t*S_dn - S_up)
+//   3. second downward transport                    I_dn(bot)  = t*I_dn(top) + S_dn + Cn*(An*I_up(X)   - t*S_up - S_dn)
+//      with X = the layer's TOP level when top_at_1 but its BOTTOM level otherwise (:801-804 vs :835-838: the reference
+//      is orientation-asymmetric as written; replicated per branch, not symmetrised).
+// The offsets of sweeps 2 and 3 are known once the previous sweep's radiances are known at every level, so the chain
+// stays affine.  Only the upward Jacobian is propagated (:791-792, 824-825).
+// ---------------------------------------------------------------------------------------------------
+struct LwResclTmaMaps { CUtensorMap tau, ssa, g, lay, lev; };
+__host__ __device__ inline size_t lw_rescl_reg_tma_smem(int rows, int nthreads) {
+  return 2 * (4 * tile_bytes(rows) + tile_bytes(rows + 1)) + (size_t)(2 * 5) * nthreads * sizeof(Float) + 2 * sizeof(uint64_t);
+}
+
+template <int CL, bool BB, bool JAC, int NCH = 8>
+__global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? 2 : 1) lw_rescl_reg_kernel(const LwNoscatRegParams p,
+                                                                                         const __grid_constant__ LwResclTmaMaps tm) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int kRegChunks = NCH, kRegCols = 32 / NCH, kRegThreads = reg_threads(NCH);
+  const int row0 = p.row0, tile_rows = p.tile_rows;
+  const size_t tb_lay = tile_bytes(tile_rows), tb_lev = tile_bytes(tile_rows + 1);
+  const size_t stageb = 4 * tb_lay + tb_lev;
+  const int te_lay = (int)(tb_lay / sizeof(Float));
+  Float* sm = reinterpret_cast<Float*>(smem_raw + 2 * stageb);  // lane-private cp.async slots: emis, sfc_src, inc_flux, jac, D
+  constexpr int NS = 5;
+  constexpr int BC0 = -1;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm + (size_t)2 * NS * kRegThreads);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = lane / kRegChunks, j = lane % kRegChunks;
+  const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
+  const bool col_ok = col_raw < p.ncol;
+  const int col = col_ok ? col_raw : p.ncol - 1;
+  const int nlay = p.nlay, nlev = nlay + 1;
+  const size_t ncol = p.ncol, nclp = ncol * nlev;
+  const RegOrient o{nlay, p.top_at_1};
+  const Float pi = reg_pi();
+  const Float tau_thresh = sqrt(sqrt((Float)RB_EPS));  // :636
+  const int k0 = j * CL;
+  const int gb = blockIdx.y * p.gpt_per_block, ge = min(p.ngpt, gb + p.gpt_per_block);
+  const int cta_col0 = blockIdx.x * (kRegThreads / 32) * kRegCols;
+  const int cw = warp * kRegCols + c;
+  auto prefetch = [&](int g, int s) {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&full_bar[s], (uint32_t)((5 * tile_rows + 1) * kTmaCols * sizeof(Float)));
+      unsigned char* dst = smem_raw + (size_t)s * stageb;
+      tma_load_tile(dst, &tm.tau, &full_bar[s], cta_col0, row0, g);
+      tma_load_tile(dst + tb_lay, &tm.ssa, &full_bar[s], cta_col0, row0, g);
+      tma_load_tile(dst + 2 * tb_lay, &tm.g, &full_bar[s], cta_col0, row0, g);
+      tma_load_tile(dst + 3 * tb_lay, &tm.lay, &full_bar[s], cta_col0, row0, g);
+      tma_load_tile(dst + 4 * tb_lay, &tm.lev, &full_bar[s], cta_col0, row0, g);
+    }
+    const size_t gi = (size_t)col + ncol * g;
+    cp_async_f(RB_SLOT(sm, NS, s, BC0 + 1), p.sfc_emis + gi);
+    cp_async_f(RB_SLOT(sm, NS, s, BC0 + 2), p.sfc_src + gi);
+    cp_async_f(RB_SLOT(sm, NS, s, BC0 + 3), p.inc_flux + gi);
+    if (JAC) cp_async_f(RB_SLOT(sm, NS, s, BC0 + 4), p.sfc_srcJac + gi);
+    cp_async_f(RB_SLOT(sm, NS, s, BC0 + 5), p.Ds + gi);
+  };
+  Float acc_up[BB ? CL : 1], acc_dn[BB ? CL : 1], acc_jac[JAC ? CL : 1];
+  Float acc_up_top = 0, acc_dn_top = 0, acc_jac_top = 0;
+#pragma unroll
+  for (int i = 0; i < CL; ++i) {
+    if (BB) { acc_up[BB ? i : 0] = 0; acc_dn[BB ? i : 0] = 0; }
+    if (JAC) acc_jac[JAC ? i : 0] = 0;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (gb < ge) prefetch(gb, 0);
+  cp_async_commit();
+  if (gb + 1 < ge) prefetch(gb + 1, 1);
+  cp_async_commit();
+  for (int g = gb; g < ge; ++g) {
+    const int s = (g - gb) & 1;
+    cp_async_wait<1>();
+    mbar_wait(&full_bar[s], (uint32_t)(((g - gb) >> 1) & 1));
+    const Float* tile_tau = reinterpret_cast<const Float*>(smem_raw + (size_t)s * stageb);
+    const Float* tile_lev = tile_tau + 4 * te_lay;
+    const Float emis = *RB_SLOT(sm, NS, s, BC0 + 1), ssrc = *RB_SLOT(sm, NS, s, BC0 + 2), inc = *RB_SLOT(sm, NS, s, BC0 + 3);
+    const Float sjac = JAC ? *RB_SLOT(sm, NS, s, BC0 + 4) : (Float)0;
+    Float* fup = p.flux_up + nclp * g;
+    Float* fdn = p.flux_dn + nclp * g;
+    for (int imu = 0; imu < p.nmus; ++imu) {
+      const Float w = p.weights[imu];
+      const Float piw = pi * w;
+      const Float D = (imu == 0) ? *RB_SLOT(sm, NS, s, BC0 + 5) : p.Ds[(size_t)col + ncol * ((size_t)g + (size_t)p.ngpt * imu)];
+      // ---------------- phase A ----------------
+      Float tr[CL], sd[CL], su[CL], an[CL], cn[CL];
+      Float Btop = *tile_at(tile_lev, o.lev(k0) - row0, cw);
+#pragma unroll
+      for (int i = 0; i < CL; ++i) {
+        const Float Bbot = *tile_at(tile_lev, o.lev(k0 + i + 1) - row0, cw);
+        const bool live = k0 + i < nlay;
+        const Float* e_lay = tile_at(tile_tau, o.lay(k0 + i) - row0, cw);
+        const Float ssal = e_lay[te_lay], gg = e_lay[2 * te_lay];
+        const Float wb = ssal * ((Float)1 - gg) * (Float)0.5;                      // :161
+        const Float scaleTau = ((Float)1 - ssal + wb);                             // :165
+        const Float cnv = rb_div((Float)0.4 * wb, live ? scaleTau : (Float)1);     // :169
+        const Float tau_loc = e_lay[0] * D * scaleTau;                             // :173
+        const Float t = rb_exp(-tau_loc);                                          // :175
+        const Float fact_big = rb_div((Float)1 - t, fmax(tau_loc, tau_thresh)) - t;
+        const Float fact_small = tau_loc * ((Float)0.5 + tau_loc * (-(Float)1 / (Float)3 + tau_loc * (Float)1 / (Float)8));
+        const Float fact = (tau_loc > tau_thresh) ? fact_big : fact_small;         // :652-656
+        const Float lay = e_lay[3 * te_lay];
+        const Float sdn = ((Float)1 - t) * Bbot + (Float)2 * fact * (lay - Bbot);  // :660-663
+        const Float sup = ((Float)1 - t) * Btop + (Float)2 * fact * (lay - Btop);
+        sd[i] = live ? sdn : (Float)0;
+        su[i] = live ? sup : (Float)0;
+        tr[i] = live ? t : (Float)1;
+        an[i] = live ? ((Float)1 - t * t) : (Float)0;                              // :176
+        cn[i] = live ? cnv : (Float)0;
+        Btop = Bbot;
+      }
+      auto store = [&](Float* gflux, int klev, Float I) {
+        if (klev > nlay || !col_ok) return;
+        Float* q = gflux + (size_t)col + ncol * o.lev(klev);
+        *q = (imu == 0) ? piw * I : *q + piw * I;
+      };
+      // ---------------- sweep 1: plain downward transport; radiance kept at every level of the chunk ----------------
+      const Float I_top = inc / (pi * w);                                           // :144
+      Float dn1[CL + 1];   // dn1[i] = first-pass radiance ABOVE layer k0+i, dn1[CL] below the chunk's last layer
+      {
+        Float A = 1, B = 0;
+#pragma unroll
+        for (int i = 0; i < CL; ++i) { A = tr[i] * A; B = tr[i] * B + sd[i]; }
+        Float out;
+        Float I = affine_handoff_down<kRegChunks>(j, A, B, I_top, out);
+        dn1[0] = I;
+#pragma unroll
+        for (int i = 0; i < CL; ++i) { I = tr[i] * I + sd[i]; dn1[i + 1] = I; }
+      }
+      // surface (:198-202), on the lane of the last chunk
+      Float Iu = dn1[CL] * ((Float)1 - emis) + emis * ssrc;
+      Float Ij = emis * sjac;
+      // ---------------- sweep 2: upward with adjustment (:786-792 / :819-825) ----------------
+      Float up[CL + 1];    // up[i] = radiance ABOVE layer k0+i (after crossing it), up[CL] = entering the chunk from below
+      {
+        Float su2[CL];
+#pragma unroll
+        for (int i = 0; i < CL; ++i) su2[i] = su[i] + cn[i] * (an[i] * dn1[i] - tr[i] * sd[i] - su[i]);
+        Float A = 1, B = 0;
+#pragma unroll
+        for (int i = CL - 1; i >= 0; --i) { A = tr[i] * A; B = tr[i] * B + su2[i]; }
+        Float out, outj;
+        Iu = affine_handoff_up<kRegChunks>(j, A, B, Iu, out);
+        if (JAC) Ij = affine_handoff_up<kRegChunks>(j, A, (Float)0, Ij, outj);
+        up[CL] = Iu;
+#pragma unroll
+        for (int i = CL - 1; i >= 0; --i) {
+          if (BB) acc_up[BB ? i : 0] += w * Iu;
+          else if (k0 + i < nlay) store(fup, k0 + i + 1, Iu);
+          if (JAC) acc_jac[JAC ? i : 0] += w * Ij;
+          Iu = tr[i] * Iu + su2[i];
+          if (JAC) Ij = tr[i] * Ij;
+          up[i] = Iu;
+        }
+      }
+      if (j == 0) {
+        if (BB) acc_up_top += w * Iu; else store(fup, 0, Iu);
+        if (JAC) acc_jac_top += w * Ij;
+      }
+      // ---------------- sweep 3: second downward transport with adjustment (:801-804 / :835-838) ----------------
+      if (j == 0) {
+        if (BB) acc_dn_top += w * I_top; else store(fdn, 0, I_top);
+      }
+      {
+        Float sd2[CL];
+#pragma unroll
+        for (int i = 0; i < CL; ++i) {
+          const Float upx = p.top_at_1 ? up[i] : up[i + 1];   // the layer's top level, or (bottom-up columns) its bottom level
+          sd2[i] = sd[i] + cn[i] * (an[i] * upx - tr[i] * su[i] - sd[i]);
+        }
+        Float A = 1, B = 0;
+#pragma unroll
+        for (int i = 0; i < CL; ++i) { A = tr[i] * A; B = tr[i] * B + sd2[i]; }
+        Float out;
+        Float I = affine_handoff_down<kRegChunks>(j, A, B, I_top, out);
+#pragma unroll
+        for (int i = 0; i < CL; ++i) {
+          I = tr[i] * I + sd2[i];
+          if (BB) acc_dn[BB ? i : 0] += w * I;
+          else store(fdn, k0 + i + 1, I);
+        }
+      }
+    }
+    __syncthreads();
+    if (g + 2 < ge) prefetch(g + 2, s);
+    cp_async_commit();
+  }
+  if (col_ok && (BB || JAC)) {
+#pragma unroll
+    for (int i = 0; i < CL; ++i) {
+      const int klev = k0 + i + 1;
+      if (klev <= nlay) {
+        const size_t o2 = (size_t)col + ncol * o.lev(klev);
+        if (BB) { p.bb_up[o2] = pi * acc_up[BB ? i : 0]; p.bb_dn[o2] = pi * acc_dn[BB ? i : 0]; }
+        if (JAC) p.flux_upJac[o2] = pi * acc_jac[JAC ? i : 0];
+      }
+    }
+    if (j == 0) {
+      const size_t o2 = (size_t)col + ncol * o.lev(0);
+      if (BB) { p.bb_up[o2] = pi * acc_up_top; p.bb_dn[o2] = pi * acc_dn_top; }
+      if (JAC) p.flux_upJac[o2] = pi * acc_jac_top;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // adding (Shonk & Hogan 2008), mo_rte_solver_kernels.F90:1135-1245, on register chunks.
 // In:  R[i] = Rdif, T[i] = Tdif, SU[i] = src_up, SD[i] = src_dn of layer k0+i (from the top).
 // The upward sweep overwrites them with what the downward sweep needs:

@@ -280,8 +280,12 @@ def compute_profiles(SST, ncol, nlay):
     gamma, q_0, c608 = f32(6.7e-3), f32(0.01864), f32(0.608)
     Tv0 = (1.0 + c608 * q_0) * SST
     half = nlay // 2
-    z_lev = np.concatenate([[0.0], 2.0 * z_trop / nlay * np.arange(1, half + 1),
-                            z_trop + 2.0 * (z_top - z_trop) / nlay * np.arange(1, half + 1)])
+    if nlay % 2 == 0:   # the reference's own split (:514-517): half the layers below 15 km, half above
+        z_lev = np.concatenate([[0.0], 2.0 * z_trop / nlay * np.arange(1, half + 1),
+                                z_trop + 2.0 * (z_top - z_trop) / nlay * np.arange(1, half + 1)])
+    else:               # odd layer counts (IFS 137): the extra layer goes to the upper half
+        hi = nlay - half
+        z_lev = np.concatenate([[0.0], z_trop / half * np.arange(1, half + 1), z_trop + (z_top - z_trop) / hi * np.arange(1, hi + 1)])
     z_lay = 0.5 * (z_lev[:nlay] + z_lev[1:nlay + 1])
 
     def prof(z):

@@ -240,6 +240,22 @@ def test_register_solvers_on_tall_columns(oracle_lib, cuda_lib, ncol, nlay, top_
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("top_at_1", [True, False])
+@pytest.mark.parametrize("ncol,nlay", [(22, 37), (24, 72), (26, 80), (22, 90), (18, 137)])
+@pytest.mark.parametrize("nmus,bb,jac", [(1, True, False), (1, True, True), (2, False, True), (3, False, False)])
+def test_lw_tang_rescaling_on_the_register_kernel(oracle_lib, cuda_lib, ncol, nlay, top_at_1, nmus, bb, jac):
+    """do_rescaling = true (mo_rte_solver_kernels.F90:148-178, 753-844; the default LW treatment of scattering optical
+    properties, mo_rte_lw.F90:395-423) with even ncol: TMA tiles, so the register kernel lw_rescl_reg_kernel runs (odd ncol
+    takes the tile kernel: tests above).  Both orientations - the second downward sweep is orientation-asymmetric in the
+    reference (:801-804 vs :835-838)."""
+    x = _lw_inputs(ncol, nlay, 5, seed=31, scattering=True)
+    ref = _run_lw_noscat(oracle_lib, None, x, top_at_1, nmus, bb, jac, True)
+    got = _run_lw_noscat(cuda_lib, "cuda:0", x, top_at_1, nmus, bb, jac, True)
+    for k in ref:
+        _close(got[k], ref[k], k)
+
+
+@pytest.mark.gpu
 def test_sw_solver_noscat_and_reductions(oracle_lib, cuda_lib):
     x = _sw_inputs(17, 29, 5, seed=8)
     x["mu0"] = np.asfortranarray(np.abs(x["mu0"]) + 0.05)
