@@ -359,9 +359,12 @@ __global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? MINB : 1) lw_nosc
           // level in either orientation (:638-644)
           const Float sdn = ((Float)1 - t) * Bbot + (Float)2 * fact * (lay - Bbot);
           const Float sup = ((Float)1 - t) * Btop + (Float)2 * fact * (lay - Btop);
-          sd[i] = live ? sdn : (Float)0;
-          su[i] = live ? sup : (Float)0;
-          tr[i] = live ? t : (Float)1;
+          // FULL = 2: a zero-filled padding row (tau = 0, zero sources) gives t = 1 and sdn = sup = 0 EXACTLY
+          // (exp(-0) = 1, the series branch of fact is 0): no select needed
+          constexpr bool SEL = FULL == 0;
+          sd[i] = (!SEL || live) ? sdn : (Float)0;
+          su[i] = (!SEL || live) ? sup : (Float)0;
+          tr[i] = (!SEL || live) ? t : (Float)1;
         }
         Btop = Bbot;
       }
@@ -1034,12 +1037,15 @@ __global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? MINB : 1) sw_2str
                                (Float)2.0 * (k_gamma4 + alpha1 * k_mu) * exp_minusktau);
       Rdir = fmax((Float)0, fmin(Rdir, ((Float)1 - Tnoscat)));         // :1107
       Tdir = fmax((Float)0, fmin(Tdir, ((Float)1 - Tnoscat - Rdir)));  // :1108
-      const bool lit = live && (mu0 > (Float)0);  // :1122-1125: no source for diffuse light where mu0 <= 0
-      R[i] = live ? Rdif : (Float)0;
+      // FULL = 2: a zero-filled padding row (tau = ssa = g = 0) gives Rdif = 0 (factor 1 - exp(-0)), Rdir = Tdir = 0
+      // (factor ssa) and Tnoscat = exp(-0) = 1 EXACTLY; only Tdif = RT_term*2k is 1 to rounding - one select, on T
+      constexpr bool SEL = FULL == 0;
+      const bool lit = (!SEL || live) && (mu0 > (Float)0);  // :1122-1125: no source for diffuse light where mu0 <= 0
+      R[i] = (!SEL || live) ? Rdif : (Float)0;
       T[i] = live ? Tdif : (Float)1;
       A3[i] = lit ? Rdir : (Float)0;
       A4[i] = lit ? Tdir : (Float)0;
-      A5[i] = live ? Tnoscat : (Float)1;
+      A5[i] = (!SEL || live) ? Tnoscat : (Float)1;
     }
     const Float alb_dir = *RB_SLOT(sm, NS, s, BC0 + 0), alb_dif = *RB_SLOT(sm, NS, s, BC0 + 1);
     const Float dir_top_g = *RB_SLOT(sm, NS, s, BC0 + 2) * mu0_top;                  // :575
@@ -1225,7 +1231,8 @@ __global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? (TMA ? 2 : 3) : 1
       const Float tdif = RT_term * (Float)2 * kk * exp_minusktau;
       const Float lev_top = Blev[i], lev_bot = Blev[i + 1];
       // :947-957; the divisor is clamped where the source is switched off anyway (tau <= 1e-8)
-      const bool has_src = live && tau > (Float)1.0e-8;
+      constexpr bool SEL = FULL == 0;   // FULL = 2: zero-filled padding rows have tau = 0 -> no source, rdif = 0 exactly; tdif by select
+      const bool has_src = (!SEL || live) && tau > (Float)1.0e-8;
       const Float Z = rb_div(lev_bot - lev_top, fmax(tau, (Float)1.0e-8) * (gamma1 + gamma2));
       const Float Zup_top = Z + lev_top;
       const Float Zup_bottom = Z + lev_bot;
@@ -1233,7 +1240,7 @@ __global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? (TMA ? 2 : 3) : 1
       const Float Zdn_bottom = -Z + lev_bot;
       const Float s_up = pi * (Zup_top - rdif * Zdn_top - tdif * Zup_bottom);
       const Float s_dn = pi * (Zdn_bottom - rdif * Zup_bottom - tdif * Zdn_top);
-      R[i] = live ? rdif : (Float)0;
+      R[i] = (!SEL || live) ? rdif : (Float)0;
       T[i] = live ? tdif : (Float)1;
       SU[i] = has_src ? s_up : (Float)0;
       SD[i] = has_src ? s_dn : (Float)0;

@@ -19,7 +19,6 @@ ncol = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 lib = pkg.lib()
 lib.set_stream(torch.cuda.current_stream().cuda_stream)
 h = HostAllSky(lib, ncol, 72, syn.make_kdist("lw"), syn.make_kdist("sw"), chunk)
-os.environ["RRTMGPB_STREAM_TRACE"] = "0"
 h.step()
 Context(lib, "cuda:0").config_checks(False, False)
 h.step()
