@@ -150,6 +150,11 @@ int rrtmgpb_gas_optics_ext_fused(const rrtmgpb_gas_optics_t* go, int ncol, int n
                                  const rrtmgpb_optical_props* clouds, const rrtmgpb_optical_props* aerosols,
                                  char* errmsg);
 
+/* gas_optics() derives top_at_1 from play(1,1) < play(1,nlay) (mo_gas_optics_rrtmgp.F90:258) - two device reads and stream
+ * synchronisations per call here.  A driver that knows the orientation may state it for the calling thread (0 / 1;
+ * -1: unset again) and keep its launches asynchronous. */
+void rrtmgpb_set_top_at_1_hint(int top_at_1);
+
 /* ---------------- express path: state in, broadband fluxes out ---------------- */
 /* = gas_optics(play, plev, tlay, tsfc, gas_concs, atmos, sources[, col_dry, tlev]) ; clouds%increment(atmos) ;
  *   rte_lw(atmos, sources, sfc_emis, fluxes[, n_gauss_angles])   with ty_fluxes_broadband

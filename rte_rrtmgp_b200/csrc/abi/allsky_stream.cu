@@ -4,10 +4,12 @@
 // Reference workload: the loop body of examples/all-sky/rrtmgp_allsky.F90:332-409.  What a host model that keeps its
 // state in CPU memory needs from an accelerator backend is not a kernel but this: inputs cross PCIe once, fluxes come
 // back once, and neither transfer is exposed.  Three streams:
-//     up    chunk k+1's input slices  (cudaMemcpy2DAsync: a column range of a Fortran (ncol, nlay) array is strided)
-//     comp  chunk k: gas_concs broadcast, cloud optics, gas optics, solver  (the C++ frontend's own calls)
-//     down  chunk k-1's five flux slices
-// ordered by events; two device input sets and two device flux sets.  With pinned host memory every copy is
+//     up      chunk k+1's input slices  (cudaMemcpy2DAsync: a column range of a Fortran (ncol, nlay) array is strided)
+//     comp    even chunks: gas_concs broadcast, cloud optics, gas optics, solver  (the C++ frontend's own calls)
+//     comp2   odd chunks, concurrently: a chunk's kernels run on grids a few waves long, and the idle tail of one
+//             chunk's kernel is filled by the other chunk's (measured: 45.4 -> see DESIGN.md ms of chunked compute)
+//     down    finished chunks' five flux slices
+// ordered by events; two device input sets, two work-array sets and two device flux sets.  With pinned host memory every copy is
 // asynchronous; with pageable memory CUDA stages them (correct, serialised).
 #include <algorithm>
 #include <cstdlib>
@@ -23,7 +25,8 @@ using namespace rrtmgpb;
 namespace {
 
 struct Streams {
-  cudaStream_t up = nullptr, down = nullptr;
+  cudaStream_t up = nullptr, down = nullptr, comp2 = nullptr;
+  cudaEvent_t joined = nullptr;
   cudaEvent_t in_ready[2] = {}, in_free[2] = {}, out_ready[2] = {}, out_free[2] = {};
 };
 Streams& streams() {
@@ -31,6 +34,8 @@ Streams& streams() {
   if (!s.up) {
     RB_CUDA_CHECK(cudaStreamCreateWithFlags(&s.up, cudaStreamNonBlocking));
     RB_CUDA_CHECK(cudaStreamCreateWithFlags(&s.down, cudaStreamNonBlocking));
+    RB_CUDA_CHECK(cudaStreamCreateWithFlags(&s.comp2, cudaStreamNonBlocking));
+    RB_CUDA_CHECK(cudaEventCreateWithFlags(&s.joined, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
       RB_CUDA_CHECK(cudaEventCreateWithFlags(&s.in_ready[i], cudaEventDisableTiming));
       RB_CUDA_CHECK(cudaEventCreateWithFlags(&s.in_free[i], cudaEventDisableTiming));
@@ -115,41 +120,50 @@ extern "C" int rrtmgpb_allsky_stream_host(const rrtmgpb_gas_optics_t* go_lw, con
       if (in->vmr_field && in->vmr_field[g]) I[k].field[(size_t)g] = take(ncl);
     for (int a = 0; a < 5; ++a) O[k].f[a] = take(nclp);
   }
-  Float* vmr = take(ncl * ngas);
-  // work arrays of the plane path (chunk sized); the express path needs none
+  // work arrays, one set per concurrent chunk: vmr, by-band cloud properties and (plane path) the chunk-sized planes
   const int* bl_lw = go_lw ? rrtmgpb_gas_optics_band_lims_gpt(go_lw) : nullptr;
   const int* bl_sw = go_sw ? rrtmgpb_gas_optics_band_lims_gpt(go_sw) : nullptr;
   std::vector<int> byband_lw(2 * (size_t)std::max(nbnd_lw, 1)), byband_sw(2 * (size_t)std::max(nbnd_sw, 1));
   for (int b = 0; b < nbnd_lw; ++b) byband_lw[2 * b] = byband_lw[2 * b + 1] = b + 1;
   for (int b = 0; b < nbnd_sw; ++b) byband_sw[2 * b] = byband_sw[2 * b + 1] = b + 1;
-  rrtmgpb_optical_props atm_lw{}, atm_sw{}, cld_lw{}, cld_sw{};
-  rrtmgpb_source_func_lw src{};
-  Float* toa = nullptr;
-  auto props = [&](rrtmgpb_optical_props& o, int kind, int ng, int nb, const int* lims, bool alloc) {
+  struct Work {
+    Float* vmr;
+    rrtmgpb_optical_props atm_lw, atm_sw, cld_lw, cld_sw;
+    rrtmgpb_source_func_lw src;
+    Float* toa;
+  } W[2] = {};
+  auto props = [&](rrtmgpb_optical_props& o, int kind, int ng, int nb, const int* lims) {
     o.kind = kind; o.ncol = nc; o.nlay = nlay; o.ngpt = ng; o.nband = nb; o.nmom = 0; o.top_at_1 = 0;
     o.band_lims_gpt = lims; o.band_lims_wvn = nullptr;
-    if (alloc) {
-      o.tau = take(ncl * ng);
-      o.ssa = kind == RRTMGPB_2STR ? take(ncl * ng) : nullptr;
-      o.g = kind == RRTMGPB_2STR ? take(ncl * ng) : nullptr;
-    }
+    o.tau = take(ncl * ng);
+    o.ssa = kind == RRTMGPB_2STR ? take(ncl * ng) : nullptr;
+    o.g = kind == RRTMGPB_2STR ? take(ncl * ng) : nullptr;
   };
-  if (go_lw && clouds) props(cld_lw, RRTMGPB_1SCL, nbnd_lw, nbnd_lw, byband_lw.data(), true);
-  if (go_sw && clouds) props(cld_sw, RRTMGPB_2STR, nbnd_sw, nbnd_sw, byband_sw.data(), true);
-  if (!express) {
-    if (go_lw) {
-      props(atm_lw, RRTMGPB_1SCL, ngpt_lw, nbnd_lw, bl_lw, true);
-      src.ncol = nc; src.nlay = nlay; src.ngpt = ngpt_lw;
-      src.lay_source = take(ncl * ngpt_lw); src.lev_source = take(nclp * ngpt_lw);
-      src.sfc_source = take((size_t)nc * ngpt_lw); src.sfc_source_Jac = take((size_t)nc * ngpt_lw);
+  const int nsets = ncol > nc ? 2 : 1;
+  for (int k = 0; k < nsets; ++k) {
+    Work& w = W[k];
+    w.vmr = take(ncl * ngas);
+    if (go_lw && clouds) props(w.cld_lw, RRTMGPB_1SCL, nbnd_lw, nbnd_lw, byband_lw.data());
+    if (go_sw && clouds) props(w.cld_sw, RRTMGPB_2STR, nbnd_sw, nbnd_sw, byband_sw.data());
+    if (!express) {
+      if (go_lw) {
+        props(w.atm_lw, RRTMGPB_1SCL, ngpt_lw, nbnd_lw, bl_lw);
+        w.src.ncol = nc; w.src.nlay = nlay; w.src.ngpt = ngpt_lw;
+        w.src.lay_source = take(ncl * ngpt_lw); w.src.lev_source = take(nclp * ngpt_lw);
+        w.src.sfc_source = take((size_t)nc * ngpt_lw); w.src.sfc_source_Jac = take((size_t)nc * ngpt_lw);
+      }
+      if (go_sw) { props(w.atm_sw, RRTMGPB_2STR, ngpt_sw, nbnd_sw, bl_sw); w.toa = take((size_t)nc * ngpt_sw); }
     }
-    if (go_sw) { props(atm_sw, RRTMGPB_2STR, ngpt_sw, nbnd_sw, bl_sw, true); toa = take((size_t)nc * ngpt_sw); }
   }
+  cudaStream_t cstream[2] = {comp, nsets > 1 ? S.comp2 : comp};
+  // the driver holds the pressures on the host: tell the frontend the orientation (no device reads / syncs per call)
+  rrtmgpb_set_top_at_1_hint(in->p_lay[0] < in->p_lay[(size_t)ncol * (nlay - 1)] ? 1 : 0);
   cudaEvent_t start;
   RB_CUDA_CHECK(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
   RB_CUDA_CHECK(cudaEventRecord(start, comp));
   RB_CUDA_CHECK(cudaStreamWaitEvent(S.up, start, 0));
   RB_CUDA_CHECK(cudaStreamWaitEvent(S.down, start, 0));
+  if (nsets > 1) RB_CUDA_CHECK(cudaStreamWaitEvent(S.comp2, start, 0));
   for (int k = 0; k < 2; ++k) {   // both sets start out free
     RB_CUDA_CHECK(cudaEventRecord(S.in_free[k], comp));
     RB_CUDA_CHECK(cudaEventRecord(S.out_free[k], S.down));
@@ -198,10 +212,17 @@ extern "C" int rrtmgpb_allsky_stream_host(const rrtmgpb_gas_optics_t* go_lw, con
   for (int ic = 0; ic < nchunk && msg.empty(); ++ic) {
     const int k = ic & 1, c0 = starts[(size_t)ic], n = starts[(size_t)ic + 1] - c0;
     if (ic + 1 < nchunk) upload(ic + 1);
-    RB_CUDA_CHECK(cudaStreamWaitEvent(comp, S.in_ready[k], 0));
-    RB_CUDA_CHECK(cudaStreamWaitEvent(comp, S.out_free[k], 0));
+    cudaStream_t cs = cstream[k];
+    rrtmgpb_set_stream(cs);   // the frontend launches on the calling thread's stream: this chunk's
+    RB_CUDA_CHECK(cudaStreamWaitEvent(cs, S.in_ready[k], 0));
+    RB_CUDA_CHECK(cudaStreamWaitEvent(cs, S.out_free[k], 0));
     const InSet& X = I[k];
-    if (trace) RB_CUDA_CHECK(cudaEventRecord(tr[(size_t)ic].c0, comp));
+    Work& w = W[k % nsets];
+    Float* vmr = w.vmr;
+    rrtmgpb_optical_props &atm_lw = w.atm_lw, &atm_sw = w.atm_sw, &cld_lw = w.cld_lw, &cld_sw = w.cld_sw;
+    rrtmgpb_source_func_lw& src = w.src;
+    Float* toa = w.toa;
+    if (trace) RB_CUDA_CHECK(cudaEventRecord(tr[(size_t)ic].c0, cs));
     // gas_concs -> vmr(n, nlay, ngas): fields as uploaded, well-mixed gases broadcast (mo_gas_optics_rrtmgp.F90:540-545)
     for (int g = 0; g < ngas; ++g) {
       Float* plane = vmr + (size_t)n * nlay * g;
@@ -233,9 +254,9 @@ extern "C" int rrtmgpb_allsky_stream_host(const rrtmgpb_gas_optics_t* go_lw, con
         if (rrtmgpb_rte_sw(&atm_sw, X.mu0, toa, X.alb_dir, X.alb_dif, &fs, nullptr, err)) { msg = err; break; }
       }
     }
-    RB_CUDA_CHECK(cudaEventRecord(S.in_free[k], comp));
-    RB_CUDA_CHECK(cudaEventRecord(S.out_ready[k], comp));
-    if (trace) RB_CUDA_CHECK(cudaEventRecord(tr[(size_t)ic].c1, comp));
+    RB_CUDA_CHECK(cudaEventRecord(S.in_free[k], cs));
+    RB_CUDA_CHECK(cudaEventRecord(S.out_ready[k], cs));
+    if (trace) RB_CUDA_CHECK(cudaEventRecord(tr[(size_t)ic].c1, cs));
     // ---- fluxes of this chunk -> host, behind the compute stream
     RB_CUDA_CHECK(cudaStreamWaitEvent(S.down, S.out_ready[k], 0));
     if (trace) RB_CUDA_CHECK(cudaEventRecord(tr[(size_t)ic].d0, S.down));
@@ -244,6 +265,12 @@ extern "C" int rrtmgpb_allsky_stream_host(const rrtmgpb_gas_optics_t* go_lw, con
       if (dsts[a] && ((a < 2 && go_lw) || (a >= 2 && go_sw))) download_cols(dsts[a], O[k].f[a], ncol, c0, n, nlev, S.down);
     RB_CUDA_CHECK(cudaEventRecord(S.out_free[k], S.down));
     if (trace) RB_CUDA_CHECK(cudaEventRecord(tr[(size_t)ic].d1, S.down));
+  }
+  rrtmgpb_set_stream(comp);
+  rrtmgpb_set_top_at_1_hint(-1);
+  if (nsets > 1) {   // join: the caller's stream continues after the auxiliary compute stream
+    RB_CUDA_CHECK(cudaEventRecord(S.joined, S.comp2));
+    RB_CUDA_CHECK(cudaStreamWaitEvent(comp, S.joined, 0));
   }
   // the call returns when the last fluxes are on the host; the compute stream is ordered behind both copy streams
   RB_CUDA_CHECK(cudaStreamSynchronize(S.down));

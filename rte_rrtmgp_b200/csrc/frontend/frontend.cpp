@@ -621,12 +621,21 @@ static int compute_gas_taus(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, 
   return ok(errmsg);
 }
 
-static int set_top_at_1(rrtmgpb_optical_props* op, const Float* play, int ncol, int nlay) {
+// A driver that already knows the vertical orientation (it holds the pressures on the host) can spare every
+// gas-optics call the two device reads + stream synchronisations below: rrtmgpb_set_top_at_1_hint(0 / 1), -1 = unset.
+// Per calling thread.
+static thread_local int tl_top_at_1_hint = -1;
+void rrtmgpb_set_top_at_1_hint(int top_at_1) { tl_top_at_1_hint = top_at_1 < 0 ? -1 : (top_at_1 != 0); }
+static int orientation(const Float* play, int ncol, int nlay) {
+  if (tl_top_at_1_hint >= 0) return tl_top_at_1_hint;
   // mo_gas_optics_rrtmgp.F90:258: top_at_1 = play(1,1) < play(1,nlay) - needs two values on the host
   Float a = 0, b = 0;
   rrtmgpb_mem_to_host(&a, play, sizeof(Float));
   rrtmgpb_mem_to_host(&b, play + (size_t)ncol * (nlay - 1), sizeof(Float));
-  op->top_at_1 = a < b;
+  return a < b;
+}
+static int set_top_at_1(rrtmgpb_optical_props* op, const Float* play, int ncol, int nlay) {
+  op->top_at_1 = orientation(play, ncol, nlay);
   return op->top_at_1;
 }
 
@@ -843,10 +852,7 @@ static int express_impl(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, cons
     cld_kind = clouds->kind;
   }
   if (!msg.empty()) return fail(errmsg, msg);
-  Float a = 0, b = 0;  // top_at_1 = play(1,1) < play(1,nlay), mo_gas_optics_rrtmgp.F90:258
-  rrtmgpb_mem_to_host(&a, play, sizeof(Float));
-  rrtmgpb_mem_to_host(&b, play + (size_t)ncol * (nlay - 1), sizeof(Float));
-  const int top_at_1 = a < b;
+  const int top_at_1 = orientation(play, ncol, nlay);  // play(1,1) < play(1,nlay), mo_gas_optics_rrtmgp.F90:258
   Float* tlev_alloc = nullptr;
   const Float* tlev_wk = tlev;
   if (!sw && !tlev) {
