@@ -466,17 +466,20 @@ def run_product(args):
             b.free()
 
         # ---- end to end through the library's HOST-buffer entry: state and fluxes in pinned host memory
-        h = HostAllSky(lib, ncol, NLAY, kd_lw, kd_sw, args.e2e_chunk, device=b.device)
-        h.step(); h.step()
-        ms_e2e = b.timed(h.step, steps)   # events on the library's compute stream; the call returns when the fluxes are on the host
-        e2e = {"value": world * ncol / (ms_e2e * 1e-3), "unit": "columns/s", "h2d_bytes_per_step": h.h2d_bytes,
-               "d2h_bytes_per_step": h.d2h_bytes, "ms_per_step": ms_e2e, "chunk_columns": args.e2e_chunk,
-               "api": "rrtmgpb_allsky_stream_host (include/rrtmgp_b200_frontend.h): host buffers in, host fluxes out, copies inside the timed region"}
-        if rank == 0 and flux_gpu is not None:
-            fh = h.fluxes_host()
-            e2e["max_abs_flux_diff_vs_resident_Wm2"] = max(float(np.max(np.abs(fh[k] - flux_gpu[k]))) for k in fh)
-        del h
-        b.free()
+        e2e = None
+        if not args.no_e2e:
+            h = HostAllSky(lib, ncol, NLAY, kd_lw, kd_sw, args.e2e_chunk, device=b.device)
+            h.step(); h.step()
+            ms_e2e = b.timed(h.step, steps)   # events on the library's compute stream; the call returns when the fluxes are on the host
+            e2e = {"value": world * ncol / (ms_e2e * 1e-3), "unit": "columns/s", "h2d_bytes_per_step": h.h2d_bytes,
+                   "d2h_bytes_per_step": h.d2h_bytes, "ms_per_step": ms_e2e,
+                   "chunk_columns": args.e2e_chunk or "library default (4 solver waves, small first chunk, 2 compute streams)",
+                   "api": "rrtmgpb_allsky_stream_host (include/rrtmgp_b200_frontend.h): host buffers in, host fluxes out, copies inside the timed region"}
+            if rank == 0 and flux_gpu is not None:
+                fh = h.fluxes_host()
+                e2e["max_abs_flux_diff_vs_resident_Wm2"] = max(float(np.max(np.abs(fh[k] - flux_gpu[k]))) for k in fh)
+            del h
+            b.free()
 
         # ---- a stock host (gfortran-style: HOST arrays into the 45 symbols, every call staged through PCIe), small slice;
         # in a child process: a failure on this correctness path must not take the bench line with it
@@ -581,6 +584,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-seq", action="store_true", help="skip the kernel-by-kernel (reference call sequence) leg")
     ap.add_argument("--no-extras", action="store_true", help="skip express / host-pointer / other-config legs")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer (e2e) leg (profiling runs only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     if args.impl == "reference":
