@@ -157,6 +157,16 @@ struct GLoad<2> {
   }
 };
 
+// the same from a shared-memory copy of the rows (experimental table staging, see gas_tau_g_kernel STAGE)
+template <int VEC>
+struct SLoad {
+  Float v[VEC];
+  __device__ __forceinline__ SLoad(const Float* p) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = p[i];
+  }
+};
+
 // 3-D interpolation (interpolate3D_byflav :791-801) of n <= kGG consecutive g-points starting at 0-based
 // table column g0: out[i] = scale0*(4 terms of row set 0) + scale1*(4 terms of row set 1).  FULL: n == kGG.
 template <int VEC, bool FULL>
@@ -240,9 +250,12 @@ __device__ __forceinline__ Float minor_scaling(const FusedParams& p, const Minor
 // CLD (KIND 1 only): false = no cell of the WARP has cloud in this band (ct == 0 in every lane, a warp-uniform fact): the
 // by-band increment then reduces, with identical arithmetic, to ssa = (tau*ssa)/max(eps, tau), g = 0 (its numerator
 // tau*ssa*0 + 0*cw*cg is exactly 0), tau unchanged - one division per value instead of three.
-template <bool SW, int VEC, int NC, bool AER, int KIND, bool CLD = true>
+// STG: the band's table rows were staged to shared memory by the block (regular bands only): stg = [8 major rows: x0..x3,
+// y0..y3][16 g-points], then [contributor][4 rows: m0, m0+eta, m1, m1+eta][16 g-points]
+template <bool SW, int VEC, int NC, bool AER, int KIND, bool CLD = true, bool STG = false>
 __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const TablesT& tt, const BandInfo& bi, bool tropo,
-                                               int jtemp, int row0, int row1, TauCell (&cell)[NC], const Float* scal) {
+                                               int jtemp, int row0, int row1, TauCell (&cell)[NC], const Float* scal,
+                                               const Float* stg = nullptr) {
   const rrtmgpb_gas_tables& t = p.t;
   const size_t ncl = (size_t)p.ncol * p.nlay;
   const int itropo = tropo ? 0 : 1;
@@ -267,8 +280,12 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
 #pragma unroll
       for (int i = 0; i < kTG; i += VEC) {
         if (FULL || i < n) {
-          const GLoad<VEC> x0(a0 + i), x1(a0 + d_eta + i), x2(a0 + d_p + i), x3(a0 + d_p + d_eta + i);
-          const GLoad<VEC> y0(b0 + i), y1(b0 + d_eta + i), y2(b0 + d_p + i), y3(b0 + d_p + d_eta + i);
+          using LD = std::conditional_t<STG, SLoad<VEC>, GLoad<VEC>>;
+          const int so = (gS - bi.bS) + i;   // STG: position inside the band's 16 staged g-points
+          const LD x0(STG ? stg + so : a0 + i), x1(STG ? stg + 16 + so : a0 + d_eta + i),
+              x2(STG ? stg + 32 + so : a0 + d_p + i), x3(STG ? stg + 48 + so : a0 + d_p + d_eta + i);
+          const LD y0(STG ? stg + 64 + so : b0 + i), y1(STG ? stg + 80 + so : b0 + d_eta + i),
+              y2(STG ? stg + 96 + so : b0 + d_p + i), y3(STG ? stg + 112 + so : b0 + d_p + d_eta + i);
 #pragma unroll
           for (int k = 0; k < NC; ++k) {
             const Float(&f)[8] = cell[k].w.fmj;
@@ -316,7 +333,10 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
 #pragma unroll
       for (int i = 0; i < kTG; i += VEC) {
         if (whole || (i >= iS && i <= iE)) {  // VEC == 2: intervals start even and have even length (TablesT::vec)
-          const GLoad<VEC> x0(m0 + i), x1(m0 + d_eta + i), y0(m1 + i), y1(m1 + d_eta + i);
+          using LD = std::conditional_t<STG, SLoad<VEC>, GLoad<VEC>>;
+          const Float* sm_m = STG ? stg + 128 + (imnr - mfirst) * 64 + (gS - bi.bS) + i : nullptr;
+          const LD x0(STG ? sm_m : m0 + i), x1(STG ? sm_m + 16 : m0 + d_eta + i), y0(STG ? sm_m + 32 : m1 + i),
+              y1(STG ? sm_m + 48 : m1 + d_eta + i);
 #pragma unroll
           for (int k = 0; k < NC; ++k) {
             const Float(&a)[4] = am[k];
@@ -415,13 +435,20 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
   }
 }
 
-template <bool SW, int VEC, bool AER, int KIND>
+// STAGE (experiment, LW only, RRTMGPB_TABLE_TMA=1): when every cell of the block interpolates between the SAME table rows
+// (a regular band; neighbouring columns in the same T / p / eta bins) one thread copies those rows - 8 of kmajor, 4 per
+// minor contributor, 128 bytes each - to shared memory with cp.async.bulk (the TMA engine), completion on an mbarrier,
+// and the block reads them from there.  Measured on B200: no faster - the gas-optics kernels are bound
+// by the L1 / shared-memory DATA pipe into the register file, which a shared-memory copy of the rows uses just the same.
+template <bool SW, int VEC, bool AER, int KIND, bool STAGE = false>
 __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_LW) gas_tau_g_kernel(const FusedParams p, const TablesT tt) {
   const rrtmgpb_gas_tables& t = p.t;
   const size_t ncl = (size_t)p.ncol * p.nlay;
   const int ibnd = p.band0 + blockIdx.x % p.nband_sub;
-  const size_t cbase = (size_t)(blockIdx.x / p.nband_sub) * (kTauCells * kGThreads) + threadIdx.x;
-  if (cbase >= ncl) return;
+  const size_t cbase_raw = (size_t)(blockIdx.x / p.nband_sub) * (kTauCells * kGThreads) + threadIdx.x;
+  if (!STAGE && cbase_raw >= ncl) return;
+  const bool thread_valid = cbase_raw < ncl;                 // STAGE: every thread stays for the block-wide barriers
+  const size_t cbase = thread_valid ? cbase_raw : ncl - 1;
   // minor-contributor scalings of this thread's cells: [contributor of the band][cell slot][thread], lane-private
   // (no barrier: a thread only reads what it wrote); tt.maxm contributors at most
   extern __shared__ __align__(16) unsigned char tau_smem_raw[];
@@ -435,7 +462,7 @@ __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_L
   for (int k = 0; k < kTauCells; ++k) {
     const size_t craw = cbase + (size_t)k * kGThreads;
     TauCell& ce = cell[k];
-    ce.valid = craw < ncl;
+    ce.valid = thread_valid && craw < ncl;
     ce.slot = k;
     const size_t c = ce.valid ? craw : cbase;  // out-of-range slots shadow the thread's first cell, never store
     ce.c = c;
@@ -478,6 +505,61 @@ __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_L
   for (int k = 1; k < kTauCells; ++k)
     shared_rows = shared_rows && tropo[k] == tropo[0] && row0[k] == row0[0] && row1[k] == row1[0];
   if (tropo[0] ? bi.mdiff[0] : bi.mdiff[1]) shared_rows = false;
+  if (STAGE) {
+    // ---- block-uniform rows?  thread 0 publishes its rows, everybody compares, one vote
+    Float* stg = reinterpret_cast<Float*>(tau_smem_raw) + (size_t)tt.maxm * kTauCells * kGThreads;   // after the scaling slots
+    __shared__ int s_rows[4];
+    __shared__ __align__(8) uint64_t s_bar;
+    const bool regular = tropo[0] ? bi.regular[0] : bi.regular[1];
+    if (threadIdx.x == 0) {
+      s_rows[0] = row0[0]; s_rows[1] = row1[0]; s_rows[2] = tropo[0] ? 1 : 0; s_rows[3] = jtemp[0];
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(&s_bar)));
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const bool same = shared_rows && regular && row0[0] == s_rows[0] && row1[0] == s_rows[1] && (tropo[0] ? 1 : 0) == s_rows[2];
+    if (__syncthreads_and(same)) {
+      const int s_eta = t.ntemp, s_p = t.ntemp * t.neta;
+      const bool tr = tropo[0];
+      const int mfirst = tr ? bi.mfirst[0] : bi.mfirst[1], mlast = tr ? bi.mlast[0] : bi.mlast[1];
+      const int nm = mlast >= mfirst ? mlast - mfirst + 1 : 0;
+      if (threadIdx.x == 0) {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+        const unsigned bytes = (unsigned)((8 + 4 * nm) * 16 * sizeof(Float));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+        auto bulk = [&](Float* dst, const Float* src) {
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+                           "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "n"(16 * (int)sizeof(Float)), "r"(bar)
+                       : "memory");
+        };
+        const Float* a0 = tt.kmajor + (size_t)row0[0] * tt.gp + (bi.bS - 1);
+        const Float* b0 = tt.kmajor + (size_t)row1[0] * tt.gp + (bi.bS - 1);
+        const size_t d_eta = (size_t)s_eta * tt.gp, d_p = (size_t)s_p * tt.gp;
+        bulk(stg, a0); bulk(stg + 16, a0 + d_eta); bulk(stg + 32, a0 + d_p); bulk(stg + 48, a0 + d_p + d_eta);
+        bulk(stg + 64, b0); bulk(stg + 80, b0 + d_eta); bulk(stg + 96, b0 + d_p); bulk(stg + 112, b0 + d_p + d_eta);
+        const MinorInfo* minfo = tr ? tt.aux.minor_lower : tt.aux.minor_upper;
+        const Float* kminor = tr ? tt.kminor_lower : tt.kminor_upper;
+        const int mpitch = tr ? tt.nkl : tt.nku;
+        const int je0 = cell[0].w.je[0], je1 = cell[0].w.je[1];
+        for (int m = 0; m < nm; ++m) {
+          const MinorInfo mi = minfo[mfirst + m];
+          const Float* m0 = kminor + (size_t)((jtemp[0] - 1) + s_eta * (je0 - 1)) * mpitch + (mi.kstart - 1);
+          const Float* m1 = kminor + (size_t)(jtemp[0] + s_eta * (je1 - 1)) * mpitch + (mi.kstart - 1);
+          const size_t de = (size_t)s_eta * mpitch;
+          Float* d = stg + 128 + m * 64;
+          bulk(d, m0); bulk(d + 16, m0 + de); bulk(d + 32, m1); bulk(d + 48, m1 + de);
+        }
+      }
+      {  // wait for the rows (phase 0 of the one-shot barrier)
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
+        asm volatile(
+            "{\n.reg .pred P1;\nWAIT_STG:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n@P1 bra DONE_STG;\nbra WAIT_STG;\nDONE_STG:\n}\n" ::"r"(bar)
+            : "memory");
+      }
+      tau_band_cells<SW, VEC, kTauCells, AER, KIND, true, true>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell, scal, stg);
+      return;
+    }
+  }
   // cloud-free warps (layers above / below the cloud deck, clear regions) take the reduced increment; the test is
   // warp-uniform, so it costs no divergence
   bool cloudy = false;
