@@ -365,22 +365,16 @@ void launch_tau(const FusedParams& p, const TablesT& tt) {
   const unsigned grid = (unsigned)((long long)ceil_div((long long)ncl, kTauCells * kGThreads) * p.nband_sub);
   // lane-private slots for the per-(cell, band) minor scalings: [contributor][cell slot][thread]
   size_t smem = (size_t)tt.maxm * kTauCells * kGThreads * sizeof(Float);
-  // experiment: RRTMGPB_TABLE_TMA=1 stages block-uniform table rows to shared memory with cp.async.bulk
-  static const bool stage_env = [] { const char* e = std::getenv("RRTMGPB_TABLE_TMA"); return e && e[0] == '1'; }();
-  const bool stage = stage_env && !sw && tt.vec == 2 && !aer_kind && op_kind == 1 && cld_kind == 1 && kTG * kTauRegChunks == 16;
-  if (stage) {
-    smem += (size_t)(8 + 4 * tt.maxm) * 16 * sizeof(Float);
-    KernelTimer* dummy = nullptr; (void)dummy;
-    auto kern = gas_tau_g_kernel<false, 2, false, 1, true>;
-    if (smem > 48 * 1024) RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kGThreads, smem, stream()>>>(p, tt);
-    RB_LAUNCH_CHECK();
-    return;
-  }
+  // table rows staged per warp by cp.async.bulk when the warp's cells share them (gas_tau_g_kernel STAGE); needs the
+  // 128-bit layout (tt.vec == 2) and 16-g-point chunks; RRTMGPB_TABLE_TMA=0 switches it off
+  static const bool stage_env = [] { const char* e = std::getenv("RRTMGPB_TABLE_TMA"); return !(e && e[0] == '0'); }();
+  const bool stage = stage_env && tt.vec == 2 && !aer_kind && kTG * kTauRegChunks == 16;
+  if (stage) smem += (size_t)(kGThreads / 32) * (kStgMinor / 16 + 4 * tt.maxm) * 16 * sizeof(Float);
 // KIND 1: the common kinds as compile-time constants (LW 1scl += 1scl clouds, SW 2str += 2str clouds, no aerosols)
 #define GAS_TAU_LAUNCH1(SWV, VECV, AERV, KINDV)                                                                   \
   do {                                                                                                            \
-    auto kern = gas_tau_g_kernel<SWV, VECV, AERV, KINDV>;                                                         \
+    auto kern = (stage && VECV == 2 && !AERV) ? gas_tau_g_kernel<SWV, VECV, AERV, KINDV, (VECV == 2 && !AERV)>    \
+                                              : gas_tau_g_kernel<SWV, VECV, AERV, KINDV, false>;                  \
     if (smem > 48 * 1024) RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, kGThreads, smem, stream()>>>(p, tt);                                                             \
   } while (0)

@@ -570,6 +570,10 @@ inline int reg_chunk_len(int nlay, int ncol) {
   return 0;
 }
 inline int reg_lanes(int nlay) { return nlay <= 80 ? 8 : 16; }
+inline bool force_pad() {  // RRTMGPB_FORCE_PAD=1: run the FULL = 2 (padded-tile) instantiations even when nlay == lanes*CL (A/B switch)
+  static const bool v = [] { const char* e = std::getenv("RRTMGPB_FORCE_PAD"); return e && e[0] == '1'; }();
+  return v;
+}
 inline bool sw_cl8() {  // RRTMGPB_SW_CL8=1: 8 layers per lane for nlay <= 64 in the SW kernel (A/B switch; default 9, see below)
   static const bool v = [] { const char* e = std::getenv("RRTMGPB_SW_CL8"); return e && e[0] == '1'; }();
   return v;
@@ -943,7 +947,7 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
     if (use_tma && !lean) {                                                                                 \
       const size_t smem = sacc ? sw_reg_tma_smem<CLV, true>(rows) : sw_reg_tma_smem<CLV, false>(rows);      \
       auto kern = sacc ? sw_2stream_reg_kernel<CLV, BBV, 2, BBV, true, 2>                                   \
-                       : (rows == nlay ? sw_2stream_reg_kernel<CLV, BBV, 2, false, true, 1>                 \
+                       : ((rows == nlay && !force_pad()) ? sw_2stream_reg_kernel<CLV, BBV, 2, false, true, 1> \
                                        : sw_2stream_reg_kernel<CLV, BBV, 2, false, true, 2>);               \
       RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
       kern<<<grid, kRegThreads, smem, stream()>>>(q, maps);                                                 \

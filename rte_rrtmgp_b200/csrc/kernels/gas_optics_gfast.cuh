@@ -157,6 +157,7 @@ struct GLoad<2> {
   }
 };
 
+constexpr int kStgRayl = 128, kStgMinor = 192;   // staged rows of a warp: [0,128) kmajor, [128,192) krayl, then 64 per contributor
 // the same from a shared-memory copy of the rows (experimental table staging, see gas_tau_g_kernel STAGE)
 template <int VEC>
 struct SLoad {
@@ -334,7 +335,7 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
       for (int i = 0; i < kTG; i += VEC) {
         if (whole || (i >= iS && i <= iE)) {  // VEC == 2: intervals start even and have even length (TablesT::vec)
           using LD = std::conditional_t<STG, SLoad<VEC>, GLoad<VEC>>;
-          const Float* sm_m = STG ? stg + 128 + (imnr - mfirst) * 64 + (gS - bi.bS) + i : nullptr;
+          const Float* sm_m = STG ? stg + kStgMinor + (imnr - mfirst) * 64 + (gS - bi.bS) + i : nullptr;
           const LD x0(STG ? sm_m : m0 + i), x1(STG ? sm_m + 16 : m0 + d_eta + i), y0(STG ? sm_m + 32 : m1 + i),
               y1(STG ? sm_m + 48 : m1 + d_eta + i);
 #pragma unroll
@@ -406,7 +407,10 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
     for (int i0 = 0; i0 < kTG; i0 += VEC) {
       if (!FULL && i0 >= n) continue;
       if (SW) {
-        const GLoad<VEC> x0(r0 + i0), x1(r0 + dr_eta + i0), y0(r1 + i0), y1(r1 + dr_eta + i0);
+        using LD = std::conditional_t<STG, SLoad<VEC>, GLoad<VEC>>;
+        const Float* sm_r = STG ? stg + kStgRayl + (gS - bi.bS) + i0 : nullptr;
+        const LD x0(STG ? sm_r : r0 + i0), x1(STG ? sm_r + 16 : r0 + dr_eta + i0), y0(STG ? sm_r + 32 : r1 + i0),
+            y1(STG ? sm_r + 48 : r1 + dr_eta + i0);
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
           const Float(&a)[4] = cell[k].w.fmn;
@@ -435,11 +439,12 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
   }
 }
 
-// STAGE (experiment, LW only, RRTMGPB_TABLE_TMA=1): when every cell of the block interpolates between the SAME table rows
-// (a regular band; neighbouring columns in the same T / p / eta bins) one thread copies those rows - 8 of kmajor, 4 per
-// minor contributor, 128 bytes each - to shared memory with cp.async.bulk (the TMA engine), completion on an mbarrier,
-// and the block reads them from there.  Measured on B200: no faster - the gas-optics kernels are bound
-// by the L1 / shared-memory DATA pipe into the register file, which a shared-memory copy of the rows uses just the same.
+// STAGE: when every cell of a WARP interpolates between the SAME table rows (a regular band; neighbouring columns in the
+// same T / p / eta bins - one vote per warp) lane 0 copies those rows - 8 of kmajor, 4 of krayl (SW), 4 per minor
+// contributor, 128 bytes each - to the warp's shared-memory slots with cp.async.bulk (the TMA engine, completion on the
+// warp's mbarrier) and the warp reads them from there: immediate-offset LDS instead of LDG with 64-bit row addresses, at
+// shared-memory latency.  Measured on B200: LW tau 5.18 -> 4.33 ms at 65,536 x 72 x 256 (block-wide
+// variant).  Warps whose cells differ take the L1 path below.  RRTMGPB_TABLE_TMA=0 switches it off.
 template <bool SW, int VEC, bool AER, int KIND, bool STAGE = false>
 __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_LW) gas_tau_g_kernel(const FusedParams p, const TablesT tt) {
   const rrtmgpb_gas_tables& t = p.t;
@@ -505,27 +510,35 @@ __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_L
   for (int k = 1; k < kTauCells; ++k)
     shared_rows = shared_rows && tropo[k] == tropo[0] && row0[k] == row0[0] && row1[k] == row1[0];
   if (tropo[0] ? bi.mdiff[0] : bi.mdiff[1]) shared_rows = false;
+  // cloud-free warps (layers above / below the cloud deck, clear regions) take the reduced increment; the test is
+  // warp-uniform, so it costs no divergence
+  bool cloudy = false;
+  if (SW && KIND == 1 && !AER) {
+    bool mine = false;
+#pragma unroll
+    for (int k = 0; k < kTauCells; ++k) mine = mine || cell[k].ct != (Float)0;
+    cloudy = __any_sync(__activemask(), mine);
+  }
   if (STAGE) {
-    // ---- block-uniform rows?  thread 0 publishes its rows, everybody compares, one vote
-    Float* stg = reinterpret_cast<Float*>(tau_smem_raw) + (size_t)tt.maxm * kTauCells * kGThreads;   // after the scaling slots
-    __shared__ int s_rows[4];
-    __shared__ __align__(8) uint64_t s_bar;
+    // ---- warp-uniform rows?  (lane 0's rows against everybody's: one vote, no block barrier)
+    const unsigned full = 0xffffffffu;
     const bool regular = tropo[0] ? bi.regular[0] : bi.regular[1];
-    if (threadIdx.x == 0) {
-      s_rows[0] = row0[0]; s_rows[1] = row1[0]; s_rows[2] = tropo[0] ? 1 : 0; s_rows[3] = jtemp[0];
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"((unsigned)__cvta_generic_to_shared(&s_bar)));
-      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    __syncthreads();
-    const bool same = shared_rows && regular && row0[0] == s_rows[0] && row1[0] == s_rows[1] && (tropo[0] ? 1 : 0) == s_rows[2];
-    if (__syncthreads_and(same)) {
+    const bool same = shared_rows && regular && row0[0] == __shfl_sync(full, row0[0], 0) && row1[0] == __shfl_sync(full, row1[0], 0) &&
+                      (int)tropo[0] == __shfl_sync(full, (int)tropo[0], 0);
+    if (__all_sync(full, same)) {
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      __shared__ __align__(8) uint64_t s_bar[kGThreads / 32];
       const int s_eta = t.ntemp, s_p = t.ntemp * t.neta;
       const bool tr = tropo[0];
       const int mfirst = tr ? bi.mfirst[0] : bi.mfirst[1], mlast = tr ? bi.mlast[0] : bi.mlast[1];
       const int nm = mlast >= mfirst ? mlast - mfirst + 1 : 0;
-      if (threadIdx.x == 0) {
-        const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
-        const unsigned bytes = (unsigned)((8 + 4 * nm) * 16 * sizeof(Float));
+      const int rows_per_warp = kStgMinor / 16 + 4 * tt.maxm;
+      Float* stg = reinterpret_cast<Float*>(tau_smem_raw) + (size_t)tt.maxm * kTauCells * kGThreads + (size_t)warp * rows_per_warp * 16;
+      const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar[warp]);
+      if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        const unsigned bytes = (unsigned)((8 + (SW ? 4 : 0) + 4 * nm) * 16 * sizeof(Float));
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
         auto bulk = [&](Float* dst, const Float* src) {
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
@@ -537,37 +550,36 @@ __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_L
         const size_t d_eta = (size_t)s_eta * tt.gp, d_p = (size_t)s_p * tt.gp;
         bulk(stg, a0); bulk(stg + 16, a0 + d_eta); bulk(stg + 32, a0 + d_p); bulk(stg + 48, a0 + d_p + d_eta);
         bulk(stg + 64, b0); bulk(stg + 80, b0 + d_eta); bulk(stg + 96, b0 + d_p); bulk(stg + 112, b0 + d_p + d_eta);
+        const int je0 = cell[0].w.je[0], je1 = cell[0].w.je[1];
+        if (SW) {
+          const Float* kr = tt.krayl + (size_t)s_p * tt.gp * (tr ? 0 : 1) + (bi.bS - 1);
+          const Float* r0 = kr + (size_t)((jtemp[0] - 1) + s_eta * (je0 - 1)) * tt.gp;
+          const Float* r1 = kr + (size_t)(jtemp[0] + s_eta * (je1 - 1)) * tt.gp;
+          const size_t dr = (size_t)s_eta * tt.gp;
+          bulk(stg + kStgRayl, r0); bulk(stg + kStgRayl + 16, r0 + dr); bulk(stg + kStgRayl + 32, r1); bulk(stg + kStgRayl + 48, r1 + dr);
+        }
         const MinorInfo* minfo = tr ? tt.aux.minor_lower : tt.aux.minor_upper;
         const Float* kminor = tr ? tt.kminor_lower : tt.kminor_upper;
         const int mpitch = tr ? tt.nkl : tt.nku;
-        const int je0 = cell[0].w.je[0], je1 = cell[0].w.je[1];
         for (int m = 0; m < nm; ++m) {
           const MinorInfo mi = minfo[mfirst + m];
           const Float* m0 = kminor + (size_t)((jtemp[0] - 1) + s_eta * (je0 - 1)) * mpitch + (mi.kstart - 1);
           const Float* m1 = kminor + (size_t)(jtemp[0] + s_eta * (je1 - 1)) * mpitch + (mi.kstart - 1);
           const size_t de = (size_t)s_eta * mpitch;
-          Float* d = stg + 128 + m * 64;
+          Float* d = stg + kStgMinor + m * 64;
           bulk(d, m0); bulk(d + 16, m0 + de); bulk(d + 32, m1); bulk(d + 48, m1 + de);
         }
       }
-      {  // wait for the rows (phase 0 of the one-shot barrier)
-        const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
-        asm volatile(
-            "{\n.reg .pred P1;\nWAIT_STG:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n@P1 bra DONE_STG;\nbra WAIT_STG;\nDONE_STG:\n}\n" ::"r"(bar)
-            : "memory");
-      }
-      tau_band_cells<SW, VEC, kTauCells, AER, KIND, true, true>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell, scal, stg);
+      __syncwarp();
+      asm volatile(
+          "{\n.reg .pred P1;\nWAIT_STG:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n@P1 bra DONE_STG;\nbra WAIT_STG;\nDONE_STG:\n}\n" ::"r"(bar)
+          : "memory");
+      if (SW && KIND == 1 && !AER && !cloudy)
+        tau_band_cells<SW, VEC, kTauCells, AER, KIND, false, true>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell, scal, stg);
+      else
+        tau_band_cells<SW, VEC, kTauCells, AER, KIND, true, true>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell, scal, stg);
       return;
     }
-  }
-  // cloud-free warps (layers above / below the cloud deck, clear regions) take the reduced increment; the test is
-  // warp-uniform, so it costs no divergence
-  bool cloudy = false;
-  if (SW && KIND == 1 && !AER) {
-    bool mine = false;
-#pragma unroll
-    for (int k = 0; k < kTauCells; ++k) mine = mine || cell[k].ct != (Float)0;
-    cloudy = __any_sync(__activemask(), mine);
   }
   if (shared_rows && SW && KIND == 1 && !AER && !cloudy) {
     tau_band_cells<SW, VEC, kTauCells, AER, KIND, false>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell, scal);
