@@ -523,8 +523,10 @@ __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_L
     // ---- warp-uniform rows?  (lane 0's rows against everybody's: one vote, no block barrier)
     const unsigned full = 0xffffffffu;
     const bool regular = tropo[0] ? bi.regular[0] : bi.regular[1];
-    const bool same = shared_rows && regular && row0[0] == __shfl_sync(full, row0[0], 0) && row1[0] == __shfl_sync(full, row1[0], 0) &&
-                      (int)tropo[0] == __shfl_sync(full, (int)tropo[0], 0);
+    // (the shuffles first, unconditionally: every lane of the warp must execute them)
+    const int r0_lane0 = __shfl_sync(full, row0[0], 0), r1_lane0 = __shfl_sync(full, row1[0], 0);
+    const int tr_lane0 = __shfl_sync(full, (int)tropo[0], 0);
+    const bool same = shared_rows && regular && row0[0] == r0_lane0 && row1[0] == r1_lane0 && (int)tropo[0] == tr_lane0;
     if (__all_sync(full, same)) {
       const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
       __shared__ __align__(8) uint64_t s_bar[kGThreads / 32];
