@@ -574,8 +574,8 @@ inline bool force_pad() {  // RRTMGPB_FORCE_PAD=1: run the FULL = 2 (padded-tile
   static const bool v = [] { const char* e = std::getenv("RRTMGPB_FORCE_PAD"); return e && e[0] == '1'; }();
   return v;
 }
-inline bool sw_cl8() {  // RRTMGPB_SW_CL8=1: 8 layers per lane for nlay <= 64 in the SW kernel (A/B switch; default 9, see below)
-  static const bool v = [] { const char* e = std::getenv("RRTMGPB_SW_CL8"); return e && e[0] == '1'; }();
+inline bool sw_cl8() {  // RRTMGPB_SW_CL9=1: 9 layers per lane for nlay <= 64 in the SW kernel too (A/B switch; default 8, see below)
+  static const bool v = [] { const char* e = std::getenv("RRTMGPB_SW_CL9"); return !(e && e[0] == '1'); }();
   return v;
 }
 inline int reg_minb() {  // experiment switch: resident CTAs per SM the register kernels are compiled for
@@ -930,9 +930,9 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
     // TMA tile staging of tau / ssa / g (kernels/tma.cuh) whenever the planes can be described
     SwTmaMaps maps;
     const int nch = reg_lanes(nlay);
-    // nlay <= 64 runs 9 layers per lane as well (like the LW kernels): with CL = 8 the eight lanes of a column read tile
-    // rows 8 apart - one swizzle phase, 8-way bank conflicts - and since the padding rows of the zero-filled tiles cost
-    // no clamped addressing any more, 72 slots at full speed beat 64 conflicting ones (B200, 65,536 x 60: see DESIGN.md)
+    // nlay <= 64 keeps 8 layers per lane here (the LW kernels run 9: with CL = 8 the eight lanes of a column read tile rows
+    // 8 apart - one swizzle phase, 8-way bank conflicts): this kernel is fp64-bound, and 64 slots with conflicts beat 72
+    // without (B200, 65,536 x 60, select-free padded tiles: 12.8 vs 13.9 ms)
     const int cl_sw = (nch == 8 && cl == 8 && !sw_cl8()) ? 9 : cl;
     const int rows = nch * cl_sw;   // zero-filled padded tiles, see rte_lw_solver_noscat
     q.tile_rows = rows; q.row0 = p.top_at_1 ? 0 : nlay - rows;

@@ -101,6 +101,17 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #ifndef RB_SW_MERGED_DIV
 #define RB_SW_MERGED_DIV 1
 #endif
+// 1: the SW kernel's FULL = 2 (zero-filled padded tiles) instantiations carry NO padding select at all: with the two
+// divisions kept separate, a zero row gives Tdif = rcp(4)*2*2*exp(-0) = 1 EXACTLY (k = sqrt(4) = 2, rt_den = 4 - every
+// factor a power of two), so the padding is pass-through by arithmetic alone
+// Measured on B200 (65,536 x 60 / x 72 forced onto the padded instantiation): ONE select per cell (on Tdif) costs the
+// SW kernel 17 % (16.28 vs 13.87 ms: the kernel lives on interleaving nine cells at the register limit), none 3 %.
+// To keep results independent of WHICH instantiation runs (even / odd ncol decides whether TMA is usable), the choice
+// between the shared and the separate reciprocal follows the SHAPE, not the instantiation: shared when nlay fills the
+// lanes exactly (FULL = 1, and FULL = 0 on such shapes), separate otherwise (FULL = 2, and FULL = 0 on such shapes).
+#ifndef RB_PAD_NOSELECT
+#define RB_PAD_NOSELECT 1
+#endif
 template <int NCH>
 __device__ __forceinline__ Float affine_handoff_down(int j, Float A, Float B, Float x_top, Float& out) {
 #if RB_HANDOFF_SCAN
@@ -987,7 +998,8 @@ __global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? MINB : 1) sw_2str
     // interleave the CL independent cells of a lane.
 #pragma unroll
     for (int i = 0; i < CL; ++i) {
-      const bool live = FULLG || k0 + i < nlay;
+      constexpr bool NOSEL = RB_PAD_NOSELECT && FULL == 2;
+      const bool live = FULLG || NOSEL || k0 + i < nlay;
       Float tau_s, w0_s, g_s;
       if (TMA) {
         const Float* e = tile_at(tile_s, o.lay(FULL ? k0 + i : min(k0 + i, nlay - 1)) - row0, cw);
@@ -1007,21 +1019,22 @@ __global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? MINB : 1) sw_2str
       const Float om_s = fabs(om) >= eps ? om : eps;                                  // :1071-1073
       const Float rt_den = kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau);
 #if RB_SW_MERGED_DIV
+      // FULL = 1: shared reciprocal; FULL = 2: separate; FULL = 0 (clamped cp.async inputs, any shape): whichever the
+      // TMA instantiation of the same shape uses (uniform at run time), so that results do not depend on the path
+      const bool MERGED = (FULL == 1) ? true : ((FULL == 2) ? !NOSEL : (RB_PAD_NOSELECT ? (NCH == 8 && nlay == kRegChunks * CL) : true));   // (16-lane TMA launches are all FULL = 2)
       // RT_term = 1/rt_den (:1052) and RT_term*w0/om_s (:1071) from ONE reciprocal, 1/(rt_den*om_s): a multiplication
       // each instead of a second division sequence (9 fp64 instructions); rt_den in [k, 2*max(k, gamma1)] and
       // |om_s| >= eps keep the product finite and normal; both quotients stay within 2 ulp of the reference's
-      const Float rt_inv = rb_rcp(rt_den * om_s);
-      Float RT_term = om_s * rt_inv;
+      const Float rt_inv = rb_rcp(MERGED ? rt_den * om_s : rt_den);
+      Float RT_term = MERGED ? om_s * rt_inv : rt_inv;
 #else
+      constexpr bool MERGED = false;
       Float RT_term = rb_rcp(rt_den);
+      const Float rt_inv = RT_term;
 #endif
       const Float Rdif = RT_term * gamma2 * ((Float)1 - exp_minus2ktau);
       const Float Tdif = RT_term * (Float)2 * kk * exp_minusktau;
-#if RB_SW_MERGED_DIV
-      RT_term = w0_s * rt_inv;
-#else
-      RT_term = rb_div(w0_s * RT_term, om_s);
-#endif
+      RT_term = MERGED ? w0_s * rt_inv : rb_div(w0_s * rt_inv, om_s);
       const Float gamma3 = ((Float)2 - (Float)3 * mu0_s * g_s) * (Float).25;
       const Float gamma4 = (Float)1 - gamma3;
       const Float alpha1 = gamma1 * gamma4 + gamma2 * gamma3;

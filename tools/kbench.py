@@ -41,6 +41,7 @@ def main():
         reps = -(-a.ncol // 1800)
         import numpy as np
         prof = {k: np.asfortranarray(np.tile(v, (reps,) + (1,) * (v.ndim - 1))[:a.ncol]) for k, v in base.items()}
+    free0 = torch.cuda.mem_get_info()[0]
     sky = AllSky(ctx, a.ncol, a.nlay, kd_lw, kd_sw, do_clouds=not a.distinct, profiles=prof, express=a.express)
     sky.step()
     ctx.config_checks(False, False)
@@ -61,7 +62,8 @@ def main():
         name, cnt, tot = ln.rsplit(" ", 2)
         ks[name] = round(float(tot) / a.steps, 3)
     mem = torch.cuda.max_memory_allocated() / 2**30
-    print(json.dumps({"tag": a.tag, "express": a.express, "peak_torch_GiB": round(mem, 2), "ncol": a.ncol, "nlay": a.nlay, "distinct": a.distinct,
+    used = (free0 - torch.cuda.mem_get_info()[0]) / 2**30   # includes the library's stream-ordered pool at its peak
+    print(json.dumps({"tag": a.tag, "express": a.express, "peak_torch_GiB": round(mem, 2), "device_GiB": round(used, 2), "ncol": a.ncol, "nlay": a.nlay, "distinct": a.distinct,
                       "ms_per_step": round(e0.elapsed_time(e1) / a.steps, 3), "kernels": ks}), flush=True)
 
 
