@@ -73,7 +73,10 @@ void rrtmgpb_init_constants(const Float* gravity, const Float* mol_weight_dry_ai
 void rrtmgpb_set_lw_2stream_lev_source_per_gpt(int on);
 
 /* Solver kernel family: 0 (default) = register-resident warp-systolic kernels when nlay <= 80 (shared-memory
- * tile kernels otherwise, and for Tang rescaling); 1 = always the shared-memory tile kernels. */
+ * tile kernels otherwise); 1 = always the shared-memory tile kernels; 2 = the register kernels, never the
+ * warp-specialised SW kernel; 3 = the warp-specialised SW two-stream kernel (csrc/kernels/solver_ws.cuh) wherever it
+ * applies (nlay <= 80, even ncol), register kernels elsewhere.  2 and 3 exist for A/B tests: both give bit-identical
+ * results. */
 void rrtmgpb_set_solver_variant(int variant);
 int rrtmgpb_get_solver_variant(void);
 

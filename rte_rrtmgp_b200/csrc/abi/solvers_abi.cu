@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include "../kernels/elementwise.cuh"
 #include "../kernels/solver_reg.cuh"
+#include "../kernels/solver_ws.cuh"
 #include "rte_kernels.h"
 #include "rrtmgp_b200_ext.h"
 
@@ -556,7 +557,7 @@ void launch_tile(K kern, const P& p, dim3 grid, size_t smem, const char* name) {
 
 // register-resident kernels: chunk length CL = ceil(nlay/8) in {8,9,10}
 inline int reg_chunk_len(int nlay, int ncol) {
-  if (g_solver_variant.load(std::memory_order_relaxed) != 0) return 0;
+  if (g_solver_variant.load(std::memory_order_relaxed) == 1) return 0;
   // the register kernels use 32-bit in-plane offsets (kernels/solver_reg.cuh): planes of 2^31 elements or more go to
   // the tile kernels, whose indices are 64-bit
   if ((long long)ncol * (nlay + 1) > (long long)INT_MAX) return 0;
@@ -589,6 +590,30 @@ inline bool reg_sacc() {  // experiment switch: SW broadband accumulators in sha
 inline bool solver_tma_enabled() {  // RRTMGPB_SOLVER_TMA=0: lane-private cp.async staging instead (A/B switch)
   static const bool v = [] { const char* e = std::getenv("RRTMGPB_SOLVER_TMA"); return !(e && e[0] == '0'); }();
   return v;
+}
+// warp-specialised SW kernel (kernels/solver_ws.cuh): RRTMGPB_SW_WS=0/1 (A/B switch; measured slower than the register
+// kernel, see the header - off by default)
+inline bool sw_ws_enabled() {
+  static const bool v = [] { const char* e = std::getenv("RRTMGPB_SW_WS"); return e ? e[0] == '1' : false; }();
+  const int variant = g_solver_variant.load(std::memory_order_relaxed);
+  return variant == 3 || (variant == 0 && v);   // rrtmgpb_set_solver_variant: 2 = register kernels only, 3 = warp-specialised where applicable
+}
+template <int CL, bool BB, bool MERGED, int NPW>
+void launch_sw_ws(const SwRegParams& q, const SwTmaMaps& maps, dim3 grid) {
+  auto kern = sw_2stream_ws_kernel<CL, BB, MERGED, NPW>;
+  constexpr size_t smem = sw_ws_smem(8 * CL);
+  RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kWsConsumerThreads + 32 * NPW, smem, stream()>>>(q, maps);
+}
+template <int CL>
+void dispatch_sw_ws(const SwRegParams& q, const SwTmaMaps& maps, dim3 grid, bool bb, bool merged) {
+#define RB_WS(BBV, MV)                                                   \
+  {                                                                      \
+    launch_sw_ws<CL, BBV, MV, 8>(q, maps, grid);                         \
+  }
+  if (bb) { if (merged) RB_WS(true, true) else RB_WS(true, false) }
+  else { if (merged) RB_WS(false, true) else RB_WS(false, false) }
+#undef RB_WS
 }
 inline int reg_gpt_groups(int ncol, int ngpt) {
   const int ctas = ceil_div(ncol, (kRegThreads / 32) * kRegCols);
@@ -938,6 +963,18 @@ void rte_sw_solver_2stream(const int* ncol_, const int* nlay_, const int* ngpt_,
     q.tile_rows = rows; q.row0 = p.top_at_1 ? 0 : nlay - rows;
     const bool use_tma = solver_tma_enabled() && make_plane_tmap(&maps.tau, q.tau, ncol, nlay, ngpt, rows) &&
                          make_plane_tmap(&maps.ssa, q.ssa, ncol, nlay, ngpt, rows) && make_plane_tmap(&maps.g, q.g, ncol, nlay, ngpt, rows);
+    if (use_tma && nch == 8 && sw_ws_enabled()) {
+      // warp-specialised kernel: same shapes as the 8-lane TMA instantiations; MERGED follows the shape as below
+      KernelTimer timer("sw_2stream_ws_kernel");
+      const bool merged = rows == nlay && !force_pad();
+      switch (cl_sw) {
+        case 8: dispatch_sw_ws<8>(q, maps, grid, bb, merged); break;
+        case 9: dispatch_sw_ws<9>(q, maps, grid, bb, merged); break;
+        default: dispatch_sw_ws<10>(q, maps, grid, bb, merged); break;
+      }
+      RB_LAUNCH_CHECK();
+      return;
+    }
     {
       KernelTimer timer("sw_2stream_reg_kernel");
 #define SWREG2(CLV, BBV)                                                                                    \

@@ -837,6 +837,52 @@ __device__ __forceinline__ void adding_reg(int j, Float (&R)[CL], Float (&T)[CL]
 }
 
 // ---------------------------------------------------------------------------------------------------
+// One SW two-stream cell (mo_rte_solver_kernels.F90:1027-1108): layer reflectance / transmittance for diffuse and direct
+// light.  Shared by the register kernel below and the warp-specialised kernel (kernels/solver_ws.cuh), so that both run
+// the same arithmetic.  mu0_s = max(sqrt(eps), mu0), mu0_3 = 3*mu0_s and r_mu0 = rb_rcp1(mu0_s) depend on (column, layer)
+// only; callers that keep a cell across g-points hoist them.
+// merged: RT_term = 1/rt_den (:1052) and RT_term*w0/om_s (:1071) from ONE reciprocal, 1/(rt_den*om_s): a multiplication
+// each instead of a second division sequence (9 fp64 instructions); rt_den in [k, 2*max(k, gamma1)] and |om_s| >= eps
+// keep the product finite and normal; both quotients stay within 2 ulp of the reference's.  Not merged: a zero cell
+// (tau = ssa = g = 0) gives Tdif = rcp(4)*2*2*exp(-0) = 1 EXACTLY, which the zero-filled padded tiles rely on.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sw_two_stream_cell(Float tau_s, Float w0_s, Float g_s, Float mu0_s, Float mu0_3, Float r_mu0,
+                                                   bool merged, Float& Rdif, Float& Tdif, Float& Rdir, Float& Tdir,
+                                                   Float& Tnoscat) {
+  const Float eps = (Float)RB_EPS;
+  const Float min_k = (Float)1.e4 * eps;  // :1005
+  const Float gamma1 = ((Float)8 - w0_s * ((Float)5 + (Float)3 * g_s)) * (Float).25;
+  const Float gamma2 = (Float)3 * (w0_s * ((Float)1 - g_s)) * (Float).25;
+  const Float kk = rb_sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), min_k));
+  const Float exp_minusktau = rb_exp(-tau_s * kk);
+  const Float exp_minus2ktau = exp_minusktau * exp_minusktau;
+  const Float k_mu = kk * mu0_s;
+  const Float om = (Float)1 - k_mu * k_mu;
+  const Float om_s = fabs(om) >= eps ? om : eps;                                  // :1071-1073
+  const Float rt_den = kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau);
+  const Float rt_inv = rb_rcp(merged ? rt_den * om_s : rt_den);
+  Float RT_term = merged ? om_s * rt_inv : rt_inv;
+  Rdif = RT_term * gamma2 * ((Float)1 - exp_minus2ktau);
+  Tdif = RT_term * (Float)2 * kk * exp_minusktau;
+  RT_term = merged ? w0_s * rt_inv : rb_div(w0_s * rt_inv, om_s);
+  const Float gamma3 = ((Float)2 - mu0_3 * g_s) * (Float).25;
+  const Float gamma4 = (Float)1 - gamma3;
+  const Float alpha1 = gamma1 * gamma4 + gamma2 * gamma3;
+  const Float alpha2 = gamma1 * gamma3 + gamma2 * gamma4;
+  const Float k_gamma3 = kk * gamma3;
+  const Float k_gamma4 = kk * gamma4;
+  Tnoscat = rb_exp<true>(-rb_div_r(tau_s, mu0_s, r_mu0));  // flushes to 0 (night columns, mu0_s = sqrt(eps))
+  Rdir = RT_term * (((Float)1 - k_mu) * (alpha2 + k_gamma3) -
+                    ((Float)1 + k_mu) * (alpha2 - k_gamma3) * exp_minus2ktau -
+                    (Float)2.0 * (k_gamma3 - alpha2 * k_mu) * exp_minusktau * Tnoscat);
+  Tdir = -RT_term * (((Float)1 + k_mu) * (alpha1 + k_gamma4) * Tnoscat -
+                     ((Float)1 - k_mu) * (alpha1 - k_gamma4) * exp_minus2ktau * Tnoscat -
+                     (Float)2.0 * (k_gamma4 + alpha1 * k_mu) * exp_minusktau);
+  Rdir = fmax((Float)0, fmin(Rdir, ((Float)1 - Tnoscat)));         // :1107
+  Tdir = fmax((Float)0, fmin(Tdir, ((Float)1 - Tnoscat - Rdir)));  // :1108
+}
+
+// ---------------------------------------------------------------------------------------------------
 // SW two-stream (mo_rte_solver_kernels.F90:503-609, 985-1127)
 // ---------------------------------------------------------------------------------------------------
 struct SwRegParams {
@@ -1008,48 +1054,12 @@ __global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? MINB : 1) sw_2str
         tau_s = *RB_SLOT(sm, NS, s, i); w0_s = *RB_SLOT(sm, NS, s, CL + i); g_s = *RB_SLOT(sm, NS, s, 2 * CL + i);
       }
       const Float mu0 = sm_mu0[i * kRegThreads + threadIdx.x];
-      const Float gamma1 = ((Float)8 - w0_s * ((Float)5 + (Float)3 * g_s)) * (Float).25;
-      const Float gamma2 = (Float)3 * (w0_s * ((Float)1 - g_s)) * (Float).25;
-      const Float kk = rb_sqrt(fmax((gamma1 - gamma2) * (gamma1 + gamma2), min_k));
-      const Float exp_minusktau = rb_exp(-tau_s * kk);
-      const Float exp_minus2ktau = exp_minusktau * exp_minusktau;
-      const Float mu0_s = fmax(min_mu0, mu0);
-      const Float k_mu = kk * mu0_s;
-      const Float om = (Float)1 - k_mu * k_mu;
-      const Float om_s = fabs(om) >= eps ? om : eps;                                  // :1071-1073
-      const Float rt_den = kk * ((Float)1 + exp_minus2ktau) + gamma1 * ((Float)1 - exp_minus2ktau);
-#if RB_SW_MERGED_DIV
       // FULL = 1: shared reciprocal; FULL = 2: separate; FULL = 0 (clamped cp.async inputs, any shape): whichever the
       // TMA instantiation of the same shape uses (uniform at run time), so that results do not depend on the path
-      const bool MERGED = (FULL == 1) ? true : ((FULL == 2) ? !NOSEL : (RB_PAD_NOSELECT ? (NCH == 8 && nlay == kRegChunks * CL) : true));   // (16-lane TMA launches are all FULL = 2)
-      // RT_term = 1/rt_den (:1052) and RT_term*w0/om_s (:1071) from ONE reciprocal, 1/(rt_den*om_s): a multiplication
-      // each instead of a second division sequence (9 fp64 instructions); rt_den in [k, 2*max(k, gamma1)] and
-      // |om_s| >= eps keep the product finite and normal; both quotients stay within 2 ulp of the reference's
-      const Float rt_inv = rb_rcp(MERGED ? rt_den * om_s : rt_den);
-      Float RT_term = MERGED ? om_s * rt_inv : rt_inv;
-#else
-      constexpr bool MERGED = false;
-      Float RT_term = rb_rcp(rt_den);
-      const Float rt_inv = RT_term;
-#endif
-      const Float Rdif = RT_term * gamma2 * ((Float)1 - exp_minus2ktau);
-      const Float Tdif = RT_term * (Float)2 * kk * exp_minusktau;
-      RT_term = MERGED ? w0_s * rt_inv : rb_div(w0_s * rt_inv, om_s);
-      const Float gamma3 = ((Float)2 - (Float)3 * mu0_s * g_s) * (Float).25;
-      const Float gamma4 = (Float)1 - gamma3;
-      const Float alpha1 = gamma1 * gamma4 + gamma2 * gamma3;
-      const Float alpha2 = gamma1 * gamma3 + gamma2 * gamma4;
-      const Float k_gamma3 = kk * gamma3;
-      const Float k_gamma4 = kk * gamma4;
-      const Float Tnoscat = rb_exp<true>(-rb_div(tau_s, mu0_s));  // flushes to 0 (night columns, mu0_s = sqrt(eps))
-      Float Rdir = RT_term * (((Float)1 - k_mu) * (alpha2 + k_gamma3) -
-                              ((Float)1 + k_mu) * (alpha2 - k_gamma3) * exp_minus2ktau -
-                              (Float)2.0 * (k_gamma3 - alpha2 * k_mu) * exp_minusktau * Tnoscat);
-      Float Tdir = -RT_term * (((Float)1 + k_mu) * (alpha1 + k_gamma4) * Tnoscat -
-                               ((Float)1 - k_mu) * (alpha1 - k_gamma4) * exp_minus2ktau * Tnoscat -
-                               (Float)2.0 * (k_gamma4 + alpha1 * k_mu) * exp_minusktau);
-      Rdir = fmax((Float)0, fmin(Rdir, ((Float)1 - Tnoscat)));         // :1107
-      Tdir = fmax((Float)0, fmin(Tdir, ((Float)1 - Tnoscat - Rdir)));  // :1108
+      const bool MERGED = RB_SW_MERGED_DIV && ((FULL == 1) ? true : ((FULL == 2) ? !NOSEL : (RB_PAD_NOSELECT ? (NCH == 8 && nlay == kRegChunks * CL) : true)));   // (16-lane TMA launches are all FULL = 2)
+      const Float mu0_s = fmax(min_mu0, mu0);
+      Float Rdif, Tdif, Rdir, Tdir, Tnoscat;
+      sw_two_stream_cell(tau_s, w0_s, g_s, mu0_s, (Float)3 * mu0_s, rb_rcp1(mu0_s), MERGED, Rdif, Tdif, Rdir, Tdir, Tnoscat);
       // FULL = 2: a zero-filled padding row (tau = ssa = g = 0) gives Rdif = 0 (factor 1 - exp(-0)), Rdir = Tdir = 0
       // (factor ssa) and Tnoscat = exp(-0) = 1 EXACTLY; only Tdif = RT_term*2k is 1 to rounding - one select, on T
       constexpr bool SEL = FULL == 0;

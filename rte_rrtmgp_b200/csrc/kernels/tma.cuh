@@ -44,17 +44,18 @@ __device__ __forceinline__ void tma_load_tile(void* smem_dst, const CUtensorMap*
           "r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(col0), "r"(row0), "r"(g)
       : "memory");
 }
-// element (row, col) of a swizzled tile whose base is 1024-byte aligned
-__device__ __forceinline__ const Float* tile_at(const Float* tile, int row, int col) {
+// element offset of (row, col) inside a swizzled tile whose base is 1024-byte aligned
+__host__ __device__ __forceinline__ int tile_off(int row, int col) {
   static_assert(sizeof(Float) == 8 || sizeof(Float) == 4, "");
   if (sizeof(Float) == 8) {
     const int chunk = (col >> 1) ^ (row & 7);
-    return tile + row * kTmaCols + chunk * 2 + (col & 1);
+    return row * kTmaCols + chunk * 2 + (col & 1);
   } else {  // single precision: 16 columns = 64-byte rows, SWIZZLE_64B (chunk index ^ ((row >> 1) & 3))
     const int chunk = (col >> 2) ^ ((row >> 1) & 3);
-    return tile + row * kTmaCols + chunk * 4 + (col & 3);
+    return row * kTmaCols + chunk * 4 + (col & 3);
   }
 }
+__device__ __forceinline__ const Float* tile_at(const Float* tile, int row, int col) { return tile + tile_off(row, col); }
 // bytes of one tile in shared memory, rounded up to the swizzle atom (1024 B)
 __host__ __device__ inline size_t tile_bytes(int rows) { return ((size_t)rows * kTmaCols * sizeof(Float) + 1023) & ~(size_t)1023; }
 
