@@ -500,6 +500,15 @@ def run_product(args):
                 extras["value_host_pointer_call_sequence"] = None
                 extras["host_pointer_note"] = f"failed: {str(e)[:160]}"
 
+        # ---- the single-precision build (RTE_ENABLE_SP): its two solvers at the headline shape, in a child process
+        if not args.no_extras and world == 1 and rank == 0:
+            try:
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sp_solver_bench.py"), str(ncol)], capture_output=True,
+                                   text=True, timeout=300)
+                extras["single_precision_solvers"] = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception as e:  # pragma: no cover
+                extras["single_precision_solvers"] = {"error": str(e)[:160]}
+
         # ---- the other BASELINE.json configurations, per GPU, few steps (supplementary; full runs: --config c3|c4|c5)
         if not args.no_extras:
             other = {}
@@ -569,7 +578,7 @@ def run_product(args):
             "clocks": summarize_clocks(samples, b.local),
             "cpu_baseline": cpu_base,
             "max_abs_flux_err_vs_oracle_Wm2": parity,
-            **{k: v for k, v in extras.items() if k in ("express", "other_configs", "host_pointer_note")},
+            **{k: v for k, v in extras.items() if k in ("express", "other_configs", "host_pointer_note", "single_precision_solvers")},
             "kernels": kernels[:14],
         }
         print(json.dumps(line), flush=True)

@@ -25,6 +25,9 @@ extern "C" {
 /* ---------------- backend plumbing ---------------- */
 /* "cuda-sm_100a" for the product library, "cpu-oracle" for the oracle. */
 const char* rrtmgpb_backend_name(void);
+/* sizeof(Float) of this build: 8 (default) or 4 (-DRTE_USE_SP, the reference's RTE_ENABLE_SP; rte/kernels/mo_rte_kind.F90:28-36).
+ * The double-precision product is lib/librte_rrtmgp_b200.so, the single-precision one lib/librte_rrtmgp_b200_sp.so. */
+int rrtmgpb_float_bytes(void);
 /* Working-memory allocation in the backend's memory space (stream-ordered pool on CUDA). */
 void* rrtmgpb_mem_alloc(size_t bytes);
 void rrtmgpb_mem_free(void* p);

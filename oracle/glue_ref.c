@@ -15,6 +15,7 @@
 #define MAXF(a, b) (((a) > (b)) ? (a) : (b))
 
 const char* rrtmgpb_backend_name(void) { return "cpu-oracle"; }
+int rrtmgpb_float_bytes(void) { return (int)sizeof(Float); }
 void* rrtmgpb_mem_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void rrtmgpb_mem_free(void* p) { free(p); }
 void rrtmgpb_mem_to_backend(void* d, const void* s, size_t n) { memcpy(d, s, n); }

@@ -13,7 +13,9 @@ from .abi import KernelLib, fzeros, to_device, to_host  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "librte_rrtmgp_b200.so")
+LIB_PATH_SP = os.path.join(_HERE, "lib", "librte_rrtmgp_b200_sp.so")
 _LIB = None
+_LIB_SP = None
 
 
 def lib():
@@ -34,3 +36,16 @@ def lib():
         if not _LIB.backend.startswith("cuda"):
             raise RuntimeError(f"{LIB_PATH} reports backend {_LIB.backend!r}; expected the CUDA build")
     return _LIB
+
+
+def lib_sp():
+    """The single-precision build of the product library (-DRTE_USE_SP, the reference's RTE_ENABLE_SP): the same 45
+    symbols on float32 arrays.  No CPU fallback either."""
+    global _LIB_SP
+    if _LIB_SP is None:
+        if not os.path.exists(LIB_PATH_SP):
+            raise RuntimeError(f"{LIB_PATH_SP} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+        _LIB_SP = KernelLib(LIB_PATH_SP)
+        if not _LIB_SP.backend.startswith("cuda") or _LIB_SP.float_bytes != 4:
+            raise RuntimeError(f"{LIB_PATH_SP}: expected the single-precision CUDA build")
+    return _LIB_SP

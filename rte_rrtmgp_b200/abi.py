@@ -57,6 +57,10 @@ class KernelLib:
         self.cdll.rrtmgpb_set_stream.argtypes = [ctypes.c_void_p]
         self.cdll.rrtmgpb_get_stream.restype = ctypes.c_void_p
         self.cdll.rrtmgpb_set_device.argtypes = [ctypes.c_int]
+        # working precision of this build (RTE_USE_SP libraries take float32 arrays and c_float scalars)
+        self.float_bytes = int(self.cdll.rrtmgpb_float_bytes())
+        self.np_float = np.float32 if self.float_bytes == 4 else np.float64
+        self._scalar = dict(_SCALAR, Float=ctypes.c_float if self.float_bytes == 4 else ctypes.c_double)
 
     def symbols(self):
         return sorted(ABI)
@@ -84,7 +88,7 @@ class KernelLib:
             if is_arr:
                 cargs.append(_ptr(val))
             else:
-                box = _SCALAR[ctype](val)
+                box = self._scalar[ctype](val)
                 keep.append(box)
                 cargs.append(ctypes.cast(ctypes.pointer(box), ctypes.c_void_p))
         fn(*cargs)
@@ -95,6 +99,12 @@ class KernelLib:
         raise AttributeError(name)
 
     # ---- plumbing ----
+    def cast(self, a):
+        """Floating-point numpy arrays in this build's working precision (anything else unchanged)."""
+        if isinstance(a, np.ndarray) and a.dtype.kind == "f" and a.dtype != self.np_float:
+            return np.asfortranarray(a, dtype=self.np_float)
+        return a
+
     def sync(self):
         self.cdll.rrtmgpb_sync()
 

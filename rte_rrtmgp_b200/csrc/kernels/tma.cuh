@@ -79,11 +79,11 @@ inline EncodeTiledFn encode_tiled_fn() {
 // Tensor map of a Fortran-ordered (ncol, nrows, ngpt) plane with box (kTmaCols, box_rows, 1); box_rows = 0: nrows.  A
 // box taller than the plane (or started at a negative row) is allowed: rows outside the tensor arrive as zeros
 // (CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE = zero fill), which the solvers use as exact pass-through padding layers.
+// Single precision: 64-byte rows, SWIZZLE_64B (tile_off), tested by tests/test_single_precision.py.
 // Returns false when the plane cannot be described (odd ncol -> strides not multiples of 16 B, misaligned base, more
 // than 256 rows, no driver).
 inline bool make_plane_tmap(CUtensorMap* tm, const Float* base, int ncol, int nrows, int ngpt, int box_rows = 0) {
   if (box_rows <= 0) box_rows = nrows;
-  if (sizeof(Float) != 8) return false;  // single-precision builds (untested tile layout) use the cp.async staging
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc || !base || box_rows > 256 || ((size_t)ncol * sizeof(Float)) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) % 16) != 0)
     return false;

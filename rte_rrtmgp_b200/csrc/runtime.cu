@@ -92,6 +92,7 @@ using namespace rrtmgpb;
 
 extern "C" {
 const char* rrtmgpb_backend_name(void) { return "cuda-sm_100a"; }
+int rrtmgpb_float_bytes(void) { return (int)sizeof(Float); }
 void* rrtmgpb_mem_alloc(size_t bytes) { return dev_alloc(bytes); }
 void rrtmgpb_mem_free(void* p) {
   table_cache_release(p);  // no-op unless p is a k-distribution table with transposed copies

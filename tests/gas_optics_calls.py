@@ -1,6 +1,7 @@
 """Callers of the five rrtmgp_* extern-ABI symbols (rrtmgp/kernels/api/mo_gas_optics_rrtmgp_kernels.F90:16,98,170,210;
 api/mo_cloud_optics_rrtmgp_kernels.F90:18) on any KernelLib (oracle or CUDA), in the Fortran argument order.  Every call
-returns host numpy arrays (Fortran shapes)."""
+returns host numpy arrays (Fortran shapes).  Floating-point arguments are cast to the library's working precision
+(`lib.np_float`: float64, or float32 for the RTE_USE_SP builds)."""
 import numpy as np
 
 import refcases as rc
@@ -29,11 +30,11 @@ def profile(kd, ncol, nlay, seed, top_at_1=False, monotonic=True):
 def interpolation(lib, device, kd, play, tlay, col_gas, keep_device=False):
     ncol, nlay = play.shape
     nf = kd.nflav
-    d = lambda a: rc.dev(a, device)
+    d = lambda a: rc.dev(lib.cast(a), device)
     out = dict(jtemp=fzeros((ncol, nlay), np.int32, device), jpress=fzeros((ncol, nlay), np.int32, device),
                tropo=fzeros((ncol, nlay), np.bool_, device), jeta=fzeros((2, ncol, nlay, nf), np.int32, device),
-               col_mix=fzeros((2, ncol, nlay, nf), device=device), fmajor=fzeros((2, 2, 2, ncol, nlay, nf), device=device),
-               fminor=fzeros((2, 2, ncol, nlay, nf), device=device))
+               col_mix=fzeros((2, ncol, nlay, nf), lib.np_float, device), fmajor=fzeros((2, 2, 2, ncol, nlay, nf), lib.np_float, device),
+               fminor=fzeros((2, 2, ncol, nlay, nf), lib.np_float, device))
     lib.rrtmgp_interpolation(ncol, nlay, kd.ngas, nf, kd.neta, kd.npres, kd.ntemp, d(kd.flavor), d(kd.press_ref_log),
                              d(kd.temp_ref), kd.press_ref_log_delta, kd.temp_ref_min, kd.temp_ref_delta,
                              kd.press_ref_trop_log, d(kd.vmr_ref), d(play), d(tlay), d(col_gas), out["jtemp"],
@@ -45,8 +46,8 @@ def interpolation(lib, device, kd, play, tlay, col_gas, keep_device=False):
 def tau_absorption(lib, device, kd, play, tlay, col_gas, it):
     """`it`: interpolation outputs living where `lib` expects them (keep_device=True)."""
     ncol, nlay = play.shape
-    d = lambda a: rc.dev(a, device)
-    tau = fzeros((ncol, nlay, kd.ngpt), device=device)
+    d = lambda a: rc.dev(lib.cast(a), device)
+    tau = fzeros((ncol, nlay, kd.ngpt), lib.np_float, device)
     lib.rrtmgp_compute_tau_absorption(
         ncol, nlay, kd.nbnd, kd.ngpt, kd.ngas, kd.nflav, kd.neta, kd.npres, kd.ntemp, kd.extra["nminorlower"],
         kd.kminor_lower.shape[2], kd.extra["nminorupper"], kd.kminor_upper.shape[2], kd.idx_h2o, d(kd.gpoint_flavor),
@@ -62,8 +63,8 @@ def tau_absorption(lib, device, kd, play, tlay, col_gas, it):
 
 def tau_rayleigh(lib, device, kd, col_dry, col_gas, it):
     ncol, nlay = col_dry.shape
-    d = lambda a: rc.dev(a, device)
-    out = fzeros((ncol, nlay, kd.ngpt), device=device)
+    d = lambda a: rc.dev(lib.cast(a), device)
+    out = fzeros((ncol, nlay, kd.ngpt), lib.np_float, device)
     lib.rrtmgp_compute_tau_rayleigh(ncol, nlay, kd.nbnd, kd.ngpt, kd.ngas, kd.nflav, kd.neta, kd.npres, kd.ntemp,
                                     d(kd.gpoint_flavor), d(kd.band_lims_gpt), d(kd.krayl), kd.idx_h2o, d(col_dry),
                                     d(col_gas), it["fminor"], it["jeta"], it["tropo"], it["jtemp"], out)
@@ -73,9 +74,9 @@ def tau_rayleigh(lib, device, kd, col_dry, col_gas, it):
 
 def planck_source(lib, device, kd, tlay, tlev, tsfc, sfc_lay, it):
     ncol, nlay = tlay.shape
-    d = lambda a: rc.dev(a, device)
-    out = [fzeros((ncol, kd.ngpt), device=device), fzeros((ncol, nlay, kd.ngpt), device=device),
-           fzeros((ncol, nlay + 1, kd.ngpt), device=device), fzeros((ncol, kd.ngpt), device=device)]
+    d = lambda a: rc.dev(lib.cast(a), device)
+    out = [fzeros((ncol, kd.ngpt), lib.np_float, device), fzeros((ncol, nlay, kd.ngpt), lib.np_float, device),
+           fzeros((ncol, nlay + 1, kd.ngpt), lib.np_float, device), fzeros((ncol, kd.ngpt), lib.np_float, device)]
     lib.rrtmgp_compute_Planck_source(ncol, nlay, kd.nbnd, kd.ngpt, kd.nflav, kd.neta, kd.npres, kd.ntemp,
                                      kd.totplnk.shape[0], d(tlay), d(tlev), d(tsfc), sfc_lay, it["fmajor"], it["jeta"],
                                      it["tropo"], it["jtemp"], it["jpress"], d(kd.gpoint_bands), d(kd.band_lims_gpt),
@@ -88,8 +89,8 @@ def planck_source(lib, device, kd, tlay, tlev, tsfc, sfc_lay, it):
 def cld_from_table(lib, device, mask, lwp, re, nsteps, step, offset, tau_t, ssa_t, asy_t):
     ncol, nlay = lwp.shape
     nb = tau_t.shape[1]
-    d = lambda a: rc.dev(a, device)
-    out = [fzeros((ncol, nlay, nb), device=device) for _ in range(3)]
+    d = lambda a: rc.dev(lib.cast(a), device)
+    out = [fzeros((ncol, nlay, nb), lib.np_float, device) for _ in range(3)]
     lib.rrtmgp_compute_cld_from_table(ncol, nlay, nb, d(mask), d(lwp), d(re), nsteps, step, offset, d(tau_t), d(ssa_t),
                                       d(asy_t), *out)
     lib.sync()
