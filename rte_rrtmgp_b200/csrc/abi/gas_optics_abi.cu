@@ -11,6 +11,7 @@
 //    walks the band's g-points, accumulating major + minor absorbers in registers, so tau is written
 //    ONCE (the reference makes three read-modify-write passes over the tau plane);
 //  * k-distribution tables are read through the read-only path; they are <= 16 MB and stay L2-resident.
+#include <cstdlib>
 #include "../kernels/elementwise.cuh"
 #include "rrtmgp_kernels.h"
 #include "rrtmgp_b200_ext.h"
@@ -484,6 +485,18 @@ void tau_absorption_impl(int ncol, int nlay, int nbnd, int ngpt, int ngas, int n
       a_cg(col_gas, ncl * (ngas + 1), Dir::In);
   DevArg<int> a_je(jeta, 2 * ncl * nflav, Dir::In, true, 8), a_jt(jtemp, ncl, Dir::In), a_jp(jpress, ncl, Dir::In);
   DevArg<Float> a_tau(tau, ncl * ngpt, accumulate ? Dir::InOut : Dir::Out);
+  // Device-resident tables whose copies the caller allows to be cached (rrtmgpb_abi_table_cache): the g-point-fastest
+  // kernels of the fused path in their ABI instantiation (kernels/gas_optics_gfast.cuh: two cells per thread sharing table
+  // loads, 128-bit loads, warp-level TMA staging of shared rows) - same arithmetic, the interpolation state read from
+  // the caller's arrays.  B200, 65,536 x 72: LW + SW absorption 15.9 -> see DESIGN.md section 4.
+  static const bool gfast_env = [] { const char* e = std::getenv("RRTMGPB_ABI_GFAST"); return !(e && e[0] == '0'); }();
+  if (gfast_env && !a_km.staged() && !a_kl.staged() && !a_ku.staged() && !a_gf.staged() && !a_bl.staged() && !a_ll.staged() &&
+      !a_lu.staged() &&
+      tau_absorption_gfast(ncol, nlay, nbnd, ngpt, ngas, nflav, neta, npres, ntemp, nminorlower, nminorklower, nminorupper,
+                           nminorkupper, idx_h2o, a_gf, a_bl, a_km, a_kl, a_ku, a_ll, a_lu, a_sdl, a_sdu, a_scl, a_scu, a_iml,
+                           a_imu, a_isl, a_isu, a_ksl, a_ksu, a_tr, a_cm, a_fj, a_fn, a_pl, a_tl, a_cg, a_je, a_jt, a_jp,
+                           a_tau, accumulate))
+    return;
   TauAbsParams p;
   p.ncol = ncol; p.nlay = nlay; p.nbnd = nbnd; p.ngpt = ngpt; p.ngas = ngas; p.nflav = nflav; p.neta = neta;
   p.npres = npres; p.ntemp = ntemp; p.idx_h2o = idx_h2o;
@@ -632,6 +645,12 @@ void rrtmgp_compute_Planck_source(const int* ncol, const int* nlay, const int* n
   DevArg<Bool> a_tr(tropo, ncl, Dir::In);
   DevArg<Float> o_sfc(sfc_src, nc * ng, Dir::Out), o_lay(lay_src, ncl * ng, Dir::Out),
       o_lev(lev_src, nclp * ng, Dir::Out), o_jac(sfc_source_Jac, nc * ng, Dir::Out);
+  static const bool gfast_env = [] { const char* e = std::getenv("RRTMGPB_ABI_GFAST"); return !(e && e[0] == '0'); }();
+  if (gfast_env && !a_pf.staged() && !a_tp.staged() && !a_bl.staged() && !a_gf.staged() &&
+      planck_source_gfast(*ncol, *nlay, *nbnd, *ngpt, *nflav, *neta, *npres, *ntemp, *nPlanckTemp, a_tl, a_tv, a_ts, *sfc_lay,
+                          a_fj, a_je, a_tr, a_jt, a_jp, a_bl, a_pf, *temp_ref_min, *totplnk_delta, a_tp, a_gf, o_sfc, o_lay,
+                          o_lev, o_jac))
+    return;
   PlanckParams p;
   p.ncol = *ncol; p.nlay = *nlay; p.nbnd = *nbnd; p.ngpt = *ngpt; p.nflav = *nflav; p.neta = *neta; p.npres = *npres;
   p.ntemp = *ntemp; p.nPlanckTemp = *nPlanckTemp; p.sfc_lay = *sfc_lay;

@@ -121,7 +121,10 @@ void table_sources(const rrtmgpb_gas_tables& t, const void* (&src)[16]) {
   for (int i = 0; i < 16; ++i) src[i] = v[i];
 }
 std::mutex g_tc_mutex;
-std::map<const void*, TableCacheEntry> g_table_cache;  // key: the loader-layout kmajor pointer
+// key: the loader-layout kmajor pointer (the Planck-only entry of the extern symbols: its pfracin pointer).  Slot 0: the
+// fused path (complete table sets); slot 1: sets assembled from the arguments of the extern symbols (no flavor / vmr_ref:
+// the interpolation weights arrive as arrays), kept apart so that a host alternating between both does not evict
+std::map<const void*, TableCacheEntry> g_table_cache_slots[2];
 
 void transpose_into(const Float* in, Float* out, int nrow, int ng, int pitch) {
   dim3 grid(ceil_div(nrow, 32), ceil_div(ng, 32)), block(32, 8);
@@ -177,9 +180,11 @@ MinorHost minor_host(int n, const int* lim, const int* idx, const int* isc, cons
   return m;
 }
 
-TablesT tables_gfast(const rrtmgpb_gas_tables& t) {
+TablesT tables_gfast(const rrtmgpb_gas_tables& t, int slot = 0) {
   std::lock_guard<std::mutex> lock(g_tc_mutex);
-  auto it = g_table_cache.find(t.kmajor);
+  std::map<const void*, TableCacheEntry>& g_table_cache = g_table_cache_slots[slot];
+  const void* key = t.kmajor ? static_cast<const void*>(t.kmajor) : static_cast<const void*>(t.planck_frac);
+  auto it = g_table_cache.find(key);
   if (it != g_table_cache.end()) {
     const TableCacheEntry& e = it->second;
     const void* src[16];
@@ -209,8 +214,10 @@ TablesT tables_gfast(const rrtmgpb_gas_tables& t) {
   // ---- small records, resolved on the host ----
   const std::vector<int> bl = to_host(t.band_lims_gpt, 2 * (size_t)t.nbnd);
   const std::vector<int> gf = to_host(t.gpoint_flavor, 2 * (size_t)t.ngpt);
-  const std::vector<int> fl = to_host(t.flavor, 2 * (size_t)t.nflav);
-  const std::vector<Float> vr = to_host(t.vmr_ref, 2 * (size_t)(t.ngas + 1) * t.ntemp);
+  // (extern-symbol table sets carry no flavor / vmr_ref: the records derived from them are only read by the fused path)
+  const std::vector<int> fl = t.flavor ? to_host(t.flavor, 2 * (size_t)t.nflav) : std::vector<int>(2 * (size_t)t.nflav, 0);
+  const std::vector<Float> vr = t.vmr_ref ? to_host(t.vmr_ref, 2 * (size_t)(t.ngas + 1) * t.ntemp)
+                                          : std::vector<Float>(2 * (size_t)(t.ngas + 1) * t.ntemp, (Float)1);
   const MinorHost mh[2] = {
       minor_host(t.nminorlower, t.minor_limits_gpt_lower, t.idx_minor_lower, t.idx_minor_scaling_lower, t.kminor_start_lower,
                  t.minor_scales_with_density_lower, t.scale_by_complement_lower),
@@ -268,7 +275,8 @@ TablesT tables_gfast(const rrtmgpb_gas_tables& t) {
   tt.aux.ratio = to_device(ratio, e.owned);
   tt.vec = (sizeof(Float) == 8 && intervals_even(bl, nullptr) && intervals_even(mh[0].lim, &mh[0].ks) &&
             intervals_even(mh[1].lim, &mh[1].ks)) ? 2 : 1;
-  g_table_cache[t.kmajor] = e;
+  RB_CUDA_CHECK(cudaStreamSynchronize(stream()));  // other host threads (other streams) may use the copies next
+  g_table_cache[key] = e;
   return e.tt;
 }
 
@@ -326,10 +334,12 @@ namespace rrtmgpb {
 // called by rrtmgpb_mem_free(): a k-distribution that is being released takes its transposed copies with it
 void table_cache_release(const void* key) {
   std::lock_guard<std::mutex> lock(g_tc_mutex);
-  auto it = g_table_cache.find(key);
-  if (it == g_table_cache.end()) return;
-  for (void* q : it->second.owned) dev_free(q);
-  g_table_cache.erase(it);
+  for (auto& g_table_cache : g_table_cache_slots) {
+    auto it = g_table_cache.find(key);
+    if (it == g_table_cache.end()) continue;
+    for (void* q : it->second.owned) dev_free(q);
+    g_table_cache.erase(it);
+  }
 }
 void table_cache_release_abi(const void* key) {
   std::lock_guard<std::mutex> lock(g_tc_mutex);
@@ -348,20 +358,22 @@ extern "C" void rrtmgpb_tables_changed(const void* kmajor) {
     return;
   }
   std::lock_guard<std::mutex> lock(g_tc_mutex);
-  for (auto& kv : g_table_cache) for (void* q : kv.second.owned) dev_free(q);
+  for (auto& g_table_cache : g_table_cache_slots) {
+    for (auto& kv : g_table_cache) for (void* q : kv.second.owned) dev_free(q);
+    g_table_cache.clear();
+  }
   for (auto& kv : g_abi_cache) for (void* q : kv.second.owned) dev_free(q);
-  g_table_cache.clear();
   g_abi_cache.clear();
 }
 
 namespace {
 // gas_tau_g_kernel for the bands p.band0 .. p.band0 + p.nband_sub - 1
-void launch_tau(const FusedParams& p, const TablesT& tt) {
+void launch_tau(const FusedParams& p, const TablesT& tt, bool abi = false) {
   const rrtmgpb_gas_tables* t = &p.t;
   const size_t ncl = (size_t)p.ncol * p.nlay;
   const bool sw = t->krayl != nullptr;
   const int op_kind = p.op_kind, cld_kind = p.cld_kind, aer_kind = p.aer_kind;
-  KernelTimer timer(sw ? "gas_tau_fused[sw]" : "gas_tau_fused[lw]");
+  KernelTimer timer(abi ? "tau_absorption" : (sw ? "gas_tau_fused[sw]" : "gas_tau_fused[lw]"));
   const unsigned grid = (unsigned)((long long)ceil_div((long long)ncl, kTauCells * kGThreads) * p.nband_sub);
   // lane-private slots for the per-(cell, band) minor scalings: [contributor][cell slot][thread]
   size_t smem = (size_t)tt.maxm * kTauCells * kGThreads * sizeof(Float);
@@ -382,7 +394,18 @@ void launch_tau(const FusedParams& p, const TablesT& tt) {
   if (aer_kind) GAS_TAU_LAUNCH1(SWV, VECV, true, 0);                                                  \
   else if (op_kind == (SWV ? 2 : 1) && cld_kind == (SWV ? 2 : 1)) GAS_TAU_LAUNCH1(SWV, VECV, false, 1); \
   else GAS_TAU_LAUNCH1(SWV, VECV, false, 0)
-  if (sw) {
+  if (abi) {  // absorption only, the interpolation state from the caller's arrays (extern symbol rrtmgp_compute_tau_absorption)
+#define GAS_TAU_LAUNCH_ABI(VECV, STGV)                                                                            \
+  do {                                                                                                            \
+    auto kern = gas_tau_g_kernel<false, VECV, false, 0, STGV, true>;                                              \
+    if (smem > 48 * 1024) RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, kGThreads, smem, stream()>>>(p, tt);                                                             \
+  } while (0)
+    if (tt.vec == 2 && stage) GAS_TAU_LAUNCH_ABI(2, true);
+    else if (tt.vec == 2) GAS_TAU_LAUNCH_ABI(2, false);
+    else GAS_TAU_LAUNCH_ABI(1, false);
+#undef GAS_TAU_LAUNCH_ABI
+  } else if (sw) {
     if (tt.vec == 2) { GAS_TAU_LAUNCH(true, 2); } else { GAS_TAU_LAUNCH(true, 1); }
   } else {
     if (tt.vec == 2) { GAS_TAU_LAUNCH(false, 2); } else { GAS_TAU_LAUNCH(false, 1); }
@@ -392,18 +415,110 @@ void launch_tau(const FusedParams& p, const TablesT& tt) {
   RB_LAUNCH_CHECK();
 }
 
-void launch_planck(const PlanckFusedParams& q, const TablesT& tt) {
-  KernelTimer timer("planck_fused");
+void launch_planck(const PlanckFusedParams& q, const TablesT& tt, bool abi = false) {
+  KernelTimer timer(abi ? "planck_source" : "planck_fused");
   // layers a thread marches through (its first level needs the Planck fractions of the layer above: 1/lay_per_chunk
   // redundant work; B200, 65,536 x 72: 9 -> 5.40 ms, 12 -> 5.31, 18 -> 5.24, 36 -> 5.22); RRTMGPB_PLANCK_CHUNK overrides
   static const int chunk_env = [] { const char* e = std::getenv("RRTMGPB_PLANCK_CHUNK"); return e ? std::atoi(e) : 0; }();
   const int lay_per_chunk = chunk_env > 0 ? chunk_env : 18, nchunk = ceil_div(q.f.nlay, lay_per_chunk);
   const unsigned grid = (unsigned)((long long)ceil_div(q.f.ncol, kGThreads) * nchunk * q.f.nband_sub);
-  if (tt.vec == 2) planck_g_kernel<2><<<grid, kGThreads, 0, stream()>>>(q, tt, lay_per_chunk, nchunk);
+  if (abi) {
+    if (tt.vec == 2) planck_g_kernel<2, true><<<grid, kGThreads, 0, stream()>>>(q, tt, lay_per_chunk, nchunk);
+    else planck_g_kernel<1, true><<<grid, kGThreads, 0, stream()>>>(q, tt, lay_per_chunk, nchunk);
+  } else if (tt.vec == 2) planck_g_kernel<2><<<grid, kGThreads, 0, stream()>>>(q, tt, lay_per_chunk, nchunk);
   else planck_g_kernel<1><<<grid, kGThreads, 0, stream()>>>(q, tt, lay_per_chunk, nchunk);
   RB_LAUNCH_CHECK();
 }
 }  // namespace
+
+// ---- the extern symbols' tau_absorption / Planck_source on the g-point-fastest kernels (ABI instantiations) ----
+namespace {
+// the three per-cell factors of the minor scaling (:467-471) from the caller's play, tlay, col_gas
+__global__ void __launch_bounds__(kFThreads) abi_cell_prep_kernel(size_t ncl, int idx_h2o, const Float* __restrict__ play,
+                                                                   const Float* __restrict__ tlay, const Float* __restrict__ col_gas,
+                                                                   Float* pt_scale, Float* vmr_fact, Float* dry_fact) {
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncl) return;
+  const Float vf = (Float)1 / col_gas[c];                                        // :470, col_gas(:,:,0) = col_dry
+  pt_scale[c] = (Float)0.01 * play[c] / tlay[c];                                 // :467
+  vmr_fact[c] = vf;
+  dry_fact[c] = (Float)1 / ((Float)1 + col_gas[c + ncl * (size_t)idx_h2o] * vf); // :471
+}
+}  // namespace
+
+namespace rrtmgpb {
+// All array arguments are DEVICE pointers (the callers have classified / staged them).  Returns false when the caller has
+// not allowed cached table copies (rrtmgpb_abi_table_cache) - the loader-layout kernels of gas_optics_abi.cu run then.
+bool tau_absorption_gfast(int ncol, int nlay, int nbnd, int ngpt, int ngas, int nflav, int neta, int npres, int ntemp,
+                          int nminorlower, int nminorklower, int nminorupper, int nminorkupper, int idx_h2o,
+                          const int* gpoint_flavor, const int* band_lims_gpt, const Float* kmajor, const Float* kminor_lower,
+                          const Float* kminor_upper, const int* minor_limits_gpt_lower, const int* minor_limits_gpt_upper,
+                          const Bool* minor_scales_with_density_lower, const Bool* minor_scales_with_density_upper,
+                          const Bool* scale_by_complement_lower, const Bool* scale_by_complement_upper,
+                          const int* idx_minor_lower, const int* idx_minor_upper, const int* idx_minor_scaling_lower,
+                          const int* idx_minor_scaling_upper, const int* kminor_start_lower, const int* kminor_start_upper,
+                          const Bool* tropo, const Float* col_mix, const Float* fmajor, const Float* fminor, const Float* play,
+                          const Float* tlay, const Float* col_gas, const int* jeta, const int* jtemp, const int* jpress,
+                          Float* tau, bool accumulate) {
+  if (!g_abi_cache_on) return false;
+  rrtmgpb_gas_tables t{};
+  t.ngas = ngas; t.nflav = nflav; t.neta = neta; t.npres = npres; t.ntemp = ntemp; t.nbnd = nbnd; t.ngpt = ngpt;
+  t.nminorlower = nminorlower; t.nminorupper = nminorupper; t.nminorklower = nminorklower; t.nminorkupper = nminorkupper;
+  t.idx_h2o = idx_h2o; t.gpoint_flavor = gpoint_flavor; t.band_lims_gpt = band_lims_gpt; t.kmajor = kmajor;
+  t.kminor_lower = kminor_lower; t.kminor_upper = kminor_upper; t.minor_limits_gpt_lower = minor_limits_gpt_lower;
+  t.minor_limits_gpt_upper = minor_limits_gpt_upper; t.minor_scales_with_density_lower = minor_scales_with_density_lower;
+  t.minor_scales_with_density_upper = minor_scales_with_density_upper; t.scale_by_complement_lower = scale_by_complement_lower;
+  t.scale_by_complement_upper = scale_by_complement_upper; t.idx_minor_lower = idx_minor_lower; t.idx_minor_upper = idx_minor_upper;
+  t.idx_minor_scaling_lower = idx_minor_scaling_lower; t.idx_minor_scaling_upper = idx_minor_scaling_upper;
+  t.kminor_start_lower = kminor_start_lower; t.kminor_start_upper = kminor_start_upper;
+  const TablesT tt = tables_gfast(t, 1);
+  const size_t ncl = (size_t)ncol * nlay;
+  Float* prep = static_cast<Float*>(dev_alloc(3 * ncl * sizeof(Float)));
+  {
+    KernelTimer timer("tau_absorption_cell_prep");
+    abi_cell_prep_kernel<<<ceil_div((long long)ncl, kFThreads), kFThreads, 0, stream()>>>(ncl, idx_h2o, play, tlay, col_gas, prep,
+                                                                                             prep + ncl, prep + 2 * ncl);
+    RB_LAUNCH_CHECK();
+  }
+  FusedParams p{};
+  p.t = t;
+  p.ncol = ncol; p.nlay = nlay; p.band0 = 0; p.nband_sub = nbnd; p.gpt0 = 0;
+  p.play = play; p.tlay = tlay;
+  p.cs.col_dry = const_cast<Float*>(col_gas);   // slice 0 of col_gas(ncol,nlay,0:ngas); read-only in the ABI instantiations
+  p.cs.pt_scale = prep; p.cs.vmr_fact = prep + ncl; p.cs.dry_fact = prep + 2 * ncl;
+  p.cs.jtemp = const_cast<int*>(jtemp); p.cs.jpress = const_cast<int*>(jpress); p.cs.tropo = const_cast<Bool*>(tropo);
+  p.op_kind = 1; p.tau = tau; p.cld_kind = 0; p.aer_kind = 0;
+  p.abi_col_gas = col_gas; p.abi_col_mix = col_mix; p.abi_fmajor = fmajor; p.abi_fminor = fminor; p.abi_jeta = jeta;
+  p.accumulate = accumulate ? 1 : 0;
+  launch_tau(p, tt, /*abi=*/true);
+  dev_free(prep);
+  return true;
+}
+
+bool planck_source_gfast(int ncol, int nlay, int nbnd, int ngpt, int nflav, int neta, int npres, int ntemp, int nPlanckTemp,
+                         const Float* tlay, const Float* tlev, const Float* tsfc, int sfc_lay, const Float* fmajor,
+                         const int* jeta, const Bool* tropo, const int* jtemp, const int* jpress, const int* band_lims_gpt,
+                         const Float* pfracin, Float temp_ref_min, Float totplnk_delta, const Float* totplnk,
+                         const int* gpoint_flavor, Float* sfc_src, Float* lay_src, Float* lev_src, Float* sfc_source_Jac) {
+  if (!g_abi_cache_on) return false;
+  rrtmgpb_gas_tables t{};
+  t.nflav = nflav; t.neta = neta; t.npres = npres; t.ntemp = ntemp; t.nbnd = nbnd; t.ngpt = ngpt;
+  t.gpoint_flavor = gpoint_flavor; t.band_lims_gpt = band_lims_gpt; t.planck_frac = pfracin; t.totplnk = totplnk;
+  t.nPlanckTemp = nPlanckTemp; t.totplnk_delta = totplnk_delta; t.temp_ref_min = temp_ref_min;
+  const TablesT tt = tables_gfast(t, 1);
+  PlanckFusedParams q{};
+  FusedParams& p = q.f;
+  p.t = t;
+  p.ncol = ncol; p.nlay = nlay; p.band0 = 0; p.nband_sub = nbnd; p.gpt0 = 0;
+  p.tlay = tlay;
+  p.cs.jtemp = const_cast<int*>(jtemp); p.cs.jpress = const_cast<int*>(jpress); p.cs.tropo = const_cast<Bool*>(tropo);
+  p.abi_fmajor = fmajor; p.abi_jeta = jeta;
+  q.tlev = tlev; q.tsfc = tsfc; q.sfc_lay = sfc_lay;
+  q.sfc_src = sfc_src; q.lay_src = lay_src; q.lev_src = lev_src; q.sfc_source_Jac = sfc_source_Jac;
+  launch_planck(q, tt, /*abi=*/true);
+  return true;
+}
+}  // namespace rrtmgpb
 
 extern "C" {
 

@@ -66,6 +66,23 @@ void table_cache_release(const void* key);            // gas_optics_fused.cu: dr
 void table_cache_release_abi(const void* key);
 // g-point-fastest copies of kmajor / kminor_* for the kernel-by-kernel ABI entry points; false: not available
 // (cache switched off, see rrtmgpb_abi_table_cache)
+// the extern symbols' tau_absorption / Planck source on the g-point-fastest kernels (gas_optics_fused.cu); device pointers
+bool tau_absorption_gfast(int ncol, int nlay, int nbnd, int ngpt, int ngas, int nflav, int neta, int npres, int ntemp,
+                          int nminorlower, int nminorklower, int nminorupper, int nminorkupper, int idx_h2o,
+                          const int* gpoint_flavor, const int* band_lims_gpt, const Float* kmajor, const Float* kminor_lower,
+                          const Float* kminor_upper, const int* minor_limits_gpt_lower, const int* minor_limits_gpt_upper,
+                          const Bool* minor_scales_with_density_lower, const Bool* minor_scales_with_density_upper,
+                          const Bool* scale_by_complement_lower, const Bool* scale_by_complement_upper,
+                          const int* idx_minor_lower, const int* idx_minor_upper, const int* idx_minor_scaling_lower,
+                          const int* idx_minor_scaling_upper, const int* kminor_start_lower, const int* kminor_start_upper,
+                          const Bool* tropo, const Float* col_mix, const Float* fmajor, const Float* fminor, const Float* play,
+                          const Float* tlay, const Float* col_gas, const int* jeta, const int* jtemp, const int* jpress,
+                          Float* tau, bool accumulate);
+bool planck_source_gfast(int ncol, int nlay, int nbnd, int ngpt, int nflav, int neta, int npres, int ntemp, int nPlanckTemp,
+                         const Float* tlay, const Float* tlev, const Float* tsfc, int sfc_lay, const Float* fmajor,
+                         const int* jeta, const Bool* tropo, const int* jtemp, const int* jpress, const int* band_lims_gpt,
+                         const Float* pfracin, Float temp_ref_min, Float totplnk_delta, const Float* totplnk,
+                         const int* gpoint_flavor, Float* sfc_src, Float* lay_src, Float* lev_src, Float* sfc_source_Jac);
 bool tables_gfast_abi(const Float* kmajor, const Float* kminor_lower, const Float* kminor_upper, int ntemp, int neta,
                       int npres, int ngpt, int nkl, int nku, const Float** kmajorT, const Float** kminorT_lower,
                       const Float** kminorT_upper, int* gp, int* pitch_lower, int* pitch_upper);

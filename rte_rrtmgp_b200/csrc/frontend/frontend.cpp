@@ -670,11 +670,13 @@ int rrtmgpb_gas_optics_int(const rrtmgpb_gas_optics_t* go, int ncol, int nlay, c
     tlev_wk = tlev_alloc;
   }
   const int sfc_lay = op->top_at_1 ? nlay : 1;  // :920 merge(nlay, 1, top_at_1)
+  rrtmgpb_abi_table_cache(1);   // immutable tables, released through rrtmgpb_mem_free (see tau_abs above)
   rrtmgp_compute_Planck_source(&ncol, &nlay, &nband, &ngpt, &k.nflav, &k.neta, &k.npres, &k.ntemp, &k.nPlanckTemp, tlay,
                                tlev_wk, tsfc, &sfc_lay, s.fmajor, s.jeta, s.tropo, s.jtemp, s.jpress, go->gpoint_bands,
                                go->band_lims_gpt, go->planck_frac, &k.temp_ref_min, &k.totplnk_delta, go->totplnk,
                                go->gpoint_flavor, sources->sfc_source, sources->lay_source, sources->lev_source,
                                sources->sfc_source_Jac);
+  rrtmgpb_abi_table_cache(0);
   rrtmgpb_mem_free(tlev_alloc);
   return ok(errmsg);
 }

@@ -81,6 +81,13 @@ struct FusedParams {
   // optional second by-band increment applied after the cloud one (aerosols), same kinds
   int aer_kind;
   const Float *aer_tau, *aer_ssa, *aer_g;
+  // ABI instantiations (rrtmgp_compute_tau_absorption / rrtmgp_compute_Planck_source through the extern symbols): the
+  // interpolation state arrives as the arrays rrtmgp_interpolation wrote - col_mix(2,ncol,nlay,nflav),
+  // fmajor(2,2,2,ncol,nlay,nflav), fminor(2,2,ncol,nlay,nflav), jeta(2,ncol,nlay,nflav) - and the gas amounts as
+  // col_gas(ncol,nlay,0:ngas); cs.jtemp / jpress / tropo point at the caller's arrays, cs.col_dry at col_gas(:,:,0)
+  const Float *abi_col_gas = nullptr, *abi_col_mix = nullptr, *abi_fmajor = nullptr, *abi_fminor = nullptr;
+  const int* abi_jeta = nullptr;
+  int accumulate = 0;   // tau = tau + result: the extern symbol's semantics (the frontend zeroes tau first, :391)
 };
 
 struct PlanckFusedParams {
@@ -107,7 +114,9 @@ struct FlavW {
 };
 
 // col_gas(igas) = igas == 0 ? col_dry : vmr(igas)*col_dry   (mo_gas_optics_rrtmgp.F90:594-609)
+template <bool ABI = false>
 __device__ __forceinline__ Float col_gas_of(const FusedParams& p, size_t c, size_t ncl, int igas, Float col_dry) {
+  if (ABI) return p.abi_col_gas[c + ncl * (size_t)igas];
   return igas == 0 ? col_dry : p.vmr[c + ncl * (size_t)(igas - 1)] * col_dry;
 }
 
@@ -138,6 +147,22 @@ __device__ __forceinline__ void flavor_weights_g(const FusedParams& p, size_t c,
     w.fmj[4 * it + 2] = fpress * w.fmn[2 * it + 0];
     w.fmj[4 * it + 3] = fpress * w.fmn[2 * it + 1];
   }
+}
+
+// ABI instantiations: the same weights read from the arrays rrtmgp_interpolation wrote (flat orders: col_mix it;
+// fmajor ie + 2*ip + 4*it = FlavW::fmj's; fminor ie + 2*it = FlavW::fmn's; jeta it), 16- / 8-byte aligned (DevArg)
+__device__ __forceinline__ void abi_load_weights(const FusedParams& p, size_t c, size_t ncl, int iflav, FlavW& w) {
+  const size_t cf = c + ncl * (size_t)iflav;
+  const Float2 cm = reinterpret_cast<const Float2*>(p.abi_col_mix)[cf];
+  w.cm[0] = cm.x; w.cm[1] = cm.y;
+  const Float2* fj = reinterpret_cast<const Float2*>(p.abi_fmajor) + 4 * cf;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { const Float2 v = fj[q]; w.fmj[2 * q] = v.x; w.fmj[2 * q + 1] = v.y; }
+  const Float2* fn = reinterpret_cast<const Float2*>(p.abi_fminor) + 2 * cf;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) { const Float2 v = fn[q]; w.fmn[2 * q] = v.x; w.fmn[2 * q + 1] = v.y; }
+  const int2 je = reinterpret_cast<const int2*>(p.abi_jeta)[cf];
+  w.je[0] = je.x; w.je[1] = je.y;
 }
 
 // VEC consecutive table entries starting at p (16-byte aligned when VEC == 2)
@@ -232,14 +257,15 @@ struct TauCell {
 
 // scaling of one minor contributor at cell c (:461-480): col_gas(minor) [* 0.01 p/T [* vmr of the scaling gas or its
 // complement]]
+template <bool ABI = false>
 __device__ __forceinline__ Float minor_scaling(const FusedParams& p, const MinorInfo& mi, size_t c, size_t ncl, Float col_dry) {
-  Float sc = col_gas_of(p, c, ncl, mi.igas, col_dry);
+  Float sc = col_gas_of<ABI>(p, c, ncl, mi.igas, col_dry);
   if (mi.dens) {
     sc = sc * p.cs.pt_scale[c];
     if (mi.isc > 0) {
       const Float vmr_fact = p.cs.vmr_fact[c], dry_fact = p.cs.dry_fact[c];
-      if (mi.comp) sc = sc * ((Float)1 - col_gas_of(p, c, ncl, mi.isc, col_dry) * vmr_fact * dry_fact);
-      else sc = sc * (col_gas_of(p, c, ncl, mi.isc, col_dry) * vmr_fact * dry_fact);
+      if (mi.comp) sc = sc * ((Float)1 - col_gas_of<ABI>(p, c, ncl, mi.isc, col_dry) * vmr_fact * dry_fact);
+      else sc = sc * (col_gas_of<ABI>(p, c, ncl, mi.isc, col_dry) * vmr_fact * dry_fact);
     }
   }
   return sc;
@@ -253,7 +279,7 @@ __device__ __forceinline__ Float minor_scaling(const FusedParams& p, const Minor
 // tau*ssa*0 + 0*cw*cg is exactly 0), tau unchanged - one division per value instead of three.
 // STG: the band's table rows were staged to shared memory by the block (regular bands only): stg = [8 major rows: x0..x3,
 // y0..y3][16 g-points], then [contributor][4 rows: m0, m0+eta, m1, m1+eta][16 g-points]
-template <bool SW, int VEC, int NC, bool AER, int KIND, bool CLD = true, bool STG = false>
+template <bool SW, int VEC, int NC, bool AER, int KIND, bool CLD = true, bool STG = false, bool ABI = false>
 __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const TablesT& tt, const BandInfo& bi, bool tropo,
                                                int jtemp, int row0, int row1, TauCell (&cell)[NC], const Float* scal,
                                                const Float* stg = nullptr) {
@@ -319,8 +345,9 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
       if (!REG && NC == 1 && mi.iflav != iflav) {
         FlavW wm;
         const size_t c = cell[0].c;
-        flavor_weights_g(p, c, ncl, mi.igas1, mi.igas2, tt.aux.ratio + (size_t)(itropo * t.nflav + mi.iflav) * t.ntemp, jtemp,
-                         p.cs.ftemp[c], p.cs.fpress[c], cell[0].col_dry, wm);
+        if (ABI) abi_load_weights(p, c, ncl, mi.iflav, wm);
+        else flavor_weights_g(p, c, ncl, mi.igas1, mi.igas2, tt.aux.ratio + (size_t)(itropo * t.nflav + mi.iflav) * t.ntemp, jtemp,
+                              p.cs.ftemp[c], p.cs.fpress[c], cell[0].col_dry, wm);
 #pragma unroll
         for (int q = 0; q < 4; ++q) am[0][q] = wm.fmn[q];
         jm0 = wm.je[0]; jm1 = wm.je[1];
@@ -377,7 +404,7 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
         };
         inc1(cld_kind, cell[k].ct, cell[k].cw);
         if (AER) inc1(p.aer_kind, cell[k].at, cell[k].aw);
-        if (cell[k].valid) p.tau[o] = to;
+        if (cell[k].valid) p.tau[o] = (ABI && p.accumulate) ? p.tau[o] + to : to;
       } else {
         auto inc2 = [&](int kind, Float ct, Float cw, Float cg) {
           if (KIND == 1 && !CLD && !AER) {                     // ct == 0: tau12 = to, tauscat12 = to*ss, g stays 0
@@ -445,7 +472,7 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
 // warp's mbarrier) and the warp reads them from there: immediate-offset LDS instead of LDG with 64-bit row addresses, at
 // shared-memory latency.  Measured on B200: LW tau 5.18 -> 4.33 ms at 65,536 x 72 x 256 (block-wide
 // variant).  Warps whose cells differ take the L1 path below.  RRTMGPB_TABLE_TMA=0 switches it off.
-template <bool SW, int VEC, bool AER, int KIND, bool STAGE = false>
+template <bool SW, int VEC, bool AER, int KIND, bool STAGE = false, bool ABI = false>
 __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_LW) gas_tau_g_kernel(const FusedParams p, const TablesT tt) {
   const rrtmgpb_gas_tables& t = p.t;
   const size_t ncl = (size_t)p.ncol * p.nlay;
@@ -472,15 +499,16 @@ __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_L
     const size_t c = ce.valid ? craw : cbase;  // out-of-range slots shadow the thread's first cell, never store
     ce.c = c;
     ce.col_dry = p.cs.col_dry[c];
-    const Float ftemp = p.cs.ftemp[c], fpress = p.cs.fpress[c];
     jtemp[k] = p.cs.jtemp[c];
     tropo[k] = p.cs.tropo[c];
     const int itropo = tropo[k] ? 0 : 1;
     const int jpress = p.cs.jpress[c] + itropo + 1;  // :390
     // (explicit selects: indexing the register copy of BandInfo with a run-time itropo would push it to local memory)
     const int iflav = tropo[k] ? bi.iflav[0] : bi.iflav[1];
-    flavor_weights_g(p, c, ncl, tropo[k] ? bi.igas1[0] : bi.igas1[1], tropo[k] ? bi.igas2[0] : bi.igas2[1],
-                     tt.aux.ratio + (size_t)(itropo * t.nflav + iflav) * t.ntemp, jtemp[k], ftemp, fpress, ce.col_dry, ce.w);
+    if (ABI) abi_load_weights(p, c, ncl, iflav, ce.w);
+    else flavor_weights_g(p, c, ncl, tropo[k] ? bi.igas1[0] : bi.igas1[1], tropo[k] ? bi.igas2[0] : bi.igas2[1],
+                          tt.aux.ratio + (size_t)(itropo * t.nflav + iflav) * t.ntemp, jtemp[k], p.cs.ftemp[c], p.cs.fpress[c],
+                          ce.col_dry, ce.w);
     row0[k] = (jtemp[k] - 1) + s_eta * (ce.w.je[0] - 1) + s_p * (jpress - 2);
     row1[k] = jtemp[k] + s_eta * (ce.w.je[1] - 1) + s_p * (jpress - 2);
     // cloud properties of this (cell, band), if the caller wants them added (mo_optical_props.F90:956-1000)
@@ -502,7 +530,7 @@ __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_L
       const MinorInfo* minfo = tropo[k] ? tt.aux.minor_lower : tt.aux.minor_upper;
       const int mfirst = tropo[k] ? bi.mfirst[0] : bi.mfirst[1], mlast = tropo[k] ? bi.mlast[0] : bi.mlast[1];
       for (int imnr = mfirst; imnr <= mlast; ++imnr)
-        scal[((imnr - mfirst) * kTauCells + k) * kGThreads] = minor_scaling(p, minfo[imnr], c, ncl, ce.col_dry);
+        scal[((imnr - mfirst) * kTauCells + k) * kGThreads] = minor_scaling<ABI>(p, minfo[imnr], c, ncl, ce.col_dry);
     }
   }
   bool shared_rows = true;
@@ -577,22 +605,22 @@ __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_L
           "{\n.reg .pred P1;\nWAIT_STG:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n@P1 bra DONE_STG;\nbra WAIT_STG;\nDONE_STG:\n}\n" ::"r"(bar)
           : "memory");
       if (SW && KIND == 1 && !AER && !cloudy)
-        tau_band_cells<SW, VEC, kTauCells, AER, KIND, false, true>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell, scal, stg);
+        tau_band_cells<SW, VEC, kTauCells, AER, KIND, false, true, ABI>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell, scal, stg);
       else
-        tau_band_cells<SW, VEC, kTauCells, AER, KIND, true, true>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell, scal, stg);
+        tau_band_cells<SW, VEC, kTauCells, AER, KIND, true, true, ABI>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell, scal, stg);
       return;
     }
   }
   if (shared_rows && SW && KIND == 1 && !AER && !cloudy) {
-    tau_band_cells<SW, VEC, kTauCells, AER, KIND, false>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell, scal);
+    tau_band_cells<SW, VEC, kTauCells, AER, KIND, false, false, ABI>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell, scal);
   } else if (shared_rows) {
-    tau_band_cells<SW, VEC, kTauCells, AER, KIND>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell, scal);
+    tau_band_cells<SW, VEC, kTauCells, AER, KIND, true, false, ABI>(p, tt, bi, tropo[0], jtemp[0], row0[0], row1[0], cell, scal);
   } else {
 #pragma unroll
     for (int k = 0; k < kTauCells; ++k) {
       if (!cell[k].valid) continue;
       TauCell one[1] = {cell[k]};
-      tau_band_cells<SW, VEC, 1, AER, KIND>(p, tt, bi, tropo[k], jtemp[k], row0[k], row1[k], one, scal);
+      tau_band_cells<SW, VEC, 1, AER, KIND, true, false, ABI>(p, tt, bi, tropo[k], jtemp[k], row0[k], row1[k], one, scal);
     }
   }
 }
@@ -614,6 +642,7 @@ __device__ __forceinline__ Float planck_band_f(const rrtmgpb_gas_tables& t, Floa
 constexpr int kPG = RB_PLANCK_PG * kGG;  // g-points per pass of the Planck kernel (previous layer's fractions stay in registers)
 
 // interpolation weights and table rows of band `bi` at cell c (:121-168, :390)
+template <bool ABI = false>
 __device__ __forceinline__ void planck_cell_weights(const FusedParams& p, const TablesT& tt, const BandInfo& bi, size_t c,
                                                     size_t ncl, FlavW& w, int& row0, int& row1) {
   const rrtmgpb_gas_tables& t = p.t;
@@ -621,6 +650,14 @@ __device__ __forceinline__ void planck_cell_weights(const FusedParams& p, const 
   const int itropo = tropo ? 0 : 1;
   const int jtemp = p.cs.jtemp[c];
   const int jpress = p.cs.jpress[c] + itropo + 1;
+  if (ABI) {  // fmajor and jeta as rrtmgp_interpolation wrote them (only these two are used below)
+    const size_t cf = c + ncl * (size_t)(tropo ? bi.iflav[0] : bi.iflav[1]);
+    const Float2* fj = reinterpret_cast<const Float2*>(p.abi_fmajor) + 4 * cf;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const Float2 v = fj[q]; w.fmj[2 * q] = v.x; w.fmj[2 * q + 1] = v.y; }
+    const int2 je = reinterpret_cast<const int2*>(p.abi_jeta)[cf];
+    w.je[0] = je.x; w.je[1] = je.y;
+  } else
   flavor_weights_g(p, c, ncl, tropo ? bi.igas1[0] : bi.igas1[1], tropo ? bi.igas2[0] : bi.igas2[1],
                    tt.aux.ratio + (size_t)(itropo * t.nflav + (tropo ? bi.iflav[0] : bi.iflav[1])) * t.ntemp, jtemp,
                    p.cs.ftemp[c], p.cs.fpress[c], p.cs.col_dry[c], w);
@@ -643,7 +680,7 @@ __device__ __forceinline__ void planck_fractions(const FusedParams& p, const Tab
 #ifndef RB_PLANCK_MINB
 #define RB_PLANCK_MINB 4
 #endif
-template <int VEC>
+template <int VEC, bool ABI = false>
 __global__ void __launch_bounds__(kGThreads, RB_PLANCK_MINB) planck_g_kernel(const PlanckFusedParams q, const TablesT tt, int lay_per_chunk,
                                                                 int nchunk) {
   const FusedParams& p = q.f;
@@ -665,7 +702,7 @@ __global__ void __launch_bounds__(kGThreads, RB_PLANCK_MINB) planck_g_kernel(con
     if (l0 > 0) {  // the chunk's first level also needs the layer above it
       FlavW w;
       int row0, row1;
-      planck_cell_weights(p, tt, bi, icol + ncol * (size_t)(l0 - 1), ncl, w, row0, row1);
+      planck_cell_weights<ABI>(p, tt, bi, icol + ncol * (size_t)(l0 - 1), ncl, w, row0, row1);
 #pragma unroll
       for (int sub = 0; sub < kPG; sub += kGG) {
         if (sub < n) {
@@ -680,7 +717,7 @@ __global__ void __launch_bounds__(kGThreads, RB_PLANCK_MINB) planck_g_kernel(con
       const size_t c = icol + ncol * ilay;
       FlavW w;
       int row0, row1;
-      planck_cell_weights(p, tt, bi, c, ncl, w, row0, row1);
+      planck_cell_weights<ABI>(p, tt, bi, c, ncl, w, row0, row1);
       const Float B_lay = planck_band_f(t, p.tlay[c], delta_r, tab);
       const Float B_lev = planck_band_f(t, q.tlev[c], delta_r, tab);
       const bool is_sfc = (ilay == q.sfc_lay - 1);

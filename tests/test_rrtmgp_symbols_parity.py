@@ -103,6 +103,71 @@ def test_tau_absorption_with_cached_gfast_tables(oracle_lib, cuda_lib):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("source", ["random", "distinct"])
+@pytest.mark.parametrize("top_at_1", [False, True])
+@pytest.mark.parametrize("kdname", sorted(KD))
+def test_tau_and_planck_symbols_on_the_gfast_kernels(oracle_lib, cuda_lib, kdname, top_at_1, source):
+    """With cached table copies allowed (rrtmgpb_abi_table_cache(1), what the C++ frontend mirror does) the extern symbols
+    rrtmgp_compute_tau_absorption and rrtmgp_compute_Planck_source run the fused path's g-point-fastest kernels in their
+    ABI instantiation (interpolation state read from the caller's arrays): regular and ragged bands, contributors of
+    another flavour, replicated-like and distinct columns, both orientations - every output against the oracle."""
+    kind, kw = KD[kdname]
+    kd = syn.make_kdist(kind, **kw)
+    ncol, nlay = (37, 19) if source == "random" else (300, 60)   # 300 columns: several blocks, whole warps
+    x = _inputs(kd, source, ncol, nlay, top_at_1, seed=29)
+    it_c = gc.interpolation(oracle_lib, None, kd, x["play"], x["tlay"], x["col_gas"], keep_device=True)
+    it_g = gc.interpolation(cuda_lib, "cuda:0", kd, x["play"], x["tlay"], x["col_gas"], keep_device=True)
+    tau_c = gc.tau_absorption(oracle_lib, None, kd, x["play"], x["tlay"], x["col_gas"], it_c)
+    cuda_lib.cdll.rrtmgpb_abi_table_cache(1)
+    try:
+        n0 = cuda_lib.launch_count()
+        tau_g = gc.tau_absorption(cuda_lib, "cuda:0", kd, x["play"], x["tlay"], x["col_gas"], it_g)
+        _close(tau_g, tau_c, "tau (g-point-fastest kernels)")
+        assert cuda_lib.launch_count() > n0
+        if kind == "lw":
+            sfc_lay = nlay if top_at_1 else 1
+            got = gc.planck_source(cuda_lib, "cuda:0", kd, x["tlay"], x["tlev"], x["tsfc"], sfc_lay, it_g)
+            ref = gc.planck_source(oracle_lib, None, kd, x["tlay"], x["tlev"], x["tsfc"], sfc_lay, it_c)
+            for a, b, n in zip(got, ref, ("sfc_src", "lay_src", "lev_src", "sfc_source_Jac")):
+                if n == "sfc_source_Jac":
+                    assert np.max(np.abs(a - b)) <= RTOL * np.max(np.abs(ref[0])), n
+                else:
+                    _close(a, b, n)
+    finally:
+        cuda_lib.cdll.rrtmgpb_abi_table_cache(0)
+
+
+@pytest.mark.gpu
+def test_tau_absorption_accumulates_on_the_gfast_kernels(oracle_lib, cuda_lib):
+    """The extern symbol ADDS to tau (the frontend zeroes it first, mo_gas_optics_rrtmgp_kernels.F90:391): a non-zero tau
+    going in must come out incremented, on either kernel family."""
+    import ctypes as C
+    from rte_rrtmgp_b200.abi import fzeros
+    kd = syn.make_kdist("lw")
+    x = gc.profile(kd, 40, 21, seed=3)
+    it_c = gc.interpolation(oracle_lib, None, kd, x["play"], x["tlay"], x["col_gas"], keep_device=True)
+    it_g = gc.interpolation(cuda_lib, "cuda:0", kd, x["play"], x["tlay"], x["col_gas"], keep_device=True)
+    base = gc.tau_absorption(oracle_lib, None, kd, x["play"], x["tlay"], x["col_gas"], it_c)
+    orig = gc.fzeros
+
+    def prefilled(shape, dtype=np.float64, device=None):
+        a = orig(shape, dtype, device)
+        if len(shape) == 3 and shape[2] == kd.ngpt:
+            a += 0.25
+        return a
+
+    for cache in (0, 1):
+        cuda_lib.cdll.rrtmgpb_abi_table_cache(cache)
+        gc.fzeros = prefilled
+        try:
+            got = gc.tau_absorption(cuda_lib, "cuda:0", kd, x["play"], x["tlay"], x["col_gas"], it_g)
+        finally:
+            gc.fzeros = orig
+            cuda_lib.cdll.rrtmgpb_abi_table_cache(0)
+        _close(got, base + 0.25, f"tau accumulate (cache={cache})")
+
+
+@pytest.mark.gpu
 def test_cld_from_table_random(oracle_lib, cuda_lib):
     kdl = syn.make_kdist("sw", gpt_per_band=1)
     lut = syn.make_cloud_lut(kdl)

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--distinct", action="store_true", help="RFMIP-like distinct columns (clear sky) instead of the replicated all-sky profile")
     ap.add_argument("--tag", default=os.environ.get("RRTMGPB_LIB", "main"))
     ap.add_argument("--express", action="store_true", help="the express path (no (ncol,nlay,ngpt) arrays)")
+    ap.add_argument("--seq", action="store_true", help="the reference call sequence: the 45 extern symbols kernel by kernel")
     ap.add_argument("--lw-only", action="store_true")
     ap.add_argument("--sw-only", action="store_true")
     a = ap.parse_args()
@@ -43,6 +44,8 @@ def main():
         prof = {k: np.asfortranarray(np.tile(v, (reps,) + (1,) * (v.ndim - 1))[:a.ncol]) for k, v in base.items()}
     free0 = torch.cuda.mem_get_info()[0]
     sky = AllSky(ctx, a.ncol, a.nlay, kd_lw, kd_sw, do_clouds=not a.distinct, profiles=prof, express=a.express)
+    if a.seq:
+        sky.fused = False
     sky.step()
     ctx.config_checks(False, False)
     sky.step()
