@@ -636,6 +636,22 @@ __device__ __forceinline__ Float planck_band_f(const rrtmgpb_gas_tables& t, Floa
   return t0 + frac * (t1 - t0);
 }
 
+// sqrt(a*b) of two Planck fractions (:699).  RB_PLANCK_FAST_SQRT: the branch-free rb_sqrt (<= 1 ulp; MUFU seed + 6 fp64
+// instructions, no slow-path call: 31 call sites with BSSY / CALL / BSYNC otherwise keep the compiler from interleaving
+// the g-points of a pass); products below 1e-290 - fractions of a band's Planck function that small carry no energy -
+// give 0 instead of a subnormal-range root.
+#ifndef RB_PLANCK_FAST_SQRT
+#define RB_PLANCK_FAST_SQRT 0
+#endif
+__device__ __forceinline__ Float planck_geo_mean(Float a, Float b) {
+  const Float m = a * b;
+#if RB_PLANCK_FAST_SQRT
+  return (m > (Float)1.0e-290) ? rb_sqrt(fmax(m, (Float)1.0e-290)) : (Float)0;
+#else
+  return sqrt(m);
+#endif
+}
+
 #ifndef RB_PLANCK_PG
 #define RB_PLANCK_PG 2
 #endif
@@ -742,18 +758,25 @@ __global__ void __launch_bounds__(kGThreads, RB_PLANCK_MINB) planck_g_kernel(con
               if (FULLC || i < ns) {
                 // streaming stores: the source planes are next read by the solver, long after they left the caches
                 __stcs(lay_c, pf[i] * B_lay);                                                    // :640
-                __stcs(lev_c, (ilay == 0) ? pf[i] * B_lev : sqrt(pf_prev[sub + i] * pf[i]) * B_lev);   // :695-701
+                __stcs(lev_c, (ilay == 0) ? pf[i] * B_lev : planck_geo_mean(pf_prev[sub + i], pf[i]) * B_lev);   // :695-701
                 lay_c += ncl; lev_c += nclp;
-                if (is_sfc) {
-                  q.sfc_src[icol + ncol * (size_t)(gS + sub + i - 1 - p.gpt0)] = pf[i] * B_sfc;            // :650-653
-                  q.sfc_source_Jac[icol + ncol * (size_t)(gS + sub + i - 1 - p.gpt0)] = pf[i] * (B_sfc1 - B_sfc);
-                }
                 pf_prev[sub + i] = pf[i];
               }
             }
           };
           if (ns == kGG) emit(std::true_type{});
           else emit(std::false_type{});
+          if (is_sfc) {  // one layer of the column only: kept out of the g-point loop above (:650-653)
+            Float* sfc_c = q.sfc_src + icol + ncol * (size_t)(gS + sub - 1 - p.gpt0);
+            Float* jac_c = q.sfc_source_Jac + icol + ncol * (size_t)(gS + sub - 1 - p.gpt0);
+#pragma unroll
+            for (int i = 0; i < kGG; ++i) {
+              if (i < ns) {
+                sfc_c[ncol * (size_t)i] = pf[i] * B_sfc;
+                jac_c[ncol * (size_t)i] = pf[i] * (B_sfc1 - B_sfc);
+              }
+            }
+          }
         }
       }
     }
