@@ -530,7 +530,11 @@ __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_L
       const MinorInfo* minfo = tropo[k] ? tt.aux.minor_lower : tt.aux.minor_upper;
       const int mfirst = tropo[k] ? bi.mfirst[0] : bi.mfirst[1], mlast = tropo[k] ? bi.mlast[0] : bi.mlast[1];
       for (int imnr = mfirst; imnr <= mlast; ++imnr)
+#ifdef RB_EXPERIMENT_NOSCAL   /* upper bound of what the scaling prologue costs (results are WRONG) */
+        scal[((imnr - mfirst) * kTauCells + k) * kGThreads] = ce.col_dry;
+#else
         scal[((imnr - mfirst) * kTauCells + k) * kGThreads] = minor_scaling<ABI>(p, minfo[imnr], c, ncl, ce.col_dry);
+#endif
     }
   }
   bool shared_rows = true;
