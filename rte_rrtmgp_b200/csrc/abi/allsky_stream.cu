@@ -79,8 +79,7 @@ extern "C" int rrtmgpb_allsky_stream_host(const rrtmgpb_gas_optics_t* go_lw, con
   if (go_sw) rrtmgpb_gas_optics_dims(go_sw, &g2, &nbnd_sw, &ngpt_sw);
   if (g1 != ngas || g2 != ngas) return fail("allsky_stream_host: ngas differs from the k-distributions'");
   // Chunk schedule: a SMALL first chunk (a quarter of the nominal width) so that compute starts as soon as possible -
-  // its upload is the only one that is not hidden behind compute - then full chunks, and whatever is left at the end
-  // (the last chunk's download is the only exposed one).  Nominal width: chunk_cols, or by default four waves of the
+  // its upload is the only one that is not hidden behind compute - then full chunks, then two one-wave chunks (below).  Nominal width: chunk_cols, or by default four waves of the
   // register solvers' 16-column CTAs (2 resident per SM), so that no chunk ends on a nearly empty wave.
   int sms = 148;
   {
@@ -96,7 +95,22 @@ extern "C" int rrtmgpb_allsky_stream_host(const rrtmgpb_gas_optics_t* go_lw, con
     const int first = ncol > nc ? std::max(std::min(wave, nc), nc / 4) : nc;
     starts.push_back(0);
     c = std::min(first, ncol);
-    while (c < ncol) { starts.push_back(c); c = std::min(c + nc, ncol); }
+    // Optional shapes of the schedule (measured on 1 and 8 GPUs):
+    //   RRTMGPB_STREAM_RAMP=1  widths 1, 2, 4 waves before the full chunks: every upload hides behind the previous chunk's
+    //                          compute even when the host's PCIe / memory paths are shared by 8 ranks
+    //   RRTMGPB_STREAM_TAIL=1  two one-wave chunks at the end: with two compute streams the last chunk of EACH stream ends
+    //                          the call, and the exposed download is one wave's fluxes (14 MB) instead of a chunk's (55 MB)
+    static const bool ramp = [] { const char* e = std::getenv("RRTMGPB_STREAM_RAMP"); return e && e[0] == '1'; }();
+    static const bool want_tail = [] { const char* e = std::getenv("RRTMGPB_STREAM_TAIL"); return e && e[0] == '1'; }();
+    const int tail = (want_tail && nc > wave && ncol - c >= 2 * nc) ? wave : 0;
+    const int body_end = ncol - 2 * tail;
+    int width = (ramp && nc > 2 * wave) ? 2 * wave : nc;
+    while (c < body_end) {
+      starts.push_back(c);
+      c = std::min(c + width, body_end);
+      width = std::min(2 * width, nc);
+    }
+    if (tail) { starts.push_back(body_end); starts.push_back(body_end + tail); }
     starts.push_back(ncol);
   }
   const size_t ncl = (size_t)nc * nlay, nclp = (size_t)nc * nlev;
