@@ -109,6 +109,13 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // To keep results independent of WHICH instantiation runs (even / odd ncol decides whether TMA is usable), the choice
 // between the shared and the separate reciprocal follows the SHAPE, not the instantiation: shared when nlay fills the
 // lanes exactly (FULL = 1, and FULL = 0 on such shapes), separate otherwise (FULL = 2, and FULL = 0 on such shapes).
+// 1: max(sqrt(eps), mu0) kept in the lane's mu0 slot and the mu0 > 0 tests as one bit per cell in a register (both depend
+// on (column, layer) only): two fp64 compares and a select pair fewer per cell and g-point, bit-identical results - and
+// 16.17 instead of 13.45 ms on B200 (255 registers: like every other change that adds a live value to this kernel, it
+// costs the compiler the interleaving of the nine cells).  Off.
+#ifndef RB_SW_MU0_HOIST
+#define RB_SW_MU0_HOIST 0
+#endif
 #ifndef RB_PAD_NOSELECT
 #define RB_PAD_NOSELECT 1
 #endif
@@ -1015,9 +1022,16 @@ __global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? MINB : 1) sw_2str
   }
   // (Tried: mu0_s, 3*mu0_s and 1/mu0_s precomputed per (column, layer) in three shared-memory planes - five fp64
   // instructions fewer per cell, but 255 registers and two more LDS per cell: 14.3 -> 16.9 ms on B200.)
+  // RB_SW_MU0_HOIST: the slot holds max(sqrt(eps), mu0) (:1065) and the mu0 > 0 tests (:1122-1125) are one bit per cell
+  // in a register - both depend on (column, layer) only; per cell and g-point that is one fp64 compare + select pair and
+  // one fp64 compare less (same values, bit-identical results)
+  unsigned lit_mask = 0;
 #pragma unroll
-  for (int i = 0; i < CL; ++i)
-    sm_mu0[i * kRegThreads + threadIdx.x] = p.mu0[(k0 + i < nlay) ? off_lay0 + lay_step * i : off_lay0];
+  for (int i = 0; i < CL; ++i) {
+    const Float m = p.mu0[(k0 + i < nlay) ? off_lay0 + lay_step * i : off_lay0];
+    sm_mu0[i * kRegThreads + threadIdx.x] = RB_SW_MU0_HOIST ? fmax(min_mu0, m) : m;
+    if (m > (Float)0) lit_mask |= 1u << i;
+  }
   const Float mu0_top = p.mu0[(size_t)col + ncol * o.lay(0)];
   const Float mu0_sfc = p.mu0[(size_t)col + ncol * o.lay(nlay - 1)];
 
@@ -1057,13 +1071,13 @@ __global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? MINB : 1) sw_2str
       // FULL = 1: shared reciprocal; FULL = 2: separate; FULL = 0 (clamped cp.async inputs, any shape): whichever the
       // TMA instantiation of the same shape uses (uniform at run time), so that results do not depend on the path
       const bool MERGED = RB_SW_MERGED_DIV && ((FULL == 1) ? true : ((FULL == 2) ? !NOSEL : (RB_PAD_NOSELECT ? (NCH == 8 && nlay == kRegChunks * CL) : true)));   // (16-lane TMA launches are all FULL = 2)
-      const Float mu0_s = fmax(min_mu0, mu0);
+      const Float mu0_s = RB_SW_MU0_HOIST ? mu0 : fmax(min_mu0, mu0);
       Float Rdif, Tdif, Rdir, Tdir, Tnoscat;
       sw_two_stream_cell(tau_s, w0_s, g_s, mu0_s, (Float)3 * mu0_s, rb_rcp1(mu0_s), MERGED, Rdif, Tdif, Rdir, Tdir, Tnoscat);
       // FULL = 2: a zero-filled padding row (tau = ssa = g = 0) gives Rdif = 0 (factor 1 - exp(-0)), Rdir = Tdir = 0
       // (factor ssa) and Tnoscat = exp(-0) = 1 EXACTLY; only Tdif = RT_term*2k is 1 to rounding - one select, on T
       constexpr bool SEL = FULL == 0;
-      const bool lit = (!SEL || live) && (mu0 > (Float)0);  // :1122-1125: no source for diffuse light where mu0 <= 0
+      const bool lit = (!SEL || live) && (RB_SW_MU0_HOIST ? ((lit_mask >> i) & 1u) != 0 : (mu0 > (Float)0));  // :1122-1125: no source for diffuse light where mu0 <= 0
       R[i] = (!SEL || live) ? Rdif : (Float)0;
       T[i] = live ? Tdif : (Float)1;
       A3[i] = lit ? Rdir : (Float)0;
