@@ -68,6 +68,11 @@ void rrtmgpb_tables_changed(const void* kmajor);
 void rrtmgpb_init_constants(const Float* gravity, const Float* mol_weight_dry_air,
                             const Float* heat_capacity_dry_air);
 
+/* Gas-optics tau kernels: blocks whose cells do not share table rows (unrelated neighbouring columns) may take a second
+ * thread mapping - 8 lanes along the 16 g-points of one cell instead of one cell pair per thread (csrc/kernels/
+ * gas_optics_gfast.cuh: tau_band_rows).  1 = on, 0 = off, -1 = the environment's RRTMGPB_TAU_ROWS (default).  Same results either way. */
+void rrtmgpb_set_gas_optics_rows_path(int on);
+
 /* ---------------- solver options ---------------- */
 /* lw_solver_2stream level-source selection.  1 (default of the CUDA library): per-g-point level source as in the
  * reference's accelerator kernels (accel/mo_rte_solver_kernels.F90:958-962); 0 (default of the oracle): the serial

@@ -30,6 +30,7 @@ void rrtmgpb_set_solver_variant(int v) { (void)v; }
 int rrtmgpb_get_solver_variant(void) { return 0; }
 void rrtmgpb_set_tma_staging(int on) { (void)on; }
 void rrtmgpb_abi_table_cache(int on) { (void)on; }
+void rrtmgpb_set_gas_optics_rows_path(int on) { (void)on; }
 void rrtmgpb_tables_changed(const void* kmajor) { (void)kmajor; }
 /* the checker's side of the fast-math probe: plain libm / IEEE arithmetic */
 void rrtmgpb_fastmath_probe(int n, const double* x, double* e, double* s, double* r, double* d) {

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -368,6 +369,7 @@ extern "C" void rrtmgpb_tables_changed(const void* kmajor) {
 
 namespace {
 // gas_tau_g_kernel for the bands p.band0 .. p.band0 + p.nband_sub - 1
+std::atomic<int> g_tau_rows{-1};
 void launch_tau(const FusedParams& p, const TablesT& tt, bool abi = false) {
   const rrtmgpb_gas_tables* t = &p.t;
   const size_t ncl = (size_t)p.ncol * p.nlay;
@@ -381,14 +383,26 @@ void launch_tau(const FusedParams& p, const TablesT& tt, bool abi = false) {
   // 128-bit layout (tt.vec == 2) and 16-g-point chunks; RRTMGPB_TABLE_TMA=0 switches it off
   static const bool stage_env = [] { const char* e = std::getenv("RRTMGPB_TABLE_TMA"); return !(e && e[0] == '0'); }();
   const bool stage = stage_env && tt.vec == 2 && !aer_kind && kTG * kTauRegChunks == 16;
-  if (stage) smem += (size_t)(kGThreads / 32) * (kStgMinor / 16 + 4 * tt.maxm) * 16 * sizeof(Float);
+  // lanes-along-g-points mapping for warps of unrelated columns (tau_band_rows): its records overlay the warp's staging
+  // slots.  RRTMGPB_TAU_ROWS=0/1 (A/B switch)
+  static const bool rows_env = [] { const char* e = std::getenv("RRTMGPB_TAU_ROWS"); return e && e[0] == '1'; }();
+  const int rows_set = g_tau_rows.load(std::memory_order_relaxed);   // rrtmgpb_set_gas_optics_rows_path: -1 = environment
+  FusedParams pr = p;
+  pr.rows_path = (stage && (rows_set < 0 ? rows_env : rows_set != 0)) ? 1 : 0;
+  {
+    const size_t per_warp = std::max((size_t)(kStgMinor / 16 + 4 * tt.maxm) * 16 * sizeof(Float), pr.rows_path ? tau_rows_warp_bytes() : (size_t)0);
+    pr.stg_stride = (int)(per_warp / sizeof(Float));
+    if (stage) smem += (size_t)(kGThreads / 32) * per_warp;
+  }
 // KIND 1: the common kinds as compile-time constants (LW 1scl += 1scl clouds, SW 2str += 2str clouds, no aerosols)
 #define GAS_TAU_LAUNCH1(SWV, VECV, AERV, KINDV)                                                                   \
   do {                                                                                                            \
-    auto kern = (stage && VECV == 2 && !AERV) ? gas_tau_g_kernel<SWV, VECV, AERV, KINDV, (VECV == 2 && !AERV)>    \
-                                              : gas_tau_g_kernel<SWV, VECV, AERV, KINDV, false>;                  \
+    auto kern = (stage && VECV == 2 && !AERV)                                                                     \
+                    ? (pr.rows_path ? gas_tau_g_kernel<SWV, VECV, AERV, KINDV, (VECV == 2 && !AERV), false, (VECV == 2 && !AERV)> \
+                                    : gas_tau_g_kernel<SWV, VECV, AERV, KINDV, (VECV == 2 && !AERV)>)             \
+                    : gas_tau_g_kernel<SWV, VECV, AERV, KINDV, false>;                                            \
     if (smem > 48 * 1024) RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, kGThreads, smem, stream()>>>(p, tt);                                                             \
+    kern<<<grid, kGThreads, smem, stream()>>>(pr, tt);                                                             \
   } while (0)
 #define GAS_TAU_LAUNCH(SWV, VECV)                                                                     \
   if (aer_kind) GAS_TAU_LAUNCH1(SWV, VECV, true, 0);                                                  \
@@ -397,9 +411,10 @@ void launch_tau(const FusedParams& p, const TablesT& tt, bool abi = false) {
   if (abi) {  // absorption only, the interpolation state from the caller's arrays (extern symbol rrtmgp_compute_tau_absorption)
 #define GAS_TAU_LAUNCH_ABI(VECV, STGV)                                                                            \
   do {                                                                                                            \
-    auto kern = gas_tau_g_kernel<false, VECV, false, 0, STGV, true>;                                              \
+    auto kern = (STGV && pr.rows_path) ? gas_tau_g_kernel<false, VECV, false, 0, STGV, true, STGV>                \
+                                       : gas_tau_g_kernel<false, VECV, false, 0, STGV, true>;                     \
     if (smem > 48 * 1024) RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, kGThreads, smem, stream()>>>(p, tt);                                                             \
+    kern<<<grid, kGThreads, smem, stream()>>>(pr, tt);                                                             \
   } while (0)
     if (tt.vec == 2 && stage) GAS_TAU_LAUNCH_ABI(2, true);
     else if (tt.vec == 2) GAS_TAU_LAUNCH_ABI(2, false);
@@ -523,6 +538,7 @@ bool planck_source_gfast(int ncol, int nlay, int nbnd, int ngpt, int nflav, int 
 extern "C" {
 
 void rrtmgpb_abi_table_cache(int on) { g_abi_cache_on = on ? 1 : 0; }
+void rrtmgpb_set_gas_optics_rows_path(int on) { g_tau_rows.store(on); }
 
 /* kept so that programs linked against earlier builds still resolve it: table staging is no longer selectable */
 void rrtmgpb_set_tma_staging(int on) { (void)on; }

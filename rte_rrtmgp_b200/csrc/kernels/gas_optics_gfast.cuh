@@ -88,6 +88,8 @@ struct FusedParams {
   const Float *abi_col_gas = nullptr, *abi_col_mix = nullptr, *abi_fmajor = nullptr, *abi_fminor = nullptr;
   const int* abi_jeta = nullptr;
   int accumulate = 0;   // tau = tau + result: the extern symbol's semantics (the frontend zeroes tau first, :391)
+  int rows_path = 0;    // 1: warps whose cells do not share table rows take the lanes-along-g-points mapping (tau_band_rows)
+  int stg_stride = 0;   // Floats between the per-warp shared-memory slots (table staging / tau_band_rows records)
 };
 
 struct PlanckFusedParams {
@@ -269,6 +271,60 @@ __device__ __forceinline__ Float minor_scaling(const FusedParams& p, const Minor
     }
   }
   return sc;
+}
+
+// One output value of the tau kernels: absorption tabs, Rayleigh tray (0 without scattering) -> combine_abs_and_rayleigh
+// (mo_gas_optics_rrtmgp.F90:1986-1994), the by-band cloud (and, AER, aerosol) increment
+// (mo_optical_props_kernels.F90:366-477) and the store at plane offset o: the `finish` lambda of tau_band_cells as a function,
+// for the lanes-along-g-points mapping (tau_band_rows) - same expressions, same results (the cells-per-thread mapping keeps
+// its lambda: moving it here changed that kernel's instruction schedule and cost 3 %).
+template <bool SW, bool AER, int KIND, bool CLD, bool ABI>
+__device__ __forceinline__ void tau_finish(const FusedParams& p, Float ct, Float cw, Float cg, Float at, Float aw, Float ag,
+                                           bool valid, size_t o, Float tabs, Float tray) {
+  const Float eps3 = (Float)3.0 * (Float)RB_TINY;  // mo_optical_props_kernels.F90:38
+  Float to = tabs, ss = 0, gg = 0;
+  if (SW) {
+    to = tabs + tray;
+    // rb_div: <= 1 ulp, no special-case code (the denominators below are >= 2*tiny, finite and normal); the IEEE
+    // division sequence made up half of this kernel's instructions (profiles/r1_v8_gas_tau_sw.txt)
+    ss = (to > (Float)2 * (Float)RB_TINY) ? rb_div(tray, to) : (Float)0;
+  }
+  // by-band increments of (to[, ss, gg]) by (ct, cw, cg): mo_optical_props_kernels.F90:366-477; the cloud one
+  // first, then (AER instantiations) the aerosol one
+  const int op_kind = KIND ? (SW ? 2 : 1) : p.op_kind;
+  const int cld_kind = KIND ? (SW ? 2 : 1) : p.cld_kind;
+  if (op_kind == 1) {
+    auto inc1 = [&](int kind, Float ct_, Float cw_) {
+      if (kind == 1) to = to + ct_;                          // inc_1scalar_by_1scalar_bybnd :379
+      else if (kind == 2) to = to + ct_ * ((Float)1 - cw_);  // inc_1scalar_by_2stream_bybnd :398
+    };
+    inc1(cld_kind, ct, cw);
+    if (AER) inc1(p.aer_kind, at, aw);
+    if (valid) p.tau[o] = (ABI && p.accumulate) ? p.tau[o] + to : to;
+  } else {
+    auto inc2 = [&](int kind, Float ct_, Float cw_, Float cg_) {
+      if (KIND == 1 && !CLD && !AER) {                     // ct == 0: tau12 = to, tauscat12 = to*ss, g stays 0
+        ss = rb_div(to * ss, fmax(eps3, to));
+      } else if (kind == 1) {                                     // inc_2stream_by_1scalar_bybnd :440-442
+        const Float tau12 = to + ct_;
+        ss = rb_div(to * ss, fmax(eps3, tau12));
+        to = tau12;
+      } else if (kind == 2) {                              // inc_2stream_by_2stream_bybnd :468-477
+        const Float tau12 = to + ct_;
+        const Float tauscat12 = to * ss + ct_ * cw_;
+        gg = rb_div(to * ss * gg + ct_ * cw_ * cg_, fmax(eps3, tauscat12));
+        ss = rb_div(tauscat12, fmax(eps3, tau12));
+        to = tau12;
+      }
+    };
+    inc2(cld_kind, ct, cw, cg);
+    if (AER) inc2(p.aer_kind, at, aw, ag);
+    if (valid) {
+      p.tau[o] = to;
+      p.ssa[o] = ss;
+      p.g[o] = gg;
+    }
+  }
 }
 
 // NC cells that share tropo, jtemp and the table rows (row0, row1 => je[0], je[1]) of band `bi`
@@ -466,13 +522,130 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Lanes-along-g-points mapping (tau_band_rows) for WARPS whose cells do NOT share table rows - unrelated neighbouring
+// columns (RFMIP-like profile sets, BASELINE config 3).  In the cells-per-thread mapping every lane of such a warp reads its
+// OWN rows: one LDG.128 is 32 L1 wavefronts (one line per lane, 16 of its 128 bytes used), every line is fetched eight times
+// for the band's 16 g-points, and the kernel is bound by the L1 data pipe (84 % busy under ncu).  Here the
+// warp first publishes the per-cell state its lanes computed in the prologue (weights, rows, cloud properties: one
+// 176-byte record per cell in the warp's own shared-memory slots - the table-staging slots, which such a warp never
+// uses; no block barrier), then re-maps: 8 consecutive lanes take the 16 g-points of ONE cell (2 each), so a table row is
+// read as one 128-byte line by 8 lanes - a warp request touches 4 lines instead of 32 - and the stores of a g-point cover
+// 4 consecutive cells = one full 32-byte sector.  Regular bands only (16 g-points, every contributor covering the band:
+// all rrtmgp-data bands); per-g-point arithmetic is tau_band_cells' expression for expression (same tau_finish), so both
+// mappings give the same results (tests/test_gas_optics_rows_path.py: bit for bit).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kRowRec = 22;   // Floats per cell record: cm[2], fmj[8], fmn[4], ct, cw, cg, amount_rayl, 6 ints, pad
+__host__ __device__ constexpr size_t tau_rows_warp_bytes() { return (size_t)32 * kRowRec * sizeof(double); }
+
+template <bool SW, int KIND, bool ABI>
+__device__ __forceinline__ void tau_band_rows(const FusedParams& p, const TablesT& tt, const BandInfo& bi,
+                                              const TauCell (&cell)[kTauCells], const bool (&tropo)[kTauCells],
+                                              const int (&jtemp)[kTauCells], const int (&row0)[kTauCells],
+                                              const int (&row1)[kTauCells], const Float* scal_block, Float* rec_warp) {
+  static_assert(sizeof(Float) == 8, "double-precision layout (the callers require TablesT::vec == 2)");
+  const rrtmgpb_gas_tables& t = p.t;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = lane & 7;    // lane j of a cell's eight: g-points bS + 2j, bS + 2j + 1
+  const int cq = lane >> 3;  // which of the 4 cells of a pass
+  const size_t ncl = (size_t)p.ncol * p.nlay;
+  const size_t cbase_warp = (size_t)(blockIdx.x / p.nband_sub) * (kTauCells * kGThreads) + (size_t)warp * 32;
+  const int s_eta = t.ntemp, s_p = t.ntemp * t.neta;
+  const size_t d_eta = (size_t)s_eta * tt.gp, d_p = (size_t)s_p * tt.gp;
+  const int gcol = (bi.bS - 1) + 2 * j;  // 0-based table column of this lane's first g-point
+#pragma unroll   // (fully unrolled: a run-time k would push the callers' per-cell register arrays to local memory)
+  for (int k = 0; k < kTauCells; ++k) {
+    __syncwarp();   // every lane is done reading the previous records
+    {
+      const TauCell& ce = cell[k];
+      Float2* r = reinterpret_cast<Float2*>(rec_warp + (size_t)lane * kRowRec);
+      r[0] = Float2{ce.w.cm[0], ce.w.cm[1]};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r[1 + q] = Float2{ce.w.fmj[2 * q], ce.w.fmj[2 * q + 1]};
+      r[5] = Float2{ce.w.fmn[0], ce.w.fmn[1]};
+      r[6] = Float2{ce.w.fmn[2], ce.w.fmn[3]};
+      r[7] = Float2{ce.ct, ce.cw};
+      r[8] = Float2{ce.cg, ce.amount_rayl};
+      int4* ri = reinterpret_cast<int4*>(r + 9);
+      ri[0] = int4{jtemp[k], row0[k], row1[k], ce.w.je[0]};
+      ri[1] = int4{ce.w.je[1], (tropo[k] ? 1 : 0) | (ce.valid ? 2 : 0), 0, 0};
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int it = 0; it < 8; ++it) {
+      const int cl = it * 4 + cq;
+      const Float2* r = reinterpret_cast<const Float2*>(rec_warp + (size_t)cl * kRowRec);
+      const int4 i0 = reinterpret_cast<const int4*>(r + 9)[0], i1 = reinterpret_cast<const int4*>(r + 9)[1];
+      const int flags = i1.y;
+      if (!(flags & 2)) continue;   // beyond the last cell
+      const bool tr = flags & 1;
+      const int jt = i0.x, r0 = i0.y, r1 = i0.z, je0 = i0.w, je1 = i1.x;
+      const Float2 cm = r[0];
+      Float f[8], a[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const Float2 v = r[1 + q]; f[2 * q] = v.x; f[2 * q + 1] = v.y; }
+      { const Float2 v = r[5], w = r[6]; a[0] = v.x; a[1] = v.y; a[2] = w.x; a[3] = w.y; }
+      Float acc[2];
+      {  // major absorbers (interpolate3D_byflav :791-801)
+        const Float* a0 = tt.kmajor + (size_t)r0 * tt.gp + gcol;
+        const Float* b0 = tt.kmajor + (size_t)r1 * tt.gp + gcol;
+        const GLoad<2> x0(a0), x1(a0 + d_eta), x2(a0 + d_p), x3(a0 + d_p + d_eta);
+        const GLoad<2> y0(b0), y1(b0 + d_eta), y2(b0 + d_p), y3(b0 + d_p + d_eta);
+#pragma unroll
+        for (int v = 0; v < 2; ++v)
+          acc[v] = cm.x * (f[0] * x0.v[v] + f[1] * x1.v[v] + f[2] * x2.v[v] + f[3] * x3.v[v]) +
+                   cm.y * (f[4] * y0.v[v] + f[5] * y1.v[v] + f[6] * y2.v[v] + f[7] * y3.v[v]);
+      }
+      {  // minor absorbers (:451-498); regular band: every contributor starts at the band's first g-point
+        const MinorInfo* minfo = tr ? tt.aux.minor_lower : tt.aux.minor_upper;
+        const Float* kminor = tr ? tt.kminor_lower : tt.kminor_upper;
+        const int mpitch = tr ? tt.nkl : tt.nku;
+        const int mfirst = tr ? bi.mfirst[0] : bi.mfirst[1], mlast = tr ? bi.mlast[0] : bi.mlast[1];
+        const size_t de = (size_t)s_eta * mpitch;
+        const Float* m0 = kminor + (size_t)((jt - 1) + s_eta * (je0 - 1)) * mpitch + 2 * j - 1;   // + kstart below
+        const Float* m1 = kminor + (size_t)(jt + s_eta * (je1 - 1)) * mpitch + 2 * j - 1;
+        const Float* sc = scal_block + (size_t)k * kGThreads + warp * 32 + cl;
+        for (int imnr = mfirst; imnr <= mlast; ++imnr) {
+          const Float scaling = sc[(size_t)(imnr - mfirst) * kTauCells * kGThreads];
+          const int ks = minfo[imnr].kstart;
+          const GLoad<2> x0(m0 + ks), x1(m0 + de + ks), y0(m1 + ks), y1(m1 + de + ks);
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const Float kint = a[0] * x0.v[v] + a[1] * x1.v[v] + a[2] * y0.v[v] + a[3] * y1.v[v];  // :757-760
+            acc[v] = acc[v] + scaling * kint;                                                     // :493
+          }
+        }
+      }
+      Float tray[2] = {0, 0};
+      const Float2 c01 = r[7], c23 = r[8];   // (ct, cw), (cg, amount_rayl)
+      if (SW) {  // Rayleigh (:554-559)
+        const Float* kr = tt.krayl + (size_t)s_p * tt.gp * (tr ? 0 : 1) + gcol;
+        const Float* q0 = kr + (size_t)((jt - 1) + s_eta * (je0 - 1)) * tt.gp;
+        const Float* q1 = kr + (size_t)(jt + s_eta * (je1 - 1)) * tt.gp;
+        const GLoad<2> x0(q0), x1(q0 + d_eta), y0(q1), y1(q1 + d_eta);
+#pragma unroll
+        for (int v = 0; v < 2; ++v) tray[v] = (a[0] * x0.v[v] + a[1] * x1.v[v] + a[2] * y0.v[v] + a[3] * y1.v[v]) * c23.y;
+      }
+      const size_t o = cbase_warp + (size_t)k * kGThreads + cl + ncl * (size_t)(gcol - p.gpt0);
+#pragma unroll
+      for (int v = 0; v < 2; ++v)
+        tau_finish<SW, false, KIND, true, ABI>(p, c01.x, c01.y, c23.x, (Float)0, (Float)0, (Float)0, true, o + ncl * (size_t)v, acc[v],
+                                               tray[v]);
+    }
+  }
+}
+
 // STAGE: when every cell of a WARP interpolates between the SAME table rows (a regular band; neighbouring columns in the
 // same T / p / eta bins - one vote per warp) lane 0 copies those rows - 8 of kmajor, 4 of krayl (SW), 4 per minor
 // contributor, 128 bytes each - to the warp's shared-memory slots with cp.async.bulk (the TMA engine, completion on the
 // warp's mbarrier) and the warp reads them from there: immediate-offset LDS instead of LDG with 64-bit row addresses, at
 // shared-memory latency.  Measured on B200: LW tau 5.18 -> 4.33 ms at 65,536 x 72 x 256 (block-wide
 // variant).  Warps whose cells differ take the L1 path below.  RRTMGPB_TABLE_TMA=0 switches it off.
-template <bool SW, int VEC, bool AER, int KIND, bool STAGE = false, bool ABI = false>
+// ROWS: the instantiation that carries the lanes-along-g-points mapping for warps of unrelated columns (tau_band_rows).  A
+// separate instantiation because its mere presence changes the register allocation of the cells-per-thread path (measured:
+// LW tau 4.38 -> 4.60 ms on the replicated profile with the path compiled in but never taken); the host launches it when
+// rrtmgpb_set_gas_optics_rows_path(1) / RRTMGPB_TAU_ROWS=1 says the columns are unrelated.
+template <bool SW, int VEC, bool AER, int KIND, bool STAGE = false, bool ABI = false, bool ROWS = false>
 __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_LW) gas_tau_g_kernel(const FusedParams p, const TablesT tt) {
   const rrtmgpb_gas_tables& t = p.t;
   const size_t ncl = (size_t)p.ncol * p.nlay;
@@ -559,7 +732,15 @@ __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_L
     const int r0_lane0 = __shfl_sync(full, row0[0], 0), r1_lane0 = __shfl_sync(full, row1[0], 0);
     const int tr_lane0 = __shfl_sync(full, (int)tropo[0], 0);
     const bool same = shared_rows && regular && row0[0] == r0_lane0 && row1[0] == r1_lane0 && (int)tropo[0] == tr_lane0;
-    if (__all_sync(full, same)) {
+    const unsigned votes = ROWS ? __ballot_sync(full, same) : (__all_sync(full, same) ? full : 0u);
+    // ---- unrelated columns (fewer than a quarter of the lanes even share rows between their own two cells, none with
+    // lane 0): the warp takes the lanes-along-g-points mapping; its records overlay the staging slots it will not use
+    if (ROWS && bi.regular[0] && bi.regular[1] && __popc(__ballot_sync(full, shared_rows)) < 8 && __popc(votes) < 8) {
+      Float* rec = reinterpret_cast<Float*>(tau_smem_raw) + (size_t)tt.maxm * kTauCells * kGThreads + (size_t)(threadIdx.x >> 5) * p.stg_stride;
+      tau_band_rows<SW, KIND, ABI>(p, tt, bi, cell, tropo, jtemp, row0, row1, reinterpret_cast<const Float*>(tau_smem_raw), rec);
+      return;
+    }
+    if (votes == full) {
       const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
       __shared__ __align__(8) uint64_t s_bar[kGThreads / 32];
       const int s_eta = t.ntemp, s_p = t.ntemp * t.neta;
@@ -567,7 +748,8 @@ __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_L
       const int mfirst = tr ? bi.mfirst[0] : bi.mfirst[1], mlast = tr ? bi.mlast[0] : bi.mlast[1];
       const int nm = mlast >= mfirst ? mlast - mfirst + 1 : 0;
       const int rows_per_warp = kStgMinor / 16 + 4 * tt.maxm;
-      Float* stg = reinterpret_cast<Float*>(tau_smem_raw) + (size_t)tt.maxm * kTauCells * kGThreads + (size_t)warp * rows_per_warp * 16;
+      Float* stg = reinterpret_cast<Float*>(tau_smem_raw) + (size_t)tt.maxm * kTauCells * kGThreads +
+                   (ROWS ? (size_t)warp * p.stg_stride : (size_t)warp * rows_per_warp * 16);
       const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar[warp]);
       if (lane == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar));

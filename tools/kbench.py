@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--tag", default=os.environ.get("RRTMGPB_LIB", "main"))
     ap.add_argument("--express", action="store_true", help="the express path (no (ncol,nlay,ngpt) arrays)")
     ap.add_argument("--seq", action="store_true", help="the reference call sequence: the 45 extern symbols kernel by kernel")
+    ap.add_argument("--rows", type=int, default=-1, help="rrtmgpb_set_gas_optics_rows_path (-1: environment)")
     ap.add_argument("--lw-only", action="store_true")
     ap.add_argument("--sw-only", action="store_true")
     a = ap.parse_args()
@@ -34,6 +35,7 @@ def main():
     lib = pkg.lib()
     lib.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx = Context(lib, "cuda:0")
+    lib.cdll.rrtmgpb_set_gas_optics_rows_path(a.rows)
     kd_lw = None if a.sw_only else syn.make_kdist("lw")
     kd_sw = None if a.lw_only else syn.make_kdist("sw")
     prof = None
