@@ -397,10 +397,12 @@ void launch_tau(const FusedParams& p, const TablesT& tt, bool abi = false) {
 // KIND 1: the common kinds as compile-time constants (LW 1scl += 1scl clouds, SW 2str += 2str clouds, no aerosols)
 #define GAS_TAU_LAUNCH1(SWV, VECV, AERV, KINDV)                                                                   \
   do {                                                                                                            \
-    auto kern = (stage && VECV == 2 && !AERV)                                                                     \
-                    ? (pr.rows_path ? gas_tau_g_kernel<SWV, VECV, AERV, KINDV, (VECV == 2 && !AERV), false, (VECV == 2 && !AERV)> \
-                                    : gas_tau_g_kernel<SWV, VECV, AERV, KINDV, (VECV == 2 && !AERV)>)             \
-                    : gas_tau_g_kernel<SWV, VECV, AERV, KINDV, false>;                                            \
+    if (stage && VECV == 2 && !AERV && pr.rows_path) {   /* the ROWS instantiations live in gas_optics_rows.cu */ \
+      launch_tau_rows(pr, tt, grid, smem, SWV, KINDV, false);                                                     \
+      break;                                                                                                      \
+    }                                                                                                             \
+    auto kern = (stage && VECV == 2 && !AERV) ? gas_tau_g_kernel<SWV, VECV, AERV, KINDV, (VECV == 2 && !AERV)>    \
+                                              : gas_tau_g_kernel<SWV, VECV, AERV, KINDV, false>;                  \
     if (smem > 48 * 1024) RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, kGThreads, smem, stream()>>>(pr, tt);                                                             \
   } while (0)
@@ -411,8 +413,11 @@ void launch_tau(const FusedParams& p, const TablesT& tt, bool abi = false) {
   if (abi) {  // absorption only, the interpolation state from the caller's arrays (extern symbol rrtmgp_compute_tau_absorption)
 #define GAS_TAU_LAUNCH_ABI(VECV, STGV)                                                                            \
   do {                                                                                                            \
-    auto kern = (STGV && pr.rows_path) ? gas_tau_g_kernel<false, VECV, false, 0, STGV, true, STGV>                \
-                                       : gas_tau_g_kernel<false, VECV, false, 0, STGV, true>;                     \
+    if (STGV && pr.rows_path) {                                                                                   \
+      launch_tau_rows(pr, tt, grid, smem, false, 0, true);                                                        \
+      break;                                                                                                      \
+    }                                                                                                             \
+    auto kern = gas_tau_g_kernel<false, VECV, false, 0, STGV, true>;                                              \
     if (smem > 48 * 1024) RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, kGThreads, smem, stream()>>>(pr, tt);                                                             \
   } while (0)

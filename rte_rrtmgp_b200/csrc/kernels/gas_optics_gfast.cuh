@@ -74,9 +74,12 @@ struct FusedParams {
   CellState cs;
   // outputs
   int op_kind;  // 1: tau ; 2: tau, ssa, g
+  int rows_path = 0;    // 1: warps whose cells do not share table rows take the lanes-along-g-points mapping (tau_band_rows)
+                        // (this and stg_stride sit in what used to be padding: the kernels' parameter offsets stay put)
   Float *tau, *ssa, *g;
   // optional by-band cloud increment (kind 0 = none; 1 = 1scl tau ; 2 = 2str tau, ssa, g)
   int cld_kind;
+  int stg_stride = 0;   // Floats between the per-warp shared-memory slots (table staging / tau_band_rows records)
   const Float *cld_tau, *cld_ssa, *cld_g;
   // optional second by-band increment applied after the cloud one (aerosols), same kinds
   int aer_kind;
@@ -88,8 +91,6 @@ struct FusedParams {
   const Float *abi_col_gas = nullptr, *abi_col_mix = nullptr, *abi_fmajor = nullptr, *abi_fminor = nullptr;
   const int* abi_jeta = nullptr;
   int accumulate = 0;   // tau = tau + result: the extern symbol's semantics (the frontend zeroes tau first, :391)
-  int rows_path = 0;    // 1: warps whose cells do not share table rows take the lanes-along-g-points mapping (tau_band_rows)
-  int stg_stride = 0;   // Floats between the per-warp shared-memory slots (table staging / tau_band_rows records)
 };
 
 struct PlanckFusedParams {
@@ -543,7 +544,7 @@ __device__ __forceinline__ void tau_band_rows(const FusedParams& p, const Tables
                                               const TauCell (&cell)[kTauCells], const bool (&tropo)[kTauCells],
                                               const int (&jtemp)[kTauCells], const int (&row0)[kTauCells],
                                               const int (&row1)[kTauCells], const Float* scal_block, Float* rec_warp) {
-  static_assert(sizeof(Float) == 8, "double-precision layout (the callers require TablesT::vec == 2)");
+  static_assert(sizeof(Float) == 8 || KIND < 0, "double-precision layout (the callers require TablesT::vec == 2)");   // (dependent: checked on instantiation)
   const rrtmgpb_gas_tables& t = p.t;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = lane & 7;    // lane j of a cell's eight: g-points bS + 2j, bS + 2j + 1
@@ -735,10 +736,12 @@ __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_L
     const unsigned votes = ROWS ? __ballot_sync(full, same) : (__all_sync(full, same) ? full : 0u);
     // ---- unrelated columns (fewer than a quarter of the lanes even share rows between their own two cells, none with
     // lane 0): the warp takes the lanes-along-g-points mapping; its records overlay the staging slots it will not use
-    if (ROWS && bi.regular[0] && bi.regular[1] && __popc(__ballot_sync(full, shared_rows)) < 8 && __popc(votes) < 8) {
-      Float* rec = reinterpret_cast<Float*>(tau_smem_raw) + (size_t)tt.maxm * kTauCells * kGThreads + (size_t)(threadIdx.x >> 5) * p.stg_stride;
-      tau_band_rows<SW, KIND, ABI>(p, tt, bi, cell, tropo, jtemp, row0, row1, reinterpret_cast<const Float*>(tau_smem_raw), rec);
-      return;
+    if constexpr (ROWS) {
+      if (bi.regular[0] && bi.regular[1] && __popc(__ballot_sync(full, shared_rows)) < 8 && __popc(votes) < 8) {
+        Float* rec = reinterpret_cast<Float*>(tau_smem_raw) + (size_t)tt.maxm * kTauCells * kGThreads + (size_t)(threadIdx.x >> 5) * p.stg_stride;
+        tau_band_rows<SW, KIND, ABI>(p, tt, bi, cell, tropo, jtemp, row0, row1, reinterpret_cast<const Float*>(tau_smem_raw), rec);
+        return;
+      }
     }
     if (votes == full) {
       const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -975,8 +978,14 @@ __global__ void __launch_bounds__(kGThreads, RB_PLANCK_MINB) planck_g_kernel(con
   }
 }
 
+// The ROWS instantiations of gas_tau_g_kernel (double precision, 128-bit table layout, staging slots present), compiled in
+// their own translation unit (abi/gas_optics_rows.cu): in the same cubin as the default instantiations they moved those
+// 100-230 KB kernels to other code addresses and cost the replicated profile 3 % with instruction-for-instruction
+// identical SASS (B200: LW tau 4.38 -> 4.52 ms, SW tau 7.47 -> 7.60 ms).
+void launch_tau_rows(const FusedParams& p, const TablesT& tt, unsigned grid, size_t smem, bool sw, int kind, bool abi);
+
 // out[r*pitch + g] = in[r + nrow*g]   (one-off table transposition)
-__global__ void transpose_table_kernel(const Float* __restrict__ in, Float* __restrict__ out, int nrow, int ng, int pitch) {
+static __global__ void transpose_table_kernel(const Float* __restrict__ in, Float* __restrict__ out, int nrow, int ng, int pitch) {
   __shared__ Float tile[32][33];
   const int r0 = blockIdx.x * 32, g0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {

@@ -35,7 +35,8 @@ def main():
     lib = pkg.lib()
     lib.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx = Context(lib, "cuda:0")
-    lib.cdll.rrtmgpb_set_gas_optics_rows_path(a.rows)
+    if a.rows >= 0:
+        lib.cdll.rrtmgpb_set_gas_optics_rows_path(a.rows)
     kd_lw = None if a.sw_only else syn.make_kdist("lw")
     kd_sw = None if a.lw_only else syn.make_kdist("sw")
     prof = None
