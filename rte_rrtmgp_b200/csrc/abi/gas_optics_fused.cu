@@ -388,7 +388,12 @@ void launch_tau(const FusedParams& p, const TablesT& tt, bool abi = false) {
   static const bool rows_env = [] { const char* e = std::getenv("RRTMGPB_TAU_ROWS"); return e && e[0] == '1'; }();
   const int rows_set = g_tau_rows.load(std::memory_order_relaxed);   // rrtmgpb_set_gas_optics_rows_path: -1 = environment
   FusedParams pr = p;
-  pr.rows_path = (stage && (rows_set < 0 ? rows_env : rows_set != 0)) ? 1 : 0;
+  // 0: off; otherwise the vote threshold of the ROWS instantiations: a warp re-maps when fewer than this many of its lanes share
+  // table rows between their own two cells (1 = the default, 28; 2..33 = that threshold, for experiments).  B200, 65,536 x 60
+  // distinct columns, LW / SW tau in ms: off 9.52 / 13.67; 12: 8.19 / 13.09; 20: 7.37 / 12.16; 24: 7.03 / 11.66; 28: 6.92 / 11.36;
+  // 33 (every warp, even uniform ones): 8.34 / 13.81
+  const int rows_req = stage ? (rows_set < 0 ? (rows_env ? 1 : 0) : rows_set) : 0;
+  pr.rows_path = rows_req <= 0 ? 0 : (rows_req == 1 ? 28 : std::min(rows_req, 33));
   {
     const size_t per_warp = std::max((size_t)(kStgMinor / 16 + 4 * tt.maxm) * 16 * sizeof(Float), pr.rows_path ? tau_rows_warp_bytes() : (size_t)0);
     pr.stg_stride = (int)(per_warp / sizeof(Float));

@@ -734,10 +734,12 @@ __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_L
     const int tr_lane0 = __shfl_sync(full, (int)tropo[0], 0);
     const bool same = shared_rows && regular && row0[0] == r0_lane0 && row1[0] == r1_lane0 && (int)tropo[0] == tr_lane0;
     const unsigned votes = ROWS ? __ballot_sync(full, same) : (__all_sync(full, same) ? full : 0u);
-    // ---- unrelated columns (fewer than a quarter of the lanes even share rows between their own two cells, none with
-    // lane 0): the warp takes the lanes-along-g-points mapping; its records overlay the staging slots it will not use
+    // ---- unrelated columns (fewer than p.rows_path = 28 of the lanes share rows even between their own two cells - profiles
+    // of one data set coincide in some T / p / eta bins by chance, so the count is rarely near zero; warps above the threshold,
+    // e.g. stratospheric layers where every profile falls into the same bins, are better off below): the warp takes the
+    // lanes-along-g-points mapping; its records overlay the staging slots it will not use
     if constexpr (ROWS) {
-      if (bi.regular[0] && bi.regular[1] && __popc(__ballot_sync(full, shared_rows)) < 8 && __popc(votes) < 8) {
+      if (bi.regular[0] && bi.regular[1] && __popc(__ballot_sync(full, shared_rows)) < p.rows_path) {   // rows_path = the threshold
         Float* rec = reinterpret_cast<Float*>(tau_smem_raw) + (size_t)tt.maxm * kTauCells * kGThreads + (size_t)(threadIdx.x >> 5) * p.stg_stride;
         tau_band_rows<SW, KIND, ABI>(p, tt, bi, cell, tropo, jtemp, row0, row1, reinterpret_cast<const Float*>(tau_smem_raw), rec);
         return;
