@@ -69,9 +69,9 @@ void rrtmgpb_init_constants(const Float* gravity, const Float* mol_weight_dry_ai
                             const Float* heat_capacity_dry_air);
 
 /* Gas-optics tau kernels: blocks whose cells do not share table rows (unrelated neighbouring columns) may take a second
- * thread mapping - 8 lanes along the 16 g-points of one cell instead of one cell pair per thread (csrc/kernels/
+ * thread mapping - 4 lanes along the 16 g-points of one cell instead of one cell pair per thread (csrc/kernels/
  * gas_optics_gfast.cuh: tau_band_rows).  1 = on, 0 = off, -1 = the environment's RRTMGPB_TAU_ROWS (default: off); 2..33 = on with that
- * vote threshold (a warp re-maps when fewer than this many lanes share rows between their two cells; 1 means 28).  Same results either way. */
+ * vote threshold (a warp re-maps when fewer than this many lanes share rows between their two cells; 1 means 32).  Same results either way. */
 void rrtmgpb_set_gas_optics_rows_path(int on);
 
 /* ---------------- solver options ---------------- */

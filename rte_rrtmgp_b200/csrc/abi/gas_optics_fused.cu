@@ -389,11 +389,12 @@ void launch_tau(const FusedParams& p, const TablesT& tt, bool abi = false) {
   const int rows_set = g_tau_rows.load(std::memory_order_relaxed);   // rrtmgpb_set_gas_optics_rows_path: -1 = environment
   FusedParams pr = p;
   // 0: off; otherwise the vote threshold of the ROWS instantiations: a warp re-maps when fewer than this many of its lanes share
-  // table rows between their own two cells (1 = the default, 28; 2..33 = that threshold, for experiments).  B200, 65,536 x 60
-  // distinct columns, LW / SW tau in ms: off 9.52 / 13.67; 12: 8.19 / 13.09; 20: 7.37 / 12.16; 24: 7.03 / 11.66; 28: 6.92 / 11.36;
-  // 33 (every warp, even uniform ones): 8.34 / 13.81
+  // table rows between their own two cells (1 = the default, 32: any lane that does not; 2..33 = that threshold, for
+  // experiments).  B200, 65,536 x 60 distinct columns, LW / SW tau in ms: off 9.52 / 13.67; two g-points per lane: 12: 8.19 / 13.09,
+  // 20: 7.37 / 12.16, 24: 7.03 / 11.66, 28: 6.92 / 11.36, 33 (every warp, even uniform ones): 8.34 / 13.81; four g-points per lane
+  // (RB_ROWS_GPL = 4, shipped): 24: 6.85 / 10.35, 28: 6.69 / 9.78, 30: 6.63 / 9.54, 32: 6.52 / 9.24; eight per lane, 28: 7.33 / 9.79
   const int rows_req = stage ? (rows_set < 0 ? (rows_env ? 1 : 0) : rows_set) : 0;
-  pr.rows_path = rows_req <= 0 ? 0 : (rows_req == 1 ? 28 : std::min(rows_req, 33));
+  pr.rows_path = rows_req <= 0 ? 0 : (rows_req == 1 ? 32 : std::min(rows_req, 33));
   {
     const size_t per_warp = std::max((size_t)(kStgMinor / 16 + 4 * tt.maxm) * 16 * sizeof(Float), pr.rows_path ? tau_rows_warp_bytes() : (size_t)0);
     pr.stg_stride = (int)(per_warp / sizeof(Float));

@@ -530,12 +530,15 @@ __device__ __forceinline__ void tau_band_cells(const FusedParams& p, const Table
 // for the band's 16 g-points, and the kernel is bound by the L1 data pipe (84 % busy under ncu).  Here the
 // warp first publishes the per-cell state its lanes computed in the prologue (weights, rows, cloud properties: one
 // 176-byte record per cell in the warp's own shared-memory slots - the table-staging slots, which such a warp never
-// uses; no block barrier), then re-maps: 8 consecutive lanes take the 16 g-points of ONE cell (2 each), so a table row is
-// read as one 128-byte line by 8 lanes - a warp request touches 4 lines instead of 32 - and the stores of a g-point cover
-// 4 consecutive cells = one full 32-byte sector.  Regular bands only (16 g-points, every contributor covering the band:
+// uses; no block barrier), then re-maps: 4 consecutive lanes take the 16 g-points of ONE cell (4 each: RB_ROWS_GPL), so a table
+// row is read as two 64-byte requests by 4 lanes - a warp request touches 8 lines instead of 32, each line is fetched twice
+// instead of eight times - and the stores of a g-point cover 8 consecutive cells = two full 32-byte sectors.  Regular bands only (16 g-points, every contributor covering the band:
 // all rrtmgp-data bands); per-g-point arithmetic is tau_band_cells' expression for expression (same tau_finish), so both
 // mappings give the same results (tests/test_gas_optics_rows_path.py: bit for bit).
 // ---------------------------------------------------------------------------------------------------
+#ifndef RB_ROWS_GPL
+#define RB_ROWS_GPL 4
+#endif
 constexpr int kRowRec = 22;   // Floats per cell record: cm[2], fmj[8], fmn[4], ct, cw, cg, amount_rayl, 6 ints, pad
 __host__ __device__ constexpr size_t tau_rows_warp_bytes() { return (size_t)32 * kRowRec * sizeof(double); }
 
@@ -547,13 +550,16 @@ __device__ __forceinline__ void tau_band_rows(const FusedParams& p, const Tables
   static_assert(sizeof(Float) == 8 || KIND < 0, "double-precision layout (the callers require TablesT::vec == 2)");   // (dependent: checked on instantiation)
   const rrtmgpb_gas_tables& t = p.t;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int j = lane & 7;    // lane j of a cell's eight: g-points bS + 2j, bS + 2j + 1
-  const int cq = lane >> 3;  // which of the 4 cells of a pass
+  // GPL g-points per lane (RB_ROWS_GPL): 2 -> eight lanes per cell, a row is one 128-byte request; 4 -> four lanes per cell, two
+  // requests of 64 bytes per row but half the per-lane pointer arithmetic per g-point
+  constexpr int GPL = RB_ROWS_GPL, LPC = 16 / GPL, CPP = 32 / LPC;   // lanes per cell, cells per pass
+  const int j = lane % LPC;    // lane j of a cell's LPC: g-points bS + GPL*j ... bS + GPL*j + GPL - 1
+  const int cq = lane / LPC;   // which of the CPP cells of a pass
   const size_t ncl = (size_t)p.ncol * p.nlay;
   const size_t cbase_warp = (size_t)(blockIdx.x / p.nband_sub) * (kTauCells * kGThreads) + (size_t)warp * 32;
   const int s_eta = t.ntemp, s_p = t.ntemp * t.neta;
   const size_t d_eta = (size_t)s_eta * tt.gp, d_p = (size_t)s_p * tt.gp;
-  const int gcol = (bi.bS - 1) + 2 * j;  // 0-based table column of this lane's first g-point
+  const int gcol = (bi.bS - 1) + GPL * j;  // 0-based table column of this lane's first g-point
 #pragma unroll   // (fully unrolled: a run-time k would push the callers' per-cell register arrays to local memory)
   for (int k = 0; k < kTauCells; ++k) {
     __syncwarp();   // every lane is done reading the previous records
@@ -573,8 +579,8 @@ __device__ __forceinline__ void tau_band_rows(const FusedParams& p, const Tables
     }
     __syncwarp();
 #pragma unroll 1
-    for (int it = 0; it < 8; ++it) {
-      const int cl = it * 4 + cq;
+    for (int it = 0; it < 32 / CPP; ++it) {
+      const int cl = it * CPP + cq;
       const Float2* r = reinterpret_cast<const Float2*>(rec_warp + (size_t)cl * kRowRec);
       const int4 i0 = reinterpret_cast<const int4*>(r + 9)[0], i1 = reinterpret_cast<const int4*>(r + 9)[1];
       const int flags = i1.y;
@@ -586,16 +592,19 @@ __device__ __forceinline__ void tau_band_rows(const FusedParams& p, const Tables
 #pragma unroll
       for (int q = 0; q < 4; ++q) { const Float2 v = r[1 + q]; f[2 * q] = v.x; f[2 * q + 1] = v.y; }
       { const Float2 v = r[5], w = r[6]; a[0] = v.x; a[1] = v.y; a[2] = w.x; a[3] = w.y; }
-      Float acc[2];
+      Float acc[GPL];
       {  // major absorbers (interpolate3D_byflav :791-801)
         const Float* a0 = tt.kmajor + (size_t)r0 * tt.gp + gcol;
         const Float* b0 = tt.kmajor + (size_t)r1 * tt.gp + gcol;
-        const GLoad<2> x0(a0), x1(a0 + d_eta), x2(a0 + d_p), x3(a0 + d_p + d_eta);
-        const GLoad<2> y0(b0), y1(b0 + d_eta), y2(b0 + d_p), y3(b0 + d_p + d_eta);
 #pragma unroll
-        for (int v = 0; v < 2; ++v)
-          acc[v] = cm.x * (f[0] * x0.v[v] + f[1] * x1.v[v] + f[2] * x2.v[v] + f[3] * x3.v[v]) +
-                   cm.y * (f[4] * y0.v[v] + f[5] * y1.v[v] + f[6] * y2.v[v] + f[7] * y3.v[v]);
+        for (int h = 0; h < GPL; h += 2) {
+          const GLoad<2> x0(a0 + h), x1(a0 + d_eta + h), x2(a0 + d_p + h), x3(a0 + d_p + d_eta + h);
+          const GLoad<2> y0(b0 + h), y1(b0 + d_eta + h), y2(b0 + d_p + h), y3(b0 + d_p + d_eta + h);
+#pragma unroll
+          for (int v = 0; v < 2; ++v)
+            acc[h + v] = cm.x * (f[0] * x0.v[v] + f[1] * x1.v[v] + f[2] * x2.v[v] + f[3] * x3.v[v]) +
+                         cm.y * (f[4] * y0.v[v] + f[5] * y1.v[v] + f[6] * y2.v[v] + f[7] * y3.v[v]);
+        }
       }
       {  // minor absorbers (:451-498); regular band: every contributor starts at the band's first g-point
         const MinorInfo* minfo = tr ? tt.aux.minor_lower : tt.aux.minor_upper;
@@ -603,33 +612,41 @@ __device__ __forceinline__ void tau_band_rows(const FusedParams& p, const Tables
         const int mpitch = tr ? tt.nkl : tt.nku;
         const int mfirst = tr ? bi.mfirst[0] : bi.mfirst[1], mlast = tr ? bi.mlast[0] : bi.mlast[1];
         const size_t de = (size_t)s_eta * mpitch;
-        const Float* m0 = kminor + (size_t)((jt - 1) + s_eta * (je0 - 1)) * mpitch + 2 * j - 1;   // + kstart below
-        const Float* m1 = kminor + (size_t)(jt + s_eta * (je1 - 1)) * mpitch + 2 * j - 1;
+        const Float* m0 = kminor + (size_t)((jt - 1) + s_eta * (je0 - 1)) * mpitch + GPL * j - 1;   // + kstart below
+        const Float* m1 = kminor + (size_t)(jt + s_eta * (je1 - 1)) * mpitch + GPL * j - 1;
         const Float* sc = scal_block + (size_t)k * kGThreads + warp * 32 + cl;
         for (int imnr = mfirst; imnr <= mlast; ++imnr) {
           const Float scaling = sc[(size_t)(imnr - mfirst) * kTauCells * kGThreads];
           const int ks = minfo[imnr].kstart;
-          const GLoad<2> x0(m0 + ks), x1(m0 + de + ks), y0(m1 + ks), y1(m1 + de + ks);
 #pragma unroll
-          for (int v = 0; v < 2; ++v) {
-            const Float kint = a[0] * x0.v[v] + a[1] * x1.v[v] + a[2] * y0.v[v] + a[3] * y1.v[v];  // :757-760
-            acc[v] = acc[v] + scaling * kint;                                                     // :493
+          for (int h = 0; h < GPL; h += 2) {
+            const GLoad<2> x0(m0 + ks + h), x1(m0 + de + ks + h), y0(m1 + ks + h), y1(m1 + de + ks + h);
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              const Float kint = a[0] * x0.v[v] + a[1] * x1.v[v] + a[2] * y0.v[v] + a[3] * y1.v[v];  // :757-760
+              acc[h + v] = acc[h + v] + scaling * kint;                                             // :493
+            }
           }
         }
       }
-      Float tray[2] = {0, 0};
+      Float tray[GPL];
+#pragma unroll
+      for (int v = 0; v < GPL; ++v) tray[v] = 0;
       const Float2 c01 = r[7], c23 = r[8];   // (ct, cw), (cg, amount_rayl)
       if (SW) {  // Rayleigh (:554-559)
         const Float* kr = tt.krayl + (size_t)s_p * tt.gp * (tr ? 0 : 1) + gcol;
         const Float* q0 = kr + (size_t)((jt - 1) + s_eta * (je0 - 1)) * tt.gp;
         const Float* q1 = kr + (size_t)(jt + s_eta * (je1 - 1)) * tt.gp;
-        const GLoad<2> x0(q0), x1(q0 + d_eta), y0(q1), y1(q1 + d_eta);
 #pragma unroll
-        for (int v = 0; v < 2; ++v) tray[v] = (a[0] * x0.v[v] + a[1] * x1.v[v] + a[2] * y0.v[v] + a[3] * y1.v[v]) * c23.y;
+        for (int h = 0; h < GPL; h += 2) {
+          const GLoad<2> x0(q0 + h), x1(q0 + d_eta + h), y0(q1 + h), y1(q1 + d_eta + h);
+#pragma unroll
+          for (int v = 0; v < 2; ++v) tray[h + v] = (a[0] * x0.v[v] + a[1] * x1.v[v] + a[2] * y0.v[v] + a[3] * y1.v[v]) * c23.y;
+        }
       }
       const size_t o = cbase_warp + (size_t)k * kGThreads + cl + ncl * (size_t)(gcol - p.gpt0);
 #pragma unroll
-      for (int v = 0; v < 2; ++v)
+      for (int v = 0; v < GPL; ++v)
         tau_finish<SW, false, KIND, true, ABI>(p, c01.x, c01.y, c23.x, (Float)0, (Float)0, (Float)0, true, o + ncl * (size_t)v, acc[v],
                                                tray[v]);
     }
@@ -734,8 +751,8 @@ __global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_L
     const int tr_lane0 = __shfl_sync(full, (int)tropo[0], 0);
     const bool same = shared_rows && regular && row0[0] == r0_lane0 && row1[0] == r1_lane0 && (int)tropo[0] == tr_lane0;
     const unsigned votes = ROWS ? __ballot_sync(full, same) : (__all_sync(full, same) ? full : 0u);
-    // ---- unrelated columns (fewer than p.rows_path = 28 of the lanes share rows even between their own two cells - profiles
-    // of one data set coincide in some T / p / eta bins by chance, so the count is rarely near zero; warps above the threshold,
+    // ---- unrelated columns (fewer than p.rows_path = 32 of the lanes share rows between their own two cells - profiles of one
+    // data set coincide in some T / p / eta bins by chance, so the count is rarely near zero; warps in which every lane shares,
     // e.g. stratospheric layers where every profile falls into the same bins, are better off below): the warp takes the
     // lanes-along-g-points mapping; its records overlay the staging slots it will not use
     if constexpr (ROWS) {
