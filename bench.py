@@ -330,13 +330,9 @@ def make_config(b, name, ncol=None):
         prof = _tile(syn.perturbed_profiles(1800, 60, seed=1234, top_at_1=True), n)
         sky = AllSky(ctx, n, 60, syn.make_kdist("lw"), syn.make_kdist("sw"), profiles=prof, do_clouds=False, col_offset=b.rank * n)
 
-        def step():   # unrelated neighbouring columns: the tau kernels' lanes-along-g-points mapping (a run-time option of the
-            b.lib.cdll.rrtmgpb_set_gas_optics_rows_path(1)   # library, include/rrtmgp_b200_ext.h; same results either way)
-            try:
-                sky.step()
-            finally:
-                b.lib.cdll.rrtmgpb_set_gas_optics_rows_path(-1)
-        return step, n, {"ncol_per_gpu": n, "nlay": 60, "resident": True, "gas_optics_rows_path": 1}, sky
+        # (unrelated neighbouring columns: from the second step on the library picks the tau kernels' lanes-along-g-points
+        #  mapping by itself - rrtmgpb_set_gas_optics_rows_path, include/rrtmgp_b200_ext.h; same results either way)
+        return sky.step, n, {"ncol_per_gpu": n, "nlay": 60, "resident": True, "gas_optics_rows_path": "automatic"}, sky
     if name == "c4":
         n, chunk = ncol or 524288, 37888   # 8 solver waves per chunk
         h = HostAllSky(b.lib, n, NLAY, syn.make_kdist("lw", ngpt=128), syn.make_kdist("sw", ngpt=112), chunk, device=b.device)

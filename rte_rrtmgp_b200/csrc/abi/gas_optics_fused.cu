@@ -37,8 +37,12 @@ constexpr int kFThreads = 128;
 
 // ---- per-cell state: mo_gas_optics_utils.F90:143-150 (col_dry), mo_gas_optics_rrtmgp_kernels.F90:99-118,
 // and the per-cell factors of the minor scaling :467-471 ----
+// stat (optional): a sampled count of neighbouring cells (consecutive columns of a layer) that fall into different
+// temperature / pressure bins or atmosphere halves - {differing pairs, pairs looked at} - from every 64th block; the host
+// reads the PREVIOUS call's counts to choose the tau kernels' thread mapping (launch_tau: automatic rows path)
+constexpr int kStatEvery = 64;
 __global__ void __launch_bounds__(kFThreads) cell_state_kernel(const FusedParams p, Float m_dry, Float m_h2o,
-                                                                Float avogad, Float grav) {
+                                                                Float avogad, Float grav, int* stat) {
   const size_t ncl = (size_t)p.ncol * p.nlay;
   const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncl) return;
@@ -72,6 +76,38 @@ __global__ void __launch_bounds__(kFThreads) cell_state_kernel(const FusedParams
   p.cs.pt_scale[c] = (Float)0.01 * pl / tl;                                // :467
   p.cs.vmr_fact[c] = vmr_fact;
   p.cs.dry_fact[c] = (Float)1 / ((Float)1 + (vh2o * col_dry) * vmr_fact);  // :471, col_gas(h2o) = vmr*col_dry
+  if (stat && blockIdx.x % kStatEvery == 0) {
+    const unsigned act = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int key = jtemp | ((int)jpress_aint << 8) | ((pl > press_ref_trop) ? (1 << 16) : 0);
+    const int nxt = __shfl_down_sync(act, key, 1);
+    const bool has_next = lane < 31 && ((act >> (lane + 1)) & 1u);
+    const unsigned differ = __ballot_sync(act, has_next && nxt != key), pairs = __ballot_sync(act, has_next);
+    if (lane == __ffs(act) - 1) {
+      atomicAdd(stat, __popc(differ));
+      atomicAdd(stat + 1, __popc(pairs));
+    }
+  }
+}
+
+// per host thread: device counters of cell_state_kernel and their pinned host mirror (copied back stream-ordered after every
+// call; read - never waited for - by the next call)
+struct RowsStat {
+  int* d = nullptr;
+  int* h = nullptr;
+  int device = -1;
+};
+RowsStat& rows_stat() {
+  thread_local RowsStat st;
+  int dev = 0;
+  RB_CUDA_CHECK(cudaGetDevice(&dev));
+  if (st.device != dev) {   // first use on this thread, or the thread moved to another device (the old pair is abandoned)
+    RB_CUDA_CHECK(cudaMalloc(&st.d, 2 * sizeof(int)));
+    RB_CUDA_CHECK(cudaHostAlloc(&st.h, 2 * sizeof(int), cudaHostAllocDefault));
+    st.h[0] = st.h[1] = 0;
+    st.device = dev;
+  }
+  return st;
 }
 
 struct Workspace {
@@ -98,9 +134,12 @@ Workspace prepare(FusedParams& p) {
   p.cs = w.cs;
   {
     KernelTimer timer("gas_cell_state");
+    RowsStat& st = rows_stat();
+    RB_CUDA_CHECK(cudaMemsetAsync(st.d, 0, 2 * sizeof(int), stream()));
     cell_state_kernel<<<ceil_div((long long)ncl, kFThreads), kFThreads, 0, stream()>>>(
-        p, (Float)g_m_dry, (Float)k_m_h2o, (Float)k_avogad, (Float)g_grav);
+        p, (Float)g_m_dry, (Float)k_m_h2o, (Float)k_avogad, (Float)g_grav, st.d);
     RB_LAUNCH_CHECK();
+    RB_CUDA_CHECK(cudaMemcpyAsync(st.h, st.d, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
   }
   return w;
 }
@@ -385,7 +424,16 @@ void launch_tau(const FusedParams& p, const TablesT& tt, bool abi = false) {
   const bool stage = stage_env && tt.vec == 2 && !aer_kind && kTG * kTauRegChunks == 16;
   // lanes-along-g-points mapping for warps of unrelated columns (tau_band_rows): its records overlay the warp's staging
   // slots.  RRTMGPB_TAU_ROWS=0/1 (A/B switch)
-  static const bool rows_env = [] { const char* e = std::getenv("RRTMGPB_TAU_ROWS"); return e && e[0] == '1'; }();
+  // rows_env: RRTMGPB_TAU_ROWS = 0 (never) / 1 (always the ROWS instantiations) / unset (-1: automatic - the ROWS instantiations
+  // when, in the previous call's sample, more than one in eight neighbouring cells fell into different T / p bins)
+  static const int rows_env_raw = [] { const char* e = std::getenv("RRTMGPB_TAU_ROWS"); return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1; }();
+  int rows_auto = 0;
+  if (!abi) {
+    const RowsStat& st = rows_stat();
+    const int differ = st.h[0], pairs = st.h[1];   // (a torn or stale read only delays the switch by a call)
+    rows_auto = (pairs > 0 && differ * 8 > pairs) ? 1 : 0;
+  }
+  const bool rows_env = rows_env_raw < 0 ? rows_auto != 0 : rows_env_raw != 0;
   const int rows_set = g_tau_rows.load(std::memory_order_relaxed);   // rrtmgpb_set_gas_optics_rows_path: -1 = environment
   FusedParams pr = p;
   // 0: off; otherwise the vote threshold of the ROWS instantiations: a warp re-maps when fewer than this many of its lanes share

@@ -70,3 +70,26 @@ def test_rows_path_mixed_and_ragged(oracle_lib, cuda_lib):
         pg, pc = _planes(g), _planes(c)
         for k in pc:
             np.testing.assert_allclose(pg[k], pc[k], rtol=1e-12, atol=1e-300, err_msg=k)
+
+
+@pytest.mark.gpu
+def test_rows_path_automatic_selection(oracle_lib, cuda_lib):
+    """Default setting (-1, RRTMGPB_TAU_ROWS unset): the fused entry samples how often neighbouring cells fall into different
+    T / p bins and the NEXT call picks the kernel instantiation from that.  Whatever it picks - distinct columns after
+    replicated ones, replicated after distinct - every step must give the same planes as the pinned mappings."""
+    kd_lw, kd_sw = syn.make_kdist("lw"), syn.make_kdist("sw")
+    ncol, nlay = 512, 60
+    prof = syn.perturbed_profiles(ncol, nlay, seed=21, top_at_1=True)
+    cuda_lib.cdll.rrtmgpb_set_gas_optics_rows_path(0)
+    try:
+        ref_d = _planes(_run(cuda_lib, "cuda:0", ncol, nlay, kd_lw, kd_sw, prof, False, True))
+        ref_r = _planes(_run(cuda_lib, "cuda:0", ncol, nlay, kd_lw, kd_sw, None, True, True))
+    finally:
+        cuda_lib.cdll.rrtmgpb_set_gas_optics_rows_path(-1)
+    d = AllSky(Context(cuda_lib, "cuda:0"), ncol, nlay, kd_lw, kd_sw, do_clouds=False, profiles=prof, fused=True)
+    r = AllSky(Context(cuda_lib, "cuda:0"), ncol, nlay, kd_lw, kd_sw, do_clouds=True, fused=True)
+    for sky, ref in ((d, ref_d), (d, ref_d), (r, ref_r), (r, ref_r), (d, ref_d), (d, ref_d)):
+        sky.step()
+        got = _planes(sky)
+        for k in ref:
+            assert np.array_equal(got[k], ref[k]), k
