@@ -421,7 +421,7 @@ void launch_tau(const FusedParams& p, const TablesT& tt, bool abi = false) {
   // table rows staged per warp by cp.async.bulk when the warp's cells share them (gas_tau_g_kernel STAGE); needs the
   // 128-bit layout (tt.vec == 2) and 16-g-point chunks; RRTMGPB_TABLE_TMA=0 switches it off
   static const bool stage_env = [] { const char* e = std::getenv("RRTMGPB_TABLE_TMA"); return !(e && e[0] == '0'); }();
-  const bool stage = stage_env && tt.vec == 2 && !aer_kind && kTG * kTauRegChunks == 16;
+  const bool stage = stage_env && tt.vec == 2 && kTG * kTauRegChunks == 16;   // (also with a second, aerosol increment: config 5)
   // lanes-along-g-points mapping for warps of unrelated columns (tau_band_rows): its records overlay the warp's staging
   // slots.  RRTMGPB_TAU_ROWS=0/1 (A/B switch)
   // rows_env: RRTMGPB_TAU_ROWS = 0 (never) / 1 (always the ROWS instantiations) / unset (-1: automatic - the ROWS instantiations
@@ -455,8 +455,8 @@ void launch_tau(const FusedParams& p, const TablesT& tt, bool abi = false) {
       launch_tau_rows(pr, tt, grid, smem, SWV, KINDV, false);                                                     \
       break;                                                                                                      \
     }                                                                                                             \
-    auto kern = (stage && VECV == 2 && !AERV) ? gas_tau_g_kernel<SWV, VECV, AERV, KINDV, (VECV == 2 && !AERV)>    \
-                                              : gas_tau_g_kernel<SWV, VECV, AERV, KINDV, false>;                  \
+    auto kern = (stage && VECV == 2) ? gas_tau_g_kernel<SWV, VECV, AERV, KINDV, (VECV == 2)>                      \
+                                     : gas_tau_g_kernel<SWV, VECV, AERV, KINDV, false>;                           \
     if (smem > 48 * 1024) RB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, kGThreads, smem, stream()>>>(pr, tt);                                                             \
   } while (0)

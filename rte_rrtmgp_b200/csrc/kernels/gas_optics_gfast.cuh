@@ -664,7 +664,7 @@ __device__ __forceinline__ void tau_band_rows(const FusedParams& p, const Tables
 // LW tau 4.38 -> 4.60 ms on the replicated profile with the path compiled in but never taken); the host launches it when
 // rrtmgpb_set_gas_optics_rows_path(1) / RRTMGPB_TAU_ROWS=1 says the columns are unrelated.
 template <bool SW, int VEC, bool AER, int KIND, bool STAGE = false, bool ABI = false, bool ROWS = false>
-__global__ void __launch_bounds__(kGThreads, SW ? RB_TAU_MINB_SW : RB_TAU_MINB_LW) gas_tau_g_kernel(const FusedParams p, const TablesT tt) {
+__global__ void __launch_bounds__(kGThreads, (SW || AER) ? RB_TAU_MINB_SW : RB_TAU_MINB_LW) gas_tau_g_kernel(const FusedParams p, const TablesT tt) {
   const rrtmgpb_gas_tables& t = p.t;
   const size_t ncl = (size_t)p.ncol * p.nlay;
   const int ibnd = p.band0 + blockIdx.x % p.nband_sub;
