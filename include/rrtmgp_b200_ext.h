@@ -71,8 +71,8 @@ void rrtmgpb_init_constants(const Float* gravity, const Float* mol_weight_dry_ai
 /* Gas-optics tau kernels: blocks whose cells do not share table rows (unrelated neighbouring columns) may take a second
  * thread mapping - 4 lanes along the 16 g-points of one cell instead of one cell pair per thread (csrc/kernels/
  * gas_optics_gfast.cuh: tau_band_rows).  1 = on, 0 = off, -1 (default) = the environment's RRTMGPB_TAU_ROWS (0 / 1; unset: AUTOMATIC -
- * the fused entry samples how often neighbouring cells fall into different temperature / pressure bins and the next call picks
- * the kernel instantiation from that; the extern symbols have no such sample and stay on the default mapping); 2..33 = on with that
+ * the fused entry and rrtmgp_compute_tau_absorption (with cached table copies) sample how often neighbouring cells fall into
+ * different temperature / pressure bins and the calling thread's next call picks the kernel instantiation from that); 2..33 = on with that
  * vote threshold (a warp re-maps when fewer than this many lanes share rows between their two cells; 1 means 32).  Same results either way. */
 void rrtmgpb_set_gas_optics_rows_path(int on);
 

@@ -41,6 +41,19 @@ constexpr int kFThreads = 128;
 // temperature / pressure bins or atmosphere halves - {differing pairs, pairs looked at} - from every 64th block; the host
 // reads the PREVIOUS call's counts to choose the tau kernels' thread mapping (launch_tau: automatic rows path)
 constexpr int kStatEvery = 64;
+__device__ __forceinline__ void neighbour_stat(int* stat, int jtemp, int jpress, bool tropo) {
+  if (!stat || blockIdx.x % kStatEvery != 0) return;
+  const unsigned act = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int key = jtemp | (jpress << 8) | (tropo ? (1 << 16) : 0);
+  const int nxt = __shfl_down_sync(act, key, 1);
+  const bool has_next = lane < 31 && ((act >> (lane + 1)) & 1u);
+  const unsigned differ = __ballot_sync(act, has_next && nxt != key), pairs = __ballot_sync(act, has_next);
+  if (lane == __ffs(act) - 1) {
+    atomicAdd(stat, __popc(differ));
+    atomicAdd(stat + 1, __popc(pairs));
+  }
+}
 __global__ void __launch_bounds__(kFThreads) cell_state_kernel(const FusedParams p, Float m_dry, Float m_h2o,
                                                                 Float avogad, Float grav, int* stat) {
   const size_t ncl = (size_t)p.ncol * p.nlay;
@@ -76,18 +89,7 @@ __global__ void __launch_bounds__(kFThreads) cell_state_kernel(const FusedParams
   p.cs.pt_scale[c] = (Float)0.01 * pl / tl;                                // :467
   p.cs.vmr_fact[c] = vmr_fact;
   p.cs.dry_fact[c] = (Float)1 / ((Float)1 + (vh2o * col_dry) * vmr_fact);  // :471, col_gas(h2o) = vmr*col_dry
-  if (stat && blockIdx.x % kStatEvery == 0) {
-    const unsigned act = __activemask();
-    const int lane = threadIdx.x & 31;
-    const int key = jtemp | ((int)jpress_aint << 8) | ((pl > press_ref_trop) ? (1 << 16) : 0);
-    const int nxt = __shfl_down_sync(act, key, 1);
-    const bool has_next = lane < 31 && ((act >> (lane + 1)) & 1u);
-    const unsigned differ = __ballot_sync(act, has_next && nxt != key), pairs = __ballot_sync(act, has_next);
-    if (lane == __ffs(act) - 1) {
-      atomicAdd(stat, __popc(differ));
-      atomicAdd(stat + 1, __popc(pairs));
-    }
-  }
+  neighbour_stat(stat, jtemp, (int)jpress_aint, pl > press_ref_trop);
 }
 
 // per host thread: device counters of cell_state_kernel and their pinned host mirror (copied back stream-ordered after every
@@ -428,7 +430,7 @@ void launch_tau(const FusedParams& p, const TablesT& tt, bool abi = false) {
   // when, in the previous call's sample, more than one in eight neighbouring cells fell into different T / p bins)
   static const int rows_env_raw = [] { const char* e = std::getenv("RRTMGPB_TAU_ROWS"); return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : -1; }();
   int rows_auto = 0;
-  if (!abi) {
+  {
     const RowsStat& st = rows_stat();
     const int differ = st.h[0], pairs = st.h[1];   // (a torn or stale read only delays the switch by a call)
     rows_auto = (pairs > 0 && differ * 8 > pairs) ? 1 : 0;
@@ -510,13 +512,16 @@ namespace {
 // the three per-cell factors of the minor scaling (:467-471) from the caller's play, tlay, col_gas
 __global__ void __launch_bounds__(kFThreads) abi_cell_prep_kernel(size_t ncl, int idx_h2o, const Float* __restrict__ play,
                                                                    const Float* __restrict__ tlay, const Float* __restrict__ col_gas,
-                                                                   Float* pt_scale, Float* vmr_fact, Float* dry_fact) {
+                                                                   const int* __restrict__ jtemp, const int* __restrict__ jpress,
+                                                                   const Bool* __restrict__ tropo, Float* pt_scale, Float* vmr_fact,
+                                                                   Float* dry_fact, int* stat) {
   const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncl) return;
   const Float vf = (Float)1 / col_gas[c];                                        // :470, col_gas(:,:,0) = col_dry
   pt_scale[c] = (Float)0.01 * play[c] / tlay[c];                                 // :467
   vmr_fact[c] = vf;
   dry_fact[c] = (Float)1 / ((Float)1 + col_gas[c + ncl * (size_t)idx_h2o] * vf); // :471
+  neighbour_stat(stat, jtemp[c], jpress[c], tropo[c]);   // (see cell_state_kernel: the next call's choice of thread mapping)
 }
 }  // namespace
 
@@ -550,9 +555,12 @@ bool tau_absorption_gfast(int ncol, int nlay, int nbnd, int ngpt, int ngas, int 
   Float* prep = static_cast<Float*>(dev_alloc(3 * ncl * sizeof(Float)));
   {
     KernelTimer timer("tau_absorption_cell_prep");
-    abi_cell_prep_kernel<<<ceil_div((long long)ncl, kFThreads), kFThreads, 0, stream()>>>(ncl, idx_h2o, play, tlay, col_gas, prep,
-                                                                                             prep + ncl, prep + 2 * ncl);
+    RowsStat& st = rows_stat();
+    RB_CUDA_CHECK(cudaMemsetAsync(st.d, 0, 2 * sizeof(int), stream()));
+    abi_cell_prep_kernel<<<ceil_div((long long)ncl, kFThreads), kFThreads, 0, stream()>>>(ncl, idx_h2o, play, tlay, col_gas, jtemp, jpress,
+                                                                                             tropo, prep, prep + ncl, prep + 2 * ncl, st.d);
     RB_LAUNCH_CHECK();
+    RB_CUDA_CHECK(cudaMemcpyAsync(st.h, st.d, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
   }
   FusedParams p{};
   p.t = t;
