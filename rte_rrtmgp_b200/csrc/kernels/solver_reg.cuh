@@ -237,8 +237,17 @@ __host__ __device__ constexpr int lw_noscat_reg_slots() { return 3 * CL + 1 + 5;
 // TMA variant (see the SW kernel and kernels/tma.cuh): tau, lay_source (nlay rows) and lev_source (nlay+1 rows) tiles
 // by cp.async.bulk.tensor, two stages; the five per-(column, g-point) values keep their lane-private cp.async slots.
 struct LwTmaMaps { CUtensorMap tau, lay, lev; };
+// RB_LW_STAGES: depth of the TMA ring of lw_noscat_reg_kernel (g-points in flight per CTA).  Neither the fp64 pipe (53 %) nor
+// issue (51 %) nor DRAM (4.8 of 6.9 TB/s) is saturated under ncu, which suggested too few bytes in flight (two stages keep
+// ~57 KB per SM outstanding); a third stage doubles that and changes nothing: 5.84 vs 5.85 ms on B200 (and 60 layers in padded
+// 72-row tiles take the same 5.8 ms as 72): the kernel's time is per g-point iteration - dependent-issue latency of the
+// scans with two warps per scheduler - not per byte.  2 stays.
+#ifndef RB_LW_STAGES
+#define RB_LW_STAGES 2
+#endif
 __host__ __device__ inline size_t lw_noscat_reg_tma_smem(int nlay, int nthreads = kRegThreads) {
-  return 2 * (2 * tile_bytes(nlay) + tile_bytes(nlay + 1)) + (size_t)(2 * 5) * nthreads * sizeof(Float) + 2 * sizeof(uint64_t);
+  return RB_LW_STAGES * (2 * tile_bytes(nlay) + tile_bytes(nlay + 1)) + (size_t)(RB_LW_STAGES * 5) * nthreads * sizeof(Float) +
+         RB_LW_STAGES * sizeof(uint64_t);
 }
 
 // FULL = 1: nlay == 8*CL, every lane's cells are real layers - the padding selects and tests fold away at compile time;
@@ -255,10 +264,11 @@ __global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? MINB : 1) lw_nosc
   const size_t tb_lay = TMA ? tile_bytes(tile_rows) : 0, tb_lev = TMA ? tile_bytes(tile_rows + 1) : 0;
   const size_t stageb = 2 * tb_lay + tb_lev;
   const int te_lay = (int)(tb_lay / sizeof(Float));
-  Float* sm = reinterpret_cast<Float*>(smem_raw + 2 * stageb);  // cp.async slots
+  constexpr int NSTG = TMA ? RB_LW_STAGES : 2;                     // ring depth (tiles and boundary-value slots)
+  Float* sm = reinterpret_cast<Float*>(smem_raw + NSTG * stageb);  // cp.async slots
   constexpr int NS = TMA ? 5 : lw_noscat_reg_slots<CL>();
   constexpr int BC0 = TMA ? -1 : 3 * CL;                          // boundary-value slots are BC0+1 .. BC0+5
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm + (size_t)2 * NS * kRegThreads);  // TMA: [2] mbarriers
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sm + (size_t)NSTG * NS * kRegThreads);  // TMA: [NSTG] mbarriers
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = lane / kRegChunks, j = lane % kRegChunks;
   const int col_raw = (blockIdx.x * (kRegThreads / 32) + warp) * kRegCols + c;
@@ -322,23 +332,26 @@ __global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? MINB : 1) lw_nosc
 
   if (TMA) {
     if (threadIdx.x == 0) {
-      mbar_init(&full_bar[0], 1);
-      mbar_init(&full_bar[1], 1);
+#pragma unroll
+      for (int i = 0; i < NSTG; ++i) mbar_init(&full_bar[i], 1);
       mbar_fence_init();
     }
     __syncthreads();
   }
   if (gb < ge) prefetch(gb, 0);
   cp_async_commit();
-  if (TMA) {  // two g-points in flight; the stage of g is refilled for g+2 at the end of iteration g
-    if (gb + 1 < ge) prefetch(gb + 1, 1);
-    cp_async_commit();
+  if (TMA) {  // NSTG g-points in flight; the stage of g is refilled for g+NSTG at the end of iteration g
+#pragma unroll
+    for (int i = 1; i < NSTG; ++i) {
+      if (gb + i < ge) prefetch(gb + i, i);
+      cp_async_commit();
+    }
   }
   for (int g = gb; g < ge; ++g) {
-    const int s = (g - gb) & 1;
+    const int s = TMA ? (g - gb) % NSTG : (g - gb) & 1;
     if (TMA) {
-      cp_async_wait<1>();                                         // boundary values of g (groups g, g+1 outstanding)
-      mbar_wait(&full_bar[s], (uint32_t)(((g - gb) >> 1) & 1));   // tiles of g
+      cp_async_wait<NSTG - 1>();                                       // boundary values of g (groups g .. g+NSTG-1 outstanding)
+      mbar_wait(&full_bar[s], (uint32_t)(((g - gb) / NSTG) & 1));      // tiles of g
     } else {
       if (g + 1 < ge) prefetch(g + 1, s ^ 1);
       cp_async_commit();
@@ -440,7 +453,7 @@ __global__ void __launch_bounds__(reg_threads(NCH), NCH == 8 ? MINB : 1) lw_nosc
     }
     if (TMA) {  // every warp of the CTA is done with stage s (all angles): hand it back to the TMA for g+2
       __syncthreads();
-      if (g + 2 < ge) prefetch(g + 2, s);
+      if (g + NSTG < ge) prefetch(g + NSTG, s);
       cp_async_commit();
     }
   }
