@@ -74,3 +74,98 @@ def test_cloud_lut_numpy_equals_c_oracle(oracle_lib):
     ref = npg.compute_cld_from_table(mask, lwp, re, nsteps, step, lut.radliq_lwr, lut.extliq, lut.ssaliq, lut.asyliq)
     for a, b in zip(got, ref):
         assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The two-stream flux solvers: the oracle (oracle/rte_solver_ref.c) against tests/numpy_solvers.py, an independent numpy
+# transcription of mo_rte_solver_kernels.F90 (lw_solver_2stream, sw_solver_2stream, adding) - bit for bit.
+# ---------------------------------------------------------------------------------------------------------------------
+import numpy_solvers as nps  # noqa: E402
+from rte_rrtmgp_b200.abi import fzeros  # noqa: E402
+
+
+def _sw_case(ncol, nlay, ngpt, seed):
+    rng = np.random.default_rng(seed)
+    mu0 = np.asfortranarray(np.repeat(rng.uniform(-0.2, 1.0, ncol)[:, None], nlay, axis=1))
+    mu0[1] = rng.uniform(0.05, 1.0, nlay)                  # a column whose mu0 varies with height
+    mu0[2, nlay // 2:] = -0.1                              # the sun sets part of the way down the column
+    tau = np.asfortranarray(10.0 ** rng.uniform(-7, 2.0, (ncol, nlay, ngpt)))
+    tau[0, 0, 0] = 0.0
+    return dict(tau=tau, ssa=np.asfortranarray(rng.uniform(0, 1.0, (ncol, nlay, ngpt))),
+                g=np.asfortranarray(rng.uniform(-0.5, 0.95, (ncol, nlay, ngpt))), mu0=mu0,
+                adir=np.asfortranarray(rng.uniform(0, 0.7, (ncol, ngpt))), adif=np.asfortranarray(rng.uniform(0, 0.7, (ncol, ngpt))),
+                inc=np.asfortranarray(10.0 * rng.random((ncol, ngpt))), dif=np.asfortranarray(2.0 * rng.random((ncol, ngpt))))
+
+
+@pytest.mark.parametrize("top_at_1", [True, False])
+@pytest.mark.parametrize("bb,bc", [(True, False), (True, True), (False, False), (False, True)])
+def test_numpy_sw_solver_2stream_equals_c_oracle(oracle_lib, top_at_1, bb, bc):
+    x = _sw_case(11, 23, 5, seed=41)
+    ncol, nlay, ngpt = x["tau"].shape
+    gup, gdn, gdr = (fzeros((ncol, nlay + 1, ngpt)) for _ in range(3))
+    bup, bdn, bdr = (fzeros((ncol, nlay + 1)) for _ in range(3))
+    oracle_lib.rte_sw_solver_2stream(ncol, nlay, ngpt, top_at_1, x["tau"], x["ssa"], x["g"], x["mu0"], x["adir"], x["adif"], x["inc"],
+                                     gup, gdn, gdr, bc, x["dif"], bb, bup, bdn, bdr)
+    got = (bup, bdn, bdr) if bb else (gup, gdn, gdr)
+    ref = nps.sw_solver_2stream(top_at_1, x["tau"], x["ssa"], x["g"], x["mu0"], x["adir"], x["adif"], x["inc"], bc, x["dif"], bb)
+    for a, b, n in zip(got, ref, ("up", "dn", "dir")):
+        assert np.max(np.abs(b)) > 0
+        assert np.array_equal(a, b), f"{n}: max diff {np.max(np.abs(a - b)):.3e}"
+
+
+@pytest.mark.parametrize("top_at_1", [True, False])
+@pytest.mark.parametrize("lev_per_gpt", [False, True])
+def test_numpy_lw_solver_2stream_equals_c_oracle(oracle_lib, top_at_1, lev_per_gpt):
+    """Both readings of lev_source: the serial kernel as written (every g-point sees g-point 1's level source,
+    mo_rte_solver_kernels.F90:422) and per g-point (the accelerator kernels)."""
+    rng = np.random.default_rng(43)
+    ncol, nlay, ngpt = 9, 21, 4
+    tau = np.asfortranarray(10.0 ** rng.uniform(-9.5, 1.5, (ncol, nlay, ngpt)))   # some below the 1e-8 source cut (:947)
+    ssa = np.asfortranarray(rng.uniform(0, 1.0, (ncol, nlay, ngpt)))
+    g = np.asfortranarray(rng.uniform(-0.4, 0.9, (ncol, nlay, ngpt)))
+    lev = np.asfortranarray(50.0 + 100.0 * rng.random((ncol, nlay + 1, ngpt)))
+    lay = np.asfortranarray(0.5 * (lev[:, 1:] + lev[:, :-1]))
+    emis = np.asfortranarray(0.8 + 0.2 * rng.random((ncol, ngpt)))
+    sfc = np.asfortranarray(100.0 + 50.0 * rng.random((ncol, ngpt)))
+    inc = np.asfortranarray(5.0 * rng.random((ncol, ngpt)))
+    gup, gdn = (fzeros((ncol, nlay + 1, ngpt)) for _ in range(2))
+    oracle_lib.cdll.rrtmgpb_set_lw_2stream_lev_source_per_gpt(1 if lev_per_gpt else 0)
+    try:
+        oracle_lib.rte_lw_solver_2stream(ncol, nlay, ngpt, top_at_1, tau, ssa, g, lay, lev, emis, sfc, inc, gup, gdn)
+    finally:
+        oracle_lib.cdll.rrtmgpb_set_lw_2stream_lev_source_per_gpt(0)
+    fu, fd = nps.lw_solver_2stream(top_at_1, tau, ssa, g, lay, lev, emis, sfc, inc, lev_per_gpt)
+    assert np.array_equal(gup, fu), f"up: max diff {np.max(np.abs(gup - fu)):.3e}"
+    assert np.array_equal(gdn, fd), f"dn: max diff {np.max(np.abs(gdn - fd)):.3e}"
+
+
+@pytest.mark.parametrize("top_at_1", [True, False])
+@pytest.mark.parametrize("nmus,bb,jac,resc", [(1, True, False, False), (1, False, False, False), (3, True, True, False),
+                                              (2, False, True, False), (1, True, True, True), (2, False, False, True)])
+def test_numpy_lw_solver_noscat_equals_c_oracle(oracle_lib, top_at_1, nmus, bb, jac, resc):
+    """Every flag combination of rte_lw_solver_noscat: broadband / g-point fluxes, 1-3 quadrature angles, surface-temperature
+    Jacobian, Tang rescaling (with its orientation-asymmetric second sweep, mo_rte_solver_kernels.F90:801-804 vs :835-838)."""
+    rng = np.random.default_rng(47)
+    ncol, nlay, ngpt = 8, 19, 4
+    tau = np.asfortranarray(10.0 ** rng.uniform(-7, 1.5, (ncol, nlay, ngpt)))     # both branches of the weighting factor (:652-656)
+    lev = np.asfortranarray(50.0 + 100.0 * rng.random((ncol, nlay + 1, ngpt)))
+    lay = np.asfortranarray(0.5 * (lev[:, 1:] + lev[:, :-1]) + rng.uniform(-1, 1, (ncol, nlay, ngpt)))
+    emis = np.asfortranarray(0.8 + 0.2 * rng.random((ncol, ngpt)))
+    sfc = np.asfortranarray(100.0 + 50.0 * rng.random((ncol, ngpt)))
+    sjac = np.asfortranarray(rng.random((ncol, ngpt)))
+    inc = np.asfortranarray(5.0 * rng.random((ncol, ngpt)))
+    ssa = np.asfortranarray(rng.uniform(0, 0.9, (ncol, nlay, ngpt)))
+    g = np.asfortranarray(rng.uniform(-0.2, 0.9, (ncol, nlay, ngpt)))
+    Ds = np.asfortranarray(np.stack([np.full((ncol, ngpt), 1.0 / m) for m in (0.61, 0.25, 0.79)[:nmus]], axis=2))
+    wts = np.array([1.0, 0.23, 0.77][:nmus]) if nmus > 1 else np.array([1.0])
+    gup, gdn = fzeros((ncol, nlay + 1, ngpt)), fzeros((ncol, nlay + 1, ngpt))
+    bup, bdn, fj = (fzeros((ncol, nlay + 1)) for _ in range(3))
+    oracle_lib.rte_lw_solver_noscat(ncol, nlay, ngpt, top_at_1, nmus, Ds, wts, tau, lay, lev, emis, sfc, inc, gup, gdn, bb, bup, bdn,
+                                    jac, sjac, fj, resc, ssa, g)
+    ref = nps.lw_solver_noscat(top_at_1, Ds, wts, tau, lay, lev, emis, sfc, inc, bb, jac, sjac, resc, ssa, g)
+    pairs = [(bup, ref[2], "bb up"), (bdn, ref[3], "bb dn")] if bb else [(gup, ref[0], "up"), (gdn, ref[1], "dn")]
+    if jac:
+        pairs.append((fj, ref[4], "jacobian"))
+    for a, b, n in pairs:
+        assert np.max(np.abs(b)) > 0, n
+        assert np.array_equal(a, b), f"{n}: max diff {np.max(np.abs(a - b)):.3e}"
