@@ -169,3 +169,41 @@ def test_numpy_lw_solver_noscat_equals_c_oracle(oracle_lib, top_at_1, nmus, bb, 
     for a, b, n in pairs:
         assert np.max(np.abs(b)) > 0, n
         assert np.array_equal(a, b), f"{n}: max diff {np.max(np.abs(a - b)):.3e}"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Optical-properties arithmetic: oracle/rte_optical_props_ref.c against tests/numpy_optical_props.py - bit for bit.
+# ---------------------------------------------------------------------------------------------------------------------
+import numpy_optical_props as npo  # noqa: E402
+import test_optical_props_parity as opp  # noqa: E402  (its operand generator and its by-reference caller)
+
+
+@pytest.mark.parametrize("bybnd", [False, True])
+@pytest.mark.parametrize("k2", opp.KINDS)
+@pytest.mark.parametrize("k1", opp.KINDS)
+@pytest.mark.parametrize("nmom1,nmom2", [(4, 2), (2, 5), (3, 3)])
+def test_numpy_increments_equal_c_oracle(oracle_lib, k1, k2, bybnd, nmom1, nmom2):
+    if "nstream" not in (k1, k2) and (nmom1, nmom2) != (3, 3):
+        pytest.skip("moment counts only matter for n-stream operands")
+    rng = np.random.default_rng(1000 + 100 * opp.KINDS.index(k1) + 10 * opp.KINDS.index(k2) + bybnd)
+    op1 = opp._props(rng, k1, opp.NGPT, nmom1)
+    op2 = opp._props(rng, k2, opp.NBND if bybnd else opp.NGPT, nmom2)
+    got = opp._call(oracle_lib, None, k1, k2, bybnd, nmom1, nmom2, op1, op2)
+    ref = npo.increment_bybnd(k1, k2, op1, op2, opp.LIMS) if bybnd else npo.increment(k1, k2, op1, op2)
+    for a, b, n in zip(got, ref, ("tau", "ssa", "g/p")):
+        assert np.array_equal(a, b), f"{k1} += {k2} bybnd={bybnd}: {n} (max diff {np.max(np.abs(a - b)):.3e})"
+
+
+def test_numpy_delta_scaling_equals_c_oracle(oracle_lib):
+    rng = np.random.default_rng(7)
+    tau, ssa, g = opp._props(rng, "2stream", opp.NGPT, 0)
+    f = np.asfortranarray(rng.uniform(0.0, 0.9, tau.shape))
+    f[rng.random(f.shape) < 0.05] = 1.0   # (1 - f) -> 0: the max(eps, .) guard (:69)
+    t1, s1, g1 = (a.copy(order="F") for a in (tau, ssa, g))
+    oracle_lib.rte_delta_scale_2str_k(opp.NCOL, opp.NLAY, opp.NGPT, t1, s1, g1)
+    t2, s2, g2 = (a.copy(order="F") for a in (tau, ssa, g))
+    oracle_lib.rte_delta_scale_2str_f_k(opp.NCOL, opp.NLAY, opp.NGPT, t2, s2, g2, f)
+    for a, b, n in zip((t1, s1, g1), npo.delta_scale_2str(tau, ssa, g), ("tau", "ssa", "g")):
+        assert np.array_equal(a, b), n
+    for a, b, n in zip((t2, s2, g2), npo.delta_scale_2str_f(tau, ssa, g, f), ("tau_f", "ssa_f", "g_f")):
+        assert np.array_equal(a, b), n
