@@ -207,3 +207,66 @@ def test_numpy_delta_scaling_equals_c_oracle(oracle_lib):
         assert np.array_equal(a, b), n
     for a, b, n in zip((t2, s2, g2), npo.delta_scale_2str_f(tau, ssa, g, f), ("tau_f", "ssa_f", "g_f")):
         assert np.array_equal(a, b), n
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Frontend-resident loops (SURVEY 8a'): oracle/glue_ref.c, oracle/rte_misc_ref.c against tests/numpy_glue.py - bit for bit.
+# ---------------------------------------------------------------------------------------------------------------------
+import ctypes as C  # noqa: E402
+
+import numpy_glue as npgl  # noqa: E402
+from rte_rrtmgp_b200.abi import _ptr  # noqa: E402
+
+
+def _P(a):
+    return C.c_void_p(_ptr(a).value)
+
+
+def test_numpy_glue_equals_c_oracle(oracle_lib):
+    rng = np.random.default_rng(53)
+    ncol, nlay, ngpt = 13, 17, 6
+    f = lambda *s: np.asfortranarray(rng.random(s))
+    c = oracle_lib.cdll
+    # col_dry
+    plev = np.asfortranarray(np.sort(rng.uniform(10.0, 1.0e5, (ncol, nlay + 1)), axis=1))
+    q = np.asfortranarray(10.0 ** rng.uniform(-6, -1.7, (ncol, nlay)))
+    col_dry = fzeros((ncol, nlay))
+    c.rrtmgpb_get_col_dry(ncol, nlay, _P(q), _P(plev), _P(col_dry))
+    assert np.array_equal(col_dry, npgl.get_layer_number(q, plev))
+    # level temperatures
+    play = np.asfortranarray(0.5 * (plev[:, 1:] + plev[:, :-1]))
+    tlay = np.asfortranarray(rng.uniform(180.0, 320.0, (ncol, nlay)))
+    tlev = fzeros((ncol, nlay + 1))
+    c.rrtmgpb_interpolate_tlev(ncol, nlay, _P(play), _P(plev), _P(tlay), _P(tlev))
+    assert np.array_equal(tlev, npgl.interpolate_tlev(play, plev, tlay))
+    # absorption + Rayleigh
+    ta = np.asfortranarray(10.0 ** rng.uniform(-9, 1, (ncol, nlay, ngpt)))
+    tr = np.asfortranarray(10.0 ** rng.uniform(-9, 0, (ncol, nlay, ngpt)))
+    ta[0, 0, :], tr[0, 0, :] = 0.0, 0.0          # t = 0: the ssa = 0 branch (:1995-1997)
+    for kind in (1, 2):
+        tau, ssa, g = (fzeros((ncol, nlay, ngpt)) for _ in range(3))
+        g += 7.0
+        c.rrtmgpb_combine_abs_and_rayleigh(ncol, nlay, ngpt, kind, _P(ta), _P(tr), _P(tau), _P(ssa), _P(g))
+        rt, rs, rg = npgl.combine_abs_and_rayleigh(ta, tr, kind == 2)
+        assert np.array_equal(tau, rt)
+        if kind == 2:
+            assert np.array_equal(ssa, rs) and np.array_equal(g, rg)
+    # liquid + ice cloud properties
+    lt, it = f(ncol, nlay, ngpt) * 5, f(ncol, nlay, ngpt) * 3
+    lt[1, 1, :], it[1, 1, :] = 0.0, 0.0          # cloud-free cell: max(epsilon, .) guards (:417-418)
+    lts, its = np.asfortranarray(lt * rng.random(lt.shape)), np.asfortranarray(it * rng.random(it.shape))
+    ltsg, itsg = np.asfortranarray(lts * rng.uniform(-0.5, 0.9, lt.shape)), np.asfortranarray(its * rng.uniform(-0.5, 0.9, it.shape))
+    for kind in (1, 2):
+        tau, ssa, g = (fzeros((ncol, nlay, ngpt)) for _ in range(3))
+        c.rrtmgpb_cloud_combine(ncol, nlay, ngpt, kind, _P(lt), _P(lts), _P(ltsg), _P(it), _P(its), _P(itsg), _P(tau), _P(ssa), _P(g))
+        rt, rs, rg = npgl.cloud_combine(lt, lts, ltsg, it, its, itsg, kind == 2)
+        assert np.array_equal(tau, rt)
+        if kind == 2:
+            assert np.array_equal(ssa, rs) and np.array_equal(g, rg)
+    # broadband reductions
+    fdn, fup = np.asfortranarray(300 * rng.random((ncol, nlay + 1, ngpt))), np.asfortranarray(300 * rng.random((ncol, nlay + 1, ngpt)))
+    bb, net = fzeros((ncol, nlay + 1)), fzeros((ncol, nlay + 1))
+    oracle_lib.rte_sum_broadband(ncol, nlay + 1, ngpt, fdn, bb)
+    oracle_lib.rte_net_broadband_full(ncol, nlay + 1, ngpt, fdn, fup, net)
+    assert np.array_equal(bb, npgl.sum_broadband(fdn))
+    assert np.array_equal(net, npgl.net_broadband_full(fdn, fup))
