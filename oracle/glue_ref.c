@@ -4,7 +4,9 @@
  * Fortran FRONTEND (SURVEY.md section 8a'), under the extension names of
  * include/rrtmgp_b200_ext.h, plus the host-memory version of the backend plumbing.
  * Each function cites the frontend lines it follows.  PARITY UNPINNED by reference golden data
- * (the frontend loops are only exercised by the reference's data-dependent regression tests).
+ * (the frontend loops are only exercised by the reference's data-dependent regression tests); pinned instead by a second,
+ * independent numpy transcription of the Fortran that must agree bit for bit (tests/numpy_glue.py, the numpy statements in
+ * tests/test_aerosol_optics.py and tests/test_cloud_sampling.py; tests/test_oracle_crosscheck.py).
  */
 #include <float.h>
 #include <stdlib.h>

@@ -9,7 +9,8 @@
  *
  * PARITY UNPINNED: every golden vector for these kernels lives in the un-vendored rrtmgp-data
  * v1.9.1 tarball (reference rrtmgp/CMakeLists.txt:18); nothing in the reference tree pins them
- * offline.  Mitigation: property tests (tests/test_gas_optics_properties.py).
+ * offline.  Mitigation: property tests (tests/test_gas_optics_properties.py) and a second, independent numpy transcription
+ * of the Fortran (tests/numpy_gas_optics.py) that this file must agree with bit for bit (tests/test_oracle_crosscheck.py).
  */
 #include <float.h>
 #include <math.h>

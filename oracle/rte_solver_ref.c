@@ -11,7 +11,9 @@
  * Parity pin: the solver paths are pinned by the reference's own analytic known-answer tests,
  * restated in tests/test_rte_lw_solver_unit.py and tests/test_rte_sw_solver_unit.py
  * (reference tests/rte_lw_solver_unit_tests.F90, tests/rte_sw_solver_unit_tests.F90).
- * lw_solver_2stream has no in-repo known-answer test: "parity unpinned" for that entry point.
+ * lw_solver_2stream has no known-answer test in the reference ("parity unpinned" against the Fortran itself); it, the other
+ * three solvers (every flag combination) and adding are additionally pinned by a second, independent numpy transcription of
+ * the Fortran (tests/numpy_solvers.py) that this file must agree with bit for bit (tests/test_oracle_crosscheck.py).
  */
 #include <math.h>
 #include <stdlib.h>
